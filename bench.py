@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: quenched Schwinger model 512x512, batched
+HierarchicalSampler draw = HMC on the coarsest level + conditioned fill-in on the two
+finer levels + action differences / accept / topological susceptibility
+(BASELINE.json configs[3]; metric: lattice site-updates/s, ESS/s reported beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one HierarchicalSampler::draw for every chain of the batch.  A
+site-update = one lattice site advanced by one leapfrog step, or one
+fine-level site filled in; both are counted from what the kernels actually executed.
+
+Arms
+  default            CUDA path through the C-ABI; `value` with states resident in HBM,
+                     `e2e` through the host-buffer entry point (mlmcpi_sampler_draw_host:
+                     pinned host state -> device every step, QoI back to the host).
+  --impl reference   the reference's own CPU implementation (its translation units in
+                     oracle/_ref, else the C port in oracle/), same cascade on a bounded
+                     sample of the workload, all host cores (one chain per process -- the
+                     reference's MPI mode is exactly independent chains).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "lattice site-updates/s (Schwinger HMC + hierarchical fill-in)"
+UNIT = "site-updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lattice", type=int, default=512)
+    ap.add_argument("--beta", type=float, default=4.0)
+    ap.add_argument("--levels", type=int, default=3)
+    ap.add_argument("--chains", type=int, default=512, help="chains per GPU")
+    ap.add_argument("--nt", type=int, default=100)
+    ap.add_argument("--dt", type=float, default=0.1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def workload_config(a):
+    return {
+        "workload": f"driver_qft quenched Schwinger {a.lattice}x{a.lattice}, hierarchical sampler "
+                    f"({a.levels} levels, coarsening both, perturbative renormalisation), HMC coarse "
+                    f"sampler nt={a.nt} dt={a.dt}, QoI topological susceptibility",
+        "lattice": [a.lattice, a.lattice], "beta": a.beta, "levels": a.levels, "nt": a.nt, "dt": a.dt,
+    }
+
+
+# --------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    """one process = one independent chain (the reference's MPI decomposition):
+    n_draws full hierarchical cascades, timed after one untimed warm-up cascade"""
+    (lattice, beta, levels, nt, dt, n_draws, seed, use_ref) = args
+    import numpy as np
+
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(seed)
+    work = 0.0
+    if use_ref:
+        R = po.ref()
+        acts = [R.action(po.SCHWINGER, [lattice, lattice, po.BOTH, 1], [beta])]
+        for _ in range(levels - 1):
+            acts.append(acts[-1].coarse())
+        x = [rng.uniform(-np.pi, np.pi, a.n) for a in acts]
+
+        def cascade():
+            w = 0.0
+            for l in range(1, levels):  # hierarchicalsampler.cc:57-60
+                x[l] = acts[l].copy_from_fine(x[l - 1])
+            _, x[levels - 1], _, _ = acts[-1].hmc_draws(nt, dt, 1, int(rng.integers(1 << 30)),
+                                                       x[levels - 1])
+            w += (nt + 1) * acts[-1].n / 2
+            for l in range(levels - 2, -1, -1):  # twolevelmetropolisstep.cc:35-97
+                a, ac = acts[l], acts[l + 1]
+                Sf, Sc = a.evaluate(x[l]), a.cond_evaluate(x[l])
+                tp = a.cond_fill(a.copy_from_coarse(x[l + 1], x[l]))
+                dS = (a.evaluate(tp) - Sf) + (ac.evaluate(ac.copy_from_fine(x[l])) - ac.evaluate(x[l + 1])) \
+                    + (Sc - a.cond_evaluate(tp))
+                if dS < 0 or rng.uniform() < np.exp(-dS):
+                    x[l] = tp
+                w += a.n / 2
+            return w
+    else:
+        orc = po.oracle()
+        mods = [po.schwinger(lattice, lattice, beta)]
+        for l in range(levels - 1):
+            mods.append(orc.coarse_model(mods[-1], 1, l, po.BOTH))
+        x = [rng.uniform(-np.pi, np.pi, orc.sample_size(m)) for m in mods]
+        state = {"draw": 0}
+
+        def cascade():
+            w = 0.0
+            state["draw"] += 1
+            for l in range(1, levels):
+                x[l] = orc.restrict(mods[l - 1], mods[l], x[l - 1])
+            _, x[levels - 1], _ = orc.hmc_step(mods[-1], nt, dt, seed, state["draw"], 0, x[levels - 1])
+            w += (nt + 1) * orc.sample_size(mods[-1]) / 2
+            for l in range(levels - 2, -1, -1):
+                Sf, Sc = orc.action(mods[l], x[l]), orc.cond_action(mods[l], x[l])
+                _, x[l], _, _, _ = orc.twolevel_step(mods[l], mods[l + 1], seed, state["draw"] * 16 + l,
+                                                     0, x[l + 1], x[l], Sf, Sc)
+                w += orc.sample_size(mods[l]) / 2
+            return w
+
+    cascade()  # warm-up (page-in, Bessel tables)
+    t0 = time.perf_counter()
+    for _ in range(n_draws):
+        work += cascade()
+    return work, time.perf_counter() - t0
+
+
+def cpu_arm(a, n_draws, cores=None):
+    """returns (site-updates/s over all cores, cores, kind, sample description)"""
+    import multiprocessing as mp
+
+    from oracle import pyoracle as po
+    if not os.path.exists(po.ORACLE_SO):
+        po.build(ref=False)
+    use_ref = po.have_ref()
+    cores = cores or len(os.sched_getaffinity(0))
+    jobs = [(a.lattice, a.beta, a.levels, a.nt, a.dt, n_draws, 1000 + c, use_ref) for c in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    work = sum(r[0] for r in res)
+    t_max = max(r[1] for r in res)
+    kind = "reference" if use_ref else "port"
+    sample = (f"{cores} independent chains (one process per core), {n_draws} full hierarchical "
+              f"cascade(s) each on the {a.lattice}x{a.lattice} workload after 1 warm-up cascade; "
+              f"slowest process {t_max:.2f} s, wall incl. start-up {wall:.1f} s")
+    return work / t_max, cores, kind, sample, work, t_max
+
+
+def reference_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    draws_total = a.steps
+    # bounded sample: one cascade at 512^2 is ~0.5 s per core; every process does one
+    # untimed warm-up cascade, then `steps` timed ones
+    value, cores, kind, sample, work, t = cpu_arm(a, max(1, draws_total))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / max(1, a.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (U(-pi,pi) start states)", "config": workload_config(a),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [s.strip() for s in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def gpu_main(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import mlmcpathintegral_b200 as mp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    ctx = mp.Context(local, seed=0x5EED0001)
+    B = a.chains
+    m = mp.schwinger(a.lattice, a.lattice, a.beta)
+    sampler = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=a.levels, nt=a.nt, dt=a.dt,
+                         renorm=mp.RENORM_PERTURBATIVE, chain0=rank * B)
+    k_max = 10
+    stats = mp.Statistics(ctx, k_max, B)
+    x = ctx.init_state(m, B, rank * B, 0)
+    sampler.set_state(x)
+    packed = ctx.empty(6 + k_max)
+
+    def step():
+        sampler.draw(x)
+        stats.record(ctx.qoi(m, mp.QOI_SCHWINGER_CHI, x))
+        stats.pack_device(packed)
+        if world > 1:  # QoI moments + autocorrelation sums: the only inter-GPU traffic
+            dist.all_reduce(packed)
+
+    for _ in range(a.warmup):
+        step()
+    stats.reset()
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local) if rank == 0 else None
+    ctx.profile(True)
+    ctx.profile_read()
+    launches0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(a.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    lf_ms, lf_launches, lf_bytes = ctx.profile_read()
+    ctx.profile(False)
+    launches = ctx.launches - launches0
+    work = sampler.work()
+    units_per_step = work["leapfrog_site_steps"] + work["filled_fine_sites"]
+    t = torch.tensor([ms], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    clk = clocks.stop() if clocks else None
+    value = units_per_step * world * a.steps / (ms_max * 1e-3)
+    st = mp.Statistics.finalize(packed.cpu().numpy(), k_max)
+    p_acc = sampler.p_accept()
+
+    # ---- e2e: the host-buffer entry point, pinned host state in, QoI out, every step
+    e2e = None
+    if not a.no_e2e:
+        n = mp.sample_size(m)
+        h_x = torch.empty(B, n, dtype=torch.float64, pin_memory=True)
+        h_q = torch.empty(B, dtype=torch.float64, pin_memory=True)
+        h_x.copy_(x)
+        torch.cuda.synchronize()
+        sampler.draw_host(h_x, mp.QOI_SCHWINGER_CHI, h_q, None)  # warm-up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k_e2e = max(1, min(a.steps, 5))
+        e0.record()
+        for _ in range(k_e2e):
+            sampler.draw_host(h_x, mp.QOI_SCHWINGER_CHI, h_q, None)
+        e1.record()
+        torch.cuda.synchronize()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": units_per_step * world * k_e2e / (float(te.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": B * n * 8, "d2h_bytes_per_step": B * 8, "steps": k_e2e,
+               "api": "mlmcpi_sampler_draw_host (pinned host SampleStates in, QoI out)"}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        else:
+            peak, which = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = lf_bytes / (lf_ms * 1e-3) / 1e9 if lf_ms > 0 else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("leapfrog_dram_bytes_per_launch")
+        nc = mp.sample_size(sampler.level_model(a.levels - 1)) // 2
+        roofline = {
+            "bound": "hbm", "kernel": "leapfrog_rowmarch_kernel", "achieved": achieved, "peak": peak,
+            "peak_source": which, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+            "traffic": traffic, "launches": lf_launches,
+            "avg_launch_ms": lf_ms / lf_launches if lf_launches else None,
+            "algorithmic_bytes_per_launch": 64 * nc * B,
+            "share_of_step": lf_ms / ms if ms > 0 else None,
+        }
+        cfg = workload_config(a)
+        cfg.update({
+            "chains_per_gpu": B, "parallelism": f"independent chains x{world} GPUs, NCCL allreduce of QoI moments",
+            "l2": "inputs larger than L2 (per-GPU fine states %.1f GiB)" % (B * mp.sample_size(m) * 8 / 2 ** 30),
+            "site_updates_per_step_per_gpu": {k: v for k, v in work.items()},
+            "value_per_gpu": value / world,
+            "acceptance_per_level": p_acc,
+            "chi_t": {"average": st["average"], "error": st["error"], "tau_int": st["tau_int"],
+                      "samples": st["samples"]},
+            "ess_per_s": st["samples"] / st["tau_int"] / (ms_max * 1e-3),
+        })
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (U(-pi,pi) start states, Philox4x32-10)", "config": cfg,
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            v, cores, kind, sample, _, _ = cpu_arm(a, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_main(a)
+    else:
+        gpu_main(a)
+
+
+if __name__ == "__main__":
+    main()

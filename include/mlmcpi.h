@@ -1,0 +1,227 @@
+/* mlmcpi.h -- C-ABI of the B200-native sampler inner loop (libmlmcpi.so).
+ *
+ * The reference (eikehmueller/mlmcpathintegral) has no FFI layer: its seam is the
+ * set of C++ abstract classes Action / ConditionedFineAction / Sampler / QoI
+ * (SURVEY.md 8b).  Every entry point below replaces the loop body behind one of
+ * those virtuals and cites it.  The C++ classes in include/mlmcpi/ that carry the
+ * reference's names are thin adapters over this file.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MLMCPI_E* code otherwise,
+ *     never throws; mlmcpi_last_error(ctx) gives the message.
+ *   - the hot-path functions take DEVICE pointers to fp64 and an integer batch
+ *     of B independent chains.  A batched state is laid out [chain][dof] with the
+ *     dof index exactly the reference's (lattice/lattice2d.hh:230-245 vertices,
+ *     :348-353 links ell = 2*Mt*j + 2*i + mu; 1-D paths contiguous), so upload and
+ *     download are plain copies and one chain is bit-identical to the reference's
+ *     SampleState::data (common/samplestate.hh:48).
+ *   - kernels are launched asynchronously on the context's stream; *_host entry
+ *     points take HOST pointers, copy in, run, copy out and synchronise.
+ *   - there is no CPU fallback: without a CUDA device mlmcpi_create fails.
+ *
+ * Random streams (counter-based Philox4x32-10, replaces std::mt19937_64,
+ * SURVEY 7.3-5): counter = (index, chain, draw_lo, stream<<24 | call number),
+ * key = (seed_lo, seed_hi ^ draw_hi); two 53-bit uniforms per call; normals by
+ * Box-Muller.  `chain0` is the global index of the first chain of the batch (the
+ * multi-GPU sharding offsets it), `draw` a caller-maintained draw counter.
+ */
+#ifndef MLMCPI_H
+#define MLMCPI_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLMCPI_VERSION 100
+
+enum { MLMCPI_OK = 0, MLMCPI_EINVAL = -1, MLMCPI_ECUDA = -2, MLMCPI_ENOMEM = -3,
+       MLMCPI_EUNSUPPORTED = -4 };
+
+/* models: action/qm/{harmonicoscillator,quarticoscillator,rotor}action.hh,
+ * action/qft/{quenchedschwinger,gff}action.hh */
+enum { MLMCPI_HO = 0, MLMCPI_QUARTIC = 1, MLMCPI_ROTOR = 2, MLMCPI_SCHWINGER = 3,
+       MLMCPI_GFF = 4 };
+/* lattice/lattice2d.hh:18-26 */
+enum { MLMCPI_COARSEN_BOTH = 0, MLMCPI_COARSEN_TEMPORAL = 1, MLMCPI_COARSEN_SPATIAL = 2,
+       MLMCPI_COARSEN_ALTERNATE = 3, MLMCPI_COARSEN_ROTATE = 4 };
+/* action/renormalisation.hh:17-21 */
+enum { MLMCPI_RENORM_NONE = 0, MLMCPI_RENORM_PERTURBATIVE = 1,
+       MLMCPI_RENORM_NONPERTURBATIVE = 2 };
+/* qoi/qm/qoixsquared.hh, qoi/qm/qoisusceptibility.hh, qoi/qft/qoi2dsusceptibility.hh,
+ * qoi/qft/qoiavgplaquette.hh, qoi/qft/qoi2dphisquared.hh */
+enum { MLMCPI_QOI_X2 = 0, MLMCPI_QOI_ROTOR_CHI = 1, MLMCPI_QOI_SCHWINGER_CHI = 2,
+       MLMCPI_QOI_AVG_PLAQUETTE = 3, MLMCPI_QOI_PHI2 = 4 };
+enum { MLMCPI_STREAM_INIT = 1, MLMCPI_STREAM_HMC_MOMENTUM = 2, MLMCPI_STREAM_HMC_ACCEPT = 3,
+       MLMCPI_STREAM_HEATBATH = 4, MLMCPI_STREAM_FILL1 = 5, MLMCPI_STREAM_FILL2 = 6,
+       MLMCPI_STREAM_FILL3 = 7, MLMCPI_STREAM_TWOLEVEL_ACCEPT = 8 };
+/* coarse-level samplers of sampler/hierarchicalsampler.hh */
+enum { MLMCPI_SAMPLER_HMC = 0, MLMCPI_SAMPLER_HEATBATH = 1 };
+
+/* One level of one model: the data members of the reference's action classes. */
+typedef struct mlmcpi_model {
+  int model;
+  int M_lat;          /* 1-D: number of sites            (lattice/lattice1d.hh) */
+  int Mt_lat, Mx_lat; /* 2-D                             (lattice/lattice2d.hh) */
+  int rotated;        /* 2-D vertex lattice: rotated level of CoarsenRotate     */
+  int coarsening;     /* how THIS level coarsens to the next: BOTH / TEMPORAL /
+                         SPATIAL / ROTATE (ALTERNATE resolved per level)        */
+  double a_lat;       /* 1-D lattice spacing T/M                                */
+  double T_final;     /* 1-D total time                                         */
+  double m0, mu2, lambda, x0; /* QM couplings                                   */
+  double beta;        /* Schwinger coupling                                     */
+  double gff_mu2;     /* GFF: a^2 m^2 (qft/gffaction.hh:174-181)                */
+} mlmcpi_model;
+
+typedef struct mlmcpi_ctx mlmcpi_ctx;
+
+/* ---- context ------------------------------------------------------------ */
+int mlmcpi_version(void);
+/* stream: a cudaStream_t (e.g. torch's current stream) or NULL for an own one */
+int mlmcpi_create(mlmcpi_ctx **ctx, int device, uint64_t seed, void *stream);
+void mlmcpi_destroy(mlmcpi_ctx *ctx);
+const char *mlmcpi_last_error(const mlmcpi_ctx *ctx);
+int mlmcpi_sync(mlmcpi_ctx *ctx);
+int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed);
+/* number of kernels this context has launched so far */
+uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx);
+/* CUDA-event timing of the leapfrog launches (the dominant kernel) on the context's
+ * stream.  _read synchronises, returns and clears out = {milliseconds, launches,
+ * algorithmic bytes (R theta, R p, W theta, W p per site-step)} */
+int mlmcpi_profile(mlmcpi_ctx *ctx, int enable);
+int mlmcpi_profile_read(mlmcpi_ctx *ctx, double out[3]);
+
+/* ---- memory: SampleState storage (common/samplestate.hh:19-53) ----------- */
+int mlmcpi_alloc(mlmcpi_ctx *ctx, size_t n_doubles, double **d_ptr); /* zero-filled */
+int mlmcpi_free(mlmcpi_ctx *ctx, double *d_ptr);
+int mlmcpi_upload(mlmcpi_ctx *ctx, double *d_dst, const double *h_src, size_t n);
+int mlmcpi_download(mlmcpi_ctx *ctx, double *h_dst, const double *d_src, size_t n);
+int mlmcpi_copy(mlmcpi_ctx *ctx, double *d_dst, const double *d_src, size_t n);
+
+/* ---- geometry (host, integer, bit-exact with lattice/lattice2d.{hh,cc}) -- */
+int mlmcpi_sample_size(const mlmcpi_model *m);
+uint32_t mlmcpi_vertex_cart2lin(int Mt, int Mx, int rotated, int i, int j);       /* lattice2d.hh:230-245 */
+void mlmcpi_vertex_lin2cart(int Mt, int Mx, int rotated, uint32_t ell, int *i, int *j); /* :255-268 */
+uint32_t mlmcpi_link_cart2lin(int Mt, int Mx, int i, int j, int mu);              /* :348-353 */
+void mlmcpi_link_lin2cart(int Mt, int Mx, uint32_t ell, int *i, int *j, int *mu); /* :367-375 */
+void mlmcpi_neighbours(int Mt, int Mx, int rotated, uint32_t ell, uint32_t nb[8]); /* lattice2d.cc:135-155 */
+int mlmcpi_coarse_shape(int Mt, int Mx, int ctype, int level, int *Mt_c, int *Mx_c, int *rot_c); /* lattice2d.cc:20-81 */
+/* coarse / fine-only vertex lists and fine->coarse map (lattice2d.cc:82-130);
+ * buffers hold n_vertices entries each; counts = {n_coarse, n_fineonly} */
+int mlmcpi_coarsening_lists(int Mt, int Mx, int ctype, int level, uint32_t *coarse,
+                            uint32_t *fineonly, uint32_t *map_vals, int *counts);
+/* Action::coarse_action() parameters (qm/{harmonicoscillator,rotor}renormalisation.hh,
+ * qft/quenchedschwingerrenormalisation.hh:45-105, qft/gffaction.hh:201-208) */
+int mlmcpi_coarse_model(const mlmcpi_model *fine, int renorm, int level, int ctype,
+                        double T_final, mlmcpi_model *coarse);
+
+/* ---- group 1: action, force, HMC ------------------------------------------ */
+/* Action::initialise_state (rotoraction.cc:82-85, quenchedschwingeraction.cc:198-204) */
+int mlmcpi_init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B,
+                      uint32_t chain0, uint64_t draw);
+/* Action::evaluate: d_S[B] */
+int mlmcpi_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_x, int B, double *d_S);
+/* Action::force: d_f[B][n] */
+int mlmcpi_force(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_x, double *d_f, int B);
+/* leapfrog trajectory of HMCSampler::single_step (sampler/hmcsampler.cc:31-46), in place */
+int mlmcpi_leapfrog(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *d_x,
+                    double *d_p, int B);
+/* momentum refresh (sampler/hmcsampler.cc:24-26) */
+int mlmcpi_hmc_momentum(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_p, int B,
+                        uint32_t chain0, uint64_t draw);
+/* HMCSampler::single_step (sampler/hmcsampler.cc:22-69) for B chains: d_x updated
+ * where accepted; d_accept[B] (int32) and d_diag[B][5] = {deltaH, S_cur, S_trial,
+ * T_cur, T_trial} may be NULL */
+int mlmcpi_hmc_step(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *d_x,
+                    int B, uint32_t chain0, uint64_t draw, int32_t *d_accept, double *d_diag);
+
+/* ---- group 2: sweeps, prolongation, fill-in ------------------------------- */
+/* one coloured sweep of Action::overrelaxation_update over all dofs
+ * (sampler/overrelaxedheatbathsampler.cc:10-18; colours: SURVEY 7.4) */
+int mlmcpi_overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B);
+/* one coloured sweep of Action::heatbath_update (overrelaxedheatbathsampler.cc:20-27) */
+int mlmcpi_heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B,
+                          uint32_t chain0, uint64_t draw);
+/* Action::copy_from_coarse of the fine action / Action::copy_from_fine of the coarse one */
+int mlmcpi_prolong(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *d_xc, double *d_x, int B);
+int mlmcpi_restrict(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *d_xf, double *d_xc, int B);
+/* ConditionedFineAction::fill_fine_points, in place on a prolonged state */
+int mlmcpi_fill(mlmcpi_ctx *ctx, const mlmcpi_model *fine, double *d_x, int B, uint32_t chain0,
+                uint64_t draw);
+/* prolongation and fill-in fused: theta' written straight from the coarse state
+ * (TwoLevelMetropolisStep::draw lines 40-42 in one pass) */
+int mlmcpi_prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *d_xc,
+                        double *d_x, int B, uint32_t chain0, uint64_t draw);
+
+/* ---- group 3: reductions, acceptance, QoIs -------------------------------- */
+/* ConditionedFineAction::evaluate: d_S[B] */
+int mlmcpi_cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *d_x, int B,
+                       double *d_S);
+/* QoI::evaluate: d_q[B]; d_Qint[B] (may be NULL) receives the integer topological
+ * charge for the two susceptibility QoIs */
+int mlmcpi_qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int qoi, const double *d_x, int B,
+               double *d_q, int64_t *d_Qint);
+/* TwoLevelMetropolisStep::draw (montecarlo/twolevelmetropolisstep.cc:35-89) for B
+ * chains.  d_xc: coarse states phi_c; d_xf: current fine states theta (updated where
+ * accepted); d_Sf / d_Scond: cached S_f(theta), S_cond(theta) (updated where
+ * accepted; fill them with mlmcpi_action / mlmcpi_cond_action as set_state does);
+ * d_accept[B], d_deltas[B][3] = {dS_fine, dS_coarse, dS_trial} may be NULL. */
+int mlmcpi_twolevel_step(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_model *coarse,
+                         const double *d_xc, double *d_xf, double *d_Sf, double *d_Scond, int B,
+                         uint32_t chain0, uint64_t draw, int32_t *d_accept, double *d_deltas);
+
+/* ---- samplers (sampler/hmcsampler.hh, overrelaxedheatbathsampler.hh,
+ *      hierarchicalsampler.hh) as batched objects ---------------------------- */
+typedef struct mlmcpi_sampler mlmcpi_sampler;
+typedef struct mlmcpi_sampler_params {
+  int kind;              /* MLMCPI_SAMPLER_*: the (coarse-level) sampler            */
+  int n_levels;          /* 1 = single-level sampler; >1 = HierarchicalSampler      */
+  int renorm, ctype;     /* coarse_action() chain                                   */
+  int nt;                /* hmc: nt, dt, n_rep  (sampler/hmcsampler.hh:21-65)       */
+  double dt;
+  int n_rep;
+  int n_sweep_overrelax; /* heatbath (sampler/overrelaxedheatbathsampler.hh)        */
+  int n_sweep_heatbath;
+} mlmcpi_sampler_params;
+int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine,
+                          const mlmcpi_sampler_params *prm, int B, uint32_t chain0,
+                          mlmcpi_sampler **s);
+void mlmcpi_sampler_destroy(mlmcpi_sampler *s);
+/* Sampler::set_state / Sampler::draw on device states [B][n] */
+int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x);
+int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept);
+/* the same with HOST buffers: h_x_in (may be NULL: keep the current state) is
+ * uploaded, one draw is made, the QoI of the new state is evaluated, and
+ * h_q[B] (and h_x_out[B][n] if not NULL) are copied back; synchronous */
+int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, double *h_q,
+                             double *h_x_out);
+/* counters: out = {n_draws, per level accepted chains ...} */
+int mlmcpi_sampler_level_model(const mlmcpi_sampler *s, int level, mlmcpi_model *m);
+int mlmcpi_sampler_stats(mlmcpi_sampler *s, double *h_p_accept /* [n_levels] */);
+/* elementary-update counters of the last draw for throughput accounting:
+ * out = {leapfrog site-steps, sweep site-updates, filled fine sites} summed over chains */
+int mlmcpi_sampler_work(const mlmcpi_sampler *s, double out[3]);
+
+/* ---- statistics (common/statistics.cc:4-97), one accumulator per chain ---- */
+typedef struct mlmcpi_stats mlmcpi_stats;
+int mlmcpi_stats_create(mlmcpi_ctx *ctx, int k_max, int B, mlmcpi_stats **st);
+void mlmcpi_stats_destroy(mlmcpi_stats *st);
+int mlmcpi_stats_reset(mlmcpi_stats *st);
+/* Statistics::record_sample for every chain from d_q[B] */
+int mlmcpi_stats_record(mlmcpi_stats *st, const double *d_q);
+/* packed moment vector summed over the chains of this batch:
+ * {n_chains, n_samples (all chains), sum avg, sum avg2, sum avg3, sum avg4, sum S_0..S_{k_max-1}}
+ * (what Statistics allreduces across MPI ranks, statistics.cc:30-35,64-79);
+ * length 6 + k_max.  Sum it over GPUs (NCCL allreduce) and hand it to _finalize. */
+int mlmcpi_stats_pack(mlmcpi_stats *st, double *h_packed);
+/* the same vector left in device memory (no synchronisation), ready for ncclAllReduce */
+int mlmcpi_stats_pack_device(mlmcpi_stats *st, double *d_packed);
+int mlmcpi_stats_packed_size(int k_max);
+/* out = {average, variance, variance_error, tau_int, error, total samples} */
+int mlmcpi_stats_finalize(const double *h_packed, int k_max, double out[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLMCPI_H */

@@ -1,0 +1,1121 @@
+// capi.cu -- the extern "C" boundary of libmlmcpi.so (include/mlmcpi.h): context,
+// memory, host-side geometry and renormalisation, model dispatch, the two-level
+// Metropolis-Hastings step, batched sampler objects and per-chain statistics.
+//
+// Reference citations relative to /root/reference/src.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+// ================================================================== context
+int ctx_fail(mlmcpi_ctx *ctx, int code, const char *what, const char *detail) {
+  if (ctx) {
+    ctx->err = what ? what : "error";
+    if (detail) {
+      ctx->err += ": ";
+      ctx->err += detail;
+    }
+  }
+  return code;
+}
+
+int ctx_check_launch(mlmcpi_ctx *ctx, const char *what) {
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return ctx_fail(ctx, MLMCPI_ECUDA, what, cudaGetErrorString(e));
+  return 0;
+}
+
+static double *grow(mlmcpi_ctx *ctx, double **buf, size_t *cap, size_t n) {
+  if (n <= *cap && *buf)
+    return *buf;
+  if (*buf)
+    cudaFree(*buf); // implicit device synchronisation: nobody still uses the old buffer
+  *buf = nullptr;
+  *cap = 0;
+  const size_t want = n + n / 8 + 64;
+  if (cudaMalloc((void **)buf, want * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    ctx_fail(ctx, MLMCPI_ENOMEM, "cudaMalloc failed for a work buffer");
+    *buf = nullptr;
+    return nullptr;
+  }
+  *cap = want;
+  return *buf;
+}
+
+double *ctx_scratch(mlmcpi_ctx *ctx, size_t n) { return grow(ctx, &ctx->scratch, &ctx->scratch_n, n); }
+double *ctx_work(mlmcpi_ctx *ctx, int which, size_t n) {
+  return grow(ctx, &ctx->work[which], &ctx->work_n[which], n);
+}
+
+void prof_begin(mlmcpi_ctx *ctx) {
+  if (!ctx->profile)
+    return;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, ctx->stream);
+  ctx->prof_events.push_back(e0);
+  ctx->prof_events.push_back(e1);
+}
+void prof_end(mlmcpi_ctx *ctx, uint64_t launches, double algorithmic_bytes) {
+  if (!ctx->profile || ctx->prof_events.empty())
+    return;
+  cudaEventRecord(ctx->prof_events.back(), ctx->stream);
+  ctx->prof_launches += launches;
+  ctx->prof_bytes += algorithmic_bytes;
+}
+
+extern "C" {
+
+int mlmcpi_profile(mlmcpi_ctx *ctx, int enable) {
+  ctx->profile = enable != 0;
+  return 0;
+}
+
+int mlmcpi_profile_read(mlmcpi_ctx *ctx, double out[3]) {
+  MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (size_t k = 0; k + 1 < ctx->prof_events.size(); k += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->prof_events[k], ctx->prof_events[k + 1]) == cudaSuccess)
+      ctx->prof_ms += ms;
+    cudaEventDestroy(ctx->prof_events[k]);
+    cudaEventDestroy(ctx->prof_events[k + 1]);
+  }
+  cudaGetLastError();
+  ctx->prof_events.clear();
+  out[0] = ctx->prof_ms;
+  out[1] = (double)ctx->prof_launches;
+  out[2] = ctx->prof_bytes;
+  ctx->prof_ms = ctx->prof_bytes = 0.0;
+  ctx->prof_launches = 0;
+  return 0;
+}
+
+int mlmcpi_version(void) { return MLMCPI_VERSION; }
+
+int mlmcpi_create(mlmcpi_ctx **out, int device, uint64_t seed, void *stream) {
+  if (!out)
+    return MLMCPI_EINVAL;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0 || device < 0 || device >= n_dev) {
+    cudaGetLastError();
+    return MLMCPI_ECUDA; // no CPU fallback
+  }
+  mlmcpi_ctx *ctx = new (std::nothrow) mlmcpi_ctx;
+  if (!ctx)
+    return MLMCPI_ENOMEM;
+  ctx->device = device;
+  ctx->seed = seed;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete ctx;
+    return MLMCPI_ECUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+    ctx->n_sm = prop.multiProcessorCount;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete ctx;
+      return MLMCPI_ECUDA;
+    }
+    ctx->own_stream = true;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void mlmcpi_destroy(mlmcpi_ctx *ctx) {
+  if (!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->scratch)
+    cudaFree(ctx->scratch);
+  for (int k = 0; k < MLMCPI_N_WORK; ++k)
+    if (ctx->work[k])
+      cudaFree(ctx->work[k]);
+  if (ctx->own_stream)
+    cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *mlmcpi_last_error(const mlmcpi_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int mlmcpi_sync(mlmcpi_ctx *ctx) {
+  MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed) {
+  ctx->seed = seed;
+  return 0;
+}
+uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx) { return ctx->launches; }
+
+// =================================================================== memory
+int mlmcpi_alloc(mlmcpi_ctx *ctx, size_t n, double **d_ptr) {
+  if (!d_ptr)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "null output pointer");
+  *d_ptr = nullptr;
+  if (n == 0)
+    return 0;
+  if (cudaMalloc((void **)d_ptr, n * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    return ctx_fail(ctx, MLMCPI_ENOMEM, "cudaMalloc failed");
+  }
+  MLMCPI_CUDA(cudaMemsetAsync(*d_ptr, 0, n * sizeof(double), ctx->stream)); // samplestate.hh:30-33
+  return 0;
+}
+int mlmcpi_free(mlmcpi_ctx *ctx, double *d_ptr) {
+  if (d_ptr)
+    MLMCPI_CUDA(cudaFree(d_ptr));
+  return 0;
+}
+int mlmcpi_upload(mlmcpi_ctx *ctx, double *d_dst, const double *h_src, size_t n) {
+  MLMCPI_CUDA(cudaMemcpyAsync(d_dst, h_src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int mlmcpi_download(mlmcpi_ctx *ctx, double *h_dst, const double *d_src, size_t n) {
+  MLMCPI_CUDA(cudaMemcpyAsync(h_dst, d_src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int mlmcpi_copy(mlmcpi_ctx *ctx, double *d_dst, const double *d_src, size_t n) {
+  MLMCPI_CUDA(cudaMemcpyAsync(d_dst, d_src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+// ================================================================= geometry
+int mlmcpi_sample_size(const mlmcpi_model *m) {
+  switch (m->model) {
+  case MLMCPI_HO:
+  case MLMCPI_QUARTIC:
+  case MLMCPI_ROTOR:
+    return m->M_lat;
+  case MLMCPI_SCHWINGER:
+    return 2 * m->Mt_lat * m->Mx_lat;
+  case MLMCPI_GFF:
+    return m->rotated ? m->Mt_lat * m->Mx_lat / 2 : m->Mt_lat * m->Mx_lat;
+  }
+  return -1;
+}
+
+uint32_t mlmcpi_vertex_cart2lin(int Mt, int Mx, int rotated, int i, int j) {
+  if (!rotated)
+    return (uint32_t)(Mt * ((j + Mx) % Mx) + ((i + Mt) % Mt));
+  const int odd = i & 1; // on a rotated lattice i and j have the same parity
+  const int ih = (((i + Mt) - odd) / 2) % (Mt / 2);
+  const int jh = (((j + Mx) - (j & 1)) / 2) % (Mx / 2);
+  return (uint32_t)((Mt / 2) * jh + ih + odd * (Mt * Mx / 4));
+}
+
+void mlmcpi_vertex_lin2cart(int Mt, int Mx, int rotated, uint32_t ell, int *i, int *j) {
+  if (!rotated) {
+    *j = (int)(ell / Mt);
+    *i = (int)(ell % Mt);
+    return;
+  }
+  const uint32_t quarter = (uint32_t)(Mt * Mx / 4);
+  const int odd = ell >= quarter ? 1 : 0;
+  const uint32_t r = ell - odd * quarter;
+  *j = 2 * (int)(r / (Mt / 2)) + odd;
+  *i = 2 * (int)(r % (Mt / 2)) + odd;
+}
+
+uint32_t mlmcpi_link_cart2lin(int Mt, int Mx, int i, int j, int mu) {
+  return (uint32_t)(2 * (Mt * ((j + Mx) % Mx) + ((i + Mt) % Mt)) + mu);
+}
+
+void mlmcpi_link_lin2cart(int Mt, int Mx, uint32_t ell, int *i, int *j, int *mu) {
+  (void)Mx;
+  const uint32_t site = ell >> 1;
+  *mu = (int)(ell & 1u);
+  *j = (int)(site / Mt);
+  *i = (int)(site % Mt);
+}
+
+void mlmcpi_neighbours(int Mt, int Mx, int rotated, uint32_t ell, uint32_t nb[8]) {
+  // nearest neighbours first, then the four next-nearest ones
+  static const int d_plain[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
+  static const int d_rot[8][2] = {{1, 1}, {1, -1}, {-1, 1}, {-1, -1}, {2, 0}, {-2, 0}, {0, 2}, {0, -2}};
+  int i, j;
+  mlmcpi_vertex_lin2cart(Mt, Mx, rotated, ell, &i, &j);
+  const int(*d)[2] = rotated ? d_rot : d_plain;
+  for (int k = 0; k < 8; ++k)
+    nb[k] = mlmcpi_vertex_cart2lin(Mt, Mx, rotated, i + d[k][0], j + d[k][1]);
+}
+
+static bool level_factors(int Mt, int Mx, int ctype, int level, int *rt, int *rx) {
+  const bool rotated = (ctype == MLMCPI_COARSEN_ROTATE) && (level & 1);
+  *rt = *rx = 1;
+  if (ctype == MLMCPI_COARSEN_BOTH || (ctype == MLMCPI_COARSEN_ROTATE && rotated))
+    *rt = *rx = 2;
+  else if (ctype == MLMCPI_COARSEN_TEMPORAL || (ctype == MLMCPI_COARSEN_ALTERNATE && !(level & 1)))
+    *rt = 2;
+  else if (ctype == MLMCPI_COARSEN_SPATIAL || (ctype == MLMCPI_COARSEN_ALTERNATE && (level & 1)))
+    *rx = 2;
+  else if (ctype != MLMCPI_COARSEN_ROTATE)
+    return false;
+  return (Mt % *rt == 0) && (Mx % *rx == 0);
+}
+
+int mlmcpi_coarse_shape(int Mt, int Mx, int ctype, int level, int *Mt_c, int *Mx_c, int *rot_c) {
+  int rt, rx;
+  const bool ok = level_factors(Mt, Mx, ctype, level, &rt, &rx);
+  *Mt_c = (Mt % rt == 0) ? Mt / rt : Mt;
+  *Mx_c = (Mx % rx == 0) ? Mx / rx : Mx;
+  *rot_c = (ctype == MLMCPI_COARSEN_ROTATE) && !(level & 1);
+  return ok && *Mt_c > 1 && *Mx_c > 1;
+}
+
+int mlmcpi_coarsening_lists(int Mt, int Mx, int ctype, int level, uint32_t *coarse,
+                            uint32_t *fineonly, uint32_t *map_vals, int *counts) {
+  int Mtc, Mxc, rotc, rt, rx;
+  if (!mlmcpi_coarse_shape(Mt, Mx, ctype, level, &Mtc, &Mxc, &rotc))
+    return MLMCPI_EINVAL;
+  level_factors(Mt, Mx, ctype, level, &rt, &rx);
+  const int rotated = (ctype == MLMCPI_COARSEN_ROTATE) && (level & 1);
+  const int nv = rotated ? Mt * Mx / 2 : Mt * Mx;
+  int nc = 0, nf = 0;
+  // walking the linear index in ascending order yields both lists already sorted
+  for (int ell = 0; ell < nv; ++ell) {
+    int i, j;
+    mlmcpi_vertex_lin2cart(Mt, Mx, rotated, ell, &i, &j);
+    bool is_c;
+    if (ctype == MLMCPI_COARSEN_ROTATE && !rotated)
+      is_c = ((i + j) % 2 == 0);
+    else
+      is_c = (i % rt == 0) && (j % rx == 0);
+    if (is_c) {
+      map_vals[nc] = mlmcpi_vertex_cart2lin(Mtc, Mxc, rotc, i / rt, j / rx);
+      coarse[nc++] = ell;
+    } else {
+      fineonly[nf++] = ell;
+    }
+  }
+  counts[0] = nc;
+  counts[1] = nf;
+  return 0;
+}
+
+// common/auxilliary.cc:7-29
+static double sigma_hat(double xi, unsigned p) {
+  if (p == 0)
+    return 1.0;
+  if (p & 1u)
+    return 0.0;
+  double num = 0.0, den = 1.0;
+  for (unsigned m = 1; m < 100; ++m) {
+    const double e = std::exp(-0.5 * xi * m * m);
+    num += 2. * std::pow((double)m, (double)p) * e;
+    den += 2. * e;
+  }
+  return num / den;
+}
+
+int mlmcpi_coarse_model(const mlmcpi_model *fine, int renorm, int level, int ctype, double T_final,
+                        mlmcpi_model *coarse) {
+  if (!fine || !coarse)
+    return MLMCPI_EINVAL;
+  *coarse = *fine;
+  const double a = fine->a_lat;
+  switch (fine->model) {
+  case MLMCPI_HO:
+  case MLMCPI_QUARTIC:
+  case MLMCPI_ROTOR:
+    if (fine->M_lat % 2 || fine->M_lat < 2)
+      return MLMCPI_EINVAL;
+    coarse->M_lat = fine->M_lat / 2;
+    coarse->a_lat = T_final / coarse->M_lat;
+    coarse->T_final = T_final;
+    if (fine->model == MLMCPI_HO) { // qm/harmonicoscillatorrenormalisation.hh:46-79
+      if (renorm == MLMCPI_RENORM_PERTURBATIVE)
+        coarse->m0 = fine->m0 * (1. - 0.5 * a * a * fine->mu2);
+      else if (renorm == MLMCPI_RENORM_NONPERTURBATIVE)
+        coarse->m0 = fine->m0 / (1. + 0.5 * a * a * fine->mu2);
+      if (renorm != MLMCPI_RENORM_NONE)
+        coarse->mu2 = fine->mu2 * (1. + 0.25 * a * a * fine->mu2);
+    } else if (fine->model == MLMCPI_ROTOR) { // qm/rotorrenormalisation.hh:38-57, .cc:8-14
+      if (renorm == MLMCPI_RENORM_PERTURBATIVE) {
+        const double xi = T_final / fine->m0;
+        const double s2 = sigma_hat(xi, 2), s4 = sigma_hat(xi, 4);
+        const double deltaI = 0.5 * (1. - 2. * xi * s2 + 0.5 * xi * xi * (s4 - s2 * s2)) /
+                              (1. - 2. * xi * s2 + xi * xi * (s4 - s2 * s2));
+        coarse->m0 = (1. + deltaI * a / fine->m0) * fine->m0;
+      } else if (renorm == MLMCPI_RENORM_NONPERTURBATIVE) {
+        return MLMCPI_EUNSUPPORTED; // the reference errors out as well
+      }
+    } // quartic: qm/quarticoscillatoraction.hh:105-110, parameters unchanged
+    return 0;
+  case MLMCPI_SCHWINGER: { // qft/quenchedschwingerrenormalisation.hh:45-105
+    int Mtc, Mxc, rotc;
+    if (ctype == MLMCPI_COARSEN_ROTATE ||
+        !mlmcpi_coarse_shape(fine->Mt_lat, fine->Mx_lat, ctype, level, &Mtc, &Mxc, &rotc))
+      return MLMCPI_EINVAL;
+    coarse->Mt_lat = Mtc;
+    coarse->Mx_lat = Mxc;
+    const bool both = (ctype == MLMCPI_COARSEN_BOTH);
+    const double beta = fine->beta;
+    coarse->beta = (both ? 0.25 : 0.5) * beta;
+    if (beta > 4.0 && renorm == MLMCPI_RENORM_PERTURBATIVE)
+      coarse->beta = (both ? 0.25 : 0.5) * (1. + (both ? 1.5 : 0.5) / beta) * beta;
+    else if (beta > 4.0 && renorm == MLMCPI_RENORM_NONPERTURBATIVE)
+      return MLMCPI_EUNSUPPORTED; // needs the chi_t quadrature
+    if (ctype == MLMCPI_COARSEN_ALTERNATE)
+      coarse->coarsening = ((level + 1) % 2 == 0) ? MLMCPI_COARSEN_TEMPORAL : MLMCPI_COARSEN_SPATIAL;
+    return 0;
+  }
+  case MLMCPI_GFF: { // qft/gffaction.hh:174-181, 201-208
+    int Mtc, Mxc, rotc;
+    if (!mlmcpi_coarse_shape(fine->Mt_lat, fine->Mx_lat, ctype, level, &Mtc, &Mxc, &rotc))
+      return MLMCPI_EINVAL;
+    const double af = (fine->rotated ? std::sqrt(2.) : 1.) / fine->Mt_lat;
+    const double ac = (rotc ? std::sqrt(2.) : 1.) / Mtc;
+    coarse->Mt_lat = Mtc;
+    coarse->Mx_lat = Mxc;
+    coarse->rotated = rotc;
+    coarse->gff_mu2 = ac * ac * (fine->gff_mu2 / (af * af));
+    return 0;
+  }
+  }
+  return MLMCPI_EINVAL;
+}
+
+} // extern "C"
+
+// constants of BesselProductDistribution (distribution/besselproductdistribution.hh:52-80)
+void besselproduct_setup(double beta, BesselProductConst *bp) {
+  static std::mutex mtx;
+  static std::map<double, BesselProductConst> cache;
+  std::lock_guard<std::mutex> lock(mtx);
+  auto it = cache.find(beta);
+  if (it != cache.end()) {
+    *bp = it->second;
+    return;
+  }
+  BesselProductConst c;
+  c.beta = beta;
+  c.I0_twobeta = std::cyl_bessel_i(0.0, 2 * beta);
+  c.log_I0_twobeta = std::log(c.I0_twobeta);
+  c.sigma_beta = M_PI / std::sqrt(2 * c.log_I0_twobeta);
+  const unsigned kmax = 16, nmax = 32;
+  std::vector<double> lf(2 * nmax + 2, 0.0); // log n! as a running sum of logs
+  for (unsigned n = 2; n < lf.size(); ++n)
+    lf[n] = lf[n - 1] + std::log((double)n);
+  auto log_nCk = [&](unsigned n, unsigned k) { return lf[n] - lf[k] - lf[n - k]; };
+  double alpha0 = 1.0;
+  for (unsigned k = 0; k <= kmax; ++k) {
+    double s = 0.0;
+    for (unsigned n = k; n <= nmax; ++n)
+      for (unsigned m = k; m <= nmax; ++m)
+        s += std::pow(0.5 * beta, 2.0 * (n + m)) *
+             std::exp(log_nCk(2 * n, n - k) + log_nCk(2 * m, m - k) - 2 * (lf[n] + lf[m]));
+    double alpha = ((k == 0) ? 2 : 4) * M_PI * s;
+    if (k == 0)
+      alpha0 = alpha;
+    else
+      alpha /= alpha0;
+    c.alphaZ[k] = alpha;
+  }
+  cache[beta] = c;
+  *bp = c;
+}
+
+// ===================================================== small generic kernels
+__global__ void reduce_finish_kernel(const double *partial, int nblk, int B, int nout, int epi,
+                                     double scale0, double scale1, double *out, int64_t *Qint) {
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= B)
+    return;
+  double s[2] = {0.0, 0.0};
+  for (int k = 0; k < nout; ++k) {
+    const double *p = partial + ((size_t)k * B + chain) * nblk;
+    double acc = 0.0;
+    for (int b = 0; b < nblk; ++b)
+      acc += p[b];
+    s[k] = acc;
+  }
+  if (epi == EPI_CHI) {
+    out[chain] = scale0 * s[0] * s[0];
+    if (Qint)
+      Qint[chain] = -(int64_t)llrint(s[1]);
+  } else {
+    out[chain] = scale0 * s[0];
+    if (nout > 1)
+      out[B + chain] = scale1 * s[1];
+  }
+}
+
+int launch_reduce_finish(mlmcpi_ctx *ctx, const double *partial, int nblk, int B, int nout, int epi,
+                         double scale0, double scale1, double *out, int64_t *Qint) {
+  reduce_finish_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(partial, nblk, B, nout, epi, scale0,
+                                                             scale1, out, Qint);
+  MLMCPI_LAUNCHED("reduce_finish");
+  return 0;
+}
+
+namespace {
+
+struct SqNormF {
+  const double *p;
+  size_t n;
+  __device__ void operator()(int chain, long long s, double acc[1]) const {
+    const double v = p[(size_t)chain * n + s];
+    acc[0] += v * v;
+  }
+};
+
+// sampler/hmcsampler.cc:48-67
+__global__ void hmc_accept_kernel(int B, uint32_t chain0, uint64_t seed, uint64_t draw,
+                                  const double *S_cur, const double *S_trial, const double *T_cur,
+                                  const double *T_trial, int32_t *accept, double *diag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B)
+    return;
+  const double deltaH = (S_trial[c] - S_cur[c]) + (T_trial[c] - T_cur[c]);
+  bool acc = deltaH < 0.0;
+  if (!acc) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_HMC_ACCEPT, draw, chain0 + c, 0);
+    double u0, u1;
+    rng_uniform2(r, u0, u1);
+    acc = u0 < exp(-deltaH);
+  }
+  accept[c] = acc ? 1 : 0;
+  if (diag) {
+    double *d = diag + 5 * (size_t)c;
+    d[0] = deltaH;
+    d[1] = S_cur[c];
+    d[2] = S_trial[c];
+    d[3] = T_cur[c];
+    d[4] = T_trial[c];
+  }
+}
+
+__global__ void masked_copy_kernel(double2 *dst, const double2 *src, size_t n2, int B,
+                                   const int32_t *accept) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n2 * B)
+    return;
+  if (accept[t / n2])
+    dst[t] = src[t];
+}
+__global__ void masked_copy1_kernel(double *dst, const double *src, size_t n, int B,
+                                    const int32_t *accept) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * B)
+    return;
+  if (accept[t / n])
+    dst[t] = src[t];
+}
+
+// montecarlo/twolevelmetropolisstep.cc:48-81; red = {S_f', S_c(theta_C), S_c(phi_c), S_cond'}
+__global__ void twolevel_accept_kernel(int B, uint32_t chain0, uint64_t seed, uint64_t draw,
+                                       const double *red, double *Sf, double *Scond,
+                                       const int32_t *mask, int32_t *accept, double *deltas) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B)
+    return;
+  const double Sf_prime = red[c], ScC = red[B + c], Scc = red[2 * B + c], Scond_prime = red[3 * B + c];
+  const double dS_fine = Sf_prime - Sf[c];
+  const double dS_coarse = ScC - Scc;
+  const double dS_trial = Scond[c] - Scond_prime;
+  const double dS = dS_fine + dS_coarse + dS_trial;
+  bool acc = dS < 0.0;
+  if (!acc) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_TWOLEVEL_ACCEPT, draw, chain0 + c, 0);
+    double u0, u1;
+    rng_uniform2(r, u0, u1);
+    acc = u0 < exp(-dS);
+  }
+  if (mask && !mask[c])
+    acc = false; // the cascade already stopped for this chain (hierarchicalsampler.cc:73-74)
+  if (acc) {
+    Sf[c] = Sf_prime;
+    Scond[c] = Scond_prime;
+  }
+  accept[c] = acc ? 1 : 0;
+  if (deltas) {
+    deltas[3 * (size_t)c] = dS_fine;
+    deltas[3 * (size_t)c + 1] = dS_coarse;
+    deltas[3 * (size_t)c + 2] = dS_trial;
+  }
+}
+
+__global__ void or_accept_kernel(int B, int32_t *acc, const int32_t *step) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < B)
+    acc[c] = (acc[c] | step[c]) ? 1 : 0;
+}
+__global__ void set_i32_kernel(int B, int32_t *a, int32_t v) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < B)
+    a[c] = v;
+}
+__global__ void count_accept_kernel(int B, const int32_t *acc, unsigned long long *counter) {
+  int v = 0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < B; c += gridDim.x * blockDim.x)
+    v += acc[c];
+  const double s = block_sum((double)v);
+  if (threadIdx.x == 0 && s > 0)
+    atomicAdd(counter, (unsigned long long)(s + 0.5));
+}
+
+} // namespace
+
+int launch_half_sqnorm(mlmcpi_ctx *ctx, const double *d_p, size_t n, int B, double *d_T) {
+  return site_reduce<1>(ctx, "half_sqnorm", SqNormF{d_p, n}, (long long)n, B, EPI_SCALE, 0.5, 0.0,
+                        d_T, nullptr);
+}
+
+int launch_hmc_accept(mlmcpi_ctx *ctx, int B, uint32_t chain0, uint64_t draw, const double *S_cur,
+                      const double *S_trial, const double *T_cur, const double *T_trial,
+                      int32_t *accept, double *diag) {
+  hmc_accept_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, chain0, ctx->seed, draw, S_cur, S_trial,
+                                                          T_cur, T_trial, accept, diag);
+  MLMCPI_LAUNCHED("hmc_accept");
+  return 0;
+}
+
+int launch_masked_copy(mlmcpi_ctx *ctx, double *dst, const double *src, size_t n, int B,
+                       const int32_t *accept) {
+  if (n % 2 == 0 && ((uintptr_t)dst % 16 == 0) && ((uintptr_t)src % 16 == 0)) {
+    masked_copy_kernel<<<cdiv((long long)(n / 2) * B, 256), 256, 0, ctx->stream>>>(
+        reinterpret_cast<double2 *>(dst), reinterpret_cast<const double2 *>(src), n / 2, B, accept);
+  } else {
+    masked_copy1_kernel<<<cdiv((long long)n * B, 256), 256, 0, ctx->stream>>>(dst, src, n, B, accept);
+  }
+  MLMCPI_LAUNCHED("masked_copy");
+  return 0;
+}
+
+// =========================================================== model dispatch
+#define DISPATCH(m, fn, ...)                                                                       \
+  do {                                                                                             \
+    if (!ctx || !(m))                                                                              \
+      return MLMCPI_EINVAL;                                                                        \
+    if (B <= 0)                                                                                    \
+      return ctx_fail(ctx, MLMCPI_EINVAL, "batch size must be positive");                          \
+    switch ((m)->model) {                                                                          \
+    case MLMCPI_HO:                                                                                \
+    case MLMCPI_QUARTIC:                                                                           \
+    case MLMCPI_ROTOR:                                                                             \
+      if ((m)->M_lat < 2)                                                                          \
+        return ctx_fail(ctx, MLMCPI_EINVAL, "M_lat must be at least 2");                           \
+      return qm::fn(__VA_ARGS__);                                                                  \
+    case MLMCPI_SCHWINGER:                                                                         \
+      if ((m)->Mt_lat < 2 || (m)->Mx_lat < 2)                                                      \
+        return ctx_fail(ctx, MLMCPI_EINVAL, "lattice extents must be at least 2");                 \
+      return schwinger::fn(__VA_ARGS__);                                                           \
+    case MLMCPI_GFF:                                                                               \
+      if ((m)->Mt_lat < 2 || (m)->Mx_lat < 2)                                                      \
+        return ctx_fail(ctx, MLMCPI_EINVAL, "lattice extents must be at least 2");                 \
+      return gff::fn(__VA_ARGS__);                                                                 \
+    }                                                                                              \
+    return ctx_fail(ctx, MLMCPI_EINVAL, "unknown model");                                          \
+  } while (0)
+
+static int twolevel_step_impl(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_model *coarse,
+                              const double *d_xc, double *d_xf, double *d_Sf, double *d_Scond, int B,
+                              uint32_t chain0, uint64_t draw, const int32_t *d_mask,
+                              int32_t *d_accept, double *d_deltas);
+
+extern "C" {
+
+int mlmcpi_init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0,
+                      uint64_t draw) {
+  DISPATCH(m, init_state, ctx, m, d_x, B, chain0, draw);
+}
+int mlmcpi_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_x, int B, double *d_S) {
+  DISPATCH(m, action, ctx, m, d_x, B, d_S);
+}
+int mlmcpi_force(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_x, double *d_f, int B) {
+  DISPATCH(m, force, ctx, m, d_x, d_f, B);
+}
+int mlmcpi_leapfrog(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *d_x,
+                    double *d_p, int B) {
+  if (nt < 0)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "nt must be non-negative");
+  DISPATCH(m, leapfrog, ctx, m, nt, dt, d_x, d_p, B);
+}
+int mlmcpi_hmc_momentum(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_p, int B, uint32_t chain0,
+                        uint64_t draw) {
+  DISPATCH(m, hmc_momentum, ctx, m, d_p, B, chain0, draw);
+}
+int mlmcpi_hmc_step(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *d_x, int B,
+                    uint32_t chain0, uint64_t draw, int32_t *d_accept, double *d_diag) {
+  if (nt < 0)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "nt must be non-negative");
+  DISPATCH(m, hmc_step, ctx, m, nt, dt, d_x, B, chain0, draw, d_accept, d_diag);
+}
+int mlmcpi_overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B) {
+  DISPATCH(m, overrelax_sweep, ctx, m, d_x, B);
+}
+int mlmcpi_heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B,
+                          uint32_t chain0, uint64_t draw) {
+  DISPATCH(m, heatbath_sweep, ctx, m, d_x, B, chain0, draw);
+}
+int mlmcpi_prolong(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_xc, double *d_x, int B) {
+  DISPATCH(m, prolong, ctx, m, d_xc, d_x, B);
+}
+int mlmcpi_restrict(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_xf, double *d_xc, int B) {
+  DISPATCH(m, restrict_, ctx, m, d_xf, d_xc, B);
+}
+int mlmcpi_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0,
+                uint64_t draw) {
+  DISPATCH(m, fill, ctx, m, d_x, B, chain0, draw);
+}
+int mlmcpi_prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_xc, double *d_x,
+                        int B, uint32_t chain0, uint64_t draw) {
+  DISPATCH(m, prolong_fill, ctx, m, d_xc, d_x, B, chain0, draw);
+}
+int mlmcpi_cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_x, int B, double *d_S) {
+  DISPATCH(m, cond_action, ctx, m, d_x, B, d_S);
+}
+int mlmcpi_qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int qoi, const double *d_x, int B, double *d_q,
+               int64_t *d_Qint) {
+  DISPATCH(m, qoi, ctx, m, qoi, d_x, B, d_q, d_Qint);
+}
+
+int mlmcpi_twolevel_step(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_model *coarse,
+                         const double *d_xc, double *d_xf, double *d_Sf, double *d_Scond, int B,
+                         uint32_t chain0, uint64_t draw, int32_t *d_accept, double *d_deltas) {
+  return twolevel_step_impl(ctx, fine, coarse, d_xc, d_xf, d_Sf, d_Scond, B, chain0, draw, nullptr,
+                            d_accept, d_deltas);
+}
+
+} // extern "C"
+
+// TwoLevelMetropolisStep::draw, montecarlo/twolevelmetropolisstep.cc:35-89
+static int twolevel_step_impl(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_model *coarse,
+                              const double *d_xc, double *d_xf, double *d_Sf, double *d_Scond, int B,
+                              uint32_t chain0, uint64_t draw, const int32_t *d_mask,
+                              int32_t *d_accept, double *d_deltas) {
+  if (!ctx || !fine || !coarse || B <= 0)
+    return MLMCPI_EINVAL;
+  const size_t nf = (size_t)mlmcpi_sample_size(fine), nc = (size_t)mlmcpi_sample_size(coarse);
+  double *theta_prime = ctx_work(ctx, 4, nf * B);
+  double *theta_C = ctx_work(ctx, 5, nc * B);
+  double *red = ctx_work(ctx, 6, (size_t)5 * B);
+  if (!theta_prime || !theta_C || !red)
+    return MLMCPI_ENOMEM;
+  int32_t *acc = d_accept ? d_accept : reinterpret_cast<int32_t *>(red + 4 * B);
+  int rc;
+  if ((rc = mlmcpi_prolong_fill(ctx, fine, d_xc, theta_prime, B, chain0, draw)))      // :40-42
+    return rc;
+  if ((rc = mlmcpi_action(ctx, fine, theta_prime, B, red)))                           // :48
+    return rc;
+  if ((rc = mlmcpi_restrict(ctx, fine, d_xf, theta_C, B)))                            // :55
+    return rc;
+  if ((rc = mlmcpi_action(ctx, coarse, theta_C, B, red + B)))                         // :57
+    return rc;
+  if ((rc = mlmcpi_action(ctx, coarse, d_xc, B, red + 2 * B)))                        // :58
+    return rc;
+  if ((rc = mlmcpi_cond_action(ctx, fine, theta_prime, B, red + 3 * B)))              // :65-66
+    return rc;
+  twolevel_accept_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, chain0, ctx->seed, draw, red, d_Sf,
+                                                               d_Scond, d_mask, acc, d_deltas);
+  MLMCPI_LAUNCHED("twolevel_accept");
+  return launch_masked_copy(ctx, d_xf, theta_prime, nf, B, acc);                      // :78-88
+}
+
+// ================================================================== samplers
+struct mlmcpi_sampler {
+  mlmcpi_ctx *ctx = nullptr;
+  mlmcpi_sampler_params prm;
+  int B = 0;
+  uint32_t chain0 = 0;
+  uint64_t draw = 0;
+  int L = 1;
+  std::vector<mlmcpi_model> model;
+  std::vector<double *> state; // [L] device [B][n_l]
+  double *Sf = nullptr, *Scond = nullptr, *q = nullptr; // [B]
+  int32_t *acc = nullptr, *acc_step = nullptr;          // [B]
+  unsigned long long *counters = nullptr;               // [L] accepted chains per level
+  uint64_t n_draws = 0;
+  double work[3] = {0, 0, 0};
+};
+
+static uint64_t level_draw(uint64_t draw, int level, int rep) {
+  return (draw << 12) | ((uint64_t)level << 8) | (uint64_t)(rep & 0xff);
+}
+
+static double n_sites(const mlmcpi_model &m) {
+  if (m.model == MLMCPI_SCHWINGER)
+    return (double)m.Mt_lat * m.Mx_lat;
+  return (double)mlmcpi_sample_size(&m);
+}
+
+// the sampler on the coarsest level: HMCSampler::draw (sampler/hmcsampler.cc:8-19) or
+// OverrelaxedHeatBathSampler::draw (sampler/overrelaxedheatbathsampler.cc:8-31)
+static int coarse_draw(mlmcpi_sampler *s) {
+  mlmcpi_ctx *ctx = s->ctx;
+  const int l = s->L - 1, B = s->B;
+  const mlmcpi_model *m = &s->model[l];
+  int rc;
+  if (s->prm.kind == MLMCPI_SAMPLER_HMC) {
+    const int n_rep = std::max(1, s->prm.n_rep);
+    for (int r = 0; r < n_rep; ++r) {
+      int32_t *a = (r == 0) ? s->acc : s->acc_step;
+      if ((rc = mlmcpi_hmc_step(ctx, m, s->prm.nt, s->prm.dt, s->state[l], B, s->chain0,
+                                level_draw(s->draw, l, r), a, nullptr)))
+        return rc;
+      if (r > 0) {
+        or_accept_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, s->acc, s->acc_step);
+        MLMCPI_LAUNCHED("or_accept");
+      }
+    }
+    s->work[0] += (double)B * n_rep * (s->prm.nt + 1) * n_sites(*m);
+  } else if (s->prm.kind == MLMCPI_SAMPLER_HEATBATH) {
+    for (int k = 0; k < s->prm.n_sweep_overrelax; ++k)
+      if ((rc = mlmcpi_overrelax_sweep(ctx, m, s->state[l], B)))
+        return rc;
+    for (int k = 0; k < s->prm.n_sweep_heatbath; ++k)
+      if ((rc = mlmcpi_heatbath_sweep(ctx, m, s->state[l], B, s->chain0, level_draw(s->draw, l, k))))
+        return rc;
+    set_i32_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, s->acc, 1);
+    MLMCPI_LAUNCHED("set_accept");
+    s->work[1] += (double)B * (s->prm.n_sweep_overrelax + s->prm.n_sweep_heatbath) * n_sites(*m);
+  } else {
+    return ctx_fail(ctx, MLMCPI_EINVAL, "unknown sampler kind");
+  }
+  return 0;
+}
+
+extern "C" {
+
+int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_sampler_params *prm,
+                          int B, uint32_t chain0, mlmcpi_sampler **out) {
+  if (!ctx || !fine || !prm || !out || B <= 0)
+    return MLMCPI_EINVAL;
+  *out = nullptr;
+  if (prm->n_levels < 1 || prm->n_levels > 16)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "n_levels out of range");
+  mlmcpi_sampler *s = new (std::nothrow) mlmcpi_sampler;
+  if (!s)
+    return MLMCPI_ENOMEM;
+  s->ctx = ctx;
+  s->prm = *prm;
+  s->B = B;
+  s->chain0 = chain0;
+  s->L = prm->n_levels;
+  s->model.push_back(*fine);
+  // HierarchicalSampler constructor, sampler/hierarchicalsampler.cc:19-29
+  for (int l = 0; l + 1 < s->L; ++l) {
+    mlmcpi_model c;
+    // a 2-D rotated lattice sits on an odd level; everything else starts at level 0
+    const int level = (fine->model == MLMCPI_GFF && fine->rotated ? 1 : 0) + l;
+    const int rc = mlmcpi_coarse_model(&s->model[l], prm->renorm, level, prm->ctype,
+                                       s->model[l].T_final, &c);
+    if (rc) {
+      delete s;
+      return ctx_fail(ctx, rc, "cannot construct the coarse action of a level");
+    }
+    s->model.push_back(c);
+  }
+  bool ok = true;
+  for (int l = 0; l < s->L && ok; ++l) {
+    double *d = nullptr;
+    ok = mlmcpi_alloc(ctx, (size_t)mlmcpi_sample_size(&s->model[l]) * B, &d) == 0;
+    s->state.push_back(d);
+  }
+  ok = ok && mlmcpi_alloc(ctx, B, &s->Sf) == 0 && mlmcpi_alloc(ctx, B, &s->Scond) == 0 &&
+       mlmcpi_alloc(ctx, B, &s->q) == 0;
+  ok = ok && cudaMalloc((void **)&s->acc, sizeof(int32_t) * B) == cudaSuccess &&
+       cudaMalloc((void **)&s->acc_step, sizeof(int32_t) * B) == cudaSuccess &&
+       cudaMalloc((void **)&s->counters, sizeof(unsigned long long) * s->L) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    mlmcpi_sampler_destroy(s);
+    return ctx_fail(ctx, MLMCPI_ENOMEM, "out of device memory for the sampler states");
+  }
+  cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->L, ctx->stream);
+  // Sampler constructors start from Action::initialise_state (e.g. hmcsampler.hh:99-101)
+  int rc = mlmcpi_init_state(ctx, fine, s->state[0], B, chain0, 0);
+  if (rc) {
+    mlmcpi_sampler_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return 0;
+}
+
+void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
+  if (!s)
+    return;
+  cudaStreamSynchronize(s->ctx->stream);
+  for (double *d : s->state)
+    if (d)
+      cudaFree(d);
+  if (s->Sf)
+    cudaFree(s->Sf);
+  if (s->Scond)
+    cudaFree(s->Scond);
+  if (s->q)
+    cudaFree(s->q);
+  if (s->acc)
+    cudaFree(s->acc);
+  if (s->acc_step)
+    cudaFree(s->acc_step);
+  if (s->counters)
+    cudaFree(s->counters);
+  delete s;
+}
+
+int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x) {
+  return mlmcpi_copy(s->ctx, s->state[0], d_x, (size_t)mlmcpi_sample_size(&s->model[0]) * s->B);
+}
+
+// HierarchicalSampler::draw, sampler/hierarchicalsampler.cc:55-81 (n_levels == 1: the
+// plain single-level sampler)
+int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
+  mlmcpi_ctx *ctx = s->ctx;
+  const int B = s->B, L = s->L;
+  int rc;
+  s->work[0] = s->work[1] = s->work[2] = 0.0;
+  for (int l = 1; l < L; ++l) // :57-60
+    if ((rc = mlmcpi_restrict(ctx, &s->model[l - 1], s->state[l - 1], s->state[l], B)))
+      return rc;
+  if ((rc = coarse_draw(s))) // :62-66
+    return rc;
+  count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc,
+                                                                         s->counters + (L - 1));
+  MLMCPI_LAUNCHED("count_accept");
+  for (int l = L - 2; l >= 0; --l) {
+    // TwoLevelMetropolisStep::set_state, montecarlo/twolevelmetropolisstep.cc:92-97
+    if ((rc = mlmcpi_action(ctx, &s->model[l], s->state[l], B, s->Sf)))
+      return rc;
+    if ((rc = mlmcpi_cond_action(ctx, &s->model[l], s->state[l], B, s->Scond)))
+      return rc;
+    // s->acc is both the incoming cascade mask and the outgoing accept flag
+    if ((rc = twolevel_step_impl(ctx, &s->model[l], &s->model[l + 1], s->state[l + 1], s->state[l],
+                                 s->Sf, s->Scond, B, s->chain0, level_draw(s->draw, l, 0), s->acc,
+                                 s->acc, nullptr)))
+      return rc;
+    count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc,
+                                                                           s->counters + l);
+    MLMCPI_LAUNCHED("count_accept");
+    s->work[2] += (double)B * n_sites(s->model[l]);
+  }
+  s->draw++;
+  s->n_draws++;
+  if (d_x_out) // :78-80
+    if ((rc = launch_masked_copy(ctx, d_x_out, s->state[0], (size_t)mlmcpi_sample_size(&s->model[0]), B,
+                                 s->acc)))
+      return rc;
+  if (d_accept)
+    MLMCPI_CUDA(cudaMemcpyAsync(d_accept, s->acc, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+  return 0;
+}
+
+int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, double *h_q,
+                             double *h_x_out) {
+  mlmcpi_ctx *ctx = s->ctx;
+  const size_t n = (size_t)mlmcpi_sample_size(&s->model[0]) * s->B;
+  int rc;
+  if (h_x_in)
+    if ((rc = mlmcpi_upload(ctx, s->state[0], h_x_in, n)))
+      return rc;
+  if ((rc = mlmcpi_sampler_draw(s, nullptr, nullptr)))
+    return rc;
+  if (h_q) {
+    if ((rc = mlmcpi_qoi(ctx, &s->model[0], qoi, s->state[0], s->B, s->q, nullptr)))
+      return rc;
+    MLMCPI_CUDA(cudaMemcpyAsync(h_q, s->q, sizeof(double) * s->B, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (h_x_out)
+    MLMCPI_CUDA(cudaMemcpyAsync(h_x_out, s->state[0], n * sizeof(double), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int mlmcpi_sampler_level_model(const mlmcpi_sampler *s, int level, mlmcpi_model *m) {
+  if (!s || !m || level < 0 || level >= s->L)
+    return MLMCPI_EINVAL;
+  *m = s->model[level];
+  return 0;
+}
+
+int mlmcpi_sampler_stats(mlmcpi_sampler *s, double *h_p_accept) {
+  mlmcpi_ctx *ctx = s->ctx;
+  std::vector<unsigned long long> c(s->L);
+  MLMCPI_CUDA(cudaMemcpyAsync(c.data(), s->counters, sizeof(unsigned long long) * s->L,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int l = 0; l < s->L; ++l)
+    h_p_accept[l] = s->n_draws ? (double)c[l] / ((double)s->n_draws * s->B) : 0.0;
+  return 0;
+}
+
+int mlmcpi_sampler_work(const mlmcpi_sampler *s, double out[3]) {
+  out[0] = s->work[0];
+  out[1] = s->work[1];
+  out[2] = s->work[2];
+  return 0;
+}
+
+} // extern "C"
+
+// ================================================================ statistics
+// common/statistics.cc:4-27 for every chain; the chain plays the role of the MPI
+// rank of the reference
+struct mlmcpi_stats {
+  mlmcpi_ctx *ctx = nullptr;
+  int k_max = 0, B = 0;
+  unsigned n_samples = 0; // identical for all chains (lockstep)
+  double *acc = nullptr;  // [4 + 2 k_max][B]: avg1..avg4, S_k[k_max], ring Q_k[k_max]
+  double *packed = nullptr;
+};
+
+namespace {
+
+__global__ void stats_record_kernel(int B, int k_max, unsigned n, double *acc, const double *q) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B)
+    return;
+  // n = number of samples including this one
+  const double Q = q[c];
+  const double w = (n - 1.0), inv = 1.0 / (1.0 * n);
+  double *a1 = acc, *a2 = acc + B, *a3 = acc + 2 * (size_t)B, *a4 = acc + 3 * (size_t)B;
+  double *S = acc + 4 * (size_t)B, *ring = acc + (4 + (size_t)k_max) * B;
+  a1[c] = (w * a1[c] + Q) * inv;
+  a2[c] = (w * a2[c] + Q * Q) * inv;
+  a3[c] = (w * a3[c] + Q * Q * Q) * inv;
+  a4[c] = (w * a4[c] + Q * Q * Q * Q) * inv;
+  const unsigned slot = (n - 1) % k_max;
+  ring[(size_t)slot * B + c] = Q;
+  const unsigned window = n < (unsigned)k_max ? n : (unsigned)k_max;
+  for (unsigned k = 0; k < window; ++k) {
+    const unsigned N_k = n - k;
+    const double Qk = ring[(size_t)((n - 1 - k) % k_max) * B + c];
+    double *Sk = S + (size_t)k * B + c;
+    *Sk = ((N_k - 1.0) * (*Sk) + Q * Qk) / (1.0 * N_k);
+  }
+}
+
+// packed[r] = sum over chains of row r (rows: avg1..avg4, S_0..S_{k_max-1})
+__global__ void stats_pack_kernel(int B, const double *acc, double *packed) {
+  const int r = blockIdx.x;
+  double v = 0.0;
+  for (int c = threadIdx.x; c < B; c += blockDim.x)
+    v += acc[(size_t)r * B + c];
+  v = block_sum(v);
+  if (threadIdx.x == 0)
+    packed[r] = v;
+}
+
+} // namespace
+
+extern "C" {
+
+int mlmcpi_stats_create(mlmcpi_ctx *ctx, int k_max, int B, mlmcpi_stats **out) {
+  if (!ctx || !out || k_max < 1 || B < 1)
+    return MLMCPI_EINVAL;
+  mlmcpi_stats *st = new (std::nothrow) mlmcpi_stats;
+  if (!st)
+    return MLMCPI_ENOMEM;
+  st->ctx = ctx;
+  st->k_max = k_max;
+  st->B = B;
+  if (mlmcpi_alloc(ctx, (size_t)(4 + 2 * k_max) * B, &st->acc) ||
+      mlmcpi_alloc(ctx, 4 + k_max, &st->packed)) {
+    mlmcpi_stats_destroy(st);
+    return MLMCPI_ENOMEM;
+  }
+  *out = st;
+  return 0;
+}
+
+void mlmcpi_stats_destroy(mlmcpi_stats *st) {
+  if (!st)
+    return;
+  cudaStreamSynchronize(st->ctx->stream);
+  if (st->acc)
+    cudaFree(st->acc);
+  if (st->packed)
+    cudaFree(st->packed);
+  delete st;
+}
+
+int mlmcpi_stats_reset(mlmcpi_stats *st) { // Statistics::hard_reset, statistics.hh:125-137
+  mlmcpi_ctx *ctx = st->ctx;
+  st->n_samples = 0;
+  MLMCPI_CUDA(cudaMemsetAsync(st->acc, 0, sizeof(double) * (4 + 2 * st->k_max) * st->B, ctx->stream));
+  return 0;
+}
+
+int mlmcpi_stats_record(mlmcpi_stats *st, const double *d_q) {
+  mlmcpi_ctx *ctx = st->ctx;
+  st->n_samples++;
+  stats_record_kernel<<<cdiv(st->B, 128), 128, 0, ctx->stream>>>(st->B, st->k_max, st->n_samples,
+                                                                st->acc, d_q);
+  MLMCPI_LAUNCHED("stats_record");
+  return 0;
+}
+
+int mlmcpi_stats_packed_size(int k_max) { return 6 + k_max; }
+
+int mlmcpi_stats_pack_device(mlmcpi_stats *st, double *d_packed) {
+  mlmcpi_ctx *ctx = st->ctx;
+  stats_pack_kernel<<<4 + st->k_max, 256, 0, ctx->stream>>>(st->B, st->acc, d_packed + 2);
+  MLMCPI_LAUNCHED("stats_pack");
+  const double head[2] = {(double)st->B, (double)st->n_samples * st->B};
+  // 16 bytes from a stack buffer: the driver stages pageable sources before returning
+  MLMCPI_CUDA(cudaMemcpyAsync(d_packed, head, sizeof(head), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int mlmcpi_stats_pack(mlmcpi_stats *st, double *h_packed) {
+  mlmcpi_ctx *ctx = st->ctx;
+  stats_pack_kernel<<<4 + st->k_max, 256, 0, ctx->stream>>>(st->B, st->acc, st->packed);
+  MLMCPI_LAUNCHED("stats_pack");
+  h_packed[0] = st->B;
+  h_packed[1] = (double)st->n_samples * st->B;
+  MLMCPI_CUDA(cudaMemcpyAsync(h_packed + 2, st->packed, sizeof(double) * (4 + st->k_max),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// common/statistics.cc:29-97 with "ranks" = chains: packed[0] = number of chains,
+// packed[1] = total number of samples; every entry is additive over GPUs
+int mlmcpi_stats_finalize(const double *p, int k_max, double out[6]) {
+  const double n_chains = p[0];
+  const double n_tot = p[1]; // mpi_allreduce_sum(n_samples_longterm)
+  if (n_chains < 1 || n_tot < 2)
+    return MLMCPI_EINVAL;
+  const double avg = p[2] / n_chains;          // mpi_allreduce_avg(avg_longterm)
+  const double avg2 = p[3] / n_chains, avg3 = p[4] / n_chains, avg4 = p[5] / n_chains;
+  const double S0 = p[6] / n_chains;
+  const double variance = n_tot / (n_tot - 1.0) * (S0 - avg * avg);
+  const double variance_error =
+      std::sqrt(1.0 / n_tot *
+                (avg4 - 4 * avg * avg3 + 8 * avg * avg * avg2 - avg2 * avg2 - 4 * avg * avg * avg * avg));
+  const double C0 = S0 - avg * avg;
+  double tau = 0.0;
+  for (int k = 1; k < k_max; ++k)
+    tau += (1. - k / n_tot) * (p[6 + k] / n_chains - avg * avg);
+  const double tau_int = std::fmax(1.0, 1.0 + 2.0 * tau / C0);
+  out[0] = avg;
+  out[1] = variance;
+  out[2] = variance_error;
+  out[3] = tau_int;
+  out[4] = std::sqrt(tau_int * variance / n_tot);
+  out[5] = n_tot;
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,524 @@
+// common.cuh -- shared device/host pieces of libmlmcpi.so (sm_100a only).
+//
+// Context, launch bookkeeping, Philox4x32-10 streams, fp64 helper maths and the
+// four fill-in / heat-bath distributions of the reference's distribution/ folder
+// as device functions.  Reference citations are relative to /root/reference/src.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mlmcpi.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+// --------------------------------------------------------------------- context
+#define MLMCPI_N_WORK 8
+struct mlmcpi_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint64_t seed = 0;
+  uint64_t launches = 0;
+  int n_sm = 148;
+  std::string err;
+  // optional timing of the dominant kernel (leapfrog) with CUDA events on ctx->stream
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events; // (begin, end) pairs not yet read
+  double prof_ms = 0.0, prof_bytes = 0.0;
+  uint64_t prof_launches = 0;
+  double *scratch = nullptr; // reduction partials / work vectors
+  size_t scratch_n = 0;
+  double *work[MLMCPI_N_WORK] = {}; // 0-3: HMC work states, 4-6: two-level step
+  size_t work_n[MLMCPI_N_WORK] = {};
+};
+
+int ctx_fail(mlmcpi_ctx *ctx, int code, const char *what, const char *detail = nullptr);
+int ctx_check_launch(mlmcpi_ctx *ctx, const char *what);
+double *ctx_scratch(mlmcpi_ctx *ctx, size_t n);          // >= n doubles, nullptr on failure
+double *ctx_work(mlmcpi_ctx *ctx, int which, size_t n);  // persistent work vector
+void prof_begin(mlmcpi_ctx *ctx);
+void prof_end(mlmcpi_ctx *ctx, uint64_t launches, double algorithmic_bytes);
+
+#define MLMCPI_CUDA(call)                                                      \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess)                                                    \
+      return ctx_fail(ctx, MLMCPI_ECUDA, #call, cudaGetErrorString(e__));      \
+  } while (0)
+
+#define MLMCPI_LAUNCHED(what)                                                  \
+  do {                                                                         \
+    int rc__ = ctx_check_launch(ctx, what);                                    \
+    if (rc__)                                                                  \
+      return rc__;                                                             \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------- RNG
+// Philox4x32-10 (Salmon et al. SC'11).  Stream convention: see include/mlmcpi.h.
+struct Rng {
+  uint32_t c0, c1, c2, a, k0, k1;
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+__device__ __forceinline__ Rng rng_init(uint64_t seed, int stream, uint64_t draw, uint32_t chain,
+                                        uint32_t index) {
+  Rng r;
+  r.c0 = index;
+  r.c1 = chain;
+  r.c2 = (uint32_t)draw;
+  r.a = ((uint32_t)stream) << 24;
+  r.k0 = (uint32_t)seed;
+  r.k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(draw >> 32);
+  return r;
+}
+
+__device__ __forceinline__ void rng_uniform2(Rng &r, double &u0, double &u1) {
+  uint32_t o[4];
+  philox4x32_10(r.c0, r.c1, r.c2, r.a, r.k0, r.k1, o);
+  r.a += 1;
+  u0 = ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) * (1.0 / 9007199254740992.0);
+  u1 = ((double)(o[2] >> 5) * 67108864.0 + (double)(o[3] >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void rng_normal2(Rng &r, double &z0, double &z1) {
+  double u0, u1, s, c;
+  rng_uniform2(r, u0, u1);
+  const double rad = sqrt(-2.0 * log(1.0 - u0));
+  sincospi(2.0 * u1, &s, &c);
+  z0 = rad * c;
+  z1 = rad * s;
+}
+
+__device__ __forceinline__ double rng_angle2(Rng &r, double &second) {
+  double u0, u1;
+  rng_uniform2(r, u0, u1);
+  second = -M_PI + 2. * M_PI * u1;
+  return -M_PI + 2. * M_PI * u0;
+}
+
+// ----------------------------------------------------------------------- maths
+// common/auxilliary.hh:42-44 (same operation order; no FMA-contractible pattern
+// feeds the floor, so the branch cut is the reference's)
+__device__ __forceinline__ double mod_2pi(const double x) {
+  return x - 2. * M_PI * floor(0.5 * (x + M_PI) / M_PI);
+}
+// integer winding number n with x = mod_2pi(x) + 2 pi n
+__device__ __forceinline__ double winding(const double x) { return floor(0.5 * (x + M_PI) / M_PI); }
+
+// e^{-z} I0(z): stands in for gsl_sf_bessel_I0_scaled
+__device__ __forceinline__ double bessel_I0_scaled(const double z) {
+  const double az = fabs(z);
+  if (az <= 600.0)
+    return exp(-az) * cyl_bessel_i0(az);
+  // Hankel asymptotic series, DLMF 10.40.1
+  double term = 1.0, sum = 1.0;
+  for (int k = 1; k < 12; ++k) {
+    term *= (2.0 * k - 1.0) * (2.0 * k - 1.0) / (8.0 * k * az);
+    sum += term;
+  }
+  return sum * rsqrt(2.0 * M_PI * az);
+}
+
+// common/fastbessel.hh:38-50
+__host__ __device__ constexpr double mbc(int n) {
+  return n == 0 ? 1.0 : 0.125 * (2.0 * n - 1.0) * (2.0 * n - 1.0) / n * mbc(n - 1);
+}
+// common/fastbessel.cc:7-49
+__device__ __forceinline__ double fast_bessel_I0_scaled(const double z) {
+  // a_n = (2n-1)^2 / (8 n) a_{n-1}, evaluated like the reference's constexpr template
+  constexpr double a1 = mbc(1), a2 = mbc(2), a3 = mbc(3), a4 = mbc(4), a5 = mbc(5), a6 = mbc(6),
+                   a7 = mbc(7);
+  if (z > 100.) {
+    const double z_inv = 1. / z;
+    double p;
+    if (z > 1100.) {
+      p = a4;
+    } else if (z > 400.) {
+      p = a5;
+      p = z_inv * p + a4;
+    } else if (z > 200.) {
+      p = a6;
+      p = z_inv * p + a5;
+      p = z_inv * p + a4;
+    } else {
+      p = a7;
+      p = z_inv * p + a6;
+      p = z_inv * p + a5;
+      p = z_inv * p + a4;
+    }
+    p = z_inv * p + a3;
+    p = z_inv * p + a2;
+    p = z_inv * p + a1;
+    p = z_inv * p + 1.0;
+    return p / sqrt(2. * M_PI * z);
+  }
+  return bessel_I0_scaled(z);
+}
+
+// --------------------------------------------------------------- distributions
+// Random numbers are consumed in blocks: one rng_normal2 + one rng_uniform2 serve
+// two consecutive attempts (z0,u0), (z1,u1) (stream convention: include/mlmcpi.h).
+
+// distribution/expsin2distribution.hh:44-58
+__device__ __forceinline__ double expsin2_draw(Rng &r, const double sigma) {
+  const double scale = M_PI / sqrt(2. * sigma);
+  for (;;) {
+    double z0, z1, u0, u1;
+    rng_normal2(r, z0, z1);
+    rng_uniform2(r, u0, u1);
+    double r_x = scale * z0;
+    if (fabs(r_x) < M_PI) {
+      const double s = sin(0.5 * r_x);
+      if (u0 < exp(-sigma * (s * s - r_x * r_x / (M_PI * M_PI))))
+        return r_x;
+    }
+    r_x = scale * z1;
+    if (fabs(r_x) < M_PI) {
+      const double s = sin(0.5 * r_x);
+      if (u1 < exp(-sigma * (s * s - r_x * r_x / (M_PI * M_PI))))
+        return r_x;
+    }
+  }
+}
+
+// distribution/expsin2distribution.cc:7-24
+__device__ __forceinline__ double expsin2_pdf(const double x, const double sigma) {
+  const double s = sin(0.5 * x);
+  const double z = 0.5 * sigma;
+  double besselI0;
+  if (z > 100.) {
+    const double z_inv = 1. / z;
+    besselI0 = sqrt(2. * M_PI * z_inv) * (1. + 0.125 * z_inv + 0.0703125 * z_inv * z_inv);
+  } else {
+    besselI0 = 2. * M_PI * bessel_I0_scaled(z);
+  }
+  return exp(-sigma * s * s) / besselI0;
+}
+
+// distribution/expcosdistribution.hh:50-65
+__device__ __forceinline__ double expcos_draw(Rng &r, const double beta, const double x_p,
+                                              const double x_m) {
+  const double fourpi2_inv = 1. / (4. * M_PI * M_PI);
+  const double dx = x_m - x_p;
+  const double tau = 2. * beta * fabs(cos(0.5 * dx));
+  const double sigma = M_PI * sqrt(2. / tau);
+  double x = 0.0;
+  bool accepted = false;
+  while (!accepted) {
+    double z0, z1, u0, u1;
+    rng_normal2(r, z0, z1);
+    rng_uniform2(r, u0, u1);
+    x = sigma * z0;
+    if ((-M_PI <= x) && (x < M_PI))
+      accepted = (u0 <= exp(tau * (cos(x) - 1. + fourpi2_inv * x * x)));
+    if (!accepted) {
+      x = sigma * z1;
+      if ((-M_PI <= x) && (x < M_PI))
+        accepted = (u1 <= exp(tau * (cos(x) - 1. + fourpi2_inv * x * x)));
+    }
+  }
+  return mod_2pi(x + 0.5 * (x_p + x_m) + (fabs(dx) > M_PI) * M_PI);
+}
+
+// distribution/expcosdistribution.cc:7-21
+__device__ __forceinline__ double expcos_pdf(const double beta, const double x, const double x_p,
+                                             const double x_m) {
+  double dx = x_p - x_m;
+  double z = x - x_m;
+  int sign_flip = (dx < 0.0) ? -1 : +1;
+  dx *= sign_flip;
+  if (dx > M_PI) {
+    sign_flip *= -1;
+    dx = 2. * M_PI - dx;
+  }
+  z *= sign_flip;
+  const double sigma = 2. * beta * fabs(cos(0.5 * dx));
+  const double Z_norm = 2. * M_PI * fast_bessel_I0_scaled(sigma);
+  return 1. / Z_norm * exp(sigma * (cos(z - 0.5 * dx) - 1.0));
+}
+
+// constants of distribution/besselproductdistribution.hh:52-80, computed on the
+// host once per level (besselproduct_setup in capi.cu) and passed by value
+struct BesselProductConst {
+  double beta;
+  double I0_twobeta;
+  double log_I0_twobeta;
+  double sigma_beta;
+  double alphaZ[17];
+};
+
+// distribution/besselproductdistribution.hh:82-142
+__device__ __forceinline__ double besselproduct_draw(Rng &r, const BesselProductConst &bp,
+                                                     const double x_p, const double x_m) {
+  const double beta = bp.beta, sigma_beta = bp.sigma_beta, L = bp.log_I0_twobeta;
+  double dx = x_m - x_p;
+  const double sign_flip = (dx < 0) ? -1 : +1;
+  dx *= sign_flip;
+  // pow(I0_twobeta, e) = exp(e * log I0_twobeta)
+  const double N_p = erf((M_PI - 0.5 * dx) / sigma_beta);
+  const double N_m = erf(0.5 * dx / sigma_beta) * exp(L * (2. * (dx / M_PI - 1.)));
+  const double C_gauss_p = exp(L * (2. * (1. - dx * dx / (4. * M_PI * M_PI))));
+  const double C_gauss_m =
+      exp(L * (2. * (1. - (dx - 2. * M_PI) * (dx - 2. * M_PI) / (4. * M_PI * M_PI))));
+  const double sigma = sigma_beta / sqrt(2.);
+  const double p_left = N_m / (N_p + N_m);
+  double x = 0.0;
+  for (;;) {
+    double xi, xi_acc, a_min, a_max, mu, C_gauss;
+    rng_uniform2(r, xi, xi_acc);
+    if (xi >= p_left) {
+      a_min = -M_PI + dx;
+      a_max = +M_PI;
+      mu = 0.5 * dx;
+      C_gauss = C_gauss_p;
+    } else {
+      a_min = -M_PI;
+      a_max = -M_PI + dx;
+      mu = 0.5 * (dx - 2. * M_PI);
+      C_gauss = C_gauss_m;
+    }
+    bool inside = false;
+    while (!inside) {
+      double z0, z1;
+      rng_normal2(r, z0, z1);
+      x = sigma * z0 + mu;
+      inside = ((x >= a_min) && (x < a_max));
+      if (!inside) {
+        x = sigma * z1 + mu;
+        inside = ((x >= a_min) && (x < a_max));
+      }
+    }
+    const double I0 = cyl_bessel_i0(fabs(2. * beta * cos(0.5 * x)));
+    const double I0_dx = cyl_bessel_i0(fabs(2. * beta * cos(0.5 * (x - dx))));
+    const double x_shifted = (x - mu) / sigma_beta;
+    const double rho_accept = I0 * I0_dx / C_gauss * exp(x_shifted * x_shifted);
+    if (xi_acc <= rho_accept)
+      break;
+  }
+  return mod_2pi(sign_flip * x + x_p);
+}
+
+// distribution/besselproductdistribution.cc:15-25 (rescaled = true)
+__device__ __forceinline__ double besselproduct_Znorm_inv_rescaled(const BesselProductConst &bp,
+                                                                   const double phi) {
+  double s = 1.0;
+#pragma unroll
+  for (int k = 1; k <= 16; ++k)
+    s += bp.alphaZ[k] * cos(k * phi);
+  return 1.0 / s;
+}
+
+// distribution/approximatebesselproductdistribution.cc:38-54 (the reference's rho,
+// SURVEY 7.3-8)
+__device__ __forceinline__ void approx_N_p_sigma2inv(const double beta, const double x0, double &N_p,
+                                                     double &sigma2_p_inv, double &sigma2_m_inv) {
+  const double epsilon = 0.125 * M_PI;
+  if (x0 < epsilon) {
+    sigma2_p_inv = beta;
+    sigma2_m_inv = 0.0;
+    N_p = 1.0;
+  } else {
+    sigma2_p_inv = beta * cos(0.25 * x0);
+    sigma2_m_inv = beta * sin(0.25 * x0);
+    const double q = sigma2_p_inv / sigma2_m_inv;
+    const double rho = q * sqrt(q) * exp(-4.0 * (sigma2_p_inv - sigma2_m_inv));
+    N_p = 1.0 / (1.0 + rho);
+  }
+}
+
+// distribution/approximatebesselproductdistribution.hh:81-106
+__device__ __forceinline__ double approxbessel_draw(Rng &r, const double beta, const double x_p,
+                                                    const double x_m) {
+  double x0 = x_p - x_m;
+  double sign_flip = (x0 < 0) ? -1 : +1;
+  x0 *= sign_flip;
+  if (x0 > M_PI) {
+    x0 = 2. * M_PI - x0;
+    sign_flip *= -1;
+  }
+  double N_p, sigma2_p_inv, sigma2_m_inv;
+  approx_N_p_sigma2inv(beta, x0, N_p, sigma2_p_inv, sigma2_m_inv);
+  double xi, unused, z0, z1;
+  rng_uniform2(r, xi, unused);
+  rng_normal2(r, z0, z1);
+  double sigma, xshift;
+  if (xi <= N_p) {
+    sigma = 1. / sqrt(sigma2_p_inv);
+    xshift = 0.0;
+  } else {
+    sigma = 1. / sqrt(sigma2_m_inv);
+    xshift = M_PI;
+  }
+  const double x = sigma * z0 + 0.5 * x0 - xshift;
+  return mod_2pi(sign_flip * x + x_m);
+}
+
+// distribution/approximatebesselproductdistribution.cc:7-35
+__device__ __forceinline__ double approxbessel_pdf(const double beta, const double x,
+                                                   const double x_p, const double x_m) {
+  double x0 = x_p - x_m;
+  double z = x - x_m;
+  double sign_flip = (x0 < 0) ? -1 : +1;
+  x0 *= sign_flip;
+  if (x0 > M_PI) {
+    x0 = 2. * M_PI - x0;
+    sign_flip *= -1;
+  }
+  z *= sign_flip;
+  double N_p, sigma2_p_inv, sigma2_m_inv;
+  approx_N_p_sigma2inv(beta, x0, N_p, sigma2_p_inv, sigma2_m_inv);
+  const double N_m = 1. - N_p;
+  const double sq_p = sqrt(sigma2_p_inv), sq_m = sqrt(sigma2_m_inv);
+  double s_p = 0.0, s_m = 0.0;
+#pragma unroll
+  for (int k = -4; k <= 4; ++k) {
+    double z_shifted = z - 0.5 * x0 + 2 * k * M_PI;
+    s_p += sq_p * exp(-0.5 * sigma2_p_inv * z_shifted * z_shifted);
+    z_shifted += M_PI;
+    s_m += sq_m * exp(-0.5 * sigma2_m_inv * z_shifted * z_shifted);
+  }
+  return sqrt(0.5 / M_PI) * (N_p * s_p + N_m * s_m);
+}
+
+// ------------------------------------------------------------------ reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum (result valid in thread 0); blockDim.x multiple of 32, <= 1024
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads(); // protect red[] against a previous use
+  if (lane == 0)
+    red[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (w == 0)
+    v = warp_sum(v);
+  return v;
+}
+
+// ------------------------------------------------------- per-model entry points
+// (implemented in qm.cu / schwinger.cu / gff.cu; dispatched from capi.cu)
+struct FillConst {
+  BesselProductConst bp; // valid when model == SCHWINGER, coarsening BOTH, beta <= 8
+};
+
+#define DECL_MODEL_API(ns)                                                                         \
+  namespace ns {                                                                                   \
+  int init_state(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);            \
+  int action(mlmcpi_ctx *, const mlmcpi_model *, const double *, int, double *);                   \
+  int force(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int);                    \
+  int leapfrog(mlmcpi_ctx *, const mlmcpi_model *, int, double, double *, double *, int);          \
+  int hmc_momentum(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);          \
+  int hmc_step(mlmcpi_ctx *, const mlmcpi_model *, int, double, double *, int, uint32_t, uint64_t, \
+               int32_t *, double *);                                                               \
+  int overrelax_sweep(mlmcpi_ctx *, const mlmcpi_model *, double *, int);                          \
+  int heatbath_sweep(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);        \
+  int prolong(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int);                  \
+  int restrict_(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int);                \
+  int fill(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);                  \
+  int prolong_fill(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t,    \
+                   uint64_t);                                                                      \
+  int cond_action(mlmcpi_ctx *, const mlmcpi_model *, const double *, int, double *);              \
+  int qoi(mlmcpi_ctx *, const mlmcpi_model *, int, const double *, int, double *, int64_t *);      \
+  }
+DECL_MODEL_API(qm)
+DECL_MODEL_API(schwinger)
+DECL_MODEL_API(gff)
+
+// host helpers shared by the model files (capi.cu)
+void besselproduct_setup(double beta, BesselProductConst *bp);
+// generic elementwise / accept kernels (capi.cu)
+int launch_hmc_accept(mlmcpi_ctx *ctx, int B, uint32_t chain0, uint64_t draw, const double *d_S_cur,
+                      const double *d_S_trial, const double *d_T_cur, const double *d_T_trial,
+                      int32_t *d_accept, double *d_diag);
+int launch_masked_copy(mlmcpi_ctx *ctx, double *d_dst, const double *d_src, size_t n, int B,
+                       const int32_t *d_accept);
+int launch_half_sqnorm(mlmcpi_ctx *ctx, const double *d_p, size_t n, int B, double *d_T);
+
+// ------------------------------------------- deterministic two-pass reductions
+// pass 1: every (chain, block) pair writes one partial per output; pass 2 sums
+// the partials of a chain in a fixed order (no atomics: results are reproducible).
+// F: __device__ void operator()(int chain, long long site, double acc[NOUT]) const
+template <int NOUT, class F>
+__global__ void site_reduce_kernel(F f, long long nsites, int nblk, int B, double *partial) {
+  const int chain = blockIdx.x / nblk, blk = blockIdx.x % nblk;
+  double acc[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k)
+    acc[k] = 0.0;
+  for (long long s = (long long)blk * blockDim.x + threadIdx.x; s < nsites;
+       s += (long long)nblk * blockDim.x)
+    f(chain, s, acc);
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k) {
+    const double v = block_sum(acc[k]);
+    if (threadIdx.x == 0)
+      partial[((size_t)k * B + chain) * nblk + blk] = v;
+  }
+}
+
+enum { EPI_SCALE = 0, EPI_CHI = 1 };
+// out[k][chain] = scale_k * sum;  EPI_CHI: out[chain] = scale_0 * sum_0^2 and
+// Qint[chain] = -round(sum_1)
+int launch_reduce_finish(mlmcpi_ctx *ctx, const double *partial, int nblk, int B, int nout, int epi,
+                         double scale0, double scale1, double *out, int64_t *Qint);
+
+// number of blocks per chain for a site reduction
+static inline int reduce_nblk(const mlmcpi_ctx *ctx, long long nsites, int B, int threads) {
+  const long long target = (long long)ctx->n_sm * 8;
+  long long nblk = (target + B - 1) / B;
+  const long long maxblk = (nsites + threads - 1) / threads;
+  if (nblk > maxblk)
+    nblk = maxblk;
+  if (nblk < 1)
+    nblk = 1;
+  return (int)nblk;
+}
+
+template <int NOUT, class F>
+int site_reduce(mlmcpi_ctx *ctx, const char *what, F f, long long nsites, int B, int epi,
+                double scale0, double scale1, double *out, int64_t *Qint) {
+  const int threads = 256;
+  const int nblk = reduce_nblk(ctx, nsites, B, threads);
+  double *partial = ctx_scratch(ctx, (size_t)NOUT * B * nblk);
+  if (!partial)
+    return MLMCPI_ENOMEM;
+  site_reduce_kernel<NOUT, F><<<nblk * B, threads, 0, ctx->stream>>>(f, nsites, nblk, B, partial);
+  MLMCPI_LAUNCHED(what);
+  return launch_reduce_finish(ctx, partial, nblk, B, NOUT, epi, scale0, scale1, out, Qint);
+}

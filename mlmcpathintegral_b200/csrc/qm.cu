@@ -1,0 +1,585 @@
+// qm.cu -- 1-D path models (harmonic oscillator, quartic oscillator, rotor).
+//
+// One WARP per chain.  A path of M <= 12800 sites is a few KiB, so a whole HMC
+// trajectory runs on-chip: x and p live in shared memory for the (nt+1) leapfrog
+// steps and HBM sees one read and one write of the path per trajectory
+// (SURVEY 7.4 "1-D paths").  Lanes stride over sites (site = lane + 32 k) so that
+// global and shared accesses are conflict-free; periodic neighbours come from
+// shared memory.  State layout [chain][site] = the reference's SampleState::data.
+//
+// Reference citations relative to /root/reference/src.
+#include "common.cuh"
+
+namespace {
+
+struct QM {
+  int model, M;
+  double a, T, m0, mu2, lambda, x0;
+};
+
+QM make_qm(const mlmcpi_model *m) {
+  QM q;
+  q.model = m->model;
+  q.M = m->M_lat;
+  q.a = m->a_lat;
+  q.T = m->T_final;
+  q.m0 = m->m0;
+  q.mu2 = m->mu2;
+  q.lambda = m->lambda;
+  q.x0 = m->x0;
+  return q;
+}
+
+constexpr int WARPS = 8;           // chains per block
+constexpr int THREADS = WARPS * 32;
+
+// force at one site.  qm/harmonicoscillatoraction.cc:21-35,
+// qm/quarticoscillatoraction.cc:31-53, qm/rotoraction.cc:58-79
+template <int MODEL>
+__device__ __forceinline__ double site_force(const QM &q, double xm, double x, double xp) {
+  if (MODEL == MLMCPI_ROTOR) {
+    return (q.m0 / q.a) * (sin(x - xm) + sin(x - xp));
+  } else {
+    const double tmp_1 = q.m0 / q.a;
+    const double tmp_2 = 2. + q.a * q.a * q.mu2;
+    double f = tmp_1 * (tmp_2 * x - xm - xp);
+    if (MODEL == MLMCPI_QUARTIC) {
+      const double xs = x - q.x0;
+      f += (q.a * q.lambda) * xs * xs * xs;
+    }
+    return f;
+  }
+}
+
+// action density of site j (needs x_{j-1}); the prefactors are applied by the caller.
+// qm/harmonicoscillatoraction.cc:8-18, qm/quarticoscillatoraction.cc:7-28,
+// qm/rotoraction.cc:9-18
+template <int MODEL>
+__device__ __forceinline__ double site_action(const QM &q, double xm, double x) {
+  const double d = x - xm;
+  if (MODEL == MLMCPI_ROTOR)
+    return 1. - cos(d);
+  const double ainv2 = 1. / (q.a * q.a);
+  if (MODEL == MLMCPI_HO)
+    return ainv2 * d * d + q.mu2 * x * x;
+  const double xs = x - q.x0;
+  const double xs2 = xs * xs;
+  return q.m0 * (ainv2 * d * d + q.mu2 * x * x) + 0.5 * q.lambda * xs2 * xs2;
+}
+template <int MODEL> __device__ __forceinline__ double action_prefactor(const QM &q) {
+  if (MODEL == MLMCPI_ROTOR)
+    return q.m0 / q.a;
+  if (MODEL == MLMCPI_HO)
+    return 0.5 * q.a * q.m0;
+  return 0.5 * q.a;
+}
+
+// qm/harmonicoscillatoraction.hh:171-189, qm/quarticoscillatoraction.hh:160-194,
+// qm/rotoraction.hh:195-213
+template <int MODEL>
+__device__ __forceinline__ void W_min_curv(const QM &q, double x_m, double x_p, double &Wmin,
+                                           double &Wcurv) {
+  if (MODEL == MLMCPI_ROTOR) {
+    Wcurv = 2.0 * q.m0 / q.a * fabs(cos(0.5 * (x_p - x_m)));
+    double sp, cp, sm, cm;
+    sincos(x_p, &sp, &cp);
+    sincos(x_m, &sm, &cm);
+    Wmin = atan2(sp + sm, cp + cm);
+  } else if (MODEL == MLMCPI_HO) {
+    Wcurv = (2. / q.a + q.a * q.mu2) * q.m0;
+    Wmin = (0.5 / (1. + 0.5 * q.a * q.a * q.mu2)) * (x_m + x_p);
+  } else {
+    const double xbar = 0.5 * (x_m + x_p);
+    Wcurv = (2. / q.a + q.a * q.mu2) * q.m0 + 3. * q.lambda * q.a * (xbar - q.x0) * (xbar - q.x0);
+    const double rho = 1. / (1. + 0.5 * q.a * q.a * q.mu2);
+    double x = xbar;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double xs = x - q.x0;
+      x = rho * (xbar - 0.5 * q.a * q.a * q.lambda / q.m0 * xs * xs * xs);
+    }
+    Wmin = x;
+  }
+}
+
+#define WARP_SETUP                                                                                 \
+  const int lane = threadIdx.x & 31;                                                               \
+  const int w = threadIdx.x >> 5;                                                                  \
+  const long long chain = (long long)blockIdx.x * WARPS + w;                                       \
+  const bool active = chain < B;                                                                   \
+  const long long c_safe = active ? chain : 0;                                                     \
+  (void)lane;                                                                                      \
+  (void)w;
+
+// ----------------------------------------------------------------- init_state
+__global__ void init_state_kernel(QM q, double *x, int B, uint32_t chain0, uint64_t seed,
+                                  uint64_t draw) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int pairs = (q.M + 1) / 2;
+  if (t >= (long long)B * pairs)
+    return;
+  const int chain = (int)(t / pairs), k = (int)(t % pairs);
+  double v0 = 0.0, v1 = 0.0;
+  if (q.model == MLMCPI_ROTOR) { // qm/rotoraction.cc:82-85
+    Rng r = rng_init(seed, MLMCPI_STREAM_INIT, draw, chain0 + chain, k);
+    v0 = rng_angle2(r, v1);
+  } // HO / quartic: zeros, qm/harmonicoscillatoraction.hh:155-158
+  double *xc = x + (size_t)chain * q.M;
+  xc[2 * k] = v0;
+  if (2 * k + 1 < q.M)
+    xc[2 * k + 1] = v1;
+}
+
+// --------------------------------------------------------------------- action
+template <int MODEL> __global__ void action_kernel(QM q, const double *x, int B, double *S) {
+  WARP_SETUP
+  const double *xc = x + (size_t)c_safe * q.M;
+  double acc = 0.0;
+  for (int s = lane; s < q.M; s += 32) {
+    const double xm = xc[s == 0 ? q.M - 1 : s - 1];
+    acc += site_action<MODEL>(q, xm, xc[s]);
+  }
+  acc = warp_sum(acc);
+  if (active && lane == 0)
+    S[chain] = action_prefactor<MODEL>(q) * acc;
+}
+
+// ---------------------------------------------------------------------- force
+template <int MODEL> __global__ void force_kernel(QM q, const double *x, double *f, int B) {
+  WARP_SETUP
+  if (!active)
+    return;
+  const double *xc = x + (size_t)chain * q.M;
+  double *fc = f + (size_t)chain * q.M;
+  for (int s = lane; s < q.M; s += 32) {
+    const double xm = xc[s == 0 ? q.M - 1 : s - 1], xp = xc[s == q.M - 1 ? 0 : s + 1];
+    fc[s] = site_force<MODEL>(q, xm, xc[s], xp);
+  }
+}
+
+// ------------------------------------------------- on-chip trajectory (device)
+// xs, ps: this warp's shared arrays.  sampler/hmcsampler.cc:31-46
+template <int MODEL>
+__device__ __forceinline__ void trajectory(const QM &q, int nt, double dt, double *xs, double *ps,
+                                           int lane) {
+  const int M = q.M;
+  for (int k = 0; k <= nt; ++k) {
+    const double dt_p = (k == 0 || k == nt) ? 0.5 * dt : dt;
+    const double dt_x = (k == nt) ? 0.0 : dt;
+    for (int s = lane; s < M; s += 32) {
+      const double xm = xs[s == 0 ? M - 1 : s - 1], xp = xs[s == M - 1 ? 0 : s + 1];
+      ps[s] -= dt_p * site_force<MODEL>(q, xm, xs[s], xp);
+    }
+    __syncwarp();
+    for (int s = lane; s < M; s += 32)
+      xs[s] += dt_x * ps[s];
+    __syncwarp();
+  }
+}
+
+template <int MODEL>
+__global__ void leapfrog_kernel(QM q, int nt, double dt, double *x, double *p, int B) {
+  extern __shared__ double smem[];
+  WARP_SETUP
+  double *xs = smem + (size_t)w * 2 * q.M, *ps = xs + q.M;
+  double *xc = x + (size_t)c_safe * q.M, *pc = p + (size_t)c_safe * q.M;
+  for (int s = lane; s < q.M; s += 32) {
+    xs[s] = xc[s];
+    ps[s] = pc[s];
+  }
+  __syncwarp();
+  trajectory<MODEL>(q, nt, dt, xs, ps, lane);
+  if (active)
+    for (int s = lane; s < q.M; s += 32) {
+      xc[s] = xs[s];
+      pc[s] = ps[s];
+    }
+}
+
+__global__ void momentum_kernel(QM q, double *p, int B, uint32_t chain0, uint64_t seed,
+                                uint64_t draw) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int pairs = (q.M + 1) / 2;
+  if (t >= (long long)B * pairs)
+    return;
+  const int chain = (int)(t / pairs), k = (int)(t % pairs);
+  Rng r = rng_init(seed, MLMCPI_STREAM_HMC_MOMENTUM, draw, chain0 + chain, k);
+  double z0, z1;
+  rng_normal2(r, z0, z1);
+  double *pc = p + (size_t)chain * q.M;
+  pc[2 * k] = z0;
+  if (2 * k + 1 < q.M)
+    pc[2 * k + 1] = z1;
+}
+
+// HMCSampler::single_step, sampler/hmcsampler.cc:22-69, one warp per chain, all
+// on-chip: momentum refresh, kinetic energies, trajectory, both action
+// evaluations, accept/reject and the conditional write-back.
+template <int MODEL>
+__global__ void hmc_step_kernel(QM q, int nt, double dt, double *x, int B, uint32_t chain0,
+                                uint64_t seed, uint64_t draw, int32_t *accept_out, double *diag) {
+  extern __shared__ double smem[];
+  WARP_SETUP
+  const int M = q.M;
+  double *xs = smem + (size_t)w * 2 * M, *ps = xs + M;
+  double *xc = x + (size_t)c_safe * M;
+  const uint32_t gchain = chain0 + (uint32_t)c_safe;
+  for (int s = lane; s < M; s += 32)
+    xs[s] = xc[s];
+  for (int k = lane; 2 * k < M; k += 32) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_HMC_MOMENTUM, draw, gchain, k);
+    double z0, z1;
+    rng_normal2(r, z0, z1);
+    ps[2 * k] = z0;
+    if (2 * k + 1 < M)
+      ps[2 * k + 1] = z1;
+  }
+  __syncwarp();
+  double T_cur = 0.0, S_cur = 0.0;
+  for (int s = lane; s < M; s += 32) {
+    T_cur += ps[s] * ps[s];
+    S_cur += site_action<MODEL>(q, xs[s == 0 ? M - 1 : s - 1], xs[s]);
+  }
+  T_cur = 0.5 * warp_sum(T_cur);
+  S_cur = action_prefactor<MODEL>(q) * warp_sum(S_cur);
+  trajectory<MODEL>(q, nt, dt, xs, ps, lane);
+  double T_trial = 0.0, S_trial = 0.0;
+  for (int s = lane; s < M; s += 32) {
+    T_trial += ps[s] * ps[s];
+    S_trial += site_action<MODEL>(q, xs[s == 0 ? M - 1 : s - 1], xs[s]);
+  }
+  T_trial = 0.5 * warp_sum(T_trial);
+  S_trial = action_prefactor<MODEL>(q) * warp_sum(S_trial);
+  const double deltaH = (S_trial - S_cur) + (T_trial - T_cur);
+  bool acc = deltaH < 0.0;
+  if (!acc) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_HMC_ACCEPT, draw, gchain, 0);
+    double u0, u1;
+    rng_uniform2(r, u0, u1);
+    acc = u0 < exp(-deltaH);
+  }
+  if (!active)
+    return;
+  if (acc)
+    for (int s = lane; s < M; s += 32)
+      xc[s] = xs[s];
+  if (lane == 0) {
+    if (accept_out)
+      accept_out[chain] = acc ? 1 : 0;
+    if (diag) {
+      double *d = diag + 5 * chain;
+      d[0] = deltaH;
+      d[1] = S_cur;
+      d[2] = S_trial;
+      d[3] = T_cur;
+      d[4] = T_trial;
+    }
+  }
+}
+
+// --------------------------------------------------------------------- sweeps
+// rotor only (qm/rotoraction.cc:21-56); colours: even sites, then odd sites
+template <bool HEATBATH>
+__global__ void rotor_sweep_kernel(QM q, double *x, int B, uint32_t chain0, uint64_t seed,
+                                   uint64_t draw) {
+  WARP_SETUP
+  const int M = q.M;
+  double *xc = x + (size_t)c_safe * M;
+  for (int colour = 0; colour < 2; ++colour) {
+    if (active)
+      for (int s = 2 * lane + colour; s < M; s += 64) {
+        const double x_m = xc[s == 0 ? M - 1 : s - 1], x_p = xc[s == M - 1 ? 0 : s + 1];
+        double x0, curv;
+        W_min_curv<MLMCPI_ROTOR>(q, x_m, x_p, x0, curv);
+        if (HEATBATH) {
+          Rng r = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, s);
+          xc[s] = mod_2pi(x0 + expsin2_draw(r, 2. * curv));
+        } else {
+          xc[s] = mod_2pi(2.0 * x0 - xc[s]);
+        }
+      }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------- prolong / restrict
+// qm/qmaction.cc:7-26
+__global__ void prolong_kernel(int M, const double *xc, double *x, int B) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Mc = M / 2;
+  if (t >= (long long)B * Mc)
+    return;
+  const long long chain = t / Mc;
+  const int j = (int)(t % Mc);
+  x[chain * M + 2 * j] = xc[t];
+}
+__global__ void restrict_kernel(int M, const double *xf, double *xc, int B) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Mc = M / 2;
+  if (t >= (long long)B * Mc)
+    return;
+  const long long chain = t / Mc;
+  const int j = (int)(t % Mc);
+  xc[t] = xf[chain * M + 2 * j];
+}
+
+// ---------------------------------------------------------------------- fill
+// qm/gaussianconditionedfineaction.cc:7-24, qm/rotorconditionedfineaction.cc:7-24.
+// xcoarse != nullptr: prolongation fused in (even sites come from the coarse path).
+template <int MODEL>
+__global__ void fill_kernel(QM q, const double *xcoarse, double *x, int B, uint32_t chain0,
+                            uint64_t seed, uint64_t draw) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Mc = q.M / 2;
+  if (t >= (long long)B * Mc)
+    return;
+  const long long chain = t / Mc;
+  const int j = (int)(t % Mc);
+  double *xc = x + chain * q.M;
+  double x_m, x_p;
+  if (xcoarse) {
+    const double *cc = xcoarse + chain * Mc;
+    x_m = cc[j];
+    x_p = cc[j == Mc - 1 ? 0 : j + 1];
+    xc[2 * j] = x_m;
+  } else {
+    x_m = xc[2 * j];
+    x_p = xc[j == Mc - 1 ? 0 : 2 * j + 2];
+  }
+  double x0, curv;
+  W_min_curv<MODEL>(q, x_m, x_p, x0, curv);
+  Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, chain0 + (uint32_t)chain, j);
+  if (MODEL == MLMCPI_ROTOR) {
+    xc[2 * j + 1] = mod_2pi(x0 + expsin2_draw(r, 2. * curv));
+  } else {
+    double z0, z1;
+    rng_normal2(r, z0, z1);
+    xc[2 * j + 1] = x0 + z0 * (1. / sqrt(curv));
+  }
+}
+
+// --------------------------------------------------------------- cond_action
+// qm/gaussianconditionedfineaction.cc:27-43, qm/rotorconditionedfineaction.cc:27-43
+template <int MODEL> __global__ void cond_action_kernel(QM q, const double *x, int B, double *S) {
+  WARP_SETUP
+  const int M = q.M, Mc = q.M / 2;
+  const double *xc = x + (size_t)c_safe * M;
+  double acc = 0.0;
+  for (int j = lane; j < Mc; j += 32) {
+    const double x_m = xc[2 * j], x_p = xc[j == Mc - 1 ? 0 : 2 * j + 2];
+    double x0, curv;
+    W_min_curv<MODEL>(q, x_m, x_p, x0, curv);
+    const double dx = xc[2 * j + 1] - x0;
+    if (MODEL == MLMCPI_ROTOR)
+      acc += -log(expsin2_pdf(dx, 2.0 * curv));
+    else
+      acc += 0.5 * curv * dx * dx - 0.5 * log(curv);
+  }
+  acc = warp_sum(acc);
+  if (active && lane == 0)
+    S[chain] = acc;
+}
+
+// ---------------------------------------------------------------------- QoIs
+// qoi/qm/qoixsquared.cc:7-20, qoi/qm/qoisusceptibility.cc:7-23
+__global__ void qoi_kernel(QM q, int qoi, const double *x, int B, double *out, int64_t *Qint) {
+  WARP_SETUP
+  const int M = q.M;
+  const double *xc = x + (size_t)c_safe * M;
+  double acc = 0.0, nwind = 0.0, dsum = 0.0;
+  for (int s = lane; s < M; s += 32) {
+    if (qoi == MLMCPI_QOI_X2) {
+      acc += xc[s] * xc[s];
+    } else {
+      const double dx = xc[s] - xc[s == 0 ? M - 1 : s - 1];
+      acc += mod_2pi(dx);
+      nwind += winding(dx);
+      dsum += dx;
+    }
+  }
+  acc = warp_sum(acc);
+  nwind = warp_sum(nwind);
+  if (active && lane == 0) {
+    if (qoi == MLMCPI_QOI_X2) {
+      out[chain] = acc / M;
+    } else {
+      const double four_pi2_inv = 0.25 / (M_PI * M_PI);
+      out[chain] = four_pi2_inv * (acc * acc) / q.T;
+      // sum_j dx_j = 0 exactly in exact arithmetic, so Q / 2 pi = - sum of windings
+      if (Qint)
+        Qint[chain] = -(int64_t)llrint(nwind);
+    }
+  }
+  (void)dsum;
+}
+
+size_t traj_smem(const QM &q) { return (size_t)WARPS * 2 * q.M * sizeof(double); }
+
+template <typename K> int prepare_smem(mlmcpi_ctx *ctx, K kernel, size_t bytes) {
+  if (bytes > 227 * 1024)
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "1-D path too long for the on-chip trajectory kernel");
+  if (bytes > 48 * 1024)
+    MLMCPI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+} // namespace
+
+#define QM_DISPATCH(MODEL_VAR, ...)                                                              \
+  switch (MODEL_VAR) {                                                                             \
+  case MLMCPI_HO: {                                                                                \
+    constexpr int MODEL = MLMCPI_HO;                                                               \
+    __VA_ARGS__;                                                                                          \
+  } break;                                                                                         \
+  case MLMCPI_QUARTIC: {                                                                           \
+    constexpr int MODEL = MLMCPI_QUARTIC;                                                          \
+    __VA_ARGS__;                                                                                          \
+  } break;                                                                                         \
+  default: {                                                                                       \
+    constexpr int MODEL = MLMCPI_ROTOR;                                                            \
+    __VA_ARGS__;                                                                                          \
+  } break;                                                                                         \
+  }
+
+namespace qm {
+
+int init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,
+               uint64_t draw) {
+  QM q = make_qm(m);
+  const long long n = (long long)B * ((q.M + 1) / 2);
+  init_state_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(q, x, B, chain0, ctx->seed, draw);
+  MLMCPI_LAUNCHED("qm::init_state");
+  return 0;
+}
+
+int action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, double *S) {
+  QM q = make_qm(m);
+  QM_DISPATCH(q.model, (action_kernel<MODEL><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, B, S)));
+  MLMCPI_LAUNCHED("qm::action");
+  return 0;
+}
+
+int force(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, double *f, int B) {
+  QM q = make_qm(m);
+  QM_DISPATCH(q.model, (force_kernel<MODEL><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, f, B)));
+  MLMCPI_LAUNCHED("qm::force");
+  return 0;
+}
+
+int leapfrog(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *x, double *p, int B) {
+  QM q = make_qm(m);
+  const size_t smem = traj_smem(q);
+  QM_DISPATCH(q.model, {
+    int rc = prepare_smem(ctx, leapfrog_kernel<MODEL>, smem);
+    if (rc)
+      return rc;
+    leapfrog_kernel<MODEL><<<cdiv(B, WARPS), THREADS, smem, ctx->stream>>>(q, nt, dt, x, p, B);
+  });
+  MLMCPI_LAUNCHED("qm::leapfrog");
+  return 0;
+}
+
+int hmc_momentum(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *p, int B, uint32_t chain0,
+                 uint64_t draw) {
+  QM q = make_qm(m);
+  const long long n = (long long)B * ((q.M + 1) / 2);
+  momentum_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(q, p, B, chain0, ctx->seed, draw);
+  MLMCPI_LAUNCHED("qm::hmc_momentum");
+  return 0;
+}
+
+int hmc_step(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *x, int B,
+             uint32_t chain0, uint64_t draw, int32_t *accept, double *diag) {
+  QM q = make_qm(m);
+  const size_t smem = traj_smem(q);
+  QM_DISPATCH(q.model, {
+    int rc = prepare_smem(ctx, hmc_step_kernel<MODEL>, smem);
+    if (rc)
+      return rc;
+    hmc_step_kernel<MODEL><<<cdiv(B, WARPS), THREADS, smem, ctx->stream>>>(
+        q, nt, dt, x, B, chain0, ctx->seed, draw, accept, diag);
+  });
+  MLMCPI_LAUNCHED("qm::hmc_step");
+  return 0;
+}
+
+int overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B) {
+  // Action::overrelaxation_update is only defined for the rotor among the QM
+  // actions (action/action.hh:84-92 default raises)
+  if (m->model != MLMCPI_ROTOR)
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "overrelaxation not defined for this action");
+  if (m->M_lat % 2)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need an even number of sites");
+  QM q = make_qm(m);
+  rotor_sweep_kernel<false><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, B, 0, 0, 0);
+  MLMCPI_LAUNCHED("qm::overrelax_sweep");
+  return 0;
+}
+
+int heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,
+                   uint64_t draw) {
+  if (m->model != MLMCPI_ROTOR)
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "heat bath not defined for this action");
+  if (m->M_lat % 2)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need an even number of sites");
+  QM q = make_qm(m);
+  rotor_sweep_kernel<true><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, B, chain0, ctx->seed, draw);
+  MLMCPI_LAUNCHED("qm::heatbath_sweep");
+  return 0;
+}
+
+int prolong(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B) {
+  if (m->M_lat % 2)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "M_lat must be even");
+  const long long n = (long long)B * (m->M_lat / 2);
+  prolong_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(m->M_lat, xc, x, B);
+  MLMCPI_LAUNCHED("qm::prolong");
+  return 0;
+}
+
+int restrict_(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xf, double *xc, int B) {
+  if (m->M_lat % 2)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "M_lat must be even");
+  const long long n = (long long)B * (m->M_lat / 2);
+  restrict_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(m->M_lat, xf, xc, B);
+  MLMCPI_LAUNCHED("qm::restrict");
+  return 0;
+}
+
+int prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
+                 uint32_t chain0, uint64_t draw) {
+  if (m->M_lat % 2)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "M_lat must be even");
+  QM q = make_qm(m);
+  const long long n = (long long)B * (q.M / 2);
+  QM_DISPATCH(q.model, (fill_kernel<MODEL><<<cdiv(n, 128), 128, 0, ctx->stream>>>(
+                           q, xc, x, B, chain0, ctx->seed, draw)));
+  MLMCPI_LAUNCHED("qm::fill");
+  return 0;
+}
+
+int fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0, uint64_t draw) {
+  return prolong_fill(ctx, m, nullptr, x, B, chain0, draw);
+}
+
+int cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, double *S) {
+  if (m->M_lat % 2)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "M_lat must be even");
+  QM q = make_qm(m);
+  QM_DISPATCH(q.model,
+              (cond_action_kernel<MODEL><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, B, S)));
+  MLMCPI_LAUNCHED("qm::cond_action");
+  return 0;
+}
+
+int qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int which, const double *x, int B, double *out,
+        int64_t *Qint) {
+  if (which != MLMCPI_QOI_X2 && which != MLMCPI_QOI_ROTOR_CHI)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "QoI not defined for 1-D paths");
+  QM q = make_qm(m);
+  qoi_kernel<<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, which, x, B, out, Qint);
+  MLMCPI_LAUNCHED("qm::qoi");
+  return 0;
+}
+
+} // namespace qm

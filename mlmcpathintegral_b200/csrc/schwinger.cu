@@ -1,0 +1,887 @@
+// schwinger.cu -- quenched Schwinger model: U(1) link angles on a periodic 2-D lattice.
+//
+// State layout [chain][ell], ell = 2*Mt*j + 2*i + mu exactly as the reference
+// (lattice/lattice2d.hh:348-353): the two links of a site are one aligned double2,
+// a warp reads 32 consecutive sites of a row = 512 contiguous bytes.
+//
+// Hot kernel: leapfrog_rowmarch_kernel.  One CTA = one lattice row segment of
+// Mt threads marching over R consecutive rows.  Each plaquette sine is computed
+// exactly once; sin P(i,j-1) is carried in a register from the previous row,
+// sin P(i-1,j) and theta(i+1,j,1) come from the neighbouring thread through
+// double-buffered shared memory (one __syncthreads per row).  HBM traffic per
+// site-step is the algorithmic minimum: R theta, R p, W theta, W p = 64 B.
+//
+// Reference citations relative to /root/reference/src.
+#include "common.cuh"
+
+namespace {
+
+struct SW {
+  int Mt, Mx;
+  double beta;
+};
+
+SW make_sw(const mlmcpi_model *m) {
+  SW s;
+  s.Mt = m->Mt_lat;
+  s.Mx = m->Mx_lat;
+  s.beta = m->beta;
+  return s;
+}
+
+__device__ __forceinline__ int wrap_inc(int i, int M) { return i + 1 == M ? 0 : i + 1; }
+__device__ __forceinline__ int wrap_dec(int i, int M) { return i == 0 ? M - 1 : i - 1; }
+
+#define TH(x, i, j, mu) (x)[2 * ((size_t)Mt * (j) + (i)) + (mu)]
+
+// plaquette angle, qft/quenchedschwingeraction.cc:14-17 (same summation order)
+__device__ __forceinline__ double plaq(const double *x, int Mt, int Mx, int i, int j) {
+  const int ip = wrap_inc(i, Mt), jp = wrap_inc(j, Mx);
+  const double2 own = *reinterpret_cast<const double2 *>(&TH(x, i, j, 0));
+  return own.x + TH(x, ip, j, 1) - TH(x, i, jp, 0) - own.y;
+}
+
+// qft/quenchedschwingeraction.cc:25-43
+__device__ __forceinline__ void staple_angles(const double *x, int Mt, int Mx, int i, int j, int mu,
+                                              double &theta_p, double &theta_m) {
+  const int ip = wrap_inc(i, Mt), im = wrap_dec(i, Mt), jp = wrap_inc(j, Mx), jm = wrap_dec(j, Mx);
+  if (mu == 0) {
+    theta_p = mod_2pi(TH(x, i, jp, 0) + TH(x, i, j, 1) - TH(x, ip, j, 1));
+    theta_m = mod_2pi(TH(x, i, jm, 0) + TH(x, ip, jm, 1) - TH(x, i, jm, 1));
+  } else {
+    theta_p = mod_2pi(TH(x, i, j, 0) + TH(x, ip, j, 1) - TH(x, i, jp, 0));
+    theta_m = mod_2pi(TH(x, im, jp, 0) + TH(x, im, j, 1) - TH(x, im, j, 0));
+  }
+}
+
+// ----------------------------------------------------------------- init_state
+// qft/quenchedschwingeraction.cc:198-204
+__global__ void init_state_kernel(SW sw, double *x, int B, uint32_t chain0, uint64_t seed,
+                                  uint64_t draw) {
+  const long long nsite = (long long)sw.Mt * sw.Mx;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsite * B)
+    return;
+  const int chain = (int)(t / nsite);
+  const uint32_t k = (uint32_t)(t % nsite);
+  Rng r = rng_init(seed, MLMCPI_STREAM_INIT, draw, chain0 + chain, k);
+  double v1;
+  const double v0 = rng_angle2(r, v1);
+  reinterpret_cast<double2 *>(x)[t] = make_double2(v0, v1);
+}
+
+// sampler/hmcsampler.cc:24-26
+__global__ void momentum_kernel(SW sw, double *p, int B, uint32_t chain0, uint64_t seed,
+                                uint64_t draw) {
+  const long long nsite = (long long)sw.Mt * sw.Mx;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsite * B)
+    return;
+  const int chain = (int)(t / nsite);
+  const uint32_t k = (uint32_t)(t % nsite);
+  Rng r = rng_init(seed, MLMCPI_STREAM_HMC_MOMENTUM, draw, chain0 + chain, k);
+  double z0, z1;
+  rng_normal2(r, z0, z1);
+  reinterpret_cast<double2 *>(p)[t] = make_double2(z0, z1);
+}
+
+// ----------------------------------------------------------------- reductions
+struct ActionF { // qft/quenchedschwingeraction.cc:7-22
+  SW sw;
+  const double *x;
+  __device__ void operator()(int chain, long long s, double acc[1]) const {
+    const int Mt = sw.Mt, Mx = sw.Mx;
+    const int j = (int)(s / Mt), i = (int)(s - (long long)j * Mt);
+    acc[0] += 1. - cos(plaq(x + (size_t)chain * 2 * Mt * Mx, Mt, Mx, i, j));
+  }
+};
+struct PlaqF { // qoi/qft/qoiavgplaquette.cc:7-27
+  SW sw;
+  const double *x;
+  __device__ void operator()(int chain, long long s, double acc[1]) const {
+    const int Mt = sw.Mt, Mx = sw.Mx;
+    const int j = (int)(s / Mt), i = (int)(s - (long long)j * Mt);
+    acc[0] += cos(plaq(x + (size_t)chain * 2 * Mt * Mx, Mt, Mx, i, j));
+  }
+};
+struct ChiF { // qoi/qft/qoi2dsusceptibility.cc:7-27
+  SW sw;
+  const double *x;
+  __device__ void operator()(int chain, long long s, double acc[2]) const {
+    const int Mt = sw.Mt, Mx = sw.Mx;
+    const int j = (int)(s / Mt), i = (int)(s - (long long)j * Mt);
+    const double th = plaq(x + (size_t)chain * 2 * Mt * Mx, Mt, Mx, i, j);
+    acc[0] += mod_2pi(th);
+    acc[1] += winding(th); // sum_P theta_P = 0 exactly => Q / 2 pi = - sum of windings
+  }
+};
+
+// ---------------------------------------------------------------------- force
+// gather form of qft/quenchedschwingeraction.cc:68-89: each link receives +F of
+// one plaquette and -F of another (two-term sums: order-independent, so this is
+// the reference's value given the same sin)
+__global__ void force_kernel(SW sw, const double *x, double *f, int B) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const long long nsite = (long long)Mt * Mx;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsite * B)
+    return;
+  const long long chain = t / nsite;
+  const int s = (int)(t - chain * nsite);
+  const int j = s / Mt, i = s - j * Mt;
+  const double *xc = x + chain * 2 * nsite;
+  const double F = sw.beta * sin(plaq(xc, Mt, Mx, i, j));
+  const double Fjm = sw.beta * sin(plaq(xc, Mt, Mx, i, wrap_dec(j, Mx)));
+  const double Fim = sw.beta * sin(plaq(xc, Mt, Mx, wrap_dec(i, Mt), j));
+  reinterpret_cast<double2 *>(f)[t] = make_double2(F - Fjm, Fim - F);
+}
+
+// ------------------------------------------------------------------- leapfrog
+// generic fallback (any Mt): three sines per site
+__global__ void leapfrog_naive_kernel(SW sw, double dt_p, double dt_x, const double *x_in,
+                                      double *x_out, double *p, int B) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const long long nsite = (long long)Mt * Mx;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsite * B)
+    return;
+  const long long chain = t / nsite;
+  const int s = (int)(t - chain * nsite);
+  const int j = s / Mt, i = s - j * Mt;
+  const double *xc = x_in + chain * 2 * nsite;
+  const double F = sw.beta * sin(plaq(xc, Mt, Mx, i, j));
+  const double Fjm = sw.beta * sin(plaq(xc, Mt, Mx, i, wrap_dec(j, Mx)));
+  const double Fim = sw.beta * sin(plaq(xc, Mt, Mx, wrap_dec(i, Mt), j));
+  double2 pp = reinterpret_cast<double2 *>(p)[t];
+  const double2 th = reinterpret_cast<const double2 *>(x_in)[t];
+  pp.x -= dt_p * (F - Fjm);
+  pp.y -= dt_p * (Fim - F);
+  reinterpret_cast<double2 *>(p)[t] = pp;
+  if (x_out)
+    reinterpret_cast<double2 *>(x_out)[t] = make_double2(th.x + dt_x * pp.x, th.y + dt_x * pp.y);
+}
+
+// row-marching kernel: blockDim.x == Mt (<= 1024), grid = (chunks per lattice) * B,
+// each block marches over R rows of one chain.
+//   sampler/hmcsampler.cc:43-45 fused: force, p -= dt_p*dp, theta += dt_x*p
+template <bool DRIFT>
+__global__ void __launch_bounds__(1024)
+    leapfrog_rowmarch_kernel(SW sw, double dt_p, double dt_x, const double *__restrict__ x_in,
+                             double *__restrict__ x_out, double *__restrict__ p, int R,
+                             int chunks) {
+  extern __shared__ double sh[]; // [2][Mt] theta(.,.,1) | [2][Mt] sin P
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const int i = threadIdx.x;
+  const int ip = wrap_inc(i, Mt), im = wrap_dec(i, Mt);
+  const int chain = blockIdx.x / chunks, chunk = blockIdx.x - chain * chunks;
+  const int j0 = chunk * R;
+  const int j1 = min(j0 + R, Mx);
+  const size_t base = (size_t)chain * Mt * Mx;
+  const double2 *xin = reinterpret_cast<const double2 *>(x_in) + base;
+  double2 *xout = reinterpret_cast<double2 *>(x_out) + base;
+  double2 *pp = reinterpret_cast<double2 *>(p) + base;
+  double *sh_t1 = sh, *sh_s = sh + 2 * Mt;
+  const double beta = sw.beta;
+
+  // prologue: sin P(i, j0-1) and P(i, j0)
+  const int jm = wrap_dec(j0, Mx);
+  double2 prev = xin[(size_t)jm * Mt + i];
+  double2 cur = xin[(size_t)j0 * Mt + i];
+  double2 nxt = xin[(size_t)wrap_inc(j0, Mx) * Mt + i];
+  sh_t1[i] = prev.y;
+  sh_t1[Mt + i] = cur.y;
+  __syncthreads();
+  double s_prev = sin(prev.x + sh_t1[ip] - cur.x - prev.y);
+  double P_cur = cur.x + sh_t1[Mt + ip] - nxt.x - cur.y;
+  __syncthreads();
+  int b = 0;
+  for (int j = j0; j < j1; ++j) {
+    // prefetch row j+2 (theta) and row j (p)
+    const int jp2 = wrap_inc(wrap_inc(j, Mx), Mx);
+    const double2 nxt2 = xin[(size_t)jp2 * Mt + i];
+    double2 pj = pp[(size_t)j * Mt + i];
+    const double s = sin(P_cur);
+    sh_s[b * Mt + i] = s;
+    sh_t1[b * Mt + i] = nxt.y;
+    __syncthreads();
+    const double s_im = sh_s[b * Mt + im];
+    const double t1p = sh_t1[b * Mt + ip];
+    const double F = beta * s;
+    pj.x -= dt_p * (F - beta * s_prev);
+    pj.y -= dt_p * (beta * s_im - F);
+    pp[(size_t)j * Mt + i] = pj;
+    if (DRIFT)
+      xout[(size_t)j * Mt + i] = make_double2(cur.x + dt_x * pj.x, cur.y + dt_x * pj.y);
+    // next row
+    P_cur = nxt.x + t1p - nxt2.x - nxt.y;
+    s_prev = s;
+    cur = nxt;
+    nxt = nxt2;
+    b ^= 1;
+  }
+}
+
+// --------------------------------------------------------------------- sweeps
+// colours: 0 {mu=0, j even}, 1 {mu=0, j odd}, 2 {mu=1, i even}, 3 {mu=1, i odd}
+template <bool HEATBATH>
+__global__ void sweep_colour_kernel(SW sw, int colour, double *x, int B, uint32_t chain0,
+                                    uint64_t seed, uint64_t draw) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const long long nhalf = (long long)Mt * Mx / 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nhalf * B)
+    return;
+  const long long chain = t / nhalf;
+  const int r = (int)(t - chain * nhalf);
+  int i, j, mu;
+  if (colour < 2) {
+    mu = 0;
+    const int j2 = r / Mt;
+    i = r - j2 * Mt;
+    j = 2 * j2 + colour;
+  } else {
+    mu = 1;
+    const int Mth = Mt / 2;
+    j = r / Mth;
+    i = 2 * (r - j * Mth) + (colour - 2);
+  }
+  double *xc = x + chain * 2 * (long long)Mt * Mx;
+  double theta_p, theta_m;
+  staple_angles(xc, Mt, Mx, i, j, mu, theta_p, theta_m);
+  const size_t ell = 2 * ((size_t)Mt * j + i) + mu;
+  if (HEATBATH) { // qft/quenchedschwingeraction.cc:46-54
+    Rng rg = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, (uint32_t)ell);
+    xc[ell] = expcos_draw(rg, sw.beta, theta_p, theta_m);
+  } else { // qft/quenchedschwingeraction.cc:57-65
+    xc[ell] = mod_2pi((theta_p + theta_m) - xc[ell]);
+  }
+}
+
+// ------------------------------------------------------- prolong / restrict
+// qft/quenchedschwingeraction.cc:92-147; one thread per coarse site
+__global__ void prolong_kernel(SW sw, int ctype, const double *xc_all, double *x_all, int B) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const int Mtc = (ctype == MLMCPI_COARSEN_SPATIAL) ? Mt : Mt / 2;
+  const int Mxc = (ctype == MLMCPI_COARSEN_TEMPORAL) ? Mx : Mx / 2;
+  const long long nc = (long long)Mtc * Mxc;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * B)
+    return;
+  const long long chain = t / nc;
+  const int s = (int)(t - chain * nc);
+  const int j = s / Mtc, i = s - j * Mtc;
+  const double2 c = reinterpret_cast<const double2 *>(xc_all)[t];
+  double *x = x_all + chain * 2 * (long long)Mt * Mx;
+  if (ctype == MLMCPI_COARSEN_BOTH) {
+    TH(x, 2 * i, 2 * j, 0) = 0.5 * c.x;
+    TH(x, 2 * i + 1, 2 * j, 0) = 0.5 * c.x;
+    TH(x, 2 * i, 2 * j, 1) = 0.5 * c.y;
+    TH(x, 2 * i, 2 * j + 1, 1) = 0.5 * c.y;
+  } else if (ctype == MLMCPI_COARSEN_TEMPORAL) {
+    TH(x, 2 * i, j, 0) = 0.5 * c.x;
+    TH(x, 2 * i + 1, j, 0) = 0.5 * c.x;
+    TH(x, 2 * i, j, 1) = c.y;
+  } else {
+    TH(x, i, 2 * j, 0) = c.x;
+    TH(x, i, 2 * j, 1) = 0.5 * c.y;
+    TH(x, i, 2 * j + 1, 1) = 0.5 * c.y;
+  }
+}
+
+// qft/quenchedschwingeraction.cc:150-195
+__global__ void restrict_kernel(SW sw, int ctype, const double *xf_all, double *xc_all, int B) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const int Mtc = (ctype == MLMCPI_COARSEN_SPATIAL) ? Mt : Mt / 2;
+  const int Mxc = (ctype == MLMCPI_COARSEN_TEMPORAL) ? Mx : Mx / 2;
+  const long long nc = (long long)Mtc * Mxc;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * B)
+    return;
+  const long long chain = t / nc;
+  const int s = (int)(t - chain * nc);
+  const int j = s / Mtc, i = s - j * Mtc;
+  const double *x = xf_all + chain * 2 * (long long)Mt * Mx;
+  double2 c;
+  if (ctype == MLMCPI_COARSEN_BOTH) {
+    c.x = mod_2pi(TH(x, 2 * i, 2 * j, 0) + TH(x, 2 * i + 1, 2 * j, 0));
+    c.y = mod_2pi(TH(x, 2 * i, 2 * j, 1) + TH(x, 2 * i, 2 * j + 1, 1));
+  } else if (ctype == MLMCPI_COARSEN_TEMPORAL) {
+    c.x = mod_2pi(TH(x, 2 * i, j, 0) + TH(x, 2 * i + 1, j, 0));
+    c.y = mod_2pi(TH(x, 2 * i, j, 1));
+  } else {
+    c.x = mod_2pi(TH(x, i, 2 * j, 0));
+    c.y = mod_2pi(TH(x, i, 2 * j, 1) + TH(x, i, 2 * j + 1, 1));
+  }
+  reinterpret_cast<double2 *>(xc_all)[t] = c;
+}
+
+// -------------------------------------------------------------------- fill-in
+// CoarsenBoth, qft/quenchedschwingerconditionedfineaction.cc:7-78.
+// STEP 1 (:14-31), in place, one thread per coarse cell
+__global__ void fill_both_step1_kernel(SW sw, double *x_all, int B, uint32_t chain0, uint64_t seed,
+                                       uint64_t draw) {
+  const int Mt = sw.Mt, Mx = sw.Mx, Mtc = Mt / 2, Mxc = Mx / 2;
+  const long long nc = (long long)Mtc * Mxc;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * B)
+    return;
+  const long long chain = t / nc;
+  const int cell = (int)(t - chain * nc);
+  const int j = cell / Mtc, i = cell - j * Mtc;
+  double *x = x_all + chain * 2 * (long long)Mt * Mx;
+  Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, chain0 + (uint32_t)chain, cell);
+  double dth_s;
+  const double dth_t = rng_angle2(r, dth_s);
+  TH(x, 2 * i, 2 * j, 0) = mod_2pi(TH(x, 2 * i, 2 * j, 0) + dth_t);
+  TH(x, 2 * i + 1, 2 * j, 0) = mod_2pi(TH(x, 2 * i + 1, 2 * j, 0) - dth_t);
+  TH(x, 2 * i, 2 * j, 1) = mod_2pi(TH(x, 2 * i, 2 * j, 1) + dth_s);
+  TH(x, 2 * i, 2 * j + 1, 1) = mod_2pi(TH(x, 2 * i, 2 * j + 1, 1) - dth_s);
+}
+
+// the interior of one coarse cell given its 4 own and 4 neighbouring perimeter
+// links: STEP 2 (:33-61) and STEP 3 (:63-77)
+struct CellLinks {
+  double A0, A1, B0, B1; // own perimeter: (2i,2j,0) (2i+1,2j,0) (2i,2j,1) (2i,2j+1,1)
+  double R0, R1;         // cell (i+1,j): (2i+2,2j,1) (2i+2,2j+1,1)
+  double T0, T1;         // cell (i,j+1): (2i,2j+2,0) (2i+1,2j+2,0)
+  double V0, V1, H0, H1; // interior: (2i+1,2j,1) (2i+1,2j+1,1) (2i,2j+1,0) (2i+1,2j+1,0)
+};
+
+template <bool APPROX>
+__device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double beta,
+                                                   const BesselProductConst &bp, uint64_t seed,
+                                                   uint64_t draw, uint32_t gchain, int Mt, int i,
+                                                   int j, int cell) {
+  {
+    const double theta_p = mod_2pi(c.A1 + c.R0 + c.R1 - c.T1);
+    const double theta_m = mod_2pi(c.B0 + c.B1 + c.T0 - c.A0);
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL2, draw, gchain, cell);
+    double unused;
+    const double dtheta = rng_angle2(r, unused);
+    const double theta_tilde = APPROX ? approxbessel_draw(r, beta, theta_p, theta_m)
+                                      : besselproduct_draw(r, bp, theta_p, theta_m);
+    c.V0 = mod_2pi(0.5 * theta_tilde + dtheta);
+    c.V1 = mod_2pi(0.5 * theta_tilde - dtheta);
+  }
+  {
+    const double theta_p = mod_2pi(c.A0 + c.V0 - c.B0);
+    const double theta_m = mod_2pi(c.B1 + c.T0 - c.V1);
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i);
+    c.H0 = expcos_draw(r, beta, theta_p, theta_m);
+  }
+  {
+    const double theta_p = mod_2pi(c.A1 + c.R0 - c.V0);
+    const double theta_m = mod_2pi(c.V1 + c.T1 - c.R1);
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i + 1);
+    c.H1 = expcos_draw(r, beta, theta_p, theta_m);
+  }
+}
+
+// STEP 2+3 in place (perimeter links already redistributed by step 1)
+template <bool APPROX>
+__global__ void fill_both_step23_kernel(SW sw, BesselProductConst bp, double *x_all, int B,
+                                        uint32_t chain0, uint64_t seed, uint64_t draw) {
+  const int Mt = sw.Mt, Mx = sw.Mx, Mtc = Mt / 2, Mxc = Mx / 2;
+  const long long nc = (long long)Mtc * Mxc;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * B)
+    return;
+  const long long chain = t / nc;
+  const int cell = (int)(t - chain * nc);
+  const int j = cell / Mtc, i = cell - j * Mtc;
+  double *x = x_all + chain * 2 * (long long)Mt * Mx;
+  const int i2 = wrap_inc(2 * i + 1, Mt), j2 = wrap_inc(2 * j + 1, Mx); // 2i+2, 2j+2 (periodic)
+  CellLinks c;
+  c.A0 = TH(x, 2 * i, 2 * j, 0);
+  c.A1 = TH(x, 2 * i + 1, 2 * j, 0);
+  c.B0 = TH(x, 2 * i, 2 * j, 1);
+  c.B1 = TH(x, 2 * i, 2 * j + 1, 1);
+  c.R0 = TH(x, i2, 2 * j, 1);
+  c.R1 = TH(x, i2, 2 * j + 1, 1);
+  c.T0 = TH(x, 2 * i, j2, 0);
+  c.T1 = TH(x, 2 * i + 1, j2, 0);
+  fill_cell_interior<APPROX>(c, sw.beta, bp, seed, draw, chain0 + (uint32_t)chain, Mt, i, j, cell);
+  TH(x, 2 * i + 1, 2 * j, 1) = c.V0;
+  TH(x, 2 * i + 1, 2 * j + 1, 1) = c.V1;
+  TH(x, 2 * i, 2 * j + 1, 0) = c.H0;
+  TH(x, 2 * i + 1, 2 * j + 1, 0) = c.H1;
+}
+
+// prolongation + all three steps in ONE pass from the coarse state: the thread of
+// cell (i,j) regenerates the step-1 variates of cells (i+1,j), (i,j+1) from their
+// Philox counters instead of waiting for them (counter-based RNG makes the three
+// phases of the reference embarrassingly parallel).  80 B of HBM traffic per cell.
+template <bool APPROX>
+__global__ void prolong_fill_both_kernel(SW sw, BesselProductConst bp, const double *xc_all,
+                                         double *x_all, int B, uint32_t chain0, uint64_t seed,
+                                         uint64_t draw) {
+  const int Mt = sw.Mt, Mx = sw.Mx, Mtc = Mt / 2, Mxc = Mx / 2;
+  const long long nc = (long long)Mtc * Mxc;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * B)
+    return;
+  const long long chain = t / nc;
+  const int cell = (int)(t - chain * nc);
+  const int j = cell / Mtc, i = cell - j * Mtc;
+  const uint32_t gchain = chain0 + (uint32_t)chain;
+  const double2 *xc = reinterpret_cast<const double2 *>(xc_all) + chain * nc;
+  double *x = x_all + chain * 2 * (long long)Mt * Mx;
+  const int ipc = wrap_inc(i, Mtc), jpc = wrap_inc(j, Mxc);
+  const int cell_r = j * Mtc + ipc, cell_t = jpc * Mtc + i;
+  const double2 own = xc[cell];
+  const double cr = xc[cell_r].y, ct = xc[cell_t].x;
+  CellLinks c;
+  {
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell);
+    double dth_s;
+    const double dth_t = rng_angle2(r, dth_s);
+    c.A0 = mod_2pi(0.5 * own.x + dth_t);
+    c.A1 = mod_2pi(0.5 * own.x - dth_t);
+    c.B0 = mod_2pi(0.5 * own.y + dth_s);
+    c.B1 = mod_2pi(0.5 * own.y - dth_s);
+  }
+  {
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell_r);
+    double dth_s;
+    (void)rng_angle2(r, dth_s);
+    c.R0 = mod_2pi(0.5 * cr + dth_s);
+    c.R1 = mod_2pi(0.5 * cr - dth_s);
+  }
+  {
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell_t);
+    double dth_s;
+    const double dth_t = rng_angle2(r, dth_s);
+    c.T0 = mod_2pi(0.5 * ct + dth_t);
+    c.T1 = mod_2pi(0.5 * ct - dth_t);
+  }
+  fill_cell_interior<APPROX>(c, sw.beta, bp, seed, draw, gchain, Mt, i, j, cell);
+  // rows 2j and 2j+1, sites 2i and 2i+1: four aligned double2 stores
+  double2 *xs = reinterpret_cast<double2 *>(x);
+  xs[(size_t)Mt * (2 * j) + 2 * i] = make_double2(c.A0, c.B0);
+  xs[(size_t)Mt * (2 * j) + 2 * i + 1] = make_double2(c.A1, c.V0);
+  xs[(size_t)Mt * (2 * j + 1) + 2 * i] = make_double2(c.H0, c.B1);
+  xs[(size_t)Mt * (2 * j + 1) + 2 * i + 1] = make_double2(c.H1, c.V1);
+}
+
+// semi-coarsening, qft/quenchedschwingerconditionedfineaction.cc:136-209.
+// phase 0: uniform redistribution of the coarsened-direction pair; phase 1: ExpCos
+// draw of the new transverse link.  One thread per coarse site.
+__global__ void fill_semi_kernel(SW sw, int ctype, int phase, double *x_all, int B, uint32_t chain0,
+                                 uint64_t seed, uint64_t draw) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const bool temporal = (ctype == MLMCPI_COARSEN_TEMPORAL);
+  const int Mtc = temporal ? Mt / 2 : Mt, Mxc = temporal ? Mx : Mx / 2;
+  const long long nc = (long long)Mtc * Mxc;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * B)
+    return;
+  const long long chain = t / nc;
+  const int cell = (int)(t - chain * nc);
+  const int j = cell / Mtc, i = cell - j * Mtc;
+  const uint32_t gchain = chain0 + (uint32_t)chain;
+  double *x = x_all + chain * 2 * (long long)Mt * Mx;
+  if (phase == 0) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell);
+    double unused;
+    const double dtheta = rng_angle2(r, unused);
+    if (temporal) {
+      TH(x, 2 * i, j, 0) = mod_2pi(TH(x, 2 * i, j, 0) + dtheta);
+      TH(x, 2 * i + 1, j, 0) = mod_2pi(TH(x, 2 * i + 1, j, 0) - dtheta);
+    } else {
+      TH(x, i, 2 * j, 1) = mod_2pi(TH(x, i, 2 * j, 1) + dtheta);
+      TH(x, i, 2 * j + 1, 1) = mod_2pi(TH(x, i, 2 * j + 1, 1) - dtheta);
+    }
+  } else {
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, cell);
+    if (temporal) {
+      const int jp = wrap_inc(j, Mx), i2 = wrap_inc(2 * i + 1, Mt);
+      const double theta_p = mod_2pi(TH(x, 2 * i, j, 1) + TH(x, 2 * i, jp, 0) - TH(x, 2 * i, j, 0));
+      const double theta_m =
+          mod_2pi(TH(x, 2 * i + 1, j, 0) + TH(x, i2, j, 1) - TH(x, 2 * i + 1, jp, 0));
+      TH(x, 2 * i + 1, j, 1) = expcos_draw(r, sw.beta, theta_p, theta_m);
+    } else {
+      const int ip = wrap_inc(i, Mt), j2 = wrap_inc(2 * j + 1, Mx);
+      const double theta_p = mod_2pi(TH(x, i, 2 * j, 0) + TH(x, ip, 2 * j, 1) - TH(x, i, 2 * j, 1));
+      const double theta_m =
+          mod_2pi(TH(x, i, 2 * j + 1, 1) + TH(x, i, j2, 0) - TH(x, ip, 2 * j + 1, 1));
+      TH(x, i, 2 * j + 1, 0) = expcos_draw(r, sw.beta, theta_p, theta_m);
+    }
+  }
+}
+
+// ------------------------------------------------------- conditioned actions
+// CoarsenBoth, beta <= 8: qft/quenchedschwingerconditionedfineaction.cc:219-250
+struct CondBothBesselF {
+  SW sw;
+  BesselProductConst bp;
+  const double *x_all;
+  __device__ void operator()(int chain, long long cell, double acc[1]) const {
+    const int Mt = sw.Mt, Mx = sw.Mx, Mtc = Mt / 2;
+    const int j = (int)(cell / Mtc), i = (int)(cell - (long long)j * Mtc);
+    const double *x = x_all + (size_t)chain * 2 * Mt * Mx;
+    const int i2 = wrap_inc(2 * i + 1, Mt), j2 = wrap_inc(2 * j + 1, Mx);
+    const double phi_12 = +TH(x, 2 * i, 2 * j + 1, 1) + TH(x, 2 * i, j2, 0);
+    const double phi_23 = +TH(x, 2 * i + 1, j2, 0) - TH(x, i2, 2 * j + 1, 1);
+    const double phi_34 = -TH(x, 2 * i + 1, 2 * j, 0) - TH(x, i2, 2 * j, 1);
+    const double phi_41 = -TH(x, 2 * i, 2 * j, 0) + TH(x, 2 * i, 2 * j, 1);
+    const double theta_1 = +TH(x, 2 * i, 2 * j + 1, 0);
+    const double theta_2 = -TH(x, 2 * i + 1, 2 * j + 1, 1);
+    const double theta_3 = -TH(x, 2 * i + 1, 2 * j + 1, 0);
+    const double theta_4 = +TH(x, 2 * i + 1, 2 * j, 1);
+    const double Phi = phi_12 + phi_23 + phi_34 + phi_41;
+    double S = -sw.beta * (cos(theta_1 - theta_2 - phi_12) + cos(theta_2 - theta_3 - phi_23) +
+                           cos(theta_3 - theta_4 - phi_34) + cos(theta_4 - theta_1 - phi_41));
+    S -= log(besselproduct_Znorm_inv_rescaled(bp, Phi));
+    acc[0] += S;
+  }
+};
+
+// one ExpCos term of the horizontal interior link (i, 2j+1, 0): :270-287 / :356-372
+__device__ __forceinline__ double cond_expcos_term_h(const double *x, int Mt, int Mx, double beta,
+                                                     int i, int j) {
+  const int ip = wrap_inc(i, Mt), j2 = wrap_inc(2 * j + 1, Mx);
+  const double phi_p = mod_2pi(-TH(x, i, 2 * j, 1) + TH(x, i, 2 * j, 0) + TH(x, ip, 2 * j, 1));
+  const double phi_m = mod_2pi(+TH(x, i, 2 * j + 1, 1) + TH(x, i, j2, 0) - TH(x, ip, 2 * j + 1, 1));
+  const double theta = mod_2pi(+TH(x, i, 2 * j + 1, 0));
+  return -log(expcos_pdf(beta, theta, phi_p, phi_m));
+}
+
+// CoarsenBoth, beta > 8: :251-288
+struct CondBothApproxF {
+  SW sw;
+  const double *x_all;
+  __device__ void operator()(int chain, long long cell, double acc[1]) const {
+    const int Mt = sw.Mt, Mx = sw.Mx, Mtc = Mt / 2;
+    const int j = (int)(cell / Mtc), i = (int)(cell - (long long)j * Mtc);
+    const double *x = x_all + (size_t)chain * 2 * Mt * Mx;
+    const int i2 = wrap_inc(2 * i + 1, Mt), j2 = wrap_inc(2 * j + 1, Mx);
+    const double phi_p = mod_2pi(+TH(x, 2 * i + 1, 2 * j, 0) + TH(x, i2, 2 * j, 1) +
+                                 TH(x, i2, 2 * j + 1, 1) - TH(x, 2 * i + 1, j2, 0));
+    const double phi_m = mod_2pi(-TH(x, 2 * i, 2 * j, 0) + TH(x, 2 * i, 2 * j, 1) +
+                                 TH(x, 2 * i, 2 * j + 1, 1) + TH(x, 2 * i, j2, 0));
+    const double theta = mod_2pi(+TH(x, 2 * i + 1, 2 * j, 1) + TH(x, 2 * i + 1, 2 * j + 1, 1));
+    double S = -log(approxbessel_pdf(sw.beta, theta, phi_p, phi_m));
+    S += cond_expcos_term_h(x, Mt, Mx, sw.beta, 2 * i, j);
+    S += cond_expcos_term_h(x, Mt, Mx, sw.beta, 2 * i + 1, j);
+    acc[0] += S;
+  }
+};
+
+// semi-coarsening: :329-379
+struct CondSemiF {
+  SW sw;
+  int ctype;
+  const double *x_all;
+  __device__ void operator()(int chain, long long cell, double acc[1]) const {
+    const int Mt = sw.Mt, Mx = sw.Mx;
+    const double *x = x_all + (size_t)chain * 2 * Mt * Mx;
+    if (ctype == MLMCPI_COARSEN_TEMPORAL) {
+      const int Mtc = Mt / 2;
+      const int j = (int)(cell / Mtc), i = (int)(cell - (long long)j * Mtc);
+      const int jp = wrap_inc(j, Mx), i2 = wrap_inc(2 * i + 1, Mt);
+      const double phi_p = mod_2pi(-TH(x, 2 * i, j, 0) + TH(x, 2 * i, j, 1) + TH(x, 2 * i, jp, 0));
+      const double phi_m =
+          mod_2pi(+TH(x, 2 * i + 1, j, 0) + TH(x, i2, j, 1) - TH(x, 2 * i + 1, jp, 0));
+      const double theta = mod_2pi(+TH(x, 2 * i + 1, j, 1));
+      acc[0] += -log(expcos_pdf(sw.beta, theta, phi_p, phi_m));
+    } else {
+      const int j = (int)(cell / Mt), i = (int)(cell - (long long)j * Mt);
+      acc[0] += cond_expcos_term_h(x, Mt, Mx, sw.beta, i, j);
+    }
+  }
+};
+
+int check_even(mlmcpi_ctx *ctx, const mlmcpi_model *m) {
+  const int c = m->coarsening;
+  if ((c == MLMCPI_COARSEN_BOTH && (m->Mt_lat % 2 || m->Mx_lat % 2)) ||
+      (c == MLMCPI_COARSEN_TEMPORAL && m->Mt_lat % 2) ||
+      (c == MLMCPI_COARSEN_SPATIAL && m->Mx_lat % 2))
+    return ctx_fail(ctx, MLMCPI_EINVAL, "lattice cannot be coarsened (odd extent)");
+  if (c != MLMCPI_COARSEN_BOTH && c != MLMCPI_COARSEN_TEMPORAL && c != MLMCPI_COARSEN_SPATIAL)
+    return ctx_fail(ctx, MLMCPI_EINVAL,
+                    "invalid coarsening for quenched Schwinger model (both/temporal/spatial)");
+  return 0;
+}
+
+long long n_coarse_sites(const mlmcpi_model *m) {
+  const int Mtc = (m->coarsening == MLMCPI_COARSEN_SPATIAL) ? m->Mt_lat : m->Mt_lat / 2;
+  const int Mxc = (m->coarsening == MLMCPI_COARSEN_TEMPORAL) ? m->Mx_lat : m->Mx_lat / 2;
+  return (long long)Mtc * Mxc;
+}
+
+// one fused leapfrog step on all chains
+int leapfrog_step(mlmcpi_ctx *ctx, const SW &sw, double dt_p, double dt_x, bool drift,
+                  const double *x_in, double *x_out, double *p, int B) {
+  const long long nsite = (long long)sw.Mt * sw.Mx;
+  if (sw.Mt <= 1024 && sw.Mt % 32 == 0 && sw.Mx >= 3) {
+    // rows per block: enough blocks for >= ~6 waves, at least 8 rows (prologue = 1 row)
+    int R = 32;
+    while (R > 8 && (long long)cdiv(sw.Mx, R) * B < (long long)ctx->n_sm * 12)
+      R >>= 1;
+    const int chunks = cdiv(sw.Mx, R);
+    const size_t smem = (size_t)4 * sw.Mt * sizeof(double);
+    if (drift)
+      leapfrog_rowmarch_kernel<true><<<chunks * B, sw.Mt, smem, ctx->stream>>>(
+          sw, dt_p, dt_x, x_in, x_out, p, R, chunks);
+    else
+      leapfrog_rowmarch_kernel<false><<<chunks * B, sw.Mt, smem, ctx->stream>>>(
+          sw, dt_p, dt_x, x_in, x_out, p, R, chunks);
+    MLMCPI_LAUNCHED("schwinger::leapfrog_rowmarch");
+  } else {
+    leapfrog_naive_kernel<<<cdiv(nsite * B, 256), 256, 0, ctx->stream>>>(
+        sw, dt_p, dt_x, x_in, drift ? x_out : nullptr, p, B);
+    MLMCPI_LAUNCHED("schwinger::leapfrog_naive");
+  }
+  return 0;
+}
+
+// trajectory of sampler/hmcsampler.cc:31-46.  x_first: state read by the first step;
+// bufA/bufB: ping-pong trial buffers; returns the buffer holding the final state.
+int trajectory(mlmcpi_ctx *ctx, const SW &sw, int nt, double dt, const double *x_first,
+               double *bufA, double *bufB, double *p, int B, double **x_final) {
+  const double *in = x_first;
+  double *out = bufA;
+  double *last = nullptr;
+  prof_begin(ctx);
+  for (int k = 0; k <= nt; ++k) {
+    const double dt_p = (k == 0 || k == nt) ? 0.5 * dt : dt;
+    const bool drift = (k != nt);
+    int rc = leapfrog_step(ctx, sw, dt_p, drift ? dt : 0.0, drift, in, out, p, B);
+    if (rc)
+      return rc;
+    if (drift) {
+      last = out;
+      in = out;
+      out = (out == bufA) ? bufB : bufA;
+    }
+  }
+  // algorithmic bytes: R theta, R p, W theta, W p per site-step; the final kick writes no theta
+  const double site_bytes = 16.0 * (double)sw.Mt * sw.Mx * B;
+  prof_end(ctx, (uint64_t)nt + 1, site_bytes * (4.0 * nt + 3.0));
+  *x_final = last; // nullptr when nt == 0 (state unchanged)
+  return 0;
+}
+
+} // namespace
+
+namespace schwinger {
+
+int init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,
+               uint64_t draw) {
+  SW sw = make_sw(m);
+  const long long n = (long long)sw.Mt * sw.Mx * B;
+  init_state_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, x, B, chain0, ctx->seed, draw);
+  MLMCPI_LAUNCHED("schwinger::init_state");
+  return 0;
+}
+
+int action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, double *S) {
+  SW sw = make_sw(m);
+  return site_reduce<1>(ctx, "schwinger::action", ActionF{sw, x}, (long long)sw.Mt * sw.Mx, B,
+                        EPI_SCALE, sw.beta, 0.0, S, nullptr);
+}
+
+int force(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, double *f, int B) {
+  SW sw = make_sw(m);
+  const long long n = (long long)sw.Mt * sw.Mx * B;
+  force_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, x, f, B);
+  MLMCPI_LAUNCHED("schwinger::force");
+  return 0;
+}
+
+int leapfrog(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *x, double *p,
+             int B) {
+  SW sw = make_sw(m);
+  const size_t n = (size_t)2 * sw.Mt * sw.Mx * B;
+  double *bufA = ctx_work(ctx, 1, n), *bufB = ctx_work(ctx, 2, n);
+  if (!bufA || !bufB)
+    return MLMCPI_ENOMEM;
+  double *fin = nullptr;
+  int rc = trajectory(ctx, sw, nt, dt, x, bufA, bufB, p, B, &fin);
+  if (rc)
+    return rc;
+  if (fin)
+    MLMCPI_CUDA(cudaMemcpyAsync(x, fin, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+int hmc_momentum(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *p, int B, uint32_t chain0,
+                 uint64_t draw) {
+  SW sw = make_sw(m);
+  const long long n = (long long)sw.Mt * sw.Mx * B;
+  momentum_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, p, B, chain0, ctx->seed, draw);
+  MLMCPI_LAUNCHED("schwinger::hmc_momentum");
+  return 0;
+}
+
+// HMCSampler::single_step, sampler/hmcsampler.cc:22-69
+int hmc_step(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *x, int B,
+             uint32_t chain0, uint64_t draw, int32_t *accept, double *diag) {
+  SW sw = make_sw(m);
+  const size_t nd = (size_t)2 * sw.Mt * sw.Mx;
+  const size_t n = nd * B;
+  double *p = ctx_work(ctx, 0, n), *bufA = ctx_work(ctx, 1, n), *bufB = ctx_work(ctx, 2, n);
+  double *red = ctx_work(ctx, 3, (size_t)5 * B); // S_cur S_trial T_cur T_trial | accept flags
+  if (!p || !bufA || !bufB || !red)
+    return MLMCPI_ENOMEM;
+  double *S_cur = red, *S_trial = red + B, *T_cur = red + 2 * B, *T_trial = red + 3 * B;
+  int32_t *acc = accept ? accept : reinterpret_cast<int32_t *>(red + 4 * B);
+  int rc;
+  if ((rc = hmc_momentum(ctx, m, p, B, chain0, draw)))
+    return rc;
+  if ((rc = launch_half_sqnorm(ctx, p, nd, B, T_cur)))
+    return rc;
+  if ((rc = action(ctx, m, x, B, S_cur)))
+    return rc;
+  double *fin = nullptr;
+  if ((rc = trajectory(ctx, sw, nt, dt, x, bufA, bufB, p, B, &fin)))
+    return rc;
+  if ((rc = launch_half_sqnorm(ctx, p, nd, B, T_trial)))
+    return rc;
+  if ((rc = action(ctx, m, fin ? fin : x, B, S_trial)))
+    return rc;
+  if ((rc = launch_hmc_accept(ctx, B, chain0, draw, S_cur, S_trial, T_cur, T_trial, acc, diag)))
+    return rc;
+  if (fin)
+    if ((rc = launch_masked_copy(ctx, x, fin, nd, B, acc)))
+      return rc;
+  return 0;
+}
+
+static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool heatbath,
+                 uint32_t chain0, uint64_t draw) {
+  if (m->Mt_lat % 2 || m->Mx_lat % 2)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need even lattice extents");
+  SW sw = make_sw(m);
+  const long long n = (long long)sw.Mt * sw.Mx / 2 * B;
+  for (int colour = 0; colour < 4; ++colour) {
+    if (heatbath)
+      sweep_colour_kernel<true><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sw, colour, x, B, chain0,
+                                                                      ctx->seed, draw);
+    else
+      sweep_colour_kernel<false><<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, colour, x, B, 0, 0, 0);
+    MLMCPI_LAUNCHED("schwinger::sweep_colour");
+  }
+  return 0;
+}
+
+int overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B) {
+  return sweep(ctx, m, x, B, false, 0, 0);
+}
+int heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,
+                   uint64_t draw) {
+  return sweep(ctx, m, x, B, true, chain0, draw);
+}
+
+int prolong(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B) {
+  int rc = check_even(ctx, m);
+  if (rc)
+    return rc;
+  SW sw = make_sw(m);
+  const long long n = n_coarse_sites(m) * B;
+  prolong_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, m->coarsening, xc, x, B);
+  MLMCPI_LAUNCHED("schwinger::prolong");
+  return 0;
+}
+
+int restrict_(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xf, double *xc, int B) {
+  int rc = check_even(ctx, m);
+  if (rc)
+    return rc;
+  SW sw = make_sw(m);
+  const long long n = n_coarse_sites(m) * B;
+  restrict_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, m->coarsening, xf, xc, B);
+  MLMCPI_LAUNCHED("schwinger::restrict");
+  return 0;
+}
+
+int fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0, uint64_t draw) {
+  int rc = check_even(ctx, m);
+  if (rc)
+    return rc;
+  SW sw = make_sw(m);
+  const long long n = n_coarse_sites(m) * B;
+  if (m->coarsening == MLMCPI_COARSEN_BOTH) {
+    fill_both_step1_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, x, B, chain0, ctx->seed, draw);
+    MLMCPI_LAUNCHED("schwinger::fill_step1");
+    BesselProductConst bp;
+    if (sw.beta > 8.0) { // quenchedschwingerconditionedfineaction.hh:39-45
+      bp.beta = sw.beta;
+      fill_both_step23_kernel<true><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sw, bp, x, B, chain0,
+                                                                          ctx->seed, draw);
+    } else {
+      besselproduct_setup(sw.beta, &bp);
+      fill_both_step23_kernel<false><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sw, bp, x, B, chain0,
+                                                                           ctx->seed, draw);
+    }
+    MLMCPI_LAUNCHED("schwinger::fill_step23");
+  } else {
+    for (int phase = 0; phase < 2; ++phase) {
+      fill_semi_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(sw, m->coarsening, phase, x, B, chain0,
+                                                             ctx->seed, draw);
+      MLMCPI_LAUNCHED("schwinger::fill_semi");
+    }
+  }
+  return 0;
+}
+
+int prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
+                 uint32_t chain0, uint64_t draw) {
+  int rc = check_even(ctx, m);
+  if (rc)
+    return rc;
+  if (m->coarsening != MLMCPI_COARSEN_BOTH) {
+    if ((rc = prolong(ctx, m, xc, x, B)))
+      return rc;
+    return fill(ctx, m, x, B, chain0, draw);
+  }
+  SW sw = make_sw(m);
+  const long long n = n_coarse_sites(m) * B;
+  BesselProductConst bp;
+  if (sw.beta > 8.0) {
+    bp.beta = sw.beta;
+    prolong_fill_both_kernel<true><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0,
+                                                                         ctx->seed, draw);
+  } else {
+    besselproduct_setup(sw.beta, &bp);
+    prolong_fill_both_kernel<false><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0,
+                                                                          ctx->seed, draw);
+  }
+  MLMCPI_LAUNCHED("schwinger::prolong_fill");
+  return 0;
+}
+
+int cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, double *S) {
+  int rc = check_even(ctx, m);
+  if (rc)
+    return rc;
+  SW sw = make_sw(m);
+  const long long n = n_coarse_sites(m);
+  if (m->coarsening == MLMCPI_COARSEN_BOTH) {
+    if (sw.beta > 8.0)
+      return site_reduce<1>(ctx, "schwinger::cond_action", CondBothApproxF{sw, x}, n, B, EPI_SCALE,
+                            1.0, 0.0, S, nullptr);
+    CondBothBesselF f;
+    f.sw = sw;
+    f.x_all = x;
+    besselproduct_setup(sw.beta, &f.bp);
+    return site_reduce<1>(ctx, "schwinger::cond_action", f, n, B, EPI_SCALE, 1.0, 0.0, S, nullptr);
+  }
+  return site_reduce<1>(ctx, "schwinger::cond_action", CondSemiF{sw, m->coarsening, x}, n, B,
+                        EPI_SCALE, 1.0, 0.0, S, nullptr);
+}
+
+int qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int which, const double *x, int B, double *out,
+        int64_t *Qint) {
+  SW sw = make_sw(m);
+  const long long n = (long long)sw.Mt * sw.Mx;
+  if (which == MLMCPI_QOI_SCHWINGER_CHI)
+    return site_reduce<2>(ctx, "schwinger::qoi_chi", ChiF{sw, x}, n, B, EPI_CHI,
+                          0.25 / (M_PI * M_PI), 0.0, out, Qint);
+  if (which == MLMCPI_QOI_AVG_PLAQUETTE)
+    return site_reduce<1>(ctx, "schwinger::qoi_plaq", PlaqF{sw, x}, n, B, EPI_SCALE,
+                          1.0 / ((double)sw.Mx * sw.Mt), 0.0, out, nullptr);
+  return ctx_fail(ctx, MLMCPI_EINVAL, "QoI not defined for the Schwinger model");
+}
+
+} // namespace schwinger

@@ -1,0 +1,542 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against
+(a) the golden vectors recorded from the reference's own translation units,
+(b) the C oracle on seeded random inputs (several chains per call), and
+(c) size-independent properties at the full BASELINE.json sizes.
+
+Tolerances (north_star): indexing / coarsening maps / topological charge bit-exact;
+action, force, QoI values <= 1e-12 relative (norm-wise for vectors); stochastic
+kernels are compared draw by draw with the oracle's restatement of the reference's
+sampling algorithms on the same Philox stream (angles compared modulo 2 pi)."""
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.util import load, qm_model, scalar, unhex
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+SEED = 0x5EED0001
+
+
+@pytest.fixture(scope="module")
+def mp():
+    import mlmcpathintegral_b200 as mp
+    return mp
+
+
+@pytest.fixture(scope="module")
+def ctx(mp):
+    c = mp.Context(0, seed=SEED)
+    yield c
+    c.close()
+
+
+def to_mp(mp, o):
+    """oracle model -> product model (same fields)"""
+    return mp.Model(model=o.model, M_lat=o.M_lat, Mt_lat=o.Mt_lat, Mx_lat=o.Mx_lat,
+                    rotated=o.rotated, coarsening=o.coarsening, a_lat=o.a_lat, T_final=o.T_final,
+                    m0=o.m0, mu2=o.mu2, lambda_=o.lambda_, x0=o.x0, beta=o.beta, gff_mu2=o.gff_mu2)
+
+
+def dev(ctx, a):
+    a = np.atleast_2d(np.asarray(a, dtype=np.float64))
+    return ctx.to_device(a)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def close(got, want, tol=TOL, what=""):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = max(float(np.max(np.abs(want))), 1e-300)
+    err = float(np.max(np.abs(got - want))) / scale
+    assert err <= tol, f"{what}: relative error {err:.3e} > {tol}"
+
+
+def ang_close(got, want, tol=1e-10, what="", max_bad=0):
+    d = np.asarray(got) - np.asarray(want)
+    d = d - 2 * np.pi * np.round(d / (2 * np.pi))
+    bad = int(np.sum(np.abs(d) > tol))
+    assert bad <= max_bad, f"{what}: {bad} entries differ by more than {tol} (max {np.max(np.abs(d)):.3e})"
+
+
+# ----------------------------------------------------------- golden fixtures
+
+
+@pytest.mark.parametrize("c", load("schwinger"), ids=lambda c: c["name"])
+def test_schwinger_golden(mp, ctx, c):
+    from tools.make_golden import angles
+    m = mp.schwinger(c["Mt"], c["Mx"], c["beta"], c["ctype"], 0)
+    x = unhex(c["x"])
+    xd = dev(ctx, x)
+    close(host(ctx.action(m, xd))[0], scalar(c["S"]), what="S")
+    close(host(ctx.force(m, xd))[0], unhex(c["force"]), what="force")
+    chi, Q = ctx.qoi(m, mp.QOI_SCHWINGER_CHI, xd, with_charge=True)
+    want_chi = scalar(c["qoi_chi"])
+    assert abs(host(chi)[0] - want_chi) <= TOL * max(want_chi, 1.0)
+    assert int(host(Q)[0]) ** 2 == int(round(want_chi * 4 * np.pi ** 2 / (2 * np.pi) ** 2))
+    close(host(ctx.qoi(m, mp.QOI_AVG_PLAQUETTE, xd))[0], scalar(c["qoi_plaq"]), what="plaq")
+    y = xd.clone()
+    ctx.overrelax_sweep(m, y)
+    ang_close(host(y)[0], unhex(c["overrelax_coloured"]), what="overrelax")
+    close(host(ctx.cond_action(m, xd))[0], scalar(c["cond_S"]), what="cond_S")
+    lf = c["leapfrog"]
+    y, p = xd.clone(), dev(ctx, unhex(c["p0"]))
+    ctx.leapfrog(m, lf["nt"], lf["dt"], y, p)
+    close(host(y)[0], unhex(lf["x"]), what="leapfrog x")
+    close(host(p)[0], unhex(lf["p"]), what="leapfrog p")
+    mc = mp.coarse_model(m, renorm=c["renorm"], level=0, ctype=c["ctype"])
+    xc = ctx.state(mc, 1)
+    ctx.restrict(m, xd, xc)
+    ang_close(host(xc)[0], unhex(c["restrict"]), tol=1e-14, what="restrict")
+    close(host(ctx.action(mc, xc))[0], scalar(c["coarse_S"]), what="coarse S")
+    y = xd.clone()
+    ctx.prolong(m, dev(ctx, angles(mp.sample_size(mc), 0.3)), y)
+    assert np.array_equal(host(y)[0], unhex(c["prolong"]))  # pure copies / halvings: exact
+    tl = c["twolevel"]
+    tp, pc = dev(ctx, unhex(tl["theta_prime"])), dev(ctx, unhex(tl["phi_coarse"]))
+    want = unhex(tl["deltas"])
+    got = [host(ctx.action(m, tp) - ctx.action(m, xd))[0],
+           host(ctx.action(mc, xc) - ctx.action(mc, pc))[0],
+           host(ctx.cond_action(m, xd) - ctx.cond_action(m, tp))[0]]
+    scale = max(abs(scalar(c["S"])), abs(scalar(c["cond_S"])), 1.0)
+    assert np.max(np.abs(np.array(got) - want)) <= TOL * scale
+
+
+@pytest.mark.parametrize("c", load("qm"), ids=lambda c: c["name"])
+def test_qm_golden(mp, ctx, c):
+    from tools.make_golden import noncompact
+    m = to_mp(mp, qm_model(po, c))
+    x = unhex(c["x"])
+    xd = dev(ctx, x)
+    rotor = c["kind"] == po.ROTOR
+    close(host(ctx.action(m, xd))[0], scalar(c["S"]), what="S")
+    close(host(ctx.force(m, xd))[0], unhex(c["force"]), what="force")
+    close(host(ctx.cond_action(m, xd))[0], scalar(c["cond_S"]), what="cond_S")
+    close(host(ctx.qoi(m, mp.QOI_X2, xd))[0], scalar(c["qoi_x2"]), what="x2")
+    if rotor:
+        chi, Q = ctx.qoi(m, mp.QOI_ROTOR_CHI, xd, with_charge=True)
+        want = scalar(c["qoi_chi"])
+        assert abs(host(chi)[0] - want) <= TOL * max(want, 1.0)
+        assert int(host(Q)[0]) ** 2 == int(round(want * 4 * np.pi ** 2 * m.T_final / (2 * np.pi) ** 2))
+        y = xd.clone()
+        ctx.overrelax_sweep(m, y)
+        ang_close(host(y)[0], unhex(c["overrelax_coloured"]), what="overrelax")
+    lf = c["leapfrog"]
+    y, p = xd.clone(), dev(ctx, unhex(c["p0"]))
+    ctx.leapfrog(m, lf["nt"], lf["dt"], y, p)
+    close(host(y)[0], unhex(lf["x"]), what="leapfrog x")
+    close(host(p)[0], unhex(lf["p"]), what="leapfrog p")
+    mc = mp.coarse_model(m, renorm=c["ip"][1])
+    xc = ctx.state(mc, 1)
+    ctx.restrict(m, xd, xc)
+    assert np.array_equal(host(xc)[0], unhex(c["restrict"]))
+    y = xd.clone()
+    ctx.prolong(m, dev(ctx, noncompact(len(x) // 2, 0.3)), y)
+    assert np.array_equal(host(y)[0], unhex(c["prolong"]))
+    close(host(ctx.action(mc, xc))[0], scalar(c["coarse_S"]), what="coarse S")
+
+
+@pytest.mark.parametrize("c", load("gff"), ids=lambda c: c["name"])
+def test_gff_golden(mp, ctx, c):
+    from tools.make_golden import noncompact
+    m = mp.gff(c["Mt"], c["Mx"], c["mass"], c["ctype"], 0)
+    xd = dev(ctx, unhex(c["x"]))
+    close(host(ctx.action(m, xd))[0], scalar(c["S"]), what="S")
+    close(host(ctx.force(m, xd))[0], unhex(c["force"]), what="force")
+    close(host(ctx.qoi(m, mp.QOI_PHI2, xd))[0], scalar(c["qoi_phi2"]), what="phi2")
+    lf = c["leapfrog"]
+    y, p = xd.clone(), dev(ctx, unhex(c["p0"]))
+    ctx.leapfrog(m, lf["nt"], lf["dt"], y, p)
+    close(host(y)[0], unhex(lf["x"]), what="leapfrog x")
+    close(host(p)[0], unhex(lf["p"]), what="leapfrog p")
+    mc = mp.coarse_model(m, level=0, ctype=c["ctype"])
+    xc = ctx.state(mc, 1)
+    ctx.restrict(m, xd, xc)
+    assert np.array_equal(host(xc)[0], unhex(c["restrict"]))
+    y = xd.clone()
+    ctx.prolong(m, dev(ctx, noncompact(mp.sample_size(mc), 0.3)), y)
+    assert np.array_equal(host(y)[0], unhex(c["prolong"]))
+    if c["ctype"] == po.ROTATE:
+        close(host(ctx.cond_action(m, xd))[0], scalar(c["cond_S"]), what="cond_S")
+        l1 = c["level1"]
+        mc.gff_mu2 = scalar(c["coarse_mu2"])
+        x1 = dev(ctx, unhex(l1["x"]))
+        close(host(ctx.force(mc, x1))[0], unhex(l1["force"]), what="level1 force")
+        close(host(ctx.cond_action(mc, x1))[0], scalar(l1["cond_S"]), what="level1 cond_S")
+        mcc = mp.coarse_model(mc, level=1, ctype=c["ctype"])
+        xcc = ctx.state(mcc, 1)
+        ctx.restrict(mc, x1, xcc)
+        assert np.array_equal(host(xcc)[0], unhex(l1["restrict"]))
+        y = x1.clone()
+        ctx.prolong(mc, dev(ctx, noncompact(mp.sample_size(mcc), 0.3)), y)
+        assert np.array_equal(host(y)[0], unhex(l1["prolong"]))
+
+
+# ------------------------------------------- oracle, seeded random inputs, B > 1
+
+MODELS = {
+    "ho32": lambda: po.ho(32),
+    "quartic64": lambda: po.quartic(64, 4.0, 1.0, 1.0, 1.0, 1.0),
+    "rotor256": lambda: po.rotor(256, 4.0, 0.25),
+    "rotor48": lambda: po.rotor(48, 4.0, 2.0),
+    "schw_both_b4_32": lambda: po.schwinger(32, 32, 4.0, po.BOTH),
+    "schw_both_b16_32x16": lambda: po.schwinger(32, 16, 16.0, po.BOTH),
+    "schw_both_12x20": lambda: po.schwinger(12, 20, 2.0, po.BOTH),
+    "schw_temporal": lambda: po.schwinger(16, 12, 5.0, po.TEMPORAL),
+    "schw_spatial": lambda: po.schwinger(12, 16, 5.0, po.SPATIAL),
+    "gff_rot16": lambda: po.gff(16, 16, 10.0, po.ROTATE, 0),
+    "gff_rot16_l1": lambda: po.gff(16, 16, 10.0, po.ROTATE, 1),
+}
+
+
+def random_state(o, rng, B, smooth=1.0):
+    n = po.oracle().sample_size(o)
+    if o.model in (po.ROTOR, po.SCHWINGER):
+        return rng.uniform(-np.pi * smooth, np.pi * smooth, (B, n))
+    return rng.normal(0.0, 0.7, (B, n))
+
+
+def coarse_of(orc, o):
+    if o.model == po.SCHWINGER:
+        return orc.coarse_model(o, 0, 0, o.coarsening)
+    if o.model == po.GFF:
+        return orc.coarse_model(o, 0, o.rotated, po.ROTATE)
+    return orc.coarse_model(o, 0, 0, 0, o.T_final)
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_deterministic_kernels_against_oracle(mp, ctx, orc, name):
+    o = MODELS[name]()
+    m = to_mp(mp, o)
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    B = 5
+    x = random_state(o, rng, B)
+    xd = dev(ctx, x)
+    S = host(ctx.action(m, xd))
+    close(S, [orc.action(o, x[b]) for b in range(B)], what="action")
+    F = host(ctx.force(m, xd))
+    close(F, [orc.force(o, x[b]) for b in range(B)], what="force")
+    p = rng.normal(size=x.shape)
+    y, pd = xd.clone(), dev(ctx, p)
+    ctx.leapfrog(m, 10, 0.02, y, pd)
+    want = [orc.leapfrog(o, 10, 0.02, x[b], p[b]) for b in range(B)]
+    close(host(y), [w[0] for w in want], tol=1e-11, what="leapfrog x")
+    close(host(pd), [w[1] for w in want], tol=1e-11, what="leapfrog p")
+    if o.model in (po.ROTOR, po.SCHWINGER, po.GFF):
+        y = xd.clone()
+        ctx.overrelax_sweep(m, y)
+        want = np.array([orc.overrelax_sweep(o, x[b], coloured=True) for b in range(B)])
+        if o.model == po.GFF:
+            close(host(y), want, what="overrelax")
+        else:
+            ang_close(host(y), want, what="overrelax")
+    oc = coarse_of(orc, o)
+    mc = to_mp(mp, oc)
+    xc = ctx.state(mc, B)
+    ctx.restrict(m, xd, xc)
+    want = np.array([orc.restrict(o, oc, x[b]) for b in range(B)])
+    ang_close(host(xc), want, tol=1e-14, what="restrict")
+    xcr = random_state(oc, rng, B)
+    y = xd.clone()
+    ctx.prolong(m, dev(ctx, xcr), y)
+    assert np.array_equal(host(y), np.array([orc.prolong(o, xcr[b], x[b]) for b in range(B)]))
+    xs = random_state(o, rng, B, smooth=0.3 if o.beta > 8 else 1.0)
+    close(host(ctx.cond_action(m, dev(ctx, xs))), [orc.cond_action(o, xs[b]) for b in range(B)],
+          tol=1e-11, what="cond_action")
+    qois = {po.HO: [po.QOI_X2], po.QUARTIC: [po.QOI_X2], po.ROTOR: [po.QOI_X2, po.QOI_ROTOR_CHI],
+            po.SCHWINGER: [po.QOI_SCHWINGER_CHI, po.QOI_AVG_PLAQUETTE], po.GFF: [po.QOI_PHI2]}[o.model]
+    for q in qois:
+        got, Q = ctx.qoi(m, q, xd, with_charge=True)
+        want = [orc.qoi(o, q, x[b]) for b in range(B)]
+        wv = np.array([w[0] for w in want])
+        assert np.max(np.abs(host(got) - wv)) <= 1e-11 * max(np.max(np.abs(wv)), 1.0)
+        if q in (po.QOI_ROTOR_CHI, po.QOI_SCHWINGER_CHI):
+            assert list(host(Q)) == [w[1] for w in want]  # integer topological charge: exact
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_stochastic_kernels_against_oracle(mp, ctx, orc, name):
+    o = MODELS[name]()
+    m = to_mp(mp, o)
+    rng = np.random.default_rng(zlib.crc32(name.encode()) + 1)
+    B, chain0, draw = 4, 7, (3 << 32) + 11
+    compact = o.model in (po.ROTOR, po.SCHWINGER)
+    cmp = ang_close if compact else (lambda a, b, tol=1e-10, what="", max_bad=0: close(a, b, tol, what))
+    # initial state and momenta
+    want = np.array([orc.init_state(o, SEED, draw, chain0 + b) for b in range(B)])
+    close(host(ctx.init_state(m, B, chain0, draw)), want, tol=1e-14, what="init_state") if np.any(want) \
+        else None
+    want = np.array([orc.hmc_momentum(o, SEED, draw, chain0 + b) for b in range(B)])
+    close(host(ctx.hmc_momentum(m, B, chain0, draw)), want, tol=1e-13, what="momentum")
+    # one HMC step (short trajectory so that rounding differences stay ~1e-13)
+    x = random_state(o, rng, B)
+    xd = dev(ctx, x)
+    acc, diag = ctx.hmc_step(m, 6, 0.03, xd, chain0, draw)
+    res = [orc.hmc_step(o, 6, 0.03, SEED, draw, chain0 + b, x[b]) for b in range(B)]
+    assert list(host(acc)) == [r[0] for r in res]
+    close(host(xd), [r[1] for r in res], tol=1e-11, what="hmc state")
+    want_diag = np.array([r[2] for r in res])
+    assert np.max(np.abs(host(diag) - want_diag)) <= 1e-10 * max(np.max(np.abs(want_diag[:, 1:])), 1.0)
+    # heat bath sweep
+    if o.model in (po.ROTOR, po.SCHWINGER, po.GFF):
+        x = random_state(o, rng, B)
+        xd = dev(ctx, x)
+        ctx.heatbath_sweep(m, xd, chain0, draw)
+        want = np.array([orc.heatbath_sweep(o, SEED, draw, chain0 + b, x[b]) for b in range(B)])
+        cmp(host(xd), want, tol=1e-9, what="heatbath")
+    # fill-in: in place, and fused with the prolongation
+    oc = coarse_of(orc, o)
+    mc = to_mp(mp, oc)
+    xc = random_state(oc, rng, B)
+    x0 = random_state(o, rng, B)
+    pro = np.array([orc.prolong(o, xc[b], x0[b]) for b in range(B)])
+    want = np.array([orc.fill(o, SEED, draw, chain0 + b, pro[b]) for b in range(B)])
+    xd = dev(ctx, pro)
+    ctx.fill(m, xd, chain0, draw)
+    cmp(host(xd), want, tol=1e-9, what="fill")
+    xd2 = dev(ctx, x0)
+    ctx.prolong_fill(m, dev(ctx, xc), xd2, chain0, draw)
+    cmp(host(xd2), want, tol=1e-9, what="prolong_fill")
+    # two-level Metropolis-Hastings step
+    xf = random_state(o, rng, B, smooth=0.3 if o.beta > 8 else 1.0)
+    xfd, xcd = dev(ctx, xf), dev(ctx, xc)
+    Sf, Sc = ctx.action(m, xfd), ctx.cond_action(m, xfd)
+    Sf0, Sc0 = host(Sf).copy(), host(Sc).copy()
+    acc, deltas = ctx.twolevel_step(m, mc, xcd, xfd, Sf, Sc, chain0, draw)
+    res = [orc.twolevel_step(o, oc, SEED, draw, chain0 + b, xc[b], xf[b], Sf0[b], Sc0[b])
+           for b in range(B)]
+    want_d = np.array([r[4] for r in res])
+    assert np.max(np.abs(host(deltas) - want_d)) <= 1e-9 * max(np.max(np.abs(want_d)), 1.0)
+    assert list(host(acc)) == [r[0] for r in res]
+    cmp(host(xfd), np.array([r[1] for r in res]), tol=1e-9, what="twolevel state")
+    close(host(Sf), [r[2] for r in res], tol=1e-10, what="cached S_f")
+
+
+# --------------------------------------------------- statistics accumulators
+
+
+def test_statistics_against_oracle(mp, ctx, orc):
+    rng = np.random.default_rng(5)
+    B, n, k_max = 6, 300, 10
+    q = np.zeros((n, B))
+    v = rng.normal(size=B)
+    for k in range(n):
+        v = 0.7 * v + rng.normal(size=B)
+        q[k] = v
+    st = mp.Statistics(ctx, k_max, B)
+    for k in range(n):
+        st.record(dev(ctx, q[k])[0])
+    packed = st.pack()
+    assert packed[0] == B and packed[1] == B * n
+    # single-chain restriction: chain b alone reproduces Statistics exactly
+    for b in range(B):
+        st1 = mp.Statistics(ctx, k_max, 1)
+        for k in range(n):
+            st1.record(dev(ctx, q[k, b:b + 1])[0])
+        out = mp.Statistics.finalize(st1.pack(), k_max)
+        want = orc.statistics(k_max, q[:, b])
+        got = [out["average"], out["variance"], out["variance_error"], out["tau_int"], out["error"],
+               out["samples"]]
+        assert np.allclose(got, want, rtol=1e-11)
+    # all chains: the "average over ranks" of statistics.cc:30-35,64-79
+    out = mp.Statistics.finalize(packed, k_max)
+    per = np.array([orc.statistics(k_max, q[:, b]) for b in range(B)])
+    assert abs(out["average"] - per[:, 0].mean()) < 1e-12
+    assert out["samples"] == B * n
+
+
+# ------------------------------------------- properties at the BASELINE sizes
+
+
+def test_schwinger_512_properties(mp, ctx):
+    m = mp.schwinger(512, 512, 4.0)
+    B = 4
+    x = ctx.init_state(m, B, 0, 1)
+    S0 = host(ctx.action(m, x))
+    # gauge invariance: the force sums to zero (SURVEY 8c pin 3)
+    F = ctx.force(m, x)
+    assert float(F.sum(dim=1).abs().max()) < 1e-8
+    # overrelaxation leaves the action unchanged
+    y = x.clone()
+    ctx.overrelax_sweep(m, y)
+    assert np.max(np.abs(host(ctx.action(m, y)) - S0)) <= 1e-11 * np.max(S0)
+    assert float((y - x).abs().max()) > 1e-3
+    # integer topological charge, consistent with the double-valued QoI
+    chi, Q = ctx.qoi(m, mp.QOI_SCHWINGER_CHI, x, with_charge=True)
+    assert np.allclose(host(chi), host(Q).astype(float) ** 2, rtol=0, atol=1e-6)
+    # restrict o prolong = identity on the coarse links (mod 2 pi)
+    mc = mp.coarse_model(m)
+    xc = ctx.init_state(mc, B, 0, 2)
+    ctx.prolong(m, xc, y)
+    xc2 = ctx.state(mc, B)
+    ctx.restrict(m, y, xc2)
+    ang_close(host(xc2), host(xc), tol=1e-14, what="restrict o prolong")
+    # the fill-in keeps the coarse links: restrict(fill(prolong(xc))) = xc
+    ctx.prolong_fill(m, xc, y, 0, 3)
+    ctx.restrict(m, y, xc2)
+    ang_close(host(xc2), host(xc), tol=1e-12, what="restrict o fill o prolong")
+    # leapfrog: reversible and (nearly) energy conserving
+    p = ctx.hmc_momentum(m, B, 0, 4)
+    H0 = host(ctx.action(m, x) + 0.5 * (p * p).sum(dim=1))
+    y, q = x.clone(), p.clone()
+    ctx.leapfrog(m, 20, 0.01, y, q)
+    H1 = host(ctx.action(m, y) + 0.5 * (q * q).sum(dim=1))
+    assert np.max(np.abs(H1 - H0)) < 0.5 and np.max(np.abs(H1 - H0)) > 0
+    q.neg_()
+    ctx.leapfrog(m, 20, 0.01, y, q)
+    assert float((y - x).abs().max()) < 1e-9
+
+
+def test_rowmarch_equals_generic_leapfrog(mp, ctx):
+    """the tiled hot kernel (Mt % 32 == 0) and the generic fallback agree"""
+    rng = np.random.default_rng(3)
+    orc = po.oracle()
+    for Mt, Mx in [(32, 8), (64, 48), (96, 33)]:
+        o = po.schwinger(Mt, Mx, 3.0)
+        m = to_mp(mp, o)
+        x, p = rng.uniform(-3, 3, (2, 2 * Mt * Mx)), rng.normal(size=(2, 2 * Mt * Mx))
+        xd, pd = dev(ctx, x), dev(ctx, p)
+        ctx.leapfrog(m, 4, 0.05, xd, pd)
+        want = [orc.leapfrog(o, 4, 0.05, x[b], p[b]) for b in range(2)]
+        close(host(xd), [w[0] for w in want], what=f"x {Mt}x{Mx}")
+        close(host(pd), [w[1] for w in want], what=f"p {Mt}x{Mx}")
+
+
+def test_rotor_c2_properties(mp, ctx):
+    """C2 shape: M_lat = 256, 8192 chains"""
+    m = mp.rotor(256, 4.0, 0.25)
+    B = 8192
+    x = ctx.init_state(m, B, 0, 0)
+    S0 = ctx.action(m, x)
+    y = x.clone()
+    ctx.overrelax_sweep(m, y)
+    assert float((ctx.action(m, y) - S0).abs().max()) < 1e-10 * float(S0.abs().max())
+    chi, Q = ctx.qoi(m, mp.QOI_ROTOR_CHI, x, with_charge=True)
+    assert np.allclose(host(chi) * m.T_final, host(Q).astype(float) ** 2, atol=1e-8)
+    mc = mp.coarse_model(m)
+    xc = ctx.state(mc, B)
+    ctx.restrict(m, x, xc)
+    assert bool((xc == x[:, ::2]).all())
+
+
+# ------------------------------------------ statistical parity with analytics
+
+
+def _mean_err(v):
+    v = np.asarray(v)
+    return v.mean(), v.std(ddof=1) / np.sqrt(len(v))
+
+
+def test_ho_hmc_matches_analytic_x2(mp, ctx):
+    """C1: harmonic oscillator, HMC, template parameters; <x^2> against
+    HarmonicOscillatorAction::Xsquared_analytical (recorded from the reference)"""
+    m = mp.ho(32, 4.0, 1.0, 1.0)
+    B = 4096
+    s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, nt=100, dt=0.1)
+    x = ctx.state(m, B)
+    for _ in range(30):
+        s.draw(x)
+    vals = []
+    for _ in range(10):
+        s.draw(x)
+        vals.append(host(ctx.qoi(m, mp.QOI_X2, x)))
+    per_chain = np.mean(vals, axis=0)
+    mean, err = _mean_err(per_chain)
+    want = float.fromhex(load("scalars")["analytic"]["ho_x2_32"])
+    assert abs(mean - want) < 5 * err + 1e-4, (mean, err, want)
+    assert 0.5 < s.p_accept()[0] <= 1.0
+
+
+def test_rotor_hierarchical_matches_exact_chit(mp, ctx):
+    """rotor M=32, hierarchical sampler (3 levels, HMC on the coarsest level):
+    susceptibility against RotorAction::chit_exact"""
+    m = mp.rotor(32, 4.0, 0.25)
+    B = 8192
+    s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=3, nt=20, dt=0.1,
+                   renorm=mp.RENORM_PERTURBATIVE)
+    x = ctx.init_state(m, B, 0, 0)
+    s.set_state(x)
+    for _ in range(40):
+        s.draw(x)
+    vals = []
+    for _ in range(20):
+        s.draw(x)
+        vals.append(host(ctx.qoi(m, mp.QOI_ROTOR_CHI, x)))
+    mean, err = _mean_err(np.mean(vals, axis=0))
+    want = float.fromhex(load("scalars")["analytic"]["rotor_chit_exact_32"])
+    assert abs(mean - want) < 5 * err, (mean, err, want)
+    pa = s.p_accept()
+    assert all(0.05 < p <= 1.0 for p in pa), pa
+
+
+def test_schwinger_samplers_match_analytic_chit(mp, ctx):
+    """quenched Schwinger 8x8, beta = 4 (P = 64 plaquettes): heat bath + overrelaxation
+    and the hierarchical sampler against quenchedschwinger_chit_analytical"""
+    want = float.fromhex(load("scalars")["analytic"]["schwinger_chit_analytical_4_64"])
+    m = mp.schwinger(8, 8, 4.0)
+    B = 4096
+    for kw in (dict(kind=mp.SAMPLER_HEATBATH, n_sweep_overrelax=2, n_sweep_heatbath=1),
+               dict(kind=mp.SAMPLER_HMC, n_levels=2, nt=20, dt=0.1)):
+        s = mp.Sampler(ctx, m, B, **kw)
+        x = ctx.init_state(m, B, 0, 0)
+        s.set_state(x)
+        for _ in range(60):
+            s.draw(x)
+        vals = []
+        for _ in range(30):
+            s.draw(x)
+            vals.append(host(ctx.qoi(m, mp.QOI_SCHWINGER_CHI, x)))
+        mean, err = _mean_err(np.mean(vals, axis=0))
+        assert abs(mean - want) < 5 * err, (kw, mean, err, want)
+        s.close()
+
+
+def test_gff_heatbath_matches_analytic_phi2(mp, ctx):
+    want = float.fromhex(load("scalars")["analytic"]["gff_phi_squared_10_16"])
+    m = mp.gff(16, 16, 10.0)
+    B = 2048
+    s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HEATBATH, n_sweep_overrelax=1, n_sweep_heatbath=1)
+    x = ctx.init_state(m, B, 0, 0)
+    s.set_state(x)
+    for _ in range(50):
+        s.draw(x)
+    vals = []
+    for _ in range(20):
+        s.draw(x)
+        vals.append(host(ctx.qoi(m, mp.QOI_PHI2, x)))
+    mean, err = _mean_err(np.mean(vals, axis=0))
+    assert abs(mean - want) < 5 * err, (mean, err, want)
+
+
+def test_host_entry_point(mp, ctx):
+    """mlmcpi_sampler_draw_host: host buffers in, QoI and state out"""
+    m = mp.schwinger(32, 32, 4.0)
+    B = 8
+    s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=2, nt=10, dt=0.05)
+    x_in = host(ctx.init_state(m, B, 0, 5))
+    q = np.zeros(B)
+    x_out = np.zeros_like(x_in)
+    s.draw_host(x_in, mp.QOI_SCHWINGER_CHI, q, x_out)
+    orc = po.oracle()
+    o = po.schwinger(32, 32, 4.0)
+    for b in range(B):
+        assert abs(q[b] - orc.qoi(o, po.QOI_SCHWINGER_CHI, x_out[b])[0]) < 1e-9
+    w = s.work()
+    assert w["leapfrog_site_steps"] == B * 11 * 16 * 16 and w["filled_fine_sites"] == B * 32 * 32
+
+
+def test_error_paths(mp, ctx):
+    with pytest.raises(mp.MlmcpiError):
+        ctx.overrelax_sweep(mp.ho(16), ctx.state(mp.ho(16), 1))       # not defined for HO
+    with pytest.raises(mp.MlmcpiError):
+        ctx.fill(mp.schwinger(7, 8, 1.0), ctx.state(mp.schwinger(7, 8, 1.0), 1))  # odd extent
+    with pytest.raises(mp.MlmcpiError):
+        ctx.qoi(mp.rotor(16), mp.QOI_PHI2, ctx.state(mp.rotor(16), 1))
+    with pytest.raises(mp.MlmcpiError):
+        m = mp.gff(8, 8, 1.0, mp.COARSEN_BOTH)
+        ctx.fill(m, ctx.state(m, 1))                                   # GFF fill needs rotate
