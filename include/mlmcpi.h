@@ -78,7 +78,10 @@ typedef struct mlmcpi_ctx mlmcpi_ctx;
 
 /* ---- context ------------------------------------------------------------ */
 int mlmcpi_version(void);
-/* stream: a cudaStream_t (e.g. torch's current stream) or NULL for an own one */
+/* stream: the cudaStream_t all kernels and copies are issued on (e.g. torch's current
+ * stream); NULL is CUDA's legacy default stream; MLMCPI_OWN_STREAM creates a private
+ * non-blocking stream (the caller then orders its own work with mlmcpi_sync) */
+#define MLMCPI_OWN_STREAM ((void *)(intptr_t)-1)
 int mlmcpi_create(mlmcpi_ctx **ctx, int device, uint64_t seed, void *stream);
 void mlmcpi_destroy(mlmcpi_ctx *ctx);
 const char *mlmcpi_last_error(const mlmcpi_ctx *ctx);

@@ -6,6 +6,7 @@ torch is used for device memory and streams only; every computation is a call in
 libmlmcpi.so.  Batched states are float64 tensors of shape [B, n_dof] in the
 reference's dof order (one row == one reference SampleState::data)."""
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -87,15 +88,20 @@ class Context:
             raise MlmcpiError("no CUDA device: mlmcpathintegral_b200 has no CPU fallback")
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream if use_torch_stream else None
+        # torch's default stream is CUDA's legacy default stream (handle 0 == NULL)
+        stream = (torch.cuda.current_stream(self.device).cuda_stream if use_torch_stream
+                  else C.c_void_p(-1))  # MLMCPI_OWN_STREAM
         h = C.c_void_p()
         rc = L.mlmcpi_create(C.byref(h), device, seed, stream)
         if rc:
             raise MlmcpiError(f"mlmcpi_create failed ({rc})")
         self.h = h
+        self._children = weakref.WeakSet()  # samplers / statistics living on this context
 
     def close(self):
         if self.h:
+            for child in list(self._children):
+                child.close()
             L.mlmcpi_destroy(self.h)
             self.h = None
 
@@ -232,6 +238,7 @@ class Sampler:
         ctx._ck(L.mlmcpi_sampler_create(ctx.h, C.byref(fine), C.byref(prm), B, chain0, C.byref(h)))
         self.h = h
         self.n = sample_size(fine)
+        ctx._children.add(self)
 
     def close(self):
         if self.h:
@@ -281,6 +288,7 @@ class Statistics:
         h = C.c_void_p()
         ctx._ck(L.mlmcpi_stats_create(ctx.h, k_max, B, C.byref(h)))
         self.h = h
+        ctx._children.add(self)
 
     def close(self):
         if self.h:

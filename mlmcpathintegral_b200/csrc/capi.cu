@@ -124,8 +124,8 @@ int mlmcpi_create(mlmcpi_ctx **out, int device, uint64_t seed, void *stream) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess)
     ctx->n_sm = prop.multiProcessorCount;
-  if (stream) {
-    ctx->stream = (cudaStream_t)stream;
+  if (stream != MLMCPI_OWN_STREAM) {
+    ctx->stream = (cudaStream_t)stream; // NULL = the legacy default stream
   } else {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
       delete ctx;
