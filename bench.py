@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--chains", type=int, default=512, help="chains per GPU")
     ap.add_argument("--nt", type=int, default=100)
     ap.add_argument("--dt", type=float, default=0.1)
+    ap.add_argument("--thermalise", type=int, default=20, help="overrelaxed heat-bath sweeps before timing")
+    ap.add_argument("--autotune", type=int, default=1, help="tune the HMC step size as HMCSampler does")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
@@ -236,8 +238,23 @@ def gpu_main(a):
                          renorm=mp.RENORM_PERTURBATIVE, chain0=rank * B)
     k_max = 10
     stats = mp.Statistics(ctx, k_max, B)
-    x = ctx.init_state(m, B, rank * B, 0)
+    # start state: hot (U(-pi,pi), Action::initialise_state) at small beta, cold at large beta,
+    # then thermalised by overrelaxed heat-bath sweeps on the fine level (untimed)
+    x = ctx.init_state(m, B, rank * B, 0) if a.beta <= 8 else ctx.state(m, B)
+    for k in range(a.thermalise):
+        ctx.overrelax_sweep(m, x)
+        ctx.heatbath_sweep(m, x, rank * B, 1000 + k)
     sampler.set_state(x)
+    tuned = None
+    if a.autotune:  # HMCSampler::autotune_stepsize (hmcsampler.cc:72-113) on the coarsest level
+        dt0 = a.dt
+        for _ in range(12):  # bring dt into the bisection bracket [dt/2, 2 dt] of the reference
+            sampler.set_dt(dt0)
+            dt_t, p_t, ok = sampler.autotune(0.8, 8, 2 * B)
+            if ok or p_t > 0.8:
+                break
+            dt0 *= 0.5
+        tuned = {"dt": dt_t, "p_accept": p_t, "converged": ok}
     packed = ctx.empty(6 + k_max)
 
     def step():
@@ -333,7 +350,7 @@ def gpu_main(a):
             "l2": "inputs larger than L2 (per-GPU fine states %.1f GiB)" % (B * mp.sample_size(m) * 8 / 2 ** 30),
             "site_updates_per_step_per_gpu": {k: v for k, v in work.items()},
             "value_per_gpu": value / world,
-            "acceptance_per_level": p_acc,
+            "acceptance_per_level": p_acc, "hmc_autotune": tuned,
             "chi_t": {"average": st["average"], "error": st["error"], "tau_int": st["tau_int"],
                       "samples": st["samples"]},
             "ess_per_s": st["samples"] / st["tau_int"] / (ms_max * 1e-3),

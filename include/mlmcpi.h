@@ -87,6 +87,12 @@ void mlmcpi_destroy(mlmcpi_ctx *ctx);
 const char *mlmcpi_last_error(const mlmcpi_ctx *ctx);
 int mlmcpi_sync(mlmcpi_ctx *ctx);
 int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed);
+/* options.  MLMCPI_OPT_EXPCOS_ENVELOPE: proposal of the ExpCos rejection sampler
+ * (distribution/expcosdistribution.hh:50-65): 0 = the reference's Gaussian envelope
+ * (variance 2 pi^2/tau, ~22 % acceptance), 1 = chord-bound envelope (variance
+ * pi^2/(4 tau), ~64 % acceptance; default).  The sampled distribution is the same. */
+enum { MLMCPI_OPT_EXPCOS_ENVELOPE = 1 };
+int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value);
 /* number of kernels this context has launched so far */
 uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx);
 /* CUDA-event timing of the leapfrog launches (the dominant kernel) on the context's
@@ -205,6 +211,11 @@ int mlmcpi_sampler_stats(mlmcpi_sampler *s, double *h_p_accept /* [n_levels] */)
 /* elementary-update counters of the last draw for throughput accounting:
  * out = {leapfrog site-steps, sweep site-updates, filled fine sites} summed over chains */
 int mlmcpi_sampler_work(const mlmcpi_sampler *s, double out[3]);
+/* HMCSampler::autotune_stepsize (sampler/hmcsampler.cc:72-113) on the coarsest level:
+ * returns 0 if tuned, 1 if not converged (dt then reverts, as in the reference) */
+int mlmcpi_sampler_autotune(mlmcpi_sampler *s, double p_accept_target, int n_rounds, int n_samples,
+                            double *dt_out, double *p_accept_out);
+int mlmcpi_sampler_set_dt(mlmcpi_sampler *s, double dt);
 
 /* ---- statistics (common/statistics.cc:4-97), one accumulator per chain ---- */
 typedef struct mlmcpi_stats mlmcpi_stats;

@@ -16,6 +16,7 @@ RENORM_NONE, RENORM_PERTURBATIVE, RENORM_NONPERTURBATIVE = range(3)
 QOI_X2, QOI_ROTOR_CHI, QOI_SCHWINGER_CHI, QOI_AVG_PLAQUETTE, QOI_PHI2 = range(5)
 SAMPLER_HMC, SAMPLER_HEATBATH = 0, 1
 E_INVAL, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4
+OPT_EXPCOS_ENVELOPE = 1
 
 
 class Model(C.Structure):
@@ -47,6 +48,7 @@ SIGNATURES = {
     "mlmcpi_last_error": (C.c_char_p, [_vp]),
     "mlmcpi_sync": (_i, [_vp]),
     "mlmcpi_set_seed": (_i, [_vp, _u64]),
+    "mlmcpi_set_option": (_i, [_vp, _i, _i]),
     "mlmcpi_launch_count": (_u64, [_vp]),
     "mlmcpi_profile": (_i, [_vp, _i]),
     "mlmcpi_profile_read": (_i, [_vp, _dp]),
@@ -87,6 +89,8 @@ SIGNATURES = {
     "mlmcpi_sampler_level_model": (_i, [_vp, _i, _MP]),
     "mlmcpi_sampler_stats": (_i, [_vp, _dp]),
     "mlmcpi_sampler_work": (_i, [_vp, _dp]),
+    "mlmcpi_sampler_autotune": (_i, [_vp, _d, _i, _i, _dp, _dp]),
+    "mlmcpi_sampler_set_dt": (_i, [_vp, _d]),
     "mlmcpi_stats_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
     "mlmcpi_stats_destroy": (None, [_vp]),
     "mlmcpi_stats_reset": (_i, [_vp]),

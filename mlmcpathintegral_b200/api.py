@@ -121,6 +121,10 @@ class Context:
     def set_seed(self, seed):
         L.mlmcpi_set_seed(self.h, seed)
 
+    def set_expcos_envelope(self, tight=True):
+        """ExpCos proposal: reference envelope (False) or the tighter chord bound (True, default)"""
+        self._ck(L.mlmcpi_set_option(self.h, _lib.OPT_EXPCOS_ENVELOPE, int(bool(tight))))
+
     @property
     def launches(self):
         return int(L.mlmcpi_launch_count(self.h))
@@ -273,6 +277,18 @@ class Sampler:
         out = (C.c_double * self.n_levels)()
         self.ctx._ck(L.mlmcpi_sampler_stats(self.h, out))
         return list(out)
+
+    def autotune(self, p_accept_target=0.8, n_rounds=100, n_samples=1000):
+        """HMCSampler::autotune_stepsize; returns (dt, last acceptance, converged)"""
+        dt, pa = C.c_double(), C.c_double()
+        rc = L.mlmcpi_sampler_autotune(self.h, p_accept_target, n_rounds, n_samples, C.byref(dt),
+                                       C.byref(pa))
+        if rc not in (0, 1):
+            self.ctx._ck(rc)
+        return dt.value, pa.value, rc == 0
+
+    def set_dt(self, dt):
+        L.mlmcpi_sampler_set_dt(self.h, dt)
 
     def work(self):
         out = (C.c_double * 3)()

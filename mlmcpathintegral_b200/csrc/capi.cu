@@ -158,6 +158,13 @@ int mlmcpi_sync(mlmcpi_ctx *ctx) {
   MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
+  if (option == MLMCPI_OPT_EXPCOS_ENVELOPE && (value == 0 || value == 1)) {
+    ctx->expcos_envelope = value;
+    return 0;
+  }
+  return ctx_fail(ctx, MLMCPI_EINVAL, "unknown option or value");
+}
 int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed) {
   ctx->seed = seed;
   return 0;
@@ -964,6 +971,66 @@ int mlmcpi_sampler_work(const mlmcpi_sampler *s, double out[3]) {
   out[0] = s->work[0];
   out[1] = s->work[1];
   out[2] = s->work[2];
+  return 0;
+}
+
+// HMCSampler::autotune_stepsize, sampler/hmcsampler.cc:72-113: bisection of dt on
+// [dt/2, 2 dt] towards the target acceptance, n_samples single_step()s per round.  The
+// B chains of the batch supply the samples in parallel: ceil(n_samples / B) steps per
+// round.  Acts on the sampler of the coarsest level.  Like the reference it keeps dt
+// unchanged if no round came within 1e-2 of the target.
+int mlmcpi_sampler_autotune(mlmcpi_sampler *s, double p_accept_target, int n_rounds, int n_samples,
+                            double *dt_out, double *p_accept_out) {
+  mlmcpi_ctx *ctx = s->ctx;
+  if (s->prm.kind != MLMCPI_SAMPLER_HMC)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "autotune is defined for the HMC sampler");
+  const int l = s->L - 1, B = s->B;
+  const mlmcpi_model *m = &s->model[l];
+  for (int lev = 1; lev < s->L; ++lev) { // tune on the restricted current state
+    int rc = mlmcpi_restrict(ctx, &s->model[lev - 1], s->state[lev - 1], s->state[lev], B);
+    if (rc)
+      return rc;
+  }
+  const double dt_original = s->prm.dt;
+  double dt_min = 0.5 * s->prm.dt, dt_max = 2. * s->prm.dt, dt = s->prm.dt, p_acc = 0.0;
+  bool converged = false;
+  const int steps = (n_samples + B - 1) / B;
+  unsigned long long *cnt = nullptr;
+  MLMCPI_CUDA(cudaMalloc((void **)&cnt, sizeof(unsigned long long)));
+  for (int k = 0; k < n_rounds; ++k) {
+    dt = 0.5 * (dt_min + dt_max);
+    cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream);
+    for (int j = 0; j < steps; ++j) {
+      int rc = mlmcpi_hmc_step(ctx, m, s->prm.nt, dt, s->state[l], B, s->chain0,
+                               level_draw(s->draw++, l, 0xff), s->acc, nullptr);
+      if (rc) {
+        cudaFree(cnt);
+        return rc;
+      }
+      count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc, cnt);
+    }
+    unsigned long long h = 0;
+    cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    p_acc = (double)h / ((double)steps * B);
+    if (p_acc > p_accept_target)
+      dt_min = dt;
+    else
+      dt_max = dt;
+    if (std::fabs(p_acc - p_accept_target) < 1.E-2)
+      converged = true;
+  }
+  cudaFree(cnt);
+  s->prm.dt = converged ? dt : dt_original;
+  if (dt_out)
+    *dt_out = s->prm.dt;
+  if (p_accept_out)
+    *p_accept_out = p_acc;
+  return converged ? 0 : 1; /* 1: "FAILED to tune, reverting" (hmcsampler.cc:107-110) */
+}
+
+int mlmcpi_sampler_set_dt(mlmcpi_sampler *s, double dt) {
+  s->prm.dt = dt;
   return 0;
 }
 

@@ -19,13 +19,15 @@ namespace {
 struct SW {
   int Mt, Mx;
   double beta;
+  int envelope; // ExpCos envelope: 0 reference, 1 tight
 };
 
-SW make_sw(const mlmcpi_model *m) {
+SW make_sw(const mlmcpi_ctx *ctx, const mlmcpi_model *m) {
   SW s;
   s.Mt = m->Mt_lat;
   s.Mx = m->Mx_lat;
   s.beta = m->beta;
+  s.envelope = ctx->expcos_envelope;
   return s;
 }
 
@@ -251,7 +253,7 @@ __global__ void sweep_colour_kernel(SW sw, int colour, double *x, int B, uint32_
   const size_t ell = 2 * ((size_t)Mt * j + i) + mu;
   if (HEATBATH) { // qft/quenchedschwingeraction.cc:46-54
     Rng rg = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, (uint32_t)ell);
-    xc[ell] = expcos_draw(rg, sw.beta, theta_p, theta_m);
+    xc[ell] = expcos_draw(rg, sw.beta, theta_p, theta_m, sw.envelope);
   } else { // qft/quenchedschwingeraction.cc:57-65
     xc[ell] = mod_2pi((theta_p + theta_m) - xc[ell]);
   }
@@ -349,6 +351,7 @@ struct CellLinks {
 
 template <bool APPROX>
 __device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double beta,
+                                                   const int envelope,
                                                    const BesselProductConst &bp, uint64_t seed,
                                                    uint64_t draw, uint32_t gchain, int Mt, int i,
                                                    int j, int cell) {
@@ -367,13 +370,13 @@ __device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double be
     const double theta_p = mod_2pi(c.A0 + c.V0 - c.B0);
     const double theta_m = mod_2pi(c.B1 + c.T0 - c.V1);
     Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i);
-    c.H0 = expcos_draw(r, beta, theta_p, theta_m);
+    c.H0 = expcos_draw(r, beta, theta_p, theta_m, envelope);
   }
   {
     const double theta_p = mod_2pi(c.A1 + c.R0 - c.V0);
     const double theta_m = mod_2pi(c.V1 + c.T1 - c.R1);
     Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i + 1);
-    c.H1 = expcos_draw(r, beta, theta_p, theta_m);
+    c.H1 = expcos_draw(r, beta, theta_p, theta_m, envelope);
   }
 }
 
@@ -400,7 +403,7 @@ __global__ void fill_both_step23_kernel(SW sw, BesselProductConst bp, double *x_
   c.R1 = TH(x, i2, 2 * j + 1, 1);
   c.T0 = TH(x, 2 * i, j2, 0);
   c.T1 = TH(x, 2 * i + 1, j2, 0);
-  fill_cell_interior<APPROX>(c, sw.beta, bp, seed, draw, chain0 + (uint32_t)chain, Mt, i, j, cell);
+  fill_cell_interior<APPROX>(c, sw.beta, sw.envelope, bp, seed, draw, chain0 + (uint32_t)chain, Mt, i, j, cell);
   TH(x, 2 * i + 1, 2 * j, 1) = c.V0;
   TH(x, 2 * i + 1, 2 * j + 1, 1) = c.V1;
   TH(x, 2 * i, 2 * j + 1, 0) = c.H0;
@@ -454,7 +457,7 @@ __global__ void prolong_fill_both_kernel(SW sw, BesselProductConst bp, const dou
     c.T0 = mod_2pi(0.5 * ct + dth_t);
     c.T1 = mod_2pi(0.5 * ct - dth_t);
   }
-  fill_cell_interior<APPROX>(c, sw.beta, bp, seed, draw, gchain, Mt, i, j, cell);
+  fill_cell_interior<APPROX>(c, sw.beta, sw.envelope, bp, seed, draw, gchain, Mt, i, j, cell);
   // rows 2j and 2j+1, sites 2i and 2i+1: four aligned double2 stores
   double2 *xs = reinterpret_cast<double2 *>(x);
   xs[(size_t)Mt * (2 * j) + 2 * i] = make_double2(c.A0, c.B0);
@@ -498,13 +501,13 @@ __global__ void fill_semi_kernel(SW sw, int ctype, int phase, double *x_all, int
       const double theta_p = mod_2pi(TH(x, 2 * i, j, 1) + TH(x, 2 * i, jp, 0) - TH(x, 2 * i, j, 0));
       const double theta_m =
           mod_2pi(TH(x, 2 * i + 1, j, 0) + TH(x, i2, j, 1) - TH(x, 2 * i + 1, jp, 0));
-      TH(x, 2 * i + 1, j, 1) = expcos_draw(r, sw.beta, theta_p, theta_m);
+      TH(x, 2 * i + 1, j, 1) = expcos_draw(r, sw.beta, theta_p, theta_m, sw.envelope);
     } else {
       const int ip = wrap_inc(i, Mt), j2 = wrap_inc(2 * j + 1, Mx);
       const double theta_p = mod_2pi(TH(x, i, 2 * j, 0) + TH(x, ip, 2 * j, 1) - TH(x, i, 2 * j, 1));
       const double theta_m =
           mod_2pi(TH(x, i, 2 * j + 1, 1) + TH(x, i, j2, 0) - TH(x, ip, 2 * j + 1, 1));
-      TH(x, i, 2 * j + 1, 0) = expcos_draw(r, sw.beta, theta_p, theta_m);
+      TH(x, i, 2 * j + 1, 0) = expcos_draw(r, sw.beta, theta_p, theta_m, sw.envelope);
     }
   }
 }
@@ -668,7 +671,7 @@ namespace schwinger {
 
 int init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,
                uint64_t draw) {
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const long long n = (long long)sw.Mt * sw.Mx * B;
   init_state_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, x, B, chain0, ctx->seed, draw);
   MLMCPI_LAUNCHED("schwinger::init_state");
@@ -676,13 +679,13 @@ int init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_
 }
 
 int action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, double *S) {
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   return site_reduce<1>(ctx, "schwinger::action", ActionF{sw, x}, (long long)sw.Mt * sw.Mx, B,
                         EPI_SCALE, sw.beta, 0.0, S, nullptr);
 }
 
 int force(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, double *f, int B) {
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const long long n = (long long)sw.Mt * sw.Mx * B;
   force_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, x, f, B);
   MLMCPI_LAUNCHED("schwinger::force");
@@ -691,7 +694,7 @@ int force(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, double *f, in
 
 int leapfrog(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *x, double *p,
              int B) {
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const size_t n = (size_t)2 * sw.Mt * sw.Mx * B;
   double *bufA = ctx_work(ctx, 1, n), *bufB = ctx_work(ctx, 2, n);
   if (!bufA || !bufB)
@@ -707,7 +710,7 @@ int leapfrog(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *
 
 int hmc_momentum(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *p, int B, uint32_t chain0,
                  uint64_t draw) {
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const long long n = (long long)sw.Mt * sw.Mx * B;
   momentum_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, p, B, chain0, ctx->seed, draw);
   MLMCPI_LAUNCHED("schwinger::hmc_momentum");
@@ -717,7 +720,7 @@ int hmc_momentum(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *p, int B, uint3
 // HMCSampler::single_step, sampler/hmcsampler.cc:22-69
 int hmc_step(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *x, int B,
              uint32_t chain0, uint64_t draw, int32_t *accept, double *diag) {
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const size_t nd = (size_t)2 * sw.Mt * sw.Mx;
   const size_t n = nd * B;
   double *p = ctx_work(ctx, 0, n), *bufA = ctx_work(ctx, 1, n), *bufB = ctx_work(ctx, 2, n);
@@ -752,7 +755,7 @@ static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool 
                  uint32_t chain0, uint64_t draw) {
   if (m->Mt_lat % 2 || m->Mx_lat % 2)
     return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need even lattice extents");
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const long long n = (long long)sw.Mt * sw.Mx / 2 * B;
   for (int colour = 0; colour < 4; ++colour) {
     if (heatbath)
@@ -777,7 +780,7 @@ int prolong(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x,
   int rc = check_even(ctx, m);
   if (rc)
     return rc;
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const long long n = n_coarse_sites(m) * B;
   prolong_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, m->coarsening, xc, x, B);
   MLMCPI_LAUNCHED("schwinger::prolong");
@@ -788,7 +791,7 @@ int restrict_(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xf, double *
   int rc = check_even(ctx, m);
   if (rc)
     return rc;
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const long long n = n_coarse_sites(m) * B;
   restrict_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, m->coarsening, xf, xc, B);
   MLMCPI_LAUNCHED("schwinger::restrict");
@@ -799,7 +802,7 @@ int fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chai
   int rc = check_even(ctx, m);
   if (rc)
     return rc;
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const long long n = n_coarse_sites(m) * B;
   if (m->coarsening == MLMCPI_COARSEN_BOTH) {
     fill_both_step1_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, x, B, chain0, ctx->seed, draw);
@@ -835,7 +838,7 @@ int prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, doubl
       return rc;
     return fill(ctx, m, x, B, chain0, draw);
   }
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const long long n = n_coarse_sites(m) * B;
   BesselProductConst bp;
   if (sw.beta > 8.0) {
@@ -855,7 +858,7 @@ int cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, 
   int rc = check_even(ctx, m);
   if (rc)
     return rc;
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const long long n = n_coarse_sites(m);
   if (m->coarsening == MLMCPI_COARSEN_BOTH) {
     if (sw.beta > 8.0)
@@ -873,7 +876,7 @@ int cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, 
 
 int qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int which, const double *x, int B, double *out,
         int64_t *Qint) {
-  SW sw = make_sw(m);
+  SW sw = make_sw(ctx, m);
   const long long n = (long long)sw.Mt * sw.Mx;
   if (which == MLMCPI_QOI_SCHWINGER_CHI)
     return site_reduce<2>(ctx, "schwinger::qoi_chi", ChiF{sw, x}, n, B, EPI_CHI,

@@ -909,22 +909,47 @@ double orc_expsin2_draw(orc_rng *r, double sigma) {
   }
 }
 
-/* distribution/expcosdistribution.hh:50-65 */
+/* Proposal of the ExpCos rejection sampler.
+ *   0: the reference's own envelope (distribution/expcosdistribution.hh:50-65).
+ *   1: NOT the reference's algorithm: the tighter chord-bound envelope
+ *      1 - cos x >= 2 x^2 / pi^2 that the product uses by default
+ *      (MLMCPI_OPT_EXPCOS_ENVELOPE = 1; uniform proposal for tau < 1/2).  The target
+ *      pdf ~ exp(tau cos x) is the reference's; tests/test_oracle_cpu.py checks both
+ *      variants against the reference's own draw() by a two-sample KS test. */
+static int g_expcos_envelope = 0;
+void orc_set_expcos_envelope(int envelope) { g_expcos_envelope = envelope; }
+
 double orc_expcos_draw(orc_rng *r, double beta, double x_p, double x_m) {
-  const double fourpi2_inv = 1. / (4. * M_PI * M_PI);
   const double dx = x_m - x_p;
   const double tau = 2. * beta * fabs(cos(0.5 * dx));
-  const double sigma = M_PI * sqrt(2. / tau);
   double x = 0.0;
   int accepted = 0;
-  while (!accepted) {
-    double z[2], u[2];
-    orc_rng_normal2(r, &z[0], &z[1]);
-    orc_rng_uniform2(r, &u[0], &u[1]);
-    for (int t = 0; t < 2 && !accepted; ++t) {
-      x = sigma * z[t];
-      if ((-M_PI <= x) && (x < M_PI))
-        accepted = (u[t] <= exp(tau * (cos(x) - 1. + fourpi2_inv * x * x)));
+  if (g_expcos_envelope == 1 && tau < 0.5) {
+    while (!accepted) {
+      double a[2], u[2];
+      orc_rng_uniform2(r, &a[0], &a[1]);
+      orc_rng_uniform2(r, &u[0], &u[1]);
+      for (int t = 0; t < 2 && !accepted; ++t) {
+        x = -M_PI + 2. * M_PI * a[t];
+        accepted = (u[t] <= exp(tau * (cos(x) - 1.)));
+      }
+    }
+  } else {
+    /* envelope 0: expcosdistribution.hh:53-61 (sigma = pi sqrt(2/tau),
+     * fourpi2_inv = 1/(4 pi^2)) */
+    const double sigma =
+        g_expcos_envelope == 1 ? 0.5 * M_PI / sqrt(tau) : M_PI * sqrt(2. / tau);
+    const double quad =
+        g_expcos_envelope == 1 ? 2. / (M_PI * M_PI) : 1. / (4. * M_PI * M_PI);
+    while (!accepted) {
+      double z[2], u[2];
+      orc_rng_normal2(r, &z[0], &z[1]);
+      orc_rng_uniform2(r, &u[0], &u[1]);
+      for (int t = 0; t < 2 && !accepted; ++t) {
+        x = sigma * z[t];
+        if ((-M_PI <= x) && (x < M_PI))
+          accepted = (u[t] <= exp(tau * (cos(x) - 1. + quad * x * x)));
+      }
     }
   }
   return orc_mod_2pi(x + 0.5 * (x_p + x_m) + (fabs(dx) > M_PI) * M_PI);

@@ -113,6 +113,8 @@ double orc_besselproduct_Znorm_inv(const double alphaZ[17], double phi, int resc
 double orc_besselproduct_pdf(double beta, double x, double x_p, double x_m);
 double orc_approxbessel_pdf(double beta, double x, double x_p, double x_m);
 double orc_expsin2_draw(orc_rng *r, double sigma);
+/* 0: the reference's envelope (default); 1: the product's tighter envelope (same pdf) */
+void orc_set_expcos_envelope(int envelope);
 double orc_expcos_draw(orc_rng *r, double beta, double x_p, double x_m);
 double orc_besselproduct_draw(orc_rng *r, double beta, double x_p, double x_m);
 double orc_approxbessel_draw(orc_rng *r, double beta, double x_p, double x_m);

@@ -151,6 +151,7 @@ class Oracle:
             "orc_besselproduct_pdf": (d, [d, d, d, d]),
             "orc_approxbessel_pdf": (d, [d, d, d, d]),
             "orc_expsin2_draw": (d, [C.POINTER(Rng), d]),
+            "orc_set_expcos_envelope": (None, [i]),
             "orc_expcos_draw": (d, [C.POINTER(Rng), d, d, d]),
             "orc_besselproduct_draw": (d, [C.POINTER(Rng), d, d, d]),
             "orc_approxbessel_draw": (d, [C.POINTER(Rng), d, d, d]),

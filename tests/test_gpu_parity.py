@@ -259,8 +259,21 @@ def test_deterministic_kernels_against_oracle(mp, ctx, orc, name):
             assert list(host(Q)) == [w[1] for w in want]  # integer topological charge: exact
 
 
-@pytest.mark.parametrize("name", list(MODELS))
-def test_stochastic_kernels_against_oracle(mp, ctx, orc, name):
+STOCHASTIC_CASES = [(n, e) for n in MODELS for e in ((0, 1) if n.startswith("schw") else (1,))]
+
+
+@pytest.fixture
+def envelope(request, ctx, orc):
+    """ExpCos proposal: 0 = the reference's envelope, 1 = the product's default (tighter)"""
+    ctx.set_expcos_envelope(bool(request.param))
+    orc.lib.orc_set_expcos_envelope(request.param)
+    yield request.param
+    ctx.set_expcos_envelope(True)
+    orc.lib.orc_set_expcos_envelope(0)
+
+
+@pytest.mark.parametrize("name,envelope", STOCHASTIC_CASES, indirect=["envelope"])
+def test_stochastic_kernels_against_oracle(mp, ctx, orc, name, envelope):
     o = MODELS[name]()
     m = to_mp(mp, o)
     rng = np.random.default_rng(zlib.crc32(name.encode()) + 1)
