@@ -91,7 +91,10 @@ int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed);
  * (distribution/expcosdistribution.hh:50-65): 0 = the reference's Gaussian envelope
  * (variance 2 pi^2/tau, ~22 % acceptance), 1 = chord-bound envelope (variance
  * pi^2/(4 tau), ~64 % acceptance; default).  The sampled distribution is the same. */
-enum { MLMCPI_OPT_EXPCOS_ENVELOPE = 1 };
+/* MLMCPI_OPT_LEAPFROG_VARIANT (2-D Schwinger leapfrog kernel; all variants compute the same
+ * step): 0 = TMA/mbarrier row pipeline (default), 1 = register row march, 2 = generic.
+ * MLMCPI_OPT_LEAPFROG_ROWS: lattice rows per thread block (0 = default). */
+enum { MLMCPI_OPT_EXPCOS_ENVELOPE = 1, MLMCPI_OPT_LEAPFROG_VARIANT = 2, MLMCPI_OPT_LEAPFROG_ROWS = 3 };
 int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value);
 /* number of kernels this context has launched so far */
 uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx);

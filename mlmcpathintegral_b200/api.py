@@ -121,6 +121,9 @@ class Context:
     def set_seed(self, seed):
         L.mlmcpi_set_seed(self.h, seed)
 
+    def set_option(self, option, value):
+        self._ck(L.mlmcpi_set_option(self.h, option, value))
+
     def set_expcos_envelope(self, tight=True):
         """ExpCos proposal: reference envelope (False) or the tighter chord bound (True, default)"""
         self._ck(L.mlmcpi_set_option(self.h, _lib.OPT_EXPCOS_ENVELOPE, int(bool(tight))))

@@ -163,6 +163,14 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
     ctx->expcos_envelope = value;
     return 0;
   }
+  if (option == MLMCPI_OPT_LEAPFROG_VARIANT && value >= 0 && value <= 2) {
+    ctx->leapfrog_variant = value;
+    return 0;
+  }
+  if (option == MLMCPI_OPT_LEAPFROG_ROWS && value >= 0) {
+    ctx->leapfrog_rows = value;
+    return 0;
+  }
   return ctx_fail(ctx, MLMCPI_EINVAL, "unknown option or value");
 }
 int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed) {
@@ -748,6 +756,12 @@ struct mlmcpi_sampler {
   std::vector<mlmcpi_model> model;
   std::vector<double *> state; // [L] device [B][n_l]
   double *Sf = nullptr, *Scond = nullptr, *q = nullptr; // [B]
+  // cached S_f / S_cond of the finest state.  state[0] only changes where the two-level step
+  // accepts, and the accept kernel updates the caches there, so the values
+  // TwoLevelMetropolisStep::set_state would recompute (twolevelmetropolisstep.cc:92-97) are
+  // already known -- bit for bit, the reductions being deterministic.
+  double *Sf0 = nullptr, *Scond0 = nullptr;
+  bool cache0_valid = false;
   int32_t *acc = nullptr, *acc_step = nullptr;          // [B]
   unsigned long long *counters = nullptr;               // [L] accepted chains per level
   uint64_t n_draws = 0;
@@ -837,6 +851,7 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
     ok = mlmcpi_alloc(ctx, (size_t)mlmcpi_sample_size(&s->model[l]) * B, &d) == 0;
     s->state.push_back(d);
   }
+  ok = ok && mlmcpi_alloc(ctx, B, &s->Sf0) == 0 && mlmcpi_alloc(ctx, B, &s->Scond0) == 0;
   ok = ok && mlmcpi_alloc(ctx, B, &s->Sf) == 0 && mlmcpi_alloc(ctx, B, &s->Scond) == 0 &&
        mlmcpi_alloc(ctx, B, &s->q) == 0;
   ok = ok && cudaMalloc((void **)&s->acc, sizeof(int32_t) * B) == cudaSuccess &&
@@ -865,6 +880,10 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
   for (double *d : s->state)
     if (d)
       cudaFree(d);
+  if (s->Sf0)
+    cudaFree(s->Sf0);
+  if (s->Scond0)
+    cudaFree(s->Scond0);
   if (s->Sf)
     cudaFree(s->Sf);
   if (s->Scond)
@@ -881,6 +900,7 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
 }
 
 int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x) {
+  s->cache0_valid = false;
   return mlmcpi_copy(s->ctx, s->state[0], d_x, (size_t)mlmcpi_sample_size(&s->model[0]) * s->B);
 }
 
@@ -901,15 +921,20 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
   MLMCPI_LAUNCHED("count_accept");
   for (int l = L - 2; l >= 0; --l) {
     // TwoLevelMetropolisStep::set_state, montecarlo/twolevelmetropolisstep.cc:92-97
-    if ((rc = mlmcpi_action(ctx, &s->model[l], s->state[l], B, s->Sf)))
-      return rc;
-    if ((rc = mlmcpi_cond_action(ctx, &s->model[l], s->state[l], B, s->Scond)))
-      return rc;
+    double *Sf = (l == 0) ? s->Sf0 : s->Sf, *Scond = (l == 0) ? s->Scond0 : s->Scond;
+    if (l > 0 || !s->cache0_valid) {
+      if ((rc = mlmcpi_action(ctx, &s->model[l], s->state[l], B, Sf)))
+        return rc;
+      if ((rc = mlmcpi_cond_action(ctx, &s->model[l], s->state[l], B, Scond)))
+        return rc;
+    }
     // s->acc is both the incoming cascade mask and the outgoing accept flag
     if ((rc = twolevel_step_impl(ctx, &s->model[l], &s->model[l + 1], s->state[l + 1], s->state[l],
-                                 s->Sf, s->Scond, B, s->chain0, level_draw(s->draw, l, 0), s->acc,
-                                 s->acc, nullptr)))
+                                 Sf, Scond, B, s->chain0, level_draw(s->draw, l, 0), s->acc, s->acc,
+                                 nullptr)))
       return rc;
+    if (l == 0)
+      s->cache0_valid = true;
     count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc,
                                                                            s->counters + l);
     MLMCPI_LAUNCHED("count_accept");
@@ -932,9 +957,11 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
   mlmcpi_ctx *ctx = s->ctx;
   const size_t n = (size_t)mlmcpi_sample_size(&s->model[0]) * s->B;
   int rc;
-  if (h_x_in)
+  if (h_x_in) {
+    s->cache0_valid = false;
     if ((rc = mlmcpi_upload(ctx, s->state[0], h_x_in, n)))
       return rc;
+  }
   if ((rc = mlmcpi_sampler_draw(s, nullptr, nullptr)))
     return rc;
   if (h_q) {

@@ -25,6 +25,8 @@ struct mlmcpi_ctx {
   bool own_stream = false;
   uint64_t seed = 0;
   int expcos_envelope = 1; // MLMCPI_OPT_EXPCOS_ENVELOPE: 0 reference, 1 tight (default)
+  int leapfrog_variant = 0; // MLMCPI_OPT_LEAPFROG_VARIANT: 0 TMA row pipeline, 1 register row march, 2 generic
+  int leapfrog_rows = 0;    // MLMCPI_OPT_LEAPFROG_ROWS: rows per block (0 = default)
   uint64_t launches = 0;
   int n_sm = 148;
   std::string err;

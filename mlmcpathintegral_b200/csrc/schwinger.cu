@@ -223,6 +223,122 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// ---- TMA (cp.async.bulk) + mbarrier row pipeline -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile("{\n"
+               ".reg .pred P1;\n"
+               "LAB_WAIT:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+               "@P1 bra DONE;\n"
+               "bra LAB_WAIT;\n"
+               "DONE:\n"
+               "}" ::"r"(smem_u32(bar)), "r"(parity)
+               : "memory");
+}
+
+// Row-pipelined leapfrog step: the hot kernel.  blockDim.x == Mt; the block marches over R
+// rows of one chain.  One elected thread streams the theta and p rows into an S-stage
+// shared-memory ring with cp.async.bulk (TMA, 1-D bulk copies: a lattice row is contiguous),
+// completion is signalled on one mbarrier per stage, so S-2 rows (S-2)*32*Mt bytes per
+// block are in flight without costing registers.  All neighbour accesses -- theta(i+1,j,1),
+// theta(i,j+1,0) -- are shared-memory reads of the staged rows; only sin P(i-1,j) is
+// exchanged between threads (double-buffered, one __syncthreads per row, which also
+// releases the stage of row j-1 for the next bulk copy).
+template <bool DRIFT, int S>
+__global__ void __launch_bounds__(1024)
+    leapfrog_rowpipe_kernel(SW sw, double dt_p, double dt_x, const double *__restrict__ x_in,
+                            double *__restrict__ x_out, double *__restrict__ p, int R, int chunks) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const int i = threadIdx.x;
+  const int ip = wrap_inc(i, Mt), im = wrap_dec(i, Mt);
+  const int chain = blockIdx.x / chunks, chunk = blockIdx.x - chain * chunks;
+  const int j0 = chunk * R;
+  const int nrow = min(R, Mx - j0); // rows this block updates
+  const size_t base = (size_t)chain * Mt * Mx;
+  const double2 *xin = reinterpret_cast<const double2 *>(x_in) + base;
+  double2 *xout = reinterpret_cast<double2 *>(x_out) + base;
+  double2 *pp = reinterpret_cast<double2 *>(p) + base;
+  const uint32_t row_bytes = 16u * Mt;
+  // smem: S stages x (theta row | p row), then sin exchange [2][Mt], then S mbarriers
+  double2 *st_theta = reinterpret_cast<double2 *>(smem_raw);
+  double2 *st_p = st_theta + (size_t)S * Mt;
+  double *sh_s = reinterpret_cast<double *>(st_p + (size_t)S * Mt);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sh_s + 2 * Mt);
+  const double beta = sw.beta;
+
+  if (i == 0) {
+    for (int s = 0; s < S; ++s)
+      mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // logical row q = 0 .. nrow+1 is lattice row j0 - 1 + q; p rows exist for q = 1 .. nrow
+  auto issue = [&](int q) {
+    const int st = q % S;
+    int j = j0 - 1 + q;
+    j = j < 0 ? j + Mx : (j >= Mx ? j - Mx : j);
+    const bool has_p = (q >= 1 && q <= nrow);
+    mbar_expect_tx(&bars[st], has_p ? 2 * row_bytes : row_bytes);
+    bulk_g2s(st_theta + (size_t)st * Mt, xin + (size_t)j * Mt, row_bytes, &bars[st]);
+    if (has_p)
+      bulk_g2s(st_p + (size_t)st * Mt, pp + (size_t)j * Mt, row_bytes, &bars[st]);
+  };
+  const int nq = nrow + 2;
+  if (i == 0)
+    for (int q = 0; q < S && q < nq; ++q)
+      issue(q);
+  // prologue: sin P(i, j0-1) from rows q = 0, 1
+  mbar_wait(&bars[0], 0);
+  mbar_wait(&bars[1 % S], 0);
+  double2 cur = st_theta[(size_t)(1 % S) * Mt + i];
+  double s_prev;
+  {
+    const double2 prev = st_theta[i];
+    s_prev = sin(prev.x + st_theta[ip].y - cur.x - prev.y);
+  }
+  int b = 0;
+  for (int r = 1; r <= nrow; ++r) { // updating logical row q = r
+    const int st = r % S, stn = (r + 1) % S;
+    mbar_wait(&bars[stn], ((r + 1) / S) & 1);
+    const double2 nxt = st_theta[(size_t)stn * Mt + i];
+    const double t1p = st_theta[(size_t)st * Mt + ip].y;
+    double2 pj = st_p[(size_t)st * Mt + i];
+    const double s = sin(cur.x + t1p - nxt.x - cur.y);
+    sh_s[b * Mt + i] = s;
+    __syncthreads(); // sin row visible; every thread is done with logical row r-1
+    if (i == 0 && r - 1 + S < nq)
+      issue(r - 1 + S);
+    const double s_im = sh_s[b * Mt + im];
+    const double F = beta * s;
+    pj.x -= dt_p * (F - beta * s_prev);
+    pj.y -= dt_p * (beta * s_im - F);
+    const size_t g = (size_t)(j0 + r - 1) * Mt + i;
+    pp[g] = pj;
+    if (DRIFT)
+      xout[g] = make_double2(cur.x + dt_x * pj.x, cur.y + dt_x * pj.y);
+    s_prev = s;
+    cur = nxt;
+    b ^= 1;
+  }
+}
+
 // --------------------------------------------------------------------- sweeps
 // colours: 0 {mu=0, j even}, 1 {mu=0, j odd}, 2 {mu=1, i even}, 3 {mu=1, i odd}
 template <bool HEATBATH>
@@ -616,20 +732,32 @@ long long n_coarse_sites(const mlmcpi_model *m) {
 int leapfrog_step(mlmcpi_ctx *ctx, const SW &sw, double dt_p, double dt_x, bool drift,
                   const double *x_in, double *x_out, double *p, int B) {
   const long long nsite = (long long)sw.Mt * sw.Mx;
-  if (sw.Mt <= 1024 && sw.Mt % 32 == 0 && sw.Mx >= 3) {
-    // rows per block: enough blocks for >= ~6 waves, at least 8 rows (prologue = 1 row)
-    int R = 32;
-    while (R > 8 && (long long)cdiv(sw.Mx, R) * B < (long long)ctx->n_sm * 12)
-      R >>= 1;
+  if (sw.Mt <= 1024 && sw.Mt % 32 == 0 && sw.Mx >= 3 && ctx->leapfrog_variant != 2) {
+    // rows per block: small chunks keep the last wave short; the price is one extra
+    // theta row read per chunk end (an L2 hit when the neighbouring chunk is in flight)
+    int R = ctx->leapfrog_rows > 0 ? ctx->leapfrog_rows : (sw.Mt <= 128 ? 4 : 8);
+    if (R > sw.Mx)
+      R = sw.Mx;
     const int chunks = cdiv(sw.Mx, R);
-    const size_t smem = (size_t)4 * sw.Mt * sizeof(double);
-    if (drift)
-      leapfrog_rowmarch_kernel<true><<<chunks * B, sw.Mt, smem, ctx->stream>>>(
-          sw, dt_p, dt_x, x_in, x_out, p, R, chunks);
-    else
-      leapfrog_rowmarch_kernel<false><<<chunks * B, sw.Mt, smem, ctx->stream>>>(
-          sw, dt_p, dt_x, x_in, x_out, p, R, chunks);
-    MLMCPI_LAUNCHED("schwinger::leapfrog_rowmarch");
+    constexpr int S = 6;
+    const size_t smem_pipe = (size_t)S * 32 * sw.Mt + 16 * sw.Mt + 8 * S;
+    if (ctx->leapfrog_variant == 0 && smem_pipe <= 200 * 1024) {
+      auto kern = drift ? leapfrog_rowpipe_kernel<true, S> : leapfrog_rowpipe_kernel<false, S>;
+      if (smem_pipe > 48 * 1024)
+        MLMCPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_pipe));
+      kern<<<chunks * B, sw.Mt, smem_pipe, ctx->stream>>>(sw, dt_p, dt_x, x_in, x_out, p, R, chunks);
+      MLMCPI_LAUNCHED("schwinger::leapfrog_rowpipe");
+    } else {
+      const size_t smem = (size_t)4 * sw.Mt * sizeof(double);
+      if (drift)
+        leapfrog_rowmarch_kernel<true><<<chunks * B, sw.Mt, smem, ctx->stream>>>(
+            sw, dt_p, dt_x, x_in, x_out, p, R, chunks);
+      else
+        leapfrog_rowmarch_kernel<false><<<chunks * B, sw.Mt, smem, ctx->stream>>>(
+            sw, dt_p, dt_x, x_in, x_out, p, R, chunks);
+      MLMCPI_LAUNCHED("schwinger::leapfrog_rowmarch");
+    }
   } else {
     leapfrog_naive_kernel<<<cdiv(nsite * B, 256), 256, 0, ctx->stream>>>(
         sw, dt_p, dt_x, x_in, drift ? x_out : nullptr, p, B);
