@@ -38,11 +38,13 @@ UNIT = "site-updates/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lattice", type=int, default=512)
-    ap.add_argument("--beta", type=float, default=4.0)
+    ap.add_argument("--beta", type=float, default=1024.0,
+                    help="fine-level coupling; default = continuum-limit point beta/P = 2^-8 at 512^2 "
+                         "(ApproximateBesselProduct fill-in); --beta 4 runs the BesselProduct regime")
     ap.add_argument("--levels", type=int, default=3)
     ap.add_argument("--chains", type=int, default=512, help="chains per GPU")
     ap.add_argument("--nt", type=int, default=100)
@@ -171,7 +173,9 @@ def reference_main(a):
 
 # --------------------------------------------------------------------------- GPU arm
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up; only the
+    samples inside the timed window [t0, t1] (host clock) are summarised"""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
@@ -179,15 +183,17 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    def stop(self, t0, t1):
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -195,26 +201,31 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, sm_all = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.f.read().splitlines():
             parts = [s.strip() for s in ln.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(parts[1]), float(parts[2])
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+            mx.append(cmax)
+            sm_all.append(clk)
+            if t0 - 0.02 <= ts <= t1 + 0.02:
+                sm.append(clk)
+                for n, v in zip(names, parts[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
         self.f.close()
         os.unlink(self.f.name)
-        if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+        use = sm if sm else sm_all[-3:]
+        if use:
+            use.sort()
+            out = {"sm_mhz": use[len(use) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm), "window_s": t1 - t0}
         return out
 
 
@@ -264,6 +275,7 @@ def gpu_main(a):
         if world > 1:  # QoI moments + autocorrelation sums: the only inter-GPU traffic
             dist.all_reduce(packed)
 
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(a.warmup):
         step()
     stats.reset()
@@ -271,16 +283,17 @@ def gpu_main(a):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local) if rank == 0 else None
     ctx.profile(True)
     ctx.profile_read()
     launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
     ev0.record()
     for _ in range(a.steps):
         step()
     ev1.record()
     torch.cuda.synchronize()
+    t_wall1 = time.time()
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
@@ -293,7 +306,7 @@ def gpu_main(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
     value = units_per_step * world * a.steps / (ms_max * 1e-3)
     st = mp.Statistics.finalize(packed.cpu().numpy(), k_max)
     p_acc = sampler.p_accept()

@@ -762,6 +762,8 @@ struct mlmcpi_sampler {
   // already known -- bit for bit, the reductions being deterministic.
   double *Sf0 = nullptr, *Scond0 = nullptr;
   bool cache0_valid = false;
+  cudaStream_t copy_stream = nullptr; // H2D stream of mlmcpi_sampler_draw_host
+  cudaEvent_t ev[9] = {};
   int32_t *acc = nullptr, *acc_step = nullptr;          // [B]
   unsigned long long *counters = nullptr;               // [L] accepted chains per level
   uint64_t n_draws = 0;
@@ -780,36 +782,77 @@ static double n_sites(const mlmcpi_model &m) {
 
 // the sampler on the coarsest level: HMCSampler::draw (sampler/hmcsampler.cc:8-19) or
 // OverrelaxedHeatBathSampler::draw (sampler/overrelaxedheatbathsampler.cc:8-31)
-static int coarse_draw(mlmcpi_sampler *s) {
+static int coarse_draw(mlmcpi_sampler *s, int c0, int B) {
   mlmcpi_ctx *ctx = s->ctx;
-  const int l = s->L - 1, B = s->B;
+  const int l = s->L - 1;
   const mlmcpi_model *m = &s->model[l];
+  double *x = s->state[l] + (size_t)c0 * mlmcpi_sample_size(m);
+  int32_t *acc = s->acc + c0, *acc_step = s->acc_step + c0;
+  const uint32_t chain0 = s->chain0 + (uint32_t)c0;
   int rc;
   if (s->prm.kind == MLMCPI_SAMPLER_HMC) {
     const int n_rep = std::max(1, s->prm.n_rep);
     for (int r = 0; r < n_rep; ++r) {
-      int32_t *a = (r == 0) ? s->acc : s->acc_step;
-      if ((rc = mlmcpi_hmc_step(ctx, m, s->prm.nt, s->prm.dt, s->state[l], B, s->chain0,
-                                level_draw(s->draw, l, r), a, nullptr)))
+      int32_t *a = (r == 0) ? acc : acc_step;
+      if ((rc = mlmcpi_hmc_step(ctx, m, s->prm.nt, s->prm.dt, x, B, chain0, level_draw(s->draw, l, r), a,
+                                nullptr)))
         return rc;
       if (r > 0) {
-        or_accept_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, s->acc, s->acc_step);
+        or_accept_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, acc, acc_step);
         MLMCPI_LAUNCHED("or_accept");
       }
     }
     s->work[0] += (double)B * n_rep * (s->prm.nt + 1) * n_sites(*m);
   } else if (s->prm.kind == MLMCPI_SAMPLER_HEATBATH) {
     for (int k = 0; k < s->prm.n_sweep_overrelax; ++k)
-      if ((rc = mlmcpi_overrelax_sweep(ctx, m, s->state[l], B)))
+      if ((rc = mlmcpi_overrelax_sweep(ctx, m, x, B)))
         return rc;
     for (int k = 0; k < s->prm.n_sweep_heatbath; ++k)
-      if ((rc = mlmcpi_heatbath_sweep(ctx, m, s->state[l], B, s->chain0, level_draw(s->draw, l, k))))
+      if ((rc = mlmcpi_heatbath_sweep(ctx, m, x, B, chain0, level_draw(s->draw, l, k))))
         return rc;
-    set_i32_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, s->acc, 1);
+    set_i32_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, acc, 1);
     MLMCPI_LAUNCHED("set_accept");
     s->work[1] += (double)B * (s->prm.n_sweep_overrelax + s->prm.n_sweep_heatbath) * n_sites(*m);
   } else {
     return ctx_fail(ctx, MLMCPI_EINVAL, "unknown sampler kind");
+  }
+  return 0;
+}
+
+// HierarchicalSampler::draw, sampler/hierarchicalsampler.cc:55-81, for the chains
+// [c0, c0 + B) of the batch (n_levels == 1: the plain single-level sampler).  Chains are
+// independent, so a draw of the whole batch may be issued range by range -- which is what
+// lets mlmcpi_sampler_draw_host overlap the upload of one range with the kernels of another.
+static int sampler_draw_range(mlmcpi_sampler *s, int c0, int B, bool cache0_valid) {
+  mlmcpi_ctx *ctx = s->ctx;
+  const int L = s->L;
+  const uint32_t chain0 = s->chain0 + (uint32_t)c0;
+  int32_t *acc = s->acc + c0;
+  auto st = [&](int l) { return s->state[l] + (size_t)c0 * mlmcpi_sample_size(&s->model[l]); };
+  int rc;
+  for (int l = 1; l < L; ++l) // :57-60
+    if ((rc = mlmcpi_restrict(ctx, &s->model[l - 1], st(l - 1), st(l), B)))
+      return rc;
+  if ((rc = coarse_draw(s, c0, B))) // :62-66
+    return rc;
+  count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, acc, s->counters + (L - 1));
+  MLMCPI_LAUNCHED("count_accept");
+  for (int l = L - 2; l >= 0; --l) {
+    // TwoLevelMetropolisStep::set_state, montecarlo/twolevelmetropolisstep.cc:92-97
+    double *Sf = ((l == 0) ? s->Sf0 : s->Sf) + c0, *Scond = ((l == 0) ? s->Scond0 : s->Scond) + c0;
+    if (l > 0 || !cache0_valid) {
+      if ((rc = mlmcpi_action(ctx, &s->model[l], st(l), B, Sf)))
+        return rc;
+      if ((rc = mlmcpi_cond_action(ctx, &s->model[l], st(l), B, Scond)))
+        return rc;
+    }
+    // acc is both the incoming cascade mask and the outgoing accept flag
+    if ((rc = twolevel_step_impl(ctx, &s->model[l], &s->model[l + 1], st(l + 1), st(l), Sf, Scond, B, chain0,
+                                 level_draw(s->draw, l, 0), acc, acc, nullptr)))
+      return rc;
+    count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, acc, s->counters + l);
+    MLMCPI_LAUNCHED("count_accept");
+    s->work[2] += (double)B * n_sites(s->model[l]);
   }
   return 0;
 }
@@ -877,6 +920,12 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
   if (!s)
     return;
   cudaStreamSynchronize(s->ctx->stream);
+  if (s->copy_stream) {
+    cudaStreamSynchronize(s->copy_stream);
+    for (int k = 0; k < 9; ++k)
+      cudaEventDestroy(s->ev[k]);
+    cudaStreamDestroy(s->copy_stream);
+  }
   for (double *d : s->state)
     if (d)
       cudaFree(d);
@@ -904,45 +953,17 @@ int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x) {
   return mlmcpi_copy(s->ctx, s->state[0], d_x, (size_t)mlmcpi_sample_size(&s->model[0]) * s->B);
 }
 
-// HierarchicalSampler::draw, sampler/hierarchicalsampler.cc:55-81 (n_levels == 1: the
-// plain single-level sampler)
 int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
   mlmcpi_ctx *ctx = s->ctx;
-  const int B = s->B, L = s->L;
+  const int B = s->B;
   int rc;
   s->work[0] = s->work[1] = s->work[2] = 0.0;
-  for (int l = 1; l < L; ++l) // :57-60
-    if ((rc = mlmcpi_restrict(ctx, &s->model[l - 1], s->state[l - 1], s->state[l], B)))
-      return rc;
-  if ((rc = coarse_draw(s))) // :62-66
+  if ((rc = sampler_draw_range(s, 0, B, s->cache0_valid)))
     return rc;
-  count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc,
-                                                                         s->counters + (L - 1));
-  MLMCPI_LAUNCHED("count_accept");
-  for (int l = L - 2; l >= 0; --l) {
-    // TwoLevelMetropolisStep::set_state, montecarlo/twolevelmetropolisstep.cc:92-97
-    double *Sf = (l == 0) ? s->Sf0 : s->Sf, *Scond = (l == 0) ? s->Scond0 : s->Scond;
-    if (l > 0 || !s->cache0_valid) {
-      if ((rc = mlmcpi_action(ctx, &s->model[l], s->state[l], B, Sf)))
-        return rc;
-      if ((rc = mlmcpi_cond_action(ctx, &s->model[l], s->state[l], B, Scond)))
-        return rc;
-    }
-    // s->acc is both the incoming cascade mask and the outgoing accept flag
-    if ((rc = twolevel_step_impl(ctx, &s->model[l], &s->model[l + 1], s->state[l + 1], s->state[l],
-                                 Sf, Scond, B, s->chain0, level_draw(s->draw, l, 0), s->acc, s->acc,
-                                 nullptr)))
-      return rc;
-    if (l == 0)
-      s->cache0_valid = true;
-    count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc,
-                                                                           s->counters + l);
-    MLMCPI_LAUNCHED("count_accept");
-    s->work[2] += (double)B * n_sites(s->model[l]);
-  }
+  s->cache0_valid = s->L > 1;
   s->draw++;
   s->n_draws++;
-  if (d_x_out) // :78-80
+  if (d_x_out) // hierarchicalsampler.cc:78-80
     if ((rc = launch_masked_copy(ctx, d_x_out, s->state[0], (size_t)mlmcpi_sample_size(&s->model[0]), B,
                                  s->acc)))
       return rc;
@@ -952,23 +973,54 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
   return 0;
 }
 
+// Host-buffer entry point.  With an input state the batch is cut into ranges of chains: the
+// H2D copy of range k+1 runs on a copy stream while the kernels of range k run on the
+// context's stream (chains are independent), so a step costs max(copy, compute) + one
+// range instead of copy + compute.
 int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, double *h_q,
                              double *h_x_out) {
   mlmcpi_ctx *ctx = s->ctx;
-  const size_t n = (size_t)mlmcpi_sample_size(&s->model[0]) * s->B;
+  const size_t nd = (size_t)mlmcpi_sample_size(&s->model[0]);
+  const size_t n = nd * s->B;
   int rc;
-  if (h_x_in) {
-    s->cache0_valid = false;
-    if ((rc = mlmcpi_upload(ctx, s->state[0], h_x_in, n)))
+  if (!h_x_in) {
+    if ((rc = mlmcpi_sampler_draw(s, nullptr, nullptr)))
       return rc;
+    if (h_q)
+      if ((rc = mlmcpi_qoi(ctx, &s->model[0], qoi, s->state[0], s->B, s->q, nullptr)))
+        return rc;
+  } else {
+    const int n_ranges = std::min(s->B, 8);
+    if (!s->copy_stream) {
+      MLMCPI_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 9; ++k)
+        MLMCPI_CUDA(cudaEventCreateWithFlags(&s->ev[k], cudaEventDisableTiming));
+    }
+    // uploads must not overtake earlier work of the compute stream on state[0]
+    MLMCPI_CUDA(cudaEventRecord(s->ev[8], ctx->stream));
+    MLMCPI_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev[8], 0));
+    s->work[0] = s->work[1] = s->work[2] = 0.0;
+    for (int k = 0; k < n_ranges; ++k) {
+      const int c0 = (int)((long long)s->B * k / n_ranges), c1 = (int)((long long)s->B * (k + 1) / n_ranges);
+      MLMCPI_CUDA(cudaMemcpyAsync(s->state[0] + c0 * nd, h_x_in + c0 * nd, (size_t)(c1 - c0) * nd * sizeof(double),
+                                  cudaMemcpyHostToDevice, s->copy_stream));
+      MLMCPI_CUDA(cudaEventRecord(s->ev[k], s->copy_stream));
+    }
+    for (int k = 0; k < n_ranges; ++k) {
+      const int c0 = (int)((long long)s->B * k / n_ranges), c1 = (int)((long long)s->B * (k + 1) / n_ranges);
+      MLMCPI_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev[k], 0));
+      if ((rc = sampler_draw_range(s, c0, c1 - c0, false)))
+        return rc;
+      if (h_q)
+        if ((rc = mlmcpi_qoi(ctx, &s->model[0], qoi, s->state[0] + c0 * nd, c1 - c0, s->q + c0, nullptr)))
+          return rc;
+    }
+    s->cache0_valid = s->L > 1;
+    s->draw++;
+    s->n_draws++;
   }
-  if ((rc = mlmcpi_sampler_draw(s, nullptr, nullptr)))
-    return rc;
-  if (h_q) {
-    if ((rc = mlmcpi_qoi(ctx, &s->model[0], qoi, s->state[0], s->B, s->q, nullptr)))
-      return rc;
+  if (h_q)
     MLMCPI_CUDA(cudaMemcpyAsync(h_q, s->q, sizeof(double) * s->B, cudaMemcpyDeviceToHost, ctx->stream));
-  }
   if (h_x_out)
     MLMCPI_CUDA(cudaMemcpyAsync(h_x_out, s->state[0], n * sizeof(double), cudaMemcpyDeviceToHost,
                                 ctx->stream));

@@ -132,6 +132,12 @@ __device__ __forceinline__ double rng_angle2(Rng &r, double &second) {
 __device__ __forceinline__ double mod_2pi(const double x) {
   return x - 2. * M_PI * floor(0.5 * (x + M_PI) / M_PI);
 }
+// the same map with the division replaced by a multiplication with 1/(2 pi): may pick the
+// other representative when x is within an ulp of an odd multiple of pi (equal modulo
+// 2 pi).  Used only by the stochastic kernels, whose outputs are angles modulo 2 pi.
+__device__ __forceinline__ double mod_2pi_fast(const double x) {
+  return x - 2. * M_PI * floor((x + M_PI) * (0.5 / M_PI));
+}
 // integer winding number n with x = mod_2pi(x) + 2 pi n
 __device__ __forceinline__ double winding(const double x) { return floor(0.5 * (x + M_PI) / M_PI); }
 
@@ -269,7 +275,7 @@ __device__ __forceinline__ double expcos_draw(Rng &r, const double beta, const d
       }
     }
   }
-  return mod_2pi(x + 0.5 * (x_p + x_m) + (fabs(dx) > M_PI) * M_PI);
+  return mod_2pi_fast(x + 0.5 * (x_p + x_m) + (fabs(dx) > M_PI) * M_PI);
 }
 
 // distribution/expcosdistribution.cc:7-21
@@ -378,9 +384,11 @@ __device__ __forceinline__ void approx_N_p_sigma2inv(const double beta, const do
   }
 }
 
-// distribution/approximatebesselproductdistribution.hh:81-106
+// distribution/approximatebesselproductdistribution.hh:81-106; xi: the uniform variate that
+// selects the mode (supplied by the caller, which gets it for free from the Philox call
+// that also yields the step-2 split angle), the normal comes from one rng_normal2
 __device__ __forceinline__ double approxbessel_draw(Rng &r, const double beta, const double x_p,
-                                                    const double x_m) {
+                                                    const double x_m, const double xi) {
   double x0 = x_p - x_m;
   double sign_flip = (x0 < 0) ? -1 : +1;
   x0 *= sign_flip;
@@ -390,8 +398,7 @@ __device__ __forceinline__ double approxbessel_draw(Rng &r, const double beta, c
   }
   double N_p, sigma2_p_inv, sigma2_m_inv;
   approx_N_p_sigma2inv(beta, x0, N_p, sigma2_p_inv, sigma2_m_inv);
-  double xi, unused, z0, z1;
-  rng_uniform2(r, xi, unused);
+  double z0, z1;
   rng_normal2(r, z0, z1);
   double sigma, xshift;
   if (xi <= N_p) {
@@ -402,7 +409,7 @@ __device__ __forceinline__ double approxbessel_draw(Rng &r, const double beta, c
     xshift = M_PI;
   }
   const double x = sigma * z0 + 0.5 * x0 - xshift;
-  return mod_2pi(sign_flip * x + x_m);
+  return mod_2pi_fast(sign_flip * x + x_m);
 }
 
 // distribution/approximatebesselproductdistribution.cc:7-35

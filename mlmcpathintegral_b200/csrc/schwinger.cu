@@ -450,10 +450,10 @@ __global__ void fill_both_step1_kernel(SW sw, double *x_all, int B, uint32_t cha
   Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, chain0 + (uint32_t)chain, cell);
   double dth_s;
   const double dth_t = rng_angle2(r, dth_s);
-  TH(x, 2 * i, 2 * j, 0) = mod_2pi(TH(x, 2 * i, 2 * j, 0) + dth_t);
-  TH(x, 2 * i + 1, 2 * j, 0) = mod_2pi(TH(x, 2 * i + 1, 2 * j, 0) - dth_t);
-  TH(x, 2 * i, 2 * j, 1) = mod_2pi(TH(x, 2 * i, 2 * j, 1) + dth_s);
-  TH(x, 2 * i, 2 * j + 1, 1) = mod_2pi(TH(x, 2 * i, 2 * j + 1, 1) - dth_s);
+  TH(x, 2 * i, 2 * j, 0) = mod_2pi_fast(TH(x, 2 * i, 2 * j, 0) + dth_t);
+  TH(x, 2 * i + 1, 2 * j, 0) = mod_2pi_fast(TH(x, 2 * i + 1, 2 * j, 0) - dth_t);
+  TH(x, 2 * i, 2 * j, 1) = mod_2pi_fast(TH(x, 2 * i, 2 * j, 1) + dth_s);
+  TH(x, 2 * i, 2 * j + 1, 1) = mod_2pi_fast(TH(x, 2 * i, 2 * j + 1, 1) - dth_s);
 }
 
 // the interior of one coarse cell given its 4 own and 4 neighbouring perimeter
@@ -472,25 +472,27 @@ __device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double be
                                                    uint64_t draw, uint32_t gchain, int Mt, int i,
                                                    int j, int cell) {
   {
-    const double theta_p = mod_2pi(c.A1 + c.R0 + c.R1 - c.T1);
-    const double theta_m = mod_2pi(c.B0 + c.B1 + c.T0 - c.A0);
+    const double theta_p = mod_2pi_fast(c.A1 + c.R0 + c.R1 - c.T1);
+    const double theta_m = mod_2pi_fast(c.B0 + c.B1 + c.T0 - c.A0);
     Rng r = rng_init(seed, MLMCPI_STREAM_FILL2, draw, gchain, cell);
-    double unused;
-    const double dtheta = rng_angle2(r, unused);
-    const double theta_tilde = APPROX ? approxbessel_draw(r, beta, theta_p, theta_m)
+    // first call of the stream: (split angle, mode selector of the approximate distribution)
+    double u0, u1;
+    rng_uniform2(r, u0, u1);
+    const double dtheta = -M_PI + 2. * M_PI * u0;
+    const double theta_tilde = APPROX ? approxbessel_draw(r, beta, theta_p, theta_m, u1)
                                       : besselproduct_draw(r, bp, theta_p, theta_m);
-    c.V0 = mod_2pi(0.5 * theta_tilde + dtheta);
-    c.V1 = mod_2pi(0.5 * theta_tilde - dtheta);
+    c.V0 = mod_2pi_fast(0.5 * theta_tilde + dtheta);
+    c.V1 = mod_2pi_fast(0.5 * theta_tilde - dtheta);
   }
   {
-    const double theta_p = mod_2pi(c.A0 + c.V0 - c.B0);
-    const double theta_m = mod_2pi(c.B1 + c.T0 - c.V1);
+    const double theta_p = mod_2pi_fast(c.A0 + c.V0 - c.B0);
+    const double theta_m = mod_2pi_fast(c.B1 + c.T0 - c.V1);
     Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i);
     c.H0 = expcos_draw(r, beta, theta_p, theta_m, envelope);
   }
   {
-    const double theta_p = mod_2pi(c.A1 + c.R0 - c.V0);
-    const double theta_m = mod_2pi(c.V1 + c.T1 - c.R1);
+    const double theta_p = mod_2pi_fast(c.A1 + c.R0 - c.V0);
+    const double theta_m = mod_2pi_fast(c.V1 + c.T1 - c.R1);
     Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i + 1);
     c.H1 = expcos_draw(r, beta, theta_p, theta_m, envelope);
   }
@@ -554,24 +556,24 @@ __global__ void prolong_fill_both_kernel(SW sw, BesselProductConst bp, const dou
     Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell);
     double dth_s;
     const double dth_t = rng_angle2(r, dth_s);
-    c.A0 = mod_2pi(0.5 * own.x + dth_t);
-    c.A1 = mod_2pi(0.5 * own.x - dth_t);
-    c.B0 = mod_2pi(0.5 * own.y + dth_s);
-    c.B1 = mod_2pi(0.5 * own.y - dth_s);
+    c.A0 = mod_2pi_fast(0.5 * own.x + dth_t);
+    c.A1 = mod_2pi_fast(0.5 * own.x - dth_t);
+    c.B0 = mod_2pi_fast(0.5 * own.y + dth_s);
+    c.B1 = mod_2pi_fast(0.5 * own.y - dth_s);
   }
   {
     Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell_r);
     double dth_s;
     (void)rng_angle2(r, dth_s);
-    c.R0 = mod_2pi(0.5 * cr + dth_s);
-    c.R1 = mod_2pi(0.5 * cr - dth_s);
+    c.R0 = mod_2pi_fast(0.5 * cr + dth_s);
+    c.R1 = mod_2pi_fast(0.5 * cr - dth_s);
   }
   {
     Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell_t);
     double dth_s;
     const double dth_t = rng_angle2(r, dth_s);
-    c.T0 = mod_2pi(0.5 * ct + dth_t);
-    c.T1 = mod_2pi(0.5 * ct - dth_t);
+    c.T0 = mod_2pi_fast(0.5 * ct + dth_t);
+    c.T1 = mod_2pi_fast(0.5 * ct - dth_t);
   }
   fill_cell_interior<APPROX>(c, sw.beta, sw.envelope, bp, seed, draw, gchain, Mt, i, j, cell);
   // rows 2j and 2j+1, sites 2i and 2i+1: four aligned double2 stores
@@ -604,25 +606,25 @@ __global__ void fill_semi_kernel(SW sw, int ctype, int phase, double *x_all, int
     double unused;
     const double dtheta = rng_angle2(r, unused);
     if (temporal) {
-      TH(x, 2 * i, j, 0) = mod_2pi(TH(x, 2 * i, j, 0) + dtheta);
-      TH(x, 2 * i + 1, j, 0) = mod_2pi(TH(x, 2 * i + 1, j, 0) - dtheta);
+      TH(x, 2 * i, j, 0) = mod_2pi_fast(TH(x, 2 * i, j, 0) + dtheta);
+      TH(x, 2 * i + 1, j, 0) = mod_2pi_fast(TH(x, 2 * i + 1, j, 0) - dtheta);
     } else {
-      TH(x, i, 2 * j, 1) = mod_2pi(TH(x, i, 2 * j, 1) + dtheta);
-      TH(x, i, 2 * j + 1, 1) = mod_2pi(TH(x, i, 2 * j + 1, 1) - dtheta);
+      TH(x, i, 2 * j, 1) = mod_2pi_fast(TH(x, i, 2 * j, 1) + dtheta);
+      TH(x, i, 2 * j + 1, 1) = mod_2pi_fast(TH(x, i, 2 * j + 1, 1) - dtheta);
     }
   } else {
     Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, cell);
     if (temporal) {
       const int jp = wrap_inc(j, Mx), i2 = wrap_inc(2 * i + 1, Mt);
-      const double theta_p = mod_2pi(TH(x, 2 * i, j, 1) + TH(x, 2 * i, jp, 0) - TH(x, 2 * i, j, 0));
+      const double theta_p = mod_2pi_fast(TH(x, 2 * i, j, 1) + TH(x, 2 * i, jp, 0) - TH(x, 2 * i, j, 0));
       const double theta_m =
-          mod_2pi(TH(x, 2 * i + 1, j, 0) + TH(x, i2, j, 1) - TH(x, 2 * i + 1, jp, 0));
+          mod_2pi_fast(TH(x, 2 * i + 1, j, 0) + TH(x, i2, j, 1) - TH(x, 2 * i + 1, jp, 0));
       TH(x, 2 * i + 1, j, 1) = expcos_draw(r, sw.beta, theta_p, theta_m, sw.envelope);
     } else {
       const int ip = wrap_inc(i, Mt), j2 = wrap_inc(2 * j + 1, Mx);
-      const double theta_p = mod_2pi(TH(x, i, 2 * j, 0) + TH(x, ip, 2 * j, 1) - TH(x, i, 2 * j, 1));
+      const double theta_p = mod_2pi_fast(TH(x, i, 2 * j, 0) + TH(x, ip, 2 * j, 1) - TH(x, i, 2 * j, 1));
       const double theta_m =
-          mod_2pi(TH(x, i, 2 * j + 1, 1) + TH(x, i, j2, 0) - TH(x, ip, 2 * j + 1, 1));
+          mod_2pi_fast(TH(x, i, 2 * j + 1, 1) + TH(x, i, j2, 0) - TH(x, ip, 2 * j + 1, 1));
       TH(x, i, 2 * j + 1, 0) = expcos_draw(r, sw.beta, theta_p, theta_m, sw.envelope);
     }
   }

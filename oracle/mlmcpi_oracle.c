@@ -1008,10 +1008,11 @@ double orc_besselproduct_draw(orc_rng *r, double beta, double x_p, double x_m) {
   return orc_mod_2pi(sign_flip * x + x_p);
 }
 
-/* distribution/approximatebesselproductdistribution.hh:81-106: one
- * orc_rng_uniform2 (first variate selects the mode) + one orc_rng_normal2
- * (first variate used) */
-double orc_approxbessel_draw(orc_rng *r, double beta, double x_p, double x_m) {
+/* distribution/approximatebesselproductdistribution.hh:81-106 with the mode-selecting
+ * uniform variate xi supplied by the caller; the normal is the first variate of one
+ * orc_rng_normal2 */
+static double approxbessel_draw_xi(orc_rng *r, double beta, double x_p, double x_m,
+                                   double xi) {
   double x0 = x_p - x_m;
   double sign_flip = (x0 < 0) ? -1 : +1;
   x0 *= sign_flip;
@@ -1021,8 +1022,7 @@ double orc_approxbessel_draw(orc_rng *r, double beta, double x_p, double x_m) {
   }
   double N_p, sigma2_p_inv, sigma2_m_inv;
   approx_N_p_sigma2inv(beta, x0, &N_p, &sigma2_p_inv, &sigma2_m_inv);
-  double xi, unused, z0, z1;
-  orc_rng_uniform2(r, &xi, &unused);
+  double z0, z1;
   orc_rng_normal2(r, &z0, &z1);
   double sigma, xshift;
   if (xi <= N_p) {
@@ -1034,6 +1034,13 @@ double orc_approxbessel_draw(orc_rng *r, double beta, double x_p, double x_m) {
   }
   const double x = sigma * z0 + 0.5 * x0 - xshift;
   return orc_mod_2pi(sign_flip * x + x_m);
+}
+
+/* stand-alone draw: xi = first variate of one orc_rng_uniform2 */
+double orc_approxbessel_draw(orc_rng *r, double beta, double x_p, double x_m) {
+  double xi, unused;
+  orc_rng_uniform2(r, &xi, &unused);
+  return approxbessel_draw_xi(r, beta, x_p, x_m, xi);
 }
 
 /* ================================================ conditioned fine actions */
@@ -1560,12 +1567,16 @@ void orc_fill(const orc_model *fine, uint64_t seed, uint64_t draw, uint32_t chai
               x[LNK(2 * i, 2 * j + 2, 0)] - x[LNK(2 * i, 2 * j, 0)]);
           orc_rng r;
           orc_rng_init(&r, seed, ORC_STREAM_FILL2, draw, chain, (Mt / 2) * j + i);
-          const double dtheta = uniform_angle(&r, NULL);
+          /* first call of the stream: (split angle, mode selector of the approximate
+           * distribution) */
+          double u0, u1;
+          orc_rng_uniform2(&r, &u0, &u1);
+          const double dtheta = -M_PI + 2. * M_PI * u0;
           double theta_tilde;
           if (beta <= 8.0)
             theta_tilde = orc_besselproduct_draw(&r, beta, theta_p, theta_m);
           else
-            theta_tilde = orc_approxbessel_draw(&r, beta, theta_p, theta_m);
+            theta_tilde = approxbessel_draw_xi(&r, beta, theta_p, theta_m, u1);
           x[LNK(2 * i + 1, 2 * j, 1)] = orc_mod_2pi(0.5 * theta_tilde + dtheta);
           x[LNK(2 * i + 1, 2 * j + 1, 1)] = orc_mod_2pi(0.5 * theta_tilde - dtheta);
         }
