@@ -266,7 +266,7 @@ def gpu_main(a):
                 break
             dt0 *= 0.5
         tuned = {"dt": dt_t, "p_accept": p_t, "converged": ok}
-    packed = ctx.empty(6 + k_max)
+    packed = ctx.empty(8 + k_max)
 
     def step():
         sampler.draw(x)
@@ -278,7 +278,7 @@ def gpu_main(a):
     clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(a.warmup):
         step()
-    stats.reset()
+    stats.hard_reset()
     ctx.sync()
     if world > 1:
         dist.barrier()

@@ -195,6 +195,10 @@ typedef struct mlmcpi_sampler_params {
   int n_rep;
   int n_sweep_overrelax; /* heatbath (sampler/overrelaxedheatbathsampler.hh)        */
   int n_sweep_heatbath;
+  int multilevel;        /* 0: HierarchicalSampler cascade; 1: MultilevelSampler level walk
+                            (sampler/multilevelsampler.cc:71-112), needs n_levels > 1      */
+  int qoi;               /* multilevel: QoI of the per-level statistics Q_sampler[l]        */
+  int n_autocorr_window; /* multilevel: window of those statistics (default 20)             */
 } mlmcpi_sampler_params;
 int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine,
                           const mlmcpi_sampler_params *prm, int B, uint32_t chain0,
@@ -220,22 +224,61 @@ int mlmcpi_sampler_autotune(mlmcpi_sampler *s, double p_accept_target, int n_rou
                             double *dt_out, double *p_accept_out);
 int mlmcpi_sampler_set_dt(mlmcpi_sampler *s, double dt);
 
+/* time n_meas batched draws with CUDA events: microseconds per chain-sample
+ * (cost_per_sample of hierarchicalsampler.cc:45-52, multilevelsampler.cc:60-67) */
+int mlmcpi_sampler_cost(mlmcpi_sampler *s, int n_meas, double *usec_per_sample);
+/* multilevel sampler: out[l] = average number of draws between independent samples on
+ * level l (t_indep), out[n_levels + l] = number of independent samples (n_indep) */
+int mlmcpi_sampler_indep(const mlmcpi_sampler *s, double *out);
+
+/* ---- MonteCarloMultiLevel (montecarlo/montecarlomultilevel.cc:7-204), batched ------
+ * Level l < L-1 owns B chains of (coarse sampler on level l+1, two-level step, Y_l =
+ * Q_l - Q_{l+1}); level L-1 owns B chains of the coarsest sampler (Y = Q).  The B chains
+ * play the role the MPI ranks would have: Statistics are averaged over them. */
+typedef struct mlmcpi_mlmc mlmcpi_mlmc;
+typedef struct mlmcpi_mlmc_params {
+  int n_level;           /* multilevelmc: n_level                                     */
+  int n_burnin;          /* multilevelmc: n_burnin (batched draws per level)           */
+  double epsilon;        /* multilevelmc: epsilon (tolerance on the root-mean-square error) */
+  int n_autocorr_window; /* statistics: n_autocorr_window                             */
+  int n_min_samples_qoi; /* statistics: n_min_samples_qoi                             */
+  int qoi;               /* MLMCPI_QOI_*                                              */
+  int max_iterations;    /* safety bound on the adaptive do-while loop (0: none)      */
+  mlmcpi_sampler_params sampler; /* the sampler built on every coarse level; its n_levels
+                            is the hierarchy depth n_max_level counted from the FINE action */
+} mlmcpi_mlmc_params;
+int mlmcpi_mlmc_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_mlmc_params *prm,
+                       int B, uint32_t chain0, mlmcpi_mlmc **out);
+void mlmcpi_mlmc_destroy(mlmcpi_mlmc *m);
+/* MonteCarloMultiLevel::evaluate (synchronous: the sample allocation is decided on the host) */
+int mlmcpi_mlmc_evaluate(mlmcpi_mlmc *m);
+/* numerical_result() / statistical_error() and the per-level table of
+ * show_detailed_statistics(): level_out[l][6] = {samples, mean of Y_l, variance, tau_int,
+ * effective cost (usec), n_target} */
+int mlmcpi_mlmc_result(mlmcpi_mlmc *m, double *value, double *error, double *level_out);
+
 /* ---- statistics (common/statistics.cc:4-97), one accumulator per chain ---- */
 typedef struct mlmcpi_stats mlmcpi_stats;
 int mlmcpi_stats_create(mlmcpi_ctx *ctx, int k_max, int B, mlmcpi_stats **st);
 void mlmcpi_stats_destroy(mlmcpi_stats *st);
+/* Statistics::reset (short-term mean and sample count only) / Statistics::hard_reset */
 int mlmcpi_stats_reset(mlmcpi_stats *st);
+int mlmcpi_stats_hard_reset(mlmcpi_stats *st);
 /* Statistics::record_sample for every chain from d_q[B] */
 int mlmcpi_stats_record(mlmcpi_stats *st, const double *d_q);
 /* packed moment vector summed over the chains of this batch:
- * {n_chains, n_samples (all chains), sum avg, sum avg2, sum avg3, sum avg4, sum S_0..S_{k_max-1}}
+ * {n_chains, long-term samples (all chains), short-term samples (all chains), sum avg,
+ *  sum avg_longterm, sum avg2_longterm, sum avg3_longterm, sum avg4_longterm,
+ *  sum S_0..S_{k_max-1}}
  * (what Statistics allreduces across MPI ranks, statistics.cc:30-35,64-79);
- * length 6 + k_max.  Sum it over GPUs (NCCL allreduce) and hand it to _finalize. */
+ * length 8 + k_max, every entry additive.  Sum it over GPUs (NCCL allreduce) and hand it
+ * to _finalize. */
 int mlmcpi_stats_pack(mlmcpi_stats *st, double *h_packed);
 /* the same vector left in device memory (no synchronisation), ready for ncclAllReduce */
 int mlmcpi_stats_pack_device(mlmcpi_stats *st, double *d_packed);
 int mlmcpi_stats_packed_size(int k_max);
-/* out = {average, variance, variance_error, tau_int, error, total samples} */
+/* out = {average, variance, variance_error, tau_int, error, samples}: average over the
+ * short-term window, variance / tau_int over the long-term one, as in the reference */
 int mlmcpi_stats_finalize(const double *h_packed, int k_max, double out[6]);
 
 #ifdef __cplusplus

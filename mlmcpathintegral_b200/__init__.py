@@ -5,4 +5,4 @@ C-ABI of include/mlmcpi.h).  Importing the package loads that library and raises
 is missing: there is no CPU path."""
 from . import _lib  # noqa: F401  (raises ImportError when libmlmcpi.so is absent)
 from .api import *  # noqa: F401,F403
-from .api import Context, MlmcpiError, Sampler, Statistics  # noqa: F401
+from .api import Context, MlmcpiError, MultilevelMC, Sampler, Statistics  # noqa: F401

@@ -32,7 +32,15 @@ class SamplerParams(C.Structure):
     """mlmcpi_sampler_params"""
     _fields_ = [("kind", C.c_int), ("n_levels", C.c_int), ("renorm", C.c_int), ("ctype", C.c_int),
                 ("nt", C.c_int), ("dt", C.c_double), ("n_rep", C.c_int),
-                ("n_sweep_overrelax", C.c_int), ("n_sweep_heatbath", C.c_int)]
+                ("n_sweep_overrelax", C.c_int), ("n_sweep_heatbath", C.c_int),
+                ("multilevel", C.c_int), ("qoi", C.c_int), ("n_autocorr_window", C.c_int)]
+
+
+class MlmcParams(C.Structure):
+    """mlmcpi_mlmc_params"""
+    _fields_ = [("n_level", C.c_int), ("n_burnin", C.c_int), ("epsilon", C.c_double),
+                ("n_autocorr_window", C.c_int), ("n_min_samples_qoi", C.c_int), ("qoi", C.c_int),
+                ("max_iterations", C.c_int), ("sampler", SamplerParams)]
 
 
 # every symbol include/mlmcpi.h declares: name -> (restype, argtypes)
@@ -91,9 +99,16 @@ SIGNATURES = {
     "mlmcpi_sampler_work": (_i, [_vp, _dp]),
     "mlmcpi_sampler_autotune": (_i, [_vp, _d, _i, _i, _dp, _dp]),
     "mlmcpi_sampler_set_dt": (_i, [_vp, _d]),
+    "mlmcpi_sampler_cost": (_i, [_vp, _i, _dp]),
+    "mlmcpi_sampler_indep": (_i, [_vp, _dp]),
+    "mlmcpi_mlmc_create": (_i, [_vp, _MP, C.POINTER(MlmcParams), _i, _u32, C.POINTER(_vp)]),
+    "mlmcpi_mlmc_destroy": (None, [_vp]),
+    "mlmcpi_mlmc_evaluate": (_i, [_vp]),
+    "mlmcpi_mlmc_result": (_i, [_vp, _dp, _dp, _dp]),
     "mlmcpi_stats_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
     "mlmcpi_stats_destroy": (None, [_vp]),
     "mlmcpi_stats_reset": (_i, [_vp]),
+    "mlmcpi_stats_hard_reset": (_i, [_vp]),
     "mlmcpi_stats_record": (_i, [_vp, _vp]),
     "mlmcpi_stats_pack": (_i, [_vp, _dp]),
     "mlmcpi_stats_pack_device": (_i, [_vp, _vp]),

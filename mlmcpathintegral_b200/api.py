@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (COARSEN_ALTERNATE, COARSEN_BOTH, COARSEN_ROTATE, COARSEN_SPATIAL,  # noqa: F401
                    COARSEN_TEMPORAL, GFF, HO, QOI_AVG_PLAQUETTE, QOI_PHI2, QOI_ROTOR_CHI,
                    QOI_SCHWINGER_CHI, QOI_X2, QUARTIC, RENORM_NONE, RENORM_PERTURBATIVE, ROTOR,
-                   SAMPLER_HEATBATH, SAMPLER_HMC, SCHWINGER, Model, SamplerParams)
+                   SAMPLER_HEATBATH, SAMPLER_HMC, SCHWINGER, MlmcParams, Model, SamplerParams)
 
 L = _lib.lib
 
@@ -236,11 +236,12 @@ class Sampler:
 
     def __init__(self, ctx, fine, B, kind=SAMPLER_HMC, n_levels=1, renorm=RENORM_NONE,
                  ctype=COARSEN_BOTH, nt=100, dt=0.1, n_rep=1, n_sweep_overrelax=10,
-                 n_sweep_heatbath=1, chain0=0):
+                 n_sweep_heatbath=1, chain0=0, multilevel=False, qoi=QOI_X2, n_autocorr_window=20):
         self.ctx, self.fine, self.B, self.n_levels = ctx, fine, B, n_levels
         prm = SamplerParams(kind=kind, n_levels=n_levels, renorm=renorm, ctype=ctype, nt=nt, dt=dt,
                             n_rep=n_rep, n_sweep_overrelax=n_sweep_overrelax,
-                            n_sweep_heatbath=n_sweep_heatbath)
+                            n_sweep_heatbath=n_sweep_heatbath, multilevel=int(multilevel), qoi=qoi,
+                            n_autocorr_window=n_autocorr_window)
         h = C.c_void_p()
         ctx._ck(L.mlmcpi_sampler_create(ctx.h, C.byref(fine), C.byref(prm), B, chain0, C.byref(h)))
         self.h = h
@@ -293,10 +294,67 @@ class Sampler:
     def set_dt(self, dt):
         L.mlmcpi_sampler_set_dt(self.h, dt)
 
+    def cost_per_sample(self, n_meas=10):
+        """microseconds per chain-sample (CUDA events over n_meas batched draws)"""
+        v = C.c_double()
+        self.ctx._ck(L.mlmcpi_sampler_cost(self.h, n_meas, C.byref(v)))
+        return v.value
+
+    def independence(self):
+        """multilevel sampler: (t_indep[l], n_indep[l]) per level"""
+        out = (C.c_double * (2 * self.n_levels))()
+        self.ctx._ck(L.mlmcpi_sampler_indep(self.h, out))
+        return list(out[:self.n_levels]), [int(v) for v in out[self.n_levels:]]
+
     def work(self):
         out = (C.c_double * 3)()
         L.mlmcpi_sampler_work(self.h, out)
         return dict(leapfrog_site_steps=out[0], sweep_site_updates=out[1], filled_fine_sites=out[2])
+
+
+class MultilevelMC:
+    """MonteCarloMultiLevel (montecarlo/montecarlomultilevel.cc), batched over B chains"""
+
+    def __init__(self, ctx, fine, B, n_level, epsilon, qoi, n_burnin=100, n_autocorr_window=20,
+                 n_min_samples_qoi=100, max_iterations=0, chain0=0, **sampler_kw):
+        self.ctx, self.n_level = ctx, n_level
+        sp = dict(kind=SAMPLER_HMC, n_levels=n_level, renorm=RENORM_NONE, ctype=COARSEN_BOTH, nt=100,
+                  dt=0.1, n_rep=1, n_sweep_overrelax=10, n_sweep_heatbath=1, multilevel=0, qoi=qoi,
+                  n_autocorr_window=n_autocorr_window)
+        sp.update(sampler_kw)
+        prm = MlmcParams(n_level=n_level, n_burnin=n_burnin, epsilon=epsilon,
+                         n_autocorr_window=n_autocorr_window, n_min_samples_qoi=n_min_samples_qoi,
+                         qoi=qoi, max_iterations=max_iterations, sampler=SamplerParams(**sp))
+        h = C.c_void_p()
+        ctx._ck(L.mlmcpi_mlmc_create(ctx.h, C.byref(fine), C.byref(prm), B, chain0, C.byref(h)))
+        self.h = h
+        ctx._children.add(self)
+
+    def close(self):
+        if self.h:
+            L.mlmcpi_mlmc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def evaluate(self):
+        """returns True when the sample allocation converged"""
+        rc = L.mlmcpi_mlmc_evaluate(self.h)
+        if rc not in (0, 1):
+            self.ctx._ck(rc)
+        return rc == 0
+
+    def result(self):
+        v, e = C.c_double(), C.c_double()
+        lv = (C.c_double * (6 * self.n_level))()
+        self.ctx._ck(L.mlmcpi_mlmc_result(self.h, C.byref(v), C.byref(e), lv))
+        keys = ("samples", "mean", "variance", "tau_int", "cost_eff_usec", "n_target")
+        levels = [dict(zip(keys, lv[6 * l:6 * l + 6])) for l in range(self.n_level)]
+        return v.value, e.value, levels
 
 
 class Statistics:
@@ -321,7 +379,11 @@ class Statistics:
             pass
 
     def reset(self):
+        """Statistics::reset: clears the short-term mean and sample count only"""
         self.ctx._ck(L.mlmcpi_stats_reset(self.h))
+
+    def hard_reset(self):
+        self.ctx._ck(L.mlmcpi_stats_hard_reset(self.h))
 
     def record(self, q):
         self.ctx._ck(L.mlmcpi_stats_record(self.h, _ptr(q)))

@@ -768,7 +768,22 @@ struct mlmcpi_sampler {
   unsigned long long *counters = nullptr;               // [L] accepted chains per level
   uint64_t n_draws = 0;
   double work[3] = {0, 0, 0};
+  // MultilevelSampler (sampler/multilevelsampler.hh): per-level statistics of the sampler
+  // QoI, persistent two-level caches, and the independence bookkeeping of the level walk
+  std::vector<mlmcpi_stats *> stats_sampler;
+  std::vector<double *> SfL, ScondL; // [L-1][B]
+  std::vector<double> t_indep;
+  std::vector<int> n_indep, t_sampler;
 };
+
+// tau_int / variance / ... of a device statistics object (host synchronisation)
+static int stats_query(mlmcpi_stats *st, int k_max, double out[6]) {
+  std::vector<double> packed(mlmcpi_stats_packed_size(k_max));
+  int rc = mlmcpi_stats_pack(st, packed.data());
+  if (rc)
+    return rc;
+  return mlmcpi_stats_finalize(packed.data(), k_max, out);
+}
 
 static uint64_t level_draw(uint64_t draw, int level, int rep) {
   return (draw << 12) | ((uint64_t)level << 8) | (uint64_t)(rep & 0xff);
@@ -857,6 +872,52 @@ static int sampler_draw_range(mlmcpi_sampler *s, int c0, int B, bool cache0_vali
   return 0;
 }
 
+// MultilevelSampler::draw, sampler/multilevelsampler.cc:71-112.  All chains walk the levels
+// in lockstep: the decision "independent sample reached on this level" uses tau_int of the
+// per-level statistics averaged over the chains, exactly what the reference's Statistics
+// does across MPI ranks.
+static int multilevel_draw(mlmcpi_sampler *s) {
+  mlmcpi_ctx *ctx = s->ctx;
+  const int L = s->L, B = s->B;
+  const int k_max = s->prm.n_autocorr_window;
+  int rc;
+  int level = L - 1;
+  do {
+    if (level == L - 1) {
+      if ((rc = coarse_draw(s, 0, B))) // :76-78
+        return rc;
+    } else { // :85-86 (the two-level step keeps theta_fine and its cached actions)
+      if ((rc = twolevel_step_impl(ctx, &s->model[level], &s->model[level + 1], s->state[level + 1],
+                                   s->state[level], s->SfL[level], s->ScondL[level], B, s->chain0,
+                                   level_draw(s->draw, level, 0), nullptr, s->acc, nullptr)))
+        return rc;
+      count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc,
+                                                                             s->counters + level);
+      MLMCPI_LAUNCHED("count_accept");
+      s->work[2] += (double)B * n_sites(s->model[level]);
+    }
+    s->draw++;
+    if ((rc = mlmcpi_qoi(ctx, &s->model[level], s->prm.qoi, s->state[level], B, s->q, nullptr))) // :89
+      return rc;
+    if ((rc = mlmcpi_stats_record(s->stats_sampler[level], s->q)))
+      return rc;
+    s->t_sampler[level]++;
+    double st[6];
+    if ((rc = stats_query(s->stats_sampler[level], k_max, st)))
+      return rc;
+    if (s->t_sampler[level] >= std::ceil(st[3])) { // :92-106
+      s->t_indep[level] =
+          (s->n_indep[level] * s->t_indep[level] + s->t_sampler[level]) / (1.0 + s->n_indep[level]);
+      s->n_indep[level]++;
+      s->t_sampler[level] = 0;
+      level--;
+    } else {
+      level = L - 1;
+    }
+  } while (level >= 0);
+  return 0;
+}
+
 extern "C" {
 
 int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_sampler_params *prm,
@@ -906,8 +967,39 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
     return ctx_fail(ctx, MLMCPI_ENOMEM, "out of device memory for the sampler states");
   }
   cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->L, ctx->stream);
-  // Sampler constructors start from Action::initialise_state (e.g. hmcsampler.hh:99-101)
-  int rc = mlmcpi_init_state(ctx, fine, s->state[0], B, chain0, 0);
+  int rc;
+  if (s->prm.multilevel) {
+    if (s->L < 2) {
+      mlmcpi_sampler_destroy(s);
+      return ctx_fail(ctx, MLMCPI_EINVAL, "the multilevel sampler needs at least two levels");
+    }
+    if (s->prm.n_autocorr_window < 1)
+      s->prm.n_autocorr_window = 20;
+    // multilevelsampler.cc:8-58: the coarsest sampler starts from Action::initialise_state,
+    // every TwoLevelMetropolisStep from the zero state (twolevelmetropolisstep.cc:11-22)
+    rc = mlmcpi_init_state(ctx, &s->model[s->L - 1], s->state[s->L - 1], B, chain0, 0);
+    s->t_indep.assign(s->L, 0.0);
+    s->n_indep.assign(s->L, 0);
+    s->t_sampler.assign(s->L, 0);
+    for (int l = 0; l < s->L && !rc; ++l) {
+      mlmcpi_stats *st = nullptr;
+      rc = mlmcpi_stats_create(ctx, s->prm.n_autocorr_window, B, &st);
+      s->stats_sampler.push_back(st);
+    }
+    for (int l = 0; l + 1 < s->L && !rc; ++l) {
+      double *a = nullptr, *b = nullptr;
+      rc = mlmcpi_alloc(ctx, B, &a) || mlmcpi_alloc(ctx, B, &b);
+      s->SfL.push_back(a);
+      s->ScondL.push_back(b);
+      if (!rc)
+        rc = mlmcpi_action(ctx, &s->model[l], s->state[l], B, a);
+      if (!rc)
+        rc = mlmcpi_cond_action(ctx, &s->model[l], s->state[l], B, b);
+    }
+  } else {
+    // Sampler constructors start from Action::initialise_state (e.g. hmcsampler.hh:99-101)
+    rc = mlmcpi_init_state(ctx, fine, s->state[0], B, chain0, 0);
+  }
   if (rc) {
     mlmcpi_sampler_destroy(s);
     return rc;
@@ -926,6 +1018,14 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
       cudaEventDestroy(s->ev[k]);
     cudaStreamDestroy(s->copy_stream);
   }
+  for (mlmcpi_stats *st : s->stats_sampler)
+    mlmcpi_stats_destroy(st);
+  for (double *d : s->SfL)
+    if (d)
+      cudaFree(d);
+  for (double *d : s->ScondL)
+    if (d)
+      cudaFree(d);
   for (double *d : s->state)
     if (d)
       cudaFree(d);
@@ -949,6 +1049,10 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
 }
 
 int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x) {
+  // MultilevelSampler::set_state only overwrites the output buffer that the next draw
+  // overwrites again (multilevelsampler.cc:115-117): the chains are unaffected
+  if (s->prm.multilevel)
+    return 0;
   s->cache0_valid = false;
   return mlmcpi_copy(s->ctx, s->state[0], d_x, (size_t)mlmcpi_sample_size(&s->model[0]) * s->B);
 }
@@ -958,6 +1062,20 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
   const int B = s->B;
   int rc;
   s->work[0] = s->work[1] = s->work[2] = 0.0;
+  if (s->prm.multilevel) {
+    if ((rc = multilevel_draw(s)))
+      return rc;
+    s->n_draws++;
+    set_i32_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, s->acc, 1); // multilevelsampler.cc:72
+    MLMCPI_LAUNCHED("set_accept");
+    if (d_x_out) // :108-109
+      if ((rc = mlmcpi_copy(ctx, d_x_out, s->state[0], (size_t)mlmcpi_sample_size(&s->model[0]) * B)))
+        return rc;
+    if (d_accept)
+      MLMCPI_CUDA(cudaMemcpyAsync(d_accept, s->acc, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+    return 0;
+  }
   if ((rc = sampler_draw_range(s, 0, B, s->cache0_valid)))
     return rc;
   s->cache0_valid = s->L > 1;
@@ -983,7 +1101,7 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
   const size_t nd = (size_t)mlmcpi_sample_size(&s->model[0]);
   const size_t n = nd * s->B;
   int rc;
-  if (!h_x_in) {
+  if (!h_x_in || s->prm.multilevel) {
     if ((rc = mlmcpi_sampler_draw(s, nullptr, nullptr)))
       return rc;
     if (h_q)
@@ -1115,28 +1233,399 @@ int mlmcpi_sampler_set_dt(mlmcpi_sampler *s, double dt) {
 
 } // extern "C"
 
+// ====================================================== cost and MLMC estimator
+extern "C" {
+
+int mlmcpi_sampler_cost(mlmcpi_sampler *s, int n_meas, double *usec_per_sample) {
+  mlmcpi_ctx *ctx = s->ctx;
+  if (n_meas < 1 || !usec_per_sample)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "bad arguments");
+  cudaEvent_t e0, e1;
+  MLMCPI_CUDA(cudaEventCreate(&e0));
+  MLMCPI_CUDA(cudaEventCreate(&e1));
+  MLMCPI_CUDA(cudaEventRecord(e0, ctx->stream));
+  for (int k = 0; k < n_meas; ++k) {
+    int rc = mlmcpi_sampler_draw(s, nullptr, nullptr);
+    if (rc)
+      return rc;
+  }
+  MLMCPI_CUDA(cudaEventRecord(e1, ctx->stream));
+  MLMCPI_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  MLMCPI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *usec_per_sample = 1.0e3 * ms / ((double)n_meas * s->B);
+  return 0;
+}
+
+int mlmcpi_sampler_indep(const mlmcpi_sampler *s, double *out) {
+  if (!s->prm.multilevel)
+    return MLMCPI_EINVAL;
+  for (int l = 0; l < s->L; ++l) {
+    out[l] = s->t_indep[l];
+    out[s->L + l] = s->n_indep[l];
+  }
+  return 0;
+}
+
+} // extern "C"
+
+struct mlmcpi_mlmc {
+  mlmcpi_ctx *ctx = nullptr;
+  mlmcpi_mlmc_params prm;
+  int B = 0, L = 0;
+  uint32_t chain0 = 0;
+  uint64_t draw = 0;
+  std::vector<mlmcpi_model> model;            // [L]
+  std::vector<mlmcpi_sampler *> coarse_sampler; // [L-1]: sampler on level l+1
+  std::vector<double *> phi_state, phi_coarse_state; // [L] device [B][n_l]
+  std::vector<double *> Sf, Scond;            // [L-1] two-level caches
+  std::vector<mlmcpi_stats *> stats_qoi;      // [L]   Y_l
+  std::vector<mlmcpi_stats *> stats_coarse;   // [L-1] Q_sampler[l]
+  std::vector<double> t_indep, cost_twolevel, cost_sampler;
+  std::vector<int> n_indep, t_sampler;
+  std::vector<double> n_target;
+  double *q_fine = nullptr, *q_coarse = nullptr;
+  int32_t *acc = nullptr;
+};
+
+namespace {
+
+__global__ void diff_kernel(int B, double *a, const double *b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < B)
+    a[c] -= b[c];
+}
+
+// MonteCarloMultiLevel::draw_coarse_sample, montecarlomultilevel.cc:170-190 (sub_sample_coarse)
+int mlmc_draw_coarse_sample(mlmcpi_mlmc *m, int level, double *state) {
+  mlmcpi_ctx *ctx = m->ctx;
+  const int k_max = m->prm.n_autocorr_window;
+  double st[6];
+  int rc;
+  if ((rc = stats_query(m->stats_coarse[level - 1], k_max, st)))
+    return rc;
+  const double tau_int = std::ceil(2. * st[3]);
+  while (m->t_sampler[level - 1] < tau_int) {
+    if ((rc = mlmcpi_sampler_draw(m->coarse_sampler[level - 1], state, nullptr)))
+      return rc;
+    if ((rc = mlmcpi_qoi(ctx, &m->model[level], m->prm.qoi, state, m->B, m->q_coarse, nullptr)))
+      return rc;
+    if ((rc = mlmcpi_stats_record(m->stats_coarse[level - 1], m->q_coarse)))
+      return rc;
+    m->t_sampler[level - 1]++;
+  }
+  m->t_indep[level - 1] = (m->n_indep[level - 1] * m->t_indep[level - 1] + m->t_sampler[level - 1]) /
+                          (1.0 + m->n_indep[level - 1]);
+  m->n_indep[level - 1]++;
+  m->t_sampler[level - 1] = 0;
+  return 0;
+}
+
+// one batched sample of Y_level (B chains); independent = draw_coarse_sample, else plain draw
+int mlmc_sample(mlmcpi_mlmc *m, int level, bool independent) {
+  mlmcpi_ctx *ctx = m->ctx;
+  const int L = m->L, B = m->B;
+  int rc;
+  if (level == L - 1) { // :86-88, :120-122
+    if (independent)
+      rc = mlmc_draw_coarse_sample(m, level, m->phi_state[level]);
+    else
+      rc = mlmcpi_sampler_draw(m->coarse_sampler[level - 1], m->phi_state[level], nullptr);
+    if (rc)
+      return rc;
+    if ((rc = mlmcpi_qoi(ctx, &m->model[level], m->prm.qoi, m->phi_state[level], B, m->q_fine, nullptr)))
+      return rc;
+  } else { // :90-97, :124-132
+    if (independent)
+      rc = mlmc_draw_coarse_sample(m, level + 1, m->phi_coarse_state[level + 1]);
+    else
+      rc = mlmcpi_sampler_draw(m->coarse_sampler[level], m->phi_coarse_state[level + 1], nullptr);
+    if (rc)
+      return rc;
+    if ((rc = twolevel_step_impl(ctx, &m->model[level], &m->model[level + 1], m->phi_coarse_state[level + 1],
+                                 m->phi_state[level], m->Sf[level], m->Scond[level], B, m->chain0,
+                                 (m->draw++ << 12) | ((uint64_t)level << 8) | 0xfe, nullptr, m->acc, nullptr)))
+      return rc;
+    if ((rc = mlmcpi_qoi(ctx, &m->model[level], m->prm.qoi, m->phi_state[level], B, m->q_fine, nullptr)))
+      return rc;
+    if ((rc = mlmcpi_qoi(ctx, &m->model[level + 1], m->prm.qoi, m->phi_coarse_state[level + 1], B, m->q_coarse,
+                         nullptr)))
+      return rc;
+    diff_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, m->q_fine, m->q_coarse);
+    MLMCPI_LAUNCHED("mlmc_diff");
+  }
+  return mlmcpi_stats_record(m->stats_qoi[level], m->q_fine);
+}
+
+// montecarlomultilevel.cc:193-204
+int mlmc_cost_eff(mlmcpi_mlmc *m, int ell, double *cost_out) {
+  double cost;
+  if (ell == m->L - 1)
+    cost = m->t_indep[ell - 1] * m->cost_sampler[ell - 1];
+  else
+    cost = m->cost_twolevel[ell] + m->t_indep[ell] * m->cost_sampler[ell];
+  double st[6];
+  int rc = stats_query(m->stats_qoi[ell], m->prm.n_autocorr_window, st);
+  if (rc)
+    return rc;
+  *cost_out = std::ceil(st[3]) * cost;
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+void mlmcpi_mlmc_destroy(mlmcpi_mlmc *m) {
+  if (!m)
+    return;
+  cudaStreamSynchronize(m->ctx->stream);
+  for (auto *s : m->coarse_sampler)
+    mlmcpi_sampler_destroy(s);
+  for (auto *st : m->stats_qoi)
+    mlmcpi_stats_destroy(st);
+  for (auto *st : m->stats_coarse)
+    mlmcpi_stats_destroy(st);
+  for (auto &v : {m->phi_state, m->phi_coarse_state, m->Sf, m->Scond})
+    for (double *d : v)
+      if (d)
+        cudaFree(d);
+  if (m->q_fine)
+    cudaFree(m->q_fine);
+  if (m->q_coarse)
+    cudaFree(m->q_coarse);
+  if (m->acc)
+    cudaFree(m->acc);
+  delete m;
+}
+
+// MonteCarloMultiLevel constructor, montecarlomultilevel.cc:7-68
+int mlmcpi_mlmc_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_mlmc_params *prm, int B,
+                       uint32_t chain0, mlmcpi_mlmc **out) {
+  if (!ctx || !fine || !prm || !out || B <= 0)
+    return MLMCPI_EINVAL;
+  *out = nullptr;
+  if (prm->n_level < 2 || prm->n_level > 16)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "multilevel MC needs 2 <= n_level <= 16");
+  mlmcpi_mlmc *m = new (std::nothrow) mlmcpi_mlmc;
+  if (!m)
+    return MLMCPI_ENOMEM;
+  m->ctx = ctx;
+  m->prm = *prm;
+  m->B = B;
+  m->L = prm->n_level;
+  m->chain0 = chain0;
+  if (m->prm.n_autocorr_window < 1)
+    m->prm.n_autocorr_window = 20;
+  const int L = m->L;
+  m->model.push_back(*fine);
+  int rc = 0;
+  for (int l = 0; l + 1 < L && !rc; ++l) {
+    mlmcpi_model c;
+    const int level = (fine->model == MLMCPI_GFF && fine->rotated ? 1 : 0) + l;
+    rc = mlmcpi_coarse_model(&m->model[l], prm->sampler.renorm, level, prm->sampler.ctype,
+                             m->model[l].T_final, &c);
+    m->model.push_back(c);
+  }
+  if (rc) {
+    delete m;
+    return ctx_fail(ctx, rc, "cannot construct the coarse action of a level");
+  }
+  m->t_indep.assign(L, 0.0);
+  m->n_indep.assign(L, 0);
+  m->t_sampler.assign(L, 0);
+  m->cost_twolevel.assign(L, 0.0);
+  m->cost_sampler.assign(L, 0.0);
+  m->n_target.assign(L, 0.0);
+  for (int l = 0; l < L && !rc; ++l) {
+    double *a = nullptr, *b = nullptr;
+    const size_t n = (size_t)mlmcpi_sample_size(&m->model[l]) * B;
+    rc = mlmcpi_alloc(ctx, n, &a) || mlmcpi_alloc(ctx, n, &b);
+    m->phi_state.push_back(a);
+    m->phi_coarse_state.push_back(b);
+    mlmcpi_stats *st = nullptr;
+    if (!rc)
+      rc = mlmcpi_stats_create(ctx, m->prm.n_autocorr_window, B, &st);
+    m->stats_qoi.push_back(st);
+  }
+  for (int l = 0; l + 1 < L && !rc; ++l) {
+    // sampler_factory->get(action[l+1]) (:37-39): the hierarchy below level l+1
+    mlmcpi_sampler_params sp = prm->sampler;
+    sp.n_levels = std::max(1, prm->sampler.n_levels - (l + 1));
+    if (sp.n_levels < 2)
+      sp.multilevel = 0;
+    sp.qoi = prm->qoi;
+    mlmcpi_sampler *s = nullptr;
+    // distinct chains for every level: offset the global chain index by the level
+    rc = mlmcpi_sampler_create(ctx, &m->model[l + 1], &sp, B, chain0 + (uint32_t)(l + 1) * 0x01000000u, &s);
+    m->coarse_sampler.push_back(s);
+    mlmcpi_stats *st = nullptr;
+    if (!rc)
+      rc = mlmcpi_stats_create(ctx, m->prm.n_autocorr_window, B, &st);
+    m->stats_coarse.push_back(st);
+    double *a = nullptr, *b = nullptr;
+    if (!rc)
+      rc = mlmcpi_alloc(ctx, B, &a) || mlmcpi_alloc(ctx, B, &b);
+    m->Sf.push_back(a);
+    m->Scond.push_back(b);
+    // TwoLevelMetropolisStep constructor (twolevelmetropolisstep.cc:11-22): zero state
+    if (!rc)
+      rc = mlmcpi_action(ctx, &m->model[l], m->phi_state[l], B, a);
+    if (!rc)
+      rc = mlmcpi_cond_action(ctx, &m->model[l], m->phi_state[l], B, b);
+  }
+  if (!rc)
+    rc = mlmcpi_alloc(ctx, B, &m->q_fine) || mlmcpi_alloc(ctx, B, &m->q_coarse);
+  if (!rc && cudaMalloc((void **)&m->acc, sizeof(int32_t) * B) != cudaSuccess)
+    rc = MLMCPI_ENOMEM;
+  if (rc) {
+    mlmcpi_mlmc_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return 0;
+}
+
+// MonteCarloMultiLevel::evaluate, montecarlomultilevel.cc:71-167
+int mlmcpi_mlmc_evaluate(mlmcpi_mlmc *m) {
+  mlmcpi_ctx *ctx = m->ctx;
+  const int L = m->L, B = m->B, k_max = m->prm.n_autocorr_window;
+  int rc;
+  // cost_per_sample of the samplers and two-level steps (measured in the reference's
+  // constructors with 10000 draws each; here a short CUDA-event measurement, usec per chain-sample)
+  for (int l = 0; l + 1 < L; ++l) {
+    if ((rc = mlmcpi_sampler_cost(m->coarse_sampler[l], 4, &m->cost_sampler[l])))
+      return rc;
+    cudaEvent_t e0, e1;
+    MLMCPI_CUDA(cudaEventCreate(&e0));
+    MLMCPI_CUDA(cudaEventCreate(&e1));
+    MLMCPI_CUDA(cudaEventRecord(e0, ctx->stream));
+    for (int k = 0; k < 4; ++k)
+      if ((rc = twolevel_step_impl(ctx, &m->model[l], &m->model[l + 1], m->phi_coarse_state[l + 1],
+                                   m->phi_state[l], m->Sf[l], m->Scond[l], B, m->chain0,
+                                   (m->draw++ << 12) | ((uint64_t)l << 8) | 0xfd, nullptr, m->acc, nullptr)))
+        return rc;
+    MLMCPI_CUDA(cudaEventRecord(e1, ctx->stream));
+    MLMCPI_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    MLMCPI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    m->cost_twolevel[l] = 1.0e3 * ms / (4.0 * B);
+  }
+  for (int l = 0; l < L; ++l)
+    if ((rc = mlmcpi_stats_hard_reset(m->stats_qoi[l])))
+      return rc;
+  const double two_epsilon_inv2 = 2. / (m->prm.epsilon * m->prm.epsilon);
+  for (int level = L - 1; level >= 0; level--) // burn-in, :83-100
+    for (int j = 0; j < m->prm.n_burnin; ++j)
+      if ((rc = mlmc_sample(m, level, false)))
+        return rc;
+  for (int l = 0; l < L; ++l) { // :102-108
+    if ((rc = mlmcpi_stats_reset(m->stats_qoi[l])))
+      return rc;
+    if (l < L - 1)
+      if ((rc = mlmcpi_stats_reset(m->stats_coarse[l])))
+        return rc;
+    m->n_target[l] = m->prm.n_min_samples_qoi;
+  }
+  bool sufficient = false;
+  int iterations = 0;
+  do {
+    for (int level = L - 1; level >= 0; level--) { // :114-137
+      double st[6];
+      if ((rc = stats_query(m->stats_qoi[level], k_max, st)))
+        return rc;
+      for (double j = st[5]; j < m->n_target[level]; j += B) // B samples per batched draw
+        if ((rc = mlmc_sample(m, level, true)))
+          return rc;
+    }
+    sufficient = true;
+    double sum_s = 0.0;
+    std::vector<double> V(L), C(L), tau(L), ns(L);
+    for (int l = 0; l < L; ++l) { // :140-146
+      double st[6];
+      if ((rc = stats_query(m->stats_qoi[l], k_max, st)))
+        return rc;
+      V[l] = st[1];
+      tau[l] = st[3];
+      ns[l] = st[5];
+      if ((rc = mlmc_cost_eff(m, l, &C[l])))
+        return rc;
+      sum_s += std::sqrt(V[l] * C[l]);
+    }
+    for (int l = 0; l < L; ++l) { // :147-158
+      m->n_target[l] = std::ceil(two_epsilon_inv2 * sum_s * std::sqrt(V[l] / C[l]) * tau[l]);
+      sufficient = sufficient && (ns[l] >= m->n_target[l]);
+    }
+    ++iterations;
+    if (m->prm.max_iterations > 0 && iterations >= m->prm.max_iterations)
+      break;
+  } while (!sufficient);
+  return sufficient ? 0 : 1;
+}
+
+int mlmcpi_mlmc_result(mlmcpi_mlmc *m, double *value, double *error, double *level_out) {
+  double v = 0.0, e2 = 0.0;
+  for (int l = 0; l < m->L; ++l) {
+    double st[6], cost = 0.0;
+    int rc = stats_query(m->stats_qoi[l], m->prm.n_autocorr_window, st);
+    if (rc)
+      return rc;
+    if ((rc = mlmc_cost_eff(m, l, &cost)))
+      return rc;
+    v += st[0];          // numerical_result(), :255-261
+    e2 += st[4] * st[4]; // statistical_error(), :264-271
+    if (level_out) {
+      double *o = level_out + 6 * l;
+      o[0] = st[5];
+      o[1] = st[0];
+      o[2] = st[1];
+      o[3] = st[3];
+      o[4] = cost;
+      o[5] = m->n_target[l];
+    }
+  }
+  if (value)
+    *value = v;
+  if (error)
+    *error = std::sqrt(e2);
+  return 0;
+}
+
+} // extern "C"
+
 // ================================================================ statistics
 // common/statistics.cc:4-27 for every chain; the chain plays the role of the MPI
-// rank of the reference
+// rank of the reference.  Rows of acc ([row][chain]):
+//   0            avg            (short-term running mean: cleared by reset())
+//   1..4         avg_longterm, avg2_longterm, avg3_longterm, avg4_longterm
+//   5..5+k-1     S_k
+//   5+k..5+2k-1  ring buffer Q_k
 struct mlmcpi_stats {
   mlmcpi_ctx *ctx = nullptr;
   int k_max = 0, B = 0;
-  unsigned n_samples = 0; // identical for all chains (lockstep)
-  double *acc = nullptr;  // [4 + 2 k_max][B]: avg1..avg4, S_k[k_max], ring Q_k[k_max]
+  unsigned n_samples = 0, n_samples_longterm = 0; // identical for all chains (lockstep)
+  double *acc = nullptr;
   double *packed = nullptr;
 };
 
 namespace {
 
-__global__ void stats_record_kernel(int B, int k_max, unsigned n, double *acc, const double *q) {
+__global__ void stats_record_kernel(int B, int k_max, unsigned n_short, unsigned n, double *acc,
+                                    const double *q) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= B)
     return;
-  // n = number of samples including this one
+  // n / n_short = number of long-term / short-term samples including this one
   const double Q = q[c];
   const double w = (n - 1.0), inv = 1.0 / (1.0 * n);
-  double *a1 = acc, *a2 = acc + B, *a3 = acc + 2 * (size_t)B, *a4 = acc + 3 * (size_t)B;
-  double *S = acc + 4 * (size_t)B, *ring = acc + (4 + (size_t)k_max) * B;
+  double *a0 = acc, *a1 = acc + B, *a2 = acc + 2 * (size_t)B, *a3 = acc + 3 * (size_t)B,
+         *a4 = acc + 4 * (size_t)B;
+  double *S = acc + 5 * (size_t)B, *ring = acc + (5 + (size_t)k_max) * B;
+  a0[c] = ((n_short - 1.0) * a0[c] + Q) / (1.0 * n_short);
   a1[c] = (w * a1[c] + Q) * inv;
   a2[c] = (w * a2[c] + Q * Q) * inv;
   a3[c] = (w * a3[c] + Q * Q * Q) * inv;
@@ -1152,7 +1641,7 @@ __global__ void stats_record_kernel(int B, int k_max, unsigned n, double *acc, c
   }
 }
 
-// packed[r] = sum over chains of row r (rows: avg1..avg4, S_0..S_{k_max-1})
+// packed[r] = sum over chains of row r (rows: avg, avg1..avg4, S_0..S_{k_max-1})
 __global__ void stats_pack_kernel(int B, const double *acc, double *packed) {
   const int r = blockIdx.x;
   double v = 0.0;
@@ -1176,8 +1665,8 @@ int mlmcpi_stats_create(mlmcpi_ctx *ctx, int k_max, int B, mlmcpi_stats **out) {
   st->ctx = ctx;
   st->k_max = k_max;
   st->B = B;
-  if (mlmcpi_alloc(ctx, (size_t)(4 + 2 * k_max) * B, &st->acc) ||
-      mlmcpi_alloc(ctx, 4 + k_max, &st->packed)) {
+  if (mlmcpi_alloc(ctx, (size_t)(5 + 2 * k_max) * B, &st->acc) ||
+      mlmcpi_alloc(ctx, 5 + k_max, &st->packed)) {
     mlmcpi_stats_destroy(st);
     return MLMCPI_ENOMEM;
   }
@@ -1196,56 +1685,74 @@ void mlmcpi_stats_destroy(mlmcpi_stats *st) {
   delete st;
 }
 
-int mlmcpi_stats_reset(mlmcpi_stats *st) { // Statistics::hard_reset, statistics.hh:125-137
+int mlmcpi_stats_hard_reset(mlmcpi_stats *st) { // Statistics::hard_reset, statistics.hh:125-137
+  mlmcpi_ctx *ctx = st->ctx;
+  st->n_samples = st->n_samples_longterm = 0;
+  MLMCPI_CUDA(cudaMemsetAsync(st->acc, 0, sizeof(double) * (5 + 2 * st->k_max) * st->B, ctx->stream));
+  return 0;
+}
+
+int mlmcpi_stats_reset(mlmcpi_stats *st) { // Statistics::reset, statistics.hh:119-122
   mlmcpi_ctx *ctx = st->ctx;
   st->n_samples = 0;
-  MLMCPI_CUDA(cudaMemsetAsync(st->acc, 0, sizeof(double) * (4 + 2 * st->k_max) * st->B, ctx->stream));
+  MLMCPI_CUDA(cudaMemsetAsync(st->acc, 0, sizeof(double) * st->B, ctx->stream));
   return 0;
 }
 
 int mlmcpi_stats_record(mlmcpi_stats *st, const double *d_q) {
   mlmcpi_ctx *ctx = st->ctx;
   st->n_samples++;
+  st->n_samples_longterm++;
   stats_record_kernel<<<cdiv(st->B, 128), 128, 0, ctx->stream>>>(st->B, st->k_max, st->n_samples,
-                                                                st->acc, d_q);
+                                                                st->n_samples_longterm, st->acc, d_q);
   MLMCPI_LAUNCHED("stats_record");
   return 0;
 }
 
-int mlmcpi_stats_packed_size(int k_max) { return 6 + k_max; }
+int mlmcpi_stats_packed_size(int k_max) { return 8 + k_max; }
+
+static void stats_head(const mlmcpi_stats *st, double head[3]) {
+  head[0] = (double)st->B;
+  head[1] = (double)st->n_samples_longterm * st->B;
+  head[2] = (double)st->n_samples * st->B;
+}
 
 int mlmcpi_stats_pack_device(mlmcpi_stats *st, double *d_packed) {
   mlmcpi_ctx *ctx = st->ctx;
-  stats_pack_kernel<<<4 + st->k_max, 256, 0, ctx->stream>>>(st->B, st->acc, d_packed + 2);
+  stats_pack_kernel<<<5 + st->k_max, 256, 0, ctx->stream>>>(st->B, st->acc, d_packed + 3);
   MLMCPI_LAUNCHED("stats_pack");
-  const double head[2] = {(double)st->B, (double)st->n_samples * st->B};
-  // 16 bytes from a stack buffer: the driver stages pageable sources before returning
+  double head[3];
+  stats_head(st, head);
+  // 24 bytes from a stack buffer: the driver stages pageable sources before returning
   MLMCPI_CUDA(cudaMemcpyAsync(d_packed, head, sizeof(head), cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 
 int mlmcpi_stats_pack(mlmcpi_stats *st, double *h_packed) {
   mlmcpi_ctx *ctx = st->ctx;
-  stats_pack_kernel<<<4 + st->k_max, 256, 0, ctx->stream>>>(st->B, st->acc, st->packed);
+  stats_pack_kernel<<<5 + st->k_max, 256, 0, ctx->stream>>>(st->B, st->acc, st->packed);
   MLMCPI_LAUNCHED("stats_pack");
-  h_packed[0] = st->B;
-  h_packed[1] = (double)st->n_samples * st->B;
-  MLMCPI_CUDA(cudaMemcpyAsync(h_packed + 2, st->packed, sizeof(double) * (4 + st->k_max),
+  stats_head(st, h_packed);
+  MLMCPI_CUDA(cudaMemcpyAsync(h_packed + 3, st->packed, sizeof(double) * (5 + st->k_max),
                               cudaMemcpyDeviceToHost, ctx->stream));
   MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
-// common/statistics.cc:29-97 with "ranks" = chains: packed[0] = number of chains,
-// packed[1] = total number of samples; every entry is additive over GPUs
+// common/statistics.cc:29-97 with "ranks" = chains.  packed = {n_chains, long-term samples
+// (all chains), short-term samples (all chains), sum avg, sum avg_longterm, sum avg2_longterm,
+// sum avg3_longterm, sum avg4_longterm, sum S_0 .. S_{k_max-1}}; every entry is additive
+// over GPUs.  out = {average, variance, variance_error, tau_int, error, samples}.
 int mlmcpi_stats_finalize(const double *p, int k_max, double out[6]) {
   const double n_chains = p[0];
   const double n_tot = p[1]; // mpi_allreduce_sum(n_samples_longterm)
-  if (n_chains < 1 || n_tot < 2)
+  const double n_short = p[2]; // mpi_allreduce_sum(n_samples)
+  if (n_chains < 1)
     return MLMCPI_EINVAL;
-  const double avg = p[2] / n_chains;          // mpi_allreduce_avg(avg_longterm)
-  const double avg2 = p[3] / n_chains, avg3 = p[4] / n_chains, avg4 = p[5] / n_chains;
-  const double S0 = p[6] / n_chains;
+  const double avg_short = p[3] / n_chains;   // mpi_allreduce_avg(avg)
+  const double avg = p[4] / n_chains;         // mpi_allreduce_avg(avg_longterm)
+  const double avg2 = p[5] / n_chains, avg3 = p[6] / n_chains, avg4 = p[7] / n_chains;
+  const double S0 = p[8] / n_chains;
   const double variance = n_tot / (n_tot - 1.0) * (S0 - avg * avg);
   const double variance_error =
       std::sqrt(1.0 / n_tot *
@@ -1253,14 +1760,15 @@ int mlmcpi_stats_finalize(const double *p, int k_max, double out[6]) {
   const double C0 = S0 - avg * avg;
   double tau = 0.0;
   for (int k = 1; k < k_max; ++k)
-    tau += (1. - k / n_tot) * (p[6 + k] / n_chains - avg * avg);
+    tau += (1. - k / n_tot) * (p[8 + k] / n_chains - avg * avg);
+  // std::fmax returns the non-NaN argument: tau_int = 1 while there is no variance yet
   const double tau_int = std::fmax(1.0, 1.0 + 2.0 * tau / C0);
-  out[0] = avg;
+  out[0] = avg_short;
   out[1] = variance;
   out[2] = variance_error;
   out[3] = tau_int;
-  out[4] = std::sqrt(tau_int * variance / n_tot);
-  out[5] = n_tot;
+  out[4] = std::sqrt(tau_int * variance / n_short);
+  out[5] = n_short;
   return 0;
 }
 

@@ -142,7 +142,7 @@ def test_stats_finalize_matches_reference_statistics(mp):
         for k in range(len(hist)):
             Nk = n - k
             S[k] = ((Nk - 1.0) * S[k] + hist[0] * hist[k]) / Nk
-    packed = np.concatenate([[1.0, float(len(q))], avg, S])
+    packed = np.concatenate([[1.0, float(len(q)), float(len(q)), avg[0]], avg, S])
     out = mp.Statistics.finalize(packed, k_max)
     got = np.array([out["average"], out["variance"], out["variance_error"], out["tau_int"],
                     out["error"], out["samples"]])

@@ -345,7 +345,7 @@ def test_statistics_against_oracle(mp, ctx, orc):
     for k in range(n):
         st.record(dev(ctx, q[k])[0])
     packed = st.pack()
-    assert packed[0] == B and packed[1] == B * n
+    assert packed[0] == B and packed[1] == B * n and packed[2] == B * n
     # single-chain restriction: chain b alone reproduces Statistics exactly
     for b in range(B):
         st1 = mp.Statistics(ctx, k_max, 1)
@@ -561,3 +561,65 @@ def test_error_paths(mp, ctx):
     with pytest.raises(mp.MlmcpiError):
         m = mp.gff(8, 8, 1.0, mp.COARSEN_BOTH)
         ctx.fill(m, ctx.state(m, 1))                                   # GFF fill needs rotate
+
+
+# ------------------------------------ multilevel sampler and multilevel Monte Carlo
+
+
+def test_statistics_reset_semantics(mp, ctx, orc):
+    """Statistics::reset clears the short-term mean and count, not the long-term moments"""
+    rng = np.random.default_rng(11)
+    B, k_max = 4, 5
+    q = rng.normal(size=(60, B))
+    st = mp.Statistics(ctx, k_max, B)
+    for k in range(20):
+        st.record(dev(ctx, q[k])[0])
+    st.reset()
+    for k in range(20, 60):
+        st.record(dev(ctx, q[k])[0])
+    out = mp.Statistics.finalize(st.pack(), k_max)
+    assert out["samples"] == 40 * B
+    assert abs(out["average"] - q[20:].mean()) < 1e-12
+    per = np.array([orc.statistics(k_max, q[:, b]) for b in range(B)])
+    # variance / tau_int use all 60 samples (long-term), like the reference
+    S0 = np.mean([np.mean(q[:, b] ** 2) for b in range(B)])
+    assert abs(out["variance"] - (60 * B) / (60 * B - 1.0) * (S0 - q.mean() ** 2)) < 1e-12
+    assert per.shape == (B, 6)
+
+
+def test_rotor_multilevel_sampler_matches_exact_chit(mp, ctx):
+    """MultilevelSampler level walk (sampler/multilevelsampler.cc:71-112), rotor M = 32"""
+    m = mp.rotor(32, 4.0, 0.25)
+    B = 4096
+    s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=3, nt=20, dt=0.1,
+                   renorm=mp.RENORM_PERTURBATIVE, multilevel=True, qoi=mp.QOI_ROTOR_CHI,
+                   n_autocorr_window=10)
+    x = ctx.state(m, B)
+    for _ in range(30):
+        s.draw(x)
+    vals = []
+    for _ in range(20):
+        s.draw(x)
+        vals.append(host(ctx.qoi(m, mp.QOI_ROTOR_CHI, x)))
+    mean, err = _mean_err(np.mean(vals, axis=0))
+    want = float.fromhex(load("scalars")["analytic"]["rotor_chit_exact_32"])
+    assert abs(mean - want) < 5 * err, (mean, err, want)
+    t_indep, n_indep = s.independence()
+    assert all(t >= 1.0 for t in t_indep) and n_indep[0] == 50
+    assert s.cost_per_sample(2) > 0
+
+
+def test_rotor_multilevel_mc_matches_exact_chit(mp, ctx):
+    """MonteCarloMultiLevel::evaluate: sum_l <Y_l> = chi_t within the estimated error"""
+    m = mp.rotor(32, 4.0, 0.25)
+    B = 2048
+    mc = mp.MultilevelMC(ctx, m, B, n_level=3, epsilon=2e-3, qoi=mp.QOI_ROTOR_CHI, n_burnin=30,
+                         n_autocorr_window=10, n_min_samples_qoi=4 * B, max_iterations=20,
+                         kind=mp.SAMPLER_HMC, nt=20, dt=0.1, renorm=mp.RENORM_PERTURBATIVE)
+    converged = mc.evaluate()
+    value, error, levels = mc.result()
+    want = float.fromhex(load("scalars")["analytic"]["rotor_chit_exact_32"])
+    assert converged, levels
+    assert error < 3e-3 and abs(value - want) < 5 * error + 1e-3, (value, error, want, levels)
+    assert all(lv["variance"] > 0 and lv["tau_int"] >= 1.0 and lv["cost_eff_usec"] > 0 for lv in levels)
+    assert all(lv["samples"] >= lv["n_target"] for lv in levels)

@@ -16,7 +16,7 @@ K_MAX = 8
 
 def packed_from_chains(q):
     """host restatement of what the device accumulators hold: q[n_samples, n_chains] ->
-    {n_chains, n_samples_total, sum avg1..4, sum S_k} (statistics.cc:4-27 per chain)"""
+    {n_chains, n_longterm, n_shortterm, sum avg, sum avg1..4, sum S_k} (statistics.cc:4-27 per chain)"""
     n, B = q.shape
     S = np.zeros((K_MAX, B))
     avg = np.zeros((4, B))
@@ -30,7 +30,7 @@ def packed_from_chains(q):
         for k in range(len(hist)):
             Nk = s - k
             S[k] = ((Nk - 1.0) * S[k] + hist[0] * hist[k]) / Nk
-    return np.concatenate([[B, n * B], avg.sum(axis=1), S.sum(axis=1)])
+    return np.concatenate([[B, n * B, n * B, avg[0].sum()], avg.sum(axis=1), S.sum(axis=1)])
 
 
 def chains(n, B, chain0):
