@@ -55,9 +55,12 @@ enum { MLMCPI_QOI_X2 = 0, MLMCPI_QOI_ROTOR_CHI = 1, MLMCPI_QOI_SCHWINGER_CHI = 2
        MLMCPI_QOI_AVG_PLAQUETTE = 3, MLMCPI_QOI_PHI2 = 4 };
 enum { MLMCPI_STREAM_INIT = 1, MLMCPI_STREAM_HMC_MOMENTUM = 2, MLMCPI_STREAM_HMC_ACCEPT = 3,
        MLMCPI_STREAM_HEATBATH = 4, MLMCPI_STREAM_FILL1 = 5, MLMCPI_STREAM_FILL2 = 6,
-       MLMCPI_STREAM_FILL3 = 7, MLMCPI_STREAM_TWOLEVEL_ACCEPT = 8 };
+       MLMCPI_STREAM_FILL3 = 7, MLMCPI_STREAM_TWOLEVEL_ACCEPT = 8, MLMCPI_STREAM_CLUSTER = 9,
+       MLMCPI_STREAM_GAUGE = 10 };
 /* coarse-level samplers of sampler/hierarchicalsampler.hh */
-enum { MLMCPI_SAMPLER_HMC = 0, MLMCPI_SAMPLER_HEATBATH = 1 };
+/* MLMCPI_SAMPLER_CLUSTER: ClusterSampler (rotor, sampler/clustersampler.cc) or
+ * QuenchedSchwingerClusterSampler (sampler/quenchedschwingerclustersampler.cc) */
+enum { MLMCPI_SAMPLER_HMC = 0, MLMCPI_SAMPLER_HEATBATH = 1, MLMCPI_SAMPLER_CLUSTER = 2 };
 
 /* One level of one model: the data members of the reference's action classes. */
 typedef struct mlmcpi_model {
@@ -166,6 +169,16 @@ int mlmcpi_fill(mlmcpi_ctx *ctx, const mlmcpi_model *fine, double *d_x, int B, u
 int mlmcpi_prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *d_xc,
                         double *d_x, int B, uint32_t chain0, uint64_t draw);
 
+/* n_updates Wolff single-cluster updates of the rotor (ClusterSampler::single_cluster_update1d,
+ * sampler/clustersampler.cc:88-132 with RotorAction::S_ell / new_reflection / flip,
+ * action/qm/rotoraction.hh:226-253); `update0` numbers the first update (Philox draw counter) */
+int mlmcpi_cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *rotor, double *d_x, int B,
+                          uint32_t chain0, uint64_t update0, int n_updates);
+/* QuenchedSchwingerClusterSampler::draw lines 52-82: links from the rotor chain psi
+ * (length Mt*Mx) followed by a random gauge transformation */
+int mlmcpi_schwinger_from_cluster(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_psi,
+                                  double *d_x, int B, uint32_t chain0, uint64_t draw);
+
 /* ---- group 3: reductions, acceptance, QoIs -------------------------------- */
 /* ConditionedFineAction::evaluate: d_S[B] */
 int mlmcpi_cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *d_x, int B,
@@ -199,6 +212,7 @@ typedef struct mlmcpi_sampler_params {
                             (sampler/multilevelsampler.cc:71-112), needs n_levels > 1      */
   int qoi;               /* multilevel: QoI of the per-level statistics Q_sampler[l]        */
   int n_autocorr_window; /* multilevel: window of those statistics (default 20)             */
+  int n_updates;         /* cluster: cluster updates per draw (clusteralgorithm: n_updates)  */
 } mlmcpi_sampler_params;
 int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine,
                           const mlmcpi_sampler_params *prm, int B, uint32_t chain0,

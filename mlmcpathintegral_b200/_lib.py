@@ -14,7 +14,7 @@ HO, QUARTIC, ROTOR, SCHWINGER, GFF = 0, 1, 2, 3, 4
 COARSEN_BOTH, COARSEN_TEMPORAL, COARSEN_SPATIAL, COARSEN_ALTERNATE, COARSEN_ROTATE = range(5)
 RENORM_NONE, RENORM_PERTURBATIVE, RENORM_NONPERTURBATIVE = range(3)
 QOI_X2, QOI_ROTOR_CHI, QOI_SCHWINGER_CHI, QOI_AVG_PLAQUETTE, QOI_PHI2 = range(5)
-SAMPLER_HMC, SAMPLER_HEATBATH = 0, 1
+SAMPLER_HMC, SAMPLER_HEATBATH, SAMPLER_CLUSTER = 0, 1, 2
 E_INVAL, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4
 OPT_EXPCOS_ENVELOPE, OPT_LEAPFROG_VARIANT, OPT_LEAPFROG_ROWS = 1, 2, 3
 
@@ -33,7 +33,8 @@ class SamplerParams(C.Structure):
     _fields_ = [("kind", C.c_int), ("n_levels", C.c_int), ("renorm", C.c_int), ("ctype", C.c_int),
                 ("nt", C.c_int), ("dt", C.c_double), ("n_rep", C.c_int),
                 ("n_sweep_overrelax", C.c_int), ("n_sweep_heatbath", C.c_int),
-                ("multilevel", C.c_int), ("qoi", C.c_int), ("n_autocorr_window", C.c_int)]
+                ("multilevel", C.c_int), ("qoi", C.c_int), ("n_autocorr_window", C.c_int),
+                ("n_updates", C.c_int)]
 
 
 class MlmcParams(C.Structure):
@@ -86,6 +87,8 @@ SIGNATURES = {
     "mlmcpi_restrict": (_i, [_vp, _MP, _vp, _vp, _i]),
     "mlmcpi_fill": (_i, [_vp, _MP, _vp, _i, _u32, _u64]),
     "mlmcpi_prolong_fill": (_i, [_vp, _MP, _vp, _vp, _i, _u32, _u64]),
+    "mlmcpi_cluster_update": (_i, [_vp, _MP, _vp, _i, _u32, _u64, _i]),
+    "mlmcpi_schwinger_from_cluster": (_i, [_vp, _MP, _vp, _vp, _i, _u32, _u64]),
     "mlmcpi_cond_action": (_i, [_vp, _MP, _vp, _i, _vp]),
     "mlmcpi_qoi": (_i, [_vp, _MP, _i, _vp, _i, _vp, _vp]),
     "mlmcpi_twolevel_step": (_i, [_vp, _MP, _MP, _vp, _vp, _vp, _vp, _i, _u32, _u64, _vp, _vp]),

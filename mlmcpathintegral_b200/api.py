@@ -15,7 +15,8 @@ from . import _lib
 from ._lib import (COARSEN_ALTERNATE, COARSEN_BOTH, COARSEN_ROTATE, COARSEN_SPATIAL,  # noqa: F401
                    COARSEN_TEMPORAL, GFF, HO, QOI_AVG_PLAQUETTE, QOI_PHI2, QOI_ROTOR_CHI,
                    QOI_SCHWINGER_CHI, QOI_X2, QUARTIC, RENORM_NONE, RENORM_PERTURBATIVE, ROTOR,
-                   SAMPLER_HEATBATH, SAMPLER_HMC, SCHWINGER, MlmcParams, Model, SamplerParams)
+                   SAMPLER_CLUSTER, SAMPLER_HEATBATH, SAMPLER_HMC, SCHWINGER, MlmcParams, Model,
+                   SamplerParams)
 
 L = _lib.lib
 
@@ -205,6 +206,14 @@ class Context:
         self._ck(L.mlmcpi_prolong_fill(self.h, C.byref(fine), _ptr(xc), _ptr(x), x.shape[0], chain0,
                                        draw))
 
+    def cluster_update(self, rotor_model, x, chain0=0, update0=0, n_updates=1):
+        self._ck(L.mlmcpi_cluster_update(self.h, C.byref(rotor_model), _ptr(x), x.shape[0], chain0,
+                                         update0, n_updates))
+
+    def schwinger_from_cluster(self, m, psi, x, chain0=0, draw=0):
+        self._ck(L.mlmcpi_schwinger_from_cluster(self.h, C.byref(m), _ptr(psi), _ptr(x), x.shape[0],
+                                                 chain0, draw))
+
     # ---- group 3
     def cond_action(self, fine, x):
         S = self.empty(x.shape[0])
@@ -236,12 +245,13 @@ class Sampler:
 
     def __init__(self, ctx, fine, B, kind=SAMPLER_HMC, n_levels=1, renorm=RENORM_NONE,
                  ctype=COARSEN_BOTH, nt=100, dt=0.1, n_rep=1, n_sweep_overrelax=10,
-                 n_sweep_heatbath=1, chain0=0, multilevel=False, qoi=QOI_X2, n_autocorr_window=20):
+                 n_sweep_heatbath=1, chain0=0, multilevel=False, qoi=QOI_X2, n_autocorr_window=20,
+                 n_updates=10):
         self.ctx, self.fine, self.B, self.n_levels = ctx, fine, B, n_levels
         prm = SamplerParams(kind=kind, n_levels=n_levels, renorm=renorm, ctype=ctype, nt=nt, dt=dt,
                             n_rep=n_rep, n_sweep_overrelax=n_sweep_overrelax,
                             n_sweep_heatbath=n_sweep_heatbath, multilevel=int(multilevel), qoi=qoi,
-                            n_autocorr_window=n_autocorr_window)
+                            n_autocorr_window=n_autocorr_window, n_updates=n_updates)
         h = C.c_void_p()
         ctx._ck(L.mlmcpi_sampler_create(ctx.h, C.byref(fine), C.byref(prm), B, chain0, C.byref(h)))
         self.h = h
@@ -320,7 +330,7 @@ class MultilevelMC:
         self.ctx, self.n_level = ctx, n_level
         sp = dict(kind=SAMPLER_HMC, n_levels=n_level, renorm=RENORM_NONE, ctype=COARSEN_BOTH, nt=100,
                   dt=0.1, n_rep=1, n_sweep_overrelax=10, n_sweep_heatbath=1, multilevel=0, qoi=qoi,
-                  n_autocorr_window=n_autocorr_window)
+                  n_autocorr_window=n_autocorr_window, n_updates=10)
         sp.update(sampler_kw)
         prm = MlmcParams(n_level=n_level, n_burnin=n_burnin, epsilon=epsilon,
                          n_autocorr_window=n_autocorr_window, n_min_samples_qoi=n_min_samples_qoi,

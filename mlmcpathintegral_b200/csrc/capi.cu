@@ -703,6 +703,19 @@ int mlmcpi_qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int qoi, const double *d_
   DISPATCH(m, qoi, ctx, m, qoi, d_x, B, d_q, d_Qint);
 }
 
+int mlmcpi_cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *rotor, double *d_x, int B, uint32_t chain0,
+                          uint64_t update0, int n_updates) {
+  if (!ctx || !rotor || B <= 0 || n_updates < 0)
+    return MLMCPI_EINVAL;
+  return qm::cluster_update(ctx, rotor, d_x, B, chain0, update0, n_updates);
+}
+int mlmcpi_schwinger_from_cluster(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_psi, double *d_x,
+                                  int B, uint32_t chain0, uint64_t draw) {
+  if (!ctx || !m || B <= 0 || m->model != MLMCPI_SCHWINGER)
+    return MLMCPI_EINVAL;
+  return schwinger::from_cluster(ctx, m, d_psi, d_x, B, chain0, draw);
+}
+
 int mlmcpi_twolevel_step(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_model *coarse,
                          const double *d_xc, double *d_xf, double *d_Sf, double *d_Scond, int B,
                          uint32_t chain0, uint64_t draw, int32_t *d_accept, double *d_deltas) {
@@ -774,6 +787,10 @@ struct mlmcpi_sampler {
   std::vector<double *> SfL, ScondL; // [L-1][B]
   std::vector<double> t_indep;
   std::vector<int> n_indep, t_sampler;
+  // QuenchedSchwingerClusterSampler: the rotor chain psi [B][Mt*Mx] and its action
+  double *psi = nullptr;
+  mlmcpi_model psi_model = {};
+  uint64_t cluster_updates = 0;
 };
 
 // tau_int / variance / ... of a device statistics object (host synchronisation)
@@ -828,6 +845,25 @@ static int coarse_draw(mlmcpi_sampler *s, int c0, int B) {
     set_i32_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, acc, 1);
     MLMCPI_LAUNCHED("set_accept");
     s->work[1] += (double)B * (s->prm.n_sweep_overrelax + s->prm.n_sweep_heatbath) * n_sites(*m);
+  } else if (s->prm.kind == MLMCPI_SAMPLER_CLUSTER) {
+    // ClusterSampler::draw (clustersampler.cc:38-50): n_updates single-cluster updates
+    const int n_updates = std::max(1, s->prm.n_updates);
+    if (m->model == MLMCPI_ROTOR) {
+      if ((rc = qm::cluster_update(ctx, m, x, B, chain0, s->cluster_updates, n_updates)))
+        return rc;
+    } else if (m->model == MLMCPI_SCHWINGER) {
+      // quenchedschwingerclustersampler.cc:40-86
+      double *psi = s->psi + (size_t)c0 * s->psi_model.M_lat;
+      if ((rc = qm::cluster_update(ctx, &s->psi_model, psi, B, chain0, s->cluster_updates, n_updates)))
+        return rc;
+      if ((rc = schwinger::from_cluster(ctx, m, psi, x, B, chain0, level_draw(s->draw, l, 0))))
+        return rc;
+    } else {
+      return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "no cluster algorithm for this action");
+    }
+    set_i32_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, acc, 1);
+    MLMCPI_LAUNCHED("set_accept");
+    s->work[1] += (double)B * n_updates; // cluster updates
   } else {
     return ctx_fail(ctx, MLMCPI_EINVAL, "unknown sampler kind");
   }
@@ -886,6 +922,7 @@ static int multilevel_draw(mlmcpi_sampler *s) {
     if (level == L - 1) {
       if ((rc = coarse_draw(s, 0, B))) // :76-78
         return rc;
+      s->cluster_updates += std::max(1, s->prm.n_updates);
     } else { // :85-86 (the two-level step keeps theta_fine and its cached actions)
       if ((rc = twolevel_step_impl(ctx, &s->model[level], &s->model[level + 1], s->state[level + 1],
                                    s->state[level], s->SfL[level], s->ScondL[level], B, s->chain0,
@@ -968,6 +1005,23 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
   }
   cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->L, ctx->stream);
   int rc;
+  if (s->prm.kind == MLMCPI_SAMPLER_CLUSTER && s->model[s->L - 1].model == MLMCPI_SCHWINGER) {
+    // quenchedschwingerclustersampler.cc:16-23: rotor chain over the Mt*Mx cells, T = 1,
+    // m0 = beta * a  (so that m0/a = beta)
+    const mlmcpi_model &mc = s->model[s->L - 1];
+    mlmcpi_model r = {};
+    r.model = MLMCPI_ROTOR;
+    r.M_lat = mc.Mt_lat * mc.Mx_lat;
+    r.T_final = 1.0;
+    r.a_lat = 1.0 / r.M_lat;
+    r.m0 = mc.beta * r.a_lat;
+    s->psi_model = r;
+    if (mlmcpi_alloc(ctx, (size_t)r.M_lat * B, &s->psi) ||
+        mlmcpi_init_state(ctx, &r, s->psi, B, chain0 + 0x00800000u, 0)) {
+      mlmcpi_sampler_destroy(s);
+      return ctx_fail(ctx, MLMCPI_ENOMEM, "cannot set up the cluster chain");
+    }
+  }
   if (s->prm.multilevel) {
     if (s->L < 2) {
       mlmcpi_sampler_destroy(s);
@@ -1018,6 +1072,8 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
       cudaEventDestroy(s->ev[k]);
     cudaStreamDestroy(s->copy_stream);
   }
+  if (s->psi)
+    cudaFree(s->psi);
   for (mlmcpi_stats *st : s->stats_sampler)
     mlmcpi_stats_destroy(st);
   for (double *d : s->SfL)
@@ -1080,6 +1136,7 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
     return rc;
   s->cache0_valid = s->L > 1;
   s->draw++;
+  s->cluster_updates += std::max(1, s->prm.n_updates);
   s->n_draws++;
   if (d_x_out) // hierarchicalsampler.cc:78-80
     if ((rc = launch_masked_copy(ctx, d_x_out, s->state[0], (size_t)mlmcpi_sample_size(&s->model[0]), B,
@@ -1135,6 +1192,7 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
     }
     s->cache0_valid = s->L > 1;
     s->draw++;
+    s->cluster_updates += std::max(1, s->prm.n_updates);
     s->n_draws++;
   }
   if (h_q)

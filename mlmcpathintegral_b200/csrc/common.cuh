@@ -498,6 +498,13 @@ DECL_MODEL_API(qm)
 DECL_MODEL_API(schwinger)
 DECL_MODEL_API(gff)
 
+namespace qm {
+int cluster_update(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t, int);
+}
+namespace schwinger {
+int from_cluster(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t, uint64_t);
+}
+
 // host helpers shared by the model files (capi.cu)
 void besselproduct_setup(double beta, BesselProductConst *bp);
 // generic elementwise / accept kernels (capi.cu)

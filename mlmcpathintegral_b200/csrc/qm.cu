@@ -413,6 +413,64 @@ __global__ void qoi_kernel(QM q, int qoi, const double *x, int B, double *out, i
   (void)dsum;
 }
 
+// ------------------------------------------------------------ Wolff cluster
+// ClusterSampler::single_cluster_update1d (sampler/clustersampler.cc:88-132) with the rotor's
+// S_ell / new_reflection / flip (qm/rotoraction.hh:226-253).  The growth of one cluster is
+// sequential, so one THREAD walks one chain; thousands of chains run side by side.  Variates:
+// one Philox stream per (chain, update): call 0 = (xbar, start site), then one uniform per
+// processed link in processing order.
+__global__ void rotor_cluster_kernel(QM q, double *x, int B, uint32_t chain0, uint64_t seed,
+                                     uint64_t update0, int n_updates) {
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= B)
+    return;
+  const int M = q.M;
+  double *xc = x + (size_t)chain * M;
+  const double coupling = 2.0 * q.m0 / q.a;
+  for (int u = 0; u < n_updates; ++u) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_CLUSTER, update0 + u, chain0 + chain, 0);
+    double u0, u1;
+    rng_uniform2(r, u0, u1);
+    const double xbar = -M_PI + 2. * M_PI * u0; // new_reflection()
+    int i0 = (int)(u1 * M);
+    if (i0 >= M)
+      i0 = M - 1;
+    double v0 = 0.0, v1 = 0.0;
+    int have = 0; // buffered uniforms
+    auto next_uniform = [&]() {
+      if (have == 0) {
+        rng_uniform2(r, v0, v1);
+        have = 2;
+      }
+      const double v = (have == 2) ? v0 : v1;
+      --have;
+      return v;
+    };
+    // process_link1d (:118-132) on the current state
+    auto process = [&](int i, int direction, int &i_next) {
+      const int nb = (i + direction + M) % M;
+      const double Sell = -coupling * cos(xc[i] - xbar) * cos(xc[nb] - xbar);
+      const double p_connect = 1. - exp(fmin(0.0, -Sell));
+      const bool bonded = next_uniform() < p_connect;
+      if (bonded)
+        xc[nb] = mod_2pi(M_PI + 2. * xbar - xc[nb]);
+      i_next = nb;
+      return bonded;
+    };
+    xc[i0] = mod_2pi(M_PI + 2. * xbar - xc[i0]); // flip(i0)
+    int i_p = i0, i_last_p;
+    bool bonded;
+    do { // forward (:96-103)
+      i_last_p = i_p;
+      bonded = process(i_p, +1, i_p);
+    } while ((i_p != i0) && bonded);
+    int i_m = i0;
+    do { // backward (:105-110)
+      bonded = process(i_m, -1, i_m);
+    } while ((i_m != i_last_p) && bonded);
+  }
+}
+
 size_t traj_smem(const QM &q) { return (size_t)WARPS * 2 * q.M * sizeof(double); }
 
 template <typename K> int prepare_smem(mlmcpi_ctx *ctx, K kernel, size_t bytes) {
@@ -569,6 +627,17 @@ int cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, 
   QM_DISPATCH(q.model,
               (cond_action_kernel<MODEL><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, B, S)));
   MLMCPI_LAUNCHED("qm::cond_action");
+  return 0;
+}
+
+int cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,
+                   uint64_t update0, int n_updates) {
+  if (m->model != MLMCPI_ROTOR)
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "cluster updates are defined for the rotor action");
+  QM q = make_qm(m);
+  rotor_cluster_kernel<<<cdiv(B, 64), 64, 0, ctx->stream>>>(q, x, B, chain0, ctx->seed, update0,
+                                                          n_updates);
+  MLMCPI_LAUNCHED("qm::cluster_update");
   return 0;
 }
 

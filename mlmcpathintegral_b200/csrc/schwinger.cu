@@ -712,6 +712,70 @@ struct CondSemiF {
   }
 };
 
+// ------------------------------------------- QuenchedSchwingerClusterSampler
+// sampler/quenchedschwingerclustersampler.cc:52-68: the rotor chain psi (length Mt*Mx)
+// fixes every plaquette; links are built by running sums.  One thread per column j for the
+// vertical links, then one thread per chain for the horizontal links of the last time slice.
+__global__ void cluster_links_vertical_kernel(SW sw, const double *psi_all, double *x_all, int B) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)Mx * B)
+    return;
+  const long long chain = t / Mx;
+  const int j = (int)(t - chain * Mx);
+  const double *psi = psi_all + chain * (long long)Mt * Mx;
+  double *x = x_all + chain * 2 * (long long)Mt * Mx;
+  for (int i = 0; i < Mt; ++i) { // zero every link of this column first (:50-51)
+    TH(x, i, j, 0) = 0.0;
+    TH(x, i, j, 1) = 0.0;
+  }
+  for (int i = 0; i < Mt - 1; ++i) {
+    const long long i_lin = (long long)i * Mx + j;
+    TH(x, i + 1, j, 1) = TH(x, i, j, 1) + psi[i_lin + 1] - psi[i_lin];
+  }
+}
+__global__ void cluster_links_horizontal_kernel(SW sw, const double *psi_all, double *x_all, int B) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= B)
+    return;
+  const double *psi = psi_all + (long long)chain * Mt * Mx;
+  double *x = x_all + (long long)chain * 2 * Mt * Mx;
+  long long i_lin = (long long)(Mt - 1) * Mx;
+  for (int j = 0; j < Mx - 1; ++j) {
+    TH(x, Mt - 1, j + 1, 0) = TH(x, Mt - 1, j, 0) - TH(x, Mt - 1, j, 1) - psi[i_lin + 1] + psi[i_lin];
+    i_lin++;
+  }
+}
+// random gauge transformation (:70-82): link (i,j,0) gets +theta(i,j) - theta(i+1,j), link
+// (i,j,1) gets +theta(i,j) - theta(i,j+1), each step followed by mod_2pi as in the reference
+__device__ __forceinline__ double gauge_angle(uint64_t seed, uint64_t draw, uint32_t gchain, int Mt, int i,
+                                              int j) {
+  Rng r = rng_init(seed, MLMCPI_STREAM_GAUGE, draw, gchain, (uint32_t)(Mt * j + i));
+  double second;
+  return rng_angle2(r, second);
+}
+__global__ void cluster_gauge_kernel(SW sw, double *x_all, int B, uint32_t chain0, uint64_t seed,
+                                     uint64_t draw) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const long long nsite = (long long)Mt * Mx;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsite * B)
+    return;
+  const long long chain = t / nsite;
+  const int s = (int)(t - chain * nsite);
+  const int j = s / Mt, i = s - j * Mt;
+  const uint32_t gchain = chain0 + (uint32_t)chain;
+  const double th = gauge_angle(seed, draw, gchain, Mt, i, j);
+  const double th_ip = gauge_angle(seed, draw, gchain, Mt, wrap_inc(i, Mt), j);
+  const double th_jp = gauge_angle(seed, draw, gchain, Mt, i, wrap_inc(j, Mx));
+  double2 *xs = reinterpret_cast<double2 *>(x_all) + t;
+  double2 v = *xs;
+  v.x = mod_2pi(mod_2pi(v.x + th) - th_ip);
+  v.y = mod_2pi(mod_2pi(v.y + th) - th_jp);
+  *xs = v;
+}
+
 int check_even(mlmcpi_ctx *ctx, const mlmcpi_model *m) {
   const int c = m->coarsening;
   if ((c == MLMCPI_COARSEN_BOTH && (m->Mt_lat % 2 || m->Mx_lat % 2)) ||
@@ -1002,6 +1066,19 @@ int cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, 
   }
   return site_reduce<1>(ctx, "schwinger::cond_action", CondSemiF{sw, m->coarsening, x}, n, B,
                         EPI_SCALE, 1.0, 0.0, S, nullptr);
+}
+
+int from_cluster(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *psi, double *x, int B,
+                 uint32_t chain0, uint64_t draw) {
+  SW sw = make_sw(ctx, m);
+  cluster_links_vertical_kernel<<<cdiv((long long)sw.Mx * B, 128), 128, 0, ctx->stream>>>(sw, psi, x, B);
+  MLMCPI_LAUNCHED("schwinger::cluster_links_vertical");
+  cluster_links_horizontal_kernel<<<cdiv(B, 64), 64, 0, ctx->stream>>>(sw, psi, x, B);
+  MLMCPI_LAUNCHED("schwinger::cluster_links_horizontal");
+  cluster_gauge_kernel<<<cdiv((long long)sw.Mt * sw.Mx * B, 256), 256, 0, ctx->stream>>>(
+      sw, x, B, chain0, ctx->seed, draw);
+  MLMCPI_LAUNCHED("schwinger::cluster_gauge");
+  return 0;
 }
 
 int qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int which, const double *x, int B, double *out,

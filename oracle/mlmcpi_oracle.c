@@ -1682,6 +1682,95 @@ int orc_twolevel_step(const orc_model *fine, const orc_model *coarse,
   return accept;
 }
 
+/* ================================================================ cluster */
+
+/* ClusterSampler::single_cluster_update1d + process_link1d, sampler/clustersampler.cc:88-132,
+ * with RotorAction::S_ell / new_reflection / flip, action/qm/rotoraction.hh:226-253.
+ * Philox: one stream per (chain, update): call 0 = (xbar, start site), then one uniform per
+ * processed link in processing order (two per call). */
+typedef struct {
+  orc_rng r;
+  double v[2];
+  int have;
+} uniform_feed;
+static double feed_next(uniform_feed *f) {
+  if (f->have == 0) {
+    orc_rng_uniform2(&f->r, &f->v[0], &f->v[1]);
+    f->have = 2;
+  }
+  const double v = (f->have == 2) ? f->v[0] : f->v[1];
+  f->have--;
+  return v;
+}
+static int process_link1d(const orc_model *m, double *x, double xbar, uniform_feed *f, int i,
+                          int direction, int *i_next) {
+  const int M = m->M_lat;
+  const int i_neighbour = (i + direction + M) % M;
+  const double Sell =
+      -2.0 * m->m0 / m->a_lat * cos(x[i] - xbar) * cos(x[i_neighbour] - xbar);
+  const double p_connect = 1. - exp(fmin(0, -Sell));
+  const int bonded = (feed_next(f) < p_connect);
+  if (bonded)
+    x[i_neighbour] = orc_mod_2pi(M_PI + 2. * xbar - x[i_neighbour]);
+  *i_next = i_neighbour;
+  return bonded;
+}
+void orc_cluster_update(const orc_model *m, uint64_t seed, uint64_t update0, int n_updates,
+                        uint32_t chain, double *x) {
+  const int M = m->M_lat;
+  for (int u = 0; u < n_updates; ++u) {
+    uniform_feed f;
+    f.have = 0;
+    orc_rng_init(&f.r, seed, ORC_STREAM_CLUSTER, update0 + u, chain, 0);
+    double u0, u1;
+    orc_rng_uniform2(&f.r, &u0, &u1);
+    const double xbar = -M_PI + 2. * M_PI * u0;
+    int i0 = (int)(u1 * M);
+    if (i0 >= M)
+      i0 = M - 1;
+    x[i0] = orc_mod_2pi(M_PI + 2. * xbar - x[i0]);
+    int i_p = i0, i_last_p, bonded;
+    do {
+      i_last_p = i_p;
+      bonded = process_link1d(m, x, xbar, &f, i_p, +1, &i_p);
+    } while ((i_p != i0) && bonded);
+    int i_m = i0;
+    do {
+      bonded = process_link1d(m, x, xbar, &f, i_m, -1, &i_m);
+    } while ((i_m != i_last_p) && bonded);
+  }
+}
+
+/* QuenchedSchwingerClusterSampler::draw, sampler/quenchedschwingerclustersampler.cc:50-82;
+ * gauge angle of site (i,j): Philox stream GAUGE, index Mt*j + i */
+void orc_schwinger_from_cluster(const orc_model *m, uint64_t seed, uint64_t draw, uint32_t chain,
+                                const double *psi, double *x) {
+  const int Mt = m->Mt_lat, Mx = m->Mx_lat;
+  for (int l = 0; l < 2 * Mt * Mx; ++l)
+    x[l] = 0.0;
+  int i_lin = 0;
+  for (int i = 0; i < Mt - 1; ++i)
+    for (int j = 0; j < Mx; ++j) {
+      x[LNK(i + 1, j, 1)] = x[LNK(i, j, 1)] + psi[i_lin + 1] - psi[i_lin];
+      i_lin++;
+    }
+  for (int j = 0; j < Mx - 1; ++j) {
+    x[LNK(Mt - 1, j + 1, 0)] =
+        x[LNK(Mt - 1, j, 0)] - x[LNK(Mt - 1, j, 1)] - psi[i_lin + 1] + psi[i_lin];
+    i_lin++;
+  }
+  for (int i = 0; i < Mt; ++i)
+    for (int j = 0; j < Mx; ++j) {
+      orc_rng r;
+      orc_rng_init(&r, seed, ORC_STREAM_GAUGE, draw, chain, (uint32_t)(Mt * j + i));
+      const double theta = uniform_angle(&r, NULL);
+      x[LNK(i, j, 0)] = orc_mod_2pi(x[LNK(i, j, 0)] + theta);
+      x[LNK(i - 1, j, 0)] = orc_mod_2pi(x[LNK(i - 1, j, 0)] - theta);
+      x[LNK(i, j, 1)] = orc_mod_2pi(x[LNK(i, j, 1)] + theta);
+      x[LNK(i, j - 1, 1)] = orc_mod_2pi(x[LNK(i, j - 1, 1)] - theta);
+    }
+}
+
 /* ============================================================== statistics */
 
 /* common/statistics.cc:4-97 (single rank): out6 = {average, variance,

@@ -40,7 +40,8 @@ enum { ORC_QOI_X2 = 0, ORC_QOI_ROTOR_CHI = 1, ORC_QOI_SCHWINGER_CHI = 2,
 /* random streams (must equal the MLMCPI_STREAM_* constants of the product) */
 enum { ORC_STREAM_INIT = 1, ORC_STREAM_HMC_MOMENTUM = 2, ORC_STREAM_HMC_ACCEPT = 3,
        ORC_STREAM_HEATBATH = 4, ORC_STREAM_FILL1 = 5, ORC_STREAM_FILL2 = 6,
-       ORC_STREAM_FILL3 = 7, ORC_STREAM_TWOLEVEL_ACCEPT = 8 };
+       ORC_STREAM_FILL3 = 7, ORC_STREAM_TWOLEVEL_ACCEPT = 8, ORC_STREAM_CLUSTER = 9,
+       ORC_STREAM_GAUGE = 10 };
 
 typedef struct {
   int model;
@@ -133,6 +134,12 @@ void orc_fill(const orc_model *fine, uint64_t seed, uint64_t draw, uint32_t chai
 int orc_twolevel_step(const orc_model *fine, const orc_model *coarse, uint64_t seed,
                       uint64_t draw, uint32_t chain, const double *x_coarse,
                       double *x_fine, double *S_fine, double *S_cond, double *out);
+
+/* ---- cluster samplers (sampler/clustersampler.cc, quenchedschwingerclustersampler.cc) ---- */
+void orc_cluster_update(const orc_model *rotor, uint64_t seed, uint64_t update0, int n_updates,
+                        uint32_t chain, double *x);
+void orc_schwinger_from_cluster(const orc_model *m, uint64_t seed, uint64_t draw, uint32_t chain,
+                                const double *psi, double *x);
 
 /* ---- statistics (common/statistics.cc) ---- */
 void orc_statistics(int k_max, int n, const double *q, double *out6);

@@ -162,6 +162,8 @@ class Oracle:
             "orc_fill": (None, [MP, u64, u64, u32, c_double_p]),
             "orc_twolevel_step": (i, [MP, MP, u64, u64, u32, c_double_p, c_double_p,
                                       c_double_p, c_double_p, c_double_p]),
+            "orc_cluster_update": (None, [MP, u64, u64, i, u32, c_double_p]),
+            "orc_schwinger_from_cluster": (None, [MP, u64, u64, u32, c_double_p, c_double_p]),
             "orc_statistics": (None, [i, i, c_double_p, c_double_p]),
         }
         for name, (res, args) in sig.items():
@@ -269,6 +271,17 @@ class Oracle:
                                          _dp(x_coarse), _dp(x_fine), C.byref(sf),
                                          C.byref(sc), _dp(out))
         return acc, x_fine, sf.value, sc.value, out
+
+    def cluster_update(self, rotor, seed, update0, n_updates, chain, x):
+        x = _arr(x).copy()
+        self.lib.orc_cluster_update(C.byref(rotor), seed, update0, n_updates, chain, _dp(x))
+        return x
+
+    def schwinger_from_cluster(self, m, seed, draw, chain, psi):
+        psi = _arr(psi)
+        x = np.zeros(self.sample_size(m))
+        self.lib.orc_schwinger_from_cluster(C.byref(m), seed, draw, chain, _dp(psi), _dp(x))
+        return x
 
     def statistics(self, k_max, q):
         q = _arr(q)

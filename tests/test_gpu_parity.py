@@ -623,3 +623,55 @@ def test_rotor_multilevel_mc_matches_exact_chit(mp, ctx):
     assert error < 3e-3 and abs(value - want) < 5 * error + 1e-3, (value, error, want, levels)
     assert all(lv["variance"] > 0 and lv["tau_int"] >= 1.0 and lv["cost_eff_usec"] > 0 for lv in levels)
     assert all(lv["samples"] >= lv["n_target"] for lv in levels)
+
+
+# ------------------------------------------------------------- cluster samplers
+
+
+def test_rotor_cluster_update_against_oracle(mp, ctx, orc):
+    rng = np.random.default_rng(21)
+    for M, m0 in [(32, 0.25), (64, 2.0), (16, 40.0)]:  # the last one: clusters wrap the ring
+        o = po.rotor(M, 4.0, m0)
+        m = to_mp(mp, o)
+        B, chain0 = 6, 3
+        x = rng.uniform(-np.pi, np.pi, (B, M))
+        xd = dev(ctx, x)
+        ctx.cluster_update(m, xd, chain0, 17, 5)
+        want = np.array([orc.cluster_update(o, SEED, 17, 5, chain0 + b, x[b]) for b in range(B)])
+        ang_close(host(xd), want, tol=1e-10, what=f"cluster M={M}")
+        assert np.abs(host(xd) - x).max() > 1e-3
+
+
+def test_schwinger_from_cluster_against_oracle(mp, ctx, orc):
+    rng = np.random.default_rng(22)
+    o = po.schwinger(8, 12, 3.0)
+    m = to_mp(mp, o)
+    B = 3
+    psi = rng.uniform(-np.pi, np.pi, (B, 8 * 12))
+    x = ctx.state(m, B)
+    ctx.schwinger_from_cluster(m, dev(ctx, psi), x, 5, 9)
+    want = np.array([orc.schwinger_from_cluster(o, SEED, 9, 5 + b, psi[b]) for b in range(B)])
+    ang_close(host(x), want, tol=1e-10, what="links from cluster")
+    # every plaquette angle is fixed by the rotor chain (gauge invariant): check one chain
+    xo = want[0]
+    P = orc.qoi(o, po.QOI_AVG_PLAQUETTE, xo)[0]
+    assert abs(host(ctx.qoi(m, mp.QOI_AVG_PLAQUETTE, x))[0] - P) < 1e-12
+
+
+def test_cluster_samplers_match_analytic_chit(mp, ctx):
+    want_rotor = float.fromhex(load("scalars")["analytic"]["rotor_chit_exact_32"])
+    want_schw = float.fromhex(load("scalars")["analytic"]["schwinger_chit_analytical_4_64"])
+    for m, qoi, want in [(mp.rotor(32, 4.0, 0.25), mp.QOI_ROTOR_CHI, want_rotor),
+                         (mp.schwinger(8, 8, 4.0), mp.QOI_SCHWINGER_CHI, want_schw)]:
+        B = 4096
+        s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_CLUSTER, n_updates=10)
+        x = ctx.state(m, B)
+        for _ in range(30):
+            s.draw(x)
+        vals = []
+        for _ in range(20):
+            s.draw(x)
+            vals.append(host(ctx.qoi(m, qoi, x)))
+        mean, err = _mean_err(np.mean(vals, axis=0))
+        assert abs(mean - want) < 5 * err, (m.model, mean, err, want)
+        s.close()
