@@ -168,7 +168,7 @@ def reference_main(a):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -378,12 +378,26 @@ def gpu_main(a):
         if world == 1 and not a.no_cpu_baseline:
             v, cores, kind, sample, _, _ = cpu_arm(a, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line of the contract, on the real stdout"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    # libraries (NCCL prints its version banner to stdout) must not pollute the one-line
+    # contract: everything else that writes to fd 1 goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         reference_main(a)
