@@ -12,6 +12,8 @@
 // site-step is the algorithmic minimum: R theta, R p, W theta, W p = 64 B.
 //
 // Reference citations relative to /root/reference/src.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -117,6 +119,71 @@ struct ChiF { // qoi/qft/qoi2dsusceptibility.cc:7-27
     acc[1] += winding(th); // sum_P theta_P = 0 exactly => Q / 2 pi = - sum of windings
   }
 };
+
+// Row-marching plaquette reduction for the action and the two QoIs.  A thread owns one
+// column and walks R rows: theta(i,j+1,0) is the next row's load, so a site costs one
+// 16-byte and one 8-byte load (the latter an L1 hit) and one transcendental; no integer
+// divisions.  MODE 0: sum (1 - cos P); 1: sum cos P; 2: sum mod_2pi(P) and sum of windings.
+template <int MODE>
+__global__ void plaq_reduce_kernel(SW sw, const double *__restrict__ x_all, int R, int chunks, int strips,
+                                   int B, double *partial) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const int per_chain = chunks * strips;
+  const int chain = blockIdx.x / per_chain;
+  const int rem = blockIdx.x - chain * per_chain;
+  const int chunk = rem / strips, strip = rem - chunk * strips;
+  const int i = strip * blockDim.x + threadIdx.x;
+  const int j0 = chunk * R, j1 = min(j0 + R, Mx);
+  double acc0 = 0.0, acc1 = 0.0;
+  if (i < Mt) {
+    const double2 *xs = reinterpret_cast<const double2 *>(x_all) + (size_t)chain * Mt * Mx;
+    const int ip = wrap_inc(i, Mt);
+    double2 cur = xs[(size_t)j0 * Mt + i];
+    for (int j = j0; j < j1; ++j) {
+      const int jp = wrap_inc(j, Mx);
+      const double2 nxt = xs[(size_t)jp * Mt + i];
+      const double t1p = xs[(size_t)j * Mt + ip].y;
+      const double P = cur.x + t1p - nxt.x - cur.y; // quenchedschwingeraction.cc:14-17
+      if (MODE == 0) {
+        acc0 += 1. - cos(P);
+      } else if (MODE == 1) {
+        acc0 += cos(P);
+      } else {
+        acc0 += mod_2pi(P);
+        acc1 += winding(P);
+      }
+      cur = nxt;
+    }
+  }
+  const double v0 = block_sum(acc0);
+  if (threadIdx.x == 0)
+    partial[(size_t)chain * per_chain + rem] = v0;
+  if (MODE == 2) {
+    const double v1 = block_sum(acc1);
+    if (threadIdx.x == 0)
+      partial[((size_t)B + chain) * per_chain + rem] = v1;
+  }
+}
+
+template <int MODE>
+int plaq_reduce(mlmcpi_ctx *ctx, const char *what, const SW &sw, const double *x, int B, int epi, double scale0,
+                double *out, int64_t *Qint) {
+  const int threads = std::min(256, ((sw.Mt + 31) / 32) * 32);
+  const int strips = cdiv(sw.Mt, threads);
+  // enough blocks for a few waves; at least 8 rows per block
+  int R = sw.Mx;
+  while (R > 8 && (long long)cdiv(sw.Mx, R) * strips * B < (long long)ctx->n_sm * 16)
+    R = (R + 1) / 2;
+  const int chunks = cdiv(sw.Mx, R);
+  const int nblk = chunks * strips;
+  const int nout = (MODE == 2) ? 2 : 1;
+  double *partial = ctx_scratch(ctx, (size_t)nout * B * nblk);
+  if (!partial)
+    return MLMCPI_ENOMEM;
+  plaq_reduce_kernel<MODE><<<nblk * B, threads, 0, ctx->stream>>>(sw, x, R, chunks, strips, B, partial);
+  MLMCPI_LAUNCHED(what);
+  return launch_reduce_finish(ctx, partial, nblk, B, nout, epi, scale0, 0.0, out, Qint);
+}
 
 // ---------------------------------------------------------------------- force
 // gather form of qft/quenchedschwingeraction.cc:68-89: each link receives +F of
@@ -874,8 +941,7 @@ int init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_
 
 int action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, double *S) {
   SW sw = make_sw(ctx, m);
-  return site_reduce<1>(ctx, "schwinger::action", ActionF{sw, x}, (long long)sw.Mt * sw.Mx, B,
-                        EPI_SCALE, sw.beta, 0.0, S, nullptr);
+  return plaq_reduce<0>(ctx, "schwinger::action", sw, x, B, EPI_SCALE, sw.beta, S, nullptr);
 }
 
 int force(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, double *f, int B) {
@@ -1086,11 +1152,10 @@ int qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int which, const double *x, int 
   SW sw = make_sw(ctx, m);
   const long long n = (long long)sw.Mt * sw.Mx;
   if (which == MLMCPI_QOI_SCHWINGER_CHI)
-    return site_reduce<2>(ctx, "schwinger::qoi_chi", ChiF{sw, x}, n, B, EPI_CHI,
-                          0.25 / (M_PI * M_PI), 0.0, out, Qint);
+    return plaq_reduce<2>(ctx, "schwinger::qoi_chi", sw, x, B, EPI_CHI, 0.25 / (M_PI * M_PI), out, Qint);
   if (which == MLMCPI_QOI_AVG_PLAQUETTE)
-    return site_reduce<1>(ctx, "schwinger::qoi_plaq", PlaqF{sw, x}, n, B, EPI_SCALE,
-                          1.0 / ((double)sw.Mx * sw.Mt), 0.0, out, nullptr);
+    return plaq_reduce<1>(ctx, "schwinger::qoi_plaq", sw, x, B, EPI_SCALE, 1.0 / ((double)sw.Mx * sw.Mt), out,
+                          nullptr);
   return ctx_fail(ctx, MLMCPI_EINVAL, "QoI not defined for the Schwinger model");
 }
 
