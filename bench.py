@@ -349,12 +349,20 @@ def gpu_main(a):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("leapfrog_dram_bytes_per_launch")
         nc = mp.sample_size(sampler.level_model(a.levels - 1)) // 2
+        steps_per_launch = (a.nt + 1) * a.steps / lf_launches if lf_launches else None
         roofline = {
-            "bound": "hbm", "kernel": "leapfrog_rowmarch_kernel", "achieved": achieved, "peak": peak,
-            "peak_source": which, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+            "bound": "hbm",
+            "kernel": "leapfrog_rowpipe2_kernel (two leapfrog steps per launch; the last, kick-only step of a "
+                      "trajectory runs in leapfrog_rowpipe_kernel)",
+            # algorithmic bytes (64 B per site and leapfrog step) / CUDA-event time of the
+            # leapfrog launches; above 1.0 because the kernel blocks two steps per pass over HBM
+            "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
+            "frac": (achieved / peak) if achieved else None,
+            "steps_per_hbm_pass": steps_per_launch,
             "traffic": traffic, "launches": lf_launches,
             "avg_launch_ms": lf_ms / lf_launches if lf_launches else None,
-            "algorithmic_bytes_per_launch": 64 * nc * B,
+            "algorithmic_bytes_per_launch": lf_bytes / lf_launches if lf_launches else None,
+            "algorithmic_bytes_per_site_step": 64,
             "share_of_step": lf_ms / ms if ms > 0 else None,
         }
         cfg = workload_config(a)

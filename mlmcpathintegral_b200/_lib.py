@@ -16,7 +16,7 @@ RENORM_NONE, RENORM_PERTURBATIVE, RENORM_NONPERTURBATIVE = range(3)
 QOI_X2, QOI_ROTOR_CHI, QOI_SCHWINGER_CHI, QOI_AVG_PLAQUETTE, QOI_PHI2 = range(5)
 SAMPLER_HMC, SAMPLER_HEATBATH, SAMPLER_CLUSTER = 0, 1, 2
 E_INVAL, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4
-OPT_EXPCOS_ENVELOPE, OPT_LEAPFROG_VARIANT, OPT_LEAPFROG_ROWS = 1, 2, 3
+OPT_EXPCOS_ENVELOPE, OPT_LEAPFROG_VARIANT, OPT_LEAPFROG_ROWS, OPT_LEAPFROG_FUSE = 1, 2, 3, 4
 
 
 class Model(C.Structure):

@@ -167,6 +167,10 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
     ctx->leapfrog_variant = value;
     return 0;
   }
+  if (option == MLMCPI_OPT_LEAPFROG_FUSE && (value == 0 || value == 1)) {
+    ctx->leapfrog_fuse = value;
+    return 0;
+  }
   if (option == MLMCPI_OPT_LEAPFROG_ROWS && value >= 0) {
     ctx->leapfrog_rows = value;
     return 0;

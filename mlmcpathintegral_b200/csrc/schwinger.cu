@@ -406,6 +406,133 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// Two leapfrog steps per HBM pass (temporal blocking).  Same row pipeline, but every thread
+// carries two stages: stage A applies step k to lattice row r+1 while stage B applies step k+1
+// to row r-1, fed from registers (own column) and three small exchange arrays (neighbouring
+// columns); still one __syncthreads per row.  The block recomputes a halo of one row of step k
+// on each side of its R output rows (R+4 theta rows and R+2 p rows are streamed in), so the
+// traffic per site is 64 + 96/R bytes for TWO steps.  p is ping-ponged as well, because the
+// halo rows of p belong to neighbouring blocks.
+template <int S>
+__global__ void __launch_bounds__(1024)
+    leapfrog_rowpipe2_kernel(SW sw, double dtpA, double dtxA, double dtpB, double dtxB,
+                             const double *__restrict__ x_in, double *__restrict__ x_out,
+                             const double *__restrict__ p_in, double *__restrict__ p_out, int R,
+                             int chunks) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const int i = threadIdx.x;
+  const int ip = wrap_inc(i, Mt), im = wrap_dec(i, Mt);
+  const int chain = blockIdx.x / chunks, chunk = blockIdx.x - chain * chunks;
+  const int j0 = chunk * R;
+  const int nrow = min(R, Mx - j0);
+  const size_t base = (size_t)chain * Mt * Mx;
+  const double2 *xin = reinterpret_cast<const double2 *>(x_in) + base;
+  const double2 *pin = reinterpret_cast<const double2 *>(p_in) + base;
+  double2 *xout = reinterpret_cast<double2 *>(x_out) + base;
+  double2 *pout = reinterpret_cast<double2 *>(p_out) + base;
+  const uint32_t row_bytes = 16u * Mt;
+  double2 *st_theta = reinterpret_cast<double2 *>(smem_raw);
+  double2 *st_p = st_theta + (size_t)S * Mt;
+  double *exA = reinterpret_cast<double *>(st_p + (size_t)S * Mt); // [2][Mt] sin P of step k
+  double *exB = exA + 2 * Mt;                                      // [2][Mt] sin P of step k+1
+  double *exT = exB + 2 * Mt;                                      // [2][Mt] theta^1(.,.,1)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(exT + 2 * Mt);
+  const double beta = sw.beta;
+
+  if (i == 0) {
+    for (int s = 0; s < S; ++s)
+      mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // logical row q = 0 .. nrow+3 is lattice row j0 - 2 + q; p rows are needed for q = 1 .. nrow+2
+  const int nq = nrow + 4;
+  auto issue = [&](int q) {
+    const int st = q % S;
+    int j = (j0 - 2 + q) % Mx;
+    if (j < 0)
+      j += Mx;
+    const bool has_p = (q >= 1 && q <= nrow + 2);
+    mbar_expect_tx(&bars[st], has_p ? 2 * row_bytes : row_bytes);
+    bulk_g2s(st_theta + (size_t)st * Mt, xin + (size_t)j * Mt, row_bytes, &bars[st]);
+    if (has_p)
+      bulk_g2s(st_p + (size_t)st * Mt, pin + (size_t)j * Mt, row_bytes, &bars[st]);
+  };
+  if (i == 0)
+    for (int q = 0; q < S && q < nq; ++q)
+      issue(q);
+  mbar_wait(&bars[0], 0);
+  mbar_wait(&bars[1 % S], 0);
+  double2 cur0 = st_theta[(size_t)(1 % S) * Mt + i];
+  double sA_prev;
+  {
+    const double2 prev = st_theta[i];
+    sA_prev = sin(prev.x + st_theta[ip].y - cur0.x - prev.y);
+  }
+  __syncthreads(); // row 0 consumed
+  if (i == 0 && S < nq)
+    issue(S);
+  double2 th1_m = make_double2(0., 0.), th1_c = th1_m, th1_p = th1_m;
+  double2 pa_m = th1_m, pa_c = th1_m, pa_p = th1_m;
+  double sB_prev = 0.0;
+  for (int t = 0; t <= nrow + 2; ++t) {
+    const bool doA = (t + 1 <= nrow + 2);
+    const int qb = t - 1;
+    const bool doB = (qb >= 1);
+    double2 nxt0 = cur0, pj = pa_p;
+    double sA = 0.0, sB = 0.0;
+    if (doA) { // stage A, row qa = t + 1: sin of the step-k plaquette
+      const int qa = t + 1;
+      const int st = qa % S, stn = (qa + 1) % S;
+      mbar_wait(&bars[stn], ((qa + 1) / S) & 1);
+      nxt0 = st_theta[(size_t)stn * Mt + i];
+      const double t1p = st_theta[(size_t)st * Mt + ip].y;
+      pj = st_p[(size_t)st * Mt + i];
+      sA = sin(cur0.x + t1p - nxt0.x - cur0.y);
+      exA[(t & 1) * Mt + i] = sA;
+    }
+    if (doB) { // stage B, row qb: sin of the step-(k+1) plaquette from theta^1
+      const double t1p = exT[(qb & 1) * Mt + ip];
+      sB = sin(th1_m.x + t1p - th1_c.x - th1_m.y);
+      exB[(t & 1) * Mt + i] = sB;
+    }
+    __syncthreads();
+    // every thread is done with theta^0 / p^0 row t + 1: refill its stage
+    if (i == 0 && t + 1 + S < nq)
+      issue(t + 1 + S);
+    if (doA) {
+      const double sA_im = exA[(t & 1) * Mt + im];
+      const double F = beta * sA;
+      pj.x -= dtpA * (F - beta * sA_prev);
+      pj.y -= dtpA * (beta * sA_im - F);
+      th1_p = make_double2(cur0.x + dtxA * pj.x, cur0.y + dtxA * pj.y);
+      pa_p = pj;
+      exT[((t + 1) & 1) * Mt + i] = th1_p.y;
+      sA_prev = sA;
+      cur0 = nxt0;
+    }
+    if (doB) {
+      if (qb >= 2) {
+        const double sB_im = exB[(t & 1) * Mt + im];
+        const double F = beta * sB;
+        double2 pb = pa_m;
+        pb.x -= dtpB * (F - beta * sB_prev);
+        pb.y -= dtpB * (beta * sB_im - F);
+        const size_t g = (size_t)(j0 + qb - 2) * Mt + i;
+        pout[g] = pb;
+        xout[g] = make_double2(th1_m.x + dtxB * pb.x, th1_m.y + dtxB * pb.y);
+      }
+      sB_prev = sB;
+    }
+    th1_m = th1_c;
+    th1_c = th1_p;
+    pa_m = pa_c;
+    pa_c = pa_p;
+  }
+}
+
 // --------------------------------------------------------------------- sweeps
 // colours: 0 {mu=0, j even}, 1 {mu=0, j odd}, 2 {mu=1, i even}, 3 {mu=1, i odd}
 template <bool HEATBATH>
@@ -899,6 +1026,28 @@ int leapfrog_step(mlmcpi_ctx *ctx, const SW &sw, double dt_p, double dt_x, bool 
   return 0;
 }
 
+// two fused leapfrog steps (step A then step B) on all chains; false if the shape is not supported
+bool leapfrog_pair_supported(const mlmcpi_ctx *ctx, const SW &sw) {
+  return ctx->leapfrog_variant == 0 && ctx->leapfrog_fuse && sw.Mt <= 1024 && sw.Mt % 32 == 0 && sw.Mx >= 8;
+}
+int leapfrog_pair(mlmcpi_ctx *ctx, const SW &sw, double dtpA, double dtxA, double dtpB, double dtxB,
+                  const double *x_in, double *x_out, const double *p_in, double *p_out, int B) {
+  // halo overhead is 96/R bytes per site and two steps: 32 rows per block by default
+  int R = ctx->leapfrog_rows > 0 ? ctx->leapfrog_rows : 32;
+  if (R > sw.Mx)
+    R = sw.Mx;
+  const int chunks = cdiv(sw.Mx, R);
+  constexpr int S = 6;
+  const size_t smem = (size_t)S * 32 * sw.Mt + 48 * sw.Mt + 8 * S;
+  auto kern = leapfrog_rowpipe2_kernel<S>;
+  if (smem > 48 * 1024)
+    MLMCPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<chunks * B, sw.Mt, smem, ctx->stream>>>(sw, dtpA, dtxA, dtpB, dtxB, x_in, x_out, p_in, p_out, R,
+                                                chunks);
+  MLMCPI_LAUNCHED("schwinger::leapfrog_rowpipe2");
+  return 0;
+}
+
 // trajectory of sampler/hmcsampler.cc:31-46.  x_first: state read by the first step;
 // bufA/bufB: ping-pong trial buffers; returns the buffer holding the final state.
 int trajectory(mlmcpi_ctx *ctx, const SW &sw, int nt, double dt, const double *x_first,
@@ -906,22 +1055,52 @@ int trajectory(mlmcpi_ctx *ctx, const SW &sw, int nt, double dt, const double *x
   const double *in = x_first;
   double *out = bufA;
   double *last = nullptr;
+  const size_t n = (size_t)2 * sw.Mt * sw.Mx * B;
+  // the fused two-step kernel ping-pongs p as well
+  double *p_alt = nullptr, *p_cur = p;
+  const bool fuse = leapfrog_pair_supported(ctx, sw) && nt >= 2 && sw.Mt * 240 + 64 <= 200 * 1024;
+  if (fuse) {
+    p_alt = ctx_work(ctx, 7, n);
+    if (!p_alt)
+      return MLMCPI_ENOMEM;
+  }
+  auto dtp = [&](int k) { return (k == 0 || k == nt) ? 0.5 * dt : dt; };
+  auto dtx = [&](int k) { return (k == nt) ? 0.0 : dt; };
   prof_begin(ctx);
-  for (int k = 0; k <= nt; ++k) {
-    const double dt_p = (k == 0 || k == nt) ? 0.5 * dt : dt;
-    const bool drift = (k != nt);
-    int rc = leapfrog_step(ctx, sw, dt_p, drift ? dt : 0.0, drift, in, out, p, B);
-    if (rc)
-      return rc;
-    if (drift) {
+  uint64_t launches = 0;
+  int k = 0;
+  while (k <= nt) {
+    int rc;
+    if (fuse && k + 1 <= nt) { // steps k and k+1 in one pass
+      double *p_next = (p_cur == p) ? p_alt : p;
+      rc = leapfrog_pair(ctx, sw, dtp(k), dtx(k), dtp(k + 1), dtx(k + 1), in, out, p_cur, p_next, B);
+      if (rc)
+        return rc;
+      p_cur = p_next;
       last = out;
       in = out;
       out = (out == bufA) ? bufB : bufA;
+      k += 2;
+    } else {
+      const bool drift = (k != nt);
+      // single step; p updated in place in whichever buffer currently holds it
+      rc = leapfrog_step(ctx, sw, dtp(k), dtx(k), drift, in, out, p_cur, B);
+      if (rc)
+        return rc;
+      if (drift) {
+        last = out;
+        in = out;
+        out = (out == bufA) ? bufB : bufA;
+      }
+      k += 1;
     }
+    ++launches;
   }
+  if (p_cur != p) // hand the momenta back in the caller's buffer
+    MLMCPI_CUDA(cudaMemcpyAsync(p, p_cur, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   // algorithmic bytes: R theta, R p, W theta, W p per site-step; the final kick writes no theta
   const double site_bytes = 16.0 * (double)sw.Mt * sw.Mx * B;
-  prof_end(ctx, (uint64_t)nt + 1, site_bytes * (4.0 * nt + 3.0));
+  prof_end(ctx, launches, site_bytes * (4.0 * nt + 3.0));
   *x_final = last; // nullptr when nt == 0 (state unchanged)
   return 0;
 }
