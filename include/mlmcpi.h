@@ -98,9 +98,11 @@ int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed);
  * step): 0 = TMA/mbarrier row pipeline (default), 1 = register row march, 2 = generic.
  * MLMCPI_OPT_LEAPFROG_ROWS: lattice rows per thread block (0 = default).
  * MLMCPI_OPT_LEAPFROG_FUSE: 1 (default) = two leapfrog steps per pass over HBM (temporal
- * blocking, variant 0 only), 0 = one step per pass. */
+ * blocking, variant 0 only), 0 = one step per pass.
+ * MLMCPI_OPT_SWEEP_REVERSE: 1 = the coloured sweeps visit the colours in descending order (the
+ * exact reverse of the default; used to make a sequence of sweeps a reversible kernel). */
 enum { MLMCPI_OPT_EXPCOS_ENVELOPE = 1, MLMCPI_OPT_LEAPFROG_VARIANT = 2, MLMCPI_OPT_LEAPFROG_ROWS = 3,
-       MLMCPI_OPT_LEAPFROG_FUSE = 4 };
+       MLMCPI_OPT_LEAPFROG_FUSE = 4, MLMCPI_OPT_SWEEP_REVERSE = 5 };
 int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value);
 /* number of kernels this context has launched so far */
 uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx);

@@ -167,6 +167,10 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
     ctx->leapfrog_variant = value;
     return 0;
   }
+  if (option == MLMCPI_OPT_SWEEP_REVERSE && (value == 0 || value == 1)) {
+    ctx->sweep_reverse = value;
+    return 0;
+  }
   if (option == MLMCPI_OPT_LEAPFROG_FUSE && (value == 0 || value == 1)) {
     ctx->leapfrog_fuse = value;
     return 0;
@@ -840,12 +844,39 @@ static int coarse_draw(mlmcpi_sampler *s, int c0, int B) {
     }
     s->work[0] += (double)B * n_rep * (s->prm.nt + 1) * n_sites(*m);
   } else if (s->prm.kind == MLMCPI_SAMPLER_HEATBATH) {
-    for (int k = 0; k < s->prm.n_sweep_overrelax; ++k)
-      if ((rc = mlmcpi_overrelax_sweep(ctx, m, x, B)))
-        return rc;
-    for (int k = 0; k < s->prm.n_sweep_heatbath; ++k)
-      if ((rc = mlmcpi_heatbath_sweep(ctx, m, x, B, chain0, level_draw(s->draw, l, k))))
-        return rc;
+    // OverrelaxedHeatBathSampler::draw, overrelaxedheatbathsampler.cc:8-31.  As the coarse sampler
+    // of a hierarchy the draw must be a REVERSIBLE kernel (delayed acceptance): every colour update
+    // is reversible, so the whole sequence is run forwards or exactly backwards with probability
+    // 1/2 (one Philox bit per draw).  A stand-alone sampler keeps the reference's order.
+    bool backwards = false;
+    if (s->L > 1) {
+      // splitmix64 of (seed, draw): the schedule must not depend on the state
+      uint64_t h = ctx->seed ^ (0x9E3779B97F4A7C15ull * (s->draw + 1));
+      h ^= h >> 30;
+      h *= 0xBF58476D1CE4E5B9ull;
+      h ^= h >> 27;
+      h *= 0x94D049BB133111EBull;
+      h ^= h >> 31;
+      backwards = (h & 1u) != 0;
+    }
+    const int saved = ctx->sweep_reverse;
+    ctx->sweep_reverse = backwards ? 1 : saved;
+    rc = 0;
+    for (int pass = 0; pass < 2 && !rc; ++pass) {
+      const bool do_hb = backwards ? (pass == 0) : (pass == 1);
+      if (do_hb) {
+        for (int k = 0; k < s->prm.n_sweep_heatbath && !rc; ++k) {
+          const int kk = backwards ? s->prm.n_sweep_heatbath - 1 - k : k;
+          rc = mlmcpi_heatbath_sweep(ctx, m, x, B, chain0, level_draw(s->draw, l, kk));
+        }
+      } else {
+        for (int k = 0; k < s->prm.n_sweep_overrelax && !rc; ++k)
+          rc = mlmcpi_overrelax_sweep(ctx, m, x, B);
+      }
+    }
+    ctx->sweep_reverse = saved;
+    if (rc)
+      return rc;
     set_i32_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, acc, 1);
     MLMCPI_LAUNCHED("set_accept");
     s->work[1] += (double)B * (s->prm.n_sweep_overrelax + s->prm.n_sweep_heatbath) * n_sites(*m);

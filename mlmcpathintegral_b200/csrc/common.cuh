@@ -28,6 +28,7 @@ struct mlmcpi_ctx {
   int leapfrog_variant = 0; // MLMCPI_OPT_LEAPFROG_VARIANT: 0 TMA row pipeline, 1 register row march, 2 generic
   int leapfrog_rows = 0;    // MLMCPI_OPT_LEAPFROG_ROWS: rows per block (0 = default)
   int leapfrog_fuse = 1;    // MLMCPI_OPT_LEAPFROG_FUSE: two leapfrog steps per HBM pass
+  int sweep_reverse = 0;    // MLMCPI_OPT_SWEEP_REVERSE: colours visited in descending order
   uint64_t launches = 0;
   int n_sm = 148;
   std::string err;

@@ -388,7 +388,8 @@ static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool 
     return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need even lattice extents");
   GF g = make_gf(m);
   const int blocks = cdiv((long long)g.N * B, 256);
-  for (int colour = 0; colour < 2; ++colour) {
+  for (int pass = 0; pass < 2; ++pass) {
+    const int colour = ctx->sweep_reverse ? 1 - pass : pass;
     if (heatbath)
       sweep_colour_kernel<true><<<blocks, 256, 0, ctx->stream>>>(g, colour, x, B, chain0, ctx->seed,
                                                                 draw);

@@ -281,11 +281,12 @@ __global__ void hmc_step_kernel(QM q, int nt, double dt, double *x, int B, uint3
 // rotor only (qm/rotoraction.cc:21-56); colours: even sites, then odd sites
 template <bool HEATBATH>
 __global__ void rotor_sweep_kernel(QM q, double *x, int B, uint32_t chain0, uint64_t seed,
-                                   uint64_t draw) {
+                                   uint64_t draw, int reverse) {
   WARP_SETUP
   const int M = q.M;
   double *xc = x + (size_t)c_safe * M;
-  for (int colour = 0; colour < 2; ++colour) {
+  for (int pass = 0; pass < 2; ++pass) {
+    const int colour = reverse ? 1 - pass : pass;
     if (active)
       for (int s = 2 * lane + colour; s < M; s += 64) {
         const double x_m = xc[s == 0 ? M - 1 : s - 1], x_p = xc[s == M - 1 ? 0 : s + 1];
@@ -569,7 +570,7 @@ int overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B) {
   if (m->M_lat % 2)
     return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need an even number of sites");
   QM q = make_qm(m);
-  rotor_sweep_kernel<false><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, B, 0, 0, 0);
+  rotor_sweep_kernel<false><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, B, 0, 0, 0, ctx->sweep_reverse);
   MLMCPI_LAUNCHED("qm::overrelax_sweep");
   return 0;
 }
@@ -581,7 +582,8 @@ int heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uin
   if (m->M_lat % 2)
     return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need an even number of sites");
   QM q = make_qm(m);
-  rotor_sweep_kernel<true><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, B, chain0, ctx->seed, draw);
+  rotor_sweep_kernel<true><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, B, chain0, ctx->seed, draw,
+                                                                     ctx->sweep_reverse);
   MLMCPI_LAUNCHED("qm::heatbath_sweep");
   return 0;
 }

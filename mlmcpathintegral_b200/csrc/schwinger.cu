@@ -727,7 +727,7 @@ __global__ void fill_both_step23_kernel(SW sw, BesselProductConst bp, double *x_
 // Philox counters instead of waiting for them (counter-based RNG makes the three
 // phases of the reference embarrassingly parallel).  80 B of HBM traffic per cell.
 template <bool APPROX>
-__global__ void prolong_fill_both_kernel(SW sw, BesselProductConst bp, const double *xc_all,
+__global__ void __launch_bounds__(128, 8) prolong_fill_both_kernel(SW sw, BesselProductConst bp, const double *xc_all,
                                          double *x_all, int B, uint32_t chain0, uint64_t seed,
                                          uint64_t draw) {
   const int Mt = sw.Mt, Mx = sw.Mx, Mtc = Mt / 2, Mxc = Mx / 2;
@@ -1196,7 +1196,8 @@ static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool 
     return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need even lattice extents");
   SW sw = make_sw(ctx, m);
   const long long n = (long long)sw.Mt * sw.Mx / 2 * B;
-  for (int colour = 0; colour < 4; ++colour) {
+  for (int pass = 0; pass < 4; ++pass) {
+    const int colour = ctx->sweep_reverse ? 3 - pass : pass;
     if (heatbath)
       sweep_colour_kernel<true><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sw, colour, x, B, chain0,
                                                                       ctx->seed, draw);
