@@ -93,7 +93,9 @@ int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed);
 /* options.  MLMCPI_OPT_EXPCOS_ENVELOPE: proposal of the ExpCos rejection sampler
  * (distribution/expcosdistribution.hh:50-65): 0 = the reference's Gaussian envelope
  * (variance 2 pi^2/tau, ~22 % acceptance), 1 = chord-bound envelope (variance
- * pi^2/(4 tau), ~64 % acceptance; default).  The sampled distribution is the same. */
+ * pi^2/(4 tau), ~64 % acceptance), 2 = chord bound for tau < 64 and the Taylor bound
+ * 1 - cos x >= x^2/2 (1 - x^2/12) for tau >= 64 (> 89 % acceptance, 99.7 % at tau = 2048;
+ * default).  The sampled distribution is the same (variant 2 truncates a tail mass < 1e-33). */
 /* MLMCPI_OPT_LEAPFROG_VARIANT (2-D Schwinger leapfrog kernel; all variants compute the same
  * step): 0 = TMA/mbarrier row pipeline (default), 1 = register row march, 2 = generic.
  * MLMCPI_OPT_LEAPFROG_ROWS: lattice rows per thread block (0 = default).
@@ -173,6 +175,12 @@ int mlmcpi_fill(mlmcpi_ctx *ctx, const mlmcpi_model *fine, double *d_x, int B, u
  * (TwoLevelMetropolisStep::draw lines 40-42 in one pass) */
 int mlmcpi_prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *d_xc,
                         double *d_x, int B, uint32_t chain0, uint64_t draw);
+/* the same, and in the same pass the two reductions TwoLevelMetropolisStep::draw needs of the
+ * new trial state (lines 48 and 65-66): d_S[0..B) = Action::evaluate(theta'), d_S[B..2B) =
+ * ConditionedFineAction::evaluate(theta').  For the Schwinger model with coarsening `both` they
+ * are accumulated from the cell's links while these are still in registers */
+int mlmcpi_prolong_fill_eval(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *d_xc,
+                             double *d_x, int B, uint32_t chain0, uint64_t draw, double *d_S);
 
 /* n_updates Wolff single-cluster updates of the rotor (ClusterSampler::single_cluster_update1d,
  * sampler/clustersampler.cc:88-132 with RotorAction::S_ell / new_reflection / flip,

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmlmcpi.so")
+# MLMCPI_LIB: alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("MLMCPI_LIB") or os.path.join(HERE, "libmlmcpi.so")
 
 HO, QUARTIC, ROTOR, SCHWINGER, GFF = 0, 1, 2, 3, 4
 COARSEN_BOTH, COARSEN_TEMPORAL, COARSEN_SPATIAL, COARSEN_ALTERNATE, COARSEN_ROTATE = range(5)
@@ -87,6 +88,7 @@ SIGNATURES = {
     "mlmcpi_restrict": (_i, [_vp, _MP, _vp, _vp, _i]),
     "mlmcpi_fill": (_i, [_vp, _MP, _vp, _i, _u32, _u64]),
     "mlmcpi_prolong_fill": (_i, [_vp, _MP, _vp, _vp, _i, _u32, _u64]),
+    "mlmcpi_prolong_fill_eval": (_i, [_vp, _MP, _vp, _vp, _i, _u32, _u64, _vp]),
     "mlmcpi_cluster_update": (_i, [_vp, _MP, _vp, _i, _u32, _u64, _i]),
     "mlmcpi_schwinger_from_cluster": (_i, [_vp, _MP, _vp, _vp, _i, _u32, _u64]),
     "mlmcpi_cond_action": (_i, [_vp, _MP, _vp, _i, _vp]),

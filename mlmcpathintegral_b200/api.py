@@ -125,9 +125,9 @@ class Context:
     def set_option(self, option, value):
         self._ck(L.mlmcpi_set_option(self.h, option, value))
 
-    def set_expcos_envelope(self, tight=True):
-        """ExpCos proposal: reference envelope (False) or the tighter chord bound (True, default)"""
-        self._ck(L.mlmcpi_set_option(self.h, _lib.OPT_EXPCOS_ENVELOPE, int(bool(tight))))
+    def set_expcos_envelope(self, variant=2):
+        """ExpCos proposal: 0 reference envelope, 1 chord bound, 2 chord + Taylor bound (default)"""
+        self._ck(L.mlmcpi_set_option(self.h, _lib.OPT_EXPCOS_ENVELOPE, int(variant)))
 
     @property
     def launches(self):
@@ -205,6 +205,13 @@ class Context:
     def prolong_fill(self, fine, xc, x, chain0=0, draw=0):
         self._ck(L.mlmcpi_prolong_fill(self.h, C.byref(fine), _ptr(xc), _ptr(x), x.shape[0], chain0,
                                        draw))
+
+    def prolong_fill_eval(self, fine, xc, x, chain0=0, draw=0):
+        """prolong_fill plus (S_f(theta'), S_cond(theta')) of the new state, one pass"""
+        S = self.empty(2 * x.shape[0])
+        self._ck(L.mlmcpi_prolong_fill_eval(self.h, C.byref(fine), _ptr(xc), _ptr(x), x.shape[0], chain0,
+                                            draw, _ptr(S)))
+        return S[:x.shape[0]], S[x.shape[0]:]
 
     def cluster_update(self, rotor_model, x, chain0=0, update0=0, n_updates=1):
         self._ck(L.mlmcpi_cluster_update(self.h, C.byref(rotor_model), _ptr(x), x.shape[0], chain0,

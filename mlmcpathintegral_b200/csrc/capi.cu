@@ -159,7 +159,7 @@ int mlmcpi_sync(mlmcpi_ctx *ctx) {
   return 0;
 }
 int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
-  if (option == MLMCPI_OPT_EXPCOS_ENVELOPE && (value == 0 || value == 1)) {
+  if (option == MLMCPI_OPT_EXPCOS_ENVELOPE && value >= 0 && value <= 2) {
     ctx->expcos_envelope = value;
     return 0;
   }
@@ -457,19 +457,22 @@ void besselproduct_setup(double beta, BesselProductConst *bp) {
 }
 
 // ===================================================== small generic kernels
+// one warp per chain: lanes stride over the per-block partials, fixed-order shuffle tree
 __global__ void reduce_finish_kernel(const double *partial, int nblk, int B, int nout, int epi,
                                      double scale0, double scale1, double *out, int64_t *Qint) {
-  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (chain >= B)
     return;
   double s[2] = {0.0, 0.0};
   for (int k = 0; k < nout; ++k) {
     const double *p = partial + ((size_t)k * B + chain) * nblk;
     double acc = 0.0;
-    for (int b = 0; b < nblk; ++b)
+    for (int b = lane; b < nblk; b += 32)
       acc += p[b];
-    s[k] = acc;
+    s[k] = warp_sum(acc);
   }
+  if (lane != 0)
+    return;
   if (epi == EPI_CHI) {
     out[chain] = scale0 * s[0] * s[0];
     if (Qint)
@@ -483,7 +486,7 @@ __global__ void reduce_finish_kernel(const double *partial, int nblk, int B, int
 
 int launch_reduce_finish(mlmcpi_ctx *ctx, const double *partial, int nblk, int B, int nout, int epi,
                          double scale0, double scale1, double *out, int64_t *Qint) {
-  reduce_finish_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(partial, nblk, B, nout, epi, scale0,
+  reduce_finish_kernel<<<cdiv(B, 4), 128, 0, ctx->stream>>>(partial, nblk, B, nout, epi, scale0,
                                                              scale1, out, Qint);
   MLMCPI_LAUNCHED("reduce_finish");
   return 0;
@@ -543,15 +546,20 @@ __global__ void masked_copy1_kernel(double *dst, const double *src, size_t n, in
     dst[t] = src[t];
 }
 
-// montecarlo/twolevelmetropolisstep.cc:48-81; red = {S_f', S_c(theta_C), S_c(phi_c), S_cond'}
+// montecarlo/twolevelmetropolisstep.cc:48-81.  red = {S_f', S_cond'}; ScC = S_c(theta_C),
+// Scc = S_c(phi_c).  Sf_out[c] = S_f of the state after the step (may alias Sf_in; nullptr: not
+// wanted), Scond is updated in place where accepted unless update_scond == 0.
 __global__ void twolevel_accept_kernel(int B, uint32_t chain0, uint64_t seed, uint64_t draw,
-                                       const double *red, double *Sf, double *Scond,
-                                       const int32_t *mask, int32_t *accept, double *deltas) {
+                                       const double *red, const double *ScC_all, const double *Scc_all,
+                                       const double *Sf_in, double *Sf_out, double *Scond,
+                                       int update_scond, const int32_t *mask, int32_t *accept,
+                                       double *deltas) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= B)
     return;
-  const double Sf_prime = red[c], ScC = red[B + c], Scc = red[2 * B + c], Scond_prime = red[3 * B + c];
-  const double dS_fine = Sf_prime - Sf[c];
+  const double Sf_prime = red[c], Scond_prime = red[B + c], ScC = ScC_all[c], Scc = Scc_all[c];
+  const double Sf_cur = Sf_in[c];
+  const double dS_fine = Sf_prime - Sf_cur;
   const double dS_coarse = ScC - Scc;
   const double dS_trial = Scond[c] - Scond_prime;
   const double dS = dS_fine + dS_coarse + dS_trial;
@@ -564,10 +572,10 @@ __global__ void twolevel_accept_kernel(int B, uint32_t chain0, uint64_t seed, ui
   }
   if (mask && !mask[c])
     acc = false; // the cascade already stopped for this chain (hierarchicalsampler.cc:73-74)
-  if (acc) {
-    Sf[c] = Sf_prime;
+  if (Sf_out)
+    Sf_out[c] = acc ? Sf_prime : Sf_cur;
+  if (acc && update_scond)
     Scond[c] = Scond_prime;
-  }
   accept[c] = acc ? 1 : 0;
   if (deltas) {
     deltas[3 * (size_t)c] = dS_fine;
@@ -649,10 +657,19 @@ int launch_masked_copy(mlmcpi_ctx *ctx, double *dst, const double *src, size_t n
     return ctx_fail(ctx, MLMCPI_EINVAL, "unknown model");                                          \
   } while (0)
 
+// d_ScC / d_Scc: S_c(theta_C) and S_c(phi_c) when the caller already knows them (nullptr: computed
+// here); d_Sf_out: S_f of the state after the step (nullptr: d_Sf is updated in place);
+// update_scond: keep d_Scond current
+struct TwoLevelKnown {
+  const double *d_ScC = nullptr, *d_Scc = nullptr;
+  double *d_Sf_out = nullptr;
+  bool sf_in_place = true, update_scond = true;
+};
 static int twolevel_step_impl(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_model *coarse,
                               const double *d_xc, double *d_xf, double *d_Sf, double *d_Scond, int B,
                               uint32_t chain0, uint64_t draw, const int32_t *d_mask,
-                              int32_t *d_accept, double *d_deltas);
+                              int32_t *d_accept, double *d_deltas,
+                              const TwoLevelKnown &known = TwoLevelKnown());
 
 extern "C" {
 
@@ -703,6 +720,10 @@ int mlmcpi_prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_
                         int B, uint32_t chain0, uint64_t draw) {
   DISPATCH(m, prolong_fill, ctx, m, d_xc, d_x, B, chain0, draw);
 }
+int mlmcpi_prolong_fill_eval(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_xc, double *d_x,
+                             int B, uint32_t chain0, uint64_t draw, double *d_S) {
+  DISPATCH(m, prolong_fill_eval, ctx, m, d_xc, d_x, B, chain0, draw, d_S);
+}
 int mlmcpi_cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_x, int B, double *d_S) {
   DISPATCH(m, cond_action, ctx, m, d_x, B, d_S);
 }
@@ -737,31 +758,39 @@ int mlmcpi_twolevel_step(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi
 static int twolevel_step_impl(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_model *coarse,
                               const double *d_xc, double *d_xf, double *d_Sf, double *d_Scond, int B,
                               uint32_t chain0, uint64_t draw, const int32_t *d_mask,
-                              int32_t *d_accept, double *d_deltas) {
+                              int32_t *d_accept, double *d_deltas, const TwoLevelKnown &known) {
   if (!ctx || !fine || !coarse || B <= 0)
     return MLMCPI_EINVAL;
   const size_t nf = (size_t)mlmcpi_sample_size(fine), nc = (size_t)mlmcpi_sample_size(coarse);
   double *theta_prime = ctx_work(ctx, 4, nf * B);
-  double *theta_C = ctx_work(ctx, 5, nc * B);
   double *red = ctx_work(ctx, 6, (size_t)5 * B);
-  if (!theta_prime || !theta_C || !red)
+  if (!theta_prime || !red)
     return MLMCPI_ENOMEM;
   int32_t *acc = d_accept ? d_accept : reinterpret_cast<int32_t *>(red + 4 * B);
   int rc;
-  if ((rc = mlmcpi_prolong_fill(ctx, fine, d_xc, theta_prime, B, chain0, draw)))      // :40-42
+  // :40-42, :48 and :65-66 in one pass: theta' = fill(prolong(phi_c)), S_f(theta'), S_cond(theta')
+  if ((rc = mlmcpi_prolong_fill_eval(ctx, fine, d_xc, theta_prime, B, chain0, draw, red)))
     return rc;
-  if ((rc = mlmcpi_action(ctx, fine, theta_prime, B, red)))                           // :48
-    return rc;
-  if ((rc = mlmcpi_restrict(ctx, fine, d_xf, theta_C, B)))                            // :55
-    return rc;
-  if ((rc = mlmcpi_action(ctx, coarse, theta_C, B, red + B)))                         // :57
-    return rc;
-  if ((rc = mlmcpi_action(ctx, coarse, d_xc, B, red + 2 * B)))                        // :58
-    return rc;
-  if ((rc = mlmcpi_cond_action(ctx, fine, theta_prime, B, red + 3 * B)))              // :65-66
-    return rc;
-  twolevel_accept_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, chain0, ctx->seed, draw, red, d_Sf,
-                                                               d_Scond, d_mask, acc, d_deltas);
+  const double *ScC = known.d_ScC, *Scc = known.d_Scc;
+  if (!ScC) {
+    double *theta_C = ctx_work(ctx, 5, nc * B);
+    if (!theta_C)
+      return MLMCPI_ENOMEM;
+    if ((rc = mlmcpi_restrict(ctx, fine, d_xf, theta_C, B)))                          // :55
+      return rc;
+    if ((rc = mlmcpi_action(ctx, coarse, theta_C, B, red + 2 * B)))                   // :57
+      return rc;
+    ScC = red + 2 * B;
+  }
+  if (!Scc) {
+    if ((rc = mlmcpi_action(ctx, coarse, d_xc, B, red + 3 * B)))                      // :58
+      return rc;
+    Scc = red + 3 * B;
+  }
+  double *Sf_out = known.d_Sf_out ? known.d_Sf_out : (known.sf_in_place ? d_Sf : nullptr);
+  twolevel_accept_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, chain0, ctx->seed, draw, red, ScC, Scc, d_Sf,
+                                                               Sf_out, d_Scond, known.update_scond ? 1 : 0,
+                                                               d_mask, acc, d_deltas);
   MLMCPI_LAUNCHED("twolevel_accept");
   return launch_masked_copy(ctx, d_xf, theta_prime, nf, B, acc);                      // :78-88
 }
@@ -783,6 +812,10 @@ struct mlmcpi_sampler {
   // already known -- bit for bit, the reductions being deterministic.
   double *Sf0 = nullptr, *Scond0 = nullptr;
   bool cache0_valid = false;
+  // hierarchical cascade: S_l of the level states right after the restriction chain (= S_c(theta_C)
+  // of the step one level finer, and S_f(theta) of the step on this level) and after the level's
+  // own update (= S_c(phi_c) of the step one level finer); [L][B] each
+  double *S_old = nullptr, *S_new = nullptr;
   cudaStream_t copy_stream = nullptr; // H2D stream of mlmcpi_sampler_draw_host
   cudaEvent_t ev[9] = {};
   int32_t *acc = nullptr, *acc_step = nullptr;          // [B]
@@ -916,25 +949,44 @@ static int sampler_draw_range(mlmcpi_sampler *s, int c0, int B, bool cache0_vali
   int32_t *acc = s->acc + c0;
   auto st = [&](int l) { return s->state[l] + (size_t)c0 * mlmcpi_sample_size(&s->model[l]); };
   int rc;
-  for (int l = 1; l < L; ++l) // :57-60
+  // S_l of every coarse level state right after the restriction chain / after its own update.
+  // theta_C = restrict(theta_fine) of TwoLevelMetropolisStep::draw line 55 IS the level state
+  // produced by the restriction chain, so its action (line 57) is S_old, and S_c(phi_c) (line 58)
+  // is S_new of the coarser level: one restriction and two reductions per step are not repeated.
+  auto S_old = [&](int l) { return s->S_old + (size_t)l * s->B + c0; };
+  auto S_new = [&](int l) { return s->S_new + (size_t)l * s->B + c0; };
+  for (int l = 1; l < L; ++l) { // :57-60
     if ((rc = mlmcpi_restrict(ctx, &s->model[l - 1], st(l - 1), st(l), B)))
       return rc;
+    if ((rc = mlmcpi_action(ctx, &s->model[l], st(l), B, S_old(l))))
+      return rc;
+  }
   if ((rc = coarse_draw(s, c0, B))) // :62-66
     return rc;
   count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, acc, s->counters + (L - 1));
   MLMCPI_LAUNCHED("count_accept");
+  if (L > 1 && (rc = mlmcpi_action(ctx, &s->model[L - 1], st(L - 1), B, S_new(L - 1))))
+    return rc;
   for (int l = L - 2; l >= 0; --l) {
     // TwoLevelMetropolisStep::set_state, montecarlo/twolevelmetropolisstep.cc:92-97
-    double *Sf = ((l == 0) ? s->Sf0 : s->Sf) + c0, *Scond = ((l == 0) ? s->Scond0 : s->Scond) + c0;
-    if (l > 0 || !cache0_valid) {
+    double *Sf = (l == 0) ? s->Sf0 + c0 : S_old(l), *Scond = ((l == 0) ? s->Scond0 : s->Scond) + c0;
+    if (l > 0) {
+      if ((rc = mlmcpi_cond_action(ctx, &s->model[l], st(l), B, Scond)))
+        return rc;
+    } else if (!cache0_valid) {
       if ((rc = mlmcpi_action(ctx, &s->model[l], st(l), B, Sf)))
         return rc;
       if ((rc = mlmcpi_cond_action(ctx, &s->model[l], st(l), B, Scond)))
         return rc;
     }
+    TwoLevelKnown known;
+    known.d_ScC = S_old(l + 1);
+    known.d_Scc = S_new(l + 1);
+    known.d_Sf_out = (l == 0) ? Sf : S_new(l);
+    known.update_scond = (l == 0);
     // acc is both the incoming cascade mask and the outgoing accept flag
     if ((rc = twolevel_step_impl(ctx, &s->model[l], &s->model[l + 1], st(l + 1), st(l), Sf, Scond, B, chain0,
-                                 level_draw(s->draw, l, 0), acc, acc, nullptr)))
+                                 level_draw(s->draw, l, 0), acc, acc, nullptr, known)))
       return rc;
     count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, acc, s->counters + l);
     MLMCPI_LAUNCHED("count_accept");
@@ -1028,6 +1080,8 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
     s->state.push_back(d);
   }
   ok = ok && mlmcpi_alloc(ctx, B, &s->Sf0) == 0 && mlmcpi_alloc(ctx, B, &s->Scond0) == 0;
+  ok = ok && mlmcpi_alloc(ctx, (size_t)s->L * B, &s->S_old) == 0 &&
+       mlmcpi_alloc(ctx, (size_t)s->L * B, &s->S_new) == 0;
   ok = ok && mlmcpi_alloc(ctx, B, &s->Sf) == 0 && mlmcpi_alloc(ctx, B, &s->Scond) == 0 &&
        mlmcpi_alloc(ctx, B, &s->q) == 0;
   ok = ok && cudaMalloc((void **)&s->acc, sizeof(int32_t) * B) == cudaSuccess &&
@@ -1120,6 +1174,10 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
   for (double *d : s->state)
     if (d)
       cudaFree(d);
+  if (s->S_old)
+    cudaFree(s->S_old);
+  if (s->S_new)
+    cudaFree(s->S_new);
   if (s->Sf0)
     cudaFree(s->Sf0);
   if (s->Scond0)

@@ -24,7 +24,7 @@ struct mlmcpi_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   uint64_t seed = 0;
-  int expcos_envelope = 1; // MLMCPI_OPT_EXPCOS_ENVELOPE: 0 reference, 1 tight (default)
+  int expcos_envelope = 2; // MLMCPI_OPT_EXPCOS_ENVELOPE: 0 reference, 1 chord, 2 chord + Taylor (default)
   int leapfrog_variant = 0; // MLMCPI_OPT_LEAPFROG_VARIANT: 0 TMA row pipeline, 1 register row march, 2 generic
   int leapfrog_rows = 0;    // MLMCPI_OPT_LEAPFROG_ROWS: rows per block (0 = default)
   int leapfrog_fuse = 1;    // MLMCPI_OPT_LEAPFROG_FUSE: two leapfrog steps per HBM pass
@@ -241,13 +241,20 @@ __device__ __forceinline__ double expsin2_pdf(const double x, const double sigma
 //                  for large tau); for tau < 1/2 a uniform proposal with acceptance
 //                  exp(tau (cos x - 1)).  Same target, fewer rejected attempts (SURVEY 8a-a11
 //                  allows a tighter envelope as long as the target pdf is unchanged).
-__device__ __forceinline__ double expcos_draw(Rng &r, const double beta, const double x_p,
-                                              const double x_m, const int envelope) {
-  const double dx = x_m - x_p;
-  const double tau = 2. * beta * fabs(cos(0.5 * dx));
+//   envelope == 2: (default) as 1, and for tau >= 64 the Taylor bound
+//                  1 - cos x >= (x^2 / 2) (1 - x^2 / 12), which on x^2 <= x1^2 = 160 / tau gives the
+//                  Gaussian envelope exp(-a x^2 / 2), a = tau (1 - x1^2 / 12) = tau - 40/3:
+//                  acceptance sqrt(1 - 40 / (3 tau)) (97 % at tau = 256, 99.7 % at tau = 2048).
+//                  Proposals with x^2 > x1^2 are rejected, i.e. the target is truncated to
+//                  |x| <= x1, which removes a probability mass < exp(-76) = 1e-33 -- thirty orders
+//                  of magnitude below the 2^-53 resolution of the uniform variates.  The squeeze
+//                  u <= 1 - tau delta x^2 / 2 <= exp(log acceptance) accepts most proposals
+//                  without evaluating cos or exp.
+#define EXPCOS_TIGHT_TAU 64.0
+__device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, const int envelope) {
   double x = 0.0;
   bool accepted = false;
-  if (envelope == 1 && tau < 0.5) {
+  if (envelope >= 1 && tau < 0.5) {
     while (!accepted) {
       double a0, a1, u0, u1;
       rng_uniform2(r, a0, a1);
@@ -259,23 +266,60 @@ __device__ __forceinline__ double expcos_draw(Rng &r, const double beta, const d
         accepted = (u1 <= exp(tau * (cos(x) - 1.)));
       }
     }
+    return x;
+  }
+  // Gaussian proposals N(0, sigma^2) restricted to an interval, log acceptance ratio
+  // tau (cos x - 1) + q x^2; one loop for the three envelopes (one copy of the code: the
+  // fill-in kernels are instruction-cache bound)
+  const bool tight = (envelope == 2 && tau >= EXPCOS_TIGHT_TAU);
+  double sigma, q, x1sq, sq;
+  if (tight) {
+    const double a = tau - 40. / 3.;
+    sigma = rsqrt(a);
+    q = 0.5 * a;
+    x1sq = 160. / tau;
+    sq = 20. / 3.; // squeeze: log acceptance >= -(20/3) x^2
   } else {
-    // sigma and the quadratic coefficient of the log acceptance ratio
-    const double sigma = envelope == 1 ? 0.5 * M_PI / sqrt(tau) : M_PI * sqrt(2. / tau);
-    const double quad = envelope == 1 ? 2. / (M_PI * M_PI) : 1. / (4. * M_PI * M_PI);
-    while (!accepted) {
-      double z0, z1, u0, u1;
-      rng_normal2(r, z0, z1);
-      rng_uniform2(r, u0, u1);
-      x = sigma * z0;
-      if ((-M_PI <= x) && (x < M_PI))
-        accepted = (u0 <= exp(tau * (cos(x) - 1. + quad * x * x)));
-      if (!accepted) {
-        x = sigma * z1;
-        if ((-M_PI <= x) && (x < M_PI))
-          accepted = (u1 <= exp(tau * (cos(x) - 1. + quad * x * x)));
+    sigma = envelope >= 1 ? 0.5 * M_PI / sqrt(tau) : M_PI * sqrt(2. / tau);
+    q = tau * (envelope >= 1 ? 2. / (M_PI * M_PI) : 1. / (4. * M_PI * M_PI));
+    x1sq = 0.0;
+    sq = 0.0;
+  }
+  while (!accepted) {
+    double z0, z1, u0, u1;
+    rng_normal2(r, z0, z1);
+    rng_uniform2(r, u0, u1);
+#pragma unroll 1
+    for (int t = 0; t < 2 && !accepted; ++t) {
+      x = sigma * (t == 0 ? z0 : z1);
+      const double u = (t == 0 ? u0 : u1);
+      const double x2 = x * x;
+      const bool inside = tight ? (x2 <= x1sq) : ((-M_PI <= x) && (x < M_PI));
+      if (inside) {
+        accepted = tight && (u <= 1. - sq * x2);
+        if (!accepted)
+          accepted = (u <= exp(tau * (cos(x) - 1.) + q * x2));
       }
     }
+  }
+  return x;
+}
+
+// by-products of a draw, from which the fused fill-in kernel evaluates -log pdf of the drawn
+// value without re-deriving the angles from the stored state: x is the accepted proposal
+// (the drawn link is mod_2pi(x + mean)), tau the concentration
+struct ExpCosDrawn {
+  double x, tau;
+};
+__device__ __forceinline__ double expcos_draw(Rng &r, const double beta, const double x_p,
+                                              const double x_m, const int envelope,
+                                              ExpCosDrawn *info = nullptr) {
+  const double dx = x_m - x_p;
+  const double tau = 2. * beta * fabs(cos(0.5 * dx));
+  const double x = expcos_draw_core(r, tau, envelope);
+  if (info) {
+    info->x = x;
+    info->tau = tau;
   }
   return mod_2pi_fast(x + 0.5 * (x_p + x_m) + (fabs(dx) > M_PI) * M_PI);
 }
@@ -358,13 +402,21 @@ __device__ __forceinline__ double besselproduct_draw(Rng &r, const BesselProduct
   return mod_2pi(sign_flip * x + x_p);
 }
 
-// distribution/besselproductdistribution.cc:15-25 (rescaled = true)
+// distribution/besselproductdistribution.cc:15-25 (rescaled = true).  cos(k phi) by the
+// Chebyshev recurrence c_k = 2 c_1 c_{k-1} - c_{k-2} (one cosine instead of sixteen; the
+// rounding error grows like k^2 eps <= 3e-14 and is weighted by the rapidly decaying alphaZ[k])
 __device__ __forceinline__ double besselproduct_Znorm_inv_rescaled(const BesselProductConst &bp,
                                                                    const double phi) {
-  double s = 1.0;
+  const double c1 = cos(phi), two_c1 = 2. * c1;
+  double ckm = 1.0, ck = c1;
+  double s = 1.0 + bp.alphaZ[1] * c1;
 #pragma unroll
-  for (int k = 1; k <= 16; ++k)
-    s += bp.alphaZ[k] * cos(k * phi);
+  for (int k = 2; k <= 16; ++k) {
+    const double cn = two_c1 * ck - ckm;
+    ckm = ck;
+    ck = cn;
+    s += bp.alphaZ[k] * cn;
+  }
   return 1.0 / s;
 }
 
@@ -386,11 +438,18 @@ __device__ __forceinline__ void approx_N_p_sigma2inv(const double beta, const do
   }
 }
 
+// by-products of an approximate-Bessel-product draw: w = x - x0/2 (the drawn value relative to
+// the main peak, before wrapping), and the mixture parameters
+struct ApproxDrawn {
+  double w, N_p, s_p, s_m;
+};
+
 // distribution/approximatebesselproductdistribution.hh:81-106; xi: the uniform variate that
 // selects the mode (supplied by the caller, which gets it for free from the Philox call
 // that also yields the step-2 split angle), the normal comes from one rng_normal2
 __device__ __forceinline__ double approxbessel_draw(Rng &r, const double beta, const double x_p,
-                                                    const double x_m, const double xi) {
+                                                    const double x_m, const double xi,
+                                                    ApproxDrawn *info = nullptr) {
   double x0 = x_p - x_m;
   double sign_flip = (x0 < 0) ? -1 : +1;
   x0 *= sign_flip;
@@ -410,8 +469,37 @@ __device__ __forceinline__ double approxbessel_draw(Rng &r, const double beta, c
     sigma = 1. / sqrt(sigma2_m_inv);
     xshift = M_PI;
   }
+  if (info) {
+    info->w = sigma * z0 - xshift;
+    info->N_p = N_p;
+    info->s_p = sigma2_p_inv;
+    info->s_m = sigma2_m_inv;
+  }
   const double x = sigma * z0 + 0.5 * x0 - xshift;
   return mod_2pi_fast(sign_flip * x + x_m);
+}
+
+// the mixture pdf of distribution/approximatebesselproductdistribution.cc:17-35 as a function of
+// w = z - x0/2 (distance from the main peak)
+__device__ __forceinline__ double approxbessel_pdf_w(const double N_p, const double sigma2_p_inv,
+                                                     const double sigma2_m_inv, const double w) {
+  const double N_m = 1. - N_p;
+  const double sq_p = sqrt(sigma2_p_inv), sq_m = sqrt(sigma2_m_inv);
+  double s_p = 0.0, s_m = 0.0;
+#pragma unroll 1
+  for (int k = -4; k <= 4; ++k) {
+    // exp(-a) == +0.0 exactly for a > 746 in IEEE double, and the second mode has weight
+    // sq_m == 0 when x0 < pi/8: skipping those terms leaves the sums bit-identical
+    double z_shifted = w + 2 * k * M_PI;
+    double a = 0.5 * sigma2_p_inv * z_shifted * z_shifted;
+    if (a < 746.0)
+      s_p += sq_p * exp(-a);
+    z_shifted += M_PI;
+    a = 0.5 * sigma2_m_inv * z_shifted * z_shifted;
+    if (a < 746.0 && sq_m != 0.0)
+      s_m += sq_m * exp(-a);
+  }
+  return sqrt(0.5 / M_PI) * (N_p * s_p + N_m * s_m);
 }
 
 // distribution/approximatebesselproductdistribution.cc:7-35
@@ -428,23 +516,7 @@ __device__ __forceinline__ double approxbessel_pdf(const double beta, const doub
   z *= sign_flip;
   double N_p, sigma2_p_inv, sigma2_m_inv;
   approx_N_p_sigma2inv(beta, x0, N_p, sigma2_p_inv, sigma2_m_inv);
-  const double N_m = 1. - N_p;
-  const double sq_p = sqrt(sigma2_p_inv), sq_m = sqrt(sigma2_m_inv);
-  double s_p = 0.0, s_m = 0.0;
-#pragma unroll
-  for (int k = -4; k <= 4; ++k) {
-    // exp(-a) == +0.0 exactly for a > 746 in IEEE double: skipping those periodic
-    // images leaves the sum bit-identical
-    double z_shifted = z - 0.5 * x0 + 2 * k * M_PI;
-    double a = 0.5 * sigma2_p_inv * z_shifted * z_shifted;
-    if (a < 746.0)
-      s_p += sq_p * exp(-a);
-    z_shifted += M_PI;
-    a = 0.5 * sigma2_m_inv * z_shifted * z_shifted;
-    if (a < 746.0)
-      s_m += sq_m * exp(-a);
-  }
-  return sqrt(0.5 / M_PI) * (N_p * s_p + N_m * s_m);
+  return approxbessel_pdf_w(N_p, sigma2_p_inv, sigma2_m_inv, z - 0.5 * x0);
 }
 
 // ------------------------------------------------------------------ reductions
@@ -493,6 +565,8 @@ struct FillConst {
   int fill(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);                  \
   int prolong_fill(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t,    \
                    uint64_t);                                                                      \
+  int prolong_fill_eval(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int,         \
+                        uint32_t, uint64_t, double *);                                             \
   int cond_action(mlmcpi_ctx *, const mlmcpi_model *, const double *, int, double *);              \
   int qoi(mlmcpi_ctx *, const mlmcpi_model *, int, const double *, int, double *, int64_t *);      \
   }

@@ -632,6 +632,17 @@ int cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, 
   return 0;
 }
 
+// prolongation + fill-in followed by S(theta') and S_cond(theta') into S_out[2][B]
+int prolong_fill_eval(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
+                      uint32_t chain0, uint64_t draw, double *S_out) {
+  int rc = prolong_fill(ctx, m, xc, x, B, chain0, draw);
+  if (rc)
+    return rc;
+  if ((rc = action(ctx, m, x, B, S_out)))
+    return rc;
+  return cond_action(ctx, m, x, B, S_out + B);
+}
+
 int cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,
                    uint64_t update0, int n_updates) {
   if (m->model != MLMCPI_ROTOR)

@@ -541,6 +541,7 @@ __global__ void sweep_colour_kernel(SW sw, int colour, double *x, int B, uint32_
   const int Mt = sw.Mt, Mx = sw.Mx;
   const long long nhalf = (long long)Mt * Mx / 2;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned wmask = __ballot_sync(0xffffffffu, t < nhalf * B);
   if (t >= nhalf * B)
     return;
   const long long chain = t / nhalf;
@@ -563,7 +564,9 @@ __global__ void sweep_colour_kernel(SW sw, int colour, double *x, int B, uint32_
   const size_t ell = 2 * ((size_t)Mt * j + i) + mu;
   if (HEATBATH) { // qft/quenchedschwingeraction.cc:46-54
     Rng rg = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, (uint32_t)ell);
-    xc[ell] = expcos_draw(rg, sw.beta, theta_p, theta_m, sw.envelope);
+    const double v = expcos_draw(rg, sw.beta, theta_p, theta_m, sw.envelope);
+    __syncwarp(wmask); // reconverge after the rejection loop: one coalesced store
+    xc[ell] = v;
   } else { // qft/quenchedschwingeraction.cc:57-65
     xc[ell] = mod_2pi((theta_p + theta_m) - xc[ell]);
   }
@@ -659,12 +662,50 @@ struct CellLinks {
   double V0, V1, H0, H1; // interior: (2i+1,2j,1) (2i+1,2j+1,1) (2i,2j+1,0) (2i+1,2j+1,0)
 };
 
-template <bool APPROX>
+// CoarsenBoth, beta <= 8: one cell of qft/quenchedschwingerconditionedfineaction.cc:219-250
+__device__ __forceinline__ double cond_both_bessel_cell(const CellLinks &c, const double beta,
+                                                        const BesselProductConst &bp) {
+  const double phi_12 = +c.B1 + c.T0;
+  const double phi_23 = +c.T1 - c.R1;
+  const double phi_34 = -c.A1 - c.R0;
+  const double phi_41 = -c.A0 + c.B0;
+  const double theta_1 = +c.H0;
+  const double theta_2 = -c.V1;
+  const double theta_3 = -c.H1;
+  const double theta_4 = +c.V0;
+  const double Phi = phi_12 + phi_23 + phi_34 + phi_41;
+  double S = -beta * (cos(theta_1 - theta_2 - phi_12) + cos(theta_2 - theta_3 - phi_23) +
+                      cos(theta_3 - theta_4 - phi_34) + cos(theta_4 - theta_1 - phi_41));
+  S -= log(besselproduct_Znorm_inv_rescaled(bp, Phi));
+  return S;
+}
+
+// sum over the four plaquettes of a cell of 1 - cos P (qft/quenchedschwingeraction.cc:14-17,
+// same summation order inside a plaquette as plaq())
+__device__ __forceinline__ double cell_plaquette_sum(const CellLinks &c) {
+  return (1. - cos(c.A0 + c.V0 - c.H0 - c.B0)) + (1. - cos(c.A1 + c.R0 - c.H1 - c.V0)) +
+         (1. - cos(c.H0 + c.V1 - c.T0 - c.B1)) + (1. - cos(c.H1 + c.R1 - c.T1 - c.V1));
+}
+
+// EVAL: also return sf = sum over the cell's plaquettes of (1 - cos P) and sc = the cell's
+// term of ConditionedFineAction::evaluate for the values just drawn.  For beta > 8 both come
+// from the by-products of the draws instead of from the stored angles: with x the accepted
+// ExpCos proposal of a horizontal interior link and tau its concentration,
+//   -log ExpCos.pdf = log(2 pi I0s(tau)) - tau (cos x - 1)      (expcosdistribution.cc:7-21)
+//   (1 - cos P) + (1 - cos P') of the two plaquettes it separates = 2 - (tau / beta) cos x
+// and the mixture pdf of the vertical pair is evaluated at w (approxbessel_pdf_w); these are the
+// reference's formulas with the angle differences taken before the final mod_2pi rounding.
+template <bool APPROX, bool EVAL>
 __device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double beta,
                                                    const int envelope,
                                                    const BesselProductConst &bp, uint64_t seed,
                                                    uint64_t draw, uint32_t gchain, int Mt, int i,
-                                                   int j, int cell) {
+                                                   int j, int cell, double &sf, double &sc,
+                                                   const unsigned wmask) {
+  // wmask: the lanes of this warp that fill a cell.  The rejection loops leave the warp
+  // diverged; without an explicit __syncwarp the code after a loop (the next draw, the
+  // evaluation, the stores) would run once per group of lanes that left the loop together.
+  ApproxDrawn ad;
   {
     const double theta_p = mod_2pi_fast(c.A1 + c.R0 + c.R1 - c.T1);
     const double theta_m = mod_2pi_fast(c.B0 + c.B1 + c.T0 - c.A0);
@@ -673,22 +714,41 @@ __device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double be
     double u0, u1;
     rng_uniform2(r, u0, u1);
     const double dtheta = -M_PI + 2. * M_PI * u0;
-    const double theta_tilde = APPROX ? approxbessel_draw(r, beta, theta_p, theta_m, u1)
+    const double theta_tilde = APPROX ? approxbessel_draw(r, beta, theta_p, theta_m, u1, EVAL ? &ad : nullptr)
                                       : besselproduct_draw(r, bp, theta_p, theta_m);
+    __syncwarp(wmask);
     c.V0 = mod_2pi_fast(0.5 * theta_tilde + dtheta);
     c.V1 = mod_2pi_fast(0.5 * theta_tilde - dtheta);
   }
-  {
-    const double theta_p = mod_2pi_fast(c.A0 + c.V0 - c.B0);
-    const double theta_m = mod_2pi_fast(c.B1 + c.T0 - c.V1);
-    Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i);
-    c.H0 = expcos_draw(r, beta, theta_p, theta_m, envelope);
+  // STEP 3 for the two horizontal interior links (2i, 2j+1, 0) and (2i+1, 2j+1, 0); a rolled
+  // loop, so that the rejection sampler exists once in the instruction stream
+  double Zprod = 1.0, tsum = 0.0, tcos = 0.0;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const double theta_p = mod_2pi_fast(h == 0 ? c.A0 + c.V0 - c.B0 : c.A1 + c.R0 - c.V0);
+    const double theta_m = mod_2pi_fast(h == 0 ? c.B1 + c.T0 - c.V1 : c.V1 + c.T1 - c.R1);
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i + h);
+    ExpCosDrawn e;
+    const double H = expcos_draw(r, beta, theta_p, theta_m, envelope, &e);
+    __syncwarp(wmask);
+    if (h == 0)
+      c.H0 = H;
+    else
+      c.H1 = H;
+    if (EVAL && APPROX) {
+      Zprod *= 2. * M_PI * fast_bessel_I0_scaled(e.tau);
+      tsum += e.tau;
+      tcos += e.tau * cos(e.x);
+    }
   }
-  {
-    const double theta_p = mod_2pi_fast(c.A1 + c.R0 - c.V0);
-    const double theta_m = mod_2pi_fast(c.V1 + c.T1 - c.R1);
-    Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i + 1);
-    c.H1 = expcos_draw(r, beta, theta_p, theta_m, envelope);
+  if (EVAL) {
+    if (APPROX) {
+      sc = (log(Zprod) - log(approxbessel_pdf_w(ad.N_p, ad.s_p, ad.s_m, ad.w))) + (tsum - tcos);
+      sf = 4. - tcos / beta;
+    } else {
+      sc = cond_both_bessel_cell(c, beta, bp);
+      sf = cell_plaquette_sum(c);
+    }
   }
 }
 
@@ -699,6 +759,7 @@ __global__ void fill_both_step23_kernel(SW sw, BesselProductConst bp, double *x_
   const int Mt = sw.Mt, Mx = sw.Mx, Mtc = Mt / 2, Mxc = Mx / 2;
   const long long nc = (long long)Mtc * Mxc;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned wmask = __ballot_sync(0xffffffffu, t < nc * B);
   if (t >= nc * B)
     return;
   const long long chain = t / nc;
@@ -715,7 +776,9 @@ __global__ void fill_both_step23_kernel(SW sw, BesselProductConst bp, double *x_
   c.R1 = TH(x, i2, 2 * j + 1, 1);
   c.T0 = TH(x, 2 * i, j2, 0);
   c.T1 = TH(x, 2 * i + 1, j2, 0);
-  fill_cell_interior<APPROX>(c, sw.beta, sw.envelope, bp, seed, draw, chain0 + (uint32_t)chain, Mt, i, j, cell);
+  double sf_unused, sc_unused;
+  fill_cell_interior<APPROX, false>(c, sw.beta, sw.envelope, bp, seed, draw, chain0 + (uint32_t)chain, Mt, i, j, cell,
+                                    sf_unused, sc_unused, wmask);
   TH(x, 2 * i + 1, 2 * j, 1) = c.V0;
   TH(x, 2 * i + 1, 2 * j + 1, 1) = c.V1;
   TH(x, 2 * i, 2 * j + 1, 0) = c.H0;
@@ -726,56 +789,71 @@ __global__ void fill_both_step23_kernel(SW sw, BesselProductConst bp, double *x_
 // cell (i,j) regenerates the step-1 variates of cells (i+1,j), (i,j+1) from their
 // Philox counters instead of waiting for them (counter-based RNG makes the three
 // phases of the reference embarrassingly parallel).  80 B of HBM traffic per cell.
-template <bool APPROX>
-__global__ void __launch_bounds__(128, 8) prolong_fill_both_kernel(SW sw, BesselProductConst bp, const double *xc_all,
+// EVAL: the block additionally reduces S_f(theta') / beta and S_cond(theta') of its cells into
+// partial[{0,1}][chain][block] (TwoLevelMetropolisStep::draw lines 48 and 65-66 without a second
+// and third pass over theta').  Grid: nblk blocks of 128 cells per chain.
+template <bool APPROX, bool EVAL>
+#ifndef FILL_MINBLK
+#define FILL_MINBLK 8
+#endif
+__global__ void __launch_bounds__(128, FILL_MINBLK) prolong_fill_both_kernel(SW sw, BesselProductConst bp, const double *xc_all,
                                          double *x_all, int B, uint32_t chain0, uint64_t seed,
-                                         uint64_t draw) {
+                                         uint64_t draw, int nblk, double *partial) {
   const int Mt = sw.Mt, Mx = sw.Mx, Mtc = Mt / 2, Mxc = Mx / 2;
-  const long long nc = (long long)Mtc * Mxc;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nc * B)
-    return;
-  const long long chain = t / nc;
-  const int cell = (int)(t - chain * nc);
-  const int j = cell / Mtc, i = cell - j * Mtc;
-  const uint32_t gchain = chain0 + (uint32_t)chain;
-  const double2 *xc = reinterpret_cast<const double2 *>(xc_all) + chain * nc;
-  double *x = x_all + chain * 2 * (long long)Mt * Mx;
-  const int ipc = wrap_inc(i, Mtc), jpc = wrap_inc(j, Mxc);
-  const int cell_r = j * Mtc + ipc, cell_t = jpc * Mtc + i;
-  const double2 own = xc[cell];
-  const double cr = xc[cell_r].y, ct = xc[cell_t].x;
-  CellLinks c;
-  {
-    Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell);
-    double dth_s;
-    const double dth_t = rng_angle2(r, dth_s);
-    c.A0 = mod_2pi_fast(0.5 * own.x + dth_t);
-    c.A1 = mod_2pi_fast(0.5 * own.x - dth_t);
-    c.B0 = mod_2pi_fast(0.5 * own.y + dth_s);
-    c.B1 = mod_2pi_fast(0.5 * own.y - dth_s);
+  const int nc = Mtc * Mxc;
+  const int chain = blockIdx.x / nblk, blk = blockIdx.x - chain * nblk;
+  const int cell = blk * blockDim.x + threadIdx.x;
+  double sf = 0.0, sc = 0.0;
+  const unsigned wmask = __ballot_sync(0xffffffffu, cell < nc);
+  if (cell < nc) {
+    const int j = cell / Mtc, i = cell - j * Mtc;
+    const uint32_t gchain = chain0 + (uint32_t)chain;
+    const double2 *xc = reinterpret_cast<const double2 *>(xc_all) + (size_t)chain * nc;
+    double *x = x_all + (size_t)chain * 2 * Mt * Mx;
+    const int ipc = wrap_inc(i, Mtc), jpc = wrap_inc(j, Mxc);
+    const int cell_r = j * Mtc + ipc, cell_t = jpc * Mtc + i;
+    const double2 own = xc[cell];
+    const double cr = xc[cell_r].y, ct = xc[cell_t].x;
+    CellLinks c;
+    {
+      Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell);
+      double dth_s;
+      const double dth_t = rng_angle2(r, dth_s);
+      c.A0 = mod_2pi_fast(0.5 * own.x + dth_t);
+      c.A1 = mod_2pi_fast(0.5 * own.x - dth_t);
+      c.B0 = mod_2pi_fast(0.5 * own.y + dth_s);
+      c.B1 = mod_2pi_fast(0.5 * own.y - dth_s);
+    }
+    {
+      Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell_r);
+      double dth_s;
+      (void)rng_angle2(r, dth_s);
+      c.R0 = mod_2pi_fast(0.5 * cr + dth_s);
+      c.R1 = mod_2pi_fast(0.5 * cr - dth_s);
+    }
+    {
+      Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell_t);
+      double dth_s;
+      const double dth_t = rng_angle2(r, dth_s);
+      c.T0 = mod_2pi_fast(0.5 * ct + dth_t);
+      c.T1 = mod_2pi_fast(0.5 * ct - dth_t);
+    }
+    fill_cell_interior<APPROX, EVAL>(c, sw.beta, sw.envelope, bp, seed, draw, gchain, Mt, i, j, cell, sf, sc, wmask);
+    // rows 2j and 2j+1, sites 2i and 2i+1: four aligned double2 stores
+    double2 *xs = reinterpret_cast<double2 *>(x);
+    xs[(size_t)Mt * (2 * j) + 2 * i] = make_double2(c.A0, c.B0);
+    xs[(size_t)Mt * (2 * j) + 2 * i + 1] = make_double2(c.A1, c.V0);
+    xs[(size_t)Mt * (2 * j + 1) + 2 * i] = make_double2(c.H0, c.B1);
+    xs[(size_t)Mt * (2 * j + 1) + 2 * i + 1] = make_double2(c.H1, c.V1);
   }
-  {
-    Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell_r);
-    double dth_s;
-    (void)rng_angle2(r, dth_s);
-    c.R0 = mod_2pi_fast(0.5 * cr + dth_s);
-    c.R1 = mod_2pi_fast(0.5 * cr - dth_s);
+  if (EVAL) {
+    const double v0 = block_sum(sf);
+    if (threadIdx.x == 0)
+      partial[(size_t)chain * nblk + blk] = v0;
+    const double v1 = block_sum(sc);
+    if (threadIdx.x == 0)
+      partial[((size_t)B + chain) * nblk + blk] = v1;
   }
-  {
-    Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell_t);
-    double dth_s;
-    const double dth_t = rng_angle2(r, dth_s);
-    c.T0 = mod_2pi_fast(0.5 * ct + dth_t);
-    c.T1 = mod_2pi_fast(0.5 * ct - dth_t);
-  }
-  fill_cell_interior<APPROX>(c, sw.beta, sw.envelope, bp, seed, draw, gchain, Mt, i, j, cell);
-  // rows 2j and 2j+1, sites 2i and 2i+1: four aligned double2 stores
-  double2 *xs = reinterpret_cast<double2 *>(x);
-  xs[(size_t)Mt * (2 * j) + 2 * i] = make_double2(c.A0, c.B0);
-  xs[(size_t)Mt * (2 * j) + 2 * i + 1] = make_double2(c.A1, c.V0);
-  xs[(size_t)Mt * (2 * j + 1) + 2 * i] = make_double2(c.H0, c.B1);
-  xs[(size_t)Mt * (2 * j + 1) + 2 * i + 1] = make_double2(c.H1, c.V1);
 }
 
 // semi-coarsening, qft/quenchedschwingerconditionedfineaction.cc:136-209.
@@ -835,19 +913,20 @@ struct CondBothBesselF {
     const int j = (int)(cell / Mtc), i = (int)(cell - (long long)j * Mtc);
     const double *x = x_all + (size_t)chain * 2 * Mt * Mx;
     const int i2 = wrap_inc(2 * i + 1, Mt), j2 = wrap_inc(2 * j + 1, Mx);
-    const double phi_12 = +TH(x, 2 * i, 2 * j + 1, 1) + TH(x, 2 * i, j2, 0);
-    const double phi_23 = +TH(x, 2 * i + 1, j2, 0) - TH(x, i2, 2 * j + 1, 1);
-    const double phi_34 = -TH(x, 2 * i + 1, 2 * j, 0) - TH(x, i2, 2 * j, 1);
-    const double phi_41 = -TH(x, 2 * i, 2 * j, 0) + TH(x, 2 * i, 2 * j, 1);
-    const double theta_1 = +TH(x, 2 * i, 2 * j + 1, 0);
-    const double theta_2 = -TH(x, 2 * i + 1, 2 * j + 1, 1);
-    const double theta_3 = -TH(x, 2 * i + 1, 2 * j + 1, 0);
-    const double theta_4 = +TH(x, 2 * i + 1, 2 * j, 1);
-    const double Phi = phi_12 + phi_23 + phi_34 + phi_41;
-    double S = -sw.beta * (cos(theta_1 - theta_2 - phi_12) + cos(theta_2 - theta_3 - phi_23) +
-                           cos(theta_3 - theta_4 - phi_34) + cos(theta_4 - theta_1 - phi_41));
-    S -= log(besselproduct_Znorm_inv_rescaled(bp, Phi));
-    acc[0] += S;
+    CellLinks c;
+    c.A0 = TH(x, 2 * i, 2 * j, 0);
+    c.A1 = TH(x, 2 * i + 1, 2 * j, 0);
+    c.B0 = TH(x, 2 * i, 2 * j, 1);
+    c.B1 = TH(x, 2 * i, 2 * j + 1, 1);
+    c.R0 = TH(x, i2, 2 * j, 1);
+    c.R1 = TH(x, i2, 2 * j + 1, 1);
+    c.T0 = TH(x, 2 * i, j2, 0);
+    c.T1 = TH(x, 2 * i + 1, j2, 0);
+    c.V0 = TH(x, 2 * i + 1, 2 * j, 1);
+    c.V1 = TH(x, 2 * i + 1, 2 * j + 1, 1);
+    c.H0 = TH(x, 2 * i, 2 * j + 1, 0);
+    c.H1 = TH(x, 2 * i + 1, 2 * j + 1, 0);
+    acc[0] += cond_both_bessel_cell(c, sw.beta, bp);
   }
 };
 
@@ -1268,30 +1347,62 @@ int fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chai
   return 0;
 }
 
-int prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
-                 uint32_t chain0, uint64_t draw) {
+// S_out: nullptr, or [2][B] receiving S_f(theta') and S_cond(theta') (fused evaluation)
+static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
+                             uint32_t chain0, uint64_t draw, double *S_out) {
   int rc = check_even(ctx, m);
   if (rc)
     return rc;
   if (m->coarsening != MLMCPI_COARSEN_BOTH) {
     if ((rc = prolong(ctx, m, xc, x, B)))
       return rc;
-    return fill(ctx, m, x, B, chain0, draw);
+    if ((rc = fill(ctx, m, x, B, chain0, draw)))
+      return rc;
+    if (S_out) {
+      if ((rc = action(ctx, m, x, B, S_out)))
+        return rc;
+      return cond_action(ctx, m, x, B, S_out + B);
+    }
+    return 0;
   }
   SW sw = make_sw(ctx, m);
-  const long long n = n_coarse_sites(m) * B;
+  const int nblk = cdiv(n_coarse_sites(m), 128);
+  const int grid = nblk * B;
+  double *partial = nullptr;
+  if (S_out && !(partial = ctx_scratch(ctx, (size_t)2 * B * nblk)))
+    return MLMCPI_ENOMEM;
   BesselProductConst bp;
   if (sw.beta > 8.0) {
     bp.beta = sw.beta;
-    prolong_fill_both_kernel<true><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0,
-                                                                         ctx->seed, draw);
+    if (S_out)
+      prolong_fill_both_kernel<true, true><<<grid, 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
+                                                                         draw, nblk, partial);
+    else
+      prolong_fill_both_kernel<true, false><<<grid, 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
+                                                                          draw, nblk, nullptr);
   } else {
     besselproduct_setup(sw.beta, &bp);
-    prolong_fill_both_kernel<false><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0,
-                                                                          ctx->seed, draw);
+    if (S_out)
+      prolong_fill_both_kernel<false, true><<<grid, 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
+                                                                          draw, nblk, partial);
+    else
+      prolong_fill_both_kernel<false, false><<<grid, 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
+                                                                           draw, nblk, nullptr);
   }
   MLMCPI_LAUNCHED("schwinger::prolong_fill");
+  if (S_out)
+    return launch_reduce_finish(ctx, partial, nblk, B, 2, EPI_SCALE, sw.beta, 1.0, S_out, nullptr);
   return 0;
+}
+
+int prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
+                 uint32_t chain0, uint64_t draw) {
+  return prolong_fill_impl(ctx, m, xc, x, B, chain0, draw, nullptr);
+}
+
+int prolong_fill_eval(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
+                      uint32_t chain0, uint64_t draw, double *S_out) {
+  return prolong_fill_impl(ctx, m, xc, x, B, chain0, draw, S_out);
 }
 
 int cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, double *S) {

@@ -912,10 +912,14 @@ double orc_expsin2_draw(orc_rng *r, double sigma) {
 /* Proposal of the ExpCos rejection sampler.
  *   0: the reference's own envelope (distribution/expcosdistribution.hh:50-65).
  *   1: NOT the reference's algorithm: the tighter chord-bound envelope
- *      1 - cos x >= 2 x^2 / pi^2 that the product uses by default
- *      (MLMCPI_OPT_EXPCOS_ENVELOPE = 1; uniform proposal for tau < 1/2).  The target
- *      pdf ~ exp(tau cos x) is the reference's; tests/test_oracle_cpu.py checks both
- *      variants against the reference's own draw() by a two-sample KS test. */
+ *      1 - cos x >= 2 x^2 / pi^2 (uniform proposal for tau < 1/2).
+ *   2: NOT the reference's algorithm: as 1 for tau < 64; for tau >= 64 the Taylor bound
+ *      1 - cos x >= x^2/2 (1 - x^2/12) on x^2 <= 160/tau, i.e. the Gaussian envelope
+ *      exp(-(tau - 40/3) x^2 / 2), with the squeeze u <= 1 - (20/3) x^2; the target is
+ *      truncated to x^2 <= 160/tau (tail mass < 1e-33).  The product's default
+ *      (MLMCPI_OPT_EXPCOS_ENVELOPE = 2).
+ *   The target pdf ~ exp(tau cos x) is the reference's; tests/test_oracle_cpu.py checks all
+ *   variants against the reference's own draw() by a two-sample KS test. */
 static int g_expcos_envelope = 0;
 void orc_set_expcos_envelope(int envelope) { g_expcos_envelope = envelope; }
 
@@ -924,7 +928,23 @@ double orc_expcos_draw(orc_rng *r, double beta, double x_p, double x_m) {
   const double tau = 2. * beta * fabs(cos(0.5 * dx));
   double x = 0.0;
   int accepted = 0;
-  if (g_expcos_envelope == 1 && tau < 0.5) {
+  if (g_expcos_envelope == 2 && tau >= 64.0) {
+    const double x1sq = 160. / tau;
+    const double a = tau - 40. / 3.;
+    const double sigma = 1.0 / sqrt(a);
+    while (!accepted) {
+      double z[2], u[2];
+      orc_rng_normal2(r, &z[0], &z[1]);
+      orc_rng_uniform2(r, &u[0], &u[1]);
+      for (int t = 0; t < 2 && !accepted; ++t) {
+        x = sigma * z[t];
+        const double x2 = x * x;
+        if (x2 <= x1sq)
+          accepted = (u[t] <= 1. - (20. / 3.) * x2) ||
+                     (u[t] <= exp(tau * (cos(x) - 1.) + 0.5 * a * x2));
+      }
+    }
+  } else if (g_expcos_envelope >= 1 && tau < 0.5) {
     while (!accepted) {
       double a[2], u[2];
       orc_rng_uniform2(r, &a[0], &a[1]);
@@ -938,9 +958,9 @@ double orc_expcos_draw(orc_rng *r, double beta, double x_p, double x_m) {
     /* envelope 0: expcosdistribution.hh:53-61 (sigma = pi sqrt(2/tau),
      * fourpi2_inv = 1/(4 pi^2)) */
     const double sigma =
-        g_expcos_envelope == 1 ? 0.5 * M_PI / sqrt(tau) : M_PI * sqrt(2. / tau);
+        g_expcos_envelope >= 1 ? 0.5 * M_PI / sqrt(tau) : M_PI * sqrt(2. / tau);
     const double quad =
-        g_expcos_envelope == 1 ? 2. / (M_PI * M_PI) : 1. / (4. * M_PI * M_PI);
+        g_expcos_envelope >= 1 ? 2. / (M_PI * M_PI) : 1. / (4. * M_PI * M_PI);
     while (!accepted) {
       double z[2], u[2];
       orc_rng_normal2(r, &z[0], &z[1]);

@@ -187,6 +187,7 @@ MODELS = {
     "schw_both_b4_32": lambda: po.schwinger(32, 32, 4.0, po.BOTH),
     "schw_both_b16_32x16": lambda: po.schwinger(32, 16, 16.0, po.BOTH),
     "schw_both_12x20": lambda: po.schwinger(12, 20, 2.0, po.BOTH),
+    "schw_both_b512_16": lambda: po.schwinger(16, 16, 512.0, po.BOTH),
     "schw_temporal": lambda: po.schwinger(16, 12, 5.0, po.TEMPORAL),
     "schw_spatial": lambda: po.schwinger(12, 16, 5.0, po.SPATIAL),
     "gff_rot16": lambda: po.gff(16, 16, 10.0, po.ROTATE, 0),
@@ -245,7 +246,7 @@ def test_deterministic_kernels_against_oracle(mp, ctx, orc, name):
     y = xd.clone()
     ctx.prolong(m, dev(ctx, xcr), y)
     assert np.array_equal(host(y), np.array([orc.prolong(o, xcr[b], x[b]) for b in range(B)]))
-    xs = random_state(o, rng, B, smooth=0.3 if o.beta > 8 else 1.0)
+    xs = random_state(o, rng, B, smooth=min(1.2 / np.sqrt(o.beta), 0.3) if o.beta > 8 else 1.0)
     close(host(ctx.cond_action(m, dev(ctx, xs))), [orc.cond_action(o, xs[b]) for b in range(B)],
           tol=1e-11, what="cond_action")
     qois = {po.HO: [po.QOI_X2], po.QUARTIC: [po.QOI_X2], po.ROTOR: [po.QOI_X2, po.QOI_ROTOR_CHI],
@@ -259,16 +260,17 @@ def test_deterministic_kernels_against_oracle(mp, ctx, orc, name):
             assert list(host(Q)) == [w[1] for w in want]  # integer topological charge: exact
 
 
-STOCHASTIC_CASES = [(n, e) for n in MODELS for e in ((0, 1) if n.startswith("schw") else (1,))]
+STOCHASTIC_CASES = [(n, e) for n in MODELS for e in ((0, 1, 2) if n.startswith("schw") else (2,))]
 
 
 @pytest.fixture
 def envelope(request, ctx, orc):
-    """ExpCos proposal: 0 = the reference's envelope, 1 = the product's default (tighter)"""
-    ctx.set_expcos_envelope(bool(request.param))
+    """ExpCos proposal: 0 = the reference's envelope, 1 = chord bound, 2 = the product's default
+    (chord bound + Taylor bound for tau >= 64)"""
+    ctx.set_expcos_envelope(request.param)
     orc.lib.orc_set_expcos_envelope(request.param)
     yield request.param
-    ctx.set_expcos_envelope(True)
+    ctx.set_expcos_envelope(2)
     orc.lib.orc_set_expcos_envelope(0)
 
 
@@ -315,8 +317,15 @@ def test_stochastic_kernels_against_oracle(mp, ctx, orc, name, envelope):
     xd2 = dev(ctx, x0)
     ctx.prolong_fill(m, dev(ctx, xc), xd2, chain0, draw)
     cmp(host(xd2), want, tol=1e-9, what="prolong_fill")
+    # ... and fused with the two reductions of the trial state: same theta', and S_f / S_cond equal
+    # to the stand-alone evaluations of that state
+    xd3 = dev(ctx, x0)
+    Sf_f, Sc_f = ctx.prolong_fill_eval(m, dev(ctx, xc), xd3, chain0, draw)
+    assert np.array_equal(host(xd3), host(xd2))
+    close(host(Sf_f), host(ctx.action(m, xd3)), tol=1e-11, what="fused S_f")
+    close(host(Sc_f), host(ctx.cond_action(m, xd3)), tol=1e-10, what="fused S_cond")
     # two-level Metropolis-Hastings step
-    xf = random_state(o, rng, B, smooth=0.3 if o.beta > 8 else 1.0)
+    xf = random_state(o, rng, B, smooth=min(1.2 / np.sqrt(o.beta), 0.3) if o.beta > 8 else 1.0)
     xfd, xcd = dev(ctx, xf), dev(ctx, xc)
     Sf, Sc = ctx.action(m, xfd), ctx.cond_action(m, xfd)
     Sf0, Sc0 = host(Sf).copy(), host(Sc).copy()
@@ -328,6 +337,43 @@ def test_stochastic_kernels_against_oracle(mp, ctx, orc, name, envelope):
     assert list(host(acc)) == [r[0] for r in res]
     cmp(host(xfd), np.array([r[1] for r in res]), tol=1e-9, what="twolevel state")
     close(host(Sf), [r[2] for r in res], tol=1e-10, what="cached S_f")
+
+
+@pytest.mark.parametrize("beta", [6.0, 96.0])
+def test_hierarchical_draw_equals_explicit_cascade(mp, ctx, beta):
+    """HierarchicalSampler::draw (hierarchicalsampler.cc:55-81) inside the library -- fused
+    fill-in + reductions, per-level action caches -- against the same cascade composed from the
+    public single-purpose entry points (restrict, hmc_step, action, cond_action, twolevel_step)"""
+    import torch
+    L, B, chain0, nt, dt = 3, 6, 3, 5, 0.05
+    m = mp.schwinger(16, 16, beta)
+    smp = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=L, nt=nt, dt=dt,
+                     renorm=mp.RENORM_PERTURBATIVE, chain0=chain0)
+    models = [smp.level_model(l) for l in range(L)]
+    x0 = ctx.init_state(m, B, chain0, 5)
+    for k in range(3):
+        ctx.heatbath_sweep(m, x0, chain0, k)
+    smp.set_state(x0)
+    out = x0.clone()
+    x = [x0.clone()] + [ctx.state(models[l], B) for l in range(1, L)]
+    level_draw = lambda d, l: (d << 12) | (l << 8)
+    n_acc = 0
+    for d in range(4):
+        smp.draw(out)
+        for l in range(1, L):
+            ctx.restrict(models[l - 1], x[l - 1], x[l])
+        mask, _ = ctx.hmc_step(models[L - 1], nt, dt, x[L - 1], chain0, level_draw(d, L - 1))
+        mask = mask.bool()
+        for l in range(L - 2, -1, -1):
+            keep = x[l].clone()
+            Sf, Sc = ctx.action(models[l], x[l]), ctx.cond_action(models[l], x[l])
+            acc, _ = ctx.twolevel_step(models[l], models[l + 1], x[l + 1], x[l], Sf, Sc, chain0,
+                                       level_draw(d, l))
+            x[l][~mask] = keep[~mask]  # `if (not accept) break`, hierarchicalsampler.cc:73-74
+            mask = mask & acc.bool()
+        n_acc += int(mask.sum())
+        ang_close(host(out), host(x[0]), tol=1e-11, what=f"draw {d}")
+    assert 0 < n_acc < 4 * B  # both branches of the cascade were exercised
 
 
 # --------------------------------------------------- statistics accumulators

@@ -299,17 +299,22 @@ def test_draws_follow_reference_distributions(orc):
              (2, 1.5, -2.0, 2.5, lambda r: orc.lib.orc_besselproduct_draw(C.byref(r), 1.5, -2.0, 2.5)),
              (3, 16.0, 0.9, 0.2, lambda r: orc.lib.orc_approxbessel_draw(C.byref(r), 16.0, 0.9, 0.2)),
              (3, 16.0, -2.0, 2.5, lambda r: orc.lib.orc_approxbessel_draw(C.byref(r), 16.0, -2.0, 2.5))]
-    def tight(beta, xp, xm):
+    def tight(beta, xp, xm, variant=1):
         def f(r):
-            orc.lib.orc_set_expcos_envelope(1)
+            orc.lib.orc_set_expcos_envelope(variant)
             v = orc.lib.orc_expcos_draw(C.byref(r), beta, xp, xm)
             orc.lib.orc_set_expcos_envelope(0)
             return v
         return f
-    # the product's tighter ExpCos envelope (incl. the uniform-proposal branch tau < 1/2)
+    # the product's tighter ExpCos envelopes (incl. the uniform-proposal branch tau < 1/2)
     cases += [(1, b, xp, xm, tight(b, xp, xm))
               for (b, xp, xm) in [(4.0, 0.9, 0.2), (4.0, 2.9, -2.8), (0.1, 0.3, -0.4), (0.6, 1.0, 1.2),
                                   (300.0, -1.0, -0.9), (2.0, 3.0, -0.1)]]
+    # variant 2: Taylor-bound envelope for tau = 2 beta |cos(dx/2)| >= 64 (tau = 64.3, 599, 2047, 142
+    # with the pi shift), chord / uniform branches below
+    cases += [(1, b, xp, xm, tight(b, xp, xm, 2))
+              for (b, xp, xm) in [(33.0, 0.5, 0.05), (300.0, -1.0, -0.9), (1024.0, 0.31, 0.25),
+                                  (500.0, 3.0, -0.1), (4.0, 0.9, 0.2), (0.1, 0.3, -0.4)]]
     for dist, prm, xp, xm, draw in cases:
         want = np.zeros(n)
         R.lib.ref_dist_draw(dist, prm, xp, xm, 4711, n, want.ctypes.data_as(po.c_double_p))
