@@ -138,6 +138,26 @@ int mlmcpi_coarsening_lists(int Mt, int Mx, int ctype, int level, uint32_t *coar
 int mlmcpi_coarse_model(const mlmcpi_model *fine, int renorm, int level, int ctype,
                         double T_final, mlmcpi_model *coarse);
 
+/* ---- analytic results and coupling matching (host, setup time only) ------------------
+ * The reference evaluates these with GSL quadrature / root finding (common/auxilliary.cc:44-209,
+ * qft/quenchedschwingerrenormalisation.cc:7-64); here: composite Gauss-Legendre + bisection. */
+double mlmcpi_sigma_hat(double xi, unsigned int p);                               /* auxilliary.cc:7-29 */
+/* E[V chi_t] of the quenched Schwinger model (qoi/qft/qoi2dsusceptibility.cc:30-50); the exact
+ * expression is defined for beta <= 2000 (NaN beyond, where the drivers use the perturbative one) */
+double mlmcpi_schwinger_chit_analytical(double beta, unsigned int n_plaq);
+double mlmcpi_schwinger_chit_perturbative(double beta, unsigned int n_plaq);
+double mlmcpi_schwinger_var_chit_continuum(double beta, unsigned int n_plaq);
+/* RotorAction::chit_exact / chit_perturbative / chit_continuum (qm/rotoraction.cc:92-115):
+ * which = 0 / 1 / 2 */
+double mlmcpi_rotor_chit(double m0, double a_lat, double T_final, int which);
+double mlmcpi_gff_phi_squared_analytical(double mass, int Mt_lat, int Mx_lat);   /* auxilliary.cc:197-209 */
+/* HarmonicOscillatorAction::Xsquared_analytical(_continuum) (qm/harmonicoscillatoraction.cc:69-80) */
+double mlmcpi_ho_xsquared_analytical(double m0, double mu2, double a_lat, int M_lat, int continuum);
+/* RenormalisedQuenchedSchwingerParameters::betacoarse_nonperturbative: n_plaq plaquettes on the
+ * fine lattice, rho_refine = 4 (coarsening both) or 2; used by mlmcpi_coarse_model for
+ * MLMCPI_RENORM_NONPERTURBATIVE */
+double mlmcpi_schwinger_betacoarse_nonperturbative(double beta, unsigned int n_plaq, int rho_refine);
+
 /* ---- group 1: action, force, HMC ------------------------------------------ */
 /* Action::initialise_state (rotoraction.cc:82-85, quenchedschwingeraction.cc:198-204) */
 int mlmcpi_init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B,

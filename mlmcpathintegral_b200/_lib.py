@@ -87,6 +87,14 @@ SIGNATURES = {
     "mlmcpi_prolong": (_i, [_vp, _MP, _vp, _vp, _i]),
     "mlmcpi_restrict": (_i, [_vp, _MP, _vp, _vp, _i]),
     "mlmcpi_fill": (_i, [_vp, _MP, _vp, _i, _u32, _u64]),
+    "mlmcpi_sigma_hat": (C.c_double, [C.c_double, C.c_uint]),
+    "mlmcpi_schwinger_chit_analytical": (C.c_double, [C.c_double, C.c_uint]),
+    "mlmcpi_schwinger_chit_perturbative": (C.c_double, [C.c_double, C.c_uint]),
+    "mlmcpi_schwinger_var_chit_continuum": (C.c_double, [C.c_double, C.c_uint]),
+    "mlmcpi_rotor_chit": (C.c_double, [C.c_double, C.c_double, C.c_double, _i]),
+    "mlmcpi_gff_phi_squared_analytical": (C.c_double, [C.c_double, _i, _i]),
+    "mlmcpi_ho_xsquared_analytical": (C.c_double, [C.c_double, C.c_double, C.c_double, _i, _i]),
+    "mlmcpi_schwinger_betacoarse_nonperturbative": (C.c_double, [C.c_double, C.c_uint, _i]),
     "mlmcpi_prolong_fill": (_i, [_vp, _MP, _vp, _vp, _i, _u32, _u64]),
     "mlmcpi_prolong_fill_eval": (_i, [_vp, _MP, _vp, _vp, _i, _u32, _u64, _vp]),
     "mlmcpi_cluster_update": (_i, [_vp, _MP, _vp, _i, _u32, _u64, _i]),

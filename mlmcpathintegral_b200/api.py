@@ -14,7 +14,8 @@ import torch
 from . import _lib
 from ._lib import (COARSEN_ALTERNATE, COARSEN_BOTH, COARSEN_ROTATE, COARSEN_SPATIAL,  # noqa: F401
                    COARSEN_TEMPORAL, GFF, HO, QOI_AVG_PLAQUETTE, QOI_PHI2, QOI_ROTOR_CHI,
-                   QOI_SCHWINGER_CHI, QOI_X2, QUARTIC, RENORM_NONE, RENORM_PERTURBATIVE, ROTOR,
+                   QOI_SCHWINGER_CHI, QOI_X2, QUARTIC, RENORM_NONE, RENORM_NONPERTURBATIVE,
+                   RENORM_PERTURBATIVE, ROTOR,
                    SAMPLER_CLUSTER, SAMPLER_HEATBATH, SAMPLER_HMC, SCHWINGER, MlmcParams, Model,
                    SamplerParams)
 

@@ -394,8 +394,13 @@ int mlmcpi_coarse_model(const mlmcpi_model *fine, int renorm, int level, int cty
     coarse->beta = (both ? 0.25 : 0.5) * beta;
     if (beta > 4.0 && renorm == MLMCPI_RENORM_PERTURBATIVE)
       coarse->beta = (both ? 0.25 : 0.5) * (1. + (both ? 1.5 : 0.5) / beta) * beta;
-    else if (beta > 4.0 && renorm == MLMCPI_RENORM_NONPERTURBATIVE)
-      return MLMCPI_EUNSUPPORTED; // needs the chi_t quadrature
+    else if (beta > 4.0 && renorm == MLMCPI_RENORM_NONPERTURBATIVE) {
+      // qft/quenchedschwingerrenormalisation.cc:7-64 (chi_t matching; host quadrature + bisection)
+      if (beta > 2000.0)
+        return MLMCPI_EUNSUPPORTED; // Phi_chit is unstable there (auxilliary.cc:45-51)
+      coarse->beta = mlmcpi_schwinger_betacoarse_nonperturbative(
+          beta, (unsigned)fine->Mt_lat * (unsigned)fine->Mx_lat, both ? 4 : 2);
+    }
     if (ctype == MLMCPI_COARSEN_ALTERNATE)
       coarse->coarsening = ((level + 1) % 2 == 0) ? MLMCPI_COARSEN_TEMPORAL : MLMCPI_COARSEN_SPATIAL;
     return 0;

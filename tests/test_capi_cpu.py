@@ -147,3 +147,36 @@ def test_stats_finalize_matches_reference_statistics(mp):
     got = np.array([out["average"], out["variance"], out["variance_error"], out["tau_int"],
                     out["error"], out["samples"]])
     assert np.allclose(got, want, rtol=1e-13, atol=0)
+
+
+def test_analytic_results_match_reference(mp):
+    """host quadrature (composite Gauss-Legendre) + bisection against the values the reference
+    computes with GSL-style QAWO/QAG and its bisection solver (golden, recorded from oracle/_ref)"""
+    L = mp._lib.lib
+    an = load("scalars")["analytic"]
+
+    def near(got, want, what):
+        # chi_t values far below 1e-12 are rounding noise in both implementations
+        assert abs(got - want) <= 1e-9 * abs(want) + 1e-14, (what, got, want)
+
+    for g in an["schwinger_chit_grid"]:
+        b, P = g["beta"], g["n_plaq"]
+        near(L.mlmcpi_schwinger_chit_analytical(b, P), float.fromhex(g["exact"]), ("exact", b, P))
+        near(L.mlmcpi_schwinger_chit_perturbative(b, P), float.fromhex(g["perturbative"]), ("pert", b, P))
+        near(L.mlmcpi_schwinger_var_chit_continuum(b, P), float.fromhex(g["var_continuum"]), ("var", b, P))
+    assert np.isnan(L.mlmcpi_schwinger_chit_analytical(2500.0, 64))
+    for g in an["schwinger_betacoarse_nonperturbative"]:
+        m = mp.schwinger(g["Mt"], g["Mt"], g["beta"], g["ctype"], 0)
+        mc = mp.coarse_model(m, renorm=mp.RENORM_NONPERTURBATIVE, ctype=g["ctype"])
+        want = float.fromhex(g["beta_coarse"])
+        assert abs(mc.beta - want) <= 1e-10 * want, (g, mc.beta, want)
+    for w, key in enumerate(["rotor_chit_exact_32", "rotor_chit_perturbative_32", "rotor_chit_continuum_32"]):
+        near(L.mlmcpi_rotor_chit(0.25, 4.0 / 32, 4.0, w), float.fromhex(an[key]), key)
+    for w in range(3):
+        near(L.mlmcpi_rotor_chit(0.25, 4.0 / 256, 4.0, w), float.fromhex(an["rotor_chit_256"][w]), ("rotor256", w))
+    near(L.mlmcpi_gff_phi_squared_analytical(10.0, 16, 16), float.fromhex(an["gff_phi_squared_10_16"]), "gff")
+    near(L.mlmcpi_ho_xsquared_analytical(1.0, 1.0, 4.0 / 32, 32, 0), float.fromhex(an["ho_x2_32"]), "ho")
+    near(L.mlmcpi_ho_xsquared_analytical(1.0, 1.0, 4.0 / 32, 32, 1), float.fromhex(an["ho_x2_continuum"]), "ho cont")
+    sh = load("scalars")["Sigma_hat"]
+    for (xi, p), y in zip(sh["args"], sh["y"]):
+        assert L.mlmcpi_sigma_hat(xi, p) == float.fromhex(y)

@@ -243,6 +243,22 @@ def scalar_cases(R):
         schwinger_chit_analytical_1_256=float(L.ref_schwinger_chit_analytical(1.0, 256)).hex(),
         gff_phi_squared_10_16=float(L.ref_gff_phi_squared_analytical(10.0, 16, 16)).hex(),
     )
+    # grid of exact / perturbative chi_t values and non-perturbatively matched coarse couplings
+    # (qft/quenchedschwingerrenormalisation.cc:7-64; ip = {Mt, Mx, coarsening, renormalisation})
+    out["analytic"]["schwinger_chit_grid"] = [
+        dict(beta=b, n_plaq=P, exact=float(L.ref_schwinger_chit_analytical(b, P)).hex(),
+             perturbative=float(L.ref_schwinger_chit_perturbative(b, P)).hex(),
+             var_continuum=float(L.ref_schwinger_var_chit_continuum(b, P)).hex())
+        for b, P in [(0.5, 64), (1.0, 256), (4.0, 256), (4.0, 4096), (16.0, 1024), (31.9, 4096),
+                     (32.1, 4096), (64.0, 16384), (256.0, 65536), (1024.0, 262144), (1999.0, 1048576)]]
+    out["analytic"]["schwinger_betacoarse_nonperturbative"] = [
+        dict(beta=b, Mt=M, ctype=ct,
+             beta_coarse=float(R.action(po.SCHWINGER, [M, M, ct, 2], [b]).coarse().param(0)).hex())
+        for b, M, ct in [(6.0, 16, po.BOTH), (16.0, 32, po.BOTH), (64.0, 64, po.BOTH),
+                         (256.0, 128, po.BOTH), (9.0, 16, po.TEMPORAL), (4.5, 8, po.BOTH),
+                         (3.0, 16, po.BOTH), (900.0, 512, po.BOTH)]]
+    a = R.action(po.ROTOR, [256, 0], [4.0, 0.25])
+    out["analytic"]["rotor_chit_256"] = [float(L.ref_rotor_chit(a.h, w)).hex() for w in range(3)]
     a = R.action(po.ROTOR, [32, 0], [4.0, 0.25])
     out["analytic"]["rotor_chit_exact_32"] = float(L.ref_rotor_chit(a.h, 0)).hex()
     out["analytic"]["rotor_chit_perturbative_32"] = float(L.ref_rotor_chit(a.h, 1)).hex()
