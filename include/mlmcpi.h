@@ -120,6 +120,10 @@ int mlmcpi_free(mlmcpi_ctx *ctx, double *d_ptr);
 int mlmcpi_upload(mlmcpi_ctx *ctx, double *d_dst, const double *h_src, size_t n);
 int mlmcpi_download(mlmcpi_ctx *ctx, double *h_dst, const double *d_src, size_t n);
 int mlmcpi_copy(mlmcpi_ctx *ctx, double *d_dst, const double *d_src, size_t n);
+/* d_out[k] = d_a[k] + alpha * d_b[k] (e.g. the MLMC differences Y = Q_fine - Q_coarse of
+ * montecarlo/montecarlotwolevel.cc:59 without a host round trip) */
+int mlmcpi_axpy(mlmcpi_ctx *ctx, double *d_out, const double *d_a, double alpha, const double *d_b,
+                size_t n);
 
 /* ---- geometry (host, integer, bit-exact with lattice/lattice2d.{hh,cc}) -- */
 int mlmcpi_sample_size(const mlmcpi_model *m);

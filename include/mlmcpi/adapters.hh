@@ -192,6 +192,8 @@ public:
   virtual unsigned int sample_size() const { return mlmcpi_sample_size(&model_); }
   virtual double evaluation_cost() const { return sample_size(); }
   virtual int get_coarsening_level() const { return level; }
+  int get_renormalisation() const { return renormalisation; }
+  int get_coarsening_type() const { return ctype; }
   const mlmcpi_model &model() const { return model_; }
 
   /** Action::coarse_action(): the renormalised action on the next-coarser lattice */
@@ -426,6 +428,7 @@ class QoI {
 public:
   QoI(const std::shared_ptr<Action> action_, int which_) : action(action_), which(which_) {}
   virtual ~QoI() {}
+  int id() const { return which; } // MLMCPI_QOI_*
   virtual const double evaluate(const std::shared_ptr<SampleState> state) {
     DeviceVector x(state->data.size()), q(1);
     x.upload(state->data.data());

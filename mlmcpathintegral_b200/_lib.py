@@ -67,6 +67,7 @@ SIGNATURES = {
     "mlmcpi_upload": (_i, [_vp, _vp, _vp, _sz]),
     "mlmcpi_download": (_i, [_vp, _vp, _vp, _sz]),
     "mlmcpi_copy": (_i, [_vp, _vp, _vp, _sz]),
+    "mlmcpi_axpy": (_i, [_vp, _vp, _vp, _d, _vp, _sz]),
     "mlmcpi_sample_size": (_i, [_MP]),
     "mlmcpi_vertex_cart2lin": (_u32, [_i, _i, _i, _i, _i]),
     "mlmcpi_vertex_lin2cart": (None, [_i, _i, _i, _u32, _ip, _ip]),

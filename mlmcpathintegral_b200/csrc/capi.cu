@@ -220,6 +220,21 @@ int mlmcpi_copy(mlmcpi_ctx *ctx, double *d_dst, const double *d_src, size_t n) {
   return 0;
 }
 
+__global__ void axpy_kernel(double *out, const double *a, double alpha, const double *b, size_t n) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n)
+    out[k] = a[k] + alpha * b[k];
+}
+int mlmcpi_axpy(mlmcpi_ctx *ctx, double *d_out, const double *d_a, double alpha, const double *d_b, size_t n) {
+  if (!ctx || !d_out || !d_a || !d_b)
+    return MLMCPI_EINVAL;
+  if (n == 0)
+    return 0;
+  axpy_kernel<<<cdiv((long long)n, 256), 256, 0, ctx->stream>>>(d_out, d_a, alpha, d_b, n);
+  MLMCPI_LAUNCHED("axpy");
+  return 0;
+}
+
 // ================================================================= geometry
 int mlmcpi_sample_size(const mlmcpi_model *m) {
   switch (m->model) {
