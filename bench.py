@@ -35,18 +35,43 @@ METRIC = "lattice site-updates/s (Schwinger HMC + hierarchical fill-in)"
 UNIT = "site-updates/s"
 
 
+# The five configurations of BASELINE.json.  `schwinger512` (configs[3]) is the one the metric
+# is quoted on and what the driver measures; the others are run on request (--workload) so that
+# every named shape has a measured throughput (profiles/r01_configs.md).
+WORKLOADS = {
+    "ho32": dict(config="configs[0]: driver_qm harmonic oscillator, single-level HMC, parameters_qm_template.in "
+                        "defaults (M_lat=32, T=4, m0=mu2=1, nt=100, dt=0.1)",
+                 model="ho", lattice=32, beta=None, levels=1, chains=65536, sampler="HMC", qoi="QOI_X2"),
+    "rotor256": dict(config="configs[1]: driver_qm topological rotor, hierarchical sampler, M_lat=256, 3 levels, "
+                            "HMC on the coarsest level",
+                     model="rotor", lattice=256, beta=None, levels=3, chains=8192, sampler="HMC",
+                     qoi="QOI_ROTOR_CHI"),
+    "gff256": dict(config="configs[2]: driver_qft GFF 256x256, 4 levels (coarsening rotate), checkerboard "
+                          "overrelaxed heat bath on the coarsest level, conditioned Gaussian fill-in above",
+                   model="gff", lattice=256, beta=None, levels=4, chains=512, sampler="heatbath", qoi="QOI_PHI2"),
+    "schwinger512": dict(config="configs[3]", model="schwinger", lattice=512, beta=1024.0, levels=3, chains=512,
+                         sampler="HMC", qoi="QOI_SCHWINGER_CHI"),
+    "schwinger1024": dict(config="configs[4]: quenched Schwinger 1024x1024, hierarchical sampler (3 levels), chains "
+                                 "sharded over the GPUs, NCCL allreduce of the QoI moments",
+                          model="schwinger", lattice=1024, beta=1024.0, levels=3, chains=128, sampler="HMC",
+                          qoi="QOI_SCHWINGER_CHI"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--lattice", type=int, default=512)
-    ap.add_argument("--beta", type=float, default=1024.0,
+    ap.add_argument("--workload", default="schwinger512", choices=sorted(WORKLOADS),
+                    help="BASELINE.json config to run; the default is the headline one (configs[3])")
+    ap.add_argument("--lattice", type=int, default=None)
+    ap.add_argument("--beta", type=float, default=None,
                     help="fine-level coupling; default = continuum-limit point beta/P = 2^-8 at 512^2 "
                          "(ApproximateBesselProduct fill-in); --beta 4 runs the BesselProduct regime")
-    ap.add_argument("--levels", type=int, default=3)
-    ap.add_argument("--chains", type=int, default=512, help="chains per GPU")
+    ap.add_argument("--levels", type=int, default=None)
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
     ap.add_argument("--nt", type=int, default=100)
     ap.add_argument("--dt", type=float, default=0.1)
     ap.add_argument("--thermalise", type=int, default=20, help="overrelaxed heat-bath sweeps before timing")
@@ -54,16 +79,35 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
-    return ap.parse_args()
+    a = ap.parse_args()
+    w = WORKLOADS[a.workload]
+    for k in ("lattice", "beta", "levels", "chains"):
+        if getattr(a, k) is None:
+            setattr(a, k, w.get(k))
+    return a
 
 
 def workload_config(a):
-    return {
-        "workload": f"driver_qft quenched Schwinger {a.lattice}x{a.lattice}, hierarchical sampler "
-                    f"({a.levels} levels, coarsening both, perturbative renormalisation), HMC coarse "
-                    f"sampler nt={a.nt} dt={a.dt}, QoI topological susceptibility",
-        "lattice": [a.lattice, a.lattice], "beta": a.beta, "levels": a.levels, "nt": a.nt, "dt": a.dt,
-    }
+    w = WORKLOADS[a.workload]
+    if w["model"] == "schwinger":
+        return {
+            "workload": f"driver_qft quenched Schwinger {a.lattice}x{a.lattice}, hierarchical sampler "
+                        f"({a.levels} levels, coarsening both, perturbative renormalisation), HMC coarse "
+                        f"sampler nt={a.nt} dt={a.dt}, QoI topological susceptibility",
+            "lattice": [a.lattice, a.lattice], "beta": a.beta, "levels": a.levels, "nt": a.nt, "dt": a.dt,
+        }
+    return {"workload": w["config"], "lattice": [a.lattice], "levels": a.levels, "nt": a.nt, "dt": a.dt}
+
+
+def build_model(mp, a):
+    w = WORKLOADS[a.workload]
+    if w["model"] == "schwinger":
+        return mp.schwinger(a.lattice, a.lattice, a.beta)
+    if w["model"] == "gff":
+        return mp.gff(a.lattice, a.lattice, 10.0)
+    if w["model"] == "rotor":
+        return mp.rotor(a.lattice)
+    return mp.ho(a.lattice)
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -156,6 +200,9 @@ def reference_main(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if WORKLOADS[a.workload]["model"] != "schwinger":
+        emit({"impl": "reference", "unavailable": "the reference arm times the Schwinger workloads only"})
+        return
     draws_total = a.steps
     # bounded sample: one cascade at 512^2 is ~0.5 s per core; every process does one
     # untimed warm-up cascade, then `steps` timed ones
@@ -244,20 +291,30 @@ def gpu_main(a):
     torch.cuda.set_device(local)
     ctx = mp.Context(local, seed=0x5EED0001)
     B = a.chains
-    m = mp.schwinger(a.lattice, a.lattice, a.beta)
-    sampler = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=a.levels, nt=a.nt, dt=a.dt,
-                         renorm=mp.RENORM_PERTURBATIVE, chain0=rank * B)
+    w = WORKLOADS[a.workload]
+    is_schwinger = w["model"] == "schwinger"
+    QOI = getattr(mp, w["qoi"])
+    m = build_model(mp, a)
+    kind = mp.SAMPLER_HMC if w["sampler"] == "HMC" else mp.SAMPLER_HEATBATH
+    sampler = mp.Sampler(ctx, m, B, kind=kind, n_levels=a.levels, nt=a.nt, dt=a.dt,
+                         renorm=mp.RENORM_PERTURBATIVE if w["model"] != "gff" else mp.RENORM_NONE,
+                         ctype=mp.COARSEN_ROTATE if w["model"] == "gff" else mp.COARSEN_BOTH,
+                         n_sweep_overrelax=1, n_sweep_heatbath=1, chain0=rank * B)
     k_max = 10
     stats = mp.Statistics(ctx, k_max, B)
     # start state: hot (U(-pi,pi), Action::initialise_state) at small beta, cold at large beta,
     # then thermalised by overrelaxed heat-bath sweeps on the fine level (untimed)
-    x = ctx.init_state(m, B, rank * B, 0) if a.beta <= 8 else ctx.state(m, B)
-    for k in range(a.thermalise):
-        ctx.overrelax_sweep(m, x)
-        ctx.heatbath_sweep(m, x, rank * B, 1000 + k)
+    if is_schwinger:
+        x = ctx.init_state(m, B, rank * B, 0) if a.beta <= 8 else ctx.state(m, B)
+    else:
+        x = ctx.init_state(m, B, rank * B, 0)
+    if w["model"] != "ho":  # (the harmonic oscillator has no heat bath; HMC burn-in below)
+        for k in range(a.thermalise):
+            ctx.overrelax_sweep(m, x)
+            ctx.heatbath_sweep(m, x, rank * B, 1000 + k)
     sampler.set_state(x)
     tuned = None
-    if a.autotune:  # HMCSampler::autotune_stepsize (hmcsampler.cc:72-113) on the coarsest level
+    if a.autotune and kind == mp.SAMPLER_HMC:  # HMCSampler::autotune_stepsize (hmcsampler.cc:72-113)
         dt0 = a.dt
         for _ in range(12):  # bring dt into the bisection bracket [dt/2, 2 dt] of the reference
             sampler.set_dt(dt0)
@@ -270,7 +327,7 @@ def gpu_main(a):
 
     def step():
         sampler.draw(x)
-        stats.record(ctx.qoi(m, mp.QOI_SCHWINGER_CHI, x))
+        stats.record(ctx.qoi(m, QOI, x))
         stats.pack_device(packed)
         if world > 1:  # QoI moments + autocorrelation sums: the only inter-GPU traffic
             dist.all_reduce(packed)
@@ -301,7 +358,7 @@ def gpu_main(a):
     ctx.profile(False)
     launches = ctx.launches - launches0
     work = sampler.work()
-    units_per_step = work["leapfrog_site_steps"] + work["filled_fine_sites"]
+    units_per_step = work["leapfrog_site_steps"] + work["filled_fine_sites"] + work["sweep_site_updates"]
     t = torch.tensor([ms], dtype=torch.float64, device=ctx.device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -319,7 +376,7 @@ def gpu_main(a):
         h_q = torch.empty(B, dtype=torch.float64, pin_memory=True)
         h_x.copy_(x)
         torch.cuda.synchronize()
-        sampler.draw_host(h_x, mp.QOI_SCHWINGER_CHI, h_q, None)  # warm-up
+        sampler.draw_host(h_x, QOI, h_q, None)  # warm-up
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -327,7 +384,7 @@ def gpu_main(a):
         k_e2e = max(1, min(a.steps, 5))
         e0.record()
         for _ in range(k_e2e):
-            sampler.draw_host(h_x, mp.QOI_SCHWINGER_CHI, h_q, None)
+            sampler.draw_host(h_x, QOI, h_q, None)
         e1.record()
         torch.cuda.synchronize()
         te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
@@ -344,11 +401,12 @@ def gpu_main(a):
         else:
             peak, which = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = lf_bytes / (lf_ms * 1e-3) / 1e9 if lf_ms > 0 else None
+        if not is_schwinger:
+            achieved = None
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("leapfrog_dram_bytes_per_launch")
-        nc = mp.sample_size(sampler.level_model(a.levels - 1)) // 2
         steps_per_launch = (a.nt + 1) * a.steps / lf_launches if lf_launches else None
         roofline = {
             "bound": "hbm",
@@ -372,8 +430,8 @@ def gpu_main(a):
             "site_updates_per_step_per_gpu": {k: v for k, v in work.items()},
             "value_per_gpu": value / world,
             "acceptance_per_level": p_acc, "hmc_autotune": tuned,
-            "chi_t": {"average": st["average"], "error": st["error"], "tau_int": st["tau_int"],
-                      "samples": st["samples"]},
+            "qoi": {"name": w["qoi"], "average": st["average"], "error": st["error"], "tau_int": st["tau_int"],
+                    "samples": st["samples"]},
             "ess_per_s": st["samples"] / st["tau_int"] / (ms_max * 1e-3),
         })
         line = {
@@ -383,7 +441,10 @@ def gpu_main(a):
             "data": "synthetic (U(-pi,pi) start states, Philox4x32-10)", "config": cfg,
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
-        if world == 1 and not a.no_cpu_baseline:
+        if not is_schwinger:
+            line["metric"] = "lattice site-updates/s (%s)" % a.workload
+            line["roofline"] = None  # 1-D paths / Gaussian fields: see profiles/r01_summary.md section 4
+        if world == 1 and not a.no_cpu_baseline and is_schwinger:
             v, cores, kind, sample, _, _ = cpu_arm(a, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         emit(line)

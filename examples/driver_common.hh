@@ -27,7 +27,8 @@ inline std::string current_time() {
 /** the sampler factory for a sampler id of the parameter file; nullptr (after a message) if
  * the combination is not supported */
 inline std::shared_ptr<SamplerFactory>
-construct_sampler_factory(const int samplerid, const bool cluster_supported, const std::shared_ptr<QoIFactory> qoi_factory,
+construct_sampler_factory(const int samplerid, const bool cluster_supported, const bool exact_supported,
+                          const std::shared_ptr<QoIFactory> qoi_factory,
                           const std::shared_ptr<SamplerFactory> coarse_sampler_factory,
                           const std::shared_ptr<ConditionedFineActionFactory> conditioned_fine_action_factory,
                           const HMCParameters param_hmc, const ClusterParameters param_cluster,
@@ -50,7 +51,9 @@ construct_sampler_factory(const int samplerid, const bool cluster_supported, con
     std::cerr << " ERROR: cluster not supported for chosen action." << std::endl;
     return nullptr;
   case SamplerExact:
-    std::cerr << " ERROR: the exact (Cholesky) samplers are not part of the device library." << std::endl;
+    if (exact_supported)
+      return std::make_shared<ExactSamplerFactory>();
+    std::cerr << " ERROR: exact sampler not supported for chosen action." << std::endl;
     return nullptr;
   }
   std::cerr << " ERROR: Unsupported sampler." << std::endl;

@@ -56,11 +56,14 @@ enum { MLMCPI_QOI_X2 = 0, MLMCPI_QOI_ROTOR_CHI = 1, MLMCPI_QOI_SCHWINGER_CHI = 2
 enum { MLMCPI_STREAM_INIT = 1, MLMCPI_STREAM_HMC_MOMENTUM = 2, MLMCPI_STREAM_HMC_ACCEPT = 3,
        MLMCPI_STREAM_HEATBATH = 4, MLMCPI_STREAM_FILL1 = 5, MLMCPI_STREAM_FILL2 = 6,
        MLMCPI_STREAM_FILL3 = 7, MLMCPI_STREAM_TWOLEVEL_ACCEPT = 8, MLMCPI_STREAM_CLUSTER = 9,
-       MLMCPI_STREAM_GAUGE = 10 };
+       MLMCPI_STREAM_GAUGE = 10, MLMCPI_STREAM_EXACT = 11 };
 /* coarse-level samplers of sampler/hierarchicalsampler.hh */
 /* MLMCPI_SAMPLER_CLUSTER: ClusterSampler (rotor, sampler/clustersampler.cc) or
  * QuenchedSchwingerClusterSampler (sampler/quenchedschwingerclustersampler.cc) */
-enum { MLMCPI_SAMPLER_HMC = 0, MLMCPI_SAMPLER_HEATBATH = 1, MLMCPI_SAMPLER_CLUSTER = 2 };
+/* MLMCPI_SAMPLER_EXACT: independent exact draws (harmonic oscillator: the Cholesky sampler of
+ * qm/harmonicoscillatoraction.cc:38-66) */
+enum { MLMCPI_SAMPLER_HMC = 0, MLMCPI_SAMPLER_HEATBATH = 1, MLMCPI_SAMPLER_CLUSTER = 2,
+       MLMCPI_SAMPLER_EXACT = 3 };
 
 /* One level of one model: the data members of the reference's action classes. */
 typedef struct mlmcpi_model {
@@ -211,6 +214,12 @@ int mlmcpi_prolong_fill_eval(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const do
  * action/qm/rotoraction.hh:226-253); `update0` numbers the first update (Philox draw counter) */
 int mlmcpi_cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *rotor, double *d_x, int B,
                           uint32_t chain0, uint64_t update0, int n_updates);
+/* HarmonicOscillatorAction::draw (qm/harmonicoscillatoraction.cc:59-66): independent exact samples
+ * x = L_cov y of the harmonic-oscillator path measure for every chain; L_cov (Cholesky factor of
+ * the inverse of the cyclic tridiagonal precision matrix, build_covariance :38-56) is computed
+ * on the host once per model and cached in the context */
+int mlmcpi_exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *ho, double *d_x, int B, uint32_t chain0,
+                      uint64_t draw);
 /* QuenchedSchwingerClusterSampler::draw lines 52-82: links from the rotor chain psi
  * (length Mt*Mx) followed by a random gauge transformation */
 int mlmcpi_schwinger_from_cluster(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_psi,

@@ -230,6 +230,13 @@ private:
 };
 typedef ClusterSamplerFactory QuenchedSchwingerClusterSamplerFactory;
 
+/** sampler = 'exact': the action's own draw() (harmonic oscillator: Cholesky sampler,
+ * qm/harmonicoscillatoraction.hh HarmonicOscillatorSamplerFactory) */
+class ExactSamplerFactory : public SamplerFactory {
+public:
+  mlmcpi_sampler_params params(const Action &a) const { return base(a, MLMCPI_SAMPLER_EXACT); }
+};
+
 /** HierarchicalSampler (sampler/hierarchicalsampler.hh:141-170): the coarse factory's recipe
  * on the coarsest of n_max_level levels, two-level Metropolis steps above it */
 class HierarchicalSamplerFactory : public SamplerFactory {

@@ -15,7 +15,7 @@ HO, QUARTIC, ROTOR, SCHWINGER, GFF = 0, 1, 2, 3, 4
 COARSEN_BOTH, COARSEN_TEMPORAL, COARSEN_SPATIAL, COARSEN_ALTERNATE, COARSEN_ROTATE = range(5)
 RENORM_NONE, RENORM_PERTURBATIVE, RENORM_NONPERTURBATIVE = range(3)
 QOI_X2, QOI_ROTOR_CHI, QOI_SCHWINGER_CHI, QOI_AVG_PLAQUETTE, QOI_PHI2 = range(5)
-SAMPLER_HMC, SAMPLER_HEATBATH, SAMPLER_CLUSTER = 0, 1, 2
+SAMPLER_HMC, SAMPLER_HEATBATH, SAMPLER_CLUSTER, SAMPLER_EXACT = 0, 1, 2, 3
 E_INVAL, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4
 OPT_EXPCOS_ENVELOPE, OPT_LEAPFROG_VARIANT, OPT_LEAPFROG_ROWS, OPT_LEAPFROG_FUSE = 1, 2, 3, 4
 
@@ -96,6 +96,7 @@ SIGNATURES = {
     "mlmcpi_gff_phi_squared_analytical": (C.c_double, [C.c_double, _i, _i]),
     "mlmcpi_ho_xsquared_analytical": (C.c_double, [C.c_double, C.c_double, C.c_double, _i, _i]),
     "mlmcpi_schwinger_betacoarse_nonperturbative": (C.c_double, [C.c_double, C.c_uint, _i]),
+    "mlmcpi_exact_draw": (_i, [_vp, _MP, _vp, _i, _u32, _u64]),
     "mlmcpi_prolong_fill": (_i, [_vp, _MP, _vp, _vp, _i, _u32, _u64]),
     "mlmcpi_prolong_fill_eval": (_i, [_vp, _MP, _vp, _vp, _i, _u32, _u64, _vp]),
     "mlmcpi_cluster_update": (_i, [_vp, _MP, _vp, _i, _u32, _u64, _i]),

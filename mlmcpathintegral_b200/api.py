@@ -16,7 +16,7 @@ from ._lib import (COARSEN_ALTERNATE, COARSEN_BOTH, COARSEN_ROTATE, COARSEN_SPAT
                    COARSEN_TEMPORAL, GFF, HO, QOI_AVG_PLAQUETTE, QOI_PHI2, QOI_ROTOR_CHI,
                    QOI_SCHWINGER_CHI, QOI_X2, QUARTIC, RENORM_NONE, RENORM_NONPERTURBATIVE,
                    RENORM_PERTURBATIVE, ROTOR,
-                   SAMPLER_CLUSTER, SAMPLER_HEATBATH, SAMPLER_HMC, SCHWINGER, MlmcParams, Model,
+                   SAMPLER_CLUSTER, SAMPLER_EXACT, SAMPLER_HEATBATH, SAMPLER_HMC, SCHWINGER, MlmcParams, Model,
                    SamplerParams)
 
 L = _lib.lib
@@ -213,6 +213,12 @@ class Context:
         self._ck(L.mlmcpi_prolong_fill_eval(self.h, C.byref(fine), _ptr(xc), _ptr(x), x.shape[0], chain0,
                                             draw, _ptr(S)))
         return S[:x.shape[0]], S[x.shape[0]:]
+
+    def exact_draw(self, m, B, chain0=0, draw=0):
+        """HarmonicOscillatorAction::draw: independent exact samples for B chains"""
+        x = self.state(m, B)
+        self._ck(L.mlmcpi_exact_draw(self.h, C.byref(m), _ptr(x), B, chain0, draw))
+        return x
 
     def cluster_update(self, rotor_model, x, chain0=0, update0=0, n_updates=1):
         self._ck(L.mlmcpi_cluster_update(self.h, C.byref(rotor_model), _ptr(x), x.shape[0], chain0,

@@ -147,6 +147,8 @@ void mlmcpi_destroy(mlmcpi_ctx *ctx) {
   for (int k = 0; k < MLMCPI_N_WORK; ++k)
     if (ctx->work[k])
       cudaFree(ctx->work[k]);
+  for (auto &kv : ctx->ho_exact_factor)
+    cudaFree(kv.second);
   if (ctx->own_stream)
     cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -758,6 +760,13 @@ int mlmcpi_cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *rotor, double *d_
     return MLMCPI_EINVAL;
   return qm::cluster_update(ctx, rotor, d_x, B, chain0, update0, n_updates);
 }
+int mlmcpi_exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0, uint64_t draw) {
+  if (!ctx || !m || !d_x || B <= 0)
+    return MLMCPI_EINVAL;
+  if (m->model != MLMCPI_HO)
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "the exact sampler is defined for the harmonic oscillator");
+  return qm::exact_draw(ctx, m, d_x, B, chain0, draw);
+}
 int mlmcpi_schwinger_from_cluster(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_psi, double *d_x,
                                   int B, uint32_t chain0, uint64_t draw) {
   if (!ctx || !m || B <= 0 || m->model != MLMCPI_SCHWINGER)
@@ -952,6 +961,14 @@ static int coarse_draw(mlmcpi_sampler *s, int c0, int B) {
     set_i32_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, acc, 1);
     MLMCPI_LAUNCHED("set_accept");
     s->work[1] += (double)B * n_updates; // cluster updates
+  } else if (s->prm.kind == MLMCPI_SAMPLER_EXACT) {
+    // HarmonicOscillatorAction::draw as a sampler (qm/harmonicoscillatoraction.hh: the action IS a
+    // Sampler): independent exact draws, always accepted
+    if ((rc = mlmcpi_exact_draw(ctx, m, x, B, chain0, level_draw(s->draw, l, 0))))
+      return rc;
+    set_i32_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, acc, 1);
+    MLMCPI_LAUNCHED("set_accept");
+    s->work[1] += (double)B * n_sites(*m);
   } else {
     return ctx_fail(ctx, MLMCPI_EINVAL, "unknown sampler kind");
   }

@@ -8,6 +8,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <array>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -41,6 +43,9 @@ struct mlmcpi_ctx {
   size_t scratch_n = 0;
   double *work[MLMCPI_N_WORK] = {}; // 0-3: HMC work states, 4-6: two-level step
   size_t work_n[MLMCPI_N_WORK] = {};
+  // exact sampler of the harmonic oscillator: transposed Cholesky factors of the covariance,
+  // device [M][M], keyed by (M, a, m0, mu2)
+  std::map<std::array<double, 4>, double *> ho_exact_factor;
 };
 
 int ctx_fail(mlmcpi_ctx *ctx, int code, const char *what, const char *detail = nullptr);
@@ -576,6 +581,7 @@ DECL_MODEL_API(gff)
 
 namespace qm {
 int cluster_update(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t, int);
+int exact_draw(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);
 }
 namespace schwinger {
 int from_cluster(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t, uint64_t);

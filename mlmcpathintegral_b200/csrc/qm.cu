@@ -8,6 +8,8 @@
 // shared memory.  State layout [chain][site] = the reference's SampleState::data.
 //
 // Reference citations relative to /root/reference/src.
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -651,6 +653,108 @@ int cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uin
   rotor_cluster_kernel<<<cdiv(B, 64), 64, 0, ctx->stream>>>(q, x, B, chain0, ctx->seed, update0,
                                                           n_updates);
   MLMCPI_LAUNCHED("qm::cluster_update");
+  return 0;
+}
+
+// HarmonicOscillatorAction::build_covariance (qm/harmonicoscillatoraction.cc:38-56) on the host:
+// the covariance C = P^{-1} of the cyclic tridiagonal precision matrix P (diagonal
+// a m0 mu2 + 2 m0 / a, off-diagonals -m0 / a) and its Cholesky factor C = L L^T, returned
+// TRANSPOSED (LT[j][i] = L[i][j]) so that the device reads are coalesced.  (The reference indexes
+// the sub-diagonal with `(i - 1) % M_lat` on unsigned integers; the periodic neighbour is meant.)
+static bool ho_exact_factor_host(const mlmcpi_model *m, std::vector<double> &LT) {
+  const int M = m->M_lat;
+  const double d = m->a_lat * m->m0 * m->mu2 + 2.0 * m->m0 / m->a_lat, c = -m->m0 / m->a_lat;
+  std::vector<double> P((size_t)M * M, 0.0), C((size_t)M * M, 0.0), L((size_t)M * M, 0.0);
+  for (int i = 0; i < M; ++i) {
+    P[(size_t)i * M + i] = d;
+    P[(size_t)i * M + (i + 1) % M] += c;
+    P[(size_t)i * M + (i + M - 1) % M] += c;
+    C[(size_t)i * M + i] = 1.0;
+  }
+  for (int k = 0; k < M; ++k) { // Gauss-Jordan; P is symmetric positive definite
+    const double piv = 1.0 / P[(size_t)k * M + k];
+    for (int j = 0; j < M; ++j) {
+      P[(size_t)k * M + j] *= piv;
+      C[(size_t)k * M + j] *= piv;
+    }
+    for (int i = 0; i < M; ++i) {
+      const double f = P[(size_t)i * M + k];
+      if (i == k || f == 0.0)
+        continue;
+      for (int j = 0; j < M; ++j) {
+        P[(size_t)i * M + j] -= f * P[(size_t)k * M + j];
+        C[(size_t)i * M + j] -= f * C[(size_t)k * M + j];
+      }
+    }
+  }
+  for (int j = 0; j < M; ++j) {
+    double s = C[(size_t)j * M + j];
+    for (int k = 0; k < j; ++k)
+      s -= L[(size_t)j * M + k] * L[(size_t)j * M + k];
+    if (!(s > 0.0))
+      return false;
+    const double ljj = std::sqrt(s);
+    L[(size_t)j * M + j] = ljj;
+    for (int i = j + 1; i < M; ++i) {
+      double t = C[(size_t)i * M + j];
+      for (int k = 0; k < j; ++k)
+        t -= L[(size_t)i * M + k] * L[(size_t)j * M + k];
+      L[(size_t)i * M + j] = t / ljj;
+    }
+  }
+  LT.assign((size_t)M * M, 0.0);
+  for (int i = 0; i < M; ++i)
+    for (int j = 0; j <= i; ++j)
+      LT[(size_t)j * M + i] = L[(size_t)i * M + j];
+  return true;
+}
+
+// HarmonicOscillatorAction::draw (qm/harmonicoscillatoraction.cc:59-66): x = L_cov y, y i.i.d.
+// N(0,1).  One block per chain; y is generated into shared memory (one Box-Muller pair per two
+// entries), thread i accumulates row i of L_cov against it (LT is shared by all chains: L2 hits).
+__global__ void ho_exact_draw_kernel(int M, const double *__restrict__ LT, double *x, uint32_t chain0,
+                                     uint64_t seed, uint64_t draw) {
+  extern __shared__ double y[];
+  const int chain = blockIdx.x;
+  for (int k = threadIdx.x; 2 * k < M; k += blockDim.x) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_EXACT, draw, chain0 + chain, k);
+    double z0, z1;
+    rng_normal2(r, z0, z1);
+    y[2 * k] = z0;
+    if (2 * k + 1 < M)
+      y[2 * k + 1] = z1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    double s = 0.0;
+    for (int j = 0; j <= i; ++j)
+      s += LT[(size_t)j * M + i] * y[j];
+    x[(size_t)chain * M + i] = s;
+  }
+}
+
+int exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0, uint64_t draw) {
+  if (m->model != MLMCPI_HO)
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "the exact sampler is defined for the harmonic oscillator");
+  const int M = m->M_lat;
+  if (M > 4096)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "exact sampler: M_lat too large for the dense Cholesky factor");
+  const std::array<double, 4> key = {(double)M, m->a_lat, m->m0, m->mu2};
+  auto it = ctx->ho_exact_factor.find(key);
+  if (it == ctx->ho_exact_factor.end()) {
+    std::vector<double> LT;
+    if (!ho_exact_factor_host(m, LT))
+      return ctx_fail(ctx, MLMCPI_EINVAL, "exact sampler: covariance matrix is not positive definite");
+    double *d = nullptr;
+    MLMCPI_CUDA(cudaMalloc((void **)&d, LT.size() * sizeof(double)));
+    MLMCPI_CUDA(cudaMemcpyAsync(d, LT.data(), LT.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream)); // LT goes out of scope
+    it = ctx->ho_exact_factor.emplace(key, d).first;
+  }
+  const int threads = std::min(1024, ((M + 31) / 32) * 32);
+  ho_exact_draw_kernel<<<B, threads, (size_t)(M + 1) * sizeof(double), ctx->stream>>>(M, it->second, x, chain0,
+                                                                                     ctx->seed, draw);
+  MLMCPI_LAUNCHED("qm::exact_draw");
   return 0;
 }
 

@@ -1418,6 +1418,100 @@ void orc_hmc_momentum(const orc_model *m, uint64_t seed, uint64_t draw,
   }
 }
 
+/* qm/harmonicoscillatoraction.cc:38-56: L_cov = Cholesky factor (lower, row-major [M][M]) of the
+ * covariance Sigma^{-1}, Sigma the cyclic tridiagonal precision matrix of the action.  The
+ * reference indexes the sub-diagonal with `(i - 1) % M_lat` on unsigned integers, which is the
+ * periodic neighbour only when M_lat divides 2^32; the periodic neighbour is meant and used here. */
+int orc_ho_exact_factor(const orc_model *m, double *L) {
+  const int M = m->M_lat;
+  const double d = m->a_lat * m->m0 * m->mu2 + 2.0 * m->m0 / m->a_lat, c = -m->m0 / m->a_lat;
+  double *P = (double *)calloc((size_t)M * M, sizeof(double));
+  double *C = (double *)calloc((size_t)M * M, sizeof(double));
+  if (!P || !C)
+    return -1;
+  for (int i = 0; i < M; ++i) {
+    P[(size_t)i * M + i] = d;
+    P[(size_t)i * M + (i + 1) % M] += c;
+    P[(size_t)i * M + (i + M - 1) % M] += c;
+  }
+  /* Gauss-Jordan inverse (the precision matrix is symmetric positive definite: no pivoting) */
+  for (int i = 0; i < M; ++i)
+    C[(size_t)i * M + i] = 1.0;
+  for (int k = 0; k < M; ++k) {
+    const double piv = 1.0 / P[(size_t)k * M + k];
+    for (int j = 0; j < M; ++j) {
+      P[(size_t)k * M + j] *= piv;
+      C[(size_t)k * M + j] *= piv;
+    }
+    for (int i = 0; i < M; ++i) {
+      if (i == k)
+        continue;
+      const double f = P[(size_t)i * M + k];
+      if (f == 0.0)
+        continue;
+      for (int j = 0; j < M; ++j) {
+        P[(size_t)i * M + j] -= f * P[(size_t)k * M + j];
+        C[(size_t)i * M + j] -= f * C[(size_t)k * M + j];
+      }
+    }
+  }
+  /* Cholesky C = L L^T */
+  memset(L, 0, (size_t)M * M * sizeof(double));
+  for (int j = 0; j < M; ++j) {
+    double s = C[(size_t)j * M + j];
+    for (int k = 0; k < j; ++k)
+      s -= L[(size_t)j * M + k] * L[(size_t)j * M + k];
+    if (!(s > 0.0)) {
+      free(P);
+      free(C);
+      return -2;
+    }
+    const double ljj = sqrt(s);
+    L[(size_t)j * M + j] = ljj;
+    for (int i = j + 1; i < M; ++i) {
+      double t = C[(size_t)i * M + j];
+      for (int k = 0; k < j; ++k)
+        t -= L[(size_t)i * M + k] * L[(size_t)j * M + k];
+      L[(size_t)i * M + j] = t / ljj;
+    }
+  }
+  free(P);
+  free(C);
+  return 0;
+}
+
+/* HarmonicOscillatorAction::draw (qm/harmonicoscillatoraction.cc:59-66): x = L_cov y with y
+ * i.i.d. standard normal (one Box-Muller pair per two entries, stream ORC_STREAM_EXACT) */
+int orc_ho_exact_draw(const orc_model *m, uint64_t seed, uint64_t draw, uint32_t chain, double *x) {
+  const int M = m->M_lat;
+  double *L = (double *)malloc(((size_t)M * M + M) * sizeof(double));
+  if (!L)
+    return -1;
+  double *y = L + (size_t)M * M;
+  const int rc = orc_ho_exact_factor(m, L);
+  if (rc) {
+    free(L);
+    return rc;
+  }
+  for (int k = 0; 2 * k < M; ++k) {
+    orc_rng r;
+    orc_rng_init(&r, seed, ORC_STREAM_EXACT, draw, chain, k);
+    double z0, z1;
+    orc_rng_normal2(&r, &z0, &z1);
+    y[2 * k] = z0;
+    if (2 * k + 1 < M)
+      y[2 * k + 1] = z1;
+  }
+  for (int i = 0; i < M; ++i) {
+    double s = 0.0;
+    for (int j = 0; j <= i; ++j)
+      s += L[(size_t)i * M + j] * y[j];
+    x[i] = s;
+  }
+  free(L);
+  return 0;
+}
+
 /* sampler/hmcsampler.cc:22-69 */
 int orc_hmc_step(const orc_model *m, int nt, double dt, uint64_t seed,
                  uint64_t draw, uint32_t chain, double *x, double *out) {

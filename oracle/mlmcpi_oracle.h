@@ -41,7 +41,7 @@ enum { ORC_QOI_X2 = 0, ORC_QOI_ROTOR_CHI = 1, ORC_QOI_SCHWINGER_CHI = 2,
 enum { ORC_STREAM_INIT = 1, ORC_STREAM_HMC_MOMENTUM = 2, ORC_STREAM_HMC_ACCEPT = 3,
        ORC_STREAM_HEATBATH = 4, ORC_STREAM_FILL1 = 5, ORC_STREAM_FILL2 = 6,
        ORC_STREAM_FILL3 = 7, ORC_STREAM_TWOLEVEL_ACCEPT = 8, ORC_STREAM_CLUSTER = 9,
-       ORC_STREAM_GAUGE = 10 };
+       ORC_STREAM_GAUGE = 10, ORC_STREAM_EXACT = 11 };
 
 typedef struct {
   int model;
@@ -114,7 +114,10 @@ double orc_besselproduct_Znorm_inv(const double alphaZ[17], double phi, int resc
 double orc_besselproduct_pdf(double beta, double x, double x_p, double x_m);
 double orc_approxbessel_pdf(double beta, double x, double x_p, double x_m);
 double orc_expsin2_draw(orc_rng *r, double sigma);
-/* 0: the reference's envelope (default); 1: the product's tighter envelope (same pdf) */
+/* exact (Cholesky) sampler of the harmonic oscillator, qm/harmonicoscillatoraction.cc:38-66 */
+int orc_ho_exact_factor(const orc_model *m, double *L);
+int orc_ho_exact_draw(const orc_model *m, uint64_t seed, uint64_t draw, uint32_t chain, double *x);
+/* 0: the reference's envelope (default); 1, 2: the product's tighter envelopes (same pdf) */
 void orc_set_expcos_envelope(int envelope);
 double orc_expcos_draw(orc_rng *r, double beta, double x_p, double x_m);
 double orc_besselproduct_draw(orc_rng *r, double beta, double x_p, double x_m);

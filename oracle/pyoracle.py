@@ -157,6 +157,8 @@ class Oracle:
             "orc_approxbessel_draw": (d, [C.POINTER(Rng), d, d, d]),
             "orc_init_state": (None, [MP, u64, u64, u32, c_double_p]),
             "orc_hmc_momentum": (None, [MP, u64, u64, u32, c_double_p]),
+            "orc_ho_exact_factor": (i, [MP, c_double_p]),
+            "orc_ho_exact_draw": (i, [MP, u64, u64, u32, c_double_p]),
             "orc_hmc_step": (i, [MP, i, d, u64, u64, u32, c_double_p, c_double_p]),
             "orc_heatbath_sweep_coloured": (None, [MP, u64, u64, u32, c_double_p]),
             "orc_fill": (None, [MP, u64, u64, u32, c_double_p]),
@@ -245,6 +247,16 @@ class Oracle:
         p = np.zeros(self.sample_size(m))
         self.lib.orc_hmc_momentum(C.byref(m), seed, draw, chain, _dp(p))
         return p
+
+    def ho_exact_factor(self, m):
+        L = np.zeros((m.M_lat, m.M_lat))
+        assert self.lib.orc_ho_exact_factor(C.byref(m), _dp(L)) == 0
+        return L
+
+    def ho_exact_draw(self, m, seed, draw, chain):
+        x = np.zeros(m.M_lat)
+        assert self.lib.orc_ho_exact_draw(C.byref(m), seed, draw, chain, _dp(x)) == 0
+        return x
 
     def hmc_step(self, m, nt, dt, seed, draw, chain, x):
         x = _arr(x).copy()

@@ -209,7 +209,8 @@ def test_driver_qft_twolevel(drivers, tmp_path):
     dict(action="rotor", sampler="cluster", n_samples=100000),
     dict(action="rotor", method="multilevel", epsilon=2.0e-3),
     dict(action="harmonicoscillator", sampler="multilevel", n_samples=100000),
-], ids=["ho-hmc", "rotor-hier", "rotor-cluster", "rotor-mlmc", "ho-multilevelsampler"])
+    dict(action="harmonicoscillator", sampler="hierarchical", coarsesampler="exact", n_samples=100000),
+], ids=["ho-hmc", "rotor-hier", "rotor-cluster", "rotor-mlmc", "ho-multilevelsampler", "ho-hier-exact"])
 def test_driver_qm_matches_analytic(drivers, tmp_path, over):
     r = run(drivers["driver_qm"], QM.format(**dict(QM_DEFAULTS, **over)), tmp_path)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr

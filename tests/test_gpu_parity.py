@@ -376,6 +376,37 @@ def test_hierarchical_draw_equals_explicit_cascade(mp, ctx, beta):
     assert 0 < n_acc < 4 * B  # both branches of the cascade were exercised
 
 
+def test_ho_exact_sampler(mp, ctx, orc):
+    """HarmonicOscillatorAction::draw (Cholesky sampler): draw by draw against the oracle, and as the
+    coarse sampler of a hierarchy (sampler = 'exact' of hierarchicalsampler.hh)"""
+    o = po.ho(32, 4.0, 1.0, 1.0)
+    m = to_mp(mp, o)
+    B, chain0, draw = 5, 11, (1 << 33) + 4
+    got = host(ctx.exact_draw(m, B, chain0, draw))
+    want = np.array([orc.ho_exact_draw(o, SEED, draw, chain0 + b) for b in range(B)])
+    close(got, want, tol=1e-11, what="exact draw")
+    with pytest.raises(mp.MlmcpiError):
+        ctx.exact_draw(mp.rotor(32), 2)
+    # <x^2> from independent exact samples: no autocorrelation, analytic mean
+    want_x2 = float.fromhex(load("scalars")["analytic"]["ho_x2_32"])
+    for levels in (1, 2):
+        Bc = 4096
+        smp = mp.Sampler(ctx, mp.ho(32 * levels), Bc, kind=mp.SAMPLER_EXACT, n_levels=levels,
+                         renorm=mp.RENORM_PERTURBATIVE)
+        st = mp.Statistics(ctx, 10, Bc)
+        mm = mp.ho(32 * levels)
+        x = ctx.state(mm, Bc)
+        for k in range(40):
+            smp.draw(x)
+            if k >= 10:
+                st.record(ctx.qoi(mm, mp.QOI_X2, x))
+        out = mp.Statistics.finalize(st.pack(), 10)
+        ref = want_x2 if levels == 1 else mp._lib.lib.mlmcpi_ho_xsquared_analytical(1.0, 1.0, 4.0 / 64, 64, 0)
+        assert abs(out["average"] - ref) < 5 * out["error"], (levels, out, ref)
+        if levels == 1:
+            assert out["tau_int"] < 1.1
+
+
 # --------------------------------------------------- statistics accumulators
 
 

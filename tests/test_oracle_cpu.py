@@ -320,3 +320,42 @@ def test_draws_follow_reference_distributions(orc):
         R.lib.ref_dist_draw(dist, prm, xp, xm, 4711, n, want.ctypes.data_as(po.c_double_p))
         got = np.array([draw(orc.rng(99, po.STREAM_FILL2, 0, 0, k)) for k in range(n)])
         assert st.ks_2samp(got, want).pvalue > 1e-3, (dist, prm, xp, xm)
+
+
+def test_ho_exact_sampler_factor(orc):
+    """orc_ho_exact_factor restates HarmonicOscillatorAction::build_covariance
+    (qm/harmonicoscillatoraction.cc:38-56): L L^T P = 1 for the cyclic tridiagonal precision matrix P"""
+    for M, T, m0, mu2 in ((32, 4.0, 1.0, 1.0), (12, 3.0, 0.7, 2.5), (64, 4.0, 0.25, 0.3)):
+        m = po.ho(M, T, m0, mu2)
+        L = orc.ho_exact_factor(m)
+        a = T / M
+        P = np.zeros((M, M))
+        for i in range(M):
+            P[i, i] = a * m0 * mu2 + 2 * m0 / a
+            P[i, (i + 1) % M] += -m0 / a
+            P[i, (i - 1) % M] += -m0 / a
+        assert np.allclose(L, np.tril(L))
+        assert np.max(np.abs(L @ L.T @ P - np.eye(M))) < 1e-10
+
+
+@needs_ref
+def test_ho_exact_sampler_matches_reference_draws(orc):
+    """exact draws of the restatement (Philox) and of the reference's own
+    HarmonicOscillatorAction::draw (mt19937_64) follow the same Gaussian: second moments within
+    statistical error, single-site marginals by a two-sample KS test"""
+    st = pytest.importorskip("scipy.stats")
+    R = po.ref()
+    M, n = 32, 20000
+    a = R.action(po.HO, [M, 0], [4.0, 1.0, 1.0])
+    want = np.zeros((n, M))
+    R.lib.ref_ho_exact_draws(a.h, n, want.ctypes.data_as(po.c_double_p))
+    m = po.ho(M, 4.0, 1.0, 1.0)
+    got = np.array([orc.ho_exact_draw(m, 77, 3, k) for k in range(n)])
+    for site in (0, 5, 31):
+        assert st.ks_2samp(got[:, site], want[:, site]).pvalue > 1e-3
+    C_got, C_want = got.T @ got / n, want.T @ want / n
+    # entries of a sample covariance have standard error ~ sqrt((C_ii C_jj + C_ij^2) / n)
+    tol = 6.0 * np.sqrt(2.0 / n) * np.max(np.diag(C_want))
+    assert np.max(np.abs(C_got - C_want)) < 2 * tol
+    C_exact = orc.ho_exact_factor(m) @ orc.ho_exact_factor(m).T
+    assert np.max(np.abs(C_got - C_exact)) < tol
