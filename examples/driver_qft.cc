@@ -110,12 +110,12 @@ int main(int argc, char *argv[]) {
     std::shared_ptr<ConditionedFineActionFactory> conditioned_fine_action_factory =
         std::make_shared<ConditionedFineActionFactory>();
     std::shared_ptr<SamplerFactory> coarse_sampler_factory = construct_sampler_factory(
-        param_hierarchical.coarsesampler(), schwinger, false, nullptr, nullptr, nullptr, param_hmc, param_cluster,
+        param_hierarchical.coarsesampler(), schwinger, !schwinger, nullptr, nullptr, nullptr, param_hmc, param_cluster,
         param_heatbath, param_hierarchical, param_stats);
     if (!coarse_sampler_factory)
       return 1;
     auto factory_for = [&](int samplerid) {
-      return construct_sampler_factory(samplerid, schwinger, false, qoi_factory, coarse_sampler_factory,
+      return construct_sampler_factory(samplerid, schwinger, !schwinger, qoi_factory, coarse_sampler_factory,
                                        conditioned_fine_action_factory, param_hmc, param_cluster, param_heatbath,
                                        param_hierarchical, param_stats);
     };

@@ -78,7 +78,18 @@ typedef struct mlmcpi_model {
   double m0, mu2, lambda, x0; /* QM couplings                                   */
   double beta;        /* Schwinger coupling                                     */
   double gff_mu2;     /* GFF: a^2 m^2 (qft/gffaction.hh:174-181)                */
+  int gff_n_gibbs;    /* GFF: n_gibbs_smooth (qft/gffaction.hh:161-168).  0: the 5-point action;
+                         > 0: the Gibbs-smoothed coarse-level action S = phi^T Q_hat phi / 2 with
+                         the dense precision matrix of gffaction.cc:133-174 (<= MLMCPI_GFF_DENSE_MAX
+                         vertices)                                                              */
+  double gff_omega;   /* GFF: overrelaxation factor of the Gibbs smoother                      */
 } mlmcpi_model;
+
+/* Largest number of vertices for which the dense matrices of GFFAction::buildMatrices are formed
+ * (O(N^2) memory, O(N^3) setup on the host).  mlmcpi_coarse_model gives a coarse GFF level the
+ * reference's n_gibbs_smooth = 2, omega = 1 (gffaction.hh:201-208) up to this size and the
+ * un-smoothed 5-point action beyond it, where the reference itself cannot be set up. */
+#define MLMCPI_GFF_DENSE_MAX 1024
 
 typedef struct mlmcpi_ctx mlmcpi_ctx;
 
@@ -214,11 +225,15 @@ int mlmcpi_prolong_fill_eval(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const do
  * action/qm/rotoraction.hh:226-253); `update0` numbers the first update (Philox draw counter) */
 int mlmcpi_cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *rotor, double *d_x, int B,
                           uint32_t chain0, uint64_t update0, int n_updates);
-/* HarmonicOscillatorAction::draw (qm/harmonicoscillatoraction.cc:59-66): independent exact samples
- * x = L_cov y of the harmonic-oscillator path measure for every chain; L_cov (Cholesky factor of
- * the inverse of the cyclic tridiagonal precision matrix, build_covariance :38-56) is computed
- * on the host once per model and cached in the context */
-int mlmcpi_exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *ho, double *d_x, int B, uint32_t chain0,
+/* Exact samplers, independent samples for every chain:
+ *  - harmonic oscillator: HarmonicOscillatorAction::draw (qm/harmonicoscillatoraction.cc:59-66),
+ *    x = L_cov y with L_cov the Cholesky factor of the inverse of the cyclic tridiagonal precision
+ *    matrix (build_covariance :38-56);
+ *  - GFF: GFFAction::draw (qft/gffaction.cc:200-213), phi = U^{-1} psi with U the upper Cholesky
+ *    factor of the 5-point precision matrix, followed by gff_n_gibbs lexicographic sweeps of
+ *    global_heatbath_update_eff (:45-65); at most MLMCPI_GFF_DENSE_MAX vertices.
+ * The dense factors are computed on the host once per model and cached in the context. */
+int mlmcpi_exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0,
                       uint64_t draw);
 /* QuenchedSchwingerClusterSampler::draw lines 52-82: links from the rotor chain psi
  * (length Mt*Mx) followed by a random gauge transformation */

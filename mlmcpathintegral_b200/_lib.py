@@ -26,7 +26,7 @@ class Model(C.Structure):
                 ("rotated", C.c_int), ("coarsening", C.c_int), ("a_lat", C.c_double),
                 ("T_final", C.c_double), ("m0", C.c_double), ("mu2", C.c_double),
                 ("lambda_", C.c_double), ("x0", C.c_double), ("beta", C.c_double),
-                ("gff_mu2", C.c_double)]
+                ("gff_mu2", C.c_double), ("gff_n_gibbs", C.c_int), ("gff_omega", C.c_double)]
 
 
 class SamplerParams(C.Structure):

@@ -149,6 +149,10 @@ void mlmcpi_destroy(mlmcpi_ctx *ctx) {
       cudaFree(ctx->work[k]);
   for (auto &kv : ctx->ho_exact_factor)
     cudaFree(kv.second);
+  for (auto &kv : ctx->gff_dense)
+    for (double *d : kv.second)
+      if (d)
+        cudaFree(d);
   if (ctx->own_stream)
     cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -432,6 +436,11 @@ int mlmcpi_coarse_model(const mlmcpi_model *fine, int renorm, int level, int cty
     coarse->Mx_lat = Mxc;
     coarse->rotated = rotc;
     coarse->gff_mu2 = ac * ac * (fine->gff_mu2 / (af * af));
+    // GFFAction::coarse_action (gffaction.hh:201-208): n_gibbs_smooth = 2, omega = 1 -- where
+    // the dense matrices can be formed
+    const int Nc = rotc ? Mtc * Mxc / 2 : Mtc * Mxc;
+    coarse->gff_n_gibbs = (Nc <= MLMCPI_GFF_DENSE_MAX) ? 2 : 0;
+    coarse->gff_omega = 1.0;
     return 0;
   }
   }
@@ -763,8 +772,11 @@ int mlmcpi_cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *rotor, double *d_
 int mlmcpi_exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0, uint64_t draw) {
   if (!ctx || !m || !d_x || B <= 0)
     return MLMCPI_EINVAL;
+  if (m->model == MLMCPI_GFF)
+    return gff::exact_draw(ctx, m, d_x, B, chain0, draw);
   if (m->model != MLMCPI_HO)
-    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "the exact sampler is defined for the harmonic oscillator");
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED,
+                    "the exact sampler is defined for the harmonic oscillator and the GFF");
   return qm::exact_draw(ctx, m, d_x, B, chain0, draw);
 }
 int mlmcpi_schwinger_from_cluster(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_psi, double *d_x,
@@ -1108,6 +1120,11 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
       delete s;
       return ctx_fail(ctx, rc, "cannot construct the coarse action of a level");
     }
+    // The Gibbs-smoothed coarse GFF action describes what the EXACT sampler draws
+    // (gffaction.cc:200-213); with a heat-bath / HMC sampler, whose stationary distribution is
+    // the 5-point action, the hierarchy keeps the 5-point action on every level
+    if (c.model == MLMCPI_GFF && prm->kind != MLMCPI_SAMPLER_EXACT)
+      c.gff_n_gibbs = 0;
     s->model.push_back(c);
   }
   bool ok = true;
@@ -1615,6 +1632,8 @@ int mlmcpi_mlmc_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_m
     const int level = (fine->model == MLMCPI_GFF && fine->rotated ? 1 : 0) + l;
     rc = mlmcpi_coarse_model(&m->model[l], prm->sampler.renorm, level, prm->sampler.ctype,
                              m->model[l].T_final, &c);
+    if (c.model == MLMCPI_GFF && prm->sampler.kind != MLMCPI_SAMPLER_EXACT)
+      c.gff_n_gibbs = 0; // see mlmcpi_sampler_create
     m->model.push_back(c);
   }
   if (rc) {

@@ -46,6 +46,9 @@ struct mlmcpi_ctx {
   // exact sampler of the harmonic oscillator: transposed Cholesky factors of the covariance,
   // device [M][M], keyed by (M, a, m0, mu2)
   std::map<std::array<double, 4>, double *> ho_exact_factor;
+  // GFF dense matrices (gffaction.cc:133-174), device [N][N] each, keyed by
+  // (Mt, Mx, rotated, mu2, n_gibbs, omega): {Q_hat, transposed inverse of the Cholesky factor U}
+  std::map<std::array<double, 6>, std::array<double *, 2>> gff_dense;
 };
 
 int ctx_fail(mlmcpi_ctx *ctx, int code, const char *what, const char *detail = nullptr);
@@ -581,6 +584,9 @@ DECL_MODEL_API(gff)
 
 namespace qm {
 int cluster_update(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t, int);
+int exact_draw(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);
+}
+namespace gff {
 int exact_draw(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);
 }
 namespace schwinger {

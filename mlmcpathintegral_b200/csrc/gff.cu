@@ -6,12 +6,17 @@
 // indices are recomputed from (i,j) in registers instead of the reference's
 // vector<vector<unsigned>> gather lists.
 //
-// Scope: the n_gibbs_smooth == 0 branch of GFFAction (the fine-level action).  The
-// reference's coarse levels use a dense N x N precision matrix (qft/gffaction.cc:25-28,
-// 133-174), which cannot be formed at the named 256^2 size; that
-// dense path is listed under "next"  and is not built here.
+// The sweeps, force, fill-in and reductions implement the n_gibbs_smooth == 0 branch of GFFAction
+// (the 5-point action).  The reference's coarse levels carry a dense N x N precision matrix Q_hat
+// (qft/gffaction.cc:25-28, 133-174) and an exact Cholesky sampler (:200-213): these are built on
+// the host for levels of at most MLMCPI_GFF_DENSE_MAX vertices (second half of this file); at the
+// named 256^2 size neither the reference nor this library can form them.
 //
 // Reference citations relative to /root/reference/src.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -302,6 +307,269 @@ int trajectory(mlmcpi_ctx *ctx, const GF &g, int nt, double dt, const double *x_
 
 } // namespace
 
+
+// ===================================================================== dense coarse levels
+// GFFAction::buildMatrices, qft/gffaction.cc:133-174, on the host with plain dense loops
+// (N <= MLMCPI_GFF_DENSE_MAX).  Row-major std::vector<double> matrices.
+namespace {
+typedef std::vector<double> Mat;
+
+Mat mat_mul(const Mat &A, const Mat &B, int N, bool transpose_b = false) {
+  Mat C((size_t)N * N, 0.0);
+  if (transpose_b) {
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < N; ++k)
+          s += A[(size_t)i * N + k] * B[(size_t)j * N + k];
+        C[(size_t)i * N + j] = s;
+      }
+  } else {
+    for (int i = 0; i < N; ++i)
+      for (int k = 0; k < N; ++k) {
+        const double a = A[(size_t)i * N + k];
+        if (a == 0.0)
+          continue;
+        for (int j = 0; j < N; ++j)
+          C[(size_t)i * N + j] += a * B[(size_t)k * N + j];
+      }
+  }
+  return C;
+}
+
+// lower Cholesky factor of a symmetric positive definite matrix; false if it is not
+bool cholesky_lower(const Mat &A, int N, Mat &L) {
+  L.assign((size_t)N * N, 0.0);
+  for (int j = 0; j < N; ++j) {
+    double s = A[(size_t)j * N + j];
+    for (int k = 0; k < j; ++k)
+      s -= L[(size_t)j * N + k] * L[(size_t)j * N + k];
+    if (!(s > 0.0))
+      return false;
+    const double ljj = std::sqrt(s);
+    L[(size_t)j * N + j] = ljj;
+    for (int i = j + 1; i < N; ++i) {
+      double t = A[(size_t)i * N + j];
+      for (int k = 0; k < j; ++k)
+        t -= L[(size_t)i * N + k] * L[(size_t)j * N + k];
+      L[(size_t)i * N + j] = t / ljj;
+    }
+  }
+  return true;
+}
+
+// inverse of a lower triangular matrix
+Mat lower_inverse(const Mat &L, int N) {
+  Mat X((size_t)N * N, 0.0);
+  for (int c = 0; c < N; ++c) {
+    X[(size_t)c * N + c] = 1.0 / L[(size_t)c * N + c];
+    for (int i = c + 1; i < N; ++i) {
+      double s = 0.0;
+      for (int k = c; k < i; ++k)
+        s += L[(size_t)i * N + k] * X[(size_t)k * N + c];
+      X[(size_t)i * N + c] = -s / L[(size_t)i * N + i];
+    }
+  }
+  return X;
+}
+
+bool spd_inverse(const Mat &A, int N, Mat &Ainv) {
+  Mat L;
+  if (!cholesky_lower(A, N, L))
+    return false;
+  const Mat Li = lower_inverse(L, N); // A^{-1} = L^{-T} L^{-1}
+  Ainv.assign((size_t)N * N, 0.0);
+  for (int k = 0; k < N; ++k)
+    for (int i = 0; i <= k; ++i) {
+      const double a = Li[(size_t)k * N + i];
+      if (a == 0.0)
+        continue;
+      for (int j = 0; j <= k; ++j)
+        Ainv[(size_t)i * N + j] += a * Li[(size_t)k * N + j];
+    }
+  return true;
+}
+
+// GFFAction::buildPrecisionMatrix, gffaction.cc:177-197
+Mat precision_matrix(const GF &g, const std::vector<double> &stencil) {
+  Mat Q((size_t)g.N * g.N, 0.0);
+  uint32_t nb[8];
+  for (int ell = 0; ell < g.N; ++ell) {
+    mlmcpi_neighbours(g.Mt, g.Mx, g.rotated, (uint32_t)ell, nb);
+    Q[(size_t)ell * g.N + ell] += stencil[0];
+    for (size_t j = 0; j + 1 < stencil.size(); ++j)
+      for (int k = 0; k < 4; ++k)
+        Q[(size_t)ell * g.N + nb[4 * j + k]] += stencil[j + 1];
+  }
+  return Q;
+}
+
+// Q_hat (only when n_gibbs > 0) and the transposed inverse of U = L^T, Q = L L^T
+bool build_dense(const GF &g, int n_gibbs, double omega, Mat &Qhat, Mat &UinvT) {
+  const int N = g.N;
+  const Mat Q = precision_matrix(g, {4. + g.mu2, -1.});
+  Mat L;
+  if (!cholesky_lower(Q, N, L))
+    return false;
+  // U^{-1} = (L^T)^{-1} = (L^{-1})^T, so the transposed inverse of U is L^{-1} itself
+  UinvT = lower_inverse(L, N);
+  Qhat.clear();
+  if (n_gibbs <= 0)
+    return true;
+  const double d = 4. + 0.5 * g.mu2;
+  const Mat Qe = precision_matrix(g, {d - 4. / d, -2. / d, -1. / d});
+  Mat Sigma, Sigma_e;
+  if (!spd_inverse(Q, N, Sigma) || !spd_inverse(Qe, N, Sigma_e))
+    return false;
+  // M = lower triangle of Q_eff (+ (1/omega - 1) diag);  G1 = 1 - M^{-1} Q_eff
+  Mat M((size_t)N * N, 0.0);
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j <= i; ++j)
+      M[(size_t)i * N + j] = Qe[(size_t)i * N + j];
+  if (std::fabs(omega - 1.0) > 1.E-14)
+    for (int i = 0; i < N; ++i)
+      M[(size_t)i * N + i] += (1. / omega - 1.) * Qe[(size_t)i * N + i];
+  Mat G1 = mat_mul(lower_inverse(M, N), Qe, N);
+  for (size_t k = 0; k < G1.size(); ++k)
+    G1[k] = -G1[k];
+  for (int i = 0; i < N; ++i)
+    G1[(size_t)i * N + i] += 1.0;
+  Mat G = G1;
+  for (int k = 1; k < n_gibbs; ++k)
+    G = mat_mul(G, G1, N);
+  Mat D(Sigma);
+  for (size_t k = 0; k < D.size(); ++k)
+    D[k] -= Sigma_e[k];
+  Mat Sh = mat_mul(mat_mul(G, D, N), G, N, true); // G (Sigma - Sigma_eff) G^T
+  for (size_t k = 0; k < Sh.size(); ++k)
+    Sh[k] += Sigma_e[k];
+  for (int i = 0; i < N; ++i) // symmetrise the rounding before the Cholesky inverse
+    for (int j = 0; j < i; ++j) {
+      const double v = 0.5 * (Sh[(size_t)i * N + j] + Sh[(size_t)j * N + i]);
+      Sh[(size_t)i * N + j] = Sh[(size_t)j * N + i] = v;
+    }
+  return spd_inverse(Sh, N, Qhat);
+}
+
+// S = phi^T Q_hat phi / 2 (gffaction.cc:25-28): one block per chain, phi staged in shared
+// memory, thread i forms row i of Q_hat phi (Q_hat is symmetric: column reads are coalesced)
+__global__ void dense_action_kernel(int N, const double *__restrict__ Qhat, const double *x, double *S) {
+  extern __shared__ double phi[];
+  const int chain = blockIdx.x;
+  for (int k = threadIdx.x; k < N; k += blockDim.x)
+    phi[k] = x[(size_t)chain * N + k];
+  __syncthreads();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double s = 0.0;
+    for (int j = 0; j < N; ++j)
+      s += Qhat[(size_t)j * N + i] * phi[j];
+    acc += phi[i] * s;
+  }
+  const double v = block_sum(acc);
+  if (threadIdx.x == 0)
+    S[chain] = 0.5 * v;
+}
+
+// phi = U^{-1} psi (gffaction.cc:200-208), psi i.i.d. N(0,1): phi_i = sum_{j >= i} Uinv[i][j] psi_j
+__global__ void dense_draw_kernel(int N, const double *__restrict__ UinvT, double *x, uint32_t chain0,
+                                  uint64_t seed, uint64_t draw) {
+  extern __shared__ double psi[];
+  const int chain = blockIdx.x;
+  for (int k = threadIdx.x; 2 * k < N; k += blockDim.x) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_EXACT, draw, chain0 + chain, k);
+    double z0, z1;
+    rng_normal2(r, z0, z1);
+    psi[2 * k] = z0;
+    if (2 * k + 1 < N)
+      psi[2 * k + 1] = z1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double s = 0.0;
+    for (int j = i; j < N; ++j)
+      s += UinvT[(size_t)j * N + i] * psi[j];
+    x[(size_t)chain * N + i] = s;
+  }
+}
+
+// GFFAction::global_heatbath_update_eff, gffaction.cc:45-65: a lexicographic (sequential) Gibbs
+// sweep with the 9-point effective action -- one thread walks one chain
+__global__ void gibbs_eff_kernel(GF g, double omega, int sweep, double *x_all, int B, uint32_t chain0,
+                                 uint64_t seed, uint64_t draw) {
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= B)
+    return;
+  double *x = x_all + (size_t)chain * g.N;
+  const double d = 4. + 0.5 * g.mu2;
+  const double diag_eff = d - 4. / d;
+  const double sigma_eff = 1. / sqrt(diag_eff);
+  const double kappa = omega / d;
+  const double gamma = sqrt(omega * (2. - omega));
+  for (int ell = 0; ell < g.N; ++ell) {
+    int i, j;
+    v_lin2cart(g.Mt, g.Mx, g.rotated, ell, i, j);
+    double Delta = (1. - omega) * diag_eff * x[ell];
+    double nn = 0.0, nnn = 0.0;
+    if (g.rotated) { // neighbour order of lattice/lattice2d.cc:138-155
+      nn += x[v_cart2lin(g.Mt, g.Mx, 1, i + 1, j + 1)];
+      nn += x[v_cart2lin(g.Mt, g.Mx, 1, i + 1, j - 1)];
+      nn += x[v_cart2lin(g.Mt, g.Mx, 1, i - 1, j + 1)];
+      nn += x[v_cart2lin(g.Mt, g.Mx, 1, i - 1, j - 1)];
+      nnn += x[v_cart2lin(g.Mt, g.Mx, 1, i + 2, j)];
+      nnn += x[v_cart2lin(g.Mt, g.Mx, 1, i - 2, j)];
+      nnn += x[v_cart2lin(g.Mt, g.Mx, 1, i, j + 2)];
+      nnn += x[v_cart2lin(g.Mt, g.Mx, 1, i, j - 2)];
+    } else {
+      nn += x[v_cart2lin(g.Mt, g.Mx, 0, i + 1, j)];
+      nn += x[v_cart2lin(g.Mt, g.Mx, 0, i - 1, j)];
+      nn += x[v_cart2lin(g.Mt, g.Mx, 0, i, j + 1)];
+      nn += x[v_cart2lin(g.Mt, g.Mx, 0, i, j - 1)];
+      nnn += x[v_cart2lin(g.Mt, g.Mx, 0, i + 1, j + 1)];
+      nnn += x[v_cart2lin(g.Mt, g.Mx, 0, i + 1, j - 1)];
+      nnn += x[v_cart2lin(g.Mt, g.Mx, 0, i - 1, j + 1)];
+      nnn += x[v_cart2lin(g.Mt, g.Mx, 0, i - 1, j - 1)];
+    }
+    Delta += 2. * kappa * nn + kappa * nnn;
+    Rng r = rng_init(seed, MLMCPI_STREAM_EXACT, draw, chain0 + chain, (uint32_t)((sweep + 1) * g.N + ell));
+    double z0, z1;
+    rng_normal2(r, z0, z1);
+    x[ell] = sigma_eff * (gamma * z0 + sigma_eff * Delta);
+  }
+}
+
+int dense_get(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double **Qhat, const double **UinvT) {
+  const GF g = make_gf(m);
+  if (g.N > MLMCPI_GFF_DENSE_MAX)
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED,
+                    "GFF dense matrices: more than MLMCPI_GFF_DENSE_MAX vertices on this level");
+  const std::array<double, 6> key = {(double)g.Mt,          (double)g.Mx, (double)g.rotated, g.mu2,
+                                     (double)m->gff_n_gibbs, m->gff_omega};
+  auto it = ctx->gff_dense.find(key);
+  if (it == ctx->gff_dense.end()) {
+    Mat Qh, Ut;
+    if (!build_dense(g, m->gff_n_gibbs, m->gff_n_gibbs > 0 ? m->gff_omega : 1.0, Qh, Ut))
+      return ctx_fail(ctx, MLMCPI_EINVAL, "GFF dense matrices: matrix not positive definite");
+    std::array<double *, 2> d = {nullptr, nullptr};
+    const size_t bytes = (size_t)g.N * g.N * sizeof(double);
+    if (!Qh.empty()) {
+      MLMCPI_CUDA(cudaMalloc((void **)&d[0], bytes));
+      MLMCPI_CUDA(cudaMemcpyAsync(d[0], Qh.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    MLMCPI_CUDA(cudaMalloc((void **)&d[1], bytes));
+    MLMCPI_CUDA(cudaMemcpyAsync(d[1], Ut.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
+    it = ctx->gff_dense.emplace(key, d).first;
+  }
+  if (Qhat)
+    *Qhat = it->second[0];
+  if (UinvT)
+    *UinvT = it->second[1];
+  return 0;
+}
+
+} // namespace
+
 namespace gff {
 
 int init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,
@@ -315,7 +583,35 @@ int init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_
 
 int action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, double *S) {
   GF g = make_gf(m);
+  if (m->gff_n_gibbs > 0) { // coarse level: S = phi^T Q_hat phi / 2, gffaction.cc:25-28
+    const double *Qhat = nullptr;
+    int rc = dense_get(ctx, m, &Qhat, nullptr);
+    if (rc)
+      return rc;
+    const int threads = std::min(512, ((g.N + 31) / 32) * 32);
+    dense_action_kernel<<<B, threads, (size_t)g.N * sizeof(double), ctx->stream>>>(g.N, Qhat, x, S);
+    MLMCPI_LAUNCHED("gff::dense_action");
+    return 0;
+  }
   return site_reduce<1>(ctx, "gff::action", ActionF{g, x}, g.N, B, EPI_SCALE, 0.5, 0.0, S, nullptr);
+}
+
+// GFFAction::draw, qft/gffaction.cc:200-213
+int exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0, uint64_t draw) {
+  GF g = make_gf(m);
+  const double *UinvT = nullptr;
+  int rc = dense_get(ctx, m, nullptr, &UinvT);
+  if (rc)
+    return rc;
+  const int threads = std::min(512, ((g.N + 31) / 32) * 32);
+  dense_draw_kernel<<<B, threads, (size_t)(g.N + 1) * sizeof(double), ctx->stream>>>(g.N, UinvT, x, chain0,
+                                                                                    ctx->seed, draw);
+  MLMCPI_LAUNCHED("gff::dense_draw");
+  for (int k = 0; k < m->gff_n_gibbs; ++k) {
+    gibbs_eff_kernel<<<cdiv(B, 32), 32, 0, ctx->stream>>>(g, m->gff_omega, k, x, B, chain0, ctx->seed, draw);
+    MLMCPI_LAUNCHED("gff::gibbs_eff");
+  }
+  return 0;
 }
 
 int force(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, double *f, int B) {

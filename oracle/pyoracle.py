@@ -321,6 +321,50 @@ class Oracle:
 #  the reference's own translation units
 # --------------------------------------------------------------------------- #
 
+def gff_dense_matrices(orc, m, n_gibbs=2, omega=1.0):
+    """numpy restatement of GFFAction::buildMatrices (qft/gffaction.cc:133-174) for the level
+    described by the GFF model `m`: returns dict(Q=5-point precision, Q_eff=9-point effective
+    precision, G=Gibbs iteration matrix ^ n_gibbs, Sigma_hat, Q_hat, U=upper Cholesky factor of Q).
+    The coarse-level action of the reference is S = phi^T Q_hat phi / 2 (gffaction.cc:25-28) and its
+    exact sampler draws phi = U^{-1} psi followed by n_gibbs lexicographic sweeps (gffaction.cc:200-213)."""
+    try:  # single-threaded BLAS: a BLAS thread pool can deadlock next to torch's OpenMP runtime
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            return _gff_dense_matrices(orc, m, n_gibbs, omega)
+    except ImportError:
+        return _gff_dense_matrices(orc, m, n_gibbs, omega)
+
+
+def _gff_dense_matrices(orc, m, n_gibbs, omega):
+    N = orc.sample_size(m)
+    mu2 = m.gff_mu2
+    nb = np.zeros((N, 8), dtype=np.uint32)
+    for ell in range(N):
+        orc.lib.orc_neighbours(m.Mt_lat, m.Mx_lat, m.rotated, ell, nb[ell].ctypes.data_as(c_u32_p))
+
+    def precision(stencil):  # GFFAction::buildPrecisionMatrix, gffaction.cc:177-197
+        Q = np.zeros((N, N))
+        for ell in range(N):
+            Q[ell, ell] += stencil[0]
+            for j in range(len(stencil) - 1):
+                for k in range(4):
+                    Q[ell, nb[ell, 4 * j + k]] += stencil[j + 1]
+        return Q
+
+    Q = precision([4.0 + mu2, -1.0])
+    d = 4.0 + 0.5 * mu2
+    Q_eff = precision([d - 4.0 / d, -2.0 / d, -1.0 / d])
+    Sigma, Sigma_eff = np.linalg.inv(Q), np.linalg.inv(Q_eff)
+    M = np.tril(Q_eff)
+    if abs(omega - 1.0) > 1e-14:
+        M = M + np.diag((1.0 / omega - 1.0) * np.diag(Q_eff))
+    G1 = np.eye(N) - np.linalg.solve(M, Q_eff)
+    G = np.linalg.matrix_power(G1, n_gibbs) if n_gibbs > 0 else np.eye(N)
+    Sigma_hat = Sigma_eff + G @ (Sigma - Sigma_eff) @ G.T
+    return dict(Q=Q, Q_eff=Q_eff, G=G, Sigma=Sigma, Sigma_hat=Sigma_hat, Q_hat=np.linalg.inv(Sigma_hat),
+                U=np.linalg.cholesky(Q).T, nb=nb)
+
+
 def have_ref():
     return os.path.exists(REF_SO)
 

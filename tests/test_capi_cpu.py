@@ -180,3 +180,12 @@ def test_analytic_results_match_reference(mp):
     sh = load("scalars")["Sigma_hat"]
     for (xi, p), y in zip(sh["args"], sh["y"]):
         assert L.mlmcpi_sigma_hat(xi, p) == float.fromhex(y)
+
+
+def test_gff_coarse_model_carries_the_gibbs_smoothed_action(mp):
+    """GFFAction::coarse_action (gffaction.hh:201-208): n_gibbs_smooth = 2, omega = 1 wherever the
+    dense matrices can be formed, the 5-point action beyond"""
+    mc = mp.coarse_model(mp.gff(32, 32, 10.0), ctype=mp.COARSEN_ROTATE)
+    assert (mc.gff_n_gibbs, mc.gff_omega, mp.sample_size(mc)) == (2, 1.0, 512)
+    big = mp.coarse_model(mp.gff(256, 256, 10.0), ctype=mp.COARSEN_ROTATE)
+    assert big.gff_n_gibbs == 0 and mp.sample_size(big) == 32768

@@ -184,7 +184,9 @@ def test_drivers_parse_reference_format_and_need_a_gpu(drivers, tmp_path):
     dict(sampler="hierarchical", coarsesampler="heatbath", renorm="nonperturbative", beta=6.0),
     dict(action="gff", coarsening="rotate", sampler="heatbath", n_samples=60000),
     dict(method="multilevel", n_max_level=2, epsilon=0.05),
-], ids=["hier-hmc", "heatbath", "cluster", "hier-hb-nonpert", "gff", "mlmc"])
+    dict(action="gff", coarsening="rotate", sampler="hierarchical", coarsesampler="exact", n_max_level=2,
+         n_samples=60000),
+], ids=["hier-hmc", "heatbath", "cluster", "hier-hb-nonpert", "gff", "mlmc", "gff-hier-exact"])
 def test_driver_qft_matches_analytic(drivers, tmp_path, over):
     r = run(drivers["driver_qft"], QFT.format(**dict(QFT_DEFAULTS, **over)), tmp_path)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr

@@ -158,6 +158,10 @@ def test_gff_golden(mp, ctx, c):
     xc = ctx.state(mc, 1)
     ctx.restrict(m, xd, xc)
     assert np.array_equal(host(xc)[0], unhex(c["restrict"]))
+    # the coarse action of the reference: Gibbs-smoothed dense precision matrix (gffaction.cc:25-28,
+    # 133-174; coarse_action() sets n_gibbs_smooth = 2, omega = 1)
+    assert mc.gff_n_gibbs == 2 and mc.gff_omega == 1.0
+    close(host(ctx.action(mc, xc))[0], scalar(c["coarse_S_gibbs"]), tol=1e-9, what="coarse S (Q_hat)")
     y = xd.clone()
     ctx.prolong(m, dev(ctx, noncompact(mp.sample_size(mc), 0.3)), y)
     assert np.array_equal(host(y)[0], unhex(c["prolong"]))
@@ -405,6 +409,51 @@ def test_ho_exact_sampler(mp, ctx, orc):
         assert abs(out["average"] - ref) < 5 * out["error"], (levels, out, ref)
         if levels == 1:
             assert out["tau_int"] < 1.1
+
+
+def test_gff_dense_coarse_level(mp, ctx, orc):
+    """GFF coarse level as the reference builds it (dense Q_hat, exact Cholesky sampler + 2 Gibbs
+    sweeps): action against the numpy restatement of buildMatrices, second moments of the exact
+    draws against Sigma_hat, and a hierarchical sampler with sampler = 'exact' on the coarsest
+    level against gff_phi_squared_analytical (with the un-smoothed 5-point coarse action the
+    two-level acceptance collapses beyond 16 x 16)"""
+    m = mp.gff(16, 16, 3.0)
+    mc = mp.coarse_model(m, ctype=mp.COARSEN_ROTATE)
+    o = po.gff(16, 16, 3.0)
+    oc = orc.coarse_model(o, 0, 0, po.ROTATE)
+    mats = po.gff_dense_matrices(orc, oc, 2, 1.0)
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(4, mp.sample_size(mc)))
+    want = 0.5 * np.einsum("bi,ij,bj->b", x, mats["Q_hat"], x)
+    close(host(ctx.action(mc, dev(ctx, x))), want, tol=1e-9, what="dense action")
+    B = 8192
+    d = host(ctx.exact_draw(mc, B, 0, 1))
+    C = d.T @ d / B
+    tol = 6.0 * np.sqrt(2.0 / B) * np.max(np.diag(mats["Sigma_hat"]))
+    assert np.max(np.abs(C - mats["Sigma_hat"])) < tol
+    # fine level: plain Cholesky sample of the 5-point action
+    d = host(ctx.exact_draw(m, B, 0, 2))
+    Sigma = np.linalg.inv(po.gff_dense_matrices(orc, o, 0, 1.0)["Q"])
+    assert np.max(np.abs(d.T @ d / B - Sigma)) < 6.0 * np.sqrt(2.0 / B) * np.max(np.diag(Sigma))
+    # (two levels: with three or more the intermediate steps pair the dense Q_hat action of a level
+    # with the 5-point conditional fill-in, gffconditionedfineaction.cc:7-25, and accept rarely)
+    for M, levels in ((16, 2), (32, 2)):
+        mm = mp.gff(M, M, 10.0)
+        Bc = 1024
+        smp = mp.Sampler(ctx, mm, Bc, kind=mp.SAMPLER_EXACT, n_levels=levels, ctype=mp.COARSEN_ROTATE)
+        assert smp.level_model(1).gff_n_gibbs == 2
+        st = mp.Statistics(ctx, 20, Bc)
+        xx = ctx.init_state(mm, Bc, 0, 0)
+        smp.set_state(xx)
+        for k in range(120):
+            smp.draw(xx)
+            if k >= 40:
+                st.record(ctx.qoi(mm, mp.QOI_PHI2, xx))
+        out = mp.Statistics.finalize(st.pack(), 20)
+        ref = mp._lib.lib.mlmcpi_gff_phi_squared_analytical(10.0, M, M)
+        p = smp.p_accept()
+        assert p[0] > 0.9, p  # (0.09 at 16^2 and 0 at 32^2 with the 5-point coarse action)
+        assert abs(out["average"] - ref) < 5 * out["error"], (M, out, ref, p)
 
 
 # --------------------------------------------------- statistics accumulators

@@ -359,3 +359,30 @@ def test_ho_exact_sampler_matches_reference_draws(orc):
     assert np.max(np.abs(C_got - C_want)) < 2 * tol
     C_exact = orc.ho_exact_factor(m) @ orc.ho_exact_factor(m).T
     assert np.max(np.abs(C_got - C_exact)) < tol
+
+
+@needs_ref
+@pytest.mark.parametrize("M,ctype", [(8, po.ROTATE), (16, po.ROTATE), (8, po.BOTH)])
+def test_gff_dense_coarse_action_matches_reference(orc, M, ctype):
+    """numpy restatement of GFFAction::buildMatrices against the reference's own coarse GFF action
+    (n_gibbs_smooth = 2, omega = 1: gffaction.hh:201-208), S = phi^T Q_hat phi / 2, and its exact
+    sampler (second moments of gffaction.cc:200-213 draws = Sigma_hat)"""
+    R = po.ref()
+    fine = R.action(po.GFF, [M, M, ctype], [3.0])
+    coarse = fine.coarse()
+    m = po.gff(M, M, 3.0, ctype)
+    mc = orc.coarse_model(m, 0, 0, ctype)
+    assert abs(coarse.param(0) - mc.gff_mu2) < 1e-15
+    mats = po.gff_dense_matrices(orc, mc, 2, 1.0)
+    rng = np.random.default_rng(M)
+    for _ in range(3):
+        x = rng.normal(size=coarse.n)
+        want = coarse.evaluate(x)
+        got = 0.5 * x @ mats["Q_hat"] @ x
+        assert abs(got - want) <= 1e-9 * abs(want), (got, want)
+    n = 20000
+    draws = np.zeros((n, coarse.n))
+    R.lib.ref_gff_exact_draws(coarse.h, n, draws.ctypes.data_as(po.c_double_p))
+    C = draws.T @ draws / n
+    tol = 6.0 * np.sqrt(2.0 / n) * np.max(np.diag(mats["Sigma_hat"]))
+    assert np.max(np.abs(C - mats["Sigma_hat"])) < tol
