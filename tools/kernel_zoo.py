@@ -43,6 +43,7 @@ def run():
             ctx.prolong(m, xc, y)
             ctx.fill(m, y, 0, 2)
             ctx.prolong_fill(m, xc, y, 0, 3)
+            ctx.prolong_fill_eval(m, xc, y, 0, 5)
             ctx.cond_action(m, y)
             Sf, Sc = ctx.action(m, x), ctx.cond_action(m, x)
             ctx.twolevel_step(m, mc, xc, x, Sf, Sc, 0, 4)
@@ -66,6 +67,11 @@ def run():
         m = mp.ho(32)
         x = ctx.state(m, 65536)
         ctx.hmc_step(m, 100, 0.1, x, 0, 1)
+        ctx.exact_draw(m, 65536, 0, 2)
+        # --- GFF 32^2: the dense coarse level (512 vertices), 512 chains
+        mc = mp.coarse_model(mp.gff(32, 32, 10.0), ctype=mp.COARSEN_ROTATE)
+        x = ctx.exact_draw(mc, 512, 0, 1)
+        ctx.action(mc, x)
         # --- GFF 256^2 (C3), 64 chains
         m = mp.gff(256, 256, 10.0)
         B = 64
