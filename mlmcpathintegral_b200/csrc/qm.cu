@@ -279,6 +279,126 @@ __global__ void hmc_step_kernel(QM q, int nt, double dt, double *x, int B, uint3
   }
 }
 
+// Register-resident variant for M = 32 * SPL: lane l owns the sites l + 32 r (r < SPL) with x and p
+// in registers for the whole trajectory; neighbours arrive by warp shuffles (site s - 1 is lane
+// l - 1's register r, or lane 31's register r - 1 for lane 0), so a leapfrog step needs no shared
+// memory and no synchronisation.  For the rotor every bond sine sin(x_s - x_{s-1}) is computed once
+// and shared with the left neighbour (sin(x - x_p) = -sin(x_p - x)): one sine per site-step instead
+// of two.  Same arithmetic per site as the generic kernel.
+template <int SPL> struct RegPath {
+  double x[SPL], p[SPL];
+};
+template <int SPL>
+__device__ __forceinline__ void left_neighbours(const double (&v)[SPL], int lane, double (&out)[SPL]) {
+  double t[SPL];
+#pragma unroll
+  for (int r = 0; r < SPL; ++r)
+    t[r] = __shfl_sync(0xffffffffu, v[r], (lane + 31) & 31);
+#pragma unroll
+  for (int r = 0; r < SPL; ++r)
+    out[r] = (lane == 0) ? t[(r + SPL - 1) % SPL] : t[r];
+}
+template <int SPL>
+__device__ __forceinline__ void right_neighbours(const double (&v)[SPL], int lane, double (&out)[SPL]) {
+  double t[SPL];
+#pragma unroll
+  for (int r = 0; r < SPL; ++r)
+    t[r] = __shfl_sync(0xffffffffu, v[r], (lane + 1) & 31);
+#pragma unroll
+  for (int r = 0; r < SPL; ++r)
+    out[r] = (lane == 31) ? t[(r + 1) % SPL] : t[r];
+}
+
+template <int MODEL, int SPL>
+__device__ __forceinline__ void path_energies(const QM &q, const RegPath<SPL> &s, int lane, double &T, double &S) {
+  double xm[SPL];
+  left_neighbours<SPL>(s.x, lane, xm);
+  double t = 0.0, a = 0.0;
+#pragma unroll
+  for (int r = 0; r < SPL; ++r) {
+    t += s.p[r] * s.p[r];
+    a += site_action<MODEL>(q, xm[r], s.x[r]);
+  }
+  T = 0.5 * warp_sum(t);
+  S = action_prefactor<MODEL>(q) * warp_sum(a);
+}
+
+template <int MODEL, int SPL>
+__global__ void __launch_bounds__(THREADS)
+    hmc_step_reg_kernel(QM q, int nt, double dt, double *x, int B, uint32_t chain0, uint64_t seed,
+                        uint64_t draw, int32_t *accept_out, double *diag) {
+  WARP_SETUP
+  double *xc = x + (size_t)c_safe * q.M;
+  const uint32_t gchain = chain0 + (uint32_t)c_safe;
+  RegPath<SPL> s;
+#pragma unroll
+  for (int r = 0; r < SPL; ++r) {
+    const int site = lane + 32 * r;
+    s.x[r] = xc[site];
+    Rng rg = rng_init(seed, MLMCPI_STREAM_HMC_MOMENTUM, draw, gchain, site >> 1);
+    double z0, z1;
+    rng_normal2(rg, z0, z1);
+    s.p[r] = (site & 1) ? z1 : z0;
+  }
+  double T_cur, S_cur;
+  path_energies<MODEL, SPL>(q, s, lane, T_cur, S_cur);
+  const double pref = q.m0 / q.a;
+  for (int k = 0; k <= nt; ++k) { // sampler/hmcsampler.cc:31-46
+    const double dt_p = (k == 0 || k == nt) ? 0.5 * dt : dt;
+    const double dt_x = (k == nt) ? 0.0 : dt;
+    double xm[SPL];
+    left_neighbours<SPL>(s.x, lane, xm);
+    if (MODEL == MLMCPI_ROTOR) {
+      double b[SPL], bn[SPL];
+#pragma unroll
+      for (int r = 0; r < SPL; ++r)
+        b[r] = sin(s.x[r] - xm[r]);
+      right_neighbours<SPL>(b, lane, bn);
+#pragma unroll
+      for (int r = 0; r < SPL; ++r)
+        s.p[r] -= dt_p * (pref * (b[r] - bn[r]));
+    } else {
+      double xp[SPL];
+      right_neighbours<SPL>(s.x, lane, xp);
+#pragma unroll
+      for (int r = 0; r < SPL; ++r)
+        s.p[r] -= dt_p * site_force<MODEL>(q, xm[r], s.x[r], xp[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < SPL; ++r)
+      s.x[r] += dt_x * s.p[r];
+  }
+  double T_trial, S_trial;
+  path_energies<MODEL, SPL>(q, s, lane, T_trial, S_trial);
+  const double deltaH = (S_trial - S_cur) + (T_trial - T_cur);
+  bool acc = deltaH < 0.0;
+  if (!acc) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_HMC_ACCEPT, draw, gchain, 0);
+    double u0, u1;
+    rng_uniform2(r, u0, u1);
+    acc = u0 < exp(-deltaH);
+  }
+  if (!active)
+    return;
+  if (acc) {
+#pragma unroll
+    for (int r = 0; r < SPL; ++r)
+      xc[lane + 32 * r] = s.x[r];
+  }
+  if (lane == 0) {
+    if (accept_out)
+      accept_out[chain] = acc ? 1 : 0;
+    if (diag) {
+      double *d = diag + 5 * chain;
+      d[0] = deltaH;
+      d[1] = S_cur;
+      d[2] = S_trial;
+      d[3] = T_cur;
+      d[4] = T_trial;
+    }
+  }
+}
+
 // --------------------------------------------------------------------- sweeps
 // rotor only (qm/rotoraction.cc:21-56); colours: even sites, then odd sites
 template <bool HEATBATH>
@@ -552,6 +672,25 @@ int hmc_momentum(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *p, int B, uint3
 int hmc_step(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *x, int B,
              uint32_t chain0, uint64_t draw, int32_t *accept, double *diag) {
   QM q = make_qm(m);
+  // register-resident trajectory when the path is 32 * {1, 2, 4, 8} sites long
+  const int spl = (q.M % 32 == 0) ? q.M / 32 : 0;
+  if (spl == 1 || spl == 2 || spl == 4 || spl == 8) {
+#define MLMCPI_REG_LAUNCH(SPL)                                                                     \
+  QM_DISPATCH(q.model, (hmc_step_reg_kernel<MODEL, SPL><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>( \
+                           q, nt, dt, x, B, chain0, ctx->seed, draw, accept, diag)))
+    if (spl == 1) {
+      MLMCPI_REG_LAUNCH(1);
+    } else if (spl == 2) {
+      MLMCPI_REG_LAUNCH(2);
+    } else if (spl == 4) {
+      MLMCPI_REG_LAUNCH(4);
+    } else {
+      MLMCPI_REG_LAUNCH(8);
+    }
+#undef MLMCPI_REG_LAUNCH
+    MLMCPI_LAUNCHED("qm::hmc_step_reg");
+    return 0;
+  }
   const size_t smem = traj_smem(q);
   QM_DISPATCH(q.model, {
     int rc = prepare_smem(ctx, hmc_step_kernel<MODEL>, smem);
