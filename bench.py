@@ -434,6 +434,13 @@ def gpu_main(a):
                     "samples": st["samples"]},
             "ess_per_s": st["samples"] / st["tau_int"] / (ms_max * 1e-3),
         })
+        if is_schwinger and a.beta > 64:
+            # honest labelling: see DESIGN.md section 6 ("ESS/s")
+            cfg["ess_note"] = ("cold start at beta/P = %.1e: every chain stays in the Q = 0 sector (neither the HMC "
+                               "nor the two-level steps change the topological charge at this coupling, in the "
+                               "reference as here), so chi_t ~ 1e-28 and ess_per_s is samples / tau_int / time of "
+                               "an essentially constant series; statistically meaningful chi_t runs are in "
+                               "tests/ (8^2 ... 32^2, beta <= 16, vs the analytic value)" % (a.beta / a.lattice ** 2))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
