@@ -552,6 +552,53 @@ def test_rowmarch_equals_generic_leapfrog(mp, ctx):
         close(host(pd), [w[1] for w in want], what=f"p {Mt}x{Mx}")
 
 
+def test_edge_shapes(mp, ctx, orc):
+    """smallest lattices, a single chain, ragged extents, widths beyond one thread block, the
+    1024 x 1024 lattice of BASELINE config 4, and 1-D paths on both sides of the register-resident
+    HMC kernel (M = 32 k) -- deterministic kernels against the oracle / against each other"""
+    rng = np.random.default_rng(11)
+    for Mt, Mx, B in [(2, 2, 1), (4, 2, 3), (2, 6, 2), (1056, 4, 1), (2048, 3, 1)]:
+        o = po.schwinger(Mt, Mx, 2.5)
+        m = to_mp(mp, o)
+        x, p = rng.uniform(-3, 3, (B, 2 * Mt * Mx)), rng.normal(size=(B, 2 * Mt * Mx))
+        xd, pd = dev(ctx, x), dev(ctx, p)
+        close(host(ctx.action(m, xd)), [orc.action(o, x[b]) for b in range(B)], what=f"S {Mt}x{Mx}")
+        close(host(ctx.force(m, xd)), [orc.force(o, x[b]) for b in range(B)], what=f"F {Mt}x{Mx}")
+        ctx.leapfrog(m, 3, 0.05, xd, pd)
+        want = [orc.leapfrog(o, 3, 0.05, x[b], p[b]) for b in range(B)]
+        close(host(xd), [w[0] for w in want], what=f"x {Mt}x{Mx}")
+        close(host(pd), [w[1] for w in want], what=f"p {Mt}x{Mx}")
+        got, Q = ctx.qoi(m, mp.QOI_SCHWINGER_CHI, dev(ctx, x), with_charge=True)
+        assert list(host(Q)) == [orc.qoi(o, po.QOI_SCHWINGER_CHI, x[b])[1] for b in range(B)]
+    # 1024 x 1024: the three leapfrog kernels (two-step TMA pipeline, one-step pipeline, generic)
+    m = mp.schwinger(1024, 1024, 4.0)
+    x0 = ctx.init_state(m, 2, 0, 1)
+    p0 = ctx.hmc_momentum(m, 2, 0, 1)
+    res = []
+    for variant, fuse in ((0, 1), (0, 0), (2, 0)):
+        ctx.set_option(mp._lib.OPT_LEAPFROG_VARIANT, variant)
+        ctx.set_option(mp._lib.OPT_LEAPFROG_FUSE, fuse)
+        x, p = x0.clone(), p0.clone()
+        ctx.leapfrog(m, 5, 0.02, x, p)
+        res.append((host(x).copy(), host(p).copy()))
+    ctx.set_option(mp._lib.OPT_LEAPFROG_VARIANT, 0)
+    ctx.set_option(mp._lib.OPT_LEAPFROG_FUSE, 1)
+    for x, p in res[1:]:
+        assert np.array_equal(x, res[0][0]) and np.array_equal(p, res[0][1])
+    # 1-D paths: M = 32 k uses the register-resident HMC kernel, M = 33 / 40 the generic one
+    for M in (2, 3, 32, 33, 40, 64, 128, 256, 288):
+        for o in (po.rotor(M, 4.0, 0.25), po.ho(M), po.quartic(M)):
+            mm = to_mp(mp, o)
+            x = rng.uniform(-2, 2, (3, M))
+            xd = dev(ctx, x)
+            acc, diag = ctx.hmc_step(mm, 7, 0.04, xd, 5, 21)
+            want = [orc.hmc_step(o, 7, 0.04, SEED, 21, 5 + b, x[b]) for b in range(3)]
+            assert list(host(acc)) == [w[0] for w in want], (M, o.model)
+            close(host(xd), [w[1] for w in want], tol=1e-11, what=f"hmc {M}")
+            wd = np.array([w[2] for w in want])
+            assert np.max(np.abs(host(diag) - wd)) <= 1e-10 * max(np.max(np.abs(wd[:, 1:])), 1.0)
+
+
 def test_rotor_c2_properties(mp, ctx):
     """C2 shape: M_lat = 256, 8192 chains"""
     m = mp.rotor(256, 4.0, 0.25)
