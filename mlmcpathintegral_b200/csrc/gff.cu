@@ -213,22 +213,38 @@ __global__ void leapfrog_kernel(GF g, double dt_p, double dt_x, const double *x_
     x_out[t] = phi + dt_x * pn;
 }
 
-// qft/gffaction.cc:32-42, 68-79; one colour per launch
+// qft/gffaction.cc:32-42, 68-79; one colour per launch, one thread per vertex OF THAT COLOUR.
+// Unrotated level: grid (strips of half a row, rows, chains), vertex i = 2 k + ((colour + j) & 1).
+// Rotated level: the vertices of colour c (= parity of i) are the contiguous half
+// [c N/2, (c+1) N/2) of the reference's index range; grid (strips of that half, 1, chains).
 template <bool HEATBATH>
 __global__ void sweep_colour_kernel(GF g, int colour, double *x, int B, uint32_t chain0,
                                     uint64_t seed, uint64_t draw) {
-  VERTEX_SETUP
-  if (colour_of(g, i, j) != colour)
-    return;
-  double *xc = x + chain * g.N;
-  const double Delta = nn_sum(g, xc, i, j);
-  if (HEATBATH) {
-    Rng r = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, ell);
-    double z0, z1;
-    rng_normal2(r, z0, z1);
-    xc[ell] = (1. / sqrt(4. + g.mu2)) * z0 + Delta / (4. + g.mu2);
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int i, j, ell;
+  if (g.rotated) {
+    if (k >= g.N / 2)
+      return;
+    ell = colour * (g.N / 2) + k;
+    v_lin2cart(g.Mt, g.Mx, 1, ell, i, j);
   } else {
-    xc[ell] = 2. * Delta / (4. + g.mu2) - xc[ell];
+    if (k >= g.Mt / 2)
+      return;
+    j = blockIdx.y;
+    i = 2 * k + ((colour + j) & 1);
+    ell = g.Mt * j + i;
+  }
+  for (int chain = blockIdx.z; chain < B; chain += gridDim.z) {
+    double *xc = x + (size_t)chain * g.N;
+    const double Delta = nn_sum(g, xc, i, j);
+    if (HEATBATH) {
+      Rng r = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, ell);
+      double z0, z1;
+      rng_normal2(r, z0, z1);
+      xc[ell] = (1. / sqrt(4. + g.mu2)) * z0 + Delta / (4. + g.mu2);
+    } else {
+      xc[ell] = 2. * Delta / (4. + g.mu2) - xc[ell];
+    }
   }
 }
 
@@ -683,14 +699,17 @@ static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool 
   if (m->Mt_lat % 2 || m->Mx_lat % 2)
     return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need even lattice extents");
   GF g = make_gf(m);
-  const int blocks = cdiv((long long)g.N * B, 256);
+  const int per_x = g.rotated ? g.N / 2 : g.Mt / 2;
+  const int threads = std::min(256, ((per_x + 31) / 32) * 32);
+  const dim3 grid(cdiv(per_x, threads), g.rotated ? 1 : g.Mx, std::min(B, 32768));
+  if (grid.y > 65535)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "lattice too large for the sweep kernel");
   for (int pass = 0; pass < 2; ++pass) {
     const int colour = ctx->sweep_reverse ? 1 - pass : pass;
     if (heatbath)
-      sweep_colour_kernel<true><<<blocks, 256, 0, ctx->stream>>>(g, colour, x, B, chain0, ctx->seed,
-                                                                draw);
+      sweep_colour_kernel<true><<<grid, threads, 0, ctx->stream>>>(g, colour, x, B, chain0, ctx->seed, draw);
     else
-      sweep_colour_kernel<false><<<blocks, 256, 0, ctx->stream>>>(g, colour, x, B, 0, 0, 0);
+      sweep_colour_kernel<false><<<grid, threads, 0, ctx->stream>>>(g, colour, x, B, 0, 0, 0);
     MLMCPI_LAUNCHED("gff::sweep_colour");
   }
   return 0;

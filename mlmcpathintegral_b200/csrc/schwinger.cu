@@ -534,41 +534,55 @@ __global__ void __launch_bounds__(1024)
 }
 
 // --------------------------------------------------------------------- sweeps
-// colours: 0 {mu=0, j even}, 1 {mu=0, j odd}, 2 {mu=1, i even}, 3 {mu=1, i odd}
+// colours: 0 {mu=0, j even}, 1 {mu=0, j odd}, 2 {mu=1, i even}, 3 {mu=1, i odd}.
+// Grid: x = strips of a lattice row, y = the rows that hold links of this colour, z = chains
+// (folded when B exceeds the grid limit) -- no integer division anywhere.
 template <bool HEATBATH>
 __global__ void sweep_colour_kernel(SW sw, int colour, double *x, int B, uint32_t chain0,
                                     uint64_t seed, uint64_t draw) {
   const int Mt = sw.Mt, Mx = sw.Mx;
-  const long long nhalf = (long long)Mt * Mx / 2;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned wmask = __ballot_sync(0xffffffffu, t < nhalf * B);
-  if (t >= nhalf * B)
-    return;
-  const long long chain = t / nhalf;
-  const int r = (int)(t - chain * nhalf);
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   int i, j, mu;
+  bool inside;
   if (colour < 2) {
     mu = 0;
-    const int j2 = r / Mt;
-    i = r - j2 * Mt;
-    j = 2 * j2 + colour;
+    i = k;
+    j = 2 * blockIdx.y + colour;
+    inside = (i < Mt);
   } else {
     mu = 1;
-    const int Mth = Mt / 2;
-    j = r / Mth;
-    i = 2 * (r - j * Mth) + (colour - 2);
+    i = 2 * k + (colour - 2);
+    j = blockIdx.y;
+    inside = (i < Mt);
   }
-  double *xc = x + chain * 2 * (long long)Mt * Mx;
-  double theta_p, theta_m;
-  staple_angles(xc, Mt, Mx, i, j, mu, theta_p, theta_m);
+  const unsigned wmask = __ballot_sync(0xffffffffu, inside);
+  if (!inside)
+    return;
   const size_t ell = 2 * ((size_t)Mt * j + i) + mu;
-  if (HEATBATH) { // qft/quenchedschwingeraction.cc:46-54
-    Rng rg = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, (uint32_t)ell);
-    const double v = expcos_draw(rg, sw.beta, theta_p, theta_m, sw.envelope);
-    __syncwarp(wmask); // reconverge after the rejection loop: one coalesced store
-    xc[ell] = v;
-  } else { // qft/quenchedschwingeraction.cc:57-65
-    xc[ell] = mod_2pi((theta_p + theta_m) - xc[ell]);
+  for (int chain = blockIdx.z; chain < B; chain += gridDim.z) {
+    double *xc = x + (size_t)chain * 2 * Mt * Mx;
+    if (HEATBATH) { // qft/quenchedschwingeraction.cc:46-54
+      double theta_p, theta_m;
+      staple_angles(xc, Mt, Mx, i, j, mu, theta_p, theta_m);
+      Rng rg = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, (uint32_t)ell);
+      const double v = expcos_draw(rg, sw.beta, theta_p, theta_m, sw.envelope);
+      __syncwarp(wmask); // reconverge after the rejection loop: one coalesced store
+      xc[ell] = v;
+    } else { // qft/quenchedschwingeraction.cc:57-65
+      // theta <- mod_2pi(theta_+ + theta_- - theta).  The reference reduces both staple angles
+      // to [-pi, pi) first; the outer mod_2pi makes those two reductions redundant modulo 2 pi
+      // (the result differs by rounding in the last bits only), so they are skipped
+      const int ip = wrap_inc(i, Mt), im = wrap_dec(i, Mt), jp = wrap_inc(j, Mx), jm = wrap_dec(j, Mx);
+      double sp, sm;
+      if (mu == 0) {
+        sp = TH(xc, i, jp, 0) + TH(xc, i, j, 1) - TH(xc, ip, j, 1);
+        sm = TH(xc, i, jm, 0) + TH(xc, ip, jm, 1) - TH(xc, i, jm, 1);
+      } else {
+        sp = TH(xc, i, j, 0) + TH(xc, ip, j, 1) - TH(xc, i, jp, 0);
+        sm = TH(xc, im, jp, 0) + TH(xc, im, j, 1) - TH(xc, im, j, 0);
+      }
+      xc[ell] = mod_2pi((sp + sm) - xc[ell]);
+    }
   }
 }
 
@@ -1274,14 +1288,18 @@ static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool 
   if (m->Mt_lat % 2 || m->Mx_lat % 2)
     return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need even lattice extents");
   SW sw = make_sw(ctx, m);
-  const long long n = (long long)sw.Mt * sw.Mx / 2 * B;
   for (int pass = 0; pass < 4; ++pass) {
     const int colour = ctx->sweep_reverse ? 3 - pass : pass;
+    const int per_row = (colour < 2) ? sw.Mt : sw.Mt / 2; // links of this colour in one row
+    const int rows = (colour < 2) ? sw.Mx / 2 : sw.Mx;
+    const int threads = std::min(heatbath ? 128 : 256, ((per_row + 31) / 32) * 32);
+    const dim3 grid(cdiv(per_row, threads), rows, std::min(B, 32768));
+    if (rows > 65535)
+      return ctx_fail(ctx, MLMCPI_EINVAL, "lattice too large for the sweep kernel");
     if (heatbath)
-      sweep_colour_kernel<true><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sw, colour, x, B, chain0,
-                                                                      ctx->seed, draw);
+      sweep_colour_kernel<true><<<grid, threads, 0, ctx->stream>>>(sw, colour, x, B, chain0, ctx->seed, draw);
     else
-      sweep_colour_kernel<false><<<cdiv(n, 256), 256, 0, ctx->stream>>>(sw, colour, x, B, 0, 0, 0);
+      sweep_colour_kernel<false><<<grid, threads, 0, ctx->stream>>>(sw, colour, x, B, 0, 0, 0);
     MLMCPI_LAUNCHED("schwinger::sweep_colour");
   }
   return 0;
