@@ -116,9 +116,11 @@ int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed);
  * MLMCPI_OPT_LEAPFROG_FUSE: 1 (default) = two leapfrog steps per pass over HBM (temporal
  * blocking, variant 0 only), 0 = one step per pass.
  * MLMCPI_OPT_SWEEP_REVERSE: 1 = the coloured sweeps visit the colours in descending order (the
- * exact reverse of the default; used to make a sequence of sweeps a reversible kernel). */
+ * exact reverse of the default; used to make a sequence of sweeps a reversible kernel).
+ * MLMCPI_OPT_OVERRELAX_ONE_PASS: 1 (default) = a Schwinger overrelaxation sweep updates all four
+ * colours in one pass over HBM (row pipeline, out of place), 0 = four colour passes; same result. */
 enum { MLMCPI_OPT_EXPCOS_ENVELOPE = 1, MLMCPI_OPT_LEAPFROG_VARIANT = 2, MLMCPI_OPT_LEAPFROG_ROWS = 3,
-       MLMCPI_OPT_LEAPFROG_FUSE = 4, MLMCPI_OPT_SWEEP_REVERSE = 5 };
+       MLMCPI_OPT_LEAPFROG_FUSE = 4, MLMCPI_OPT_SWEEP_REVERSE = 5, MLMCPI_OPT_OVERRELAX_ONE_PASS = 6 };
 int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value);
 /* number of kernels this context has launched so far */
 uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx);
@@ -200,6 +202,9 @@ int mlmcpi_hmc_step(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, d
 /* one coloured sweep of Action::overrelaxation_update over all dofs
  * (sampler/overrelaxedheatbathsampler.cc:10-18; colours: SURVEY 7.4) */
 int mlmcpi_overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B);
+/* n_sweeps of them back to back (the n_sweep_overrelax loop of overrelaxedheatbathsampler.cc:10-18);
+ * for the Schwinger model the sweeps ping-pong between d_x and a work buffer, one pass over HBM each */
+int mlmcpi_overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, int n_sweeps);
 /* one coloured sweep of Action::heatbath_update (overrelaxedheatbathsampler.cc:20-27) */
 int mlmcpi_heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B,
                           uint32_t chain0, uint64_t draw);

@@ -18,6 +18,7 @@ QOI_X2, QOI_ROTOR_CHI, QOI_SCHWINGER_CHI, QOI_AVG_PLAQUETTE, QOI_PHI2 = range(5)
 SAMPLER_HMC, SAMPLER_HEATBATH, SAMPLER_CLUSTER, SAMPLER_EXACT = 0, 1, 2, 3
 E_INVAL, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4
 OPT_EXPCOS_ENVELOPE, OPT_LEAPFROG_VARIANT, OPT_LEAPFROG_ROWS, OPT_LEAPFROG_FUSE = 1, 2, 3, 4
+OPT_SWEEP_REVERSE, OPT_OVERRELAX_ONE_PASS = 5, 6
 
 
 class Model(C.Structure):
@@ -84,6 +85,7 @@ SIGNATURES = {
     "mlmcpi_hmc_momentum": (_i, [_vp, _MP, _vp, _i, _u32, _u64]),
     "mlmcpi_hmc_step": (_i, [_vp, _MP, _i, _d, _vp, _i, _u32, _u64, _vp, _vp]),
     "mlmcpi_overrelax_sweep": (_i, [_vp, _MP, _vp, _i]),
+    "mlmcpi_overrelax_sweeps": (_i, [_vp, _MP, _vp, _i, _i]),
     "mlmcpi_heatbath_sweep": (_i, [_vp, _MP, _vp, _i, _u32, _u64]),
     "mlmcpi_prolong": (_i, [_vp, _MP, _vp, _vp, _i]),
     "mlmcpi_restrict": (_i, [_vp, _MP, _vp, _vp, _i]),

@@ -191,6 +191,9 @@ class Context:
     def overrelax_sweep(self, m, x):
         self._ck(L.mlmcpi_overrelax_sweep(self.h, C.byref(m), _ptr(x), x.shape[0]))
 
+    def overrelax_sweeps(self, m, x, n_sweeps):
+        self._ck(L.mlmcpi_overrelax_sweeps(self.h, C.byref(m), _ptr(x), x.shape[0], n_sweeps))
+
     def heatbath_sweep(self, m, x, chain0=0, draw=0):
         self._ck(L.mlmcpi_heatbath_sweep(self.h, C.byref(m), _ptr(x), x.shape[0], chain0, draw))
 

@@ -181,6 +181,10 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
     ctx->leapfrog_fuse = value;
     return 0;
   }
+  if (option == MLMCPI_OPT_OVERRELAX_ONE_PASS && (value == 0 || value == 1)) {
+    ctx->overrelax_one_pass = value;
+    return 0;
+  }
   if (option == MLMCPI_OPT_LEAPFROG_ROWS && value >= 0) {
     ctx->leapfrog_rows = value;
     return 0;
@@ -733,6 +737,19 @@ int mlmcpi_hmc_step(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, d
 int mlmcpi_overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B) {
   DISPATCH(m, overrelax_sweep, ctx, m, d_x, B);
 }
+int mlmcpi_overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, int n_sweeps) {
+  if (!ctx || !m || B <= 0 || n_sweeps < 0)
+    return MLMCPI_EINVAL;
+  if (m->model == MLMCPI_SCHWINGER && m->Mt_lat >= 2 && m->Mx_lat >= 2 && m->Mt_lat % 2 == 0 &&
+      m->Mx_lat % 2 == 0)
+    return schwinger::overrelax_sweeps(ctx, m, d_x, B, n_sweeps);
+  for (int k = 0; k < n_sweeps; ++k) {
+    const int rc = mlmcpi_overrelax_sweep(ctx, m, d_x, B);
+    if (rc)
+      return rc;
+  }
+  return 0;
+}
 int mlmcpi_heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B,
                           uint32_t chain0, uint64_t draw) {
   DISPATCH(m, heatbath_sweep, ctx, m, d_x, B, chain0, draw);
@@ -944,8 +961,7 @@ static int coarse_draw(mlmcpi_sampler *s, int c0, int B) {
           rc = mlmcpi_heatbath_sweep(ctx, m, x, B, chain0, level_draw(s->draw, l, kk));
         }
       } else {
-        for (int k = 0; k < s->prm.n_sweep_overrelax && !rc; ++k)
-          rc = mlmcpi_overrelax_sweep(ctx, m, x, B);
+        rc = mlmcpi_overrelax_sweeps(ctx, m, x, B, s->prm.n_sweep_overrelax);
       }
     }
     ctx->sweep_reverse = saved;

@@ -31,6 +31,7 @@ struct mlmcpi_ctx {
   int leapfrog_rows = 0;    // MLMCPI_OPT_LEAPFROG_ROWS: rows per block (0 = default)
   int leapfrog_fuse = 1;    // MLMCPI_OPT_LEAPFROG_FUSE: two leapfrog steps per HBM pass
   int sweep_reverse = 0;    // MLMCPI_OPT_SWEEP_REVERSE: colours visited in descending order
+  int overrelax_one_pass = 1; // MLMCPI_OPT_OVERRELAX_ONE_PASS: all colours of a Schwinger OR sweep in one HBM pass
   uint64_t launches = 0;
   int n_sm = 148;
   std::string err;
@@ -590,6 +591,7 @@ namespace gff {
 int exact_draw(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);
 }
 namespace schwinger {
+int overrelax_sweeps(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int);
 int from_cluster(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t, uint64_t);
 }
 

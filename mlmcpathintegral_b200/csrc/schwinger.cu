@@ -586,6 +586,97 @@ __global__ void sweep_colour_kernel(SW sw, int colour, double *x, int B, uint32_
   }
 }
 
+// One overrelaxation sweep (all four colours, ascending order) in ONE pass over HBM, out of place.
+// The four colour passes above read the whole lattice four times to update a quarter of the links
+// each.  Here a block of Mt threads (one per column) marches over R rows of one chain with the
+// colours pipelined over rows: with e an even row, new theta_0 of row e+2 (colour 0: old
+// neighbours only), then new theta_0 of row e+1 (colour 1: needs the new rows e and e+2), then new
+// theta_1 of rows e and e+1 (colours 2 and 3: need the new theta_0 of rows e, e+1, e+2; even
+// columns first, odd columns after a barrier).  Old rows live in a 4-slot ring in shared memory, new
+// theta_0 rows in a 3-slot ring.  One row below and two rows above the chunk are read in addition
+// (theta_0 of the first and of the row after the last are recomputed, not stored), so the traffic is
+// 16 (1 + 3/R) B read + 16 B written per site; the update of every link is the same expression
+// on the same operands as in sweep_colour_kernel<false>, i.e. the result is bit-identical.
+__global__ void __launch_bounds__(1024)
+    overrelax_rowpipe_kernel(SW sw, const double *__restrict__ x_in, double *__restrict__ x_out, int R,
+                             int chunks) {
+  extern __shared__ __align__(16) double sm_or[];
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const int i = threadIdx.x;
+  const int ip = wrap_inc(i, Mt), im = wrap_dec(i, Mt);
+  const int chain = blockIdx.x / chunks, chunk = blockIdx.x - chain * chunks;
+  const int e0 = chunk * R;
+  const int nrow = min(R, Mx - e0); // even
+  const size_t base = (size_t)chain * Mt * Mx;
+  const double2 *xin = reinterpret_cast<const double2 *>(x_in) + base;
+  double2 *xout = reinterpret_cast<double2 *>(x_out) + base;
+  double2 *old = reinterpret_cast<double2 *>(sm_or); // [4][Mt]: (theta_0, theta_1) of old rows
+  double *An = sm_or + (size_t)8 * Mt;               // [3][Mt]: new theta_0
+  double *Bn = An + (size_t)3 * Mt;                  // [2][Mt]: new theta_1 of the two rows in flight
+  // logical row q = 0, 1, ... is lattice row e0 - 1 + q (periodic)
+  auto row_of = [&](int q) {
+    int j = e0 - 1 + q;
+    j = j < 0 ? j + Mx : j;
+    return j >= Mx ? j - Mx : j;
+  };
+  // colour 0 / 1 on logical row q: use_new selects the new theta_0 of the rows below and above
+  auto update_t0 = [&](int q, bool use_new) {
+    const double2 *o = old + (size_t)(q & 3) * Mt, *om = old + (size_t)((q - 1) & 3) * Mt;
+    const double up = use_new ? An[(size_t)((q + 1) % 3) * Mt + i] : old[(size_t)((q + 1) & 3) * Mt + i].x;
+    const double dn = use_new ? An[(size_t)((q - 1) % 3) * Mt + i] : om[i].x;
+    const double sp = up + o[i].y - o[ip].y;
+    const double sm = dn + om[ip].y - om[i].y;
+    An[(size_t)(q % 3) * Mt + i] = mod_2pi((sp + sm) - o[i].x);
+  };
+  // colour 2 (even columns, old neighbours) or colour 3 (odd columns, new neighbours) on row q
+  auto update_t1 = [&](int q, int slot, bool use_new) {
+    const double2 *o = old + (size_t)(q & 3) * Mt;
+    const double *A = An + (size_t)(q % 3) * Mt, *Aup = An + (size_t)((q + 1) % 3) * Mt;
+    const double *Bs = Bn + (size_t)slot * Mt;
+    const double bp = use_new ? Bs[ip] : o[ip].y, bm = use_new ? Bs[im] : o[im].y;
+    const double sp = A[i] + bp - Aup[i];
+    const double sm = Aup[im] + bm - A[im];
+    return mod_2pi((sp + sm) - o[i].y);
+  };
+  old[i] = xin[(size_t)row_of(0) * Mt + i];
+  old[(size_t)Mt + i] = xin[(size_t)row_of(1) * Mt + i];
+  old[(size_t)2 * Mt + i] = xin[(size_t)row_of(2) * Mt + i];
+  // rows of the next pair are prefetched into registers one iteration ahead
+  double2 pre0 = xin[(size_t)row_of(3) * Mt + i], pre1 = xin[(size_t)row_of(4) * Mt + i];
+  __syncthreads();
+  update_t0(1, false); // colour 0 on the first (even) row of the chunk
+  const bool even_col = (i & 1) == 0;
+  for (int p = 0; 2 * p < nrow; ++p) {
+    const int q = 1 + 2 * p; // logical index of the even row e
+    __syncthreads();         // every thread is done with the rows these two slots held
+    old[(size_t)((q + 2) & 3) * Mt + i] = pre0;
+    old[(size_t)((q + 3) & 3) * Mt + i] = pre1;
+    if (2 * (p + 1) < nrow) {
+      pre0 = xin[(size_t)row_of(q + 4) * Mt + i];
+      pre1 = xin[(size_t)row_of(q + 5) * Mt + i];
+    }
+    __syncthreads();
+    update_t0(q + 2, false); // colour 0, row e + 2
+    __syncthreads();
+    update_t0(q + 1, true); // colour 1, row e + 1
+    __syncthreads();
+    double b0 = 0.0, b1 = 0.0;
+    if (even_col) { // colour 2 on rows e and e + 1
+      b0 = update_t1(q, 0, false);
+      b1 = update_t1(q + 1, 1, false);
+      Bn[i] = b0;
+      Bn[(size_t)Mt + i] = b1;
+    }
+    __syncthreads();
+    if (!even_col) { // colour 3
+      b0 = update_t1(q, 0, true);
+      b1 = update_t1(q + 1, 1, true);
+    }
+    xout[(size_t)row_of(q) * Mt + i] = make_double2(An[(size_t)(q % 3) * Mt + i], b0);
+    xout[(size_t)row_of(q + 1) * Mt + i] = make_double2(An[(size_t)((q + 1) % 3) * Mt + i], b1);
+  }
+}
+
 // ------------------------------------------------------- prolong / restrict
 // qft/quenchedschwingeraction.cc:92-147; one thread per coarse site
 __global__ void prolong_kernel(SW sw, int ctype, const double *xc_all, double *x_all, int B) {
@@ -1305,8 +1396,50 @@ static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool 
   return 0;
 }
 
+// n_sweeps overrelaxation sweeps.  Ascending colour order on lattices with even extents and at most
+// 1024 columns: the one-pass kernel, ping-ponging between x and a work buffer (copied back when
+// n_sweeps is odd); otherwise four colour passes per sweep, in place.
+int overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, int n_sweeps) {
+  SW sw = make_sw(ctx, m);
+  const bool one_pass = !ctx->sweep_reverse && ctx->overrelax_one_pass && sw.Mt % 2 == 0 && sw.Mx % 2 == 0 &&
+                        sw.Mt <= 1024;
+  if (!one_pass) {
+    for (int k = 0; k < n_sweeps; ++k) {
+      int rc = sweep(ctx, m, x, B, false, 0, 0);
+      if (rc)
+        return rc;
+    }
+    return 0;
+  }
+  const size_t n = (size_t)2 * sw.Mt * sw.Mx * B;
+  double *tmp = ctx_work(ctx, 1, n);
+  if (!tmp)
+    return MLMCPI_ENOMEM;
+  int R = 32;
+  while (R > 2 && (sw.Mx % R != 0))
+    R /= 2;
+  if (sw.Mx % R != 0)
+    R = sw.Mx;
+  const int chunks = sw.Mx / R;
+  const size_t smem = (size_t)13 * sw.Mt * sizeof(double);
+  if (smem > 48 * 1024)
+    MLMCPI_CUDA(cudaFuncSetAttribute(overrelax_rowpipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  double *src = x, *dst = tmp;
+  for (int k = 0; k < n_sweeps; ++k) {
+    overrelax_rowpipe_kernel<<<chunks * B, sw.Mt, smem, ctx->stream>>>(sw, src, dst, R, chunks);
+    MLMCPI_LAUNCHED("schwinger::overrelax_rowpipe");
+    std::swap(src, dst);
+  }
+  if (src != x)
+    MLMCPI_CUDA(cudaMemcpyAsync(x, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
 int overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B) {
-  return sweep(ctx, m, x, B, false, 0, 0);
+  if (m->Mt_lat % 2 || m->Mx_lat % 2)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need even lattice extents");
+  return overrelax_sweeps(ctx, m, x, B, 1);
 }
 int heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,
                    uint64_t draw) {

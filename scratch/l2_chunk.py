@@ -17,10 +17,10 @@ def run(chunk, n_or=10, n_hb=1):
     def f():
         for c0 in range(0,B,chunk):
             xs=x[c0:c0+chunk]
-            for k in range(n_or): ctx.overrelax_sweep(m,xs)
+            ctx.overrelax_sweeps(m,xs,n_or)
             for k in range(n_hb): ctx.heatbath_sweep(m,xs,c0,5)
     return f
-for chunk in (256,64,32,16,8,4):
+for chunk in (256,):
     t=timeit(run(chunk))
     t_or=timeit(run(chunk,10,0)); 
     print(f"chunk {chunk:4d} ({chunk*4} MiB): 10 OR + 1 HB = {t:.2f} ms ; 10 OR = {t_or:.2f} ms -> {B*512*512*10/t_or/1e6:.1f} G site-updates/s", flush=True)
@@ -33,5 +33,5 @@ def rung(chunk):
             for k in range(10): ctx.overrelax_sweep(mg,xs)
             ctx.heatbath_sweep(mg,xs,c0,5)
     return f
-for chunk in (512,128,64,32,16):
+for chunk in (512,):
     print(f"gff chunk {chunk} ({chunk*0.5} MiB): {timeit(rung(chunk)):.2f} ms", flush=True)

@@ -599,6 +599,37 @@ def test_edge_shapes(mp, ctx, orc):
             assert np.max(np.abs(host(diag) - wd)) <= 1e-10 * max(np.max(np.abs(wd[:, 1:])), 1.0)
 
 
+def test_overrelax_one_pass_equals_colour_passes(mp, ctx):
+    """the one-pass row-pipelined overrelaxation sweep (all four colours, out of place) gives the
+    bits of the four colour passes, for chunked and wrapped lattices and several sweeps in a row"""
+    for Mt, Mx, B in [(2, 2, 2), (4, 2, 1), (6, 4, 3), (32, 8, 2), (64, 96, 2), (96, 34, 2), (512, 512, 2),
+                      (1024, 64, 1)]:
+        m = mp.schwinger(Mt, Mx, 2.0)
+        x0 = ctx.init_state(m, B, 0, 3)
+        ref = x0.clone()
+        ctx.set_option(mp._lib.OPT_OVERRELAX_ONE_PASS, 0)
+        for _ in range(3):
+            ctx.overrelax_sweep(m, ref)
+        ctx.set_option(mp._lib.OPT_OVERRELAX_ONE_PASS, 1)
+        got = x0.clone()
+        for _ in range(3):
+            ctx.overrelax_sweep(m, got)
+        assert bool((got == ref).all()), (Mt, Mx)
+    # inside the sampler: 3 overrelaxation sweeps + 1 heat bath per draw, both settings
+    m = mp.schwinger(64, 64, 3.0)
+    outs = []
+    for one_pass in (0, 1):
+        ctx.set_option(mp._lib.OPT_OVERRELAX_ONE_PASS, one_pass)
+        smp = mp.Sampler(ctx, m, 4, kind=mp.SAMPLER_HEATBATH, n_sweep_overrelax=3, n_sweep_heatbath=1)
+        x = ctx.init_state(m, 4, 0, 9)
+        smp.set_state(x)
+        for _ in range(3):
+            smp.draw(x)
+        outs.append(host(x).copy())
+    ctx.set_option(mp._lib.OPT_OVERRELAX_ONE_PASS, 1)
+    ang_close(outs[0], outs[1], tol=1e-12, what="sampler with one-pass overrelaxation")
+
+
 def test_rotor_c2_properties(mp, ctx):
     """C2 shape: M_lat = 256, 8192 chains"""
     m = mp.rotor(256, 4.0, 0.25)
