@@ -49,6 +49,11 @@ WORKLOADS = {
     "gff256": dict(config="configs[2]: driver_qft GFF 256x256, 4 levels (coarsening rotate), checkerboard "
                           "overrelaxed heat bath on the coarsest level, conditioned Gaussian fill-in above",
                    model="gff", lattice=256, beta=None, levels=4, chains=512, sampler="heatbath", qoi="QOI_PHI2"),
+    "schwinger512_heatbath": dict(config="driver_qft quenched Schwinger 512x512, single-level overrelaxed heat bath "
+                                         "sampler with the parameters_qft_template.in defaults (10 overrelaxation "
+                                         "sweeps + 1 heat-bath sweep per draw)",
+                                  model="schwinger", lattice=512, beta=1024.0, levels=1, chains=512,
+                                  sampler="heatbath", qoi="QOI_SCHWINGER_CHI", n_sweep_overrelax=10),
     "schwinger512": dict(config="configs[3]", model="schwinger", lattice=512, beta=1024.0, levels=3, chains=512,
                          sampler="HMC", qoi="QOI_SCHWINGER_CHI"),
     "schwinger1024": dict(config="configs[4]: quenched Schwinger 1024x1024, hierarchical sampler (3 levels), chains "
@@ -89,7 +94,7 @@ def parse():
 
 def workload_config(a):
     w = WORKLOADS[a.workload]
-    if w["model"] == "schwinger":
+    if w["model"] == "schwinger" and w["sampler"] == "HMC":
         return {
             "workload": f"driver_qft quenched Schwinger {a.lattice}x{a.lattice}, hierarchical sampler "
                         f"({a.levels} levels, coarsening both, perturbative renormalisation), HMC coarse "
@@ -200,8 +205,8 @@ def reference_main(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if WORKLOADS[a.workload]["model"] != "schwinger":
-        emit({"impl": "reference", "unavailable": "the reference arm times the Schwinger workloads only"})
+    if WORKLOADS[a.workload]["model"] != "schwinger" or WORKLOADS[a.workload]["sampler"] != "HMC":
+        emit({"impl": "reference", "unavailable": "the reference arm times the Schwinger HMC workloads only"})
         return
     draws_total = a.steps
     # bounded sample: one cascade at 512^2 is ~0.5 s per core; every process does one
@@ -299,7 +304,7 @@ def gpu_main(a):
     sampler = mp.Sampler(ctx, m, B, kind=kind, n_levels=a.levels, nt=a.nt, dt=a.dt,
                          renorm=mp.RENORM_PERTURBATIVE if w["model"] != "gff" else mp.RENORM_NONE,
                          ctype=mp.COARSEN_ROTATE if w["model"] == "gff" else mp.COARSEN_BOTH,
-                         n_sweep_overrelax=1, n_sweep_heatbath=1, chain0=rank * B)
+                         n_sweep_overrelax=w.get("n_sweep_overrelax", 1), n_sweep_heatbath=1, chain0=rank * B)
     k_max = 10
     stats = mp.Statistics(ctx, k_max, B)
     # start state: hot (U(-pi,pi), Action::initialise_state) at small beta, cold at large beta,
@@ -448,10 +453,10 @@ def gpu_main(a):
             "data": "synthetic (U(-pi,pi) start states, Philox4x32-10)", "config": cfg,
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
-        if not is_schwinger:
+        if not is_schwinger or kind != mp.SAMPLER_HMC:
             line["metric"] = "lattice site-updates/s (%s)" % a.workload
             line["roofline"] = None  # 1-D paths / Gaussian fields: see profiles/r01_summary.md section 4
-        if world == 1 and not a.no_cpu_baseline and is_schwinger:
+        if world == 1 and not a.no_cpu_baseline and is_schwinger and kind == mp.SAMPLER_HMC:
             # bounded sample: ~0.2 s per cascade and core -> about cpu_seconds of CPU work per core
             v, cores, kind, sample, _, _ = cpu_arm(a, max(1, int(a.cpu_seconds / 0.6)))
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
