@@ -118,9 +118,13 @@ int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed);
  * MLMCPI_OPT_SWEEP_REVERSE: 1 = the coloured sweeps visit the colours in descending order (the
  * exact reverse of the default; used to make a sequence of sweeps a reversible kernel).
  * MLMCPI_OPT_OVERRELAX_ONE_PASS: 1 (default) = a Schwinger overrelaxation sweep updates all four
- * colours in one pass over HBM (row pipeline, out of place), 0 = four colour passes; same result. */
+ * colours in one pass over HBM (row pipeline, out of place), 0 = four colour passes; same result.
+ * MLMCPI_OPT_FUSED_QM_HIERARCHY: 1 (default) = HierarchicalSampler::draw for 1-D paths with an HMC coarse
+ * sampler runs as ONE kernel (one warp per chain, every level on chip), 0 = the sequence of
+ * single-purpose kernels; same draw. */
 enum { MLMCPI_OPT_EXPCOS_ENVELOPE = 1, MLMCPI_OPT_LEAPFROG_VARIANT = 2, MLMCPI_OPT_LEAPFROG_ROWS = 3,
-       MLMCPI_OPT_LEAPFROG_FUSE = 4, MLMCPI_OPT_SWEEP_REVERSE = 5, MLMCPI_OPT_OVERRELAX_ONE_PASS = 6 };
+       MLMCPI_OPT_LEAPFROG_FUSE = 4, MLMCPI_OPT_SWEEP_REVERSE = 5, MLMCPI_OPT_OVERRELAX_ONE_PASS = 6,
+       MLMCPI_OPT_FUSED_QM_HIERARCHY = 7 };
 int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value);
 /* number of kernels this context has launched so far */
 uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx);

@@ -185,6 +185,10 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
     ctx->overrelax_one_pass = value;
     return 0;
   }
+  if (option == MLMCPI_OPT_FUSED_QM_HIERARCHY && (value == 0 || value == 1)) {
+    ctx->fused_qm_hierarchy = value;
+    return 0;
+  }
   if (option == MLMCPI_OPT_LEAPFROG_ROWS && value >= 0) {
     ctx->leapfrog_rows = value;
     return 0;
@@ -1014,6 +1018,23 @@ static int sampler_draw_range(mlmcpi_sampler *s, int c0, int B, bool cache0_vali
   int32_t *acc = s->acc + c0;
   auto st = [&](int l) { return s->state[l] + (size_t)c0 * mlmcpi_sample_size(&s->model[l]); };
   int rc;
+  // 1-D paths with an HMC coarse sampler: the whole cascade in one kernel, one warp per chain
+  if (L > 1 && ctx->fused_qm_hierarchy && s->model[0].model <= MLMCPI_ROTOR && s->prm.kind == MLMCPI_SAMPLER_HMC &&
+      std::max(1, s->prm.n_rep) == 1) {
+    double *states[16];
+    for (int l = 0; l < L && l < 16; ++l)
+      states[l] = st(l);
+    rc = qm::hierarchical_draw(ctx, s->model.data(), L, s->prm.nt, s->prm.dt, states, B, chain0, s->draw,
+                               s->Sf0 + c0, s->Scond0 + c0, cache0_valid, acc, s->counters);
+    if (rc <= 0) {
+      if (rc == 0) {
+        s->work[0] += (double)B * (s->prm.nt + 1) * n_sites(s->model[L - 1]);
+        for (int l = L - 2; l >= 0; --l)
+          s->work[2] += (double)B * n_sites(s->model[l]);
+      }
+      return rc;
+    }
+  }
   // S_l of every coarse level state right after the restriction chain / after its own update.
   // theta_C = restrict(theta_fine) of TwoLevelMetropolisStep::draw line 55 IS the level state
   // produced by the restriction chain, so its action (line 57) is S_old, and S_c(phi_c) (line 58)

@@ -32,6 +32,7 @@ struct mlmcpi_ctx {
   int leapfrog_fuse = 1;    // MLMCPI_OPT_LEAPFROG_FUSE: two leapfrog steps per HBM pass
   int sweep_reverse = 0;    // MLMCPI_OPT_SWEEP_REVERSE: colours visited in descending order
   int overrelax_one_pass = 1; // MLMCPI_OPT_OVERRELAX_ONE_PASS: all colours of a Schwinger OR sweep in one HBM pass
+  int fused_qm_hierarchy = 1; // MLMCPI_OPT_FUSED_QM_HIERARCHY: 1-D hierarchical draw in one kernel
   uint64_t launches = 0;
   int n_sm = 148;
   std::string err;
@@ -586,6 +587,8 @@ DECL_MODEL_API(gff)
 namespace qm {
 int cluster_update(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t, int);
 int exact_draw(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);
+int hierarchical_draw(mlmcpi_ctx *, const mlmcpi_model *, int, int, double, double *const *, int, uint32_t,
+                      uint64_t, double *, double *, bool, int32_t *, unsigned long long *);
 }
 namespace gff {
 int exact_draw(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);

@@ -323,18 +323,15 @@ __device__ __forceinline__ void path_energies(const QM &q, const RegPath<SPL> &s
   S = action_prefactor<MODEL>(q) * warp_sum(a);
 }
 
+// HMCSampler::single_step (sampler/hmcsampler.cc:22-69) on a register-resident path: momentum
+// refresh, trajectory, both energies, accept test.  Returns the accept flag (warp uniform); out[5] =
+// {deltaH, S_cur, S_trial, T_cur, T_trial}.  s.x holds the TRIAL state on return.
 template <int MODEL, int SPL>
-__global__ void __launch_bounds__(THREADS)
-    hmc_step_reg_kernel(QM q, int nt, double dt, double *x, int B, uint32_t chain0, uint64_t seed,
-                        uint64_t draw, int32_t *accept_out, double *diag) {
-  WARP_SETUP
-  double *xc = x + (size_t)c_safe * q.M;
-  const uint32_t gchain = chain0 + (uint32_t)c_safe;
-  RegPath<SPL> s;
+__device__ __forceinline__ bool hmc_step_reg_core(const QM &q, int nt, double dt, RegPath<SPL> &s, int lane,
+                                                  uint32_t gchain, uint64_t seed, uint64_t draw, double out[5]) {
 #pragma unroll
   for (int r = 0; r < SPL; ++r) {
     const int site = lane + 32 * r;
-    s.x[r] = xc[site];
     Rng rg = rng_init(seed, MLMCPI_STREAM_HMC_MOMENTUM, draw, gchain, site >> 1);
     double z0, z1;
     rng_normal2(rg, z0, z1);
@@ -378,6 +375,27 @@ __global__ void __launch_bounds__(THREADS)
     rng_uniform2(r, u0, u1);
     acc = u0 < exp(-deltaH);
   }
+  out[0] = deltaH;
+  out[1] = S_cur;
+  out[2] = S_trial;
+  out[3] = T_cur;
+  out[4] = T_trial;
+  return acc;
+}
+
+template <int MODEL, int SPL>
+__global__ void __launch_bounds__(THREADS)
+    hmc_step_reg_kernel(QM q, int nt, double dt, double *x, int B, uint32_t chain0, uint64_t seed,
+                        uint64_t draw, int32_t *accept_out, double *diag) {
+  WARP_SETUP
+  double *xc = x + (size_t)c_safe * q.M;
+  const uint32_t gchain = chain0 + (uint32_t)c_safe;
+  RegPath<SPL> s;
+#pragma unroll
+  for (int r = 0; r < SPL; ++r)
+    s.x[r] = xc[lane + 32 * r];
+  double out[5];
+  const bool acc = hmc_step_reg_core<MODEL, SPL>(q, nt, dt, s, lane, gchain, seed, draw, out);
   if (!active)
     return;
   if (acc) {
@@ -390,13 +408,177 @@ __global__ void __launch_bounds__(THREADS)
       accept_out[chain] = acc ? 1 : 0;
     if (diag) {
       double *d = diag + 5 * chain;
-      d[0] = deltaH;
-      d[1] = S_cur;
-      d[2] = S_trial;
-      d[3] = T_cur;
-      d[4] = T_trial;
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        d[k] = out[k];
     }
   }
+}
+
+// ---------------------------------------------------------- fused hierarchical draw (1-D paths)
+// HierarchicalSampler::draw (sampler/hierarchicalsampler.cc:55-81) with an HMC sampler on the
+// coarsest level, for ONE chain per warp entirely on chip: the restriction chain, the HMC step
+// (registers), and for every finer level the two-level Metropolis-Hastings step
+// (montecarlo/twolevelmetropolisstep.cc:35-97: prolongation + fill-in, S_f / S_cond of the trial
+// state, the three action differences, accept, commit) run in one kernel on shared-memory copies
+// of the level states; only the states, the accept flag and the two cached actions of the finest
+// level touch global memory.  Arithmetic, summation orders and Philox counters are those of the
+// single-purpose kernels above, so the draw is identical to the unfused sequence of launches.
+#define QMH_MAX_LEVELS 4
+struct QMH {
+  QM q[QMH_MAX_LEVELS];
+  int L;
+};
+
+template <int MODEL>
+__device__ __forceinline__ double warp_action(const QM &q, const double *xs, int lane) {
+  double acc = 0.0;
+  for (int s = lane; s < q.M; s += 32)
+    acc += site_action<MODEL>(q, xs[s == 0 ? q.M - 1 : s - 1], xs[s]);
+  return action_prefactor<MODEL>(q) * warp_sum(acc);
+}
+template <int MODEL>
+__device__ __forceinline__ double warp_cond_action(const QM &q, const double *xs, int lane) {
+  const int Mc = q.M / 2;
+  double acc = 0.0;
+  for (int j = lane; j < Mc; j += 32) {
+    const double x_m = xs[2 * j], x_p = xs[j == Mc - 1 ? 0 : 2 * j + 2];
+    double x0, curv;
+    W_min_curv<MODEL>(q, x_m, x_p, x0, curv);
+    const double dx = xs[2 * j + 1] - x0;
+    if (MODEL == MLMCPI_ROTOR)
+      acc += -log(expsin2_pdf(dx, 2.0 * curv));
+    else
+      acc += 0.5 * curv * dx * dx - 0.5 * log(curv);
+  }
+  return warp_sum(acc);
+}
+
+template <int MODEL, int SPL>
+__global__ void __launch_bounds__(THREADS)
+    hierarchical_draw_kernel(QMH h, int nt, double dt, double *x0_all, double *x1_all, double *x2_all,
+                             double *x3_all, int B, uint32_t chain0, uint64_t seed, uint64_t draw,
+                             double *Sf0, double *Scond0, int cache0_valid, int32_t *accept_out,
+                             unsigned long long *counters) {
+  extern __shared__ double smem[];
+  WARP_SETUP
+  const int L = h.L;
+  const int M0 = h.q[0].M;
+  // per warp: level states (M0 + M0/2 + ... < 2 M0) and the trial state (M0)
+  double *lev[QMH_MAX_LEVELS];
+  double *base_w = smem + (size_t)w * 3 * M0;
+  {
+    int off = 0;
+    for (int l = 0; l < L; ++l) {
+      lev[l] = base_w + off;
+      off += h.q[l].M;
+    }
+  }
+  double *trial = base_w + 2 * M0;
+  double *glob[QMH_MAX_LEVELS] = {x0_all, x1_all, x2_all, x3_all};
+  const uint32_t gchain = chain0 + (uint32_t)c_safe;
+  auto level_draw = [&](int level) { return (draw << 12) | ((uint64_t)level << 8); };
+  // restriction chain (hierarchicalsampler.cc:57-60; qm/qmaction.cc:18-26: every second site)
+  for (int s = lane; s < M0; s += 32)
+    lev[0][s] = x0_all[(size_t)c_safe * M0 + s];
+  __syncwarp();
+  for (int l = 1; l < L; ++l) {
+    for (int s = lane; s < h.q[l].M; s += 32)
+      lev[l][s] = lev[l - 1][2 * s];
+    __syncwarp();
+  }
+  double S_old[QMH_MAX_LEVELS], S_new[QMH_MAX_LEVELS];
+  for (int l = 1; l + 1 < L; ++l)
+    S_old[l] = warp_action<MODEL>(h.q[l], lev[l], lane);
+  // coarsest level: HMC step in registers
+  bool acc;
+  {
+    const QM &qc = h.q[L - 1];
+    RegPath<SPL> s;
+#pragma unroll
+    for (int r = 0; r < SPL; ++r)
+      s.x[r] = lev[L - 1][lane + 32 * r];
+    double out[5];
+    acc = hmc_step_reg_core<MODEL, SPL>(qc, nt, dt, s, lane, gchain, seed, level_draw(L - 1), out);
+    S_old[L - 1] = out[1];
+    if (acc) {
+#pragma unroll
+      for (int r = 0; r < SPL; ++r)
+        lev[L - 1][lane + 32 * r] = s.x[r];
+    }
+    __syncwarp();
+    // the unfused path re-evaluates the action of the (possibly unchanged) coarsest state
+    S_new[L - 1] = warp_action<MODEL>(qc, lev[L - 1], lane);
+  }
+  if (active && lane == 0)
+    atomicAdd(counters + (L - 1), (unsigned long long)(acc ? 1 : 0));
+  for (int l = L - 2; l >= 0; --l) {
+    const QM &q = h.q[l];
+    const int M = q.M, Mc = M / 2;
+    double Sf, Scond;
+    if (l > 0) { // TwoLevelMetropolisStep::set_state, twolevelmetropolisstep.cc:92-97
+      Sf = S_old[l];
+      Scond = warp_cond_action<MODEL>(q, lev[l], lane);
+    } else if (cache0_valid) {
+      Sf = Sf0[c_safe];
+      Scond = Scond0[c_safe];
+    } else {
+      Sf = warp_action<MODEL>(q, lev[0], lane);
+      Scond = warp_cond_action<MODEL>(q, lev[0], lane);
+    }
+    // theta' = fill(prolong(phi_c)), :40-42 (qm fill_kernel)
+    const uint64_t ldraw = level_draw(l);
+    for (int j = lane; j < Mc; j += 32) {
+      const double x_m = lev[l + 1][j], x_p = lev[l + 1][j == Mc - 1 ? 0 : j + 1];
+      trial[2 * j] = x_m;
+      double x0, curv;
+      W_min_curv<MODEL>(q, x_m, x_p, x0, curv);
+      Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, ldraw, gchain, j);
+      if (MODEL == MLMCPI_ROTOR) {
+        trial[2 * j + 1] = mod_2pi(x0 + expsin2_draw(r, 2. * curv));
+      } else {
+        double z0, z1;
+        rng_normal2(r, z0, z1);
+        trial[2 * j + 1] = x0 + z0 * (1. / sqrt(curv));
+      }
+    }
+    __syncwarp();
+    const double Sf_prime = warp_action<MODEL>(q, trial, lane);          // :48
+    const double Scond_prime = warp_cond_action<MODEL>(q, trial, lane);  // :65-66
+    // :55-58: S_c(theta_C) and S_c(phi_c) are the coarser level's action before / after its update
+    const double dS_fine = Sf_prime - Sf;
+    const double dS_coarse = S_old[l + 1] - S_new[l + 1];
+    const double dS_trial = Scond - Scond_prime;
+    const double dS = dS_fine + dS_coarse + dS_trial;
+    bool a2 = dS < 0.0;
+    if (!a2) {
+      Rng r = rng_init(seed, MLMCPI_STREAM_TWOLEVEL_ACCEPT, ldraw, gchain, 0);
+      double u0, u1;
+      rng_uniform2(r, u0, u1);
+      a2 = u0 < exp(-dS);
+    }
+    if (!acc)
+      a2 = false; // the cascade already stopped for this chain (hierarchicalsampler.cc:73-74)
+    acc = a2;
+    if (acc)
+      for (int s = lane; s < M; s += 32)
+        lev[l][s] = trial[s];
+    __syncwarp();
+    S_new[l] = acc ? Sf_prime : Sf;
+    if (l == 0 && active && lane == 0) {
+      Sf0[chain] = S_new[0];
+      Scond0[chain] = acc ? Scond_prime : Scond;
+    }
+    if (active && lane == 0)
+      atomicAdd(counters + l, (unsigned long long)(acc ? 1 : 0));
+  }
+  if (!active)
+    return;
+  for (int l = 0; l < L; ++l)
+    for (int s = lane; s < h.q[l].M; s += 32)
+      glob[l][(size_t)chain * h.q[l].M + s] = lev[l][s];
+  if (lane == 0)
+    accept_out[chain] = acc ? 1 : 0;
 }
 
 // --------------------------------------------------------------------- sweeps
@@ -782,6 +964,53 @@ int prolong_fill_eval(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, 
   if ((rc = action(ctx, m, x, B, S_out)))
     return rc;
   return cond_action(ctx, m, x, B, S_out + B);
+}
+
+// fused HierarchicalSampler::draw for 1-D paths (HMC coarse sampler); returns 1 if the shape is
+// not covered (the caller then uses the sequence of single-purpose kernels)
+int hierarchical_draw(mlmcpi_ctx *ctx, const mlmcpi_model *models, int L, int nt, double dt, double *const *states,
+                      int B, uint32_t chain0, uint64_t draw, double *Sf0, double *Scond0, bool cache0_valid,
+                      int32_t *accept, unsigned long long *counters) {
+  if (L < 2 || L > QMH_MAX_LEVELS)
+    return 1;
+  const int Mc = models[L - 1].M_lat;
+  const int spl = (Mc % 32 == 0) ? Mc / 32 : 0;
+  if (!(spl == 1 || spl == 2 || spl == 4 || spl == 8))
+    return 1;
+  QMH h;
+  h.L = L;
+  for (int l = 0; l < L; ++l) {
+    h.q[l] = make_qm(&models[l]);
+    if (l > 0 && models[l].M_lat * 2 != models[l - 1].M_lat)
+      return 1;
+  }
+  const size_t smem = (size_t)WARPS * 3 * models[0].M_lat * sizeof(double);
+  if (smem > 200 * 1024)
+    return 1;
+  double *st[QMH_MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
+  for (int l = 0; l < L; ++l)
+    st[l] = states[l];
+#define MLMCPI_HIER_LAUNCH(SPL)                                                                    \
+  QM_DISPATCH(h.q[0].model, {                                                                      \
+    int rc = prepare_smem(ctx, hierarchical_draw_kernel<MODEL, SPL>, smem);                        \
+    if (rc)                                                                                        \
+      return rc;                                                                                   \
+    hierarchical_draw_kernel<MODEL, SPL><<<cdiv(B, WARPS), THREADS, smem, ctx->stream>>>(          \
+        h, nt, dt, st[0], st[1], st[2], st[3], B, chain0, ctx->seed, draw, Sf0, Scond0,            \
+        cache0_valid ? 1 : 0, accept, counters);                                                   \
+  })
+  if (spl == 1) {
+    MLMCPI_HIER_LAUNCH(1);
+  } else if (spl == 2) {
+    MLMCPI_HIER_LAUNCH(2);
+  } else if (spl == 4) {
+    MLMCPI_HIER_LAUNCH(4);
+  } else {
+    MLMCPI_HIER_LAUNCH(8);
+  }
+#undef MLMCPI_HIER_LAUNCH
+  MLMCPI_LAUNCHED("qm::hierarchical_draw");
+  return 0;
 }
 
 int cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,

@@ -630,6 +630,34 @@ def test_overrelax_one_pass_equals_colour_passes(mp, ctx):
     ang_close(outs[0], outs[1], tol=1e-12, what="sampler with one-pass overrelaxation")
 
 
+def test_fused_qm_hierarchy_equals_kernel_sequence(mp, ctx):
+    """HierarchicalSampler::draw for 1-D paths as ONE kernel (one warp per chain, all levels on chip)
+    against the sequence of single-purpose kernels: same states, same acceptance counters"""
+    cases = [(mp.rotor(64, 4.0, 0.25), 2), (mp.rotor(256, 4.0, 0.25), 3), (mp.rotor(128, 4.0, 0.25), 2),
+             (mp.ho(128), 3), (mp.ho(64), 2), (mp.quartic(256), 4), (mp.quartic(64), 2)]
+    for m, L in cases:
+        B = 37
+        res = []
+        for fused in (0, 1):
+            ctx.set_option(mp._lib.OPT_FUSED_QM_HIERARCHY, fused)
+            smp = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=L, nt=12, dt=0.08,
+                             renorm=mp.RENORM_PERTURBATIVE, chain0=5)
+            x = ctx.init_state(m, B, 5, 2) if m.model == mp.ROTOR else ctx.exact_draw(mp.ho(m.M_lat), B, 5, 2)
+            smp.set_state(x)
+            launches0 = ctx.launches
+            for _ in range(6):
+                smp.draw(x)
+            res.append((host(x).copy(), smp.p_accept(), ctx.launches - launches0))
+        ctx.set_option(mp._lib.OPT_FUSED_QM_HIERARCHY, 1)
+        # (bit-identical for the rotor; the compiler contracts a few multiply-adds of the Gaussian
+        # fill-in differently inside the fused kernel: last-bit differences for the oscillators)
+        diff = np.max(np.abs(res[0][0] - res[1][0]))
+        assert diff <= (0.0 if m.model == mp.ROTOR else 1e-12), (m.model, m.M_lat, L, diff)
+        assert res[0][1] == res[1][1]
+        assert res[1][2] < res[0][2] / 3  # one kernel (+ the masked copy) per draw
+        assert 0.0 < res[1][1][0] < 1.0
+
+
 def test_rotor_c2_properties(mp, ctx):
     """C2 shape: M_lat = 256, 8192 chains"""
     m = mp.rotor(256, 4.0, 0.25)
