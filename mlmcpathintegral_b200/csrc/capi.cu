@@ -1349,7 +1349,8 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
       if ((rc = mlmcpi_qoi(ctx, &s->model[0], qoi, s->state[0], s->B, s->q, nullptr)))
         return rc;
   } else {
-    const int n_ranges = std::min(s->B, 8);
+    // ranges of at least 8 MiB (below that the per-range launches cost more than the overlap gains)
+    const int n_ranges = (int)std::max<size_t>(1, std::min<size_t>({(size_t)s->B, (size_t)8, n * sizeof(double) >> 23}));
     if (!s->copy_stream) {
       MLMCPI_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
       for (int k = 0; k < 9; ++k)
