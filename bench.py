@@ -457,8 +457,8 @@ def gpu_main(a):
             line["metric"] = "lattice site-updates/s (%s)" % a.workload
             line["roofline"] = None  # 1-D paths / Gaussian fields: see profiles/r01_summary.md section 4
         if world == 1 and not a.no_cpu_baseline and is_schwinger and kind == mp.SAMPLER_HMC:
-            # bounded sample: ~0.2 s per cascade and core -> about cpu_seconds of CPU work per core
-            v, cores, kind, sample, _, _ = cpu_arm(a, max(1, int(a.cpu_seconds / 0.6)))
+            # bounded sample: ~0.19 s per cascade and core -> about 0.75 x cpu_seconds of CPU work per core
+            v, cores, kind, sample, _, _ = cpu_arm(a, max(1, int(a.cpu_seconds / 0.25)))
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         emit(line)
     if world > 1:
