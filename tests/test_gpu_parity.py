@@ -537,6 +537,52 @@ def test_schwinger_512_properties(mp, ctx):
     assert float((y - x).abs().max()) < 1e-9
 
 
+def test_schwinger_1024_and_gff_256_properties(mp, ctx):
+    """size-independent properties at the remaining BASELINE sizes: Schwinger 1024 x 1024 (config 4)
+    at the continuum-limit coupling, GFF 256 x 256 with coarsening rotate (config 2)"""
+    m = mp.schwinger(1024, 1024, 4096.0)
+    B = 2
+    x = ctx.init_state(m, B, 0, 1)
+    for k in range(2):
+        ctx.heatbath_sweep(m, x, 0, k)
+    S0 = host(ctx.action(m, x))
+    assert float(ctx.force(m, x).sum(dim=1).abs().max()) < 1e-6
+    y = x.clone()
+    ctx.overrelax_sweeps(m, y, 3)  # one-pass kernel, 1024 threads per block
+    assert np.max(np.abs(host(ctx.action(m, y)) - S0)) <= 1e-11 * np.max(S0)
+    chi, Q = ctx.qoi(m, mp.QOI_SCHWINGER_CHI, x, with_charge=True)
+    assert np.allclose(host(chi), host(Q).astype(float) ** 2, rtol=0, atol=1e-5)
+    mc = mp.coarse_model(m, renorm=mp.RENORM_PERTURBATIVE)
+    xc = ctx.state(mc, B)
+    ctx.restrict(m, x, xc)
+    xc2 = ctx.state(mc, B)
+    Sf, Sc = ctx.prolong_fill_eval(m, xc, y, 0, 3)  # ApproximateBesselProduct path, tau ~ 8000
+    ctx.restrict(m, y, xc2)
+    ang_close(host(xc2), host(xc), tol=1e-12, what="restrict o fill o prolong")
+    close(host(Sf), host(ctx.action(m, y)), tol=1e-11, what="fused S_f at 1024^2")
+    close(host(Sc), host(ctx.cond_action(m, y)), tol=1e-10, what="fused S_cond at 1024^2")
+    # GFF 256^2: overrelaxation conserves the action, restrict o prolong = id on both level types,
+    # the heat bath reaches the analytic <phi^2>
+    g = mp.gff(256, 256, 10.0)
+    Bg = 64
+    phi = ctx.init_state(g, Bg, 0, 0)
+    S0 = host(ctx.action(g, phi))
+    y = phi.clone()
+    ctx.overrelax_sweep(g, y)
+    assert np.max(np.abs(host(ctx.action(g, y)) - S0)) <= 1e-11 * np.max(S0)
+    gl = g
+    for level in range(3):
+        gc = mp.coarse_model(gl, level=level, ctype=mp.COARSEN_ROTATE)
+        xc = ctx.init_state(gc, 2, 0, 5 + level)
+        fine = ctx.state(gl, 2)
+        ctx.prolong(gl, xc, fine)
+        back = ctx.state(gc, 2)
+        ctx.restrict(gl, fine, back)
+        assert bool((back == xc).all()), level
+        gl = gc
+        gl.gff_n_gibbs = 0
+
+
 def test_rowmarch_equals_generic_leapfrog(mp, ctx):
     """the tiled hot kernel (Mt % 32 == 0) and the generic fallback agree"""
     rng = np.random.default_rng(3)
