@@ -827,6 +827,24 @@ def test_host_entry_point(mp, ctx):
         assert abs(q[b] - orc.qoi(o, po.QOI_SCHWINGER_CHI, x_out[b])[0]) < 1e-9
     w = s.work()
     assert w["leapfrog_site_steps"] == B * 11 * 16 * 16 and w["filled_fine_sites"] == B * 32 * 32
+    # the host entry point issues the draw range by range (upload overlapped with compute): same
+    # draws as the device entry point, for the 2-D cascade and for the fused 1-D cascade
+    for mm, Bc, kw in ((mp.schwinger(64, 64, 6.0), 48, dict(n_levels=2, nt=8, dt=0.05)),
+                       (mp.rotor(256, 4.0, 0.25), 16384, dict(n_levels=3, nt=10, dt=0.1))):
+        xs = ctx.init_state(mm, Bc, 0, 5)
+        for k in range(3):
+            ctx.heatbath_sweep(mm, xs, 0, k)
+        a = mp.Sampler(ctx, mm, Bc, kind=mp.SAMPLER_HMC, renorm=mp.RENORM_PERTURBATIVE, **kw)
+        b = mp.Sampler(ctx, mm, Bc, kind=mp.SAMPLER_HMC, renorm=mp.RENORM_PERTURBATIVE, **kw)
+        xa = xs.clone()
+        a.set_state(xa)
+        h_in, h_out, hq = host(xs).copy(), np.zeros((Bc, mp.sample_size(mm))), np.zeros(Bc)
+        for d in range(3):
+            a.draw(xa)
+            b.draw_host(h_in, mp.QOI_X2 if mm.model == mp.ROTOR else mp.QOI_AVG_PLAQUETTE, hq, h_out)
+            h_in = h_out.copy()
+            ang_close(h_out, host(xa), tol=1e-12, what=f"draw_host vs draw, step {d}")
+        assert a.p_accept() == b.p_accept()
 
 
 def test_error_paths(mp, ctx):
