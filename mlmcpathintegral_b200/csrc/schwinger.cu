@@ -619,61 +619,72 @@ __global__ void __launch_bounds__(1024)
     j = j < 0 ? j + Mx : j;
     return j >= Mx ? j - Mx : j;
   };
-  // colour 0 / 1 on logical row q: use_new selects the new theta_0 of the rows below and above
-  auto update_t0 = [&](int q, bool use_new) {
+  // Own-column values stay in registers (o0..o3: old rows q-1..q+2 relative to the stage that uses
+  // them; a0..a2: new theta_0); shared memory only serves the neighbouring columns.
+  // colour 0 / 1 on logical row q for this column: `up` / `dn` = theta_0 above / below (old for
+  // colour 0, new for colour 1), own = old (theta_0, theta_1) of row q, below = old row q - 1
+  auto t0_update = [&](int q, double up, double dn, double2 own, double2 below) {
     const double2 *o = old + (size_t)(q & 3) * Mt, *om = old + (size_t)((q - 1) & 3) * Mt;
-    const double up = use_new ? An[(size_t)((q + 1) % 3) * Mt + i] : old[(size_t)((q + 1) & 3) * Mt + i].x;
-    const double dn = use_new ? An[(size_t)((q - 1) % 3) * Mt + i] : om[i].x;
-    const double sp = up + o[i].y - o[ip].y;
-    const double sm = dn + om[ip].y - om[i].y;
-    An[(size_t)(q % 3) * Mt + i] = mod_2pi((sp + sm) - o[i].x);
+    const double sp = up + own.y - o[ip].y;
+    const double sm = dn + om[ip].y - below.y;
+    const double v = mod_2pi((sp + sm) - own.x);
+    An[(size_t)(q % 3) * Mt + i] = v;
+    return v;
   };
-  // colour 2 (even columns, old neighbours) or colour 3 (odd columns, new neighbours) on row q
-  auto update_t1 = [&](int q, int slot, bool use_new) {
+  // colour 2 (even columns, old neighbours) or colour 3 (odd columns, new neighbours) on row q;
+  // a_own / a_up = new theta_0 of this column on rows q and q + 1, b_own = old theta_1
+  auto t1_update = [&](int q, int slot, bool use_new, double a_own, double a_up, double b_own) {
     const double2 *o = old + (size_t)(q & 3) * Mt;
     const double *A = An + (size_t)(q % 3) * Mt, *Aup = An + (size_t)((q + 1) % 3) * Mt;
     const double *Bs = Bn + (size_t)slot * Mt;
     const double bp = use_new ? Bs[ip] : o[ip].y, bm = use_new ? Bs[im] : o[im].y;
-    const double sp = A[i] + bp - Aup[i];
+    const double sp = a_own + bp - a_up;
     const double sm = Aup[im] + bm - A[im];
-    return mod_2pi((sp + sm) - o[i].y);
+    return mod_2pi((sp + sm) - b_own);
   };
-  old[i] = xin[(size_t)row_of(0) * Mt + i];
-  old[(size_t)Mt + i] = xin[(size_t)row_of(1) * Mt + i];
-  old[(size_t)2 * Mt + i] = xin[(size_t)row_of(2) * Mt + i];
+  double2 r0 = xin[(size_t)row_of(0) * Mt + i]; // old rows q - 1, q, q + 1 of this column
+  double2 r1 = xin[(size_t)row_of(1) * Mt + i];
+  double2 r2 = xin[(size_t)row_of(2) * Mt + i];
+  old[i] = r0;
+  old[(size_t)Mt + i] = r1;
+  old[(size_t)2 * Mt + i] = r2;
   // rows of the next pair are prefetched into registers one iteration ahead
   double2 pre0 = xin[(size_t)row_of(3) * Mt + i], pre1 = xin[(size_t)row_of(4) * Mt + i];
   __syncthreads();
-  update_t0(1, false); // colour 0 on the first (even) row of the chunk
+  double a_q = t0_update(1, r2.x, r0.x, r1, r0); // colour 0 on the first (even) row of the chunk
   const bool even_col = (i & 1) == 0;
   for (int p = 0; 2 * p < nrow; ++p) {
-    const int q = 1 + 2 * p; // logical index of the even row e
+    const int q = 1 + 2 * p; // logical index of the even row e; r1 = old row q, r2 = old row q + 1
     __syncthreads();         // every thread is done with the rows these two slots held
-    old[(size_t)((q + 2) & 3) * Mt + i] = pre0;
-    old[(size_t)((q + 3) & 3) * Mt + i] = pre1;
+    const double2 r3 = pre0, r4 = pre1; // old rows q + 2, q + 3
+    old[(size_t)((q + 2) & 3) * Mt + i] = r3;
+    old[(size_t)((q + 3) & 3) * Mt + i] = r4;
     if (2 * (p + 1) < nrow) {
       pre0 = xin[(size_t)row_of(q + 4) * Mt + i];
       pre1 = xin[(size_t)row_of(q + 5) * Mt + i];
     }
     __syncthreads();
-    update_t0(q + 2, false); // colour 0, row e + 2
+    const double a_q2 = t0_update(q + 2, r4.x, r2.x, r3, r2); // colour 0, row e + 2
     __syncthreads();
-    update_t0(q + 1, true); // colour 1, row e + 1
+    const double a_q1 = t0_update(q + 1, a_q2, a_q, r2, r1); // colour 1, row e + 1
     __syncthreads();
     double b0 = 0.0, b1 = 0.0;
     if (even_col) { // colour 2 on rows e and e + 1
-      b0 = update_t1(q, 0, false);
-      b1 = update_t1(q + 1, 1, false);
+      b0 = t1_update(q, 0, false, a_q, a_q1, r1.y);
+      b1 = t1_update(q + 1, 1, false, a_q1, a_q2, r2.y);
       Bn[i] = b0;
       Bn[(size_t)Mt + i] = b1;
     }
     __syncthreads();
     if (!even_col) { // colour 3
-      b0 = update_t1(q, 0, true);
-      b1 = update_t1(q + 1, 1, true);
+      b0 = t1_update(q, 0, true, a_q, a_q1, r1.y);
+      b1 = t1_update(q + 1, 1, true, a_q1, a_q2, r2.y);
     }
-    xout[(size_t)row_of(q) * Mt + i] = make_double2(An[(size_t)(q % 3) * Mt + i], b0);
-    xout[(size_t)row_of(q + 1) * Mt + i] = make_double2(An[(size_t)((q + 1) % 3) * Mt + i], b1);
+    xout[(size_t)row_of(q) * Mt + i] = make_double2(a_q, b0);
+    xout[(size_t)row_of(q + 1) * Mt + i] = make_double2(a_q1, b1);
+    a_q = a_q2;
+    r1 = r3;
+    r2 = r4;
   }
 }
 
