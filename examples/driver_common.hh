@@ -13,7 +13,7 @@ namespace mlmcpi {
 template <class P> bool read_section(P &param, const std::string &filename) {
   if (param.readFile(filename))
     return false;
-  std::cout << param << std::endl;
+  pcout() << param << std::endl;
   return true;
 }
 
@@ -62,11 +62,11 @@ construct_sampler_factory(const int samplerid, const bool cluster_supported, con
 
 inline void print_comparison(double numerical_result, double statistical_error, double analytical_result) {
   const double diff = std::fabs(numerical_result - analytical_result);
-  std::cout << std::setprecision(8) << std::fixed;
-  std::cout << "Comparison to analytical result " << std::endl;
-  std::cout << "  (analytical - numerical) = " << diff;
-  std::cout << std::setprecision(3) << std::fixed;
-  std::cout << " = " << diff / statistical_error << " * (statistical error) " << std::endl << std::endl;
+  pcout() << std::setprecision(8) << std::fixed;
+  pcout() << "Comparison to analytical result " << std::endl;
+  pcout() << "  (analytical - numerical) = " << diff;
+  pcout() << std::setprecision(3) << std::fixed;
+  pcout() << " = " << diff / statistical_error << " * (statistical error) " << std::endl << std::endl;
 }
 
 } // namespace mlmcpi

@@ -4,7 +4,7 @@
 // independent chains.  Supported actions: quenchedschwinger, gff (the O(3) sigma model is outside
 // the device library).
 //
-//   g++ -std=c++17 -O2 -Iinclude examples/driver_qft.cc -Lmlmcpathintegral_b200 -lmlmcpi
+//   g++ -std=c++17 -O2 -Iinclude examples/driver_qft.cc -Lmlmcpathintegral_b200 -lmlmcpi -lmlmcpi_comm
 //       -Wl,-rpath,$PWD/mlmcpathintegral_b200 -o driver_qft
 //   ./driver_qft PARAMETERFILE [CHAINS]
 #include "driver_common.hh"
@@ -14,17 +14,17 @@ using namespace mlmcpi;
 int main(int argc, char *argv[]) {
   Timer total_time("total");
   total_time.start();
-  std::cout << "++===================================++" << std::endl;
-  std::cout << "!!   Path integral multilevel MCMC   !!" << std::endl;
-  std::cout << "!!   2D lattice field theories, B200 !!" << std::endl;
-  std::cout << "++===================================++" << std::endl << std::endl;
-  std::cout << "Starting run at " << current_time() << std::endl;
+  pcout() << "++===================================++" << std::endl;
+  pcout() << "!!   Path integral multilevel MCMC   !!" << std::endl;
+  pcout() << "!!   2D lattice field theories, B200 !!" << std::endl;
+  pcout() << "++===================================++" << std::endl << std::endl;
+  pcout() << "Starting run at " << current_time() << std::endl;
   if (argc < 2 || argc > 3) {
-    std::cout << "Usage: " << argv[0] << " PARAMETERFILE [CHAINS]" << std::endl << std::endl;
+    pcout() << "Usage: " << argv[0] << " PARAMETERFILE [CHAINS]" << std::endl << std::endl;
     return 0;
   }
   const std::string filename = argv[1];
-  std::cout << " Reading parameter from file '" << filename << "'" << std::endl << std::endl;
+  pcout() << " Reading parameter from file '" << filename << "'" << std::endl << std::endl;
 
   /* ====== Read parameters ====== */
   GeneralParameters param_general;
@@ -63,7 +63,7 @@ int main(int argc, char *argv[]) {
       !read_section(param_multilevelmc, filename) || !read_section(param_device, filename))
     return 1;
   batch_size() = (argc == 3) ? std::max(1, std::atoi(argv[2])) : param_device.chains();
-  std::cout << "Running " << batch_size() << " independent chains side by side on the device." << std::endl;
+  pcout() << "Running " << batch_size() << " independent chains side by side on the device." << std::endl;
 
   try {
     /* ====== Lattice, quantity of interest, action ====== */
@@ -72,39 +72,39 @@ int main(int argc, char *argv[]) {
     const bool schwinger = (param_qft.action() == ActionQuenchedSchwinger);
     std::shared_ptr<Action> action;
     std::shared_ptr<QoIFactory> qoi_factory;
-    std::cout << std::endl;
+    pcout() << std::endl;
     if (schwinger) {
       action = std::make_shared<QuenchedSchwingerAction>(lattice, nullptr, param_schwinger.renormalisation(),
                                                          param_schwinger.beta());
       qoi_factory = std::make_shared<QoI2DSusceptibilityFactory>();
-      std::cout << "QoI = Susceptibility Q[phi]^2 " << std::endl;
+      pcout() << "QoI = Susceptibility Q[phi]^2 " << std::endl;
     } else {
       action = std::make_shared<GFFAction>(lattice, nullptr, param_gff.mass());
       qoi_factory = std::make_shared<QoI2DPhiSquaredFactory>();
-      std::cout << "QoI = Mean squared field 1/M*sum phi^2 " << std::endl;
+      pcout() << "QoI = Mean squared field 1/M*sum phi^2 " << std::endl;
     }
     std::shared_ptr<QoI> qoi = qoi_factory->get(action);
 
     /* ====== Analytical results (driver_qft.cc:280-318) ====== */
     const unsigned int n_cells = param_lattice.Mt_lat() * param_lattice.Mx_lat();
     double analytical_result = 0.0, numerical_result = 0.0, statistical_error = 1.0;
-    std::cout << std::endl << std::setprecision(8) << std::fixed;
+    pcout() << std::endl << std::setprecision(8) << std::fixed;
     if (schwinger) {
       const double beta = param_schwinger.beta();
       analytical_result = (beta > 2000.0) ? mlmcpi_schwinger_chit_perturbative(beta, n_cells)
                                           : mlmcpi_schwinger_chit_analytical(beta, n_cells);
-      std::cout << " Analytical results" << std::endl;
-      std::cout << "      E[V*chi_t]              = " << analytical_result;
+      pcout() << " Analytical results" << std::endl;
+      pcout() << "      E[V*chi_t]              = " << analytical_result;
       if (beta > 2000.0)
-        std::cout << " + O(beta^{-2}) = O(" << std::pow(beta, -2) << ")";
-      std::cout << std::endl;
-      std::cout << "      lim_{a->0} Var[V*chi_t] = " << mlmcpi_schwinger_var_chit_continuum(beta, n_cells) << std::endl
+        pcout() << " + O(beta^{-2}) = O(" << std::pow(beta, -2) << ")";
+      pcout() << std::endl;
+      pcout() << "      lim_{a->0} Var[V*chi_t] = " << mlmcpi_schwinger_var_chit_continuum(beta, n_cells) << std::endl
                 << std::endl;
     } else {
       analytical_result =
           mlmcpi_gff_phi_squared_analytical(param_gff.mass(), param_lattice.Mt_lat(), param_lattice.Mx_lat());
-      std::cout << " Analytical result" << std::endl;
-      std::cout << "      E[Q^2]              = " << analytical_result << std::endl;
+      pcout() << " Analytical result" << std::endl;
+      pcout() << "      E[Q^2]              = " << analytical_result << std::endl;
     }
 
     std::shared_ptr<ConditionedFineActionFactory> conditioned_fine_action_factory =
@@ -121,26 +121,26 @@ int main(int argc, char *argv[]) {
     };
 
     if (param_general.method() == MethodSingleLevel) {
-      std::cout << "+--------------------------------+" << std::endl;
-      std::cout << "! Single level MC                !" << std::endl;
-      std::cout << "+--------------------------------+" << std::endl << std::endl;
+      pcout() << "+--------------------------------+" << std::endl;
+      pcout() << "! Single level MC                !" << std::endl;
+      pcout() << "+--------------------------------+" << std::endl << std::endl;
       std::shared_ptr<SamplerFactory> sampler_factory = factory_for(param_singlelevelmc.sampler());
       if (!sampler_factory)
         return 1;
       MonteCarloSingleLevel montecarlo_singlelevel(action, qoi, sampler_factory, param_stats, param_singlelevelmc);
       montecarlo_singlelevel.evaluate();
-      std::cout << std::endl;
+      pcout() << std::endl;
       montecarlo_singlelevel.show_statistics();
       numerical_result = montecarlo_singlelevel.numerical_result();
       statistical_error = montecarlo_singlelevel.statistical_error();
-      std::cout << "=== Sampler statistics === " << std::endl;
+      pcout() << "=== Sampler statistics === " << std::endl;
       montecarlo_singlelevel.get_sampler()->show_stats();
-      std::cout << std::endl;
+      pcout() << std::endl;
     }
     if (param_general.method() == MethodTwoLevel) {
-      std::cout << "+--------------------------------+" << std::endl;
-      std::cout << "! Two level MC                   !" << std::endl;
-      std::cout << "+--------------------------------+" << std::endl << std::endl;
+      pcout() << "+--------------------------------+" << std::endl;
+      pcout() << "! Two level MC                   !" << std::endl;
+      pcout() << "+--------------------------------+" << std::endl << std::endl;
       std::shared_ptr<SamplerFactory> sampler_factory = factory_for(param_twolevelmc.sampler());
       if (!sampler_factory)
         return 1;
@@ -148,12 +148,12 @@ int main(int argc, char *argv[]) {
                                              param_stats, param_twolevelmc);
       montecarlo_twolevel.evaluate_difference();
       montecarlo_twolevel.show_statistics();
-      std::cout << std::endl;
+      pcout() << std::endl;
     }
     if (param_general.method() == MethodMultiLevel) {
-      std::cout << "+--------------------------------+" << std::endl;
-      std::cout << "! Multilevel MC                  !" << std::endl;
-      std::cout << "+--------------------------------+" << std::endl << std::endl;
+      pcout() << "+--------------------------------+" << std::endl;
+      pcout() << "! Multilevel MC                  !" << std::endl;
+      pcout() << "+--------------------------------+" << std::endl << std::endl;
       // (the reference refuses to run this method on more than one MPI rank; here the chains of
       // the batch step through the levels in lockstep)
       std::shared_ptr<SamplerFactory> sampler_factory = factory_for(param_multilevelmc.sampler());
@@ -174,6 +174,6 @@ int main(int argc, char *argv[]) {
     return 1; // the message has been printed where the error was raised (action/action.hh:48-52)
   }
   total_time.stop();
-  std::cout << total_time << std::endl;
+  pcout() << total_time << std::endl;
   return 0;
 }

@@ -3,7 +3,7 @@
 // parameters_qm_*.in file and runs the single-, two- or multilevel method on a batch of
 // independent chains.
 //
-//   g++ -std=c++17 -O2 -Iinclude examples/driver_qm.cc -Lmlmcpathintegral_b200 -lmlmcpi
+//   g++ -std=c++17 -O2 -Iinclude examples/driver_qm.cc -Lmlmcpathintegral_b200 -lmlmcpi -lmlmcpi_comm
 //       -Wl,-rpath,$PWD/mlmcpathintegral_b200 -o driver_qm
 //   ./driver_qm PARAMETERFILE [CHAINS]
 #include "driver_common.hh"
@@ -13,17 +13,17 @@ using namespace mlmcpi;
 int main(int argc, char *argv[]) {
   Timer total_time("total");
   total_time.start();
-  std::cout << "++===================================++" << std::endl;
-  std::cout << "!!   Path integral multilevel MCMC   !!" << std::endl;
-  std::cout << "!!   quantum mechanics, B200         !!" << std::endl;
-  std::cout << "++===================================++" << std::endl << std::endl;
-  std::cout << "Starting run at " << current_time() << std::endl;
+  pcout() << "++===================================++" << std::endl;
+  pcout() << "!!   Path integral multilevel MCMC   !!" << std::endl;
+  pcout() << "!!   quantum mechanics, B200         !!" << std::endl;
+  pcout() << "++===================================++" << std::endl << std::endl;
+  pcout() << "Starting run at " << current_time() << std::endl;
   if (argc < 2 || argc > 3) {
-    std::cout << "Usage: " << argv[0] << " PARAMETERFILE [CHAINS]" << std::endl << std::endl;
+    pcout() << "Usage: " << argv[0] << " PARAMETERFILE [CHAINS]" << std::endl << std::endl;
     return 0;
   }
   const std::string filename = argv[1];
-  std::cout << " Reading parameter from file '" << filename << "'" << std::endl << std::endl;
+  pcout() << " Reading parameter from file '" << filename << "'" << std::endl << std::endl;
 
   /* ====== Read parameters ====== */
   GeneralParameters param_general;
@@ -64,7 +64,7 @@ int main(int argc, char *argv[]) {
       !read_section(param_multilevelmc, filename) || !read_section(param_device, filename))
     return 1;
   batch_size() = (argc == 3) ? std::max(1, std::atoi(argv[2])) : param_device.chains();
-  std::cout << "Running " << batch_size() << " independent chains side by side on the device." << std::endl;
+  pcout() << "Running " << batch_size() << " independent chains side by side on the device." << std::endl;
 
   try {
     /* ====== Lattice, quantity of interest, action (driver_qm.cc:222-262) ====== */
@@ -75,7 +75,7 @@ int main(int argc, char *argv[]) {
     if (rotor) {
       action = std::make_shared<RotorAction>(lattice, param_rotor.renormalisation(), param_rotor.m0());
       qoi_factory = std::make_shared<QoISusceptibilityFactory>();
-      std::cout << "QoI = Susceptibility Q[X]^2/T " << std::endl;
+      pcout() << "QoI = Susceptibility Q[X]^2/T " << std::endl;
     } else {
       if (param_qm.action() == ActionHarmonicOscillator)
         action = std::make_shared<HarmonicOscillatorAction>(lattice, param_ho.renormalisation(), param_ho.m0(),
@@ -84,10 +84,10 @@ int main(int argc, char *argv[]) {
         action = std::make_shared<QuarticOscillatorAction>(lattice, RenormalisationNone, param_qo.m0(), param_qo.mu2(),
                                                            param_qo.lambda(), param_qo.x0());
       qoi_factory = std::make_shared<QoIXsquaredFactory>();
-      std::cout << "QoI = X^2 " << std::endl;
+      pcout() << "QoI = X^2 " << std::endl;
     }
     std::shared_ptr<QoI> qoi = qoi_factory->get(action);
-    std::cout << std::endl;
+    pcout() << std::endl;
 
     /* ====== Analytical results (driver_qm.cc:268-303) ====== */
     const bool has_analytical = (param_qm.action() != ActionQuarticOscillator);
@@ -97,9 +97,9 @@ int main(int argc, char *argv[]) {
     const double a_lat = lattice->geta_lat();
     if (estimates_mean && param_qm.action() == ActionHarmonicOscillator) {
       analytical_result = mlmcpi_ho_xsquared_analytical(param_ho.m0(), param_ho.mu2(), a_lat, param_lattice.M_lat(), 0);
-      std::cout << std::endl << std::setprecision(6) << std::fixed;
-      std::cout << " Analytical result        <x^2> = " << analytical_result << std::endl;
-      std::cout << " Continuum limit [a -> 0] <x^2> = "
+      pcout() << std::endl << std::setprecision(6) << std::fixed;
+      pcout() << " Analytical result        <x^2> = " << analytical_result << std::endl;
+      pcout() << " Continuum limit [a -> 0] <x^2> = "
                 << mlmcpi_ho_xsquared_analytical(param_ho.m0(), param_ho.mu2(), a_lat, param_lattice.M_lat(), 1)
                 << std::endl
                 << std::endl;
@@ -107,11 +107,11 @@ int main(int argc, char *argv[]) {
     if (estimates_mean && rotor) {
       const double m0 = param_rotor.m0(), T = param_lattice.T_final();
       analytical_result = mlmcpi_rotor_chit(m0, a_lat, T, 0);
-      std::cout << std::endl << std::setprecision(6) << std::fixed;
-      std::cout << " Analytical result        <chi_t> = " << analytical_result << std::endl;
-      std::cout << " Perturbative expansion   <chi_t> = " << mlmcpi_rotor_chit(m0, a_lat, T, 1)
+      pcout() << std::endl << std::setprecision(6) << std::fixed;
+      pcout() << " Analytical result        <chi_t> = " << analytical_result << std::endl;
+      pcout() << " Perturbative expansion   <chi_t> = " << mlmcpi_rotor_chit(m0, a_lat, T, 1)
                 << " + O((a/I)^2), a/I = " << a_lat / m0 << std::endl;
-      std::cout << " Continuum limit [a -> 0] <chi_t> = " << mlmcpi_rotor_chit(m0, a_lat, T, 2) << std::endl
+      pcout() << " Continuum limit [a -> 0] <chi_t> = " << mlmcpi_rotor_chit(m0, a_lat, T, 2) << std::endl
                 << std::endl;
     }
 
@@ -129,26 +129,26 @@ int main(int argc, char *argv[]) {
     };
 
     if (param_general.method() == MethodSingleLevel) {
-      std::cout << "+--------------------------------+" << std::endl;
-      std::cout << "! Single level MC                !" << std::endl;
-      std::cout << "+--------------------------------+" << std::endl << std::endl;
+      pcout() << "+--------------------------------+" << std::endl;
+      pcout() << "! Single level MC                !" << std::endl;
+      pcout() << "+--------------------------------+" << std::endl << std::endl;
       std::shared_ptr<SamplerFactory> sampler_factory = factory_for(param_singlelevelmc.sampler());
       if (!sampler_factory)
         return 1;
       MonteCarloSingleLevel montecarlo_singlelevel(action, qoi, sampler_factory, param_stats, param_singlelevelmc);
       montecarlo_singlelevel.evaluate();
-      std::cout << std::endl;
+      pcout() << std::endl;
       montecarlo_singlelevel.show_statistics();
       numerical_result = montecarlo_singlelevel.numerical_result();
       statistical_error = montecarlo_singlelevel.statistical_error();
-      std::cout << "=== Sampler statistics === " << std::endl;
+      pcout() << "=== Sampler statistics === " << std::endl;
       montecarlo_singlelevel.get_sampler()->show_stats();
-      std::cout << std::endl;
+      pcout() << std::endl;
     }
     if (param_general.method() == MethodTwoLevel) {
-      std::cout << "+--------------------------------+" << std::endl;
-      std::cout << "! Two level MC                   !" << std::endl;
-      std::cout << "+--------------------------------+" << std::endl << std::endl;
+      pcout() << "+--------------------------------+" << std::endl;
+      pcout() << "! Two level MC                   !" << std::endl;
+      pcout() << "+--------------------------------+" << std::endl << std::endl;
       std::shared_ptr<SamplerFactory> sampler_factory = factory_for(param_twolevelmc.sampler());
       if (!sampler_factory)
         return 1;
@@ -156,12 +156,12 @@ int main(int argc, char *argv[]) {
                                              param_stats, param_twolevelmc);
       montecarlo_twolevel.evaluate_difference();
       montecarlo_twolevel.show_statistics();
-      std::cout << std::endl;
+      pcout() << std::endl;
     }
     if (param_general.method() == MethodMultiLevel) {
-      std::cout << "+--------------------------------+" << std::endl;
-      std::cout << "! Multilevel MC                  !" << std::endl;
-      std::cout << "+--------------------------------+" << std::endl << std::endl;
+      pcout() << "+--------------------------------+" << std::endl;
+      pcout() << "! Multilevel MC                  !" << std::endl;
+      pcout() << "+--------------------------------+" << std::endl << std::endl;
       std::shared_ptr<SamplerFactory> sampler_factory = factory_for(param_multilevelmc.sampler());
       if (!sampler_factory)
         return 1;
@@ -180,6 +180,6 @@ int main(int argc, char *argv[]) {
     return 1; // the message has been printed where the error was raised (action/action.hh:48-52)
   }
   total_time.stop();
-  std::cout << total_time << std::endl;
+  pcout() << total_time << std::endl;
   return 0;
 }

@@ -103,6 +103,10 @@ int mlmcpi_create(mlmcpi_ctx **ctx, int device, uint64_t seed, void *stream);
 void mlmcpi_destroy(mlmcpi_ctx *ctx);
 const char *mlmcpi_last_error(const mlmcpi_ctx *ctx);
 int mlmcpi_sync(mlmcpi_ctx *ctx);
+/* the device index and the cudaStream_t (as void *) of the context, for code that issues its own
+ * work in order with the library's (e.g. the NCCL all-reduce of libmlmcpi_comm.so) */
+int mlmcpi_device(const mlmcpi_ctx *ctx);
+void *mlmcpi_stream(const mlmcpi_ctx *ctx);
 int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed);
 /* options.  MLMCPI_OPT_EXPCOS_ENVELOPE: proposal of the ExpCos rejection sampler
  * (distribution/expcosdistribution.hh:50-65): 0 = the reference's Gaussian envelope

@@ -29,7 +29,8 @@
 namespace mlmcpi {
 
 // ------------------------------------------------------------------ device context
-/** process-wide context (device $MLMCPI_DEVICE or 0); there is no CPU fallback */
+/** process-wide context (device $MLMCPI_DEVICE, else $MLMCPI_RANK -- one process per GPU --, else 0);
+ * there is no CPU fallback */
 class Device {
 public:
   static mlmcpi_ctx *ctx() {
@@ -47,6 +48,8 @@ public:
 private:
   Device() {
     const char *dev = std::getenv("MLMCPI_DEVICE");
+    if (!dev)
+      dev = std::getenv("MLMCPI_RANK");
     if (mlmcpi_create(&ctx_, dev ? std::atoi(dev) : 0, 0x5EED0001ull, nullptr) != 0) {
       std::cerr << "ERROR: no CUDA device (mlmcpi has no CPU fallback)" << std::endl;
       throw std::runtime_error("mlmcpi_create failed");

@@ -12,10 +12,49 @@
 #include <chrono>
 #include <iomanip>
 
+#include "../mlmcpi_comm.h"
 #include "adapters.hh"
 #include "parameters.hh"
 
 namespace mlmcpi {
+
+/** the processes of one run (one per GPU): rank, world size and the NCCL communicator from the
+ * environment (MLMCPI_RANK, MLMCPI_WORLD_SIZE, MLMCPI_COMM_FILE; examples/run_multi_gpu.sh sets
+ * them).  The role of mpi/mpi_wrapper.hh: chains are sharded over the processes, Statistics
+ * all-reduce their packed moments, everything else is process-local. */
+class Parallel {
+public:
+  static mlmcpi_comm *comm() {
+    static Parallel p;
+    return p.comm_;
+  }
+  /** rank and world size come straight from the environment, so that they are known (e.g. for
+   * master-only output) before a device is touched */
+  static int rank() { return std::max(0, env_int("MLMCPI_RANK", 0)); }
+  static int world_size() { return std::max(1, env_int("MLMCPI_WORLD_SIZE", 1)); }
+  static bool master() { return rank() == 0; }
+
+private:
+  static int env_int(const char *name, int fallback) {
+    const char *v = std::getenv(name);
+    return v ? std::atoi(v) : fallback;
+  }
+  Parallel() {
+    if (mlmcpi_comm_create_from_env(Device::ctx(), &comm_) != 0) {
+      std::cerr << "ERROR: cannot set up the NCCL communicator (MLMCPI_RANK / MLMCPI_WORLD_SIZE / MLMCPI_COMM_FILE)"
+                << std::endl;
+      throw std::runtime_error("mlmcpi_comm_create_from_env failed");
+    }
+  }
+  ~Parallel() { mlmcpi_comm_destroy(comm_); }
+  mlmcpi_comm *comm_ = nullptr;
+};
+
+/** std::cout on the master process, a sink elsewhere (mpi_parallel::cout of the reference) */
+inline std::ostream &pcout() {
+  static std::ostream sink(nullptr);
+  return Parallel::master() ? std::cout : sink;
+}
 
 /** number of chains per device of this process (set once by the driver) */
 inline unsigned int &batch_size() {
@@ -59,9 +98,8 @@ public:
 
 private:
   std::vector<double> query() const {
-    std::vector<double> packed(mlmcpi_stats_packed_size((int)k_max_)), out(6);
-    Device::check(mlmcpi_stats_pack(st_, packed.data()), "stats pack");
-    Device::check(mlmcpi_stats_finalize(packed.data(), (int)k_max_, out.data()), "stats finalize");
+    std::vector<double> out(6); // moments summed over the chains of ALL processes
+    Device::check(mlmcpi_comm_stats(Parallel::comm(), st_, (int)k_max_, out.data()), "stats all-reduce");
     return out;
   }
   const std::string label_;
@@ -96,7 +134,9 @@ public:
                  bool autotune_hmc)
       : action_(action), B_(batch_size()), n_levels_(prm.n_levels),
         x_((size_t)action->sample_size() * batch_size()) {
-    Device::check(mlmcpi_sampler_create(Device::ctx(), &action->model(), &prm, (int)B_, 0, &s_), "sampler create");
+    Device::check(mlmcpi_sampler_create(Device::ctx(), &action->model(), &prm, (int)B_,
+                                        (uint32_t)(Parallel::rank() * B_), &s_),
+                  "sampler create");
     // the reference's sampler constructors burn in and, for HMC, tune the step size
     // (sampler/hmcsampler.hh:99-108, overrelaxedheatbathsampler.hh:118-126, clustersampler.cc:30-35)
     for (unsigned int k = 0; k < n_burnin; ++k)
@@ -104,11 +144,11 @@ public:
     if (autotune_hmc && prm.kind == MLMCPI_SAMPLER_HMC) {
       double dt = 0, pa = 0;
       const int rc = mlmcpi_sampler_autotune(s_, 0.8, 100, 1000, &dt, &pa);
-      std::cout << std::setprecision(6) << std::fixed;
+      pcout() << std::setprecision(6) << std::fixed;
       if (rc == 0)
-        std::cout << "  Tuned         dt_{HMC} = " << dt << "  [ acceptance probability = " << pa << " ]" << std::endl;
+        pcout() << "  Tuned         dt_{HMC} = " << dt << "  [ acceptance probability = " << pa << " ]" << std::endl;
       else
-        std::cout << "  FAILED to tune HMC step size, reverting to dt_{HMC} = " << dt << std::endl;
+        pcout() << "  FAILED to tune HMC step size, reverting to dt_{HMC} = " << dt << std::endl;
     }
   }
   ~BatchedSampler() { mlmcpi_sampler_destroy(s_); }
@@ -127,19 +167,19 @@ public:
   void show_stats() {
     std::vector<double> p(n_levels_);
     Device::check(mlmcpi_sampler_stats(s_, p.data()), "sampler stats");
-    std::cout << std::setprecision(4) << std::fixed;
-    std::cout << "  cost per sample = " << cost_per_sample() << " mu s per chain (" << B_ << " chains side by side)"
+    pcout() << std::setprecision(4) << std::fixed;
+    pcout() << "  cost per sample = " << cost_per_sample() << " mu s per chain (" << B_ << " chains side by side)"
               << std::endl
               << std::endl;
     if (n_levels_ == 1) {
-      std::cout << std::setprecision(5) << std::fixed;
-      std::cout << "  acceptance probability  p = " << p[0] << std::endl;
-      std::cout << "  rejection probability 1-p = " << 1. - p[0] << std::endl;
+      pcout() << std::setprecision(5) << std::fixed;
+      pcout() << "  acceptance probability  p = " << p[0] << std::endl;
+      pcout() << "  rejection probability 1-p = " << 1. - p[0] << std::endl;
       return;
     }
-    std::cout << "  acceptance rate = " << p[0] << std::endl;
+    pcout() << "  acceptance rate = " << p[0] << std::endl;
     for (int l = 0; l < n_levels_; ++l)
-      std::cout << "  level " << l << " "
+      pcout() << "  level " << l << " "
                 << (l == 0 ? "[finest]  " : (l == n_levels_ - 1 ? "[coarsest]" : "          ")) << " :  p = " << p[l]
                 << std::endl;
   }
@@ -320,7 +360,7 @@ public:
     stats_Q.hard_reset();
     for (unsigned int i = 0; i < n_burnin; ++i)
       sample();
-    std::cout << "Burnin completed" << std::endl;
+    pcout() << "Burnin completed" << std::endl;
     const double two_epsilon_inv2 = 2. / (epsilon * epsilon);
     stats_Q.reset();
     unsigned long n_target = (n_samples > 0) ? n_samples : n_min_samples_qoi;
@@ -339,12 +379,14 @@ public:
     n_draws = n_local;
   }
   void show_statistics() {
-    std::cout << stats_Q << std::endl;
-    std::cout << timer << std::endl;
+    pcout() << stats_Q << std::endl;
+    pcout() << timer << std::endl;
     const double sites = (action->model().model == MLMCPI_SCHWINGER) ? 0.5 * action->sample_size() : action->sample_size();
-    std::cout << std::setprecision(3) << std::scientific << " throughput: " << (double)n_draws * B / timer.elapsed()
-              << " samples/s, " << (double)n_draws * B / stats_Q.tau_int() / timer.elapsed()
-              << " effective samples/s on " << B << " chains x " << (unsigned long)sites << " sites" << std::endl
+    const double all = (double)B * Parallel::world_size();
+    pcout() << std::setprecision(3) << std::scientific << " throughput: " << (double)n_draws * all / timer.elapsed()
+              << " samples/s, " << (double)n_draws * all / stats_Q.tau_int() / timer.elapsed()
+              << " effective samples/s on " << Parallel::world_size() << " x " << B << " chains x "
+              << (unsigned long)sites << " sites" << std::endl
               << std::endl;
   }
   double numerical_result() const { return stats_Q.average(); }
@@ -352,7 +394,10 @@ public:
   std::shared_ptr<BatchedSampler> get_sampler() { return sampler; }
 
 private:
-  unsigned long distribute_n(unsigned long n) const { return (n + B - 1) / B; } // mpi_wrapper.cc distribute_n
+  unsigned long distribute_n(unsigned long n) const { // mpi_wrapper.cc distribute_n over all chains
+    const unsigned long all = (unsigned long)B * Parallel::world_size();
+    return (n + all - 1) / all;
+  }
   void sample() {
     sampler->draw();
     Device::check(mlmcpi_qoi(Device::ctx(), &action->model(), qoi->id(), sampler->states(), (int)B, q_.ptr(), nullptr),
@@ -385,9 +430,9 @@ public:
         stats_diff("delta QoI", param_twolevelmc.n_delta_autocorr_window(), batch_size()),
         stats_coarse_sampler("QoI[coarsesampler]", param_stats.n_autocorr_window(), batch_size()),
         theta((size_t)fine_action_->sample_size() * batch_size()), cache(6 * (size_t)batch_size()) {
-    std::cout << "Twolevel Monte Carlo:" << std::endl;
-    std::cout << "  fine action   : " << fine_action->info_string() << std::endl;
-    std::cout << "  coarse action : " << coarse_action->info_string() << std::endl;
+    pcout() << "Twolevel Monte Carlo:" << std::endl;
+    pcout() << "  fine action   : " << fine_action->info_string() << std::endl;
+    pcout() << "  coarse action : " << coarse_action->info_string() << std::endl;
     coarse_sampler = sampler_factory->get(coarse_action);
     // TwoLevelMetropolisStep constructor: zero state and its cached actions (twolevelmetropolisstep.cc:11-22)
     Device::check(mlmcpi_action(Device::ctx(), &fine_action->model(), theta.ptr(), (int)B, Sf()), "S_f");
@@ -402,9 +447,10 @@ public:
     stats_diff.hard_reset();
     for (unsigned int k = 0; k < n_burnin; ++k)
       sample();
-    std::cout << "Burnin completed" << std::endl;
+    pcout() << "Burnin completed" << std::endl;
     stats_coarse_sampler.reset();
-    const unsigned long n_local_samples = (n_samples + B - 1) / B;
+    const unsigned long all_chains = (unsigned long)B * Parallel::world_size();
+    const unsigned long n_local_samples = (n_samples + all_chains - 1) / all_chains;
     stats_coarse.hard_reset();
     stats_fine.hard_reset();
     stats_diff.hard_reset();
@@ -413,19 +459,19 @@ public:
   }
   /** montecarlotwolevel.cc:95-108 */
   void show_statistics() {
-    std::cout << stats_fine << std::endl;
-    std::cout << stats_coarse << std::endl;
-    std::cout << stats_diff << std::endl;
-    std::cout << std::endl;
-    std::cout << "=== Coarse level sampler statistics === " << std::endl;
-    std::cout << stats_coarse_sampler << std::endl;
+    pcout() << stats_fine << std::endl;
+    pcout() << stats_coarse << std::endl;
+    pcout() << stats_diff << std::endl;
+    pcout() << std::endl;
+    pcout() << "=== Coarse level sampler statistics === " << std::endl;
+    pcout() << stats_coarse_sampler << std::endl;
     coarse_sampler->show_stats();
-    std::cout << std::endl;
-    std::cout << "=== Two level sampler statistics === " << std::endl;
-    std::cout << std::setprecision(5) << std::fixed;
+    pcout() << std::endl;
+    pcout() << "=== Two level sampler statistics === " << std::endl;
+    pcout() << std::setprecision(5) << std::fixed;
     const double p = n_total ? (double)n_accepted / ((double)n_total * B) : 0.0;
-    std::cout << "  acceptance probability  p = " << p << std::endl;
-    std::cout << "  rejection probability 1-p = " << 1. - p << std::endl;
+    pcout() << "  acceptance probability  p = " << p << std::endl;
+    pcout() << "  rejection probability 1-p = " << 1. - p << std::endl;
   }
   const BatchedStatistics &get_stats_diff() const { return stats_diff; }
   const BatchedStatistics &get_stats_fine() const { return stats_fine; }
@@ -454,7 +500,8 @@ private:
   void sample() {
     draw_coarse_sample();
     Device::check(mlmcpi_twolevel_step(Device::ctx(), &fine_action->model(), &coarse_action->model(),
-                                       coarse_sampler->states(), theta.ptr(), Sf(), Scond(), (int)B, 0, draw_counter++,
+                                       coarse_sampler->states(), theta.ptr(), Sf(), Scond(), (int)B,
+                                       (uint32_t)(Parallel::rank() * B), draw_counter++,
                                        accept(), nullptr),
                   "TwoLevelMetropolisStep::draw");
     Device::check(mlmcpi_qoi(Device::ctx(), &fine_action->model(), qoi, theta.ptr(), (int)B, q_fine(), nullptr),
@@ -493,6 +540,10 @@ public:
                        std::shared_ptr<ConditionedFineActionFactory> /*conditioned_fine_action_factory*/,
                        const StatisticsParameters param_stats, const MultiLevelMCParameters param_multilevelmc)
       : n_level(param_multilevelmc.n_level()), epsilon(param_multilevelmc.epsilon()), timer("MultilevelMC") {
+    if (Parallel::world_size() > 1) { // (the reference refuses as well, driver_qft.cc:409-414)
+      std::cerr << " The multilevel method runs on the chains of ONE device." << std::endl;
+      throw std::runtime_error("multilevel method on more than one process");
+    }
     mlmcpi_mlmc_params p = {};
     p.n_level = (int)n_level;
     p.n_burnin = (int)param_multilevelmc.n_burnin();
@@ -520,21 +571,21 @@ public:
   double statistical_error() const { return error_; }
   /** montecarlomultilevel.cc:207-240 */
   void show_statistics() {
-    std::cout << std::setprecision(6) << std::fixed;
-    std::cout << " Q: Avg +/- Err = " << value_ << " +/- " << error_ << std::endl;
-    std::cout << " tolerance epsilon = " << epsilon << std::endl;
-    std::cout << timer << std::endl << std::endl;
+    pcout() << std::setprecision(6) << std::fixed;
+    pcout() << " Q: Avg +/- Err = " << value_ << " +/- " << error_ << std::endl;
+    pcout() << " tolerance epsilon = " << epsilon << std::endl;
+    pcout() << timer << std::endl << std::endl;
   }
   /** per-level table: samples, mean and variance of Y_l, tau_int, effective cost, target */
   void show_detailed_statistics() {
-    std::cout << " level      samples        E[Y_l]        Var[Y_l]     tau_int    cost_eff [mu s]    n_target" << std::endl;
+    pcout() << " level      samples        E[Y_l]        Var[Y_l]     tau_int    cost_eff [mu s]    n_target" << std::endl;
     for (unsigned int l = 0; l < n_level; ++l) {
       const double *r = &level_[6 * l];
-      std::cout << std::setw(6) << l << std::setw(13) << (unsigned long)r[0] << std::scientific << std::setprecision(4)
+      pcout() << std::setw(6) << l << std::setw(13) << (unsigned long)r[0] << std::scientific << std::setprecision(4)
                 << std::setw(14) << r[1] << std::setw(16) << r[2] << std::fixed << std::setprecision(3) << std::setw(12)
                 << r[3] << std::setw(19) << r[4] << std::setw(12) << (unsigned long)r[5] << std::endl;
     }
-    std::cout << std::endl;
+    pcout() << std::endl;
   }
 
 private:

@@ -58,6 +58,8 @@ SIGNATURES = {
     "mlmcpi_destroy": (None, [_vp]),
     "mlmcpi_last_error": (C.c_char_p, [_vp]),
     "mlmcpi_sync": (_i, [_vp]),
+    "mlmcpi_device": (_i, [_vp]),
+    "mlmcpi_stream": (_vp, [_vp]),
     "mlmcpi_set_seed": (_i, [_vp, _u64]),
     "mlmcpi_set_option": (_i, [_vp, _i, _i]),
     "mlmcpi_launch_count": (_u64, [_vp]),

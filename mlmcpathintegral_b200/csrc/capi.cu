@@ -160,6 +160,9 @@ void mlmcpi_destroy(mlmcpi_ctx *ctx) {
 
 const char *mlmcpi_last_error(const mlmcpi_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 
+int mlmcpi_device(const mlmcpi_ctx *ctx) { return ctx ? ctx->device : -1; }
+void *mlmcpi_stream(const mlmcpi_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
 int mlmcpi_sync(mlmcpi_ctx *ctx) {
   MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;

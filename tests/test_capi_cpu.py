@@ -189,3 +189,19 @@ def test_gff_coarse_model_carries_the_gibbs_smoothed_action(mp):
     assert (mc.gff_n_gibbs, mc.gff_omega, mp.sample_size(mc)) == (2, 1.0, 512)
     big = mp.coarse_model(mp.gff(256, 256, 10.0), ctype=mp.COARSEN_ROTATE)
     assert big.gff_n_gibbs == 0 and mp.sample_size(big) == 32768
+
+
+def test_comm_library_exports_every_declared_symbol(mp):
+    """libmlmcpi_comm.so (NCCL all-reduce of the statistics moments) loads and exports what
+    include/mlmcpi_comm.h declares; a single-process communicator needs neither NCCL traffic nor a GPU"""
+    hdr = open(os.path.join(ROOT, "include", "mlmcpi_comm.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mlmcpi_comm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) == 8, declared
+    path = os.path.join(os.path.dirname(mp._lib.LIB_PATH), "libmlmcpi_comm.so")
+    if not os.path.exists(path):
+        pytest.skip("NCCL not installed: libmlmcpi_comm.so not built")
+    lib = C.CDLL(path)
+    assert not [s for s in sorted(declared) if not hasattr(lib, s)]
+    lib.mlmcpi_comm_world_size.argtypes = [C.c_void_p]
+    assert lib.mlmcpi_comm_world_size(None) == 1 and lib.mlmcpi_comm_rank(None) == 0

@@ -135,7 +135,7 @@ def drivers(tmp_path_factory):
     for name in ("driver_qm", "driver_qft"):
         exe = str(out / name)
         subprocess.run(["g++", "-std=c++17", "-O2", "-w", f"-I{ROOT}/include", f"{ROOT}/examples/{name}.cc",
-                        f"-L{LIBDIR}", "-lmlmcpi", f"-Wl,-rpath,{LIBDIR}", "-o", exe], check=True)
+                        f"-L{LIBDIR}", "-lmlmcpi", "-lmlmcpi_comm", f"-Wl,-rpath,{LIBDIR}", "-o", exe], check=True)
         exes[name] = exe
     return exes
 
@@ -216,4 +216,23 @@ def test_driver_qft_twolevel(drivers, tmp_path):
 def test_driver_qm_matches_analytic(drivers, tmp_path, over):
     r = run(drivers["driver_qm"], QM.format(**dict(QM_DEFAULTS, **over)), tmp_path)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr
+    assert sigma_ratio(r.stdout) < 5.0, r.stdout[-1500:]
+
+
+@pytest.mark.gpu
+def test_driver_two_processes_two_gpus(drivers, tmp_path):
+    """one process per GPU (examples/run_multi_gpu.sh): chains sharded over the processes, packed
+    Statistics moments all-reduced with NCCL; twice the chains, the same analytic value"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    p = tmp_path / "parameters.in"
+    p.write_text(QFT.format(**dict(QFT_DEFAULTS, n_samples=200000)))
+    r = subprocess.run([os.path.join(ROOT, "examples", "run_multi_gpu.sh"), "2", drivers["driver_qft"], str(p), "64"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr
+    assert r.stdout.count("Single level MC") == 1  # only the master prints
+    assert "on 2 x 64 chains" in r.stdout
+    m = re.search(r"Q: # samples   = ([0-9]+)", r.stdout)
+    assert m and int(m.group(1)) >= 200000
     assert sigma_ratio(r.stdout) < 5.0, r.stdout[-1500:]
