@@ -282,17 +282,15 @@ __device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, con
   // tau (cos x - 1) + q x^2; one loop for the three envelopes (one copy of the code: the
   // fill-in kernels are instruction-cache bound)
   const bool tight = (envelope == 2 && tau >= EXPCOS_TIGHT_TAU);
-  double sigma, q, x1sq, sq;
+  double sigma, q, sq;
   if (tight) {
     const double a = tau - 40. / 3.;
     sigma = rsqrt(a);
     q = 0.5 * a;
-    x1sq = 160. / tau;
     sq = 20. / 3.; // squeeze: log acceptance >= -(20/3) x^2
   } else {
     sigma = envelope >= 1 ? 0.5 * M_PI / sqrt(tau) : M_PI * sqrt(2. / tau);
     q = tau * (envelope >= 1 ? 2. / (M_PI * M_PI) : 1. / (4. * M_PI * M_PI));
-    x1sq = 0.0;
     sq = 0.0;
   }
   while (!accepted) {
@@ -304,7 +302,7 @@ __device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, con
       x = sigma * (t == 0 ? z0 : z1);
       const double u = (t == 0 ? u0 : u1);
       const double x2 = x * x;
-      const bool inside = tight ? (x2 <= x1sq) : ((-M_PI <= x) && (x < M_PI));
+      const bool inside = tight ? (tau * x2 <= 160.) : ((-M_PI <= x) && (x < M_PI)); // x^2 <= 160 / tau
       if (inside) {
         accepted = tight && (u <= 1. - sq * x2);
         if (!accepted)

@@ -45,16 +45,17 @@ __device__ __forceinline__ double plaq(const double *x, int Mt, int Mx, int i, i
   return own.x + TH(x, ip, j, 1) - TH(x, i, jp, 0) - own.y;
 }
 
-// qft/quenchedschwingeraction.cc:25-43
+// qft/quenchedschwingeraction.cc:25-43.  Only the heat bath uses the two angles (as the arguments
+// of the ExpCos draw, whose result is an angle modulo 2 pi): the reciprocal-multiply mod_2pi.
 __device__ __forceinline__ void staple_angles(const double *x, int Mt, int Mx, int i, int j, int mu,
                                               double &theta_p, double &theta_m) {
   const int ip = wrap_inc(i, Mt), im = wrap_dec(i, Mt), jp = wrap_inc(j, Mx), jm = wrap_dec(j, Mx);
   if (mu == 0) {
-    theta_p = mod_2pi(TH(x, i, jp, 0) + TH(x, i, j, 1) - TH(x, ip, j, 1));
-    theta_m = mod_2pi(TH(x, i, jm, 0) + TH(x, ip, jm, 1) - TH(x, i, jm, 1));
+    theta_p = mod_2pi_fast(TH(x, i, jp, 0) + TH(x, i, j, 1) - TH(x, ip, j, 1));
+    theta_m = mod_2pi_fast(TH(x, i, jm, 0) + TH(x, ip, jm, 1) - TH(x, i, jm, 1));
   } else {
-    theta_p = mod_2pi(TH(x, i, j, 0) + TH(x, ip, j, 1) - TH(x, i, jp, 0));
-    theta_m = mod_2pi(TH(x, im, jp, 0) + TH(x, im, j, 1) - TH(x, im, j, 0));
+    theta_p = mod_2pi_fast(TH(x, i, j, 0) + TH(x, ip, j, 1) - TH(x, i, jp, 0));
+    theta_m = mod_2pi_fast(TH(x, im, jp, 0) + TH(x, im, j, 1) - TH(x, im, j, 0));
   }
 }
 

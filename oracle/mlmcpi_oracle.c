@@ -929,7 +929,6 @@ double orc_expcos_draw(orc_rng *r, double beta, double x_p, double x_m) {
   double x = 0.0;
   int accepted = 0;
   if (g_expcos_envelope == 2 && tau >= 64.0) {
-    const double x1sq = 160. / tau;
     const double a = tau - 40. / 3.;
     const double sigma = 1.0 / sqrt(a);
     while (!accepted) {
@@ -939,7 +938,7 @@ double orc_expcos_draw(orc_rng *r, double beta, double x_p, double x_m) {
       for (int t = 0; t < 2 && !accepted; ++t) {
         x = sigma * z[t];
         const double x2 = x * x;
-        if (x2 <= x1sq)
+        if (tau * x2 <= 160.)
           accepted = (u[t] <= 1. - (20. / 3.) * x2) ||
                      (u[t] <= exp(tau * (cos(x) - 1.) + 0.5 * a * x2));
       }
