@@ -654,9 +654,11 @@ __global__ void __launch_bounds__(1024)
   __syncthreads();
   double a_q = t0_update(1, r2.x, r0.x, r1, r0); // colour 0 on the first (even) row of the chunk
   const bool even_col = (i & 1) == 0;
+  __syncthreads(); // the first iteration reuses the slot of logical row 0
   for (int p = 0; 2 * p < nrow; ++p) {
     const int q = 1 + 2 * p; // logical index of the even row e; r1 = old row q, r2 = old row q + 1
-    __syncthreads();         // every thread is done with the rows these two slots held
+    // The two ring slots written next held rows q - 2 and q - 1; their last readers were the
+    // even-column threads of the previous iteration, before its colour-2/3 barrier.
     const double2 r3 = pre0, r4 = pre1; // old rows q + 2, q + 3
     old[(size_t)((q + 2) & 3) * Mt + i] = r3;
     old[(size_t)((q + 3) & 3) * Mt + i] = r4;
