@@ -795,6 +795,36 @@ def test_schwinger_samplers_match_analytic_chit(mp, ctx):
         s.close()
 
 
+@pytest.mark.parametrize("beta", [9.0, 16.0])
+def test_schwinger_hierarchical_approx_path_matches_analytic_chit(mp, ctx, beta):
+    """beta > 8 selects the ApproximateBesselProduct fill-in (quenchedschwingerconditionedfineaction.cc:45-48,
+    250-285) and, here, the fused by-product evaluation of S_f / S_cond: two-level cascade with a heat-bath
+    coarse sampler on 8x8, started from a thermalised state, against quenchedschwinger_chit_analytical.
+    (From a HOT start the reference's own cascade leaves a fraction of the chains frozen in |Q| > 0 sectors --
+    scratch/ref_phys_hot.py -- and so does this library; the reference starts cold.)"""
+    L, B = 8, 4096
+    m = mp.schwinger(L, L, beta)
+    want = mp._lib.lib.mlmcpi_schwinger_chit_analytical(beta, L * L)
+    x = ctx.init_state(m, B, 0, 0)
+    for k in range(50):
+        ctx.heatbath_sweep(m, x, 0, k)
+    s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HEATBATH, n_levels=2, renorm=mp.RENORM_PERTURBATIVE,
+                   n_sweep_overrelax=2, n_sweep_heatbath=1)
+    s.set_state(x)
+    for _ in range(100):
+        s.draw(x)
+    vals = []
+    for _ in range(300):
+        s.draw(x)
+        vals.append(host(ctx.qoi(m, mp.QOI_SCHWINGER_CHI, x)))
+    mean, err = _mean_err(np.mean(vals, axis=0))
+    assert abs(mean - want) < 5 * err, (beta, mean, err, want)
+    pa = s.p_accept()
+    # the reference's own cascade: 0.753 (beta = 9) and 0.892 (beta = 16), scratch/ref_phys.py
+    assert abs(pa[0] - (0.753 if beta == 9.0 else 0.89)) < 0.02, pa
+    s.close()
+
+
 def test_gff_heatbath_matches_analytic_phi2(mp, ctx):
     want = float.fromhex(load("scalars")["analytic"]["gff_phi_squared_10_16"])
     m = mp.gff(16, 16, 10.0)
