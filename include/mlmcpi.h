@@ -108,6 +108,21 @@ int mlmcpi_sync(mlmcpi_ctx *ctx);
 int mlmcpi_device(const mlmcpi_ctx *ctx);
 void *mlmcpi_stream(const mlmcpi_ctx *ctx);
 int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed);
+/* The one exchange between the processes of a run (one process per GPU): an in-place
+ * SUM over all processes of n doubles in DEVICE memory, issued in order on the stream of ctx
+ * (ncclAllReduce: mlmcpi_comm_attach of libmlmcpi_comm.so installs it; any other transport may be
+ * plugged in).  Once set, every Statistics query the library makes for a host-side decision --
+ * tau_int in MultilevelSampler::draw (sampler/multilevelsampler.cc:84-99) and in
+ * MonteCarloMultiLevel::draw_coarse_sample (montecarlo/montecarlomultilevel.cc:170-190), the
+ * variances / sample counts of the allocation loop (:139-158), the measured costs and the HMC
+ * autotune acceptance -- is taken over the chains of ALL processes, which is what
+ * mpi_allreduce_avg does inside the reference's Statistics (common/statistics.cc:30-35,64-79).
+ * All processes then take identical decisions and stay in lockstep.  world_size / rank describe
+ * the calling process; fn == NULL removes the hook. */
+typedef int (*mlmcpi_allreduce_fn)(void *user, double *d_buf, size_t n);
+int mlmcpi_set_allreduce(mlmcpi_ctx *ctx, mlmcpi_allreduce_fn fn, void *user, int world_size, int rank);
+int mlmcpi_world_size(const mlmcpi_ctx *ctx);
+int mlmcpi_rank(const mlmcpi_ctx *ctx);
 /* options.  MLMCPI_OPT_EXPCOS_ENVELOPE: proposal of the ExpCos rejection sampler
  * (distribution/expcosdistribution.hh:50-65): 0 = the reference's Gaussian envelope
  * (variance 2 pi^2/tau, ~22 % acceptance), 1 = chord-bound envelope (variance

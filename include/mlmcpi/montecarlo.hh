@@ -45,6 +45,9 @@ private:
                 << std::endl;
       throw std::runtime_error("mlmcpi_comm_create_from_env failed");
     }
+    // the library's own Statistics queries (MultilevelSampler, MonteCarloMultiLevel, HMC autotune)
+    // run over the chains of all processes from here on
+    Device::check(mlmcpi_comm_attach(comm_), "mlmcpi_comm_attach");
   }
   ~Parallel() { mlmcpi_comm_destroy(comm_); }
   mlmcpi_comm *comm_ = nullptr;
@@ -540,10 +543,10 @@ public:
                        std::shared_ptr<ConditionedFineActionFactory> /*conditioned_fine_action_factory*/,
                        const StatisticsParameters param_stats, const MultiLevelMCParameters param_multilevelmc)
       : n_level(param_multilevelmc.n_level()), epsilon(param_multilevelmc.epsilon()), timer("MultilevelMC") {
-    if (Parallel::world_size() > 1) { // (the reference refuses as well, driver_qft.cc:409-414)
-      std::cerr << " The multilevel method runs on the chains of ONE device." << std::endl;
-      throw std::runtime_error("multilevel method on more than one process");
-    }
+    // (the reference refuses to run this method on more than one rank, driver_qft.cc:409-414; here
+    // the chains are sharded over the processes and every Statistics query of the allocation loop is
+    // taken over all of them -- SURVEY 8e -- so all processes walk through the same loop)
+    (void)Parallel::comm();
     mlmcpi_mlmc_params p = {};
     p.n_level = (int)n_level;
     p.n_burnin = (int)param_multilevelmc.n_burnin();
@@ -553,7 +556,9 @@ public:
     p.qoi = qoi_factory_->id();
     p.max_iterations = 0;
     p.sampler = sampler_factory->params(*fine_action_);
-    Device::check(mlmcpi_mlmc_create(Device::ctx(), &fine_action_->model(), &p, (int)batch_size(), 0, &m_), "mlmc create");
+    Device::check(mlmcpi_mlmc_create(Device::ctx(), &fine_action_->model(), &p, (int)batch_size(),
+                                     (uint32_t)(Parallel::rank() * batch_size()), &m_),
+                  "mlmc create");
   }
   ~MonteCarloMultiLevel() { mlmcpi_mlmc_destroy(m_); }
   /** montecarlomultilevel.cc:71-167 */

@@ -36,6 +36,10 @@ int mlmcpi_comm_rank(const mlmcpi_comm *comm);
 int mlmcpi_comm_world_size(const mlmcpi_comm *comm);
 /* in-place sum over the ranks of n doubles in device memory (asynchronous, stream of ctx) */
 int mlmcpi_comm_allreduce_sum(mlmcpi_comm *comm, double *d_buf, size_t n);
+/* install the communicator as the all-reduce of its context (mlmcpi_set_allreduce): from then on the
+ * library's own Statistics queries -- MultilevelSampler, MonteCarloMultiLevel, autotune -- run over
+ * the chains of all ranks */
+int mlmcpi_comm_attach(mlmcpi_comm *comm);
 /* Statistics over ALL chains of ALL ranks: pack on the device, all-reduce, finalize;
  * out = {average, variance, variance_error, tau_int, error, samples} as mlmcpi_stats_finalize
  * (synchronises; identical on every rank) */

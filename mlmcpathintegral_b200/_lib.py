@@ -49,6 +49,8 @@ class MlmcParams(C.Structure):
 # every symbol include/mlmcpi.h declares: name -> (restype, argtypes)
 _vp, _i, _u32, _u64, _d, _sz = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_double, C.c_size_t
 _MP = C.POINTER(Model)
+# mlmcpi_allreduce_fn: int (*)(void *user, double *d_buf, size_t n)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 _ip = C.POINTER(C.c_int)
 _u32p = C.POINTER(C.c_uint32)
 _dp = C.POINTER(C.c_double)
@@ -58,6 +60,9 @@ SIGNATURES = {
     "mlmcpi_destroy": (None, [_vp]),
     "mlmcpi_last_error": (C.c_char_p, [_vp]),
     "mlmcpi_sync": (_i, [_vp]),
+    "mlmcpi_set_allreduce": (_i, [_vp, _vp, _vp, _i, _i]),
+    "mlmcpi_world_size": (_i, [_vp]),
+    "mlmcpi_rank": (_i, [_vp]),
     "mlmcpi_device": (_i, [_vp]),
     "mlmcpi_stream": (_vp, [_vp]),
     "mlmcpi_set_seed": (_i, [_vp, _u64]),

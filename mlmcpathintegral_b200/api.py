@@ -130,6 +130,54 @@ class Context:
         """ExpCos proposal: 0 reference envelope, 1 chord bound, 2 chord + Taylor bound (default)"""
         self._ck(L.mlmcpi_set_option(self.h, _lib.OPT_EXPCOS_ENVELOPE, int(variant)))
 
+    def attach_process_group(self, group=None):
+        """mlmcpi_set_allreduce with torch.distributed as the transport: from now on the library's
+        own Statistics queries (MultilevelSampler, MonteCarloMultiLevel, HMC autotune) run over the
+        chains of ALL processes of the group, so every process takes the same host-side decisions
+        (common/statistics.cc:30-35,64-79 averages the same moments over MPI ranks).  NCCL groups
+        reduce a device staging tensor, other backends (gloo) a host one."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world == 1:
+            self._ck(L.mlmcpi_set_allreduce(self.h, None, None, 1, 0))
+            self._allreduce_cb = None
+            return
+        on_device = dist.get_backend(group) == "nccl"
+        stage = {}
+
+        def hook(_user, d_buf, n):
+            try:
+                t = stage.get(n)
+                if t is None:
+                    t = stage[n] = torch.zeros(n, dtype=torch.float64,
+                                               device=self.device if on_device else "cpu")
+                tp = C.c_void_p(t.data_ptr())
+                if on_device:
+                    # a host-decision path (a few calls per allocation round): plain synchronisation
+                    # orders the library's stream and the stream NCCL is issued on
+                    self._ck(L.mlmcpi_copy(self.h, tp, d_buf, n))
+                    self.sync()
+                    dist.all_reduce(t, group=group)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    self._ck(L.mlmcpi_copy(self.h, d_buf, tp, n))
+                else:
+                    self._ck(L.mlmcpi_download(self.h, tp, d_buf, n))  # synchronises
+                    dist.all_reduce(t, group=group)
+                    self._ck(L.mlmcpi_upload(self.h, d_buf, tp, n))
+                    self.sync()
+                return 0
+            except Exception:  # never unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return _lib.E_CUDA
+
+        self._allreduce_cb = _lib.ALLREDUCE_FN(hook)  # keep the thunk alive
+        self._ck(L.mlmcpi_set_allreduce(self.h, C.cast(self._allreduce_cb, C.c_void_p), None, world, rank))
+
+    @property
+    def world_size(self):
+        return int(L.mlmcpi_world_size(self.h))
+
     @property
     def launches(self):
         return int(L.mlmcpi_launch_count(self.h))

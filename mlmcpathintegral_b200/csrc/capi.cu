@@ -26,6 +26,27 @@ int ctx_fail(mlmcpi_ctx *ctx, int code, const char *what, const char *detail) {
   return code;
 }
 
+int ctx_allreduce_host(mlmcpi_ctx *ctx, double *h, size_t n) {
+  if (!ctx->allreduce || ctx->world <= 1 || n == 0)
+    return 0;
+  if (ctx->reduce_buf_n < n) {
+    if (ctx->reduce_buf)
+      cudaFree(ctx->reduce_buf);
+    ctx->reduce_buf = nullptr;
+    ctx->reduce_buf_n = 0;
+    MLMCPI_CUDA(cudaMalloc((void **)&ctx->reduce_buf, sizeof(double) * std::max<size_t>(n, 64)));
+    ctx->reduce_buf_n = std::max<size_t>(n, 64);
+  }
+  MLMCPI_CUDA(cudaMemcpyAsync(ctx->reduce_buf, h, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  // (pageable source: the copy is staged before the call returns)
+  const int rc = ctx->allreduce(ctx->allreduce_user, ctx->reduce_buf, n);
+  if (rc)
+    return ctx_fail(ctx, rc < 0 ? rc : MLMCPI_ECUDA, "all-reduce hook failed");
+  MLMCPI_CUDA(cudaMemcpyAsync(h, ctx->reduce_buf, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int ctx_check_launch(mlmcpi_ctx *ctx, const char *what) {
   ctx->launches++;
   cudaError_t e = cudaGetLastError();
@@ -144,6 +165,8 @@ void mlmcpi_destroy(mlmcpi_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch)
     cudaFree(ctx->scratch);
+  if (ctx->reduce_buf)
+    cudaFree(ctx->reduce_buf);
   for (int k = 0; k < MLMCPI_N_WORK; ++k)
     if (ctx->work[k])
       cudaFree(ctx->work[k]);
@@ -202,6 +225,17 @@ int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed) {
   ctx->seed = seed;
   return 0;
 }
+int mlmcpi_set_allreduce(mlmcpi_ctx *ctx, mlmcpi_allreduce_fn fn, void *user, int world_size, int rank) {
+  if (!ctx || world_size < 1 || rank < 0 || rank >= world_size)
+    return ctx ? ctx_fail(ctx, MLMCPI_EINVAL, "bad world size / rank") : MLMCPI_EINVAL;
+  ctx->allreduce = fn;
+  ctx->allreduce_user = user;
+  ctx->world = fn ? world_size : 1;
+  ctx->rank = fn ? rank : 0;
+  return 0;
+}
+int mlmcpi_world_size(const mlmcpi_ctx *ctx) { return ctx ? ctx->world : 1; }
+int mlmcpi_rank(const mlmcpi_ctx *ctx) { return ctx ? ctx->rank : 0; }
 uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx) { return ctx->launches; }
 
 // =================================================================== memory
@@ -861,6 +895,7 @@ static int twolevel_step_impl(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const m
 }
 
 // ================================================================== samplers
+static mlmcpi_ctx *mlmcpi_stats_ctx(mlmcpi_stats *st);
 struct mlmcpi_sampler {
   mlmcpi_ctx *ctx = nullptr;
   mlmcpi_sampler_params prm;
@@ -904,6 +939,9 @@ static int stats_query(mlmcpi_stats *st, int k_max, double out[6]) {
   std::vector<double> packed(mlmcpi_stats_packed_size(k_max));
   int rc = mlmcpi_stats_pack(st, packed.data());
   if (rc)
+    return rc;
+  // over the chains of ALL processes (statistics.cc:30-35,64-79: mpi_allreduce_avg of the moments)
+  if ((rc = ctx_allreduce_host(mlmcpi_stats_ctx(st), packed.data(), packed.size())))
     return rc;
   return mlmcpi_stats_finalize(packed.data(), k_max, out);
 }
@@ -1455,7 +1493,15 @@ int mlmcpi_sampler_autotune(mlmcpi_sampler *s, double p_accept_target, int n_rou
     unsigned long long h = 0;
     cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
-    p_acc = (double)h / ((double)steps * B);
+    double acc_tot[2] = {(double)h, (double)steps * B};
+    {
+      const int rc = ctx_allreduce_host(ctx, acc_tot, 2); // all processes tune to the same dt
+      if (rc) {
+        cudaFree(cnt);
+        return rc;
+      }
+    }
+    p_acc = acc_tot[0] / acc_tot[1];
     if (p_acc > p_accept_target)
       dt_min = dt;
     else
@@ -1763,6 +1809,16 @@ int mlmcpi_mlmc_evaluate(mlmcpi_mlmc *m) {
     cudaEventDestroy(e1);
     m->cost_twolevel[l] = 1.0e3 * ms / (4.0 * B);
   }
+  if (ctx->world > 1) { // every process must allocate samples with the same costs: mean over the processes
+    std::vector<double> c(m->cost_sampler.begin(), m->cost_sampler.end());
+    c.insert(c.end(), m->cost_twolevel.begin(), m->cost_twolevel.end());
+    if ((rc = ctx_allreduce_host(ctx, c.data(), c.size())))
+      return rc;
+    for (int l = 0; l < L; ++l) {
+      m->cost_sampler[l] = c[l] / ctx->world;
+      m->cost_twolevel[l] = c[L + l] / ctx->world;
+    }
+  }
   for (int l = 0; l < L; ++l)
     if ((rc = mlmcpi_stats_hard_reset(m->stats_qoi[l])))
       return rc;
@@ -1786,7 +1842,8 @@ int mlmcpi_mlmc_evaluate(mlmcpi_mlmc *m) {
       double st[6];
       if ((rc = stats_query(m->stats_qoi[level], k_max, st)))
         return rc;
-      for (double j = st[5]; j < m->n_target[level]; j += B) // B samples per batched draw
+      // B samples per batched draw and process (st[5] counts the samples of all processes)
+      for (double j = st[5]; j < m->n_target[level]; j += (double)B * ctx->world)
         if ((rc = mlmc_sample(m, level, true)))
           return rc;
     }
@@ -1859,6 +1916,8 @@ struct mlmcpi_stats {
   double *acc = nullptr;
   double *packed = nullptr;
 };
+
+static mlmcpi_ctx *mlmcpi_stats_ctx(mlmcpi_stats *st) { return st->ctx; }
 
 namespace {
 

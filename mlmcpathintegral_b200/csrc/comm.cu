@@ -119,6 +119,18 @@ int mlmcpi_comm_allreduce_sum(mlmcpi_comm *c, double *d_buf, size_t n) {
   return rc == ncclSuccess ? 0 : MLMCPI_ECUDA;
 }
 
+static int comm_allreduce_thunk(void *user, double *d_buf, size_t n) {
+  return mlmcpi_comm_allreduce_sum((mlmcpi_comm *)user, d_buf, n);
+}
+
+int mlmcpi_comm_attach(mlmcpi_comm *c) {
+  if (!c)
+    return MLMCPI_EINVAL;
+  if (c->world == 1)
+    return mlmcpi_set_allreduce(c->ctx, nullptr, nullptr, 1, 0);
+  return mlmcpi_set_allreduce(c->ctx, comm_allreduce_thunk, c, c->world, c->rank);
+}
+
 int mlmcpi_comm_stats(mlmcpi_comm *c, mlmcpi_stats *st, int k_max, double out[6]) {
   if (!c || !st || !out)
     return MLMCPI_EINVAL;

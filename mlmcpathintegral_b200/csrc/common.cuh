@@ -35,6 +35,12 @@ struct mlmcpi_ctx {
   int fused_qm_hierarchy = 1; // MLMCPI_OPT_FUSED_QM_HIERARCHY: 1-D hierarchical draw in one kernel
   uint64_t launches = 0;
   int n_sm = 148;
+  // sum over the processes of a run (mlmcpi_set_allreduce); nullptr: single process
+  int (*allreduce)(void *user, double *d_buf, size_t n) = nullptr;
+  void *allreduce_user = nullptr;
+  int world = 1, rank = 0;
+  double *reduce_buf = nullptr; // device staging of ctx_allreduce_host
+  size_t reduce_buf_n = 0;
   std::string err;
   // optional timing of the dominant kernel (leapfrog) with CUDA events on ctx->stream
   bool profile = false;
@@ -57,6 +63,8 @@ int ctx_fail(mlmcpi_ctx *ctx, int code, const char *what, const char *detail = n
 int ctx_check_launch(mlmcpi_ctx *ctx, const char *what);
 double *ctx_scratch(mlmcpi_ctx *ctx, size_t n);          // >= n doubles, nullptr on failure
 double *ctx_work(mlmcpi_ctx *ctx, int which, size_t n);  // persistent work vector
+// in-place sum over all processes of n host doubles (no-op without a hook); synchronises
+int ctx_allreduce_host(mlmcpi_ctx *ctx, double *h, size_t n);
 void prof_begin(mlmcpi_ctx *ctx);
 void prof_end(mlmcpi_ctx *ctx, uint64_t launches, double algorithmic_bytes);
 

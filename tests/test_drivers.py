@@ -236,3 +236,20 @@ def test_driver_two_processes_two_gpus(drivers, tmp_path):
     m = re.search(r"Q: # samples   = ([0-9]+)", r.stdout)
     assert m and int(m.group(1)) >= 200000
     assert sigma_ratio(r.stdout) < 5.0, r.stdout[-1500:]
+
+
+@pytest.mark.gpu
+def test_driver_multilevel_two_processes_two_gpus(drivers, tmp_path):
+    """the multilevel method over two processes / GPUs (the reference refuses more than one rank,
+    driver_qft.cc:409-414): chains sharded, every Statistics query of the allocation loop all-reduced
+    (mlmcpi_comm_attach), both processes walk through the same loop"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    p = tmp_path / "parameters.in"
+    p.write_text(QFT.format(**dict(QFT_DEFAULTS, method="multilevel", n_max_level=2, epsilon=0.05)))
+    r = subprocess.run([os.path.join(ROOT, "examples", "run_multi_gpu.sh"), "2", drivers["driver_qft"], str(p), "64"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr
+    assert r.stdout.count("tolerance epsilon") == 1  # only the master prints
+    assert sigma_ratio(r.stdout) < 5.0, r.stdout[-1500:]
