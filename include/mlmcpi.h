@@ -276,6 +276,12 @@ int mlmcpi_cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *
  * charge for the two susceptibility QoIs */
 int mlmcpi_qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int qoi, const double *d_x, int B,
                double *d_q, int64_t *d_Qint);
+/* Start state for chains that are advanced by two-level Metropolis steps (MonteCarloTwoLevel,
+ * MonteCarloMultiLevel, MultilevelSampler, HierarchicalSampler): the reference's zero state
+ * (twolevelmetropolisstep.cc:11-22) followed by 50 local heat-bath sweeps where the action has a heat
+ * bath.  With B chains side by side EVERY chain has to forget its start, and the exactly cold state is
+ * metastable under the two-level step (profiles/r01_summary.md 10.2). */
+int mlmcpi_thermal_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0);
 /* TwoLevelMetropolisStep::draw (montecarlo/twolevelmetropolisstep.cc:35-89) for B
  * chains.  d_xc: coarse states phi_c; d_xf: current fine states theta (updated where
  * accepted); d_Sf / d_Scond: cached S_f(theta), S_cond(theta) (updated where

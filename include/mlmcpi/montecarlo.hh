@@ -437,7 +437,11 @@ public:
     pcout() << "  fine action   : " << fine_action->info_string() << std::endl;
     pcout() << "  coarse action : " << coarse_action->info_string() << std::endl;
     coarse_sampler = sampler_factory->get(coarse_action);
-    // TwoLevelMetropolisStep constructor: zero state and its cached actions (twolevelmetropolisstep.cc:11-22)
+    // TwoLevelMetropolisStep constructor: zero state and its cached actions (twolevelmetropolisstep.cc:11-22);
+    // every one of the B chains has to forget its start: thermalised zero state (mlmcpi_thermal_state)
+    Device::check(mlmcpi_thermal_state(Device::ctx(), &fine_action->model(), theta.ptr(), (int)B,
+                                       (uint32_t)(Parallel::rank() * B)),
+                  "thermal start");
     Device::check(mlmcpi_action(Device::ctx(), &fine_action->model(), theta.ptr(), (int)B, Sf()), "S_f");
     Device::check(mlmcpi_cond_action(Device::ctx(), &fine_action->model(), theta.ptr(), (int)B, Scond()), "S_cond");
   }

@@ -112,6 +112,7 @@ SIGNATURES = {
     "mlmcpi_schwinger_from_cluster": (_i, [_vp, _MP, _vp, _vp, _i, _u32, _u64]),
     "mlmcpi_cond_action": (_i, [_vp, _MP, _vp, _i, _vp]),
     "mlmcpi_qoi": (_i, [_vp, _MP, _i, _vp, _i, _vp, _vp]),
+    "mlmcpi_thermal_state": (_i, [_vp, _MP, _vp, _i, _u32]),
     "mlmcpi_twolevel_step": (_i, [_vp, _MP, _MP, _vp, _vp, _vp, _vp, _i, _u32, _u64, _vp, _vp]),
     "mlmcpi_sampler_create": (_i, [_vp, _MP, C.POINTER(SamplerParams), _i, _u32, C.POINTER(_vp)]),
     "mlmcpi_sampler_destroy": (None, [_vp]),

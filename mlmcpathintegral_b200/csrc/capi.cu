@@ -844,6 +844,12 @@ int mlmcpi_schwinger_from_cluster(mlmcpi_ctx *ctx, const mlmcpi_model *m, const 
   return schwinger::from_cluster(ctx, m, d_psi, d_x, B, chain0, draw);
 }
 
+static int thermal_start(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0);
+int mlmcpi_thermal_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0) {
+  if (!ctx || !m || !d_x || B <= 0)
+    return MLMCPI_EINVAL;
+  return thermal_start(ctx, m, d_x, B, chain0);
+}
 int mlmcpi_twolevel_step(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_model *coarse,
                          const double *d_xc, double *d_xf, double *d_Sf, double *d_Scond, int B,
                          uint32_t chain0, uint64_t draw, int32_t *d_accept, double *d_deltas) {
@@ -944,6 +950,36 @@ static int stats_query(mlmcpi_stats *st, int k_max, double out[6]) {
   if ((rc = ctx_allreduce_host(mlmcpi_stats_ctx(st), packed.data(), packed.size())))
     return rc;
   return mlmcpi_stats_finalize(packed.data(), k_max, out);
+}
+
+// Start state of a chain that is advanced by two-level Metropolis steps.  The reference starts such
+// chains from the zero state (twolevelmetropolisstep.cc:11-22, hierarchicalsampler.cc:43-44) and relies
+// on ONE long chain to forget it.  With B chains side by side every chain has to be thermalised, and
+// the exactly cold state is metastable under the two-level step (S_f(theta') - S_f(0) grows with the
+// volume: 16^2, beta = 4: acceptance 3 % for the first 100 draws, profiles/r01_summary.md 10.2), as is the
+// hot state for beta > 8 (10.1).  So: zero state, then MLMCPI_THERMAL_SWEEPS local heat-bath sweeps where
+// the action has a heat bath (rotor, GFF, Schwinger); any start state is legitimate, burn-in follows.
+#define MLMCPI_THERMAL_SWEEPS 50
+static int thermal_start(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0) {
+  const size_t n = (size_t)mlmcpi_sample_size(m) * B;
+  MLMCPI_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
+  const bool sweeps = m->model == MLMCPI_ROTOR || m->model == MLMCPI_GFF ||
+                      (m->model == MLMCPI_SCHWINGER && m->Mt_lat % 2 == 0 && m->Mx_lat % 2 == 0);
+  if (!sweeps)
+    return 0;
+  if (m->model == MLMCPI_GFF) {
+    const int rc = mlmcpi_init_state(ctx, m, x, B, chain0, 0);
+    if (rc)
+      return rc;
+  }
+  for (int k = 0; k < MLMCPI_THERMAL_SWEEPS; ++k) {
+    const int rc = mlmcpi_heatbath_sweep(ctx, m, x, B, chain0, (0xFFFFull << 40) + (uint64_t)k);
+    if (rc == MLMCPI_EUNSUPPORTED || rc == MLMCPI_EINVAL) // no coloured sweep for this shape: zero state
+      return k == 0 ? 0 : rc;
+    if (rc)
+      return rc;
+  }
+  return 0;
 }
 
 static uint64_t level_draw(uint64_t draw, int level, int rep) {
@@ -1267,13 +1303,19 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
       s->SfL.push_back(a);
       s->ScondL.push_back(b);
       if (!rc)
+        rc = thermal_start(ctx, &s->model[l], s->state[l], B, chain0);
+      if (!rc)
         rc = mlmcpi_action(ctx, &s->model[l], s->state[l], B, a);
       if (!rc)
         rc = mlmcpi_cond_action(ctx, &s->model[l], s->state[l], B, b);
     }
   } else {
-    // Sampler constructors start from Action::initialise_state (e.g. hmcsampler.hh:99-101)
-    rc = mlmcpi_init_state(ctx, fine, s->state[0], B, chain0, 0);
+    // Sampler constructors start from Action::initialise_state (e.g. hmcsampler.hh:99-101); the
+    // hierarchical sampler from the zero state (hierarchicalsampler.cc:43-44), here thermalised
+    if (s->L > 1)
+      rc = thermal_start(ctx, fine, s->state[0], B, chain0);
+    else
+      rc = mlmcpi_init_state(ctx, fine, s->state[0], B, chain0, 0);
   }
   if (rc) {
     mlmcpi_sampler_destroy(s);
@@ -1764,7 +1806,46 @@ int mlmcpi_mlmc_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_m
       rc = mlmcpi_alloc(ctx, B, &a) || mlmcpi_alloc(ctx, B, &b);
     m->Sf.push_back(a);
     m->Scond.push_back(b);
-    // TwoLevelMetropolisStep constructor (twolevelmetropolisstep.cc:11-22): zero state
+    // The reference's sampler constructors burn in (hmcsampler.hh:99-108, ...); so does this one, from
+    // the thermalised zero state, and phi_coarse_state / the coarsest phi_state start as a state of the
+    // sampler: a two-level step never sees the all-zero coarse state as a "sample".  (The reference's
+    // TwoLevelMetropolisStep constructor times 10 000 draws with a zero coarse state,
+    // twolevelmetropolisstep.cc:23-29, which parks theta_fine in a state of very large weight
+    // pi_f / (pi_c q); one long chain forgets that, B short ones do not: 16^2, beta = 4, n_burnin = 100
+    // left a bias of 9 sigma -- profiles/r01_summary.md 10.2.)
+    const int n_therm = std::max(m->prm.n_burnin, 100);
+    const size_t n_c = (size_t)mlmcpi_sample_size(&m->model[l + 1]) * B;
+    if (!rc && s->L == 1 && s->prm.kind != MLMCPI_SAMPLER_EXACT)
+      rc = thermal_start(ctx, &m->model[l + 1], s->state[0], B, chain0);
+    for (int k = 0; k < n_therm && !rc; ++k)
+      rc = mlmcpi_sampler_draw(s, nullptr, nullptr);
+    if (!rc)
+      rc = mlmcpi_copy(ctx, m->phi_coarse_state[l + 1], s->state[0], n_c);
+    if (!rc && l + 1 == L - 1)
+      rc = mlmcpi_copy(ctx, m->phi_state[l + 1], s->state[0], n_c);
+    // TwoLevelMetropolisStep constructor (twolevelmetropolisstep.cc:11-22): zero state.  Here EVERY one
+    // of the B chains has to forget its start, and the exactly cold state is metastable under the
+    // two-level step (16^2, beta = 4: 3 % acceptance over the first 100 draws; 32^2: none in 2000).  The
+    // chain of level l starts from a state of the sampler the user configured, run on level l itself:
+    // the (burnt-in) coarse sampler of the next finer level for l >= 1, a temporary one for l = 0.
+    if (!rc) {
+      mlmcpi_sampler *ts = (l == 0) ? nullptr : m->coarse_sampler[l - 1];
+      if (l == 0) {
+        mlmcpi_sampler_params tp = prm->sampler;
+        tp.n_levels = std::max(1, prm->sampler.n_levels);
+        tp.multilevel = 0;
+        tp.qoi = prm->qoi;
+        rc = mlmcpi_sampler_create(ctx, &m->model[0], &tp, B, chain0 + 0x00400000u, &ts);
+        if (!rc && ts->L == 1 && ts->prm.kind != MLMCPI_SAMPLER_EXACT)
+          rc = thermal_start(ctx, &m->model[0], ts->state[0], B, chain0);
+        for (int k = 0; k < n_therm && !rc; ++k)
+          rc = mlmcpi_sampler_draw(ts, nullptr, nullptr);
+      }
+      if (!rc)
+        rc = mlmcpi_copy(ctx, m->phi_state[l], ts->state[0], (size_t)mlmcpi_sample_size(&m->model[l]) * B);
+      if (l == 0 && ts)
+        mlmcpi_sampler_destroy(ts);
+    }
     if (!rc)
       rc = mlmcpi_action(ctx, &m->model[l], m->phi_state[l], B, a);
     if (!rc)
