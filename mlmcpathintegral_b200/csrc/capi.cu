@@ -934,6 +934,7 @@ struct mlmcpi_sampler {
   std::vector<double *> SfL, ScondL; // [L-1][B]
   std::vector<double> t_indep;
   std::vector<int> n_indep, t_sampler;
+  std::vector<uint64_t> n_steps; // steps taken on every level (acceptance rates of the level walk)
   // QuenchedSchwingerClusterSampler: the rotor chain psi [B][Mt*Mx] and its action
   double *psi = nullptr;
   mlmcpi_model psi_model = {};
@@ -1172,6 +1173,8 @@ static int multilevel_draw(mlmcpi_sampler *s) {
     if (level == L - 1) {
       if ((rc = coarse_draw(s, 0, B))) // :76-78
         return rc;
+      count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc, s->counters + level);
+      MLMCPI_LAUNCHED("count_accept");
       s->cluster_updates += std::max(1, s->prm.n_updates);
     } else { // :85-86 (the two-level step keeps theta_fine and its cached actions)
       if ((rc = twolevel_step_impl(ctx, &s->model[level], &s->model[level + 1], s->state[level + 1],
@@ -1184,6 +1187,7 @@ static int multilevel_draw(mlmcpi_sampler *s) {
       s->work[2] += (double)B * n_sites(s->model[level]);
     }
     s->draw++;
+    s->n_steps[level]++;
     if ((rc = mlmcpi_qoi(ctx, &s->model[level], s->prm.qoi, s->state[level], B, s->q, nullptr))) // :89
       return rc;
     if ((rc = mlmcpi_stats_record(s->stats_sampler[level], s->q)))
@@ -1292,6 +1296,7 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
     s->t_indep.assign(s->L, 0.0);
     s->n_indep.assign(s->L, 0);
     s->t_sampler.assign(s->L, 0);
+    s->n_steps.assign(s->L, 0);
     for (int l = 0; l < s->L && !rc; ++l) {
       mlmcpi_stats *st = nullptr;
       rc = mlmcpi_stats_create(ctx, s->prm.n_autocorr_window, B, &st);
@@ -1485,8 +1490,11 @@ int mlmcpi_sampler_stats(mlmcpi_sampler *s, double *h_p_accept) {
   MLMCPI_CUDA(cudaMemcpyAsync(c.data(), s->counters, sizeof(unsigned long long) * s->L,
                               cudaMemcpyDeviceToHost, ctx->stream));
   MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int l = 0; l < s->L; ++l)
-    h_p_accept[l] = s->n_draws ? (double)c[l] / ((double)s->n_draws * s->B) : 0.0;
+  for (int l = 0; l < s->L; ++l) {
+    // the level walk of the MultilevelSampler takes several steps per draw on the coarser levels
+    const double n = s->prm.multilevel ? (double)s->n_steps[l] : (double)s->n_draws;
+    h_p_accept[l] = n > 0 ? (double)c[l] / (n * s->B) : 0.0;
+  }
   return 0;
 }
 
