@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(1024)
     }
     __syncthreads();
     const double a_q2 = t0_update(q + 2, r4.x, r2.x, r3, r2); // colour 0, row e + 2
-    __syncthreads();
+    // (no barrier: colour 1 reads old neighbours and this thread's own new theta_0 values only)
     const double a_q1 = t0_update(q + 1, a_q2, a_q, r2, r1); // colour 1, row e + 1
     __syncthreads();
     double b0 = 0.0, b1 = 0.0;
