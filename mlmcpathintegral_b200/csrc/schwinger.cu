@@ -611,83 +611,90 @@ __global__ void __launch_bounds__(1024)
   const size_t base = (size_t)chain * Mt * Mx;
   const double2 *xin = reinterpret_cast<const double2 *>(x_in) + base;
   double2 *xout = reinterpret_cast<double2 *>(x_out) + base;
-  double2 *old = reinterpret_cast<double2 *>(sm_or); // [4][Mt]: (theta_0, theta_1) of old rows
-  double *An = sm_or + (size_t)8 * Mt;               // [3][Mt]: new theta_0
-  double *Bn = An + (size_t)3 * Mt;                  // [2][Mt]: new theta_1 of the two rows in flight
-  // logical row q = 0, 1, ... is lattice row e0 - 1 + q (periodic)
-  auto row_of = [&](int q) {
-    int j = e0 - 1 + q;
-    j = j < 0 ? j + Mx : j;
-    return j >= Mx ? j - Mx : j;
-  };
-  // Own-column values stay in registers (o0..o3: old rows q-1..q+2 relative to the stage that uses
-  // them; a0..a2: new theta_0); shared memory only serves the neighbouring columns.
+  // Shared memory serves the NEIGHBOURING columns only, and of the old rows the neighbours need
+  // theta_1 alone (every old theta_0 an update uses is the thread's own column: registers).  So the
+  // old ring holds theta_1 rows as plain doubles: half the footprint, and the 8-byte loads of a warp
+  // are contiguous (the former double2 ring cost two wavefronts per load -- 44 % of the shared-memory
+  // wavefronts were bank conflicts, ncu).
+  double *old1 = sm_or;                  // [4][Mt]: old theta_1 of rows q - 1 .. q + 2 (slot = row & 3)
+  double *An = sm_or + (size_t)4 * Mt;   // [3][Mt]: new theta_0 (slot = row % 3)
+  double *Bn = An + (size_t)3 * Mt;      // [2][Mt]: new theta_1 of the two rows in flight
+  // logical row q = 0, 1, ... is lattice row e0 - 1 + q (periodic); e0 and Mx are even, so inside the
+  // loop only the prefetched row e0 + 2p + 4 can wrap, and it wraps to row 0 exactly
+  const int jm1 = e0 == 0 ? Mx - 1 : e0 - 1;
+  const int j3 = e0 + 2 >= Mx ? e0 + 2 - Mx : e0 + 2; // rows of q = 3, 4 (the pair after the first)
   // colour 0 / 1 on logical row q for this column: `up` / `dn` = theta_0 above / below (old for
-  // colour 0, new for colour 1), own = old (theta_0, theta_1) of row q, below = old row q - 1
-  auto t0_update = [&](int q, double up, double dn, double2 own, double2 below) {
-    const double2 *o = old + (size_t)(q & 3) * Mt, *om = old + (size_t)((q - 1) & 3) * Mt;
-    const double sp = up + own.y - o[ip].y;
-    const double sm = dn + om[ip].y - below.y;
+  // colour 0, new for colour 1), own = old (theta_0, theta_1) of row q, below = old row q - 1;
+  // o / om = old theta_1 rows q and q - 1, a_out = the An row that receives the result
+  auto t0_update = [&](const double *o, const double *om, double *a_out, double up, double dn, double2 own,
+                       double2 below) {
+    const double sp = up + own.y - o[ip];
+    const double sm = dn + om[ip] - below.y;
     const double v = mod_2pi((sp + sm) - own.x);
-    An[(size_t)(q % 3) * Mt + i] = v;
+    a_out[i] = v;
     return v;
   };
-  // colour 2 (even columns, old neighbours) or colour 3 (odd columns, new neighbours) on row q;
-  // a_own / a_up = new theta_0 of this column on rows q and q + 1, b_own = old theta_1
-  auto t1_update = [&](int q, int slot, bool use_new, double a_own, double a_up, double b_own) {
-    const double2 *o = old + (size_t)(q & 3) * Mt;
-    const double *A = An + (size_t)(q % 3) * Mt, *Aup = An + (size_t)((q + 1) % 3) * Mt;
-    const double *Bs = Bn + (size_t)slot * Mt;
-    const double bp = use_new ? Bs[ip] : o[ip].y, bm = use_new ? Bs[im] : o[im].y;
-    const double sp = a_own + bp - a_up;
-    const double sm = Aup[im] + bm - A[im];
+  // colour 2 (even columns, old theta_1 neighbours in nb) or colour 3 (odd columns, new ones) on a row;
+  // A / Aup = new theta_0 of that row and of the row above, a_own / a_up = this column's, b_own = old theta_1
+  auto t1_update = [&](const double *nb, const double *A, const double *Aup, double a_own, double a_up,
+                       double b_own) {
+    const double sp = a_own + nb[ip] - a_up;
+    const double sm = Aup[im] + nb[im] - A[im];
     return mod_2pi((sp + sm) - b_own);
   };
-  double2 r0 = xin[(size_t)row_of(0) * Mt + i]; // old rows q - 1, q, q + 1 of this column
-  double2 r1 = xin[(size_t)row_of(1) * Mt + i];
-  double2 r2 = xin[(size_t)row_of(2) * Mt + i];
-  old[i] = r0;
-  old[(size_t)Mt + i] = r1;
-  old[(size_t)2 * Mt + i] = r2;
+  double2 r0 = xin[jm1 * Mt + i]; // old rows q - 1, q, q + 1 of this column
+  double2 r1 = xin[e0 * Mt + i];
+  double2 r2 = xin[(e0 + 1) * Mt + i];
+  old1[i] = r0.y;
+  old1[Mt + i] = r1.y;
+  old1[2 * Mt + i] = r2.y;
   // rows of the next pair are prefetched into registers one iteration ahead
-  double2 pre0 = xin[(size_t)row_of(3) * Mt + i], pre1 = xin[(size_t)row_of(4) * Mt + i];
+  double2 pre0 = xin[j3 * Mt + i], pre1 = xin[(j3 + 1) * Mt + i];
   __syncthreads();
-  double a_q = t0_update(1, r2.x, r0.x, r1, r0); // colour 0 on the first (even) row of the chunk
+  double a_q = t0_update(old1 + Mt, old1, An + Mt, r2.x, r0.x, r1, r0); // colour 0 on the first (even) row
   const bool even_col = (i & 1) == 0;
   __syncthreads(); // the first iteration reuses the slot of logical row 0
+  int jin = j3 + 2 >= Mx ? j3 + 2 - Mx : j3 + 2; // lattice row of logical row q + 4
+  int jout = e0;                                 // lattice row of logical row q
+  int s3 = 1;                                    // q % 3
   for (int p = 0; 2 * p < nrow; ++p) {
     const int q = 1 + 2 * p; // logical index of the even row e; r1 = old row q, r2 = old row q + 1
     // The two ring slots written next held rows q - 2 and q - 1; their last readers were the
     // even-column threads of the previous iteration, before its colour-2/3 barrier.
     const double2 r3 = pre0, r4 = pre1; // old rows q + 2, q + 3
-    old[(size_t)((q + 2) & 3) * Mt + i] = r3;
-    old[(size_t)((q + 3) & 3) * Mt + i] = r4;
+    double *o_q = old1 + (q & 3) * Mt, *o_q1 = old1 + ((q + 1) & 3) * Mt, *o_q2 = old1 + ((q + 2) & 3) * Mt;
+    double *a_s = An + s3 * Mt, *a_s1 = An + (s3 == 2 ? 0 : s3 + 1) * Mt, *a_s2 = An + (s3 == 0 ? 2 : s3 - 1) * Mt;
+    o_q2[i] = r3.y;
+    old1[((q + 3) & 3) * Mt + i] = r4.y;
     if (2 * (p + 1) < nrow) {
-      pre0 = xin[(size_t)row_of(q + 4) * Mt + i];
-      pre1 = xin[(size_t)row_of(q + 5) * Mt + i];
+      pre0 = xin[jin * Mt + i];
+      pre1 = xin[(jin + 1) * Mt + i];
     }
     __syncthreads();
-    const double a_q2 = t0_update(q + 2, r4.x, r2.x, r3, r2); // colour 0, row e + 2
+    const double a_q2 = t0_update(o_q2, o_q1, a_s2, r4.x, r2.x, r3, r2); // colour 0, row e + 2
     // (no barrier: colour 1 reads old neighbours and this thread's own new theta_0 values only)
-    const double a_q1 = t0_update(q + 1, a_q2, a_q, r2, r1); // colour 1, row e + 1
+    const double a_q1 = t0_update(o_q1, o_q, a_s1, a_q2, a_q, r2, r1);   // colour 1, row e + 1
     __syncthreads();
     double b0 = 0.0, b1 = 0.0;
     if (even_col) { // colour 2 on rows e and e + 1
-      b0 = t1_update(q, 0, false, a_q, a_q1, r1.y);
-      b1 = t1_update(q + 1, 1, false, a_q1, a_q2, r2.y);
+      b0 = t1_update(o_q, a_s, a_s1, a_q, a_q1, r1.y);
+      b1 = t1_update(o_q1, a_s1, a_s2, a_q1, a_q2, r2.y);
       Bn[i] = b0;
-      Bn[(size_t)Mt + i] = b1;
+      Bn[Mt + i] = b1;
     }
     __syncthreads();
     if (!even_col) { // colour 3
-      b0 = t1_update(q, 0, true, a_q, a_q1, r1.y);
-      b1 = t1_update(q + 1, 1, true, a_q1, a_q2, r2.y);
+      b0 = t1_update(Bn, a_s, a_s1, a_q, a_q1, r1.y);
+      b1 = t1_update(Bn + Mt, a_s1, a_s2, a_q1, a_q2, r2.y);
     }
-    xout[(size_t)row_of(q) * Mt + i] = make_double2(a_q, b0);
-    xout[(size_t)row_of(q + 1) * Mt + i] = make_double2(a_q1, b1);
+    xout[jout * Mt + i] = make_double2(a_q, b0);
+    xout[(jout + 1) * Mt + i] = make_double2(a_q1, b1);
     a_q = a_q2;
     r1 = r3;
     r2 = r4;
+    jout += 2;
+    jin = jin + 2 >= Mx ? 0 : jin + 2;
+    s3 = s3 == 0 ? 2 : s3 - 1; // (q + 2) % 3
   }
 }
 
@@ -1435,7 +1442,7 @@ int overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, i
   if (sw.Mx % R != 0)
     R = sw.Mx;
   const int chunks = sw.Mx / R;
-  const size_t smem = (size_t)13 * sw.Mt * sizeof(double);
+  const size_t smem = (size_t)9 * sw.Mt * sizeof(double);
   if (smem > 48 * 1024)
     MLMCPI_CUDA(cudaFuncSetAttribute(overrelax_rowpipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
