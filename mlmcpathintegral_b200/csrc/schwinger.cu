@@ -1436,8 +1436,12 @@ int overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, i
   double *tmp = ctx_work(ctx, 1, n);
   if (!tmp)
     return MLMCPI_ENOMEM;
-  int R = 32;
+  // rows per block: 3 halo rows are re-read per chunk (64 rows: 5 % extra reads; measured best at
+  // 512^2 and 1024^2, profiles/r01_summary.md section 11), fewer when the grid would not fill the SMs
+  int R = 64;
   while (R > 2 && (sw.Mx % R != 0))
+    R /= 2;
+  while (R > 8 && (long long)(sw.Mx / R) * B < 4LL * ctx->n_sm)
     R /= 2;
   if (sw.Mx % R != 0)
     R = sw.Mx;
