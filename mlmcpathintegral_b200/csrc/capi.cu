@@ -784,6 +784,8 @@ int mlmcpi_overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x,
   if (m->model == MLMCPI_SCHWINGER && m->Mt_lat >= 2 && m->Mx_lat >= 2 && m->Mt_lat % 2 == 0 &&
       m->Mx_lat % 2 == 0)
     return schwinger::overrelax_sweeps(ctx, m, d_x, B, n_sweeps);
+  if (m->model == MLMCPI_GFF)
+    return gff::overrelax_sweeps(ctx, m, d_x, B, n_sweeps);
   for (int k = 0; k < n_sweeps; ++k) {
     const int rc = mlmcpi_overrelax_sweep(ctx, m, d_x, B);
     if (rc)
@@ -1035,7 +1037,15 @@ static int coarse_draw(mlmcpi_sampler *s, int c0, int B) {
     const int saved = ctx->sweep_reverse;
     ctx->sweep_reverse = backwards ? 1 : saved;
     rc = 0;
-    for (int pass = 0; pass < 2 && !rc; ++pass) {
+    const bool gff_sequence = m->model == MLMCPI_GFF && !ctx->sweep_reverse && m->Mt_lat % 2 == 0 && m->Mx_lat % 2 == 0;
+    if (gff_sequence) { // all sweeps of the draw ping-pong through the one-pass kernel (one copy back at most)
+      std::vector<uint64_t> hb_draws(std::max(0, s->prm.n_sweep_heatbath));
+      for (int k = 0; k < (int)hb_draws.size(); ++k)
+        hb_draws[k] = level_draw(s->draw, l, k);
+      rc = gff::sweep_sequence(ctx, m, x, B, std::max(0, s->prm.n_sweep_overrelax), (int)hb_draws.size(), chain0,
+                               hb_draws.data());
+    }
+    for (int pass = 0; pass < 2 && !rc && !gff_sequence; ++pass) {
       const bool do_hb = backwards ? (pass == 0) : (pass == 1);
       if (do_hb) {
         for (int k = 0; k < s->prm.n_sweep_heatbath && !rc; ++k) {

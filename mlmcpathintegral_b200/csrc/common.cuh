@@ -613,6 +613,8 @@ int hierarchical_draw(mlmcpi_ctx *, const mlmcpi_model *, int, int, double, doub
 }
 namespace gff {
 int exact_draw(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);
+int overrelax_sweeps(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int);
+int sweep_sequence(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int, int, uint32_t, const uint64_t *);
 }
 namespace schwinger {
 int overrelax_sweeps(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int);

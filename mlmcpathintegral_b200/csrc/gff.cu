@@ -213,6 +213,21 @@ __global__ void leapfrog_kernel(GF g, double dt_p, double dt_x, const double *x_
     x_out[t] = phi + dt_x * pn;
 }
 
+// the update of one vertex given the sum Delta over its four neighbours: heat bath
+// (qft/gffaction.cc:32-42) or overrelaxation (:68-79); one function for every sweep kernel, so that they
+// produce the same bits
+template <bool HEATBATH>
+__device__ __forceinline__ double site_update(const GF &g, const double Delta, const double phi, uint64_t seed,
+                                              uint64_t draw, uint32_t gchain, int ell) {
+  if (HEATBATH) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, gchain, ell);
+    double z0, z1;
+    rng_normal2(r, z0, z1);
+    return (1. / sqrt(4. + g.mu2)) * z0 + Delta / (4. + g.mu2);
+  }
+  return 2. * Delta / (4. + g.mu2) - phi;
+}
+
 // qft/gffaction.cc:32-42, 68-79; one colour per launch, one thread per vertex OF THAT COLOUR.
 // Unrotated level: grid (strips of half a row, rows, chains), vertex i = 2 k + ((colour + j) & 1).
 // Rotated level: the vertices of colour c (= parity of i) are the contiguous half
@@ -237,14 +252,111 @@ __global__ void sweep_colour_kernel(GF g, int colour, double *x, int B, uint32_t
   for (int chain = blockIdx.z; chain < B; chain += gridDim.z) {
     double *xc = x + (size_t)chain * g.N;
     const double Delta = nn_sum(g, xc, i, j);
-    if (HEATBATH) {
-      Rng r = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, ell);
-      double z0, z1;
-      rng_normal2(r, z0, z1);
-      xc[ell] = (1. / sqrt(4. + g.mu2)) * z0 + Delta / (4. + g.mu2);
-    } else {
-      xc[ell] = 2. * Delta / (4. + g.mu2) - xc[ell];
+    xc[ell] = site_update<HEATBATH>(g, Delta, xc[ell], seed, draw, chain0 + (uint32_t)chain, ell);
+  }
+}
+
+// One sweep (both colours, ascending order; overrelaxation or heat bath) of an UNROTATED level in ONE pass
+// over HBM, out of place.  The two colour passes above read the whole field twice to update half of it each
+// (24 B per site against the algorithmic 16 B).  Here a block of Mt/2 threads marches over R rows of one
+// chain; thread t owns the columns 2t and 2t+1 (one double2 per row: in every row one of the two is a
+// colour-0 site, the other a colour-1 site, so all lanes work in both stages).  With r the row being
+// finished: stage A = colour 0 on row r+1 (old neighbours: rows r, r+1, r+2), stage B = colour 1 on row r
+// (new colour-0 neighbours: rows r-1, r, r+1).  The column neighbours of a site are the thread's own other
+// column (register) and ONE value of an adjacent thread, exchanged through two small shared-memory rings
+// (4 x Mt/2 old colour-1 values, 2 x Mt/2 new colour-0 values); row neighbours are registers.  One barrier
+// per row.  Two rows below and two above the chunk are read in addition (their colour-0 values are
+// recomputed, not stored): 8 (1 + 4/R) B read + 8 B written per site.  Every site is updated by
+// site_update on the same operands in the same order as in sweep_colour_kernel: bit-identical.
+template <bool HEATBATH>
+__global__ void __launch_bounds__(1024)
+    sweep_rowpipe_kernel(GF g, const double *__restrict__ x_in, double *__restrict__ x_out, int R, int chunks,
+                         uint32_t chain0, uint64_t seed, uint64_t draw) {
+  extern __shared__ __align__(16) double sm_gff[];
+  const int Mt = g.Mt, Mx = g.Mx, H = Mt / 2;
+  const int t = threadIdx.x;
+  const int tp = t + 1 == H ? 0 : t + 1, tm = t == 0 ? H - 1 : t - 1;
+  const int chain = blockIdx.x / chunks, chunk = blockIdx.x - chain * chunks;
+  const int e0 = chunk * R; // even
+  const int nrow = min(R, Mx - e0);
+  const double2 *xin = reinterpret_cast<const double2 *>(x_in + (size_t)chain * g.N);
+  double2 *xout = reinterpret_cast<double2 *>(x_out + (size_t)chain * g.N);
+  double *c1val = sm_gff;                // [4][H]: old colour-1 value of this thread's pair, rows by (row & 3)
+  double *n0row = sm_gff + (size_t)4 * H; // [2][H]: new colour-0 value, rows by (row & 1)
+  const uint32_t gchain = chain0 + (uint32_t)chain;
+  auto wrap = [&](int j) { return j < 0 ? j + Mx : (j >= Mx ? j - Mx : j); };
+  // colour 0 on lattice row j (parity par = j & 1; Mx is even, so the parity survives the wrap):
+  // below / own / above = old rows j-1, j, j+1 of this thread's pair
+  // (slot = ring slot of that row: the UNWRAPPED row number & 3)
+  auto stage_a = [&](int j, int slot, int par, double2 below, double2 own, double2 above) {
+    const double *cv = c1val + (size_t)slot * H;
+    double d = 0.0;
+    if (par == 0) { // site 2t: neighbours (2t+1, j) own .y, (2t-1, j) of thread t-1, (2t, j+1), (2t, j-1)
+      d += own.y;
+      d += cv[tm];
+      d += above.x;
+      d += below.x;
+      return site_update<HEATBATH>(g, d, own.x, seed, draw, gchain, Mt * j + 2 * t);
     }
+    d += cv[tp]; // site 2t+1: neighbours (2t+2, j) of thread t+1, (2t, j) own .x
+    d += own.x;
+    d += above.y;
+    d += below.y;
+    return site_update<HEATBATH>(g, d, own.y, seed, draw, gchain, Mt * j + 2 * t + 1);
+  };
+  int jl = wrap(e0 - 2);
+  double2 o0 = xin[(size_t)jl * H + t]; // old rows e0-2, e0-1, e0, e0+1
+  jl = wrap(e0 - 1);
+  double2 o1 = xin[(size_t)jl * H + t];
+  double2 o2 = xin[(size_t)e0 * H + t];
+  double2 o3 = xin[(size_t)(e0 + 1) * H + t];
+  // (e0 - 1) is odd: its colour-1 column is 2t (.x); e0 is even: 2t+1 (.y); e0 + 1 odd: .x
+  c1val[(size_t)((e0 - 1) & 3) * H + t] = o1.x;
+  c1val[(size_t)(e0 & 3) * H + t] = o2.y;
+  c1val[(size_t)((e0 + 1) & 3) * H + t] = o3.x;
+  int jn = wrap(e0 + 2); // lattice row of the next row to load (e0 + 2 wraps to 0 at most)
+  double2 pre = xin[(size_t)jn * H + t];
+  __syncthreads();
+  double nm1 = stage_a(wrap(e0 - 1), (e0 - 1) & 3, 1, o0, o1, o2); // new colour-0 values of rows e0-1 and e0
+  double n0 = stage_a(e0, e0 & 3, 0, o1, o2, o3);
+  n0row[(size_t)(e0 & 1) * H + t] = n0;
+  __syncthreads();
+  // loop invariant for output row r: o2 = old(r), o3 = old(r+1), pre = old(r+2), nm1 / n0 = new colour 0 of
+  // rows r-1 / r; c1val holds rows r-1 .. r+1, n0row row r
+  for (int k = 0; k < nrow; ++k) {
+    const int r = e0 + k, par = k & 1; // e0 even: parity of r
+    const double2 o4 = pre;            // old row r + 2
+    c1val[(size_t)((r + 2) & 3) * H + t] = par == 0 ? o4.y : o4.x;
+    if (k + 1 < nrow) {
+      jn = jn + 1 == Mx ? 0 : jn + 1;
+      pre = xin[(size_t)jn * H + t];
+    }
+    const int r1 = r + 1 == Mx ? 0 : r + 1;
+    const double n1 = stage_a(r1, (r + 1) & 3, par ^ 1, o2, o3, o4); // colour 0 on row r + 1
+    n0row[(size_t)((r + 1) & 1) * H + t] = n1;
+    // colour 1 on row r: the new colour-0 neighbours
+    const double *nr = n0row + (size_t)(r & 1) * H;
+    double d = 0.0, m;
+    if (par == 0) { // site 2t+1: (2t+2, r) of thread t+1, (2t, r) own, (2t+1, r+1), (2t+1, r-1)
+      d += nr[tp];
+      d += n0;
+      d += n1;
+      d += nm1;
+      m = site_update<HEATBATH>(g, d, o2.y, seed, draw, gchain, Mt * r + 2 * t + 1);
+      xout[(size_t)r * H + t] = make_double2(n0, m);
+    } else { // site 2t: (2t+1, r) own, (2t-1, r) of thread t-1
+      d += n0;
+      d += nr[tm];
+      d += n1;
+      d += nm1;
+      m = site_update<HEATBATH>(g, d, o2.x, seed, draw, gchain, Mt * r + 2 * t);
+      xout[(size_t)r * H + t] = make_double2(m, n0);
+    }
+    __syncthreads();
+    o2 = o3;
+    o3 = o4;
+    nm1 = n0;
+    n0 = n1;
   }
 }
 
@@ -713,6 +825,54 @@ static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool 
     MLMCPI_LAUNCHED("gff::sweep_colour");
   }
   return 0;
+}
+// n_or overrelaxation sweeps followed by n_hb heat-bath sweeps (draw counters hb_draws[k]): the one-pass
+// kernel on unrotated levels with even extents (ascending colour order), ping-ponging between x and a
+// work buffer, one copy back when the number of sweeps is odd; otherwise two colour passes per sweep.
+int sweep_sequence(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, int n_or, int n_hb, uint32_t chain0,
+                   const uint64_t *hb_draws) {
+  GF g = make_gf(m);
+  const bool one_pass = !ctx->sweep_reverse && ctx->overrelax_one_pass && !g.rotated && g.Mt % 2 == 0 &&
+                        g.Mx % 2 == 0 && g.Mt >= 64 && g.Mt <= 2048 && g.Mx >= 4;
+  if (!one_pass) {
+    int rc = 0;
+    for (int k = 0; k < n_or && !rc; ++k)
+      rc = sweep(ctx, m, x, B, false, 0, 0);
+    for (int k = 0; k < n_hb && !rc; ++k)
+      rc = sweep(ctx, m, x, B, true, chain0, hb_draws[k]);
+    return rc;
+  }
+  if (n_or + n_hb == 0)
+    return 0;
+  const size_t n = (size_t)g.N * B;
+  double *tmp = ctx_work(ctx, 1, n);
+  if (!tmp)
+    return MLMCPI_ENOMEM;
+  int R = 64;
+  while (R > 2 && g.Mx % R != 0)
+    R /= 2;
+  while (R > 8 && (long long)(g.Mx / R) * B < 4LL * ctx->n_sm)
+    R /= 2;
+  const int chunks = g.Mx / R, H = g.Mt / 2;
+  const size_t smem = (size_t)6 * H * sizeof(double);
+  double *src = x, *dst = tmp;
+  for (int k = 0; k < n_or + n_hb; ++k) {
+    if (k < n_or)
+      sweep_rowpipe_kernel<false><<<chunks * B, H, smem, ctx->stream>>>(g, src, dst, R, chunks, 0, 0, 0);
+    else
+      sweep_rowpipe_kernel<true><<<chunks * B, H, smem, ctx->stream>>>(g, src, dst, R, chunks, chain0, ctx->seed,
+                                                                         hb_draws[k - n_or]);
+    MLMCPI_LAUNCHED("gff::sweep_rowpipe");
+    std::swap(src, dst);
+  }
+  if (src != x)
+    MLMCPI_CUDA(cudaMemcpyAsync(x, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+int overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, int n_sweeps) {
+  if (m->Mt_lat % 2 || m->Mx_lat % 2)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need even lattice extents");
+  return sweep_sequence(ctx, m, x, B, n_sweeps, 0, 0, nullptr);
 }
 int overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B) {
   return sweep(ctx, m, x, B, false, 0, 0);
