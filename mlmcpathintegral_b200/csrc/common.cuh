@@ -164,6 +164,15 @@ __device__ __forceinline__ double div_pi(const double u) {
   r = fma(-q, M_PI, u);
   return fma(r, c, q);
 }
+// the same for a divisor b known at run time with c = RN(1 / b) (computed once per thread: the callers'
+// divisor is a kernel argument): u / b, correctly rounded
+__device__ __forceinline__ double div_exact(const double u, const double b, const double c) {
+  double q = u * c;
+  double r = fma(-q, b, u);
+  q = fma(r, c, q);
+  r = fma(-q, b, u);
+  return fma(r, c, q);
+}
 __device__ __forceinline__ double mod_2pi(const double x) {
   return x - 2. * M_PI * floor(div_pi(0.5 * (x + M_PI)));
 }

@@ -223,9 +223,9 @@ __device__ __forceinline__ double site_update(const GF &g, const double Delta, c
     Rng r = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, gchain, ell);
     double z0, z1;
     rng_normal2(r, z0, z1);
-    return (1. / sqrt(4. + g.mu2)) * z0 + Delta / (4. + g.mu2);
+    return (1. / sqrt(4. + g.mu2)) * z0 + div_exact(Delta, 4. + g.mu2, 1. / (4. + g.mu2));
   }
-  return 2. * Delta / (4. + g.mu2) - phi;
+  return div_exact(2. * Delta, 4. + g.mu2, 1. / (4. + g.mu2)) - phi;
 }
 
 // qft/gffaction.cc:32-42, 68-79; one colour per launch, one thread per vertex OF THAT COLOUR.
@@ -314,8 +314,11 @@ __global__ void __launch_bounds__(1024)
   c1val[(size_t)((e0 - 1) & 3) * H + t] = o1.x;
   c1val[(size_t)(e0 & 3) * H + t] = o2.y;
   c1val[(size_t)((e0 + 1) & 3) * H + t] = o3.x;
-  int jn = wrap(e0 + 2); // lattice row of the next row to load (e0 + 2 wraps to 0 at most)
+  // two rows are kept in flight per thread
+  int jn = wrap(e0 + 2); // lattice row of the last row requested (e0 + 2 wraps to 0 at most)
   double2 pre = xin[(size_t)jn * H + t];
+  jn = jn + 1 == Mx ? 0 : jn + 1;
+  double2 pre2 = xin[(size_t)jn * H + t]; // row e0 + 3
   __syncthreads();
   double nm1 = stage_a(wrap(e0 - 1), (e0 - 1) & 3, 1, o0, o1, o2); // new colour-0 values of rows e0-1 and e0
   double n0 = stage_a(e0, e0 & 3, 0, o1, o2, o3);
@@ -327,9 +330,10 @@ __global__ void __launch_bounds__(1024)
     const int r = e0 + k, par = k & 1; // e0 even: parity of r
     const double2 o4 = pre;            // old row r + 2
     c1val[(size_t)((r + 2) & 3) * H + t] = par == 0 ? o4.y : o4.x;
-    if (k + 1 < nrow) {
+    pre = pre2;
+    if (k + 2 < nrow) { // row r + 4, the "row r + 2" of iteration k + 2
       jn = jn + 1 == Mx ? 0 : jn + 1;
-      pre = xin[(size_t)jn * H + t];
+      pre2 = xin[(size_t)jn * H + t];
     }
     const int r1 = r + 1 == Mx ? 0 : r + 1;
     const double n1 = stage_a(r1, (r + 1) & 3, par ^ 1, o2, o3, o4); // colour 0 on row r + 1

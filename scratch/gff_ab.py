@@ -10,7 +10,7 @@ def timeit(f, n=5):
     for _ in range(n): f()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/n
-for (Mt,Mx,B) in ((256,256,512),(512,512,128),(64,6,300),(128,64,2048),(1024,1024,32)):
+for (Mt,Mx,B) in ((256,256,512),(256,256,666),(256,256,333),(256,256,1024),(512,512,128)):
     m=mp.gff(Mt,Mx,10.0)
     x0=ctx.init_state(m,B,0,1)
     res={}
