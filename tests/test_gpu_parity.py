@@ -676,6 +676,36 @@ def test_overrelax_one_pass_equals_colour_passes(mp, ctx):
     ang_close(outs[0], outs[1], tol=1e-12, what="sampler with one-pass overrelaxation")
 
 
+def test_gff_one_pass_sweeps_equal_colour_passes(mp, ctx):
+    """the one-pass row-pipelined GFF sweep (both colours, two columns per thread, out of place) gives the bits
+    of the two colour passes: overrelaxation (odd and even numbers of sweeps: with and without the copy back),
+    and overrelaxation + heat-bath sequences inside the sampler, for chunked, wrapped and narrow lattices"""
+    for Mt, Mx, B in [(64, 4, 3), (64, 6, 5), (128, 64, 4), (256, 256, 3), (96, 34, 2), (2048, 8, 1), (32, 32, 2)]:
+        m = mp.gff(Mt, Mx, 10.0)
+        x0 = ctx.init_state(m, B, 0, 3)
+        for n in (3, 4):
+            outs = []
+            for one_pass in (0, 1):
+                ctx.set_option(mp._lib.OPT_OVERRELAX_ONE_PASS, one_pass)
+                x = x0.clone()
+                ctx.overrelax_sweeps(m, x, n)
+                outs.append(x)
+            assert bool((outs[0] == outs[1]).all()), (Mt, Mx, n)
+            assert not bool((outs[0] == x0).all())
+        outs = []
+        for one_pass in (0, 1):
+            ctx.set_option(mp._lib.OPT_OVERRELAX_ONE_PASS, one_pass)
+            smp = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HEATBATH, n_sweep_overrelax=2, n_sweep_heatbath=2)
+            x = x0.clone()
+            smp.set_state(x)
+            for _ in range(3):
+                smp.draw(x)
+            outs.append(x.clone())
+            smp.close()
+        ctx.set_option(mp._lib.OPT_OVERRELAX_ONE_PASS, 1)
+        assert bool((outs[0] == outs[1]).all()), (Mt, Mx, "sampler")
+
+
 def test_fused_qm_hierarchy_equals_kernel_sequence(mp, ctx):
     """HierarchicalSampler::draw for 1-D paths as ONE kernel (one warp per chain, all levels on chip)
     against the sequence of single-purpose kernels: same states, same acceptance counters"""
