@@ -38,14 +38,20 @@ GF make_gf(const mlmcpi_model *m) {
 }
 
 // lattice/lattice2d.hh:230-245 (i, j may be out of range by less than one period)
+// (the periodic wraps are conditional subtractions, not integer remainders: i and j are at most one
+// lattice spacing outside [0, Mt) x [0, Mx) -- a remainder by a run-time divisor costs ~25 instructions
+// and nn_sum needs eight of them per vertex)
+__device__ __forceinline__ int wrap_period(int v, int M) { return v < 0 ? v + M : (v >= M ? v - M : v); }
 __device__ __forceinline__ int v_cart2lin(int Mt, int Mx, int rotated, int i, int j) {
   if (rotated) {
     const int Mth = Mt / 2, Mxh = Mx / 2;
-    const int is = ((i + Mt) - (i & 1)) / 2;
-    const int js = ((j + Mx) - (j & 1)) / 2;
-    return Mth * (js % Mxh) + is % Mth + (Mt * Mx / 4) * (i & 1);
+    int is = ((i + Mt) - (i & 1)) >> 1; // in [Mth - 1, 2 Mth]
+    int js = ((j + Mx) - (j & 1)) >> 1;
+    is = is >= 2 * Mth ? is - 2 * Mth : (is >= Mth ? is - Mth : is);
+    js = js >= 2 * Mxh ? js - 2 * Mxh : (js >= Mxh ? js - Mxh : js);
+    return Mth * js + is + (Mt * Mx / 4) * (i & 1);
   }
-  return Mt * ((j + Mx) % Mx) + ((i + Mt) % Mt);
+  return Mt * wrap_period(j, Mx) + wrap_period(i, Mt);
 }
 // lattice/lattice2d.hh:255-268
 __device__ __forceinline__ void v_lin2cart(int Mt, int Mx, int rotated, int ell, int &i, int &j) {
@@ -117,7 +123,8 @@ __device__ __forceinline__ bool is_coarse(const GF &g, int i, int j, int &rho_t,
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;                            \
   if (t >= (long long)g.N * B)                                                                     \
     return;                                                                                        \
-  const long long chain = t / g.N;                                                                 \
+  /* a 64-bit division costs ~60 instructions: 32-bit whenever the index fits */                  \
+  const long long chain = t < 0x7fffffffLL ? (long long)((unsigned)t / (unsigned)g.N) : t / g.N;   \
   const int ell = (int)(t - chain * g.N);                                                          \
   int i, j;                                                                                        \
   v_lin2cart(g.Mt, g.Mx, g.rotated, ell, i, j);
