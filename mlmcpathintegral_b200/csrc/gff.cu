@@ -119,15 +119,37 @@ __device__ __forceinline__ bool is_coarse(const GF &g, int i, int j, int &rho_t,
   return (i % rho_t == 0) && (j % rho_x == 0);
 }
 
-#define VERTEX_SETUP                                                                               \
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;                            \
-  if (t >= (long long)g.N * B)                                                                     \
+// One thread per vertex without integer divisions: grid (strips of a row, rows, chains).  On an
+// unrotated level row y is lattice row j = y (ell = Mt j + i); on a rotated level the reference's index
+// range is the even-even block followed by the odd-odd block (lattice2d.hh:230-245), each made of Mx/2
+// rows of Mt/2 vertices: row y has parity p = (y >= Mx/2), j = 2 (y - p Mx/2) + p, i = 2 k + p.
+// The body runs once per chain of the thread's z-slice; `t` is the index into a [chain][ell] array.
+__device__ __forceinline__ bool vertex_of(const GF &g, int k, int y, int &i, int &j, int &ell) {
+  if (g.rotated) {
+    const int Mth = g.Mt / 2, Mxh = g.Mx / 2;
+    const int par = y >= Mxh ? 1 : 0, jh = y - par * Mxh;
+    i = 2 * k + par;
+    j = 2 * jh + par;
+    ell = (g.Mt * g.Mx / 4) * par + Mth * jh + k;
+    return k < Mth;
+  }
+  i = k;
+  j = y;
+  ell = g.Mt * y + k;
+  return k < g.Mt;
+}
+#define VERTEX_LOOP_BEGIN                                                                          \
+  int i, j, ell;                                                                                   \
+  if (!vertex_of(g, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, i, j, ell))                 \
     return;                                                                                        \
-  /* a 64-bit division costs ~60 instructions: 32-bit whenever the index fits */                  \
-  const long long chain = t < 0x7fffffffLL ? (long long)((unsigned)t / (unsigned)g.N) : t / g.N;   \
-  const int ell = (int)(t - chain * g.N);                                                          \
-  int i, j;                                                                                        \
-  v_lin2cart(g.Mt, g.Mx, g.rotated, ell, i, j);
+  for (long long chain = blockIdx.z; chain < B; chain += gridDim.z) {                              \
+    const long long t = chain * g.N + ell;
+#define VERTEX_LOOP_END }
+#define VERTEX_THREADS 128
+static inline dim3 vertex_grid(const GF &g, int B) {
+  const int rowlen = g.rotated ? g.Mt / 2 : g.Mt;
+  return dim3((unsigned)cdiv(rowlen, VERTEX_THREADS), (unsigned)g.Mx, (unsigned)std::min(B, 65535));
+}
 
 // start state: i.i.d. N(0, 1/(4+mu2)) (the reference draws exactly from the
 // Gaussian by sparse Cholesky, qft/gffaction.cc:121-123, 200-213: SURVEY 8f-3)
@@ -169,9 +191,7 @@ __global__ void momentum_kernel(GF g, double *p, int B, uint32_t chain0, uint64_
 struct ActionF { // qft/gffaction.cc:7-24
   GF g;
   const double *x;
-  __device__ void operator()(int chain, long long ell, double acc[1]) const {
-    int i, j;
-    v_lin2cart(g.Mt, g.Mx, g.rotated, (int)ell, i, j);
+  __device__ void operator()(int chain, int i, int j, int ell, double acc[1]) const {
     const double *xc = x + (size_t)chain * g.N;
     const double phi = xc[ell];
     acc[0] += phi * ((4. + g.mu2) * phi - nn_sum(g, xc, i, j));
@@ -180,7 +200,7 @@ struct ActionF { // qft/gffaction.cc:7-24
 struct Phi2F { // qoi/qft/qoi2dphisquared.cc:7-15
   GF g;
   const double *x;
-  __device__ void operator()(int chain, long long ell, double acc[1]) const {
+  __device__ void operator()(int chain, int, int, int ell, double acc[1]) const {
     const double phi = x[(size_t)chain * g.N + ell];
     acc[0] += phi * phi;
   }
@@ -188,9 +208,8 @@ struct Phi2F { // qoi/qft/qoi2dphisquared.cc:7-15
 struct CondF { // qft/gffconditionedfineaction.cc:28-50
   GF g;
   const double *x;
-  __device__ void operator()(int chain, long long ell, double acc[1]) const {
-    int i, j, rt, rx;
-    v_lin2cart(g.Mt, g.Mx, g.rotated, (int)ell, i, j);
+  __device__ void operator()(int chain, int i, int j, int ell, double acc[1]) const {
+    int rt, rx;
     if (is_coarse(g, i, j, rt, rx))
       return;
     const double *xc = x + (size_t)chain * g.N;
@@ -200,17 +219,50 @@ struct CondF { // qft/gffconditionedfineaction.cc:28-50
   }
 };
 
+// pass 1 of the deterministic two-pass reductions (common.cuh) over the vertices of a level, row by row
+// without integer divisions (vertex_of): block (blk, chain) sums the rows blk, blk + nblk, ...
+template <class F>
+__global__ void vertex_reduce_kernel(F f, GF g, int nblk, int B, double *partial) {
+  const int blk = blockIdx.x, chain = blockIdx.y;
+  const int rowlen = g.rotated ? g.Mt / 2 : g.Mt;
+  double acc[1] = {0.0};
+  for (int y = blk; y < g.Mx; y += nblk)
+    for (int k = threadIdx.x; k < rowlen; k += blockDim.x) {
+      int i, j, ell;
+      vertex_of(g, k, y, i, j, ell);
+      f(chain, i, j, ell, acc);
+    }
+  const double v = block_sum(acc[0]);
+  if (threadIdx.x == 0)
+    partial[(size_t)chain * nblk + blk] = v;
+}
+template <class F>
+int vertex_reduce(mlmcpi_ctx *ctx, const char *what, F f, const GF &g, int B, double scale, double *out) {
+  const int rowlen = g.rotated ? g.Mt / 2 : g.Mt;
+  const int threads = std::min(256, std::max(32, ((rowlen + 31) / 32) * 32));
+  int nblk = std::min(g.Mx, std::max(1, cdiv((long long)ctx->n_sm * 8, B)));
+  if (B > 65535)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "more than 65535 chains in a GFF reduction");
+  double *partial = ctx_scratch(ctx, (size_t)B * nblk);
+  if (!partial)
+    return MLMCPI_ENOMEM;
+  vertex_reduce_kernel<F><<<dim3(nblk, B), threads, 0, ctx->stream>>>(f, g, nblk, B, partial);
+  MLMCPI_LAUNCHED(what);
+  return launch_reduce_finish(ctx, partial, nblk, B, 1, EPI_SCALE, scale, 1.0, out, nullptr);
+}
+
 // qft/gffaction.cc:82-94
 __global__ void force_kernel(GF g, const double *x, double *f, int B) {
-  VERTEX_SETUP
+  VERTEX_LOOP_BEGIN
   const double *xc = x + chain * g.N;
   f[t] = (4. + g.mu2) * xc[ell] - nn_sum(g, xc, i, j);
+  VERTEX_LOOP_END
 }
 
 // sampler/hmcsampler.cc:43-45 fused (ping-pong phi buffers)
 __global__ void leapfrog_kernel(GF g, double dt_p, double dt_x, const double *x_in, double *x_out,
                                 double *p, int B) {
-  VERTEX_SETUP
+  VERTEX_LOOP_BEGIN
   const double *xc = x_in + chain * g.N;
   const double phi = xc[ell];
   const double F = (4. + g.mu2) * phi - nn_sum(g, xc, i, j);
@@ -218,6 +270,7 @@ __global__ void leapfrog_kernel(GF g, double dt_p, double dt_x, const double *x_
   p[t] = pn;
   if (x_out)
     x_out[t] = phi + dt_x * pn;
+  VERTEX_LOOP_END
 }
 
 // the update of one vertex given the sum Delta over its four neighbours: heat bath
@@ -375,23 +428,24 @@ __global__ void __launch_bounds__(1024)
 template <bool TO_FINE>
 __global__ void transfer_kernel(GF g, int Mtc, int Mxc, int rotc, int Nc, const double *src,
                                 double *dst, int B) {
-  VERTEX_SETUP
+  VERTEX_LOOP_BEGIN
   int rt, rx;
   if (!is_coarse(g, i, j, rt, rx))
-    return;
-  const int ellc = v_cart2lin(Mtc, Mxc, rotc, i / rt, j / rx);
+    return; // (the same for every chain)
+  const int ellc = v_cart2lin(Mtc, Mxc, rotc, rt == 2 ? i >> 1 : i, rx == 2 ? j >> 1 : j);
   if (TO_FINE)
     dst[t] = src[chain * Nc + ellc];
   else
     dst[chain * Nc + ellc] = src[t];
+  VERTEX_LOOP_END
 }
 
 // qft/gffconditionedfineaction.cc:7-25
 __global__ void fill_kernel(GF g, double *x, int B, uint32_t chain0, uint64_t seed, uint64_t draw) {
-  VERTEX_SETUP
+  VERTEX_LOOP_BEGIN
   int rt, rx;
   if (is_coarse(g, i, j, rt, rx))
-    return;
+    return; // (the same for every chain)
   double *xc = x + chain * g.N;
   const double Delta = nn_sum(g, xc, i, j);
   Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, chain0 + (uint32_t)chain, ell);
@@ -399,6 +453,7 @@ __global__ void fill_kernel(GF g, double *x, int B, uint32_t chain0, uint64_t se
   rng_normal2(r, z0, z1);
   const double sigma = 1. / sqrt(4. + g.mu2);
   xc[ell] = sigma * (z0 + sigma * Delta);
+  VERTEX_LOOP_END
 }
 
 int coarse_dims(mlmcpi_ctx *ctx, const mlmcpi_model *m, int *Mtc, int *Mxc, int *rotc) {
@@ -418,7 +473,7 @@ int check_rotate(mlmcpi_ctx *ctx, const mlmcpi_model *m) {
 
 int step(mlmcpi_ctx *ctx, const GF &g, double dt_p, double dt_x, bool drift, const double *in,
          double *out, double *p, int B) {
-  leapfrog_kernel<<<cdiv((long long)g.N * B, 256), 256, 0, ctx->stream>>>(g, dt_p, dt_x, in,
+  leapfrog_kernel<<<vertex_grid(g, B), VERTEX_THREADS, 0, ctx->stream>>>(g, dt_p, dt_x, in,
                                                                          drift ? out : nullptr, p, B);
   MLMCPI_LAUNCHED("gff::leapfrog");
   return 0;
@@ -732,7 +787,7 @@ int action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, doubl
     MLMCPI_LAUNCHED("gff::dense_action");
     return 0;
   }
-  return site_reduce<1>(ctx, "gff::action", ActionF{g, x}, g.N, B, EPI_SCALE, 0.5, 0.0, S, nullptr);
+  return vertex_reduce(ctx, "gff::action", ActionF{g, x}, g, B, 0.5, S);
 }
 
 // GFFAction::draw, qft/gffaction.cc:200-213
@@ -755,7 +810,7 @@ int exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_
 
 int force(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, double *f, int B) {
   GF g = make_gf(m);
-  force_kernel<<<cdiv((long long)g.N * B, 256), 256, 0, ctx->stream>>>(g, x, f, B);
+  force_kernel<<<vertex_grid(g, B), VERTEX_THREADS, 0, ctx->stream>>>(g, x, f, B);
   MLMCPI_LAUNCHED("gff::force");
   return 0;
 }
@@ -899,7 +954,7 @@ int prolong(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x,
     return rc;
   GF g = make_gf(m);
   const int Nc = rotc ? Mtc * Mxc / 2 : Mtc * Mxc;
-  transfer_kernel<true><<<cdiv((long long)g.N * B, 256), 256, 0, ctx->stream>>>(g, Mtc, Mxc, rotc, Nc,
+  transfer_kernel<true><<<vertex_grid(g, B), VERTEX_THREADS, 0, ctx->stream>>>(g, Mtc, Mxc, rotc, Nc,
                                                                                xc, x, B);
   MLMCPI_LAUNCHED("gff::prolong");
   return 0;
@@ -911,7 +966,7 @@ int restrict_(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xf, double *
     return rc;
   GF g = make_gf(m);
   const int Nc = rotc ? Mtc * Mxc / 2 : Mtc * Mxc;
-  transfer_kernel<false><<<cdiv((long long)g.N * B, 256), 256, 0, ctx->stream>>>(g, Mtc, Mxc, rotc,
+  transfer_kernel<false><<<vertex_grid(g, B), VERTEX_THREADS, 0, ctx->stream>>>(g, Mtc, Mxc, rotc,
                                                                                 Nc, xf, xc, B);
   MLMCPI_LAUNCHED("gff::restrict");
   return 0;
@@ -922,7 +977,7 @@ int fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chai
   if (rc)
     return rc;
   GF g = make_gf(m);
-  fill_kernel<<<cdiv((long long)g.N * B, 256), 256, 0, ctx->stream>>>(g, x, B, chain0, ctx->seed,
+  fill_kernel<<<vertex_grid(g, B), VERTEX_THREADS, 0, ctx->stream>>>(g, x, B, chain0, ctx->seed,
                                                                      draw);
   MLMCPI_LAUNCHED("gff::fill");
   return 0;
@@ -941,8 +996,7 @@ int cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, 
   if (rc)
     return rc;
   GF g = make_gf(m);
-  return site_reduce<1>(ctx, "gff::cond_action", CondF{g, x}, g.N, B, EPI_SCALE, 1.0, 0.0, S,
-                        nullptr);
+  return vertex_reduce(ctx, "gff::cond_action", CondF{g, x}, g, B, 1.0, S);
 }
 
 // prolongation + fill-in followed by S(theta') and S_cond(theta') into S_out[2][B]
@@ -962,8 +1016,7 @@ int qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int which, const double *x, int 
   if (which != MLMCPI_QOI_PHI2)
     return ctx_fail(ctx, MLMCPI_EINVAL, "QoI not defined for the GFF model");
   GF g = make_gf(m);
-  return site_reduce<1>(ctx, "gff::qoi_phi2", Phi2F{g, x}, g.N, B, EPI_SCALE, 1.0 / g.N, 0.0, out,
-                        nullptr);
+  return vertex_reduce(ctx, "gff::qoi_phi2", Phi2F{g, x}, g, B, 1.0 / g.N, out);
 }
 
 } // namespace gff

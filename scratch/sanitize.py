@@ -23,3 +23,13 @@ gg=mp.gff(32,32,10.0); xg=ctx.init_state(gg,3,0,0); ctx.overrelax_sweep(gg,xg); 
 g1=mp.coarse_model(gg,ctype=mp.COARSEN_ROTATE); g1.gff_n_gibbs=0; x1=ctx.init_state(g1,3,0,0); ctx.overrelax_sweep(g1,x1); ctx.heatbath_sweep(g1,x1,0,1)
 m=mp.schwinger(12,20,2.0); x=ctx.init_state(m,3,0,1); ctx.heatbath_sweep(m,x,0,1)
 ctx.sync(); print("sanitize workload done")
+# end of round: one-pass GFF sweeps (OR + HB sequences, wrapped / chunked shapes), larger one-pass Schwinger OR,
+# GFF hierarchical cascade on the cheaper index maps
+for Mt,Mx,B in ((64,4,2),(64,6,3),(128,64,2),(96,34,1),(256,128,1)):
+    gm=mp.gff(Mt,Mx,10.0); xg=ctx.init_state(gm,B,0,0); ctx.overrelax_sweeps(gm,xg,3)
+    sg=mp.Sampler(ctx,gm,B,kind=mp.SAMPLER_HEATBATH,n_sweep_overrelax=2,n_sweep_heatbath=1); sg.set_state(xg); sg.draw(xg); sg.draw(xg); sg.close()
+for Mt,Mx,B in ((512,128,1),(1024,64,1),(64,128,2)):
+    m=mp.schwinger(Mt,Mx,2.0); x=ctx.init_state(m,B,0,1); ctx.overrelax_sweeps(m,x,2)
+gh=mp.gff(32,32,10.0); sh=mp.Sampler(ctx,gh,5,kind=mp.SAMPLER_HEATBATH,n_levels=3,ctype=mp.COARSEN_ROTATE,n_sweep_overrelax=1,n_sweep_heatbath=1)
+xh=ctx.init_state(gh,5,0,0); sh.set_state(xh); sh.draw(xh); sh.draw(xh)
+ctx.sync(); print("sanitize workload 2 done")
