@@ -138,6 +138,22 @@ __device__ __forceinline__ bool vertex_of(const GF &g, int k, int y, int &i, int
   ell = g.Mt * y + k;
   return k < g.Mt;
 }
+// the FINE-ONLY vertices of a level under CoarsenRotate (lattice2d.cc:20-110): on an unrotated level the
+// vertices with i + j odd (half of every row), on a rotated level the odd-odd block (the second half of
+// the index range).  Rows of Mt/2 vertices each; Mx (unrotated) or Mx/2 (rotated) rows.
+__device__ __forceinline__ bool fine_vertex_of(const GF &g, int k, int y, int &i, int &j, int &ell) {
+  const int Mth = g.Mt / 2;
+  if (g.rotated) {
+    i = 2 * k + 1;
+    j = 2 * y + 1;
+    ell = g.Mt * g.Mx / 4 + Mth * y + k;
+  } else {
+    i = 2 * k + ((y + 1) & 1);
+    j = y;
+    ell = g.Mt * y + i;
+  }
+  return k < Mth;
+}
 #define VERTEX_LOOP_BEGIN                                                                          \
   int i, j, ell;                                                                                   \
   if (!vertex_of(g, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, i, j, ell))                 \
@@ -221,24 +237,29 @@ struct CondF { // qft/gffconditionedfineaction.cc:28-50
 
 // pass 1 of the deterministic two-pass reductions (common.cuh) over the vertices of a level, row by row
 // without integer divisions (vertex_of): block (blk, chain) sums the rows blk, blk + nblk, ...
-template <class F>
+// FINE_ONLY: the fine-only vertices of CoarsenRotate (fine_vertex_of)
+template <class F, bool FINE_ONLY>
 __global__ void vertex_reduce_kernel(F f, GF g, int nblk, int B, double *partial) {
   const int blk = blockIdx.x, chain = blockIdx.y;
-  const int rowlen = g.rotated ? g.Mt / 2 : g.Mt;
+  const int rowlen = (g.rotated || FINE_ONLY) ? g.Mt / 2 : g.Mt;
+  const int nrows = (FINE_ONLY && g.rotated) ? g.Mx / 2 : g.Mx;
   double acc[1] = {0.0};
-  for (int y = blk; y < g.Mx; y += nblk)
+  for (int y = blk; y < nrows; y += nblk)
     for (int k = threadIdx.x; k < rowlen; k += blockDim.x) {
       int i, j, ell;
-      vertex_of(g, k, y, i, j, ell);
+      if (FINE_ONLY)
+        fine_vertex_of(g, k, y, i, j, ell);
+      else
+        vertex_of(g, k, y, i, j, ell);
       f(chain, i, j, ell, acc);
     }
   const double v = block_sum(acc[0]);
   if (threadIdx.x == 0)
     partial[(size_t)chain * nblk + blk] = v;
 }
-template <class F>
+template <class F, bool FINE_ONLY = false>
 int vertex_reduce(mlmcpi_ctx *ctx, const char *what, F f, const GF &g, int B, double scale, double *out) {
-  const int rowlen = g.rotated ? g.Mt / 2 : g.Mt;
+  const int rowlen = (g.rotated || FINE_ONLY) ? g.Mt / 2 : g.Mt;
   const int threads = std::min(256, std::max(32, ((rowlen + 31) / 32) * 32));
   int nblk = std::min(g.Mx, std::max(1, cdiv((long long)ctx->n_sm * 8, B)));
   if (B > 65535)
@@ -246,7 +267,7 @@ int vertex_reduce(mlmcpi_ctx *ctx, const char *what, F f, const GF &g, int B, do
   double *partial = ctx_scratch(ctx, (size_t)B * nblk);
   if (!partial)
     return MLMCPI_ENOMEM;
-  vertex_reduce_kernel<F><<<dim3(nblk, B), threads, 0, ctx->stream>>>(f, g, nblk, B, partial);
+  vertex_reduce_kernel<F, FINE_ONLY><<<dim3(nblk, B), threads, 0, ctx->stream>>>(f, g, nblk, B, partial);
   MLMCPI_LAUNCHED(what);
   return launch_reduce_finish(ctx, partial, nblk, B, 1, EPI_SCALE, scale, 1.0, out, nullptr);
 }
@@ -438,6 +459,23 @@ __global__ void transfer_kernel(GF g, int Mtc, int Mxc, int rotc, int Nc, const 
   else
     dst[chain * Nc + ellc] = src[t];
   VERTEX_LOOP_END
+}
+
+// qft/gffconditionedfineaction.cc:7-25 for CoarsenRotate: one thread per FINE vertex (the generic kernel
+// below leaves every other lane idle on the checkerboard)
+__global__ void fill_rotate_kernel(GF g, double *x, int B, uint32_t chain0, uint64_t seed, uint64_t draw) {
+  int i, j, ell;
+  if (!fine_vertex_of(g, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, i, j, ell))
+    return;
+  const double sigma = 1. / sqrt(4. + g.mu2);
+  for (long long chain = blockIdx.z; chain < B; chain += gridDim.z) {
+    double *xc = x + chain * g.N;
+    const double Delta = nn_sum(g, xc, i, j);
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, chain0 + (uint32_t)chain, ell);
+    double z0, z1;
+    rng_normal2(r, z0, z1);
+    xc[ell] = sigma * (z0 + sigma * Delta);
+  }
 }
 
 // qft/gffconditionedfineaction.cc:7-25
@@ -977,8 +1015,13 @@ int fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chai
   if (rc)
     return rc;
   GF g = make_gf(m);
-  fill_kernel<<<vertex_grid(g, B), VERTEX_THREADS, 0, ctx->stream>>>(g, x, B, chain0, ctx->seed,
-                                                                     draw);
+  if (g.ctype == MLMCPI_COARSEN_ROTATE) {
+    const dim3 grid((unsigned)cdiv(g.Mt / 2, VERTEX_THREADS), (unsigned)(g.rotated ? g.Mx / 2 : g.Mx),
+                    (unsigned)std::min(B, 65535));
+    fill_rotate_kernel<<<grid, VERTEX_THREADS, 0, ctx->stream>>>(g, x, B, chain0, ctx->seed, draw);
+  } else {
+    fill_kernel<<<vertex_grid(g, B), VERTEX_THREADS, 0, ctx->stream>>>(g, x, B, chain0, ctx->seed, draw);
+  }
   MLMCPI_LAUNCHED("gff::fill");
   return 0;
 }
@@ -996,6 +1039,8 @@ int cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, 
   if (rc)
     return rc;
   GF g = make_gf(m);
+  if (g.ctype == MLMCPI_COARSEN_ROTATE) // every other vertex is coarse: visit the fine ones only
+    return vertex_reduce<CondF, true>(ctx, "gff::cond_action", CondF{g, x}, g, B, 1.0, S);
   return vertex_reduce(ctx, "gff::cond_action", CondF{g, x}, g, B, 1.0, S);
 }
 
