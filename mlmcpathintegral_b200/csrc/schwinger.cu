@@ -200,9 +200,9 @@ __global__ void force_kernel(SW sw, const double *x, double *f, int B) {
   const int s = (int)(t - chain * nsite);
   const int j = s / Mt, i = s - j * Mt;
   const double *xc = x + chain * 2 * nsite;
-  const double F = sw.beta * sin(plaq(xc, Mt, Mx, i, j));
-  const double Fjm = sw.beta * sin(plaq(xc, Mt, Mx, i, wrap_dec(j, Mx)));
-  const double Fim = sw.beta * sin(plaq(xc, Mt, Mx, wrap_dec(i, Mt), j));
+  const double F = sw.beta * sin_force(plaq(xc, Mt, Mx, i, j));
+  const double Fjm = sw.beta * sin_force(plaq(xc, Mt, Mx, i, wrap_dec(j, Mx)));
+  const double Fim = sw.beta * sin_force(plaq(xc, Mt, Mx, wrap_dec(i, Mt), j));
   reinterpret_cast<double2 *>(f)[t] = make_double2(F - Fjm, Fim - F);
 }
 
@@ -219,9 +219,9 @@ __global__ void leapfrog_naive_kernel(SW sw, double dt_p, double dt_x, const dou
   const int s = (int)(t - chain * nsite);
   const int j = s / Mt, i = s - j * Mt;
   const double *xc = x_in + chain * 2 * nsite;
-  const double F = sw.beta * sin(plaq(xc, Mt, Mx, i, j));
-  const double Fjm = sw.beta * sin(plaq(xc, Mt, Mx, i, wrap_dec(j, Mx)));
-  const double Fim = sw.beta * sin(plaq(xc, Mt, Mx, wrap_dec(i, Mt), j));
+  const double F = sw.beta * sin_force(plaq(xc, Mt, Mx, i, j));
+  const double Fjm = sw.beta * sin_force(plaq(xc, Mt, Mx, i, wrap_dec(j, Mx)));
+  const double Fim = sw.beta * sin_force(plaq(xc, Mt, Mx, wrap_dec(i, Mt), j));
   double2 pp = reinterpret_cast<double2 *>(p)[t];
   const double2 th = reinterpret_cast<const double2 *>(x_in)[t];
   pp.x -= dt_p * (F - Fjm);
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(1024)
   sh_t1[i] = prev.y;
   sh_t1[Mt + i] = cur.y;
   __syncthreads();
-  double s_prev = sin(prev.x + sh_t1[ip] - cur.x - prev.y);
+  double s_prev = sin_force(prev.x + sh_t1[ip] - cur.x - prev.y);
   double P_cur = cur.x + sh_t1[Mt + ip] - nxt.x - cur.y;
   __syncthreads();
   int b = 0;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(1024)
     const int jp2 = wrap_inc(wrap_inc(j, Mx), Mx);
     const double2 nxt2 = xin[(size_t)jp2 * Mt + i];
     double2 pj = pp[(size_t)j * Mt + i];
-    const double s = sin(P_cur);
+    const double s = sin_force(P_cur);
     sh_s[b * Mt + i] = s;
     sh_t1[b * Mt + i] = nxt.y;
     __syncthreads();
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(1024)
   double s_prev;
   {
     const double2 prev = st_theta[i];
-    s_prev = sin(prev.x + st_theta[ip].y - cur.x - prev.y);
+    s_prev = sin_force(prev.x + st_theta[ip].y - cur.x - prev.y);
   }
   int b = 0;
   for (int r = 1; r <= nrow; ++r) { // updating logical row q = r
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(1024)
     const double2 nxt = st_theta[(size_t)stn * Mt + i];
     const double t1p = st_theta[(size_t)st * Mt + ip].y;
     double2 pj = st_p[(size_t)st * Mt + i];
-    const double s = sin(cur.x + t1p - nxt.x - cur.y);
+    const double s = sin_force(cur.x + t1p - nxt.x - cur.y);
     sh_s[b * Mt + i] = s;
     __syncthreads(); // sin row visible; every thread is done with logical row r-1
     if (i == 0 && r - 1 + S < nq)
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(1024)
   double sA_prev;
   {
     const double2 prev = st_theta[i];
-    sA_prev = sin(prev.x + st_theta[ip].y - cur0.x - prev.y);
+    sA_prev = sin_force(prev.x + st_theta[ip].y - cur0.x - prev.y);
   }
   __syncthreads(); // row 0 consumed
   if (i == 0 && S < nq)
@@ -491,12 +491,12 @@ __global__ void __launch_bounds__(1024)
       nxt0 = st_theta[(size_t)stn * Mt + i];
       const double t1p = st_theta[(size_t)st * Mt + ip].y;
       pj = st_p[(size_t)st * Mt + i];
-      sA = sin(cur0.x + t1p - nxt0.x - cur0.y);
+      sA = sin_force(cur0.x + t1p - nxt0.x - cur0.y);
       exA[(t & 1) * Mt + i] = sA;
     }
     if (doB) { // stage B, row qb: sin of the step-(k+1) plaquette from theta^1
       const double t1p = exT[(qb & 1) * Mt + ip];
-      sB = sin(th1_m.x + t1p - th1_c.x - th1_m.y);
+      sB = sin_force(th1_m.x + t1p - th1_c.x - th1_m.y);
       exB[(t & 1) * Mt + i] = sB;
     }
     __syncthreads();
