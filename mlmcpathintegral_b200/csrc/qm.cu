@@ -40,7 +40,7 @@ constexpr int THREADS = WARPS * 32;
 template <int MODEL>
 __device__ __forceinline__ double site_force(const QM &q, double xm, double x, double xp) {
   if (MODEL == MLMCPI_ROTOR) {
-    return (q.m0 / q.a) * (sin(x - xm) + sin(x - xp));
+    return (q.m0 / q.a) * (sin_force(x - xm) + sin_force(x - xp));
   } else {
     const double tmp_1 = q.m0 / q.a;
     const double tmp_2 = 2. + q.a * q.a * q.mu2;
@@ -349,7 +349,7 @@ __device__ __forceinline__ bool hmc_step_reg_core(const QM &q, int nt, double dt
       double b[SPL], bn[SPL];
 #pragma unroll
       for (int r = 0; r < SPL; ++r)
-        b[r] = sin(s.x[r] - xm[r]);
+        b[r] = sin_force(s.x[r] - xm[r]);
       right_neighbours<SPL>(b, lane, bn);
 #pragma unroll
       for (int r = 0; r < SPL; ++r)
