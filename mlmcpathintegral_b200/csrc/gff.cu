@@ -240,34 +240,34 @@ struct CondF { // qft/gffconditionedfineaction.cc:28-50
 // FINE_ONLY: the fine-only vertices of CoarsenRotate (fine_vertex_of)
 template <class F, bool FINE_ONLY>
 __global__ void vertex_reduce_kernel(F f, GF g, int nblk, int B, double *partial) {
-  const int blk = blockIdx.x, chain = blockIdx.y;
+  const int blk = blockIdx.x;
   const int rowlen = (g.rotated || FINE_ONLY) ? g.Mt / 2 : g.Mt;
   const int nrows = (FINE_ONLY && g.rotated) ? g.Mx / 2 : g.Mx;
-  double acc[1] = {0.0};
-  for (int y = blk; y < nrows; y += nblk)
-    for (int k = threadIdx.x; k < rowlen; k += blockDim.x) {
-      int i, j, ell;
-      if (FINE_ONLY)
-        fine_vertex_of(g, k, y, i, j, ell);
-      else
-        vertex_of(g, k, y, i, j, ell);
-      f(chain, i, j, ell, acc);
-    }
-  const double v = block_sum(acc[0]);
-  if (threadIdx.x == 0)
-    partial[(size_t)chain * nblk + blk] = v;
+  for (int chain = blockIdx.y; chain < B; chain += gridDim.y) { // (gridDim.y = min(B, 65535))
+    double acc[1] = {0.0};
+    for (int y = blk; y < nrows; y += nblk)
+      for (int k = threadIdx.x; k < rowlen; k += blockDim.x) {
+        int i, j, ell;
+        if (FINE_ONLY)
+          fine_vertex_of(g, k, y, i, j, ell);
+        else
+          vertex_of(g, k, y, i, j, ell);
+        f(chain, i, j, ell, acc);
+      }
+    const double v = block_sum(acc[0]);
+    if (threadIdx.x == 0)
+      partial[(size_t)chain * nblk + blk] = v;
+  }
 }
 template <class F, bool FINE_ONLY = false>
 int vertex_reduce(mlmcpi_ctx *ctx, const char *what, F f, const GF &g, int B, double scale, double *out) {
   const int rowlen = (g.rotated || FINE_ONLY) ? g.Mt / 2 : g.Mt;
   const int threads = std::min(256, std::max(32, ((rowlen + 31) / 32) * 32));
   int nblk = std::min(g.Mx, std::max(1, cdiv((long long)ctx->n_sm * 8, B)));
-  if (B > 65535)
-    return ctx_fail(ctx, MLMCPI_EINVAL, "more than 65535 chains in a GFF reduction");
   double *partial = ctx_scratch(ctx, (size_t)B * nblk);
   if (!partial)
     return MLMCPI_ENOMEM;
-  vertex_reduce_kernel<F, FINE_ONLY><<<dim3(nblk, B), threads, 0, ctx->stream>>>(f, g, nblk, B, partial);
+  vertex_reduce_kernel<F, FINE_ONLY><<<dim3(nblk, std::min(B, 65535)), threads, 0, ctx->stream>>>(f, g, nblk, B, partial);
   MLMCPI_LAUNCHED(what);
   return launch_reduce_finish(ctx, partial, nblk, B, 1, EPI_SCALE, scale, 1.0, out, nullptr);
 }
