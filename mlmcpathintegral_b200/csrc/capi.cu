@@ -995,6 +995,14 @@ static double n_sites(const mlmcpi_model &m) {
   return (double)mlmcpi_sample_size(&m);
 }
 
+// draws that amount to MLMCPI_CLUSTER_BURNIN_UPDATES single-cluster updates (every update changes the
+// topological charge by +-1 with probability ~1/2, so a few thousand updates equilibrate chi_t ~ 10)
+#define MLMCPI_CLUSTER_BURNIN_UPDATES 4000
+static int cluster_burnin_draws(const mlmcpi_sampler *s) {
+  const int n_updates = std::max(1, s->prm.n_updates);
+  return (MLMCPI_CLUSTER_BURNIN_UPDATES + n_updates - 1) / n_updates;
+}
+
 // the sampler on the coarsest level: HMCSampler::draw (sampler/hmcsampler.cc:8-19) or
 // OverrelaxedHeatBathSampler::draw (sampler/overrelaxedheatbathsampler.cc:8-31)
 static int coarse_draw(mlmcpi_sampler *s, int c0, int B) {
@@ -1092,6 +1100,42 @@ static int coarse_draw(mlmcpi_sampler *s, int c0, int B) {
   } else {
     return ctx_fail(ctx, MLMCPI_EINVAL, "unknown sampler kind");
   }
+  return 0;
+}
+
+// Start state of a hierarchical sampler whose coarse sampler proposes INDEPENDENT states (cluster,
+// exact): the two-level steps are then independence samplers with weight w = pi_f / (pi_c q), and a
+// chain started from a state of atypically large w never leaves it (measured, profiles/r02_summary.md:
+// 512^2, beta = 1024, 3 levels, zero state + 50 heat-bath sweeps: no chain accepts in 130 draws, while
+// the very same 256^2 <- 128^2 step accepts 36 % as the top of a 256^2 hierarchy).  The start state
+// is therefore drawn the way the proposals are -- a coarse sample, prolonged and filled in level by
+// level, i.e. a sample of pi_c q q ... -- whose weight is typical by construction.  Any start state is
+// legitimate (burn-in follows); the stationary distribution is untouched.
+static int cascade_start(mlmcpi_sampler *s) {
+  mlmcpi_ctx *ctx = s->ctx;
+  const int L = s->L, B = s->B;
+  int rc;
+  const uint64_t start_draw = 0xFFFEull << 40;
+  const uint64_t saved = s->draw;
+  s->draw = start_draw;
+  if (s->prm.kind == MLMCPI_SAMPLER_CLUSTER && s->model[L - 1].model != MLMCPI_SCHWINGER) {
+    // decorrelate the rotor chain from its hot start: clustersampler.cc:27-31 (burn-in draws);
+    // the chain behind the Schwinger cluster sampler was burnt in when it was set up
+    const int n_burn = cluster_burnin_draws(s);
+    for (int k = 0; k < n_burn; ++k) {
+      if ((rc = coarse_draw(s, 0, B)))
+        return rc;
+      s->cluster_updates += std::max(1, s->prm.n_updates);
+    }
+  } else if ((rc = coarse_draw(s, 0, B))) {
+    return rc;
+  }
+  s->draw = saved;
+  for (int l = L - 2; l >= 0; --l)
+    if ((rc = mlmcpi_prolong_fill(ctx, &s->model[l], s->state[l + 1], s->state[l], B, s->chain0,
+                                  level_draw(start_draw, l, 0))))
+      return rc;
+  s->work[0] = s->work[1] = s->work[2] = 0.0;
   return 0;
 }
 
@@ -1287,11 +1331,21 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
     r.a_lat = 1.0 / r.M_lat;
     r.m0 = mc.beta * r.a_lat;
     s->psi_model = r;
+    // Start of the rotor chain: the reference starts hot (U(-pi,pi) per site) and then runs 10^4
+    // draws in the constructors (clustersampler.cc:19-31).  A hot chain of M sites carries O(sqrt(M))
+    // windings which single-cluster updates remove only slowly (128^2 cells, beta = 64: chi_t still ten
+    // times too large after 2000 updates), so the chain starts cold, is thermalised locally by heat-bath
+    // sweeps and the cluster burn-in below only has to spread the topological charge.
     if (mlmcpi_alloc(ctx, (size_t)r.M_lat * B, &s->psi) ||
-        mlmcpi_init_state(ctx, &r, s->psi, B, chain0 + 0x00800000u, 0)) {
+        thermal_start(ctx, &r, s->psi, B, chain0 + 0x00800000u)) {
       mlmcpi_sampler_destroy(s);
       return ctx_fail(ctx, MLMCPI_ENOMEM, "cannot set up the cluster chain");
     }
+    if (qm::cluster_update(ctx, &r, s->psi, B, chain0, s->cluster_updates, MLMCPI_CLUSTER_BURNIN_UPDATES)) {
+      mlmcpi_sampler_destroy(s);
+      return ctx_fail(ctx, MLMCPI_ECUDA, "cluster burn-in failed");
+    }
+    s->cluster_updates += MLMCPI_CLUSTER_BURNIN_UPDATES;
   }
   if (s->prm.multilevel) {
     if (s->L < 2) {
@@ -1327,7 +1381,9 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
   } else {
     // Sampler constructors start from Action::initialise_state (e.g. hmcsampler.hh:99-101); the
     // hierarchical sampler from the zero state (hierarchicalsampler.cc:43-44), here thermalised
-    if (s->L > 1)
+    if (s->L > 1 && (s->prm.kind == MLMCPI_SAMPLER_CLUSTER || s->prm.kind == MLMCPI_SAMPLER_EXACT))
+      rc = cascade_start(s);
+    else if (s->L > 1)
       rc = thermal_start(ctx, fine, s->state[0], B, chain0);
     else
       rc = mlmcpi_init_state(ctx, fine, s->state[0], B, chain0, 0);

@@ -720,59 +720,130 @@ __global__ void qoi_kernel(QM q, int qoi, const double *x, int B, double *out, i
 
 // ------------------------------------------------------------ Wolff cluster
 // ClusterSampler::single_cluster_update1d (sampler/clustersampler.cc:88-132) with the rotor's
-// S_ell / new_reflection / flip (qm/rotoraction.hh:226-253).  The growth of one cluster is
-// sequential, so one THREAD walks one chain; thousands of chains run side by side.  Variates:
-// one Philox stream per (chain, update): call 0 = (xbar, start site), then one uniform per
-// processed link in processing order.
-__global__ void rotor_cluster_kernel(QM q, double *x, int B, uint32_t chain0, uint64_t seed,
-                                     uint64_t update0, int n_updates) {
-  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
-  if (chain >= B)
+// S_ell / new_reflection / flip (qm/rotoraction.hh:226-253).
+//
+// Variates: Philox stream CLUSTER, draw = update number; index 0 = (xbar, start site); index
+// 1 + k = the two uniforms of link k (between the sites k and k+1 mod M): the first decides the
+// link when the cluster grows FORWARD over it, the second when it grows BACKWARD.  The bond test
+// of a link therefore depends only on the link, not on how many links were processed before it,
+// and the growth of a cluster -- two runs of bonded links away from the start site, SURVEY 8f-2 --
+// is evaluated speculatively: one WARP per chain tests 64 forward and 64 backward links per
+// round (the flipped value of the near site is computed on the fly, so the arithmetic of every
+// test is that of the sequential walk) and a ballot finds the end of each run.  Expected run
+// length is O(m0/a) sites, i.e. one to a few rounds.  If the two runs would meet (the cluster
+// wraps the ring: short chains only) the update is walked link by link by lane 0 with the same
+// variates, statement for statement as the reference does, including its double flips.
+__device__ __forceinline__ double cluster_flip(const double xbar, const double x) {
+  return mod_2pi(M_PI + 2. * xbar - x); // RotorAction::flip, rotoraction.hh:245-253
+}
+__device__ __forceinline__ bool cluster_bond(const double coupling, const double xbar, const double x_near,
+                                             const double x_far, const double u) {
+  const double Sell = -coupling * cos(x_near - xbar) * cos(x_far - xbar); // S_ell, rotoraction.hh:226-231
+  const double p_connect = 1. - exp(fmin(0.0, -Sell));                    // clustersampler.cc:124-126
+  return u < p_connect;
+}
+__device__ __forceinline__ double cluster_link_uniform(uint64_t seed, uint64_t update, uint32_t gchain, int link,
+                                                       int backward) {
+  Rng r = rng_init(seed, MLMCPI_STREAM_CLUSTER, update, gchain, 1u + (uint32_t)link);
+  double uf, ub;
+  rng_uniform2(r, uf, ub);
+  return backward ? ub : uf;
+}
+// the reference's walk, one link at a time (lane 0 only; wrap-around case)
+__device__ void cluster_update_sequential(double *xc, int M, double coupling, double xbar, int i0, uint64_t seed,
+                                          uint64_t update, uint32_t gchain) {
+  auto process = [&](int i, int direction, int &i_next) { // process_link1d (:118-132)
+    const int nb = (i + direction + M) % M;
+    const int link = direction > 0 ? i : nb;
+    const bool bonded = cluster_bond(coupling, xbar, xc[i], xc[nb],
+                                     cluster_link_uniform(seed, update, gchain, link, direction < 0));
+    if (bonded)
+      xc[nb] = cluster_flip(xbar, xc[nb]);
+    i_next = nb;
+    return bonded;
+  };
+  xc[i0] = cluster_flip(xbar, xc[i0]); // flip(i0)
+  int i_p = i0, i_last_p;
+  bool bonded;
+  do { // forward (:96-103)
+    i_last_p = i_p;
+    bonded = process(i_p, +1, i_p);
+  } while ((i_p != i0) && bonded);
+  int i_m = i0;
+  do { // backward (:105-110)
+    bonded = process(i_m, -1, i_m);
+  } while ((i_m != i_last_p) && bonded);
+}
+
+constexpr int CLUSTER_LPL = 2; // links per lane, direction and round
+
+__global__ void __launch_bounds__(128) rotor_cluster_kernel(QM q, double *x, int B, uint32_t chain0, uint64_t seed,
+                                                             uint64_t update0, int n_updates) {
+  const int lane = threadIdx.x & 31;
+  const int chain = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (chain >= B) // whole warps leave together
     return;
   const int M = q.M;
   double *xc = x + (size_t)chain * M;
   const double coupling = 2.0 * q.m0 / q.a;
+  const uint32_t gchain = chain0 + (uint32_t)chain;
+  constexpr int W = 32 * CLUSTER_LPL;
   for (int u = 0; u < n_updates; ++u) {
-    Rng r = rng_init(seed, MLMCPI_STREAM_CLUSTER, update0 + u, chain0 + chain, 0);
+    const uint64_t update = update0 + u;
+    Rng r = rng_init(seed, MLMCPI_STREAM_CLUSTER, update, gchain, 0);
     double u0, u1;
     rng_uniform2(r, u0, u1);
     const double xbar = -M_PI + 2. * M_PI * u0; // new_reflection()
     int i0 = (int)(u1 * M);
     if (i0 >= M)
       i0 = M - 1;
-    double v0 = 0.0, v1 = 0.0;
-    int have = 0; // buffered uniforms
-    auto next_uniform = [&]() {
-      if (have == 0) {
-        rng_uniform2(r, v0, v1);
-        have = 2;
+    // t_f = first forward iteration whose link does not bond (iteration t: from site i0+t to
+    // i0+t+1), s_b = the same backwards (iteration s: from i0-s to i0-s-1).  Iterations up to
+    // M-2 see an unflipped far site as long as the runs do not meet.
+    int t_f = -1, s_b = -1;
+    for (int base = 0; base < M - 1 && (t_f < 0 || s_b < 0); base += W) {
+#pragma unroll
+      for (int k = 0; k < CLUSTER_LPL; ++k) {
+        const int it = base + 32 * k + lane;
+        bool fail_f = false, fail_b = false;
+        if (it < M - 1) {
+          if (t_f < 0) {
+            int a = i0 + it;
+            a -= (a >= M) ? M : 0;
+            const int b = (a + 1 == M) ? 0 : a + 1;
+            fail_f = !cluster_bond(coupling, xbar, cluster_flip(xbar, xc[a]), xc[b],
+                                   cluster_link_uniform(seed, update, gchain, a, 0));
+          }
+          if (s_b < 0) {
+            int a = i0 - it;
+            a += (a < 0) ? M : 0;
+            const int b = (a == 0) ? M - 1 : a - 1;
+            fail_b = !cluster_bond(coupling, xbar, cluster_flip(xbar, xc[a]), xc[b],
+                                   cluster_link_uniform(seed, update, gchain, b, 1));
+          }
+        }
+        const unsigned mf = __ballot_sync(0xffffffffu, fail_f), mb = __ballot_sync(0xffffffffu, fail_b);
+        if (t_f < 0 && mf)
+          t_f = base + 32 * k + __ffs(mf) - 1;
+        if (s_b < 0 && mb)
+          s_b = base + 32 * k + __ffs(mb) - 1;
       }
-      const double v = (have == 2) ? v0 : v1;
-      --have;
-      return v;
-    };
-    // process_link1d (:118-132) on the current state
-    auto process = [&](int i, int direction, int &i_next) {
-      const int nb = (i + direction + M) % M;
-      const double Sell = -coupling * cos(xc[i] - xbar) * cos(xc[nb] - xbar);
-      const double p_connect = 1. - exp(fmin(0.0, -Sell));
-      const bool bonded = next_uniform() < p_connect;
-      if (bonded)
-        xc[nb] = mod_2pi(M_PI + 2. * xbar - xc[nb]);
-      i_next = nb;
-      return bonded;
-    };
-    xc[i0] = mod_2pi(M_PI + 2. * xbar - xc[i0]); // flip(i0)
-    int i_p = i0, i_last_p;
-    bool bonded;
-    do { // forward (:96-103)
-      i_last_p = i_p;
-      bonded = process(i_p, +1, i_p);
-    } while ((i_p != i0) && bonded);
-    int i_m = i0;
-    do { // backward (:105-110)
-      bonded = process(i_m, -1, i_m);
-    } while ((i_m != i_last_p) && bonded);
+    }
+    if (t_f < 0 || s_b < 0 || t_f + s_b > M - 2) {
+      // the runs meet: far sites were flipped before their link is tested -- walk it
+      if (lane == 0)
+        cluster_update_sequential(xc, M, coupling, xbar, i0, seed, update, gchain);
+    } else {
+      // the cluster = the ring segment [i0 - s_b, i0 + t_f], every site flipped once
+      const int n_flip = 1 + t_f + s_b;
+      for (int k = lane; k < n_flip; k += 32) {
+        int site = i0 - s_b + k;
+        site += (site < 0) ? M : 0;
+        site -= (site >= M) ? M : 0;
+        xc[site] = cluster_flip(xbar, xc[site]);
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -1018,8 +1089,8 @@ int cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uin
   if (m->model != MLMCPI_ROTOR)
     return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "cluster updates are defined for the rotor action");
   QM q = make_qm(m);
-  rotor_cluster_kernel<<<cdiv(B, 64), 64, 0, ctx->stream>>>(q, x, B, chain0, ctx->seed, update0,
-                                                          n_updates);
+  rotor_cluster_kernel<<<cdiv((long long)B * 32, 128), 128, 0, ctx->stream>>>(q, x, B, chain0, ctx->seed,
+                                                                            update0, n_updates);
   MLMCPI_LAUNCHED("qm::cluster_update");
   return 0;
 }

@@ -1799,30 +1799,22 @@ int orc_twolevel_step(const orc_model *fine, const orc_model *coarse,
 
 /* ClusterSampler::single_cluster_update1d + process_link1d, sampler/clustersampler.cc:88-132,
  * with RotorAction::S_ell / new_reflection / flip, action/qm/rotoraction.hh:226-253.
- * Philox: one stream per (chain, update): call 0 = (xbar, start site), then one uniform per
- * processed link in processing order (two per call). */
-typedef struct {
-  orc_rng r;
-  double v[2];
-  int have;
-} uniform_feed;
-static double feed_next(uniform_feed *f) {
-  if (f->have == 0) {
-    orc_rng_uniform2(&f->r, &f->v[0], &f->v[1]);
-    f->have = 2;
-  }
-  const double v = (f->have == 2) ? f->v[0] : f->v[1];
-  f->have--;
-  return v;
-}
-static int process_link1d(const orc_model *m, double *x, double xbar, uniform_feed *f, int i,
-                          int direction, int *i_next) {
+ * Philox stream CLUSTER, draw = update: index 0 = (xbar, start site); index 1 + k = the two
+ * uniforms of link k (sites k, k+1 mod M): the first is used when the link is processed in the
+ * forward walk, the second in the backward walk. */
+static int process_link1d(const orc_model *m, double *x, double xbar, uint64_t seed, uint64_t update,
+                          uint32_t chain, int i, int direction, int *i_next) {
   const int M = m->M_lat;
   const int i_neighbour = (i + direction + M) % M;
+  const int link = direction > 0 ? i : i_neighbour;
+  orc_rng r;
+  double uf, ub;
+  orc_rng_init(&r, seed, ORC_STREAM_CLUSTER, update, chain, 1u + (uint32_t)link);
+  orc_rng_uniform2(&r, &uf, &ub);
   const double Sell =
       -2.0 * m->m0 / m->a_lat * cos(x[i] - xbar) * cos(x[i_neighbour] - xbar);
   const double p_connect = 1. - exp(fmin(0, -Sell));
-  const int bonded = (feed_next(f) < p_connect);
+  const int bonded = ((direction > 0 ? uf : ub) < p_connect);
   if (bonded)
     x[i_neighbour] = orc_mod_2pi(M_PI + 2. * xbar - x[i_neighbour]);
   *i_next = i_neighbour;
@@ -1832,11 +1824,10 @@ void orc_cluster_update(const orc_model *m, uint64_t seed, uint64_t update0, int
                         uint32_t chain, double *x) {
   const int M = m->M_lat;
   for (int u = 0; u < n_updates; ++u) {
-    uniform_feed f;
-    f.have = 0;
-    orc_rng_init(&f.r, seed, ORC_STREAM_CLUSTER, update0 + u, chain, 0);
+    orc_rng r;
+    orc_rng_init(&r, seed, ORC_STREAM_CLUSTER, update0 + u, chain, 0);
     double u0, u1;
-    orc_rng_uniform2(&f.r, &u0, &u1);
+    orc_rng_uniform2(&r, &u0, &u1);
     const double xbar = -M_PI + 2. * M_PI * u0;
     int i0 = (int)(u1 * M);
     if (i0 >= M)
@@ -1845,11 +1836,11 @@ void orc_cluster_update(const orc_model *m, uint64_t seed, uint64_t update0, int
     int i_p = i0, i_last_p, bonded;
     do {
       i_last_p = i_p;
-      bonded = process_link1d(m, x, xbar, &f, i_p, +1, &i_p);
+      bonded = process_link1d(m, x, xbar, seed, update0 + u, chain, i_p, +1, &i_p);
     } while ((i_p != i0) && bonded);
     int i_m = i0;
     do {
-      bonded = process_link1d(m, x, xbar, &f, i_m, -1, &i_m);
+      bonded = process_link1d(m, x, xbar, seed, update0 + u, chain, i_m, -1, &i_m);
     } while ((i_m != i_last_p) && bonded);
   }
 }

@@ -40,7 +40,7 @@ def main():
     kinds = {"cluster": mp.SAMPLER_CLUSTER, "HMC": mp.SAMPLER_HMC, "heatbath": mp.SAMPLER_HEATBATH}
     for L in [int(s) for s in a.sizes.split(",")]:
         beta = a.beta if a.beta else L * L / a.ratio
-        exact = _lib.L.mlmcpi_schwinger_chit_analytical(beta, L * L)
+        exact = _lib.lib.mlmcpi_schwinger_chit_analytical(beta, L * L)
         for name in a.samplers.split(","):
             B = a.chains if L <= 256 else max(64, a.chains // 4)
             m = mp.schwinger(L, L, beta)
