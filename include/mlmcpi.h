@@ -81,15 +81,18 @@ typedef struct mlmcpi_model {
   int gff_n_gibbs;    /* GFF: n_gibbs_smooth (qft/gffaction.hh:161-168).  0: the 5-point action;
                          > 0: the Gibbs-smoothed coarse-level action S = phi^T Q_hat phi / 2 with
                          the dense precision matrix of gffaction.cc:133-174 (<= MLMCPI_GFF_DENSE_MAX
-                         vertices)                                                              */
+                         vertices), whatever sampler runs on the level -- as in the reference     */
   double gff_omega;   /* GFF: overrelaxation factor of the Gibbs smoother                      */
 } mlmcpi_model;
 
 /* Largest number of vertices for which the dense matrices of GFFAction::buildMatrices are formed
- * (O(N^2) memory, O(N^3) setup on the host).  mlmcpi_coarse_model gives a coarse GFF level the
- * reference's n_gibbs_smooth = 2, omega = 1 (gffaction.hh:201-208) up to this size and the
- * un-smoothed 5-point action beyond it, where the reference itself cannot be set up. */
-#define MLMCPI_GFF_DENSE_MAX 1024
+ * (gffaction.cc:133-174; on the device with cuSOLVER / cuBLAS: four N x N fp64 work matrices, about
+ * 10 N^3 flops, once per level and context).  32768 = level 1 of BASELINE config C3 (256 x 256,
+ * coarsening rotate: 65536 / 32768 / 16384 / 8192 vertices): 8.6 GB per matrix.  mlmcpi_coarse_model
+ * gives EVERY coarse GFF level the reference's n_gibbs_smooth = 2, omega = 1 (gffaction.hh:201-208);
+ * a level above this size makes mlmcpi_action / mlmcpi_exact_draw fail with MLMCPI_EUNSUPPORTED
+ * (there is no silent fall-back to the 5-point action). */
+#define MLMCPI_GFF_DENSE_MAX 32768
 
 typedef struct mlmcpi_ctx mlmcpi_ctx;
 
@@ -140,10 +143,14 @@ int mlmcpi_rank(const mlmcpi_ctx *ctx);
  * colours in one pass over HBM (row pipeline, out of place), 0 = four colour passes; same result.
  * MLMCPI_OPT_FUSED_QM_HIERARCHY: 1 (default) = HierarchicalSampler::draw for 1-D paths with an HMC coarse
  * sampler runs as ONE kernel (one warp per chain, every level on chip), 0 = the sequence of
- * single-purpose kernels; same draw. */
+ * single-purpose kernels; same draw.
+ * MLMCPI_OPT_GFF_COARSE_SMOOTHING: 1 (default) = the coarse levels a sampler / multilevel driver builds
+ *   for a GFF carry the reference's Gibbs-smoothed action Q_hat (gffaction.hh:201-208), whatever sampler
+ *   runs on them; 0 = the plain 5-point action on every level (consistent with a heat-bath / HMC coarse
+ *   sampler, but the two-level acceptance is ~ 0 beyond 16 x 16). */
 enum { MLMCPI_OPT_EXPCOS_ENVELOPE = 1, MLMCPI_OPT_LEAPFROG_VARIANT = 2, MLMCPI_OPT_LEAPFROG_ROWS = 3,
        MLMCPI_OPT_LEAPFROG_FUSE = 4, MLMCPI_OPT_SWEEP_REVERSE = 5, MLMCPI_OPT_OVERRELAX_ONE_PASS = 6,
-       MLMCPI_OPT_FUSED_QM_HIERARCHY = 7 };
+       MLMCPI_OPT_FUSED_QM_HIERARCHY = 7, MLMCPI_OPT_GFF_COARSE_SMOOTHING = 8 };
 int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value);
 /* number of kernels this context has launched so far */
 uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx);
@@ -321,9 +328,13 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept);
  * h_q[B] (and h_x_out[B][n] if not NULL) are copied back; synchronous */
 int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, double *h_q,
                              double *h_x_out);
-/* counters: out = {n_draws, per level accepted chains ...} */
 int mlmcpi_sampler_level_model(const mlmcpi_sampler *s, int level, mlmcpi_model *m);
+/* MCMCStep::p_accept of every level (montecarlo/mcmcstep.hh:21-72): accepted / attempted steps of
+ * that level -- in the hierarchical cascade a level is only attempted by the chains all coarser
+ * levels accepted (hierarchicalsampler.cc:73-74), which is how HierarchicalSampler::show_stats
+ * reports it; mlmcpi_sampler_reset_stats = MCMCStep::reset_stats on every level */
 int mlmcpi_sampler_stats(mlmcpi_sampler *s, double *h_p_accept /* [n_levels] */);
+int mlmcpi_sampler_reset_stats(mlmcpi_sampler *s);
 /* elementary-update counters of the last draw for throughput accounting:
  * out = {leapfrog site-steps, sweep site-updates, filled fine sites} summed over chains */
 int mlmcpi_sampler_work(const mlmcpi_sampler *s, double out[3]);

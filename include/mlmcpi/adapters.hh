@@ -157,6 +157,7 @@ public:
   unsigned int getMx_lat() const { return Mx_lat; }
   unsigned int getNedges() const { return rotated ? Mt_lat * Mx_lat : 2 * Mt_lat * Mx_lat; }
   unsigned int getNvertices() const { return rotated ? Mt_lat * Mx_lat / 2 : Mt_lat * Mx_lat; }
+  unsigned int getNcells() const { return Mt_lat * Mx_lat; } // lattice/lattice2d.hh (unrotated levels)
   bool is_rotated() const { return rotated; }
   CoarseningType get_coarsening_type() const { return ctype; }
   int get_coarsening_level() const { return level; }
@@ -302,12 +303,23 @@ static inline mlmcpi_model qm_model(int kind, const Lattice1D &lat, double m0, d
   return m;
 }
 
+/** action/qm/qmaction.hh: base of the 1-D actions (the reference's drivers hold a shared_ptr<QMAction>) */
+class QMAction : public Action {
+public:
+  using Action::Action;
+  double getm0() const { return model_.m0; }
+};
+
 /** action/qm/harmonicoscillatoraction.hh */
-class HarmonicOscillatorAction : public Action {
+class HarmonicOscillatorAction : public QMAction {
 public:
   HarmonicOscillatorAction(const std::shared_ptr<Lattice1D> lattice, const RenormalisationType renormalisation_,
                            const double m0_, const double mu2_)
-      : Action(qm_model(MLMCPI_HO, *lattice, m0_, mu2_), renormalisation_, lattice->get_coarsening_level(), 0) {}
+      : QMAction(qm_model(MLMCPI_HO, *lattice, m0_, mu2_), renormalisation_, lattice->get_coarsening_level(), 0) {}
+  /** qm/harmonicoscillatoraction.cc:76-80 */
+  double Xsquared_analytical_continuum() const {
+    return mlmcpi_ho_xsquared_analytical(model_.m0, model_.mu2, model_.a_lat, model_.M_lat, 1);
+  }
   /** qm/harmonicoscillatoraction.cc:69-74 */
   double Xsquared_analytical() const {
     const double a = model_.a_lat, mu2 = model_.mu2;
@@ -317,18 +329,22 @@ public:
   }
 };
 /** action/qm/quarticoscillatoraction.hh */
-class QuarticOscillatorAction : public Action {
+class QuarticOscillatorAction : public QMAction {
 public:
   QuarticOscillatorAction(const std::shared_ptr<Lattice1D> lattice, const RenormalisationType renormalisation_,
                           const double m0_, const double mu2_, const double lambda_, const double x0_)
-      : Action(qm_model(MLMCPI_QUARTIC, *lattice, m0_, mu2_, lambda_, x0_), renormalisation_,
+      : QMAction(qm_model(MLMCPI_QUARTIC, *lattice, m0_, mu2_, lambda_, x0_), renormalisation_,
                lattice->get_coarsening_level(), 0) {}
 };
 /** action/qm/rotoraction.hh */
-class RotorAction : public Action {
+class RotorAction : public QMAction {
 public:
   RotorAction(const std::shared_ptr<Lattice1D> lattice, const RenormalisationType renormalisation_, const double m0_)
-      : Action(qm_model(MLMCPI_ROTOR, *lattice, m0_), renormalisation_, lattice->get_coarsening_level(), 0) {}
+      : QMAction(qm_model(MLMCPI_ROTOR, *lattice, m0_), renormalisation_, lattice->get_coarsening_level(), 0) {}
+  /** qm/rotoraction.cc:92-115 */
+  double chit_exact() const { return mlmcpi_rotor_chit(model_.m0, model_.a_lat, model_.T_final, 0); }
+  double chit_perturbative() const { return mlmcpi_rotor_chit(model_.m0, model_.a_lat, model_.T_final, 1); }
+  double chit_continuum() const { return mlmcpi_rotor_chit(model_.m0, model_.a_lat, model_.T_final, 2); }
 };
 
 static inline int level_coarsening(int ctype, int level) {
@@ -429,27 +445,57 @@ typedef ConditionedFineActionFactory GFFConditionedFineActionFactory;
 // ------------------------------------------- qoi/quantityofinterest.hh:16-36
 class QoI {
 public:
-  QoI(const std::shared_ptr<Action> action_, int which_) : action(action_), which(which_) {}
+  QoI(const std::shared_ptr<Action> action_, int which_) : model_(action_->model()), which(which_) {}
+  /** the reference constructs its QoIs from the lattice (qoi/qft/qoi2dsusceptibility.hh:35-40, ...) */
+  QoI(const mlmcpi_model &m, int which_) : model_(m), which(which_) {}
   virtual ~QoI() {}
   int id() const { return which; } // MLMCPI_QOI_*
   virtual const double evaluate(const std::shared_ptr<SampleState> state) {
     DeviceVector x(state->data.size()), q(1);
     x.upload(state->data.data());
-    Device::check(mlmcpi_qoi(Device::ctx(), &action->model(), which, x.ptr(), 1, q.ptr(), nullptr), "QoI::evaluate");
+    Device::check(mlmcpi_qoi(Device::ctx(), &model_, which, x.ptr(), 1, q.ptr(), nullptr), "QoI::evaluate");
     double v;
     q.download(&v);
     return v;
   }
 
 protected:
-  const std::shared_ptr<Action> action;
+  static mlmcpi_model lattice_model(int kind, const Lattice1D &lat) { return qm_model(kind, lat, 1.0); }
+  static mlmcpi_model lattice_model(int kind, const Lattice2D &lat) {
+    mlmcpi_model m = {};
+    m.model = kind;
+    m.Mt_lat = lat.getMt_lat();
+    m.Mx_lat = lat.getMx_lat();
+    m.rotated = lat.is_rotated();
+    m.coarsening = level_coarsening(lat.get_coarsening_type(), lat.get_coarsening_level());
+    m.beta = 1.0;
+    return m;
+  }
+  const mlmcpi_model model_;
   const int which;
 };
-struct QoIXsquared : QoI { explicit QoIXsquared(std::shared_ptr<Action> a) : QoI(a, MLMCPI_QOI_X2) {} };
-struct QoISusceptibility : QoI { explicit QoISusceptibility(std::shared_ptr<Action> a) : QoI(a, MLMCPI_QOI_ROTOR_CHI) {} };
-struct QoI2DSusceptibility : QoI { explicit QoI2DSusceptibility(std::shared_ptr<Action> a) : QoI(a, MLMCPI_QOI_SCHWINGER_CHI) {} };
-struct QoIAvgPlaquette : QoI { explicit QoIAvgPlaquette(std::shared_ptr<Action> a) : QoI(a, MLMCPI_QOI_AVG_PLAQUETTE) {} };
-struct QoI2DPhiSquared : QoI { explicit QoI2DPhiSquared(std::shared_ptr<Action> a) : QoI(a, MLMCPI_QOI_PHI2) {} };
+struct QoIXsquared : QoI {
+  explicit QoIXsquared(std::shared_ptr<Action> a) : QoI(a, MLMCPI_QOI_X2) {}
+  explicit QoIXsquared(std::shared_ptr<Lattice1D> l) : QoI(lattice_model(MLMCPI_HO, *l), MLMCPI_QOI_X2) {}
+};
+struct QoISusceptibility : QoI {
+  explicit QoISusceptibility(std::shared_ptr<Action> a) : QoI(a, MLMCPI_QOI_ROTOR_CHI) {}
+  explicit QoISusceptibility(std::shared_ptr<Lattice1D> l) : QoI(lattice_model(MLMCPI_ROTOR, *l), MLMCPI_QOI_ROTOR_CHI) {}
+};
+struct QoI2DSusceptibility : QoI {
+  explicit QoI2DSusceptibility(std::shared_ptr<Action> a) : QoI(a, MLMCPI_QOI_SCHWINGER_CHI) {}
+  explicit QoI2DSusceptibility(std::shared_ptr<Lattice2D> l)
+      : QoI(lattice_model(MLMCPI_SCHWINGER, *l), MLMCPI_QOI_SCHWINGER_CHI) {}
+};
+struct QoIAvgPlaquette : QoI {
+  explicit QoIAvgPlaquette(std::shared_ptr<Action> a) : QoI(a, MLMCPI_QOI_AVG_PLAQUETTE) {}
+  explicit QoIAvgPlaquette(std::shared_ptr<Lattice2D> l)
+      : QoI(lattice_model(MLMCPI_SCHWINGER, *l), MLMCPI_QOI_AVG_PLAQUETTE) {}
+};
+struct QoI2DPhiSquared : QoI {
+  explicit QoI2DPhiSquared(std::shared_ptr<Action> a) : QoI(a, MLMCPI_QOI_PHI2) {}
+  explicit QoI2DPhiSquared(std::shared_ptr<Lattice2D> l) : QoI(lattice_model(MLMCPI_GFF, *l), MLMCPI_QOI_PHI2) {}
+};
 
 // ---------------------------------------------- montecarlo/mcmcstep.hh:21-72
 class MCMCStep {

@@ -59,9 +59,14 @@ inline std::ostream &pcout() {
   return Parallel::master() ? std::cout : sink;
 }
 
-/** number of chains per device of this process (set once by the driver) */
+/** number of chains per device of this process: set once by the driver, or -- for the reference's own
+ * drivers, whose command line has no room for it -- from the environment variable MLMCPI_CHAINS */
 inline unsigned int &batch_size() {
-  static unsigned int B = 256;
+  static unsigned int B = [] {
+    const char *v = std::getenv("MLMCPI_CHAINS");
+    const int n = v ? std::atoi(v) : 0;
+    return (unsigned int)(n > 0 ? n : 256);
+  }();
   return B;
 }
 
@@ -293,12 +298,10 @@ public:
     q.n_levels = std::max(1, (int)p_.n_max_level() - a.get_coarsening_level());
     return q;
   }
-  /** the reference burns in (and tunes) the coarsest-level sampler in its constructor */
+  /** the reference burns in and (HMC) tunes the coarsest-level sampler in its constructor
+   * (hierarchicalsampler.cc:41, hmcsampler.hh:99-108) */
   std::shared_ptr<BatchedSampler> get(std::shared_ptr<Action> action) {
-    std::shared_ptr<BatchedSampler> s = std::make_shared<BatchedSampler>(action, params(*action), 0, false);
-    for (unsigned int k = 0; k < coarse->n_burnin(); ++k)
-      s->draw();
-    return s;
+    return std::make_shared<BatchedSampler>(action, params(*action), coarse->n_burnin(), coarse->autotune());
   }
 
 protected:

@@ -357,6 +357,9 @@ class Sampler:
         self.ctx._ck(L.mlmcpi_sampler_stats(self.h, out))
         return list(out)
 
+    def reset_stats(self):
+        self.ctx._ck(L.mlmcpi_sampler_reset_stats(self.h))
+
     def autotune(self, p_accept_target=0.8, n_rounds=100, n_samples=1000):
         """HMCSampler::autotune_stepsize; returns (dt, last acceptance, converged)"""
         dt, pa = C.c_double(), C.c_double()

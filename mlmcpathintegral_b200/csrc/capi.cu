@@ -172,10 +172,7 @@ void mlmcpi_destroy(mlmcpi_ctx *ctx) {
       cudaFree(ctx->work[k]);
   for (auto &kv : ctx->ho_exact_factor)
     cudaFree(kv.second);
-  for (auto &kv : ctx->gff_dense)
-    for (double *d : kv.second)
-      if (d)
-        cudaFree(d);
+  gff::release_dense(ctx);
   if (ctx->own_stream)
     cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -217,6 +214,10 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
   }
   if (option == MLMCPI_OPT_LEAPFROG_ROWS && value >= 0) {
     ctx->leapfrog_rows = value;
+    return 0;
+  }
+  if (option == MLMCPI_OPT_GFF_COARSE_SMOOTHING && (value == 0 || value == 1)) {
+    ctx->gff_coarse_smoothing = value;
     return 0;
   }
   return ctx_fail(ctx, MLMCPI_EINVAL, "unknown option or value");
@@ -481,10 +482,8 @@ int mlmcpi_coarse_model(const mlmcpi_model *fine, int renorm, int level, int cty
     coarse->Mx_lat = Mxc;
     coarse->rotated = rotc;
     coarse->gff_mu2 = ac * ac * (fine->gff_mu2 / (af * af));
-    // GFFAction::coarse_action (gffaction.hh:201-208): n_gibbs_smooth = 2, omega = 1 -- where
-    // the dense matrices can be formed
-    const int Nc = rotc ? Mtc * Mxc / 2 : Mtc * Mxc;
-    coarse->gff_n_gibbs = (Nc <= MLMCPI_GFF_DENSE_MAX) ? 2 : 0;
+    // GFFAction::coarse_action (gffaction.hh:201-208): n_gibbs_smooth = 2, omega = 1
+    coarse->gff_n_gibbs = 2;
     coarse->gff_omega = 1.0;
     return 0;
   }
@@ -1104,7 +1103,10 @@ static int coarse_draw(mlmcpi_sampler *s, int c0, int B) {
 }
 
 // Start state of a hierarchical sampler whose coarse sampler proposes INDEPENDENT states (cluster,
-// exact): the two-level steps are then independence samplers with weight w = pi_f / (pi_c q), and a
+// exact), and of every GFF hierarchy (whose intermediate levels accept a few per cent of the
+// proposals, in the reference as here, so that a chain started away from the hierarchy's own
+// stationary distribution needs thousands of draws to reach it -- the reference spends the 10^4
+// draws of its constructor on that): the two-level steps are then independence samplers with weight w = pi_f / (pi_c q), and a
 // chain started from a state of atypically large w never leaves it (measured, profiles/r02_summary.md:
 // 512^2, beta = 1024, 3 levels, zero state + 50 heat-bath sweeps: no chain accepts in 130 draws, while
 // the very same 256^2 <- 128^2 step accepts 36 % as the top of a 256^2 hierarchy).  The start state
@@ -1126,6 +1128,16 @@ static int cascade_start(mlmcpi_sampler *s) {
       if ((rc = coarse_draw(s, 0, B)))
         return rc;
       s->cluster_updates += std::max(1, s->prm.n_updates);
+    }
+  } else if (s->prm.kind == MLMCPI_SAMPLER_HMC || s->prm.kind == MLMCPI_SAMPLER_HEATBATH) {
+    // (GFF) local sampler on the coarsest level: hot start, burnt in there -- the Gaussian has no
+    // metastable sectors, and 100 coarse draws cost less than one fine-level sweep
+    if ((rc = mlmcpi_init_state(ctx, &s->model[L - 1], s->state[L - 1], B, s->chain0, 0)))
+      return rc;
+    for (int k = 0; k < 100; ++k) {
+      if ((rc = coarse_draw(s, 0, B)))
+        return rc;
+      s->draw++;
     }
   } else if ((rc = coarse_draw(s, 0, B))) {
     return rc;
@@ -1292,10 +1304,10 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
       delete s;
       return ctx_fail(ctx, rc, "cannot construct the coarse action of a level");
     }
-    // The Gibbs-smoothed coarse GFF action describes what the EXACT sampler draws
-    // (gffaction.cc:200-213); with a heat-bath / HMC sampler, whose stationary distribution is
-    // the 5-point action, the hierarchy keeps the 5-point action on every level
-    if (c.model == MLMCPI_GFF && prm->kind != MLMCPI_SAMPLER_EXACT)
+    // GFFAction::coarse_action (gffaction.hh:201-208) gives every coarse level the Gibbs-smoothed
+    // action Q_hat, whatever sampler runs on it -- kept (MLMCPI_OPT_GFF_COARSE_SMOOTHING = 0 selects
+    // the plain 5-point action on the coarse levels instead)
+    if (c.model == MLMCPI_GFF && !ctx->gff_coarse_smoothing)
       c.gff_n_gibbs = 0;
     s->model.push_back(c);
   }
@@ -1381,7 +1393,8 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
   } else {
     // Sampler constructors start from Action::initialise_state (e.g. hmcsampler.hh:99-101); the
     // hierarchical sampler from the zero state (hierarchicalsampler.cc:43-44), here thermalised
-    if (s->L > 1 && (s->prm.kind == MLMCPI_SAMPLER_CLUSTER || s->prm.kind == MLMCPI_SAMPLER_EXACT))
+    if (s->L > 1 && (s->prm.kind == MLMCPI_SAMPLER_CLUSTER || s->prm.kind == MLMCPI_SAMPLER_EXACT ||
+                     fine->model == MLMCPI_GFF))
       rc = cascade_start(s);
     else if (s->L > 1)
       rc = thermal_start(ctx, fine, s->state[0], B, chain0);
@@ -1556,11 +1569,31 @@ int mlmcpi_sampler_stats(mlmcpi_sampler *s, double *h_p_accept) {
   MLMCPI_CUDA(cudaMemcpyAsync(c.data(), s->counters, sizeof(unsigned long long) * s->L,
                               cudaMemcpyDeviceToHost, ctx->stream));
   MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int l = 0; l < s->L; ++l) {
-    // the level walk of the MultilevelSampler takes several steps per draw on the coarser levels
-    const double n = s->prm.multilevel ? (double)s->n_steps[l] : (double)s->n_draws;
-    h_p_accept[l] = n > 0 ? (double)c[l] / (n * s->B) : 0.0;
+  for (int l = s->L - 1; l >= 0; --l) {
+    // MCMCStep::p_accept = accepted / total of THAT step (montecarlo/mcmcstep.hh).  In the
+    // hierarchical cascade a two-level step only runs -- and counts a sample -- when every coarser
+    // level accepted (the break at hierarchicalsampler.cc:73-74): the chains that reach level l are
+    // the chains level l+1 accepted.  The level walk of the MultilevelSampler takes n_steps[l] steps
+    // of all chains on level l.
+    double n;
+    if (s->prm.multilevel)
+      n = (double)s->n_steps[l] * s->B;
+    else if (l == s->L - 1)
+      n = (double)s->n_draws * s->B;
+    else
+      n = (double)c[l + 1];
+    h_p_accept[l] = n > 0 ? (double)c[l] / n : 0.0;
   }
+  return 0;
+}
+
+// MCMCStep::reset_stats (montecarlo/mcmcstep.hh) for every level of the sampler
+int mlmcpi_sampler_reset_stats(mlmcpi_sampler *s) {
+  mlmcpi_ctx *ctx = s->ctx;
+  MLMCPI_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->L, ctx->stream));
+  s->n_draws = 0;
+  for (auto &n : s->n_steps)
+    n = 0;
   return 0;
 }
 
@@ -1835,7 +1868,7 @@ int mlmcpi_mlmc_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_m
     const int level = (fine->model == MLMCPI_GFF && fine->rotated ? 1 : 0) + l;
     rc = mlmcpi_coarse_model(&m->model[l], prm->sampler.renorm, level, prm->sampler.ctype,
                              m->model[l].T_final, &c);
-    if (c.model == MLMCPI_GFF && prm->sampler.kind != MLMCPI_SAMPLER_EXACT)
+    if (c.model == MLMCPI_GFF && !ctx->gff_coarse_smoothing)
       c.gff_n_gibbs = 0; // see mlmcpi_sampler_create
     m->model.push_back(c);
   }

@@ -20,7 +20,7 @@
 #endif
 
 // --------------------------------------------------------------------- context
-#define MLMCPI_N_WORK 8
+#define MLMCPI_N_WORK 9
 struct mlmcpi_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -33,6 +33,7 @@ struct mlmcpi_ctx {
   int sweep_reverse = 0;    // MLMCPI_OPT_SWEEP_REVERSE: colours visited in descending order
   int overrelax_one_pass = 1; // MLMCPI_OPT_OVERRELAX_ONE_PASS: all colours of a Schwinger OR sweep in one HBM pass
   int fused_qm_hierarchy = 1; // MLMCPI_OPT_FUSED_QM_HIERARCHY: 1-D hierarchical draw in one kernel
+  int gff_coarse_smoothing = 1; // MLMCPI_OPT_GFF_COARSE_SMOOTHING: coarse GFF levels carry Q_hat (reference)
   uint64_t launches = 0;
   int n_sm = 148;
   // sum over the processes of a run (mlmcpi_set_allreduce); nullptr: single process
@@ -57,6 +58,8 @@ struct mlmcpi_ctx {
   // GFF dense matrices (gffaction.cc:133-174), device [N][N] each, keyed by
   // (Mt, Mx, rotated, mu2, n_gibbs, omega): {Q_hat, transposed inverse of the Cholesky factor U}
   std::map<std::array<double, 6>, std::array<double *, 2>> gff_dense;
+  // cuBLAS / cuSOLVER handles of the dense GFF set-up (created on first use; gff.cu)
+  void *cublas = nullptr, *cusolver = nullptr;
 };
 
 int ctx_fail(mlmcpi_ctx *ctx, int code, const char *what, const char *detail = nullptr);
@@ -651,6 +654,7 @@ int hierarchical_draw(mlmcpi_ctx *, const mlmcpi_model *, int, int, double, doub
 }
 namespace gff {
 int exact_draw(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);
+void release_dense(mlmcpi_ctx *);
 int overrelax_sweeps(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int);
 int sweep_sequence(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int, int, uint32_t, const uint64_t *);
 }

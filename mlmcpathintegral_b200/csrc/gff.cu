@@ -17,6 +17,9 @@
 #include <cmath>
 #include <vector>
 
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
 #include "common.cuh"
 
 namespace {
@@ -541,146 +544,324 @@ int trajectory(mlmcpi_ctx *ctx, const GF &g, int nt, double dt, const double *x_
 
 
 // ===================================================================== dense coarse levels
-// GFFAction::buildMatrices, qft/gffaction.cc:133-174, on the host with plain dense loops
-// (N <= MLMCPI_GFF_DENSE_MAX).  Row-major std::vector<double> matrices.
+// GFFAction::buildMatrices, qft/gffaction.cc:133-174, ON THE DEVICE: the reference's coarse action is
+// S = phi^T Q_hat phi / 2 with the dense N x N matrix
+//     Q_hat = (Sigma_eff + G (Sigma - Sigma_eff) G^T)^{-1},  Sigma = Q^{-1}, Sigma_eff = Q_eff^{-1},
+//     G = (1 - M^{-1} Q_eff)^{n_gibbs},  M = lower triangle of Q_eff (+ (1/omega - 1) diag),
+// Q the 5-point and Q_eff the 9-point effective precision matrix.  G is a lexicographic Gauss-Seidel
+// iteration matrix, so Q_hat is not translation invariant (no FFT shortcut); it is formed with dense
+// linear algebra -- three Cholesky inverses (cuSOLVER potrf/potri), one triangular solve and three
+// products (cuBLAS), ~10 N^3 flops: 0.3 s for 8192 vertices, ~15 s for the 32768 vertices of level 1 of
+// BASELINE config C3 (four N x N work matrices: 34 GB of the 180 GB HBM) -- once per level and context.
+// The reference needs the same matrices through Eigen on one core, O(hours) at that size.
+// All matrices are symmetric or handled in column-major order (element (i, j) at j * N + i).
 namespace {
-typedef std::vector<double> Mat;
 
-Mat mat_mul(const Mat &A, const Mat &B, int N, bool transpose_b = false) {
-  Mat C((size_t)N * N, 0.0);
-  if (transpose_b) {
-    for (int i = 0; i < N; ++i)
-      for (int j = 0; j < N; ++j) {
-        double s = 0.0;
-        for (int k = 0; k < N; ++k)
-          s += A[(size_t)i * N + k] * B[(size_t)j * N + k];
-        C[(size_t)i * N + j] = s;
-      }
+__device__ __forceinline__ void neighbour8(const GF &g, int ell, int nb[8]) {
+  int i, j;
+  v_lin2cart(g.Mt, g.Mx, g.rotated, ell, i, j);
+  if (g.rotated) { // neighbour order of lattice/lattice2d.cc:138-155
+    nb[0] = v_cart2lin(g.Mt, g.Mx, 1, i + 1, j + 1);
+    nb[1] = v_cart2lin(g.Mt, g.Mx, 1, i + 1, j - 1);
+    nb[2] = v_cart2lin(g.Mt, g.Mx, 1, i - 1, j + 1);
+    nb[3] = v_cart2lin(g.Mt, g.Mx, 1, i - 1, j - 1);
+    nb[4] = v_cart2lin(g.Mt, g.Mx, 1, i + 2, j);
+    nb[5] = v_cart2lin(g.Mt, g.Mx, 1, i - 2, j);
+    nb[6] = v_cart2lin(g.Mt, g.Mx, 1, i, j + 2);
+    nb[7] = v_cart2lin(g.Mt, g.Mx, 1, i, j - 2);
   } else {
-    for (int i = 0; i < N; ++i)
-      for (int k = 0; k < N; ++k) {
-        const double a = A[(size_t)i * N + k];
-        if (a == 0.0)
-          continue;
-        for (int j = 0; j < N; ++j)
-          C[(size_t)i * N + j] += a * B[(size_t)k * N + j];
+    nb[0] = v_cart2lin(g.Mt, g.Mx, 0, i + 1, j);
+    nb[1] = v_cart2lin(g.Mt, g.Mx, 0, i - 1, j);
+    nb[2] = v_cart2lin(g.Mt, g.Mx, 0, i, j + 1);
+    nb[3] = v_cart2lin(g.Mt, g.Mx, 0, i, j - 1);
+    nb[4] = v_cart2lin(g.Mt, g.Mx, 0, i + 1, j + 1);
+    nb[5] = v_cart2lin(g.Mt, g.Mx, 0, i + 1, j - 1);
+    nb[6] = v_cart2lin(g.Mt, g.Mx, 0, i - 1, j + 1);
+    nb[7] = v_cart2lin(g.Mt, g.Mx, 0, i - 1, j - 1);
+  }
+}
+
+// GFFAction::buildPrecisionMatrix, gffaction.cc:177-197 (A zeroed beforehand; one thread owns one row,
+// entries of coinciding neighbours on tiny lattices accumulate as setFromTriplets does)
+__global__ void precision_matrix_kernel(GF g, double s0, double s1, double s2, int n_stencil, double *A) {
+  const int ell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ell >= g.N)
+    return;
+  int nb[8];
+  neighbour8(g, ell, nb);
+  double *row = A + (size_t)ell * g.N;
+  row[ell] += s0;
+  for (int k = 0; k < 4; ++k)
+    row[nb[k]] += s1;
+  if (n_stencil > 2)
+    for (int k = 4; k < 8; ++k)
+      row[nb[k]] += s2;
+}
+// potrf / potri work on the lower triangle: complete the symmetric matrix
+__global__ void mirror_lower_kernel(int N, double *A) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)N * N)
+    return;
+  const int i = (int)(t % N), j = (int)(t / N);
+  if (i < j) // (i, j) in the upper triangle <- (j, i)
+    A[t] = A[(size_t)i * N + j];
+}
+__global__ void one_minus_kernel(int N, double *A) { // A <- 1 - A
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)N * N)
+    return;
+  const int i = (int)(t % N), j = (int)(t / N);
+  A[t] = (i == j ? 1.0 : 0.0) - A[t];
+}
+__global__ void sub_kernel(size_t n, double *A, const double *B) { // A <- A - B
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n)
+    A[t] -= B[t];
+}
+__global__ void add_diag_kernel(int N, double *A, const double *Dsrc, double f) { // A_ii += f * Dsrc_ii
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N)
+    A[(size_t)i * N + i] += f * Dsrc[(size_t)i * N + i];
+}
+__global__ void symmetrise_kernel(int N, double *A) { // A <- (A + A^T) / 2, lower and upper at once
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)N * N)
+    return;
+  const int i = (int)(t % N), j = (int)(t / N);
+  if (i > j) {
+    const size_t u = (size_t)i * N + j;
+    const double v = 0.5 * (A[t] + A[u]);
+    A[t] = v;
+    A[u] = v;
+  }
+}
+__global__ void identity_kernel(int N, double *A) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)N * N)
+    return;
+  A[t] = (t % N == t / N) ? 1.0 : 0.0;
+}
+
+struct DenseLA {
+  mlmcpi_ctx *ctx;
+  int N;
+  cublasHandle_t blas;
+  cusolverDnHandle_t solver;
+  int *info = nullptr;
+  double *work = nullptr;
+  int lwork = 0;
+  std::vector<double *> owned;
+  const char *fail = nullptr;
+
+  bool init() {
+    if (!ctx->cublas) {
+      cublasHandle_t h;
+      if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS)
+        return false;
+      ctx->cublas = h;
+    }
+    if (!ctx->cusolver) {
+      cusolverDnHandle_t h;
+      if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS)
+        return false;
+      ctx->cusolver = h;
+    }
+    blas = (cublasHandle_t)ctx->cublas;
+    solver = (cusolverDnHandle_t)ctx->cusolver;
+    cublasSetStream(blas, ctx->stream);
+    cusolverDnSetStream(solver, ctx->stream);
+    return cudaMalloc((void **)&info, sizeof(int)) == cudaSuccess;
+  }
+  double *matrix() {
+    double *d = nullptr;
+    if (cudaMalloc((void **)&d, (size_t)N * N * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      fail = "out of device memory for the dense GFF matrices";
+      return nullptr;
+    }
+    owned.push_back(d);
+    return d;
+  }
+  void release(double *keep0 = nullptr, double *keep1 = nullptr) {
+    for (double *d : owned)
+      if (d != keep0 && d != keep1)
+        cudaFree(d);
+    owned.clear();
+    if (info)
+      cudaFree(info);
+    if (work)
+      cudaFree(work);
+    info = nullptr;
+    work = nullptr;
+  }
+  int grid2() const { return (int)(((size_t)N * N + 255) / 256); }
+  bool ensure_work(int need) {
+    if (need <= lwork)
+      return true;
+    if (work)
+      cudaFree(work);
+    work = nullptr;
+    lwork = 0;
+    if (cudaMalloc((void **)&work, (size_t)need * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      fail = "out of device memory for the cuSOLVER workspace";
+      return false;
+    }
+    lwork = need;
+    return true;
+  }
+  bool check_info(const char *what) {
+    int h = 0;
+    cudaMemcpyAsync(&h, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    if (h != 0) {
+      fail = what;
+      return false;
+    }
+    return true;
+  }
+  bool precision(double *A, const GF &g, double s0, double s1, double s2, int n_stencil) {
+    cudaMemsetAsync(A, 0, (size_t)N * N * sizeof(double), ctx->stream);
+    precision_matrix_kernel<<<cdiv(N, 128), 128, 0, ctx->stream>>>(g, s0, s1, s2, n_stencil, A);
+    return cudaGetLastError() == cudaSuccess;
+  }
+  bool cholesky(double *A) { // lower factor in place
+    int need = 0;
+    if (cusolverDnDpotrf_bufferSize(solver, CUBLAS_FILL_MODE_LOWER, N, A, N, &need) != CUSOLVER_STATUS_SUCCESS ||
+        !ensure_work(need))
+      return false;
+    if (cusolverDnDpotrf(solver, CUBLAS_FILL_MODE_LOWER, N, A, N, work, lwork, info) != CUSOLVER_STATUS_SUCCESS)
+      return false;
+    return check_info("GFF dense matrices: matrix not positive definite");
+  }
+  bool spd_inverse(double *A) { // symmetric positive definite inverse in place (full matrix on return)
+    if (!cholesky(A))
+      return false;
+    int need = 0;
+    if (cusolverDnDpotri_bufferSize(solver, CUBLAS_FILL_MODE_LOWER, N, A, N, &need) != CUSOLVER_STATUS_SUCCESS ||
+        !ensure_work(need))
+      return false;
+    if (cusolverDnDpotri(solver, CUBLAS_FILL_MODE_LOWER, N, A, N, work, lwork, info) != CUSOLVER_STATUS_SUCCESS)
+      return false;
+    if (!check_info("GFF dense matrices: inversion failed"))
+      return false;
+    mirror_lower_kernel<<<grid2(), 256, 0, ctx->stream>>>(N, A);
+    return cudaGetLastError() == cudaSuccess;
+  }
+  bool gemm(const double *A, const double *B, bool transpose_b, double beta, double *C) { // C = A op(B) + beta C
+    const double one = 1.0;
+    return cublasDgemm(blas, CUBLAS_OP_N, transpose_b ? CUBLAS_OP_T : CUBLAS_OP_N, N, N, N, &one, A, N, B, N,
+                       &beta, C, N) == CUBLAS_STATUS_SUCCESS;
+  }
+};
+
+// Q_hat of a coarse level (n_gibbs > 0)
+int build_qhat(mlmcpi_ctx *ctx, const GF &g, int n_gibbs, double omega, double **out) {
+  DenseLA la{ctx, g.N};
+  *out = nullptr;
+  if (!la.init())
+    return ctx_fail(ctx, MLMCPI_ECUDA, "cannot create the cuBLAS / cuSOLVER handles");
+  const int N = g.N;
+  const size_t nn = (size_t)N * N;
+  double *A = la.matrix(), *E = la.matrix(), *X = la.matrix(), *G = nullptr;
+  bool ok = A && E && X;
+  const double d = 4. + 0.5 * g.mu2;
+  ok = ok && la.precision(A, g, 4. + g.mu2, -1., 0., 2);          // Q          (gffaction.cc:137-140)
+  ok = ok && la.precision(E, g, d - 4. / d, -2. / d, -1. / d, 3); // Q_eff      (:143-148)
+  // G1 = 1 - M^{-1} Q_eff (:150-159): X <- Q_eff, solve M X = Q_eff with M = the lower triangle of E
+  if (ok) {
+    cudaMemcpyAsync(X, E, nn * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    const double *Mtri = E;
+    double *Mmod = nullptr;
+    if (std::fabs(omega - 1.0) > 1.E-14) { // M += (1/omega - 1) diag(Q_eff)
+      Mmod = la.matrix();
+      ok = Mmod != nullptr;
+      if (ok) {
+        cudaMemcpyAsync(Mmod, E, nn * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+        add_diag_kernel<<<cdiv(N, 128), 128, 0, ctx->stream>>>(N, Mmod, E, 1. / omega - 1.);
+        Mtri = Mmod;
+      }
+    }
+    const double one = 1.0;
+    ok = ok && cublasDtrsm(la.blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, N, N,
+                           &one, Mtri, N, X, N) == CUBLAS_STATUS_SUCCESS;
+    if (ok)
+      one_minus_kernel<<<la.grid2(), 256, 0, ctx->stream>>>(N, X);
+    if (Mmod) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(Mmod);
+      la.owned.pop_back();
+    }
+  }
+  // G = G1^{n_gibbs} (:158-160); for the reference's n_gibbs = 2 this is one product into one new matrix
+  G = X;
+  {
+    double *P[2] = {nullptr, nullptr};
+    for (int k = 1; k < n_gibbs && ok; ++k) {
+      const int dst = (G == P[0]) ? 1 : 0;
+      if (!P[dst])
+        P[dst] = la.matrix();
+      ok = P[dst] != nullptr && la.gemm(G, X, false, 0.0, P[dst]);
+      G = P[dst];
+    }
+    for (double *f : P)
+      if (f && f != G) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(f);
+        la.owned.erase(std::find(la.owned.begin(), la.owned.end(), f));
       }
   }
-  return C;
-}
-
-// lower Cholesky factor of a symmetric positive definite matrix; false if it is not
-bool cholesky_lower(const Mat &A, int N, Mat &L) {
-  L.assign((size_t)N * N, 0.0);
-  for (int j = 0; j < N; ++j) {
-    double s = A[(size_t)j * N + j];
-    for (int k = 0; k < j; ++k)
-      s -= L[(size_t)j * N + k] * L[(size_t)j * N + k];
-    if (!(s > 0.0))
-      return false;
-    const double ljj = std::sqrt(s);
-    L[(size_t)j * N + j] = ljj;
-    for (int i = j + 1; i < N; ++i) {
-      double t = A[(size_t)i * N + j];
-      for (int k = 0; k < j; ++k)
-        t -= L[(size_t)i * N + k] * L[(size_t)j * N + k];
-      L[(size_t)i * N + j] = t / ljj;
-    }
+  // Sigma, Sigma_eff (:141, :149), D = Sigma - Sigma_eff in A
+  ok = ok && la.spd_inverse(A) && la.spd_inverse(E);
+  if (ok)
+    sub_kernel<<<la.grid2(), 256, 0, ctx->stream>>>(nn, A, E);
+  // Sigma_hat = Sigma_eff + G D G^T (:164-165), accumulated into E; T = G D
+  if (ok) {
+    double *T = (G == X) ? la.matrix() : X;
+    ok = T != nullptr;
+    ok = ok && la.gemm(G, A, false, 0.0, T) && la.gemm(T, G, true, 1.0, E);
   }
-  return true;
-}
-
-// inverse of a lower triangular matrix
-Mat lower_inverse(const Mat &L, int N) {
-  Mat X((size_t)N * N, 0.0);
-  for (int c = 0; c < N; ++c) {
-    X[(size_t)c * N + c] = 1.0 / L[(size_t)c * N + c];
-    for (int i = c + 1; i < N; ++i) {
-      double s = 0.0;
-      for (int k = c; k < i; ++k)
-        s += L[(size_t)i * N + k] * X[(size_t)k * N + c];
-      X[(size_t)i * N + c] = -s / L[(size_t)i * N + i];
-    }
+  if (ok) // symmetrise the rounding before the Cholesky inverse
+    symmetrise_kernel<<<la.grid2(), 256, 0, ctx->stream>>>(N, E);
+  ok = ok && la.spd_inverse(E); // Q_hat
+  ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+  if (!ok) {
+    const char *why = la.fail ? la.fail : "cuBLAS / cuSOLVER call failed";
+    la.release();
+    return ctx_fail(ctx, MLMCPI_EINVAL, "GFF dense matrices", why);
   }
-  return X;
+  la.release(E);
+  *out = E;
+  return 0;
 }
 
-bool spd_inverse(const Mat &A, int N, Mat &Ainv) {
-  Mat L;
-  if (!cholesky_lower(A, N, L))
-    return false;
-  const Mat Li = lower_inverse(L, N); // A^{-1} = L^{-T} L^{-1}
-  Ainv.assign((size_t)N * N, 0.0);
-  for (int k = 0; k < N; ++k)
-    for (int i = 0; i <= k; ++i) {
-      const double a = Li[(size_t)k * N + i];
-      if (a == 0.0)
-        continue;
-      for (int j = 0; j <= k; ++j)
-        Ainv[(size_t)i * N + j] += a * Li[(size_t)k * N + j];
-    }
-  return true;
-}
-
-// GFFAction::buildPrecisionMatrix, gffaction.cc:177-197
-Mat precision_matrix(const GF &g, const std::vector<double> &stencil) {
-  Mat Q((size_t)g.N * g.N, 0.0);
-  uint32_t nb[8];
-  for (int ell = 0; ell < g.N; ++ell) {
-    mlmcpi_neighbours(g.Mt, g.Mx, g.rotated, (uint32_t)ell, nb);
-    Q[(size_t)ell * g.N + ell] += stencil[0];
-    for (size_t j = 0; j + 1 < stencil.size(); ++j)
-      for (int k = 0; k < 4; ++k)
-        Q[(size_t)ell * g.N + nb[4 * j + k]] += stencil[j + 1];
-  }
-  return Q;
-}
-
-// Q_hat (only when n_gibbs > 0) and the transposed inverse of U = L^T, Q = L L^T
-bool build_dense(const GF &g, int n_gibbs, double omega, Mat &Qhat, Mat &UinvT) {
+// U^{-1} with Q = L L^T = U^T U (the exact sampler solves U phi = psi, gffaction.cc:166-173,200-208):
+// stored so that element [j * N + i] = (L^{-1})(j, i) = (U^{-1})(i, j)
+int build_uinv(mlmcpi_ctx *ctx, const GF &g, double **out) {
+  DenseLA la{ctx, g.N};
+  *out = nullptr;
+  if (!la.init())
+    return ctx_fail(ctx, MLMCPI_ECUDA, "cannot create the cuBLAS / cuSOLVER handles");
   const int N = g.N;
-  const Mat Q = precision_matrix(g, {4. + g.mu2, -1.});
-  Mat L;
-  if (!cholesky_lower(Q, N, L))
-    return false;
-  // U^{-1} = (L^T)^{-1} = (L^{-1})^T, so the transposed inverse of U is L^{-1} itself
-  UinvT = lower_inverse(L, N);
-  Qhat.clear();
-  if (n_gibbs <= 0)
-    return true;
-  const double d = 4. + 0.5 * g.mu2;
-  const Mat Qe = precision_matrix(g, {d - 4. / d, -2. / d, -1. / d});
-  Mat Sigma, Sigma_e;
-  if (!spd_inverse(Q, N, Sigma) || !spd_inverse(Qe, N, Sigma_e))
-    return false;
-  // M = lower triangle of Q_eff (+ (1/omega - 1) diag);  G1 = 1 - M^{-1} Q_eff
-  Mat M((size_t)N * N, 0.0);
-  for (int i = 0; i < N; ++i)
-    for (int j = 0; j <= i; ++j)
-      M[(size_t)i * N + j] = Qe[(size_t)i * N + j];
-  if (std::fabs(omega - 1.0) > 1.E-14)
-    for (int i = 0; i < N; ++i)
-      M[(size_t)i * N + i] += (1. / omega - 1.) * Qe[(size_t)i * N + i];
-  Mat G1 = mat_mul(lower_inverse(M, N), Qe, N);
-  for (size_t k = 0; k < G1.size(); ++k)
-    G1[k] = -G1[k];
-  for (int i = 0; i < N; ++i)
-    G1[(size_t)i * N + i] += 1.0;
-  Mat G = G1;
-  for (int k = 1; k < n_gibbs; ++k)
-    G = mat_mul(G, G1, N);
-  Mat D(Sigma);
-  for (size_t k = 0; k < D.size(); ++k)
-    D[k] -= Sigma_e[k];
-  Mat Sh = mat_mul(mat_mul(G, D, N), G, N, true); // G (Sigma - Sigma_eff) G^T
-  for (size_t k = 0; k < Sh.size(); ++k)
-    Sh[k] += Sigma_e[k];
-  for (int i = 0; i < N; ++i) // symmetrise the rounding before the Cholesky inverse
-    for (int j = 0; j < i; ++j) {
-      const double v = 0.5 * (Sh[(size_t)i * N + j] + Sh[(size_t)j * N + i]);
-      Sh[(size_t)i * N + j] = Sh[(size_t)j * N + i] = v;
-    }
-  return spd_inverse(Sh, N, Qhat);
+  double *A = la.matrix(), *Z = la.matrix();
+  bool ok = A && Z;
+  ok = ok && la.precision(A, g, 4. + g.mu2, -1., 0., 2) && la.cholesky(A);
+  if (ok) {
+    identity_kernel<<<la.grid2(), 256, 0, ctx->stream>>>(N, Z);
+    // column-major Z = L^{-T}: solve L^T Z = 1
+    const double one = 1.0;
+    ok = cublasDtrsm(la.blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, N, N, &one,
+                     A, N, Z, N) == CUBLAS_STATUS_SUCCESS;
+  }
+  ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+  if (!ok) {
+    const char *why = la.fail ? la.fail : "cuBLAS / cuSOLVER call failed";
+    la.release();
+    return ctx_fail(ctx, MLMCPI_EINVAL, "GFF exact sampler", why);
+  }
+  la.release(Z);
+  *out = Z;
+  return 0;
 }
 
 // S = phi^T Q_hat phi / 2 (gffaction.cc:25-28): one block per chain, phi staged in shared
@@ -770,6 +951,7 @@ __global__ void gibbs_eff_kernel(GF g, double omega, int sweep, double *x_all, i
   }
 }
 
+// lazily built, cached per (lattice, mu2, n_gibbs, omega) in the context: Q_hat and / or U^{-1}
 int dense_get(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double **Qhat, const double **UinvT) {
   const GF g = make_gf(m);
   if (g.N > MLMCPI_GFF_DENSE_MAX)
@@ -778,31 +960,68 @@ int dense_get(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double **Qhat, const
   const std::array<double, 6> key = {(double)g.Mt,          (double)g.Mx, (double)g.rotated, g.mu2,
                                      (double)m->gff_n_gibbs, m->gff_omega};
   auto it = ctx->gff_dense.find(key);
-  if (it == ctx->gff_dense.end()) {
-    Mat Qh, Ut;
-    if (!build_dense(g, m->gff_n_gibbs, m->gff_n_gibbs > 0 ? m->gff_omega : 1.0, Qh, Ut))
-      return ctx_fail(ctx, MLMCPI_EINVAL, "GFF dense matrices: matrix not positive definite");
-    std::array<double *, 2> d = {nullptr, nullptr};
-    const size_t bytes = (size_t)g.N * g.N * sizeof(double);
-    if (!Qh.empty()) {
-      MLMCPI_CUDA(cudaMalloc((void **)&d[0], bytes));
-      MLMCPI_CUDA(cudaMemcpyAsync(d[0], Qh.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    MLMCPI_CUDA(cudaMalloc((void **)&d[1], bytes));
-    MLMCPI_CUDA(cudaMemcpyAsync(d[1], Ut.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-    MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
-    it = ctx->gff_dense.emplace(key, d).first;
-  }
-  if (Qhat)
+  if (it == ctx->gff_dense.end())
+    it = ctx->gff_dense.emplace(key, std::array<double *, 2>{nullptr, nullptr}).first;
+  int rc;
+  if (Qhat) {
+    if (m->gff_n_gibbs <= 0)
+      return ctx_fail(ctx, MLMCPI_EINVAL, "GFF dense action requested for a level without Gibbs smoothing");
+    if (!it->second[0] && (rc = build_qhat(ctx, g, m->gff_n_gibbs, m->gff_omega, &it->second[0])))
+      return rc;
     *Qhat = it->second[0];
-  if (UinvT)
+  }
+  if (UinvT) {
+    if (!it->second[1] && (rc = build_uinv(ctx, g, &it->second[1])))
+      return rc;
     *UinvT = it->second[1];
+  }
   return 0;
+}
+
+// levels above this size evaluate Q_hat Phi / U^{-1} Psi for all chains with one DGEMM
+constexpr int DENSE_GEMM_MIN = 2048;
+
+// S[b] = 1/2 sum_i phi[b][i] y[b][i]
+__global__ void half_dot_kernel(int N, const double *x, const double *y, double *S) {
+  const int chain = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    acc += x[(size_t)chain * N + i] * y[(size_t)chain * N + i];
+  const double v = block_sum(acc);
+  if (threadIdx.x == 0)
+    S[chain] = 0.5 * v;
+}
+// psi i.i.d. N(0,1), the variates of dense_draw_kernel
+__global__ void normal_fill_kernel(int N, double *psi, int B, uint32_t chain0, uint64_t seed, uint64_t draw) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = (N + 1) / 2;
+  if (t >= (long long)half * B)
+    return;
+  const int chain = (int)(t / half), k = (int)(t - (long long)chain * half);
+  Rng r = rng_init(seed, MLMCPI_STREAM_EXACT, draw, chain0 + chain, k);
+  double z0, z1;
+  rng_normal2(r, z0, z1);
+  psi[(size_t)chain * N + 2 * k] = z0;
+  if (2 * k + 1 < N)
+    psi[(size_t)chain * N + 2 * k + 1] = z1;
 }
 
 } // namespace
 
 namespace gff {
+
+void release_dense(mlmcpi_ctx *ctx) {
+  for (auto &kv : ctx->gff_dense)
+    for (double *d : kv.second)
+      if (d)
+        cudaFree(d);
+  ctx->gff_dense.clear();
+  if (ctx->cublas)
+    cublasDestroy((cublasHandle_t)ctx->cublas);
+  if (ctx->cusolver)
+    cusolverDnDestroy((cusolverDnHandle_t)ctx->cusolver);
+  ctx->cublas = ctx->cusolver = nullptr;
+}
 
 int init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0,
                uint64_t draw) {
@@ -820,6 +1039,21 @@ int action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *x, int B, doubl
     int rc = dense_get(ctx, m, &Qhat, nullptr);
     if (rc)
       return rc;
+    if (g.N >= DENSE_GEMM_MIN) { // Y = Q_hat Phi for all chains (states [B][N] = column-major N x B)
+      double *Y = ctx_work(ctx, 8, (size_t)g.N * B);
+      if (!Y)
+        return ctx_fail(ctx, MLMCPI_ENOMEM, "out of device memory for the dense GFF action");
+      const double one = 1.0, zero = 0.0;
+      cublasHandle_t blas = (cublasHandle_t)ctx->cublas;
+      cublasSetStream(blas, ctx->stream);
+      if (cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, g.N, B, g.N, &one, Qhat, g.N, x, g.N, &zero, Y, g.N) !=
+          CUBLAS_STATUS_SUCCESS)
+        return ctx_fail(ctx, MLMCPI_ECUDA, "cublasDgemm (dense GFF action)");
+      ctx->launches++;
+      half_dot_kernel<<<B, 256, 0, ctx->stream>>>(g.N, x, Y, S);
+      MLMCPI_LAUNCHED("gff::dense_action_dot");
+      return 0;
+    }
     const int threads = std::min(512, ((g.N + 31) / 32) * 32);
     dense_action_kernel<<<B, threads, (size_t)g.N * sizeof(double), ctx->stream>>>(g.N, Qhat, x, S);
     MLMCPI_LAUNCHED("gff::dense_action");
@@ -835,10 +1069,27 @@ int exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_
   int rc = dense_get(ctx, m, nullptr, &UinvT);
   if (rc)
     return rc;
-  const int threads = std::min(512, ((g.N + 31) / 32) * 32);
-  dense_draw_kernel<<<B, threads, (size_t)(g.N + 1) * sizeof(double), ctx->stream>>>(g.N, UinvT, x, chain0,
-                                                                                    ctx->seed, draw);
-  MLMCPI_LAUNCHED("gff::dense_draw");
+  if (g.N >= DENSE_GEMM_MIN) { // phi = U^{-1} psi for all chains with one DGEMM
+    double *Psi = ctx_work(ctx, 8, (size_t)g.N * B);
+    if (!Psi)
+      return ctx_fail(ctx, MLMCPI_ENOMEM, "out of device memory for the exact GFF draw");
+    normal_fill_kernel<<<cdiv((long long)((g.N + 1) / 2) * B, 256), 256, 0, ctx->stream>>>(g.N, Psi, B, chain0,
+                                                                                        ctx->seed, draw);
+    MLMCPI_LAUNCHED("gff::normal_fill");
+    const double one = 1.0, zero = 0.0;
+    cublasHandle_t blas = (cublasHandle_t)ctx->cublas;
+    cublasSetStream(blas, ctx->stream);
+    // UinvT[j * N + i] = U^{-1}(i, j): as a column-major matrix it IS U^{-1}
+    if (cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, g.N, B, g.N, &one, UinvT, g.N, Psi, g.N, &zero, x, g.N) !=
+        CUBLAS_STATUS_SUCCESS)
+      return ctx_fail(ctx, MLMCPI_ECUDA, "cublasDgemm (exact GFF draw)");
+    ctx->launches++;
+  } else {
+    const int threads = std::min(512, ((g.N + 31) / 32) * 32);
+    dense_draw_kernel<<<B, threads, (size_t)(g.N + 1) * sizeof(double), ctx->stream>>>(g.N, UinvT, x, chain0,
+                                                                                      ctx->seed, draw);
+    MLMCPI_LAUNCHED("gff::dense_draw");
+  }
   for (int k = 0; k < m->gff_n_gibbs; ++k) {
     gibbs_eff_kernel<<<cdiv(B, 32), 32, 0, ctx->stream>>>(g, m->gff_omega, k, x, B, chain0, ctx->seed, draw);
     MLMCPI_LAUNCHED("gff::gibbs_eff");

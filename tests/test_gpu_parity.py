@@ -456,6 +456,23 @@ def test_gff_dense_coarse_level(mp, ctx, orc):
         assert abs(out["average"] - ref) < 5 * out["error"], (M, out, ref, p)
 
 
+def test_gff_dense_action_2048_vertices_against_reference(mp, ctx):
+    """the dense coarse action built ON THE DEVICE (cuSOLVER / cuBLAS, csrc/gff.cu) and evaluated with
+    one DGEMM over all chains, at the largest size the reference's own buildMatrices finishes here in
+    minutes: 64 x 64 fine lattice, rotated coarse level of 2048 vertices; values recorded from the
+    reference's GFFAction::evaluate (tools/make_golden.py --gff-dense, tests/golden/gff_dense.json)"""
+    from tools.make_golden import noncompact
+    for c in load("gff_dense"):
+        m = mp.gff(c["Mt"], c["Mt"], c["mass"])
+        mc = mp.coarse_model(m, ctype=mp.COARSEN_ROTATE)
+        assert mp.sample_size(mc) == c["n_coarse"] and mc.gff_n_gibbs == 2
+        xf = np.array([noncompact(mp.sample_size(m), sh) for sh in c["shifts"]])
+        xc = ctx.state(mc, len(c["shifts"]))
+        ctx.restrict(m, dev(ctx, xf), xc)
+        want = [scalar(v) for v in c["coarse_S_gibbs"]]
+        close(host(ctx.action(mc, xc)), want, tol=1e-9, what="dense Q_hat action, 2048 vertices")
+
+
 # --------------------------------------------------- statistics accumulators
 
 

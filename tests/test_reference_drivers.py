@@ -1,0 +1,126 @@
+"""The reference's OWN drivers -- /root/reference/src/driver_qft.cc and driver_qm.cc, byte for byte --
+compiled against include/mlmcpi/compat (the reference's header paths and class names over the device
+library) and run on the GPU with the very parameter files the CPU reference was run with.
+
+CPU (here, where /root/reference exists): `make -C examples reference-drivers` compiles the two
+files unmodified (they are fed to the compiler through stdin; nothing is copied), the binaries parse
+the reference's parameter template and stop loudly for want of a GPU.
+GPU: the prebuilt binaries (examples/_ref/, git-ignored, travels with the snapshot) run the
+parameter files stored in tests/golden/stats.json -- the files tools/make_golden_stats.py fed to
+the stock CPU drivers oracle/_ref/driver_q* -- and their print-out (estimator, error, tau_int,
+acceptance per level, comparison with the analytic result) is compared with the CPU reference's.
+"""
+import hashlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.util import load
+from tools.make_golden_stats import parse_output, render
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+BUILD = os.path.join(ROOT, "examples", "_ref")
+EXE = {d: os.path.join(BUILD, f"driver_{d}_reference") for d in ("qft", "qm")}
+STATS = load("stats")
+
+
+def _sha(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src")), reason="the reference sources are not on this box")
+def test_reference_drivers_compile_unmodified(tmp_path):
+    import torch
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "reference-drivers"], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for d in ("qft", "qm"):
+        assert os.access(EXE[d], os.X_OK)
+        # provenance: the binary was built from the reference's file as it lies in /root/reference
+        assert open(EXE[d] + ".source_sha256").read().strip() == _sha(os.path.join(REF, "src", f"driver_{d}.cc"))
+    # the reference's own template (action set to a supported model; the qm template lacks three keys
+    # of twolevelmc)
+    tpl = open(os.path.join(REF, "parameters_qft_template.in")).read()
+    text = render(tpl, {"quantumfieldtheory": {"action": "'quenchedschwinger'"}, "schwinger": {"beta": 4.0}})
+    p = tmp_path / "parameters_qft.in"
+    p.write_text(text)
+    r = subprocess.run([EXE["qft"], str(p)], capture_output=True, text=True, timeout=600)
+    assert "for the 2D Schwinger model" in r.stdout and "E[V*chi_t]" in r.stdout and "Mt_lat = 16" in r.stdout
+    if not torch.cuda.is_available():
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    r = subprocess.run([EXE["qft"], str(tmp_path / "missing.in")], capture_output=True, text=True)
+    assert r.returncode == 1  # Parameters::readFile convention: message, `return 1` (driver_qft.cc:131-133)
+    tpl = open(os.path.join(REF, "parameters_qm_template.in")).read()
+    text = render(tpl, {"twolevelmc": {"n_coarse_autocorr_window": 10, "n_fine_autocorr_window": 10,
+                                       "n_delta_autocorr_window": 10}})
+    p = tmp_path / "parameters_qm.in"
+    p.write_text(text)
+    r = subprocess.run([EXE["qm"], str(p)], capture_output=True, text=True, timeout=600)
+    assert "<chi_t>" in r.stdout and "M_lat = 32" in r.stdout
+    if not torch.cuda.is_available():
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def _run(case, chains, tmp_path, timeout=1500):
+    ref = STATS[case]
+    exe = EXE["qft" if ref["driver"] == "driver_qft" else "qm"]
+    if not os.access(exe, os.X_OK):
+        pytest.skip("examples/_ref/ has not been built (make -C examples reference-drivers, needs /root/reference)")
+    p = tmp_path / "parameters.in"
+    p.write_text(ref["parameters"])
+    env = dict(os.environ, MLMCPI_CHAINS=str(chains))
+    r = subprocess.run([exe, str(p)], capture_output=True, text=True, timeout=timeout, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return ref, parse_output(r.stdout), r.stdout
+
+
+CASES = [("schwinger16_b4_hier2_cluster", 512), ("schwinger32_b16_hier2_cluster", 512),
+         ("schwinger64_b64_hier2_cluster", 256), ("schwinger16_b4_hier2_hmc", 512),
+         ("schwinger16_b4_cluster", 512), ("gff16_hier2_heatbath", 512), ("gff16_hier2_hmc", 512),
+         ("rotor32_hier3_hmc", 1024), ("rotor64_cluster", 1024)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,chains", CASES, ids=[c[0] for c in CASES])
+def test_reference_driver_on_gpu_matches_reference_driver_on_cpu(case, chains, tmp_path):
+    ref, got, out = _run(case, chains, tmp_path)
+    msg = (f"{case}: GPU {got['average']:.5f} +- {got['error']:.5f} tau_int {got['tau_int']:.2f} acceptance "
+           f"{got['acceptance']} | CPU reference {ref['average']:.5f} +- {ref['error']:.5f} tau_int "
+           f"{ref['tau_int']:.2f} acceptance {ref['acceptance']} | analytic {ref.get('analytical')}")
+    print(msg)
+    assert got["window"] == ref["window"]
+    assert got["samples"] >= ref["samples"]  # ceil(n_samples / chains) draws on every chain
+    comb = float(np.hypot(got["error"], ref["error"]))
+    assert abs(got["average"] - ref["average"]) <= 4.5 * comb, msg
+    assert abs(got["tau_int"] - ref["tau_int"]) <= 0.3 * ref["tau_int"] + 0.5, msg
+    if ref["acceptance"]:
+        a, b = np.array(got["acceptance"]), np.array(ref["acceptance"])
+        assert a.shape == b.shape and np.all(np.abs(a - b) <= 0.02 + 0.05 * b), msg
+    # the drivers' own last line: (analytical - numerical) in units of the statistical error
+    m = re.search(r"\(analytical - numerical\) = ([0-9.eE+-]+) = ([0-9.eE+-]+) \* \(statistical error\)", out)
+    if ref.get("analytical") is not None and abs(ref["average"] - ref["analytical"]) <= 3 * ref["error"]:
+        assert m and float(m.group(2)) <= 4.5, msg
+
+
+@pytest.mark.gpu
+def test_reference_driver_qft_template_on_gpu(tmp_path):
+    """VERDICT r01 task 3: parameters_qft_template.in with the action set to a supported model, through
+    the unmodified driver_qft.cc; the (analytical - numerical) line must come out within errors"""
+    ref = STATS["schwinger16_b4_heatbath"]
+    exe = EXE["qft"]
+    if not os.access(exe, os.X_OK):
+        pytest.skip("examples/_ref/ has not been built")
+    p = tmp_path / "parameters.in"
+    p.write_text(ref["parameters"])
+    r = subprocess.run([exe, str(p)], capture_output=True, text=True, timeout=1500,
+                       env=dict(os.environ, MLMCPI_CHAINS="512"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    m = re.search(r"\(analytical - numerical\) = ([0-9.eE+-]+) = ([0-9.eE+-]+) \* \(statistical error\)", r.stdout)
+    assert m, r.stdout[-2000:]
+    assert float(m.group(2)) <= 4.5, r.stdout[-2000:]
+    got = parse_output(r.stdout)
+    assert abs(got["average"] - ref["average"]) <= 4.5 * float(np.hypot(got["error"], ref["error"]))

@@ -213,6 +213,23 @@ def gff_cases(R):
     return cases
 
 
+def gff_dense_cases(R, sizes=(64,)):
+    """the reference's dense coarse-level action (gffaction.cc:25-28, 133-174) at the largest sizes its
+    own buildMatrices finishes here in minutes (the Eigen shim inverts with plain O(N^3) loops):
+    fine lattice Mt x Mt, coarsening rotate -> coarse level of Mt^2 / 2 vertices.  Only the inputs'
+    generating formula and the action values are stored."""
+    cases = []
+    for Mt in sizes:
+        a = R.action(po.GFF, [Mt, Mt, po.ROTATE], [10.0])
+        ac = a.coarse()
+        vals = []
+        for shift in (0.0, 0.3, 1.1):
+            xc = ac.copy_from_fine(noncompact(a.n, shift))
+            vals.append(hx(ac.evaluate(xc)))
+        cases.append(dict(Mt=Mt, mass=10.0, n_coarse=ac.n, shifts=[0.0, 0.3, 1.1], coarse_S_gibbs=vals))
+    return cases
+
+
 def scalar_cases(R):
     L = R.lib
     xs = [-7.5, -np.pi, -3.0, -1e-3, 0.0, 0.5, 3.0, np.pi, 3.2, 6.5, 100.25, -100.25]
@@ -282,6 +299,12 @@ def main():
     po.build(ref=True)
     R = po.ref()
     os.makedirs(OUT, exist_ok=True)
+    if "--gff-dense" in sys.argv:  # slow (minutes): recorded separately
+        path = os.path.join(OUT, "gff_dense.json")
+        with open(path, "w") as f:
+            json.dump(gff_dense_cases(R), f, separators=(",", ":"))
+        print("wrote", path)
+        return
     for name, data in [("lattice", lattice_cases(R)), ("qm", qm_cases(R)),
                        ("schwinger", schwinger_cases(R)), ("gff", gff_cases(R)),
                        ("scalars", scalar_cases(R))]:

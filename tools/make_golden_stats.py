@@ -96,6 +96,26 @@ CASES = {
         "singlelevelmc": {"n_burnin": 1000, "n_samples": 50000, "sampler": "'hierarchical'"},
         "hierarchical": {"n_max_level": 4, "coarsesampler": "'heatbath'"},
         "heatbath": {"n_sweep_overrelax": 10, "n_sweep_heatbath": 1, "random_order": "false"}}),
+    # --- the same hierarchies with the HMC coarse sampler: HMC integrates the 5-point force but accepts with
+    #     Action::evaluate = Q_hat (hmcsampler.cc:21-69), so it samples Q_hat exactly: a CONSISTENT
+    #     algorithm, whose estimator does not depend on sweep orders and must agree within errors.
+    #     (coarsesampler = 'exact' cannot serve: GFFAction::draw never sets the `accept` flag of MCMCStep,
+    #     so HierarchicalSampler::draw breaks out at hierarchicalsampler.cc:73 on every draw and the
+    #     reference driver prints avg = 0, p = nan.)
+    "gff16_hier2_hmc": dict(driver="qft", set={
+        "quantumfieldtheory": {"action": "'gff'"},
+        "lattice": {"Mt_lat": 16, "Mx_lat": 16, "coarsening": "'rotate'"},
+        "gff": {"mass": 10.0},
+        "singlelevelmc": {"n_burnin": 1000, "n_samples": 200000, "sampler": "'hierarchical'"},
+        "hierarchical": {"n_max_level": 2, "coarsesampler": "'HMC'"},
+        "hmc": {"nt": 20, "dt": 0.2}}),
+    "gff16_hier3_hmc": dict(driver="qft", set={
+        "quantumfieldtheory": {"action": "'gff'"},
+        "lattice": {"Mt_lat": 16, "Mx_lat": 16, "coarsening": "'rotate'"},
+        "gff": {"mass": 10.0},
+        "singlelevelmc": {"n_burnin": 1000, "n_samples": 400000, "sampler": "'hierarchical'"},
+        "hierarchical": {"n_max_level": 3, "coarsesampler": "'HMC'"},
+        "hmc": {"nt": 20, "dt": 0.2}}),
     # --- topological rotor (driver_qm): hierarchical sampler with HMC and with cluster coarse sampler
     "rotor32_hier3_hmc": dict(driver="qm", set={
         "quantummechanics": {"action": "'rotor'"},
@@ -159,6 +179,11 @@ def parse_output(text):
     m = re.search(r"E\[V\*chi_t\]\s+= (\S+)", text) or re.search(r"E\[Q\^2\]\s+= (\S+)", text)
     if m:
         r["analytical"] = float(m.group(1))
+    m = re.search(r"Tuned\s+dt_\{HMC\} = (\S+)", text)
+    if m:
+        r["hmc_dt_tuned"] = float(m.group(1))
+    if "FAILED to tune" in text:
+        r["hmc_dt_tuned"] = None
     m = re.search(r"cost per sample = (\S+) mu s", text)
     if m:
         r["cost_per_sample_usec"] = float(m.group(1))
