@@ -238,6 +238,14 @@ int mlmcpi_overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x,
 /* one coloured sweep of Action::heatbath_update (overrelaxedheatbathsampler.cc:20-27) */
 int mlmcpi_heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B,
                           uint32_t chain0, uint64_t draw);
+/* Action::heatbath_update / Action::overrelaxation_update of ONE degree of freedom ell (the per-dof
+ * interface of action/action.hh:85-110; rotoraction.cc:21-56, gffaction.cc:32-42,68-79,
+ * quenchedschwingeraction.cc:46-65) on all chains: the building block the reference's
+ * OverrelaxedHeatBathSampler loops over (overrelaxedheatbathsampler.cc:8-31, any order incl.
+ * random_order).  One launch per call -- present for interface parity; the sweeps above are the
+ * fast path.  heatbath != 0: variates of (chain0 + chain, draw, ell), as in mlmcpi_heatbath_sweep. */
+int mlmcpi_dof_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, int ell, int heatbath,
+                      uint32_t chain0, uint64_t draw);
 /* Action::copy_from_coarse of the fine action / Action::copy_from_fine of the coarse one */
 int mlmcpi_prolong(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *d_xc, double *d_x, int B);
 int mlmcpi_restrict(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const double *d_xf, double *d_xc, int B);

@@ -260,6 +260,19 @@ public:
     Device::check(mlmcpi_heatbath_sweep(Device::ctx(), &model_, x.ptr(), 1, 0, sweep_counter++), "heat bath sweep");
     x.download(state->data.data());
   }
+  /** per-dof interface, action/action.hh:85-110: the updates OverrelaxedHeatBathSampler::draw loops over
+   * (one single-dof kernel launch per call -- interface parity; the sweeps above are the fast path) */
+  virtual void heatbath_update(std::shared_ptr<SampleState> state, const unsigned int ell) { dof_update(state, ell, 1); }
+  virtual void overrelaxation_update(std::shared_ptr<SampleState> state, const unsigned int ell) {
+    dof_update(state, ell, 0);
+  }
+  /** action/action.hh:104-110: the dofs a heat-bath sweep visits (all of them for the actions here) */
+  virtual const std::vector<unsigned int> &get_heatbath_indexset() {
+    if (heatbath_indexset.empty())
+      for (unsigned int ell = 0; ell < sample_size(); ++ell)
+        heatbath_indexset.push_back(ell);
+    return heatbath_indexset;
+  }
   virtual std::string info_string() const {
     std::stringstream s;
     if (model_.model <= MLMCPI_ROTOR)
@@ -282,6 +295,14 @@ protected:
     throw std::runtime_error(msg);
   }
   mlmcpi_model model_;
+  void dof_update(std::shared_ptr<SampleState> state, const unsigned int ell, int heatbath) {
+    DeviceVector x(check_size(state));
+    x.upload(state->data.data());
+    Device::check(mlmcpi_dof_update(Device::ctx(), &model_, x.ptr(), 1, (int)ell, heatbath, 0, sweep_counter++),
+                  heatbath ? "heatbath_update" : "overrelaxation_update");
+    x.download(state->data.data());
+  }
+  std::vector<unsigned int> heatbath_indexset;
   mlmcpi_model fine_model_ = {};
   bool has_fine_ = false;
   RenormalisationType renormalisation;
@@ -336,9 +357,45 @@ public:
       : QMAction(qm_model(MLMCPI_QUARTIC, *lattice, m0_, mu2_, lambda_, x0_), renormalisation_,
                lattice->get_coarsening_level(), 0) {}
 };
-/** action/qm/rotoraction.hh */
-class RotorAction : public QMAction {
+/** action/clusteraction.hh:25-72: what the generic ClusterSampler needs from an action.  The batched
+ * cluster kernels (csrc/qm.cu) have S_ell / new_reflection / flip of the rotor built in; this host
+ * interface exists so that code written against the reference's ClusterAction keeps compiling. */
+class ClusterAction {
 public:
+  virtual ~ClusterAction() {}
+  virtual double S_ell(const std::shared_ptr<SampleState> x_path, const unsigned int i, const unsigned int j) const = 0;
+  virtual void new_reflection() const = 0;
+  virtual void flip(std::shared_ptr<SampleState> x_path, const unsigned int ell) const = 0;
+  virtual void initialise_state(std::shared_ptr<SampleState> x_path) const = 0;
+  virtual unsigned int sample_size() const = 0;
+};
+
+/** action/qm/rotoraction.hh */
+class RotorAction : public QMAction, public ClusterAction {
+public:
+  /** rotoraction.hh:226-253 */
+  virtual double S_ell(const std::shared_ptr<SampleState> x_path, const unsigned int i, const unsigned int j) const {
+    return -2. * model_.m0 / model_.a_lat * std::cos(x_path->data[i] - xbar) * std::cos(x_path->data[j] - xbar);
+  }
+  virtual void new_reflection() const {
+    // splitmix64 stream: the host-side reflection angle of the interface; the batched kernels draw
+    // theirs from Philox (stream CLUSTER)
+    reflection_state += 0x9E3779B97F4A7C15ull;
+    uint64_t z = reflection_state;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    xbar = -M_PI + 2. * M_PI * ((double)(z >> 11) * (1.0 / 9007199254740992.0));
+  }
+  virtual void flip(std::shared_ptr<SampleState> x_path, const unsigned int ell) const {
+    const double x = M_PI + 2. * xbar - x_path->data[ell];
+    x_path->data[ell] = x - 2. * M_PI * std::floor(0.5 * (x + M_PI) / M_PI); // mod_2pi, auxilliary.hh:42-44
+  }
+  virtual void initialise_state(std::shared_ptr<SampleState> x_path) const { Action::initialise_state(x_path); }
+  virtual unsigned int sample_size() const { return Action::sample_size(); }
+  mutable double xbar = 0.0;
+  mutable uint64_t reflection_state = 21172817ull; // the reference's rotor seed, rotoraction.hh:106
+
   RotorAction(const std::shared_ptr<Lattice1D> lattice, const RenormalisationType renormalisation_, const double m0_)
       : QMAction(qm_model(MLMCPI_ROTOR, *lattice, m0_), renormalisation_, lattice->get_coarsening_level(), 0) {}
   /** qm/rotoraction.cc:92-115 */
@@ -599,6 +656,25 @@ public:
     burn_in(p.n_burnin, action->sample_size());
   }
 };
+
+/** sampler/clustersampler.hh:66-160 (1-D rotor) and sampler/quenchedschwingerclustersampler.hh:24-98:
+ * n_updates Wolff single-cluster updates per draw */
+class ClusterSampler : public Sampler {
+public:
+  ClusterSampler(const std::shared_ptr<Action> action, const unsigned int n_updates = 10,
+                 const unsigned int n_burnin = 100)
+      : Sampler(action, cluster_params(n_updates)) {
+    burn_in(n_burnin, action->sample_size());
+  }
+
+private:
+  static mlmcpi_sampler_params cluster_params(unsigned int n_updates) {
+    mlmcpi_sampler_params q = make_params(MLMCPI_SAMPLER_CLUSTER, 1, 0, 0, 0, 0, 1, 0, 0);
+    q.n_updates = (int)n_updates;
+    return q;
+  }
+};
+typedef ClusterSampler QuenchedSchwingerClusterSampler;
 
 /** sampler/hierarchicalsampler.hh: HMC or heat bath on the coarsest of n_max_level levels */
 class HierarchicalSampler : public Sampler {

@@ -245,6 +245,10 @@ class Context:
     def heatbath_sweep(self, m, x, chain0=0, draw=0):
         self._ck(L.mlmcpi_heatbath_sweep(self.h, C.byref(m), _ptr(x), x.shape[0], chain0, draw))
 
+    def dof_update(self, m, x, ell, heatbath=False, chain0=0, draw=0):
+        """Action::heatbath_update / overrelaxation_update of one degree of freedom on all chains"""
+        self._ck(L.mlmcpi_dof_update(self.h, C.byref(m), _ptr(x), x.shape[0], ell, int(heatbath), chain0, draw))
+
     def prolong(self, fine, xc, x):
         self._ck(L.mlmcpi_prolong(self.h, C.byref(fine), _ptr(xc), _ptr(x), x.shape[0]))
 

@@ -796,6 +796,10 @@ int mlmcpi_heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, i
                           uint32_t chain0, uint64_t draw) {
   DISPATCH(m, heatbath_sweep, ctx, m, d_x, B, chain0, draw);
 }
+int mlmcpi_dof_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, int ell, int heatbath,
+                      uint32_t chain0, uint64_t draw) {
+  DISPATCH(m, dof_update, ctx, m, d_x, B, ell, heatbath, chain0, draw);
+}
 int mlmcpi_prolong(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_xc, double *d_x, int B) {
   DISPATCH(m, prolong, ctx, m, d_xc, d_x, B);
 }

@@ -632,6 +632,7 @@ struct FillConst {
                int32_t *, double *);                                                               \
   int overrelax_sweep(mlmcpi_ctx *, const mlmcpi_model *, double *, int);                          \
   int heatbath_sweep(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);        \
+  int dof_update(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int, int, uint32_t, uint64_t);   \
   int prolong(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int);                  \
   int restrict_(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int);                \
   int fill(mlmcpi_ctx *, const mlmcpi_model *, double *, int, uint32_t, uint64_t);                  \

@@ -340,6 +340,20 @@ __global__ void sweep_colour_kernel(GF g, int colour, double *x, int B, uint32_t
   }
 }
 
+// Action::heatbath_update / overrelaxation_update of ONE vertex (qft/gffaction.cc:32-42, 68-79): the
+// per-dof interface of action/action.hh:85-110, one thread per chain
+template <bool HEATBATH>
+__global__ void dof_update_kernel(GF g, int ell, double *x, int B, uint32_t chain0, uint64_t seed, uint64_t draw) {
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= B)
+    return;
+  int i, j;
+  v_lin2cart(g.Mt, g.Mx, g.rotated, ell, i, j);
+  double *xc = x + (size_t)chain * g.N;
+  const double Delta = nn_sum(g, xc, i, j);
+  xc[ell] = site_update<HEATBATH>(g, Delta, xc[ell], seed, draw, chain0 + (uint32_t)chain, ell);
+}
+
 // One sweep (both colours, ascending order; overrelaxation or heat bath) of an UNROTATED level in ONE pass
 // over HBM, out of place.  The two colour passes above read the whole field twice to update half of it each
 // (24 B per site against the algorithmic 16 B).  Here a block of Mt/2 threads marches over R rows of one
@@ -1224,6 +1238,19 @@ int sweep_sequence(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, int
     MLMCPI_CUDA(cudaMemcpyAsync(x, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
+int dof_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, int ell, int heatbath, uint32_t chain0,
+               uint64_t draw) {
+  GF g = make_gf(m);
+  if (ell < 0 || ell >= g.N)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "vertex index out of range");
+  if (heatbath)
+    dof_update_kernel<true><<<cdiv(B, 128), 128, 0, ctx->stream>>>(g, ell, x, B, chain0, ctx->seed, draw);
+  else
+    dof_update_kernel<false><<<cdiv(B, 128), 128, 0, ctx->stream>>>(g, ell, x, B, 0, 0, 0);
+  MLMCPI_LAUNCHED("gff::dof_update");
+  return 0;
+}
+
 int overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, int n_sweeps) {
   if (m->Mt_lat % 2 || m->Mx_lat % 2)
     return ctx_fail(ctx, MLMCPI_EINVAL, "coloured sweeps need even lattice extents");

@@ -607,6 +607,26 @@ __global__ void rotor_sweep_kernel(QM q, double *x, int B, uint32_t chain0, uint
   }
 }
 
+// Action::heatbath_update / overrelaxation_update of ONE site (qm/rotoraction.cc:21-56): the per-dof
+// interface of action/action.hh:85-110, one thread per chain
+template <bool HEATBATH>
+__global__ void rotor_dof_update_kernel(QM q, int s, double *x, int B, uint32_t chain0, uint64_t seed, uint64_t draw) {
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= B)
+    return;
+  const int M = q.M;
+  double *xc = x + (size_t)chain * M;
+  const double x_m = xc[s == 0 ? M - 1 : s - 1], x_p = xc[s == M - 1 ? 0 : s + 1];
+  double x0, curv;
+  W_min_curv<MLMCPI_ROTOR>(q, x_m, x_p, x0, curv);
+  if (HEATBATH) {
+    Rng r = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, s);
+    xc[s] = mod_2pi(x0 + expsin2_draw(r, 2. * curv));
+  } else {
+    xc[s] = mod_2pi(2.0 * x0 - xc[s]);
+  }
+}
+
 // ------------------------------------------------------- prolong / restrict
 // qm/qmaction.cc:7-26
 __global__ void prolong_kernel(int M, const double *xc, double *x, int B) {
@@ -966,6 +986,21 @@ int overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B) {
   QM q = make_qm(m);
   rotor_sweep_kernel<false><<<cdiv(B, WARPS), THREADS, 0, ctx->stream>>>(q, x, B, 0, 0, 0, ctx->sweep_reverse);
   MLMCPI_LAUNCHED("qm::overrelax_sweep");
+  return 0;
+}
+
+int dof_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, int ell, int heatbath, uint32_t chain0,
+               uint64_t draw) {
+  if (m->model != MLMCPI_ROTOR)
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "heat bath / overrelaxation not defined for this action");
+  QM q = make_qm(m);
+  if (ell < 0 || ell >= q.M)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "site index out of range");
+  if (heatbath)
+    rotor_dof_update_kernel<true><<<cdiv(B, 128), 128, 0, ctx->stream>>>(q, ell, x, B, chain0, ctx->seed, draw);
+  else
+    rotor_dof_update_kernel<false><<<cdiv(B, 128), 128, 0, ctx->stream>>>(q, ell, x, B, 0, 0, 0);
+  MLMCPI_LAUNCHED("qm::dof_update");
   return 0;
 }
 

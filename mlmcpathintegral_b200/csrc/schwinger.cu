@@ -587,6 +587,36 @@ __global__ void sweep_colour_kernel(SW sw, int colour, double *x, int B, uint32_
   }
 }
 
+// Action::heatbath_update / overrelaxation_update of ONE link ell (qft/quenchedschwingeraction.cc:46-65):
+// the per-dof interface of action/action.hh:85-110, one thread per chain.  The overrelaxation follows
+// the reference's operation order (both staple angles reduced to [-pi, pi) first), so that a
+// lexicographic sweep of single-link calls reproduces the reference's sweep.
+template <bool HEATBATH>
+__global__ void dof_update_kernel(SW sw, int ell, double *x, int B, uint32_t chain0, uint64_t seed, uint64_t draw) {
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= B)
+    return;
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const int mu = ell & 1, site = ell >> 1;
+  const int j = site / Mt, i = site - j * Mt;
+  double *xc = x + (size_t)chain * 2 * Mt * Mx;
+  const int ip = wrap_inc(i, Mt), im = wrap_dec(i, Mt), jp = wrap_inc(j, Mx), jm = wrap_dec(j, Mx);
+  double theta_p, theta_m;
+  if (mu == 0) { // compute_staple_angles, :25-43
+    theta_p = mod_2pi(TH(xc, i, jp, 0) + TH(xc, i, j, 1) - TH(xc, ip, j, 1));
+    theta_m = mod_2pi(TH(xc, i, jm, 0) + TH(xc, ip, jm, 1) - TH(xc, i, jm, 1));
+  } else {
+    theta_p = mod_2pi(TH(xc, i, j, 0) + TH(xc, ip, j, 1) - TH(xc, i, jp, 0));
+    theta_m = mod_2pi(TH(xc, im, jp, 0) + TH(xc, im, j, 1) - TH(xc, im, j, 0));
+  }
+  if (HEATBATH) {
+    Rng rg = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, (uint32_t)ell);
+    xc[ell] = expcos_draw(rg, sw.beta, theta_p, theta_m, sw.envelope);
+  } else {
+    xc[ell] = mod_2pi(theta_p + theta_m - xc[ell]);
+  }
+}
+
 // One overrelaxation sweep (all four colours, ascending order) in ONE pass over HBM, out of place.
 // The four colour passes above read the whole lattice four times to update a quarter of the links
 // each.  Here a block of Mt threads (one per column) marches over R rows of one chain with the
@@ -1420,6 +1450,19 @@ static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool 
 // n_sweeps overrelaxation sweeps.  Ascending colour order on lattices with even extents and at most
 // 1024 columns: the one-pass kernel, ping-ponging between x and a work buffer (copied back when
 // n_sweeps is odd); otherwise four colour passes per sweep, in place.
+int dof_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, int ell, int heatbath, uint32_t chain0,
+               uint64_t draw) {
+  SW sw = make_sw(ctx, m);
+  if (ell < 0 || ell >= 2 * sw.Mt * sw.Mx)
+    return ctx_fail(ctx, MLMCPI_EINVAL, "link index out of range");
+  if (heatbath)
+    dof_update_kernel<true><<<cdiv(B, 128), 128, 0, ctx->stream>>>(sw, ell, x, B, chain0, ctx->seed, draw);
+  else
+    dof_update_kernel<false><<<cdiv(B, 128), 128, 0, ctx->stream>>>(sw, ell, x, B, 0, 0, 0);
+  MLMCPI_LAUNCHED("schwinger::dof_update");
+  return 0;
+}
+
 int overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, int n_sweeps) {
   SW sw = make_sw(ctx, m);
   const bool one_pass = !ctx->sweep_reverse && ctx->overrelax_one_pass && sw.Mt % 2 == 0 && sw.Mx % 2 == 0 &&

@@ -183,12 +183,15 @@ def test_analytic_results_match_reference(mp):
 
 
 def test_gff_coarse_model_carries_the_gibbs_smoothed_action(mp):
-    """GFFAction::coarse_action (gffaction.hh:201-208): n_gibbs_smooth = 2, omega = 1 wherever the
-    dense matrices can be formed, the 5-point action beyond"""
+    """GFFAction::coarse_action (gffaction.hh:201-208): n_gibbs_smooth = 2, omega = 1 on EVERY coarse
+    level (there is no silent fall-back to the 5-point action; level 1 of BASELINE config C3 has 32768
+    vertices = MLMCPI_GFF_DENSE_MAX)"""
     mc = mp.coarse_model(mp.gff(32, 32, 10.0), ctype=mp.COARSEN_ROTATE)
     assert (mc.gff_n_gibbs, mc.gff_omega, mp.sample_size(mc)) == (2, 1.0, 512)
     big = mp.coarse_model(mp.gff(256, 256, 10.0), ctype=mp.COARSEN_ROTATE)
-    assert big.gff_n_gibbs == 0 and mp.sample_size(big) == 32768
+    assert big.gff_n_gibbs == 2 and mp.sample_size(big) == 32768
+    hdr = open(os.path.join(ROOT, "include", "mlmcpi.h")).read()
+    assert "#define MLMCPI_GFF_DENSE_MAX 32768" in hdr
 
 
 def test_comm_library_exports_every_declared_symbol(mp):

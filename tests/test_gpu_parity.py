@@ -456,6 +456,35 @@ def test_gff_dense_coarse_level(mp, ctx, orc):
         assert abs(out["average"] - ref) < 5 * out["error"], (M, out, ref, p)
 
 
+def test_per_dof_updates_reproduce_the_reference_lexicographic_sweep(mp, ctx):
+    """Action::overrelaxation_update(state, ell) through mlmcpi_dof_update: one call per degree of freedom
+    in the reference's lexicographic order reproduces the sweep recorded from the reference's own
+    OverrelaxedHeatBathSampler loop (golden `overrelax_lex`); the heat-bath variant equals the coloured
+    sweep's update of the same link on the same input (same variate, same arithmetic)."""
+    for c in load("schwinger")[:2]:
+        m = mp.schwinger(c["Mt"], c["Mx"], c["beta"], c["ctype"], 0)
+        x = dev(ctx, np.tile(unhex(c["x"]), (3, 1)))
+        for ell in range(x.shape[1]):
+            ctx.dof_update(m, x, ell)
+        ang_close(host(x)[0], unhex(c["overrelax_lex"]), tol=1e-11, what="lexicographic overrelaxation (Schwinger)")
+        assert np.array_equal(host(x)[0], host(x)[2])
+    for c in load("gff")[:1]:
+        m = mp.gff(c["Mt"], c["Mx"], c["mass"], c["ctype"], 0)
+        x = dev(ctx, unhex(c["x"]))
+        for ell in range(x.shape[1]):
+            ctx.dof_update(m, x, ell)
+        close(host(x)[0], unhex(c["overrelax_lex"]), tol=1e-12, what="lexicographic overrelaxation (GFF)")
+    # heat bath: link 0 belongs to colour 0, which the coloured sweep updates first, from the same
+    # neighbours, with the variate of (chain, draw, link)
+    c = load("schwinger")[0]
+    m = mp.schwinger(c["Mt"], c["Mx"], c["beta"], c["ctype"], 0)
+    a, b = dev(ctx, np.tile(unhex(c["x"]), (4, 1))), dev(ctx, np.tile(unhex(c["x"]), (4, 1)))
+    ctx.dof_update(m, a, 0, heatbath=True, chain0=3, draw=11)
+    ctx.heatbath_sweep(m, b, 3, 11)
+    assert np.array_equal(host(a)[:, 0], host(b)[:, 0])
+    assert len(set(host(a)[:, 0])) == 4  # one variate stream per chain
+
+
 def test_gff_dense_action_2048_vertices_against_reference(mp, ctx):
     """the dense coarse action built ON THE DEVICE (cuSOLVER / cuBLAS, csrc/gff.cu) and evaluated with
     one DGEMM over all chains, at the largest size the reference's own buildMatrices finishes here in
