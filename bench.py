@@ -81,6 +81,9 @@ def parse():
     ap.add_argument("--dt", type=float, default=0.1)
     ap.add_argument("--thermalise", type=int, default=20, help="overrelaxed heat-bath sweeps before timing")
     ap.add_argument("--autotune", type=int, default=1, help="tune the HMC step size as HMCSampler does")
+    ap.add_argument("--ess-draws", type=int, default=40, help="draws of the ESS leg (cluster coarse sampler); 0 = skip")
+    ap.add_argument("--ess-updates", type=int, default=100, help="cluster updates per draw in the ESS leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the beta = 4, sweep-roofline and MLMC legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
@@ -281,6 +284,132 @@ class ClockSampler:
         return out
 
 
+def _timed(torch, fn, n):
+    """CUDA-event time (ms) of n calls of fn on the current stream, after one untimed call"""
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def ess_leg(mp, ctx, torch, dist, a, m, B, rank, world):
+    """ESS/s on the topological susceptibility from an ERGODIC sampler on the same lattice and beta: the
+    hierarchical sampler with the cluster coarse sampler (hierarchical: coarsesampler = 'cluster',
+    sampler/quenchedschwingerclustersampler.cc:40-86 -- the reference's topology-changing move).  With the
+    HMC coarse sampler of the throughput leg every chain stays in the sector it starts in at this coupling
+    (coarse beta ~ 64: no tunnelling, in the reference as here; profiles/r02_summary.md section 1)."""
+    k_max = 20
+    s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_CLUSTER, n_levels=a.levels, renorm=mp.RENORM_PERTURBATIVE,
+                   ctype=mp.COARSEN_BOTH, n_updates=a.ess_updates, chain0=(world + rank) * B)
+    st = mp.Statistics(ctx, k_max, B)
+    x = s.get_state()
+    packed = ctx.empty(8 + k_max)
+    n_burn = 10
+    for _ in range(n_burn):  # the start state is a draw of the cascade itself (cascade start): short burn-in
+        s.draw(x)
+    s.reset_stats()
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.ess_draws):
+        s.draw(x)
+        st.record(ctx.qoi(m, mp.QOI_SCHWINGER_CHI, x))
+        st.pack_device(packed)
+        if world > 1:
+            dist.all_reduce(packed)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    r = mp.Statistics.finalize(packed.cpu().numpy(), k_max)
+    exact = mp._lib.lib.mlmcpi_schwinger_chit_analytical(a.beta, a.lattice * a.lattice)
+    out = {
+        "sampler": f"hierarchical ({a.levels} levels), coarse sampler 'cluster' with {a.ess_updates} updates per draw",
+        "chains_per_gpu": B, "draws": a.ess_draws, "burnin_draws": n_burn, "ms_per_draw": ms / a.ess_draws,
+        "acceptance_per_level": s.p_accept(),
+        "qoi": {"name": "QOI_SCHWINGER_CHI", "average": r["average"], "error": r["error"], "tau_int": r["tau_int"],
+                "window": k_max, "samples": r["samples"], "analytic": exact,
+                "deviation_sigma": abs(r["average"] - exact) / r["error"] if r["error"] > 0 else None},
+        "ess_per_s": r["samples"] / r["tau_int"] / (ms * 1e-3),
+    }
+    st.close()
+    s.close()
+    del x
+    torch.cuda.empty_cache()
+    return out
+
+
+def beta4_leg(mp, ctx, torch, a, rank):
+    """the BesselProduct regime (beta <= 8 on every level: quenchedschwingerconditionedfineaction.hh:39-45)
+    of the same hierarchy, timed: HMC on the coarsest level + two exact-conditional fill-ins"""
+    B = max(32, a.chains // 4)
+    m = mp.schwinger(a.lattice, a.lattice, 4.0)
+    s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=a.levels, nt=a.nt, dt=a.dt,
+                   renorm=mp.RENORM_PERTURBATIVE, ctype=mp.COARSEN_BOTH, chain0=rank * B)
+    x = ctx.init_state(m, B, rank * B, 0)
+    for k in range(5):
+        ctx.overrelax_sweep(m, x)
+        ctx.heatbath_sweep(m, x, rank * B, 2000 + k)
+    s.set_state(x)
+    s.draw(x)
+    ms = _timed(torch, lambda: s.draw(x), 3) / 3
+    w = s.work()
+    units = w["leapfrog_site_steps"] + w["filled_fine_sites"]
+    out = {"beta": 4.0, "fill_in": "BesselProduct (exact conditional, beta <= 8)", "chains_per_gpu": B,
+           "ms_per_step": ms, "site_updates_per_s_per_gpu": units / (ms * 1e-3),
+           "filled_fine_sites_per_s_per_gpu": w["filled_fine_sites"] / (ms * 1e-3),
+           "acceptance_per_level": s.p_accept(),
+           "note": "two-level acceptance collapses with the volume at fixed beta (16^2: 0.2, 512^2: < 1e-3), in the "
+                   "reference as here; this leg times the kernels of the regime"}
+    s.close()
+    del x
+    torch.cuda.empty_cache()
+    return out
+
+
+def sweeps_leg(mp, ctx, torch, a, m, x, peak):
+    """roofline of the update sweeps (north_star: >= 90 % of HBM on the Schwinger / GFF sweeps), CUDA events
+    in this very run: algorithmic bytes (32 B per Schwinger site, 16 B per GFF vertex) / time"""
+    out = {}
+    B, sites = x.shape[0], a.lattice * a.lattice
+    n = 10
+    ms = _timed(torch, lambda: ctx.overrelax_sweeps(m, x, 2), n) / (2 * n)
+    out["schwinger_overrelaxation"] = {"kernel": "overrelax_rowpipe_kernel (4 colours in one pass)", "ms_per_sweep": ms,
+                                       "bytes_per_sweep": 32.0 * sites * B}
+    ms = _timed(torch, lambda: ctx.heatbath_sweep(m, x, 0, 77), 4) / 4
+    out["schwinger_heatbath"] = {"kernel": "heat-bath sweep (ExpCos rejection sampler per link)", "ms_per_sweep": ms,
+                                 "bytes_per_sweep": 32.0 * sites * B}
+    g = mp.gff(256, 256, 10.0)
+    Bg = 2048
+    xg = ctx.init_state(g, Bg, 0, 0)
+    ms = _timed(torch, lambda: ctx.overrelax_sweeps(g, xg, 2), n) / (2 * n)
+    out["gff_overrelaxation"] = {"kernel": "gff::sweep_rowpipe_kernel<false> (2 colours in one pass)", "ms_per_sweep": ms,
+                                 "bytes_per_sweep": 16.0 * 65536 * Bg}
+    hb = mp.Sampler(ctx, g, Bg, kind=mp.SAMPLER_HEATBATH, n_sweep_overrelax=0, n_sweep_heatbath=2)
+    hb.set_state(xg)
+    ms = _timed(torch, lambda: hb.draw(None), n) / (2 * n)
+    out["gff_heatbath"] = {"kernel": "gff::sweep_rowpipe_kernel<true> (2 colours in one pass, 1 normal per vertex)",
+                           "ms_per_sweep": ms, "bytes_per_sweep": 16.0 * 65536 * Bg}
+    hb.close()
+    for v in out.values():
+        v["achieved_gbs"] = v["bytes_per_sweep"] / (v["ms_per_sweep"] * 1e-3) / 1e9
+        v["peak_gbs"] = peak
+        v["frac"] = v["achieved_gbs"] / peak
+    del xg
+    torch.cuda.empty_cache()
+    return out
+
+
 def gpu_main(a):
     import numpy as np
     import torch
@@ -399,12 +528,24 @@ def gpu_main(a):
                "h2d_bytes_per_step": B * n * 8, "d2h_bytes_per_step": B * 8, "steps": k_e2e,
                "api": "mlmcpi_sampler_draw_host (pinned host SampleStates in, QoI out)"}
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, which = 6650.0, "fallback (B200_PROFILING.md)"
+    headline = is_schwinger and kind == mp.SAMPLER_HMC
+    # ---- further measured legs (outside the timed region of `value`): every rank runs the ESS leg (its
+    #      moments are all-reduced), rank 0 alone the single-GPU kernel legs
+    ess = sweeps = beta4 = None
+    if headline and a.ess_draws > 0:
+        ess = ess_leg(mp, ctx, torch, dist, a, m, B, rank, world)
+    if headline and not a.no_extra and rank == 0:
+        sweeps = sweeps_leg(mp, ctx, torch, a, m, x, peak)
+        beta4 = beta4_leg(mp, ctx, torch, a, rank)
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-        else:
-            peak, which = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = lf_bytes / (lf_ms * 1e-3) / 1e9 if lf_ms > 0 else None
         if not is_schwinger:
             achieved = None
@@ -422,7 +563,9 @@ def gpu_main(a):
             "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None,
             "steps_per_hbm_pass": steps_per_launch,
-            "traffic": traffic, "launches": lf_launches,
+            "traffic": traffic, "traffic_source": "static: ncu --set full capture of this kernel at this shape, "
+                                                  "profiles/roofline_traffic.json (not re-measured in this run)",
+            "launches": lf_launches,
             "avg_launch_ms": lf_ms / lf_launches if lf_launches else None,
             "algorithmic_bytes_per_launch": lf_bytes / lf_launches if lf_launches else None,
             "algorithmic_bytes_per_site_step": 64,
@@ -435,17 +578,25 @@ def gpu_main(a):
             "site_updates_per_step_per_gpu": {k: v for k, v in work.items()},
             "value_per_gpu": value / world,
             "acceptance_per_level": p_acc, "hmc_autotune": tuned,
-            "qoi": {"name": w["qoi"], "average": st["average"], "error": st["error"], "tau_int": st["tau_int"],
-                    "samples": st["samples"]},
-            "ess_per_s": st["samples"] / st["tau_int"] / (ms_max * 1e-3),
         })
-        if is_schwinger and a.beta > 64:
-            # honest labelling: see DESIGN.md section 6 ("ESS/s")
-            cfg["ess_note"] = ("cold start at beta/P = %.1e: every chain stays in the Q = 0 sector (neither the HMC "
-                               "nor the two-level steps change the topological charge at this coupling, in the "
-                               "reference as here), so chi_t ~ 1e-28 and ess_per_s is samples / tau_int / time of "
-                               "an essentially constant series; statistically meaningful chi_t runs are in "
-                               "tests/ (8^2 ... 32^2, beta <= 16, vs the analytic value)" % (a.beta / a.lattice ** 2))
+        timed_qoi = {"name": w["qoi"], "average": st["average"], "error": st["error"], "tau_int": st["tau_int"],
+                     "samples": st["samples"]}
+        if ess is not None:
+            # the QoI / ESS figures of the line come from the ergodic sampler (ess_leg); the series of the
+            # throughput leg is reported beside them and labelled for what it is
+            cfg["qoi"] = ess["qoi"]
+            cfg["ess_per_s"] = ess["ess_per_s"]
+            cfg["ess"] = ess
+            cfg["qoi_of_timed_steps"] = dict(timed_qoi, note=(
+                "HMC coarse sampler at coarse beta ~ %.0f: no tunnelling between topological sectors (in the "
+                "reference as here), every chain keeps the charge of its thermalised start state; the QoI and "
+                "ESS/s of this line are measured with the cluster coarse sampler instead (config.ess)"
+                % (a.beta / 4 ** (a.levels - 1))))
+        else:
+            cfg["qoi"] = timed_qoi
+            cfg["ess_per_s"] = st["samples"] / st["tau_int"] / (ms_max * 1e-3)
+        if sweeps is not None:
+            cfg["extra"] = {"schwinger%d_beta4" % a.lattice: beta4}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
@@ -453,6 +604,8 @@ def gpu_main(a):
             "data": "synthetic (U(-pi,pi) start states, Philox4x32-10)", "config": cfg,
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
+        if sweeps is not None:
+            line["roofline_sweeps"] = sweeps
         if not is_schwinger or kind != mp.SAMPLER_HMC:
             line["metric"] = "lattice site-updates/s (%s)" % a.workload
             line["roofline"] = None  # 1-D paths / Gaussian fields: see profiles/r01_summary.md section 4

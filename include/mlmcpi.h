@@ -331,6 +331,10 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s);
 /* Sampler::set_state / Sampler::draw on device states [B][n] */
 int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x);
 int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept);
+/* the current states [B][n] of the chains.  mlmcpi_sampler_draw only overwrites d_x_out where the draw
+ * was accepted (MCMCStep::copy_if_rejected = false, hierarchicalsampler.cc:78-80), so an output buffer
+ * that is to hold the chains' states from the first draw on is initialised with this call */
+int mlmcpi_sampler_get_state(mlmcpi_sampler *s, double *d_x);
 /* the same with HOST buffers: h_x_in (may be NULL: keep the current state) is
  * uploaded, one draw is made, the QoI of the new state is evaluated, and
  * h_q[B] (and h_x_out[B][n] if not NULL) are copied back; synchronous */

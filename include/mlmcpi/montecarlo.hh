@@ -145,6 +145,8 @@ public:
     Device::check(mlmcpi_sampler_create(Device::ctx(), &action->model(), &prm, (int)B_,
                                         (uint32_t)(Parallel::rank() * B_), &s_),
                   "sampler create");
+    // draw() leaves the output of a rejected chain untouched: start from the chains' states, not from zeros
+    Device::check(mlmcpi_sampler_get_state(s_, x_.ptr()), "sampler state");
     // the reference's sampler constructors burn in and, for HMC, tune the step size
     // (sampler/hmcsampler.hh:99-108, overrelaxedheatbathsampler.hh:118-126, clustersampler.cc:30-35)
     for (unsigned int k = 0; k < n_burnin; ++k)

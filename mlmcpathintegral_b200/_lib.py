@@ -121,6 +121,7 @@ SIGNATURES = {
     "mlmcpi_sampler_draw_host": (_i, [_vp, _vp, _i, _vp, _vp]),
     "mlmcpi_sampler_level_model": (_i, [_vp, _i, _MP]),
     "mlmcpi_dof_update": (_i, [_vp, _MP, _vp, _i, _i, _i, _u32, _u64]),
+    "mlmcpi_sampler_get_state": (_i, [_vp, _vp]),
     "mlmcpi_sampler_stats": (_i, [_vp, _dp]),
     "mlmcpi_sampler_reset_stats": (_i, [_vp]),
     "mlmcpi_sampler_work": (_i, [_vp, _dp]),

@@ -341,6 +341,13 @@ class Sampler:
     def set_state(self, x):
         self.ctx._ck(L.mlmcpi_sampler_set_state(self.h, _ptr(x)))
 
+    def get_state(self, x=None):
+        """the current state of every chain (draw() only overwrites its output where it accepted)"""
+        if x is None:
+            x = self.ctx.state(self.fine, self.B)
+        self.ctx._ck(L.mlmcpi_sampler_get_state(self.h, _ptr(x)))
+        return x
+
     def draw(self, x_out=None, accept=None):
         self.ctx._ck(L.mlmcpi_sampler_draw(self.h, _ptr(x_out), _ptr(accept)))
 

@@ -1107,10 +1107,7 @@ static int coarse_draw(mlmcpi_sampler *s, int c0, int B) {
 }
 
 // Start state of a hierarchical sampler whose coarse sampler proposes INDEPENDENT states (cluster,
-// exact), and of every GFF hierarchy (whose intermediate levels accept a few per cent of the
-// proposals, in the reference as here, so that a chain started away from the hierarchy's own
-// stationary distribution needs thousands of draws to reach it -- the reference spends the 10^4
-// draws of its constructor on that): the two-level steps are then independence samplers with weight w = pi_f / (pi_c q), and a
+// exact): the two-level steps are then independence samplers with weight w = pi_f / (pi_c q), and a
 // chain started from a state of atypically large w never leaves it (measured, profiles/r02_summary.md:
 // 512^2, beta = 1024, 3 levels, zero state + 50 heat-bath sweeps: no chain accepts in 130 draws, while
 // the very same 256^2 <- 128^2 step accepts 36 % as the top of a 256^2 hierarchy).  The start state
@@ -1134,8 +1131,8 @@ static int cascade_start(mlmcpi_sampler *s) {
       s->cluster_updates += std::max(1, s->prm.n_updates);
     }
   } else if (s->prm.kind == MLMCPI_SAMPLER_HMC || s->prm.kind == MLMCPI_SAMPLER_HEATBATH) {
-    // (GFF) local sampler on the coarsest level: hot start, burnt in there -- the Gaussian has no
-    // metastable sectors, and 100 coarse draws cost less than one fine-level sweep
+    // local sampler on the coarsest level: hot start, burnt in there (100 coarse draws cost less than
+    // one fine-level sweep)
     if ((rc = mlmcpi_init_state(ctx, &s->model[L - 1], s->state[L - 1], B, s->chain0, 0)))
       return rc;
     for (int k = 0; k < 100; ++k) {
@@ -1153,6 +1150,32 @@ static int cascade_start(mlmcpi_sampler *s) {
       return rc;
   s->work[0] = s->work[1] = s->work[2] = 0.0;
   return 0;
+}
+
+// Start state of a GFF hierarchy.  With three or more levels the intermediate two-level steps accept a
+// few per cent of the proposals (in the reference as here: Q_hat of a level is paired with the 5-point
+// fill-in), the chains are sticky, and an ENSEMBLE of chains started away from the stationary
+// distribution approaches it over tens of thousands of draws (measured, profiles/r02_summary.md: 16^2,
+// 3 levels, cascade start: <phi^2> 0.3230 -> 0.3354 over 30 000 draws, exact 0.3380; started from an exact
+// sample the same kernel keeps 0.3381 +- 0.0004 from the first block on).  One long chain, as the
+// reference runs, pays that once; B short ones cannot.  So the chains start from samples of the
+// fine-level action itself: the Cholesky sampler where the level is small enough for its dense factor,
+// otherwise a hot state thermalised by overrelaxed heat-bath sweeps on the fine level (the massive GFF
+// has no slow modes beyond the correlation length 1 / (a m)).
+static int gff_equilibrium_start(mlmcpi_sampler *s) {
+  mlmcpi_ctx *ctx = s->ctx;
+  const mlmcpi_model *m = &s->model[0];
+  const int B = s->B;
+  const int N = mlmcpi_sample_size(m);
+  if (N <= 4096)
+    return mlmcpi_exact_draw(ctx, m, s->state[0], B, s->chain0, 0xFFFDull << 40);
+  int rc = mlmcpi_init_state(ctx, m, s->state[0], B, s->chain0, 0);
+  for (int k = 0; k < 100 && !rc; ++k) {
+    rc = mlmcpi_overrelax_sweeps(ctx, m, s->state[0], B, 5);
+    if (!rc)
+      rc = mlmcpi_heatbath_sweep(ctx, m, s->state[0], B, s->chain0, (0xFFFDull << 40) + (uint64_t)k);
+  }
+  return rc;
 }
 
 // HierarchicalSampler::draw, sampler/hierarchicalsampler.cc:55-81, for the chains
@@ -1397,8 +1420,17 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
   } else {
     // Sampler constructors start from Action::initialise_state (e.g. hmcsampler.hh:99-101); the
     // hierarchical sampler from the zero state (hierarchicalsampler.cc:43-44), here thermalised
-    if (s->L > 1 && (s->prm.kind == MLMCPI_SAMPLER_CLUSTER || s->prm.kind == MLMCPI_SAMPLER_EXACT ||
-                     fine->model == MLMCPI_GFF))
+    // GFF with the reference's Q_hat on the coarse levels and a heat-bath coarse sampler: the coarse chain
+    // samples the 5-point action, not Q_hat, the hierarchy's stationary distribution is NOT the fine-level
+    // action (tests/golden/stats.json: the reference's own estimate is 10 % low), and an exact fine-level
+    // sample is a metastable start for it (32^2, 4 levels: no level accepts); its chains start the way
+    // its proposals are made (cascade start).  Every consistent GFF hierarchy starts in equilibrium.
+    const bool gff_inconsistent =
+        fine->model == MLMCPI_GFF && s->prm.kind == MLMCPI_SAMPLER_HEATBATH && ctx->gff_coarse_smoothing;
+    if (s->L > 1 && fine->model == MLMCPI_GFF && !gff_inconsistent)
+      rc = gff_equilibrium_start(s);
+    else if (s->L > 1 && (s->prm.kind == MLMCPI_SAMPLER_CLUSTER || s->prm.kind == MLMCPI_SAMPLER_EXACT ||
+                          gff_inconsistent))
       rc = cascade_start(s);
     else if (s->L > 1)
       rc = thermal_start(ctx, fine, s->state[0], B, chain0);
@@ -1466,6 +1498,13 @@ int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x) {
     return 0;
   s->cache0_valid = false;
   return mlmcpi_copy(s->ctx, s->state[0], d_x, (size_t)mlmcpi_sample_size(&s->model[0]) * s->B);
+}
+
+// the current state of every chain (what the sampler classes keep in phi_state_cur / phi_sampler_state[0])
+int mlmcpi_sampler_get_state(mlmcpi_sampler *s, double *d_x) {
+  if (!s || !d_x)
+    return MLMCPI_EINVAL;
+  return mlmcpi_copy(s->ctx, d_x, s->state[0], (size_t)mlmcpi_sample_size(&s->model[0]) * s->B);
 }
 
 int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {

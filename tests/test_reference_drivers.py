@@ -80,7 +80,7 @@ def _run(case, chains, tmp_path, timeout=1500):
 
 CASES = [("schwinger16_b4_hier2_cluster", 512), ("schwinger32_b16_hier2_cluster", 512),
          ("schwinger64_b64_hier2_cluster", 256), ("schwinger16_b4_hier2_hmc", 512),
-         ("schwinger16_b4_cluster", 512), ("gff16_hier2_heatbath", 512), ("gff16_hier2_hmc", 512),
+         ("schwinger16_b4_cluster", 512), ("gff16_hier2_heatbath", 512), ("gff16_hier2_hmc", 128),
          ("rotor32_hier3_hmc", 1024), ("rotor64_cluster", 1024)]
 
 

@@ -57,7 +57,7 @@ def main():
                         break
                     dt0 *= 0.5
                 tuned = dt_t
-            x = ctx.state(m, B)
+            x = s.get_state()
             for _ in range(a.burnin):
                 s.draw(x)
             st = mp.Statistics(ctx, a.window, B)
