@@ -135,8 +135,10 @@ int mlmcpi_rank(const mlmcpi_ctx *ctx);
 /* MLMCPI_OPT_LEAPFROG_VARIANT (2-D Schwinger leapfrog kernel; all variants compute the same
  * step): 0 = TMA/mbarrier row pipeline (default), 1 = register row march, 2 = generic.
  * MLMCPI_OPT_LEAPFROG_ROWS: lattice rows per thread block (0 = default).
- * MLMCPI_OPT_LEAPFROG_FUSE: 1 (default) = two leapfrog steps per pass over HBM (temporal
- * blocking, variant 0 only), 0 = one step per pass.
+ * MLMCPI_OPT_LEAPFROG_FUSE: leapfrog steps per pass over HBM (temporal blocking, variant 0 only):
+ * 0 = one; 1 (default) = four for Mt in {64, 128, 256}, two for Mt = 512 (K-stage register pipeline
+ * with compile-time block size), two for every other Mt (round-1 kernel); 2 / 3 = two / four steps
+ * through the K-stage kernel; 4 = the round-1 two-step kernel.  Same trajectory, bit for bit.
  * MLMCPI_OPT_SWEEP_REVERSE: 1 = the coloured sweeps visit the colours in descending order (the
  * exact reverse of the default; used to make a sequence of sweeps a reversible kernel).
  * MLMCPI_OPT_OVERRELAX_ONE_PASS: 1 (default) = a Schwinger overrelaxation sweep updates all four

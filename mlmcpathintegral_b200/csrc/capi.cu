@@ -200,7 +200,7 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
     ctx->sweep_reverse = value;
     return 0;
   }
-  if (option == MLMCPI_OPT_LEAPFROG_FUSE && (value == 0 || value == 1)) {
+  if (option == MLMCPI_OPT_LEAPFROG_FUSE && value >= 0 && value <= 4) {
     ctx->leapfrog_fuse = value;
     return 0;
   }

@@ -29,7 +29,7 @@ struct mlmcpi_ctx {
   int expcos_envelope = 2; // MLMCPI_OPT_EXPCOS_ENVELOPE: 0 reference, 1 chord, 2 chord + Taylor (default)
   int leapfrog_variant = 0; // MLMCPI_OPT_LEAPFROG_VARIANT: 0 TMA row pipeline, 1 register row march, 2 generic
   int leapfrog_rows = 0;    // MLMCPI_OPT_LEAPFROG_ROWS: rows per block (0 = default)
-  int leapfrog_fuse = 1;    // MLMCPI_OPT_LEAPFROG_FUSE: two leapfrog steps per HBM pass
+  int leapfrog_fuse = 1;    // MLMCPI_OPT_LEAPFROG_FUSE: leapfrog steps per HBM pass (0: one, 1: auto, 2/3: 2/4 steps, 4: round-1 kernel)
   int sweep_reverse = 0;    // MLMCPI_OPT_SWEEP_REVERSE: colours visited in descending order
   int overrelax_one_pass = 1; // MLMCPI_OPT_OVERRELAX_ONE_PASS: all colours of a Schwinger OR sweep in one HBM pass
   int fused_qm_hierarchy = 1; // MLMCPI_OPT_FUSED_QM_HIERARCHY: 1-D hierarchical draw in one kernel
@@ -167,33 +167,46 @@ __device__ __forceinline__ double div_pi(const double u) {
   r = fma(-q, M_PI, u);
   return fma(r, c, q);
 }
-// sin(x) for the force kernels, branch-free and without the coefficient-table loads of the library routine
-// (which checks for special values, reduces modulo pi/2, branches to a slow path for huge arguments and
-// fetches one of two coefficient sets from a table: ~40 instructions, and this is the one transcendental
-// of a leapfrog site-step).  Reduction modulo pi with a two-term Cody-Waite split (exact products through
-// FMA; k pi_lo restores the bits of pi beyond the double), then r + r^3 q(r^2) with the degree-8 minimax-type
-// polynomial q fitted on |r| <= pi/2 (1 + 1e-7) (scratch fit against 60-digit sines: 2.2e-16 absolute), sign
-// by the parity of k.  Arguments here are plaquette angles, O(10); beyond 1e6 the library routine is used.
-static __device__ __noinline__ double sin_library(const double x) { return sin(x); } // (one copy, off the hot path)
+// sin(x) for the force kernels: straight-line code -- no branch, no special cases, no coefficient-table
+// loads, no float <-> int conversion instructions.  (The library routine checks for special values, reduces
+// modulo pi/2, branches to a slow path for huge arguments and fetches one of two coefficient sets: ~40
+// instructions, and this is the one transcendental of a leapfrog site-step.  A branch inside the routine also
+// makes every call its own basic block, which keeps the compiler from interleaving the independent sines of a
+// multi-stage leapfrog iteration: ncu showed 12 warps per SM each crawling through one dependent chain.)
+//   k = rint(x / pi) by the magic-number addition (the FMA rounds x * RN(1/pi) + 1.5 * 2^52 once; the parity
+//   of k is the lowest mantissa bit), r = x - k pi with a two-term Cody-Waite split (exact products through
+//   FMA: the reduction error is |k| * 2^-107, i.e. negligible for every |x| < 2^50, beyond which the spacing
+//   of doubles exceeds 1/4 and a sine is noise anyway), then r + r^3 q(r^2) with the degree-8 minimax-type
+//   polynomial q fitted on |r| <= pi/2 (1 + 1e-7) (scratch fit against 60-digit sines: 2.2e-16 absolute),
+//   sign by the parity of k (an XOR on the high word).
+// The constants live in the constant bank and enter the DFMAs as c[bank][offset] operands; written as
+// literals they are re-materialised with two uniform moves each, per sine and loop iteration.
+static __constant__ double SIN_FORCE_C[13] = {
+    0x1.45f306dc9c883p-2,  // RN(1 / pi)
+    0x1.921fb54442d18p+1,  // pi_hi
+    0x1.1a62633145c07p-53, // pi_lo
+    -0x1.275f311897998p-57, 0x1.9507ff1c3c031p-49, -0x1.ae7ee3a7e2a24p-41, 0x1.612460b6ab110p-33,
+    -0x1.ae64567e733b6p-26, 0x1.71de3a556b9b6p-19, -0x1.a01a01a01a00dp-13, 0x1.1111111111111p-7,
+    -0x1.5555555555555p-3,
+    0x1.8p+52}; // 1.5 * 2^52
 __device__ __forceinline__ double sin_force(const double x) {
-  if (fabs(x) > 1.0e6)
-    return sin_library(x);
-  const int ki = __double2int_rn(x * 0x1.45f306dc9c883p-2);
-  const double k = (double)ki;
-  double r = fma(-k, 0x1.921fb54442d18p+1, x);
-  r = fma(-k, 0x1.1a62633145c07p-53, r);
+  const double kd = fma(x, SIN_FORCE_C[0], SIN_FORCE_C[12]);
+  const int parity_bit = __double2loint(kd) << 31; // lowest mantissa bit = parity of k -> sign bit
+  const double k = kd - SIN_FORCE_C[12];
+  double r = fma(-k, SIN_FORCE_C[1], x);
+  r = fma(-k, SIN_FORCE_C[2], r);
   const double t = r * r;
-  double q = -0x1.275f311897998p-57;
-  q = fma(q, t, 0x1.9507ff1c3c031p-49);
-  q = fma(q, t, -0x1.ae7ee3a7e2a24p-41);
-  q = fma(q, t, 0x1.612460b6ab110p-33);
-  q = fma(q, t, -0x1.ae64567e733b6p-26);
-  q = fma(q, t, 0x1.71de3a556b9b6p-19);
-  q = fma(q, t, -0x1.a01a01a01a00dp-13);
-  q = fma(q, t, 0x1.1111111111111p-7);
-  q = fma(q, t, -0x1.5555555555555p-3);
+  double q = SIN_FORCE_C[3];
+  q = fma(q, t, SIN_FORCE_C[4]);
+  q = fma(q, t, SIN_FORCE_C[5]);
+  q = fma(q, t, SIN_FORCE_C[6]);
+  q = fma(q, t, SIN_FORCE_C[7]);
+  q = fma(q, t, SIN_FORCE_C[8]);
+  q = fma(q, t, SIN_FORCE_C[9]);
+  q = fma(q, t, SIN_FORCE_C[10]);
+  q = fma(q, t, SIN_FORCE_C[11]);
   const double s = fma(r * t, q, r);
-  return (ki & 1) ? -s : s;
+  return __hiloint2double(__double2hiint(s) ^ parity_bit, __double2loint(s));
 }
 
 // the same for a divisor b known at run time with c = RN(1 / b) (computed once per thread: the callers'

@@ -14,6 +14,8 @@
 // Reference citations relative to /root/reference/src.
 #include <algorithm>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -187,6 +189,20 @@ int plaq_reduce(mlmcpi_ctx *ctx, const char *what, const SW &sw, const double *x
 }
 
 // ---------------------------------------------------------------------- force
+// One site of sampler/hmcsampler.cc:43-45 given the three plaquette forces F = beta sin P(i,j),
+// F_jm = beta sin P(i,j-1), F_im = beta sin P(i-1,j): p -= dt_p dS/dtheta, theta += dt_x p.  Every leapfrog
+// kernel goes through this one function, with the roundings pinned by intrinsics (products beta sin P
+// rounded once, the force differences rounded, the two axpy's fused), so that all variants produce the
+// same bits whatever the compiler would contract in their different loop bodies.
+__device__ __forceinline__ double plaq_force(const double beta, const double P) { return __dmul_rn(beta, sin_force(P)); }
+__device__ __forceinline__ void leap_site(const double dt_p, const double dt_x, const double F, const double F_jm,
+                                          const double F_im, double2 &p, const double2 th, double2 &th_new) {
+  p.x = __fma_rn(-dt_p, __dsub_rn(F, F_jm), p.x);
+  p.y = __fma_rn(-dt_p, __dsub_rn(F_im, F), p.y);
+  th_new.x = __fma_rn(dt_x, p.x, th.x);
+  th_new.y = __fma_rn(dt_x, p.y, th.y);
+}
+
 // gather form of qft/quenchedschwingeraction.cc:68-89: each link receives +F of
 // one plaquette and -F of another (two-term sums: order-independent, so this is
 // the reference's value given the same sin)
@@ -200,10 +216,10 @@ __global__ void force_kernel(SW sw, const double *x, double *f, int B) {
   const int s = (int)(t - chain * nsite);
   const int j = s / Mt, i = s - j * Mt;
   const double *xc = x + chain * 2 * nsite;
-  const double F = sw.beta * sin_force(plaq(xc, Mt, Mx, i, j));
-  const double Fjm = sw.beta * sin_force(plaq(xc, Mt, Mx, i, wrap_dec(j, Mx)));
-  const double Fim = sw.beta * sin_force(plaq(xc, Mt, Mx, wrap_dec(i, Mt), j));
-  reinterpret_cast<double2 *>(f)[t] = make_double2(F - Fjm, Fim - F);
+  const double F = plaq_force(sw.beta, plaq(xc, Mt, Mx, i, j));
+  const double Fjm = plaq_force(sw.beta, plaq(xc, Mt, Mx, i, wrap_dec(j, Mx)));
+  const double Fim = plaq_force(sw.beta, plaq(xc, Mt, Mx, wrap_dec(i, Mt), j));
+  reinterpret_cast<double2 *>(f)[t] = make_double2(__dsub_rn(F, Fjm), __dsub_rn(Fim, F));
 }
 
 // ------------------------------------------------------------------- leapfrog
@@ -219,16 +235,16 @@ __global__ void leapfrog_naive_kernel(SW sw, double dt_p, double dt_x, const dou
   const int s = (int)(t - chain * nsite);
   const int j = s / Mt, i = s - j * Mt;
   const double *xc = x_in + chain * 2 * nsite;
-  const double F = sw.beta * sin_force(plaq(xc, Mt, Mx, i, j));
-  const double Fjm = sw.beta * sin_force(plaq(xc, Mt, Mx, i, wrap_dec(j, Mx)));
-  const double Fim = sw.beta * sin_force(plaq(xc, Mt, Mx, wrap_dec(i, Mt), j));
+  const double F = plaq_force(sw.beta, plaq(xc, Mt, Mx, i, j));
+  const double Fjm = plaq_force(sw.beta, plaq(xc, Mt, Mx, i, wrap_dec(j, Mx)));
+  const double Fim = plaq_force(sw.beta, plaq(xc, Mt, Mx, wrap_dec(i, Mt), j));
   double2 pp = reinterpret_cast<double2 *>(p)[t];
   const double2 th = reinterpret_cast<const double2 *>(x_in)[t];
-  pp.x -= dt_p * (F - Fjm);
-  pp.y -= dt_p * (Fim - F);
+  double2 tn;
+  leap_site(dt_p, dt_x, F, Fjm, Fim, pp, th, tn);
   reinterpret_cast<double2 *>(p)[t] = pp;
   if (x_out)
-    reinterpret_cast<double2 *>(x_out)[t] = make_double2(th.x + dt_x * pp.x, th.y + dt_x * pp.y);
+    reinterpret_cast<double2 *>(x_out)[t] = tn;
 }
 
 // row-marching kernel: blockDim.x == Mt (<= 1024), grid = (chunks per lattice) * B,
@@ -261,7 +277,7 @@ __global__ void __launch_bounds__(1024)
   sh_t1[i] = prev.y;
   sh_t1[Mt + i] = cur.y;
   __syncthreads();
-  double s_prev = sin_force(prev.x + sh_t1[ip] - cur.x - prev.y);
+  double s_prev = plaq_force(beta, prev.x + sh_t1[ip] - cur.x - prev.y);
   double P_cur = cur.x + sh_t1[Mt + ip] - nxt.x - cur.y;
   __syncthreads();
   int b = 0;
@@ -270,18 +286,17 @@ __global__ void __launch_bounds__(1024)
     const int jp2 = wrap_inc(wrap_inc(j, Mx), Mx);
     const double2 nxt2 = xin[(size_t)jp2 * Mt + i];
     double2 pj = pp[(size_t)j * Mt + i];
-    const double s = sin_force(P_cur);
+    const double s = plaq_force(beta, P_cur); // (the exchanged quantity is the force beta sin P)
     sh_s[b * Mt + i] = s;
     sh_t1[b * Mt + i] = nxt.y;
     __syncthreads();
     const double s_im = sh_s[b * Mt + im];
     const double t1p = sh_t1[b * Mt + ip];
-    const double F = beta * s;
-    pj.x -= dt_p * (F - beta * s_prev);
-    pj.y -= dt_p * (beta * s_im - F);
+    double2 tn;
+    leap_site(dt_p, dt_x, s, s_prev, s_im, pj, cur, tn);
     pp[(size_t)j * Mt + i] = pj;
     if (DRIFT)
-      xout[(size_t)j * Mt + i] = make_double2(cur.x + dt_x * pj.x, cur.y + dt_x * pj.y);
+      xout[(size_t)j * Mt + i] = tn;
     // next row
     P_cur = nxt.x + t1p - nxt2.x - nxt.y;
     s_prev = s;
@@ -379,7 +394,7 @@ __global__ void __launch_bounds__(1024)
   double s_prev;
   {
     const double2 prev = st_theta[i];
-    s_prev = sin_force(prev.x + st_theta[ip].y - cur.x - prev.y);
+    s_prev = plaq_force(beta, prev.x + st_theta[ip].y - cur.x - prev.y);
   }
   int b = 0;
   for (int r = 1; r <= nrow; ++r) { // updating logical row q = r
@@ -388,19 +403,18 @@ __global__ void __launch_bounds__(1024)
     const double2 nxt = st_theta[(size_t)stn * Mt + i];
     const double t1p = st_theta[(size_t)st * Mt + ip].y;
     double2 pj = st_p[(size_t)st * Mt + i];
-    const double s = sin_force(cur.x + t1p - nxt.x - cur.y);
+    const double s = plaq_force(beta, cur.x + t1p - nxt.x - cur.y);
     sh_s[b * Mt + i] = s;
-    __syncthreads(); // sin row visible; every thread is done with logical row r-1
+    __syncthreads(); // force row visible; every thread is done with logical row r-1
     if (i == 0 && r - 1 + S < nq)
       issue(r - 1 + S);
     const double s_im = sh_s[b * Mt + im];
-    const double F = beta * s;
-    pj.x -= dt_p * (F - beta * s_prev);
-    pj.y -= dt_p * (beta * s_im - F);
+    double2 tn;
+    leap_site(dt_p, dt_x, s, s_prev, s_im, pj, cur, tn);
     const size_t g = (size_t)(j0 + r - 1) * Mt + i;
     pp[g] = pj;
     if (DRIFT)
-      xout[g] = make_double2(cur.x + dt_x * pj.x, cur.y + dt_x * pj.y);
+      xout[g] = tn;
     s_prev = s;
     cur = nxt;
     b ^= 1;
@@ -470,7 +484,7 @@ __global__ void __launch_bounds__(1024)
   double sA_prev;
   {
     const double2 prev = st_theta[i];
-    sA_prev = sin_force(prev.x + st_theta[ip].y - cur0.x - prev.y);
+    sA_prev = plaq_force(beta, prev.x + st_theta[ip].y - cur0.x - prev.y);
   }
   __syncthreads(); // row 0 consumed
   if (i == 0 && S < nq)
@@ -491,12 +505,12 @@ __global__ void __launch_bounds__(1024)
       nxt0 = st_theta[(size_t)stn * Mt + i];
       const double t1p = st_theta[(size_t)st * Mt + ip].y;
       pj = st_p[(size_t)st * Mt + i];
-      sA = sin_force(cur0.x + t1p - nxt0.x - cur0.y);
+      sA = plaq_force(beta, cur0.x + t1p - nxt0.x - cur0.y);
       exA[(t & 1) * Mt + i] = sA;
     }
     if (doB) { // stage B, row qb: sin of the step-(k+1) plaquette from theta^1
       const double t1p = exT[(qb & 1) * Mt + ip];
-      sB = sin_force(th1_m.x + t1p - th1_c.x - th1_m.y);
+      sB = plaq_force(beta, th1_m.x + t1p - th1_c.x - th1_m.y);
       exB[(t & 1) * Mt + i] = sB;
     }
     __syncthreads();
@@ -505,10 +519,7 @@ __global__ void __launch_bounds__(1024)
       issue(t + 1 + S);
     if (doA) {
       const double sA_im = exA[(t & 1) * Mt + im];
-      const double F = beta * sA;
-      pj.x -= dtpA * (F - beta * sA_prev);
-      pj.y -= dtpA * (beta * sA_im - F);
-      th1_p = make_double2(cur0.x + dtxA * pj.x, cur0.y + dtxA * pj.y);
+      leap_site(dtpA, dtxA, sA, sA_prev, sA_im, pj, cur0, th1_p);
       pa_p = pj;
       exT[((t + 1) & 1) * Mt + i] = th1_p.y;
       sA_prev = sA;
@@ -517,13 +528,11 @@ __global__ void __launch_bounds__(1024)
     if (doB) {
       if (qb >= 2) {
         const double sB_im = exB[(t & 1) * Mt + im];
-        const double F = beta * sB;
-        double2 pb = pa_m;
-        pb.x -= dtpB * (F - beta * sB_prev);
-        pb.y -= dtpB * (beta * sB_im - F);
+        double2 pb = pa_m, tn;
+        leap_site(dtpB, dtxB, sB, sB_prev, sB_im, pb, th1_m, tn);
         const size_t g = (size_t)(j0 + qb - 2) * Mt + i;
         pout[g] = pb;
-        xout[g] = make_double2(th1_m.x + dtxB * pb.x, th1_m.y + dtxB * pb.y);
+        xout[g] = tn;
       }
       sB_prev = sB;
     }
@@ -531,6 +540,194 @@ __global__ void __launch_bounds__(1024)
     th1_c = th1_p;
     pa_m = pa_c;
     pa_c = pa_p;
+  }
+}
+
+// K leapfrog steps per HBM pass: the register pipeline of leapfrog_rowpipe2_kernel generalised to K
+// stages, with the block size MT = Mt a compile-time constant.  Stage s applies step k+s to logical row
+// q = t - 2 s in iteration t (rows q = 0 .. R + 2K - 1 are the lattice rows j0 - K .. j0 + R + K - 1: K halo
+// rows per side are recomputed); its inputs theta^s rows q, q+1 and p^s row q are the outputs stage s-1
+// left in registers one and two iterations earlier (stage 0: the TMA ring), the neighbouring columns'
+// sin P^s(i-1, q) and theta^s(i+1, q, 1) arrive through double-buffered shared-memory rows, and ONE
+// __syncthreads per row serves all stages.  HBM traffic per site and K steps: 32 (1 + (2K - 1)/R) B read +
+// 32 B written, i.e. 71 B for K = 4, R = 32 against the algorithmic 4 x 64 B.
+//
+// Why a second kernel rather than more template parameters on the first: the two-step kernel is capped at
+// 64 registers by __launch_bounds__(1024), re-materialises the 36 constants of its two sines in every
+// iteration and recomputes ring indices with integer divisions (cuobjdump: 290 instructions per thread
+// and iteration of which 50 are fp64; profiles/r02_summary.md section 4).  Here: compile-time MT, ring
+// stage and mbarrier phase carried incrementally, the producer's row pointer advanced by additions only.
+// Every site update is the expression of the other leapfrog kernels on the same operands: bit-identical
+// trajectories (tests/test_gpu_parity.py::test_rowmarch_equals_generic_leapfrog, test_leapfrog_variants_*).
+template <int K> struct LeapDt {
+  double dtp[K], dtx[K];
+};
+
+#ifndef MLMCPI_LFK_BLOCKS_128
+#define MLMCPI_LFK_BLOCKS_128 4 // resident blocks per SM the register allocation aims at, MT <= 128 (measured: 3 -> 27.5, 4 -> 25.5, 5 (spills) -> 50 us per step)
+#endif
+template <int K, int MT, int S>
+__global__ void __launch_bounds__(MT, (MT <= 128 ? MLMCPI_LFK_BLOCKS_128 : (MT <= 256 ? 2 : 1)))
+    leapfrog_rowpipek_kernel(const double beta, const LeapDt<K> dt, const int Mx, const double *__restrict__ x_in,
+                             double *__restrict__ x_out, const double *__restrict__ p_in,
+                             double *__restrict__ p_out, const int R, const int chunks) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2 *const st_theta = reinterpret_cast<double2 *>(smem_raw); // [S][MT]
+  double2 *const st_p = st_theta + S * MT;                         // [S][MT]
+  double *const exS = reinterpret_cast<double *>(st_p + S * MT);   // [K][2][MT] sin P^s
+  double *const exT = exS + K * 2 * MT;                            // [K][2][MT] theta^s(., ., 1), s >= 1
+  uint64_t *const bars = reinterpret_cast<uint64_t *>(exT + K * 2 * MT);
+  const int i = threadIdx.x;
+  const int ip = (i + 1 == MT) ? 0 : i + 1, im = (i == 0) ? MT - 1 : i - 1;
+  const int chain = blockIdx.x / chunks, chunk = blockIdx.x - chain * chunks;
+  const int j0 = chunk * R;
+  const int nrow = min(R, Mx - j0);
+  const int nq = nrow + 2 * K; // logical rows; p rows exist for q = 1 .. nq - 2
+  const size_t base = (size_t)chain * MT * Mx;
+  const double2 *const xin = reinterpret_cast<const double2 *>(x_in) + base;
+  const double2 *const pin = reinterpret_cast<const double2 *>(p_in) + base;
+  // output row of the last stage: logical row q is lattice row j0 - K + q
+  double2 *const xout = reinterpret_cast<double2 *>(x_out) + base + (ptrdiff_t)(j0 - K) * MT + i;
+  double2 *const pout = reinterpret_cast<double2 *>(p_out) + base + (ptrdiff_t)(j0 - K) * MT + i;
+  constexpr uint32_t row_bytes = 16u * MT;
+
+  if (i == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // producer state (thread 0): next logical row to stream, its lattice row and ring stage
+  int iq = 0, ij = j0 - K, ist = 0;
+  ij = ij < 0 ? ij + Mx : ij; // (K <= Mx)
+  auto issue = [&]() {
+    const bool has_p = (iq >= 1 && iq <= nq - 2);
+    mbar_expect_tx(&bars[ist], has_p ? 2 * row_bytes : row_bytes);
+    bulk_g2s(st_theta + ist * MT, xin + (size_t)ij * MT, row_bytes, &bars[ist]);
+    if (has_p)
+      bulk_g2s(st_p + ist * MT, pin + (size_t)ij * MT, row_bytes, &bars[ist]);
+    ++iq;
+    ij = (ij + 1 == Mx) ? 0 : ij + 1;
+    ist = (ist + 1 == S) ? 0 : ist + 1;
+  };
+  if (i == 0)
+    for (int q = 0; q < S && q < nq; ++q)
+      issue();
+
+  // consumer state: ring stage of row t (st), ring stage / phase of row t + 1 (stn, phn)
+  int st = 0, stn = (1 == S) ? 0 : 1;
+  uint32_t phn = 0;
+  mbar_wait(&bars[0], 0);
+  double2 cur0 = st_theta[i];
+  // th[s][.], pq[s][.]: theta^{s+1}, p^{s+1} of the two rows stage s finished last.  In an iteration of
+  // parity P stage s+1 reads row q from slot P and row q + 1 from slot P ^ 1, and -- the stages being
+  // updated in DESCENDING order -- stage s then writes its new row q + 2 into slot P: no register moves.
+  double2 th[K][2], pq[K][2];
+  double sprev[K];
+#pragma unroll
+  for (int s = 0; s < K; ++s) {
+    sprev[s] = 0.0;
+    th[s][0] = th[s][1] = pq[s][0] = pq[s][1] = make_double2(0., 0.);
+  }
+  // one iteration; PAR = t & 1 and STEADY (every stage does a full update: 3K - 2 <= t <= nq - 2) are
+  // compile-time, so the exchange-buffer offsets are constants and the steady state has no range checks
+  auto iteration = [&](auto par_c, auto steady_c, const int t) {
+    constexpr int PAR = decltype(par_c)::value;
+    constexpr bool STEADY = decltype(steady_c)::value;
+    // Shared-memory loads first, then the K independent sines, then the stores: a store to one exchange
+    // row followed by a load from another must stay in program order (the compiler cannot prove that they
+    // do not alias), which would chain the K sines one after the other (seen in the SASS: four back-to-back
+    // dependent sequences of 20 fp64 instructions, "wait" the dominant stall reason)
+    double ss[K], P[K];
+    bool act[K];
+    double2 nxt0 = cur0, pj0 = make_double2(0., 0.);
+    act[0] = STEADY || (t <= nq - 2);
+    if (act[0]) {
+      mbar_wait(&bars[stn], phn);
+      nxt0 = st_theta[stn * MT + i];
+      const double t1p = st_theta[st * MT + ip].y;
+      pj0 = st_p[st * MT + i];
+      P[0] = cur0.x + t1p - nxt0.x - cur0.y;
+    } else {
+      P[0] = 0.0;
+    }
+#pragma unroll
+    for (int s = 1; s < K; ++s) {
+      const int q = t - 2 * s;
+      act[s] = STEADY || (q >= s && q <= nq - 2 - s);
+      const double2 c = th[s - 1][PAR], n = th[s - 1][PAR ^ 1];
+      const double t1p = exT[(s * 2 + PAR) * MT + ip]; // (finite garbage while the stage is idle)
+      P[s] = c.x + t1p - n.x - c.y;
+    }
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+      ss[s] = plaq_force(beta, P[s]);
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+      if (act[s])
+        exS[(s * 2 + PAR) * MT + i] = ss[s];
+    __syncthreads();
+    // every thread is done with the staged row t: stream the next row into its stage
+    if (i == 0 && iq < nq)
+      issue();
+    double s_im[K];
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+      s_im[s] = exS[(s * 2 + PAR) * MT + im];
+    double2 pn[K], tn[K];
+    bool upd[K];
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const int q = t - 2 * s;
+      upd[s] = STEADY || (act[s] && q >= s + 1);
+      const double2 c = (s == 0) ? cur0 : th[s - 1][PAR];
+      pn[s] = (s == 0) ? pj0 : pq[s - 1][PAR];
+      leap_site(dt.dtp[s], dt.dtx[s], ss[s], sprev[s], s_im[s], pn[s], c, tn[s]);
+    }
+    // stores and the register hand-over, last stage first (stage s overwrites the slot stage s + 1 just read)
+#pragma unroll
+    for (int s = K - 1; s >= 0; --s) {
+      const int q = t - 2 * s;
+      if (upd[s]) {
+        if (s == K - 1) {
+          pout[(ptrdiff_t)q * MT] = pn[s];
+          xout[(ptrdiff_t)q * MT] = tn[s];
+        } else {
+          th[s][PAR] = tn[s];
+          pq[s][PAR] = pn[s];
+          exT[((s + 1) * 2 + PAR) * MT + i] = tn[s].y; // theta^{s+1}(i, q, 1) for the neighbouring column
+        }
+      }
+      if (act[s])
+        sprev[s] = ss[s];
+    }
+    if (act[0])
+      cur0 = nxt0;
+    st = stn;
+    stn = (stn + 1 == S) ? 0 : stn + 1;
+    phn ^= (stn == 0) ? 1u : 0u;
+  };
+  using P0 = std::integral_constant<int, 0>;
+  using P1 = std::integral_constant<int, 1>;
+  const int t_last = nq + K - 3;
+  // ramp-up (t < 3K - 2; 3K - 2 is even for even K), steady state in pairs, ramp-down
+  constexpr int T0 = (3 * K - 2 + 1) & ~1; // first even t of the steady state
+  int t = 0;
+  for (; t < T0 && t <= t_last; t += 2) {
+    iteration(P0{}, std::false_type{}, t);
+    if (t + 1 <= t_last)
+      iteration(P1{}, std::false_type{}, t + 1);
+  }
+  for (; t + 1 <= nq - 2; t += 2) {
+    iteration(P0{}, std::true_type{}, t);
+    iteration(P1{}, std::true_type{}, t + 1);
+  }
+  for (; t <= t_last; t += 2) {
+    iteration(P0{}, std::false_type{}, t);
+    if (t + 1 <= t_last)
+      iteration(P1{}, std::false_type{}, t + 1);
   }
 }
 
@@ -1283,6 +1480,65 @@ int leapfrog_pair(mlmcpi_ctx *ctx, const SW &sw, double dtpA, double dtxA, doubl
   return 0;
 }
 
+// K fused leapfrog steps on all chains (leapfrog_rowpipek_kernel); returns MLMCPI_EUNSUPPORTED when the shape
+// has no specialisation (the caller then falls back to the pair / single-step kernels)
+template <int K, int MT>
+int leapfrog_multi_launch(mlmcpi_ctx *ctx, const SW &sw, const double *dtp, const double *dtx, const double *x_in,
+                          double *x_out, const double *p_in, double *p_out, int B) {
+  constexpr int S = 8;
+  // rows per block: the halo costs (2K - 1) / R extra reads and K / R extra arithmetic; 64 rows measured best
+  // for K = 4 on 128^2 x 512 chains (32: 28.0, 43: 27.5, 64: 25.5, 128: 28.5 us per step)
+  int R = ctx->leapfrog_rows > 0 ? ctx->leapfrog_rows : (K >= 4 ? 64 : 32);
+  if (R > sw.Mx)
+    R = sw.Mx;
+  const int chunks = cdiv(sw.Mx, R);
+  LeapDt<K> dt;
+  for (int k = 0; k < K; ++k) {
+    dt.dtp[k] = dtp[k];
+    dt.dtx[k] = dtx[k];
+  }
+  const size_t smem = (size_t)S * 32 * MT + (size_t)K * 32 * MT + 8 * S;
+  auto kern = leapfrog_rowpipek_kernel<K, MT, S>;
+  if (smem > 48 * 1024)
+    MLMCPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<chunks * B, MT, smem, ctx->stream>>>(sw.beta, dt, sw.Mx, x_in, x_out, p_in, p_out, R, chunks);
+  MLMCPI_LAUNCHED("schwinger::leapfrog_rowpipek");
+  return 0;
+}
+template <int K>
+int leapfrog_multi(mlmcpi_ctx *ctx, const SW &sw, const double *dtp, const double *dtx, const double *x_in,
+                   double *x_out, const double *p_in, double *p_out, int B) {
+  if (sw.Mx < 2 * K + 2)
+    return MLMCPI_EUNSUPPORTED;
+  switch (sw.Mt) {
+  case 64:
+    return leapfrog_multi_launch<K, 64>(ctx, sw, dtp, dtx, x_in, x_out, p_in, p_out, B);
+  case 128:
+    return leapfrog_multi_launch<K, 128>(ctx, sw, dtp, dtx, x_in, x_out, p_in, p_out, B);
+  case 256:
+    return leapfrog_multi_launch<K, 256>(ctx, sw, dtp, dtx, x_in, x_out, p_in, p_out, B);
+  case 512:
+    return leapfrog_multi_launch<K, 512>(ctx, sw, dtp, dtx, x_in, x_out, p_in, p_out, B);
+  }
+  return MLMCPI_EUNSUPPORTED;
+}
+// steps per HBM pass for this shape: MLMCPI_OPT_LEAPFROG_FUSE = 1 picks 4 where the register pipeline
+// fits three blocks per SM (Mt <= 128) and 2 otherwise; 2, 3 (= 4 steps) select explicitly
+int leapfrog_steps_per_pass(const mlmcpi_ctx *ctx, const SW &sw) {
+  if (ctx->leapfrog_variant != 0 || !ctx->leapfrog_fuse)
+    return 1;
+  const bool specialised = sw.Mt == 64 || sw.Mt == 128 || sw.Mt == 256 || sw.Mt == 512;
+  if (!specialised)
+    return 0; // the generic pair kernel
+  if (ctx->leapfrog_fuse == 4)
+    return 0; // the round-1 two-step kernel
+  if (ctx->leapfrog_fuse == 2)
+    return 2;
+  if (ctx->leapfrog_fuse == 3)
+    return 4;
+  return sw.Mt <= 256 ? 4 : 2;
+}
+
 // trajectory of sampler/hmcsampler.cc:31-46.  x_first: state read by the first step;
 // bufA/bufB: ping-pong trial buffers; returns the buffer holding the final state.
 int trajectory(mlmcpi_ctx *ctx, const SW &sw, int nt, double dt, const double *x_first,
@@ -1304,8 +1560,31 @@ int trajectory(mlmcpi_ctx *ctx, const SW &sw, int nt, double dt, const double *x
   prof_begin(ctx);
   uint64_t launches = 0;
   int k = 0;
+  const int per_pass = fuse ? leapfrog_steps_per_pass(ctx, sw) : 1;
   while (k <= nt) {
     int rc;
+    const int K = (per_pass >= 4 && k + 3 <= nt) ? 4 : ((per_pass >= 2 && k + 1 <= nt) ? 2 : 0);
+    if (K) { // steps k .. k+K-1 in one pass (compile-time block size, K-stage register pipeline)
+      double a[4], b[4];
+      for (int q = 0; q < K; ++q) {
+        a[q] = dtp(k + q);
+        b[q] = dtx(k + q);
+      }
+      double *p_next = (p_cur == p) ? p_alt : p;
+      rc = (K == 4) ? leapfrog_multi<4>(ctx, sw, a, b, in, out, p_cur, p_next, B)
+                    : leapfrog_multi<2>(ctx, sw, a, b, in, out, p_cur, p_next, B);
+      if (rc == 0) {
+        p_cur = p_next;
+        last = out;
+        in = out;
+        out = (out == bufA) ? bufB : bufA;
+        k += K;
+        ++launches;
+        continue;
+      }
+      if (rc != MLMCPI_EUNSUPPORTED)
+        return rc;
+    }
     if (fuse && k + 1 <= nt) { // steps k and k+1 in one pass
       double *p_next = (p_cur == p) ? p_alt : p;
       rc = leapfrog_pair(ctx, sw, dtp(k), dtx(k), dtp(k + 1), dtx(k + 1), in, out, p_cur, p_next, B);

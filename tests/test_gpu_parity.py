@@ -691,6 +691,45 @@ def test_edge_shapes(mp, ctx, orc):
             assert np.max(np.abs(host(diag) - wd)) <= 1e-10 * max(np.max(np.abs(wd[:, 1:])), 1.0)
 
 
+def test_leapfrog_k_stage_pipeline_is_bit_identical(mp, ctx, orc):
+    """leapfrog_rowpipek_kernel (2 / 4 leapfrog steps per HBM pass, compile-time block size) against the
+    one-step pipeline and the round-1 two-step kernel: identical bits, for every specialised Mt, ragged
+    last chunks (Mx not a multiple of the 32 rows per block), chunks shorter than the pipeline depth,
+    trajectories whose length leaves 1, 2 or 3 steps for the fall-back kernels, and against the oracle"""
+    rng = np.random.default_rng(17)
+    for Mt, Mx, B, nt in [(64, 64, 3, 9), (128, 128, 2, 12), (128, 40, 2, 7), (256, 34, 2, 6), (512, 12, 1, 5),
+                          (128, 10, 2, 4), (64, 200, 2, 11)]:
+        m = mp.schwinger(Mt, Mx, 5.0)
+        x0 = dev(ctx, rng.uniform(-3, 3, (B, 2 * Mt * Mx)))
+        p0 = dev(ctx, rng.normal(size=(B, 2 * Mt * Mx)))
+        res = {}
+        for fuse in (0, 2, 3, 4, 1):
+            ctx.set_option(mp._lib.OPT_LEAPFROG_FUSE, fuse)
+            x, p = x0.clone(), p0.clone()
+            ctx.leapfrog(m, nt, 0.03, x, p)
+            res[fuse] = (host(x).copy(), host(p).copy())
+        ctx.set_option(mp._lib.OPT_LEAPFROG_FUSE, 1)
+        for fuse in (2, 3, 4, 1):
+            assert np.array_equal(res[fuse][0], res[0][0]), (Mt, Mx, nt, fuse, "theta")
+            assert np.array_equal(res[fuse][1], res[0][1]), (Mt, Mx, nt, fuse, "p")
+        o = po.schwinger(Mt, Mx, 5.0)
+        xo, po_ = orc.leapfrog(o, nt, 0.03, host(x0)[0], host(p0)[0])
+        close(res[1][0][0], xo, tol=1e-11, what=f"theta vs oracle {Mt}x{Mx}")
+        close(res[1][1][0], po_, tol=1e-11, what=f"p vs oracle {Mt}x{Mx}")
+    # rows-per-block option: 8 rows (the halo is then as large as the chunk) and 64
+    m = mp.schwinger(128, 128, 5.0)
+    x0, p0 = ctx.init_state(m, 2, 0, 1), ctx.hmc_momentum(m, 2, 0, 1)
+    out = []
+    for rows in (0, 8, 64):
+        ctx.set_option(mp._lib.OPT_LEAPFROG_ROWS, rows)
+        x, p = x0.clone(), p0.clone()
+        ctx.leapfrog(m, 8, 0.05, x, p)
+        out.append((host(x).copy(), host(p).copy()))
+    ctx.set_option(mp._lib.OPT_LEAPFROG_ROWS, 0)
+    for x, p in out[1:]:
+        assert np.array_equal(x, out[0][0]) and np.array_equal(p, out[0][1])
+
+
 def test_overrelax_one_pass_equals_colour_passes(mp, ctx):
     """the one-pass row-pipelined overrelaxation sweep (all four colours, out of place) gives the
     bits of the four colour passes, for chunked and wrapped lattices and several sweeps in a row"""
