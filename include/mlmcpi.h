@@ -146,13 +146,17 @@ int mlmcpi_rank(const mlmcpi_ctx *ctx);
  * MLMCPI_OPT_FUSED_QM_HIERARCHY: 1 (default) = HierarchicalSampler::draw for 1-D paths with an HMC coarse
  * sampler runs as ONE kernel (one warp per chain, every level on chip), 0 = the sequence of
  * single-purpose kernels; same draw.
+ * MLMCPI_OPT_CASCADE_CACHE: 1 (default) = HierarchicalSampler::draw of the quenched Schwinger model with the
+ *   HMC coarse sampler keeps the coarse level states tentative until the whole cascade has accepted, which
+ *   makes the per-draw restriction chain and its action / conditioned-action reductions redundant (their
+ *   results are cached); 0 = the literal sequence of hierarchicalsampler.cc:55-81.  Same draws, bit for bit.
  * MLMCPI_OPT_GFF_COARSE_SMOOTHING: 1 (default) = the coarse levels a sampler / multilevel driver builds
  *   for a GFF carry the reference's Gibbs-smoothed action Q_hat (gffaction.hh:201-208), whatever sampler
  *   runs on them; 0 = the plain 5-point action on every level (consistent with a heat-bath / HMC coarse
  *   sampler, but the two-level acceptance is ~ 0 beyond 16 x 16). */
 enum { MLMCPI_OPT_EXPCOS_ENVELOPE = 1, MLMCPI_OPT_LEAPFROG_VARIANT = 2, MLMCPI_OPT_LEAPFROG_ROWS = 3,
        MLMCPI_OPT_LEAPFROG_FUSE = 4, MLMCPI_OPT_SWEEP_REVERSE = 5, MLMCPI_OPT_OVERRELAX_ONE_PASS = 6,
-       MLMCPI_OPT_FUSED_QM_HIERARCHY = 7, MLMCPI_OPT_GFF_COARSE_SMOOTHING = 8 };
+       MLMCPI_OPT_FUSED_QM_HIERARCHY = 7, MLMCPI_OPT_GFF_COARSE_SMOOTHING = 8, MLMCPI_OPT_CASCADE_CACHE = 9 };
 int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value);
 /* number of kernels this context has launched so far */
 uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx);

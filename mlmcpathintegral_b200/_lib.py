@@ -18,7 +18,7 @@ QOI_X2, QOI_ROTOR_CHI, QOI_SCHWINGER_CHI, QOI_AVG_PLAQUETTE, QOI_PHI2 = range(5)
 SAMPLER_HMC, SAMPLER_HEATBATH, SAMPLER_CLUSTER, SAMPLER_EXACT = 0, 1, 2, 3
 E_INVAL, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4
 OPT_EXPCOS_ENVELOPE, OPT_LEAPFROG_VARIANT, OPT_LEAPFROG_ROWS, OPT_LEAPFROG_FUSE = 1, 2, 3, 4
-OPT_SWEEP_REVERSE, OPT_OVERRELAX_ONE_PASS, OPT_FUSED_QM_HIERARCHY, OPT_GFF_COARSE_SMOOTHING = 5, 6, 7, 8
+OPT_SWEEP_REVERSE, OPT_OVERRELAX_ONE_PASS, OPT_FUSED_QM_HIERARCHY, OPT_GFF_COARSE_SMOOTHING, OPT_CASCADE_CACHE = 5, 6, 7, 8, 9
 
 
 class Model(C.Structure):

@@ -216,6 +216,10 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
     ctx->leapfrog_rows = value;
     return 0;
   }
+  if (option == MLMCPI_OPT_CASCADE_CACHE && (value == 0 || value == 1)) {
+    ctx->cascade_cache = value;
+    return 0;
+  }
   if (option == MLMCPI_OPT_GFF_COARSE_SMOOTHING && (value == 0 || value == 1)) {
     ctx->gff_coarse_smoothing = value;
     return 0;
@@ -604,13 +608,25 @@ __global__ void hmc_accept_kernel(int B, uint32_t chain0, uint64_t seed, uint64_
   }
 }
 
-__global__ void masked_copy_kernel(double2 *dst, const double2 *src, size_t n2, int B,
-                                   const int32_t *accept) {
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n2 * B)
-    return;
-  if (accept[t / n2])
-    dst[t] = src[t];
+// dst[chain] = src[chain] where accept[chain]: blocks of a rejected chain leave at once (the chain index is
+// block-uniform: grid.y folds the chains, no per-thread division).  WRAP: angles are reduced to [-pi, pi)
+// on the way (what Action::copy_from_fine's mod_2pi would make of them).
+template <bool WRAP>
+__global__ void masked_copy_kernel(double2 *dst, const double2 *src, size_t n2, int B, const int32_t *accept) {
+  for (int chain = blockIdx.y; chain < B; chain += gridDim.y) {
+    if (!accept[chain])
+      continue;
+    const double2 *s = src + (size_t)chain * n2;
+    double2 *d = dst + (size_t)chain * n2;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (size_t)gridDim.x * blockDim.x) {
+      double2 v = s[t];
+      if (WRAP) {
+        v.x = mod_2pi(v.x);
+        v.y = mod_2pi(v.y);
+      }
+      d[t] = v;
+    }
+  }
 }
 __global__ void masked_copy1_kernel(double *dst, const double *src, size_t n, int B,
                                     const int32_t *accept) {
@@ -695,11 +711,19 @@ int launch_hmc_accept(mlmcpi_ctx *ctx, int B, uint32_t chain0, uint64_t draw, co
 }
 
 int launch_masked_copy(mlmcpi_ctx *ctx, double *dst, const double *src, size_t n, int B,
-                       const int32_t *accept) {
+                       const int32_t *accept, bool wrap_angles) {
   if (n % 2 == 0 && ((uintptr_t)dst % 16 == 0) && ((uintptr_t)src % 16 == 0)) {
-    masked_copy_kernel<<<cdiv((long long)(n / 2) * B, 256), 256, 0, ctx->stream>>>(
-        reinterpret_cast<double2 *>(dst), reinterpret_cast<const double2 *>(src), n / 2, B, accept);
+    const size_t n2 = n / 2;
+    const dim3 grid((unsigned)std::min<size_t>(64, (n2 + 1023) / 1024), (unsigned)std::min(B, 65535));
+    if (wrap_angles)
+      masked_copy_kernel<true><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<double2 *>(dst),
+                                                             reinterpret_cast<const double2 *>(src), n2, B, accept);
+    else
+      masked_copy_kernel<false><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<double2 *>(dst),
+                                                              reinterpret_cast<const double2 *>(src), n2, B, accept);
   } else {
+    if (wrap_angles)
+      return ctx_fail(ctx, MLMCPI_EINVAL, "masked copy with angle reduction needs an even, aligned state");
     masked_copy1_kernel<<<cdiv((long long)n * B, 256), 256, 0, ctx->stream>>>(dst, src, n, B, accept);
   }
   MLMCPI_LAUNCHED("masked_copy");
@@ -940,6 +964,12 @@ struct mlmcpi_sampler {
   std::vector<double> t_indep;
   std::vector<int> n_indep, t_sampler;
   std::vector<uint64_t> n_steps; // steps taken on every level (acceptance rates of the level walk)
+  // cascade_draw_cached: the coarse levels are only ever changed by a fully accepted cascade, so
+  // state[l] == restrict^l(state[0]) holds between draws and S_l(state[l]) / S_cond(state[l]) are cached
+  bool cascade_valid = false;
+  std::vector<double *> trial;   // [L] theta'_l of the current draw, levels 1 .. L-2 (sampler-owned)
+  double *Scond_lvl = nullptr;   // [L][B] S_cond(state[l]), 1 <= l <= L-2
+  double *Sprime = nullptr;      // [L][2][B] S_f(theta'_l), S_cond(theta'_l) of the current draw
   // QuenchedSchwingerClusterSampler: the rotor chain psi [B][Mt*Mx] and its action
   double *psi = nullptr;
   mlmcpi_model psi_model = {};
@@ -1252,6 +1282,105 @@ static int sampler_draw_range(mlmcpi_sampler *s, int c0, int B, bool cache0_vali
   return 0;
 }
 
+// commit of a fully accepted cascade on a coarse level: the cached actions follow the state
+__global__ void cascade_commit_kernel(int B, const int32_t *acc, double *S_old, const double *S_prime, double *Scond,
+                                      const double *Scond_prime) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B || !acc[c])
+    return;
+  S_old[c] = S_prime[c];
+  if (Scond)
+    Scond[c] = Scond_prime[c];
+}
+
+// HierarchicalSampler::draw (hierarchicalsampler.cc:55-81) for the quenched Schwinger model with the HMC
+// coarse sampler, WITHOUT the per-draw restriction chain and its reductions.
+//
+// In the reference every draw starts with x[l] = restrict(x[l-1]) for all levels, because a cascade that
+// stopped half-way has left accepted states on the coarse levels that do not belong to the fine state.
+// Here a draw never touches the coarse level states until the whole cascade has accepted: the HMC
+// trajectory ends in a work buffer, the two-level steps propose into trial buffers, each level passes
+// its TRIAL state up as the coarse proposal of the next finer step, and only the chains that accept
+// on level 0 copy their trial states into state[l] (l >= 1) at the end.  Since restrict(fill(prolong(
+// phi))) == phi bit for bit (tests: restrict o fill o prolong = id), state[l] then IS the restriction of
+// the new fine state -- what the reference's restriction chain would produce at the start of the next
+// draw -- and for all other chains nothing changed.  With the states the cached actions stay valid:
+// S_l(state[l]) (= S_c(theta_C) of step l-1 and S_f(theta) of step l) and S_cond(state[l]).  Per draw this
+// removes two restrictions, four full-lattice reductions, the conditioned-action pass of level 1 and the
+// level >= 1 commits of rejected cascades (2.0 of 9.4 ms at 512^2 x 512 chains); the draws are the same,
+// bit for bit (tests/test_gpu_parity.py::test_hierarchical_draw_equals_explicit_cascade).
+static int cascade_draw_cached(mlmcpi_sampler *s) {
+  mlmcpi_ctx *ctx = s->ctx;
+  const int L = s->L, B = s->B;
+  const uint32_t chain0 = s->chain0;
+  int rc;
+  auto S_old = [&](int l) { return s->S_old + (size_t)l * B; };
+  auto Scond_l = [&](int l) { return s->Scond_lvl + (size_t)l * B; };
+  auto Sp = [&](int l, int k) { return s->Sprime + ((size_t)l * 2 + k) * B; };
+  if (!s->cascade_valid) {
+    for (int l = 1; l < L; ++l) {
+      if ((rc = mlmcpi_restrict(ctx, &s->model[l - 1], s->state[l - 1], s->state[l], B)))
+        return rc;
+      if ((rc = mlmcpi_action(ctx, &s->model[l], s->state[l], B, S_old(l))))
+        return rc;
+      if (l <= L - 2 && (rc = mlmcpi_cond_action(ctx, &s->model[l], s->state[l], B, Scond_l(l))))
+        return rc;
+    }
+    s->cascade_valid = true;
+  }
+  if (!s->cache0_valid) {
+    if ((rc = mlmcpi_action(ctx, &s->model[0], s->state[0], B, s->Sf0)))
+      return rc;
+    if ((rc = mlmcpi_cond_action(ctx, &s->model[0], s->state[0], B, s->Scond0)))
+      return rc;
+  }
+  // coarsest level: tentative HMC step (hmcsampler.cc:21-69)
+  const double *coarse_trial = nullptr;
+  if ((rc = schwinger::hmc_trial(ctx, &s->model[L - 1], s->prm.nt, s->prm.dt, s->state[L - 1], B, chain0,
+                                 level_draw(s->draw, L - 1, 0), S_old(L - 1), Sp(L - 1, 0), s->acc, &coarse_trial)))
+    return rc;
+  const double *const hmc_fin = coarse_trial; // (the trajectory's end state, in an HMC work buffer)
+  s->work[0] += (double)B * (s->prm.nt + 1) * n_sites(s->model[L - 1]);
+  count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc, s->counters + (L - 1));
+  MLMCPI_LAUNCHED("count_accept");
+  for (int l = L - 2; l >= 0; --l) {
+    const size_t nf = (size_t)mlmcpi_sample_size(&s->model[l]);
+    double *theta_prime = (l == 0) ? ctx_work(ctx, 4, nf * B) : s->trial[l];
+    if (!theta_prime)
+      return MLMCPI_ENOMEM;
+    // theta' = fill(prolong(trial state of level l+1)), S_f(theta'), S_cond(theta')  (twolevelmetropolisstep.cc:40-66)
+    if ((rc = mlmcpi_prolong_fill_eval(ctx, &s->model[l], coarse_trial, theta_prime, B, chain0,
+                                       level_draw(s->draw, l, 0), Sp(l, 0))))
+      return rc;
+    twolevel_accept_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(
+        B, chain0, ctx->seed, level_draw(s->draw, l, 0), Sp(l, 0), S_old(l + 1), Sp(l + 1, 0),
+        (l == 0) ? s->Sf0 : S_old(l), (l == 0) ? s->Sf0 : nullptr, (l == 0) ? s->Scond0 : Scond_l(l),
+        (l == 0) ? 1 : 0, s->acc, s->acc, nullptr);
+    MLMCPI_LAUNCHED("twolevel_accept");
+    count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc, s->counters + l);
+    MLMCPI_LAUNCHED("count_accept");
+    s->work[2] += (double)B * n_sites(s->model[l]);
+    if (l == 0) {
+      if ((rc = launch_masked_copy(ctx, s->state[0], theta_prime, nf, B, s->acc))) // :78-88
+        return rc;
+    }
+    coarse_trial = theta_prime;
+  }
+  // the chains whose cascade accepted on every level take their trial states on the coarse levels
+  for (int l = 1; l < L; ++l) {
+    // (the HMC trajectory does not reduce its angles; the restriction of the accepted fine state, which
+    // this copy stands in for, does: quenchedschwingeraction.cc:152-195)
+    const double *src = (l == L - 1) ? hmc_fin : s->trial[l];
+    if (src != s->state[l] && (rc = launch_masked_copy(ctx, s->state[l], src, (size_t)mlmcpi_sample_size(&s->model[l]),
+                                                       B, s->acc, l == L - 1)))
+      return rc;
+    cascade_commit_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, s->acc, S_old(l), Sp(l, 0),
+                                                                (l <= L - 2) ? Scond_l(l) : nullptr, Sp(l, 1));
+    MLMCPI_LAUNCHED("cascade_commit");
+  }
+  return 0;
+}
+
 // MultilevelSampler::draw, sampler/multilevelsampler.cc:71-112.  All chains walk the levels
 // in lockstep: the decision "independent sample reached on this level" uses tau_int of the
 // per-level statistics averaged over the chains, exactly what the reference's Statistics
@@ -1300,6 +1429,13 @@ static int multilevel_draw(mlmcpi_sampler *s) {
     }
   } while (level >= 0);
   return 0;
+}
+
+// cascade_draw_cached serves the hierarchical sampler of the quenched Schwinger model with one HMC
+// trajectory per draw on the coarsest level (BASELINE config C4 / C5)
+static bool cascade_cache_applies(const mlmcpi_sampler *s) {
+  return s->ctx->cascade_cache && s->L >= 2 && !s->prm.multilevel && s->model[0].model == MLMCPI_SCHWINGER &&
+         s->prm.kind == MLMCPI_SAMPLER_HMC && std::max(1, s->prm.n_rep) == 1 && s->prm.nt >= 1;
 }
 
 extern "C" {
@@ -1358,6 +1494,18 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
     return ctx_fail(ctx, MLMCPI_ENOMEM, "out of device memory for the sampler states");
   }
   cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->L, ctx->stream);
+  if (cascade_cache_applies(s)) {
+    s->trial.assign(s->L, nullptr);
+    for (int l = 1; l + 2 <= s->L && ok; ++l)
+      ok = mlmcpi_alloc(ctx, (size_t)mlmcpi_sample_size(&s->model[l]) * B, &s->trial[l]) == 0;
+    ok = ok && mlmcpi_alloc(ctx, (size_t)s->L * B, &s->Scond_lvl) == 0 &&
+         mlmcpi_alloc(ctx, (size_t)s->L * 2 * B, &s->Sprime) == 0;
+    if (!ok) {
+      cudaGetLastError();
+      mlmcpi_sampler_destroy(s);
+      return ctx_fail(ctx, MLMCPI_ENOMEM, "out of device memory for the cascade's trial states");
+    }
+  }
   int rc;
   if (s->prm.kind == MLMCPI_SAMPLER_CLUSTER && s->model[s->L - 1].model == MLMCPI_SCHWINGER) {
     // quenchedschwingerclustersampler.cc:16-23: rotor chain over the Mt*Mx cells, T = 1,
@@ -1457,6 +1605,13 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
   }
   if (s->psi)
     cudaFree(s->psi);
+  for (double *d : s->trial)
+    if (d)
+      cudaFree(d);
+  if (s->Scond_lvl)
+    cudaFree(s->Scond_lvl);
+  if (s->Sprime)
+    cudaFree(s->Sprime);
   for (mlmcpi_stats *st : s->stats_sampler)
     mlmcpi_stats_destroy(st);
   for (double *d : s->SfL)
@@ -1497,6 +1652,7 @@ int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x) {
   if (s->prm.multilevel)
     return 0;
   s->cache0_valid = false;
+  s->cascade_valid = false;
   return mlmcpi_copy(s->ctx, s->state[0], d_x, (size_t)mlmcpi_sample_size(&s->model[0]) * s->B);
 }
 
@@ -1526,8 +1682,14 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
                                   ctx->stream));
     return 0;
   }
-  if ((rc = sampler_draw_range(s, 0, B, s->cache0_valid)))
-    return rc;
+  if (cascade_cache_applies(s) && !s->trial.empty()) {
+    if ((rc = cascade_draw_cached(s)))
+      return rc;
+  } else {
+    s->cascade_valid = false;
+    if ((rc = sampler_draw_range(s, 0, B, s->cache0_valid)))
+      return rc;
+  }
   s->cache0_valid = s->L > 1;
   s->draw++;
   s->cluster_updates += std::max(1, s->prm.n_updates);
@@ -1579,6 +1741,7 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
     for (int k = 0; k < n_ranges; ++k) {
       const int c0 = (int)((long long)s->B * k / n_ranges), c1 = (int)((long long)s->B * (k + 1) / n_ranges);
       MLMCPI_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev[k], 0));
+      s->cascade_valid = false;
       if ((rc = sampler_draw_range(s, c0, c1 - c0, false)))
         return rc;
       if (h_q)
@@ -1657,6 +1820,7 @@ int mlmcpi_sampler_autotune(mlmcpi_sampler *s, double p_accept_target, int n_rou
   mlmcpi_ctx *ctx = s->ctx;
   if (s->prm.kind != MLMCPI_SAMPLER_HMC)
     return ctx_fail(ctx, MLMCPI_EINVAL, "autotune is defined for the HMC sampler");
+  s->cascade_valid = false; // the tuning steps advance state[L-1]
   const int l = s->L - 1, B = s->B;
   const mlmcpi_model *m = &s->model[l];
   for (int lev = 1; lev < s->L; ++lev) { // tune on the restricted current state

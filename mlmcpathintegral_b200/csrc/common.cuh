@@ -33,6 +33,7 @@ struct mlmcpi_ctx {
   int sweep_reverse = 0;    // MLMCPI_OPT_SWEEP_REVERSE: colours visited in descending order
   int overrelax_one_pass = 1; // MLMCPI_OPT_OVERRELAX_ONE_PASS: all colours of a Schwinger OR sweep in one HBM pass
   int fused_qm_hierarchy = 1; // MLMCPI_OPT_FUSED_QM_HIERARCHY: 1-D hierarchical draw in one kernel
+  int cascade_cache = 1; // MLMCPI_OPT_CASCADE_CACHE: Schwinger / HMC hierarchy without the per-draw restriction chain
   int gff_coarse_smoothing = 1; // MLMCPI_OPT_GFF_COARSE_SMOOTHING: coarse GFF levels carry Q_hat (reference)
   uint64_t launches = 0;
   int n_sm = 148;
@@ -675,6 +676,8 @@ int sweep_sequence(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int, int, 
 namespace schwinger {
 int overrelax_sweeps(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int);
 int from_cluster(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t, uint64_t);
+int hmc_trial(mlmcpi_ctx *, const mlmcpi_model *, int, double, const double *, int, uint32_t, uint64_t,
+              const double *, double *, int32_t *, const double **);
 }
 
 // host helpers shared by the model files (capi.cu)
@@ -684,7 +687,7 @@ int launch_hmc_accept(mlmcpi_ctx *ctx, int B, uint32_t chain0, uint64_t draw, co
                       const double *d_S_trial, const double *d_T_cur, const double *d_T_trial,
                       int32_t *d_accept, double *d_diag);
 int launch_masked_copy(mlmcpi_ctx *ctx, double *d_dst, const double *d_src, size_t n, int B,
-                       const int32_t *d_accept);
+                       const int32_t *d_accept, bool wrap_angles = false);
 int launch_half_sqnorm(mlmcpi_ctx *ctx, const double *d_p, size_t n, int B, double *d_T);
 
 // ------------------------------------------- deterministic two-pass reductions

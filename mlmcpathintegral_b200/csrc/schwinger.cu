@@ -1729,6 +1729,38 @@ static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool 
 // n_sweeps overrelaxation sweeps.  Ascending colour order on lattices with even extents and at most
 // 1024 columns: the one-pass kernel, ping-ponging between x and a work buffer (copied back when
 // n_sweeps is odd); otherwise four colour passes per sweep, in place.
+// HMCSampler::single_step without the commit: the trajectory's end state stays in a work buffer (*fin),
+// d_accept tells which chains would take it, d_S_trial is its action.  d_S_cur: the action of x, known to the
+// caller (the hierarchical cascade caches it: csrc/capi.cu:cascade_draw_cached).  Same variates, same
+// arithmetic, same accept flags as hmc_step.
+int hmc_trial(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, const double *x, int B, uint32_t chain0,
+              uint64_t draw, const double *d_S_cur, double *d_S_trial, int32_t *d_accept, const double **fin_out) {
+  SW sw = make_sw(ctx, m);
+  const size_t nd = (size_t)2 * sw.Mt * sw.Mx;
+  const size_t n = nd * B;
+  double *p = ctx_work(ctx, 0, n), *bufA = ctx_work(ctx, 1, n), *bufB = ctx_work(ctx, 2, n);
+  double *red = ctx_work(ctx, 3, (size_t)5 * B);
+  if (!p || !bufA || !bufB || !red)
+    return MLMCPI_ENOMEM;
+  double *T_cur = red + 2 * B, *T_trial = red + 3 * B;
+  int rc;
+  if ((rc = hmc_momentum(ctx, m, p, B, chain0, draw)))
+    return rc;
+  if ((rc = launch_half_sqnorm(ctx, p, nd, B, T_cur)))
+    return rc;
+  double *fin = nullptr;
+  if ((rc = trajectory(ctx, sw, nt, dt, x, bufA, bufB, p, B, &fin)))
+    return rc;
+  if ((rc = launch_half_sqnorm(ctx, p, nd, B, T_trial)))
+    return rc;
+  if ((rc = action(ctx, m, fin ? fin : x, B, d_S_trial)))
+    return rc;
+  if ((rc = launch_hmc_accept(ctx, B, chain0, draw, d_S_cur, d_S_trial, T_cur, T_trial, d_accept, nullptr)))
+    return rc;
+  *fin_out = fin ? fin : x;
+  return 0;
+}
+
 int dof_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, int ell, int heatbath, uint32_t chain0,
                uint64_t draw) {
   SW sw = make_sw(ctx, m);

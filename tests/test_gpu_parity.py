@@ -380,6 +380,43 @@ def test_hierarchical_draw_equals_explicit_cascade(mp, ctx, beta):
     assert 0 < n_acc < 4 * B  # both branches of the cascade were exercised
 
 
+def test_cached_cascade_equals_literal_cascade(mp, ctx):
+    """MLMCPI_OPT_CASCADE_CACHE: the hierarchical Schwinger draw that keeps the coarse levels tentative (no
+    restriction chain, cached level actions) against the literal sequence of hierarchicalsampler.cc:55-81:
+    identical states and acceptance counters over many draws, 2 to 4 levels, with set_state and autotune
+    (which advance coarse states behind the cache's back) in between"""
+    for M, beta, L, B in [(32, 9.0, 2, 16), (64, 64.0, 3, 12), (64, 16.0, 4, 8), (32, 4.0, 3, 10)]:
+        m = mp.schwinger(M, M, beta)
+        res = []
+        for cache in (0, 1):
+            ctx.set_option(mp._lib.OPT_CASCADE_CACHE, cache)
+            smp = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=L, nt=6, dt=0.05,
+                             renorm=mp.RENORM_PERTURBATIVE, chain0=7)
+            x = ctx.init_state(m, B, 7, 3)
+            for k in range(3):
+                ctx.heatbath_sweep(m, x, 7, k)
+            smp.set_state(x)
+            states = []
+            for d in range(12):
+                smp.draw(x)
+                states.append(host(x).copy())
+                if d == 4:
+                    smp.autotune(0.8, 2, 2 * B)
+                    smp.set_dt(0.05)
+                if d == 8:
+                    smp.set_state(x)
+            res.append((states, smp.p_accept(), host(smp.get_state()).copy()))
+            smp.close()
+        ctx.set_option(mp._lib.OPT_CASCADE_CACHE, 1)
+        # (identical up to the last bits of the coarse angles: theta'_l stands in for restrict(fill(prolong(
+        # theta'_l))), which reproduces it up to rounding)
+        for d, (a, b) in enumerate(zip(res[0][0], res[1][0])):
+            ang_close(a, b, tol=1e-9, what=f"{M}^2 beta {beta} {L} levels, draw {d}")
+        assert res[0][1] == res[1][1]
+        ang_close(res[0][2], res[1][2], tol=1e-9, what="get_state")
+        assert 0.0 < res[1][1][0] < 1.0 or L == 2
+
+
 def test_ho_exact_sampler(mp, ctx, orc):
     """HarmonicOscillatorAction::draw (Cholesky sampler): draw by draw against the oracle, and as the
     coarse sampler of a hierarchy (sampler = 'exact' of hierarchicalsampler.hh)"""
