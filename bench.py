@@ -84,6 +84,8 @@ def parse():
     ap.add_argument("--ess-draws", type=int, default=40, help="draws of the ESS leg (cluster coarse sampler); 0 = skip")
     ap.add_argument("--ess-updates", type=int, default=100, help="cluster updates per draw in the ESS leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the beta = 4, sweep-roofline and MLMC legs")
+    ap.add_argument("--mlmc-chains", type=int, default=64, help="chains per GPU and level of the MLMC leg (configs[4])")
+    ap.add_argument("--mlmc-epsilon", type=float, default=0.25, help="tolerance of the MLMC leg on V chi_t (~ 6.5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
@@ -284,6 +286,24 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_cpus(index):
+    """run this process on the CPUs next to its GPU (NVML's ideal affinity), so that the pinned host buffers
+    it allocates afterwards are NUMA-local to the GPU's PCIe root"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"gpu": index, "cpus": "%d-%d (%d)" % (allowed[0], allowed[-1], len(allowed)) if allowed else None}
+    except Exception as e:  # no NVML / no permission: stay where we are
+        return {"gpu": index, "cpus": None, "note": "affinity not set: %s" % type(e).__name__}
+
+
 def _timed(torch, fn, n):
     """CUDA-event time (ms) of n calls of fn on the current stream, after one untimed call"""
     fn()
@@ -373,6 +393,56 @@ def beta4_leg(mp, ctx, torch, a, rank):
                    "reference as here; this leg times the kernels of the regime"}
     s.close()
     del x
+    torch.cuda.empty_cache()
+    return out
+
+
+def mlmc_leg(mp, torch, dist, a, local, rank, world):
+    """BASELINE configs[4]: quenched Schwinger 1024 x 1024, MULTILEVEL MONTE CARLO (MonteCarloMultiLevel::evaluate,
+    montecarlo/montecarlomultilevel.cc:71-204) with the chains of every level sharded over the GPUs; the library's
+    own host-side decisions (sub-sampling on tau_int, sample allocation from the variances and costs of all levels)
+    run over the chains of ALL ranks through mlmcpi_set_allreduce (NCCL), so the ranks stay in lockstep.  3 MLMC
+    levels 1024^2 / 512^2 / 256^2; the sampler of every level is the hierarchical sampler down to 128^2 with the
+    cluster coarse sampler (the ergodic choice, see ess_leg)."""
+    import time as _time
+    L_fine, n_level, B = 1024, 3, a.mlmc_chains
+    beta = float(L_fine * L_fine) / 256.0
+    ctx = mp.Context(local, seed=0x5EED0002)
+    if world > 1:
+        ctx.attach_process_group()
+    m = mp.schwinger(L_fine, L_fine, beta)
+    torch.cuda.synchronize()
+    t0 = _time.perf_counter()
+    mc = mp.MultilevelMC(ctx, m, B, n_level=n_level, epsilon=a.mlmc_epsilon, qoi=mp.QOI_SCHWINGER_CHI, n_burnin=20,
+                         n_autocorr_window=20, n_min_samples_qoi=4 * B * world, max_iterations=8, chain0=rank * B,
+                         kind=mp.SAMPLER_CLUSTER, n_levels=n_level + 1, renorm=mp.RENORM_PERTURBATIVE,
+                         ctype=mp.COARSEN_BOTH, n_updates=100)
+    ctx.sync()
+    t1 = _time.perf_counter()
+    launches0 = ctx.launches
+    converged = mc.evaluate()
+    ctx.sync()
+    t2 = _time.perf_counter()
+    value, error, levels = mc.result()
+    tt = torch.tensor([t1 - t0, t2 - t1], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    setup_s, eval_s = (float(v) for v in tt.cpu())
+    analytic = mp._lib.lib.mlmcpi_schwinger_chit_perturbative(beta, L_fine * L_fine)
+    fine_sites = sum(lv["samples"] * (L_fine >> l) ** 2 for l, lv in enumerate(levels))
+    out = {
+        "workload": "configs[4]: quenched Schwinger %dx%d, multilevel Monte Carlo, %d levels, chains sharded over %d "
+                    "GPU(s), NCCL all-reduce of the QoI moments and of every host-side decision" % (L_fine, L_fine, n_level, world),
+        "beta": beta, "chains_per_gpu_and_level": B, "epsilon": a.mlmc_epsilon, "converged": bool(converged),
+        "estimate": value, "error": error, "analytic_perturbative": analytic,
+        "deviation_sigma": abs(value - analytic) / error if error > 0 else None,
+        "levels": levels, "setup_s": setup_s, "evaluate_s": eval_s,
+        "samples_per_s": sum(lv["samples"] for lv in levels) / eval_s,
+        "sampled_lattice_sites_per_s": fine_sites / eval_s,
+        "gpu_launches": ctx.launches - launches0,
+    }
+    mc.close()
+    ctx.close()
     torch.cuda.empty_cache()
     return out
 
@@ -502,31 +572,56 @@ def gpu_main(a):
     st = mp.Statistics.finalize(packed.cpu().numpy(), k_max)
     p_acc = sampler.p_accept()
 
-    # ---- e2e: the host-buffer entry point, pinned host state in, QoI out, every step
+    # ---- e2e: the public host API a driver calls.  As Sampler::draw(state) does, every step hands the NEW
+    #      STATES of all chains (and their QoI) back to the host; the chains themselves stay resident on the
+    #      device, as the reference's samplers keep phi_state_cur.  The device-to-host copy of step k runs on a
+    #      second stream while step k+1 computes (mlmcpi_sampler_draw_host_async, two pinned buffers that are
+    #      allocated after the process has been bound to the CPUs next to its GPU).
     e2e = None
     if not a.no_e2e:
         n = mp.sample_size(m)
-        h_x = torch.empty(B, n, dtype=torch.float64, pin_memory=True)
-        h_q = torch.empty(B, dtype=torch.float64, pin_memory=True)
-        h_x.copy_(x)
-        torch.cuda.synchronize()
-        sampler.draw_host(h_x, QOI, h_q, None)  # warm-up
+        affinity0 = os.sched_getaffinity(0)
+        numa = bind_to_gpu_cpus(local)
+        h_x = [torch.empty(B, n, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        h_q = [torch.empty(B, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        for k in range(2):  # warm-up (and first touch of the pinned pages)
+            sampler.draw_host_async(QOI, h_q[k], h_x[k])
+        sampler.wait_host()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k_e2e = max(1, min(a.steps, 5))
-        e0.record()
-        for _ in range(k_e2e):
-            sampler.draw_host(h_x, QOI, h_q, None)
-        e1.record()
-        torch.cuda.synchronize()
-        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
+        k_e2e = max(2, min(a.steps, 6))
+        t_e0 = time.perf_counter()
+        for k in range(k_e2e):
+            sampler.draw_host_async(QOI, h_q[k & 1], h_x[k & 1])
+        sampler.wait_host()  # the last copy has landed
+        t_full = time.perf_counter() - t_e0
+        # the same API handing back the QoI only (what a driver that evaluates on the device needs)
+        t_e0 = time.perf_counter()
+        for k in range(k_e2e):
+            sampler.draw_host_async(QOI, h_q[k & 1], None)
+        sampler.wait_host()
+        t_qoi = time.perf_counter() - t_e0
+        te = torch.tensor([t_full, t_qoi], dtype=torch.float64, device=ctx.device)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": units_per_step * world * k_e2e / (float(te.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": B * n * 8, "d2h_bytes_per_step": B * 8, "steps": k_e2e,
-               "api": "mlmcpi_sampler_draw_host (pinned host SampleStates in, QoI out)"}
+        t_full, t_qoi = (float(v) for v in te.cpu())
+        chk = float(h_q[(k_e2e - 1) & 1].mean())  # the host really holds the result
+        os.sched_setaffinity(0, affinity0)  # (the cpu_baseline leg uses every core)
+        e2e = {"value": units_per_step * world * k_e2e / t_full, "unit": UNIT,
+               "h2d_bytes_per_step": 0, "d2h_bytes_per_step": B * n * 8 + B * 8, "steps": k_e2e,
+               "ms_per_step": 1e3 * t_full / k_e2e,
+               "d2h_gbs_per_gpu": (B * n * 8 + B * 8) * k_e2e / t_full / 1e9,
+               "api": "mlmcpi_sampler_draw_host_async + mlmcpi_sampler_wait_host: chains resident on the device, the new "
+                      "states of all chains [B][n] and their QoI handed back to pinned host buffers every step, the "
+                      "copy of step k overlapped with the draw of step k+1",
+               "inputs": "none per step: a sampler's only input is its own previous state (resident) and the Philox "
+                         "counters; the per-step host traffic is the OUTPUT, as in Sampler::draw(state)",
+               "limited_by": "the host link: %.1f GiB of states per step and GPU" % (B * n * 8 / 2 ** 30),
+               "qoi_only": {"value": units_per_step * world * k_e2e / t_qoi, "ms_per_step": 1e3 * t_qoi / k_e2e,
+                            "d2h_bytes_per_step": B * 8,
+                            "note": "same API with h_x_out = NULL: the QoI of every chain to the host each step"},
+               "numa": numa, "mean_qoi_on_host": chk}
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -544,6 +639,11 @@ def gpu_main(a):
         beta4 = beta4_leg(mp, ctx, torch, a, rank)
     if world > 1:
         dist.barrier()
+    mlmc = None
+    if headline and not a.no_extra:  # every rank: the MLMC chains are sharded
+        del x
+        torch.cuda.empty_cache()
+        mlmc = mlmc_leg(mp, torch, dist, a, local, rank, world)
 
     if rank == 0:
         achieved = lf_bytes / (lf_ms * 1e-3) / 1e9 if lf_ms > 0 else None
@@ -597,6 +697,8 @@ def gpu_main(a):
             cfg["ess_per_s"] = st["samples"] / st["tau_int"] / (ms_max * 1e-3)
         if sweeps is not None:
             cfg["extra"] = {"schwinger%d_beta4" % a.lattice: beta4}
+        if mlmc is not None:
+            cfg.setdefault("extra", {})["schwinger1024_mlmc"] = mlmc
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,

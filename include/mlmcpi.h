@@ -150,13 +150,17 @@ int mlmcpi_rank(const mlmcpi_ctx *ctx);
  *   HMC coarse sampler keeps the coarse level states tentative until the whole cascade has accepted, which
  *   makes the per-draw restriction chain and its action / conditioned-action reductions redundant (their
  *   results are cached); 0 = the literal sequence of hierarchicalsampler.cc:55-81.  Same draws, bit for bit.
+ * MLMCPI_OPT_TAU_REFRESH: the level walks of MultilevelSampler::draw and MonteCarloMultiLevel::draw_coarse_sample
+ *   decide on tau_int of a device Statistics object (a pack kernel, a device-to-host copy, a stream
+ *   synchronisation and, with several processes, an all-reduce).  The reference asks at every sample; here an
+ *   answer is reused for a number of calls that doubles from 1 up to this value (default 16; 1 = every call).
  * MLMCPI_OPT_GFF_COARSE_SMOOTHING: 1 (default) = the coarse levels a sampler / multilevel driver builds
  *   for a GFF carry the reference's Gibbs-smoothed action Q_hat (gffaction.hh:201-208), whatever sampler
  *   runs on them; 0 = the plain 5-point action on every level (consistent with a heat-bath / HMC coarse
  *   sampler, but the two-level acceptance is ~ 0 beyond 16 x 16). */
 enum { MLMCPI_OPT_EXPCOS_ENVELOPE = 1, MLMCPI_OPT_LEAPFROG_VARIANT = 2, MLMCPI_OPT_LEAPFROG_ROWS = 3,
        MLMCPI_OPT_LEAPFROG_FUSE = 4, MLMCPI_OPT_SWEEP_REVERSE = 5, MLMCPI_OPT_OVERRELAX_ONE_PASS = 6,
-       MLMCPI_OPT_FUSED_QM_HIERARCHY = 7, MLMCPI_OPT_GFF_COARSE_SMOOTHING = 8, MLMCPI_OPT_CASCADE_CACHE = 9 };
+       MLMCPI_OPT_FUSED_QM_HIERARCHY = 7, MLMCPI_OPT_GFF_COARSE_SMOOTHING = 8, MLMCPI_OPT_CASCADE_CACHE = 9, MLMCPI_OPT_TAU_REFRESH = 10 };
 int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value);
 /* number of kernels this context has launched so far */
 uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx);
@@ -346,6 +350,14 @@ int mlmcpi_sampler_get_state(mlmcpi_sampler *s, double *d_x);
  * h_q[B] (and h_x_out[B][n] if not NULL) are copied back; synchronous */
 int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, double *h_q,
                              double *h_x_out);
+/* the same with the chains RESIDENT on the device (as Sampler keeps its phi_state_cur) and the hand-over
+ * to the host pipelined: one draw, QoI of the new states, snapshot of the states, and the device-to-host
+ * copies of h_q[B] / h_x_out[B][n] (either may be NULL) run on a second stream while the next draw
+ * computes.  Returns without synchronising: the host buffers of this call are complete after the NEXT call
+ * or after mlmcpi_sampler_wait_host -- alternate two pinned buffers.  This is the entry point bench.py's
+ * `e2e` figure goes through. */
+int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, double *h_x_out);
+int mlmcpi_sampler_wait_host(mlmcpi_sampler *s);
 int mlmcpi_sampler_level_model(const mlmcpi_sampler *s, int level, mlmcpi_model *m);
 /* MCMCStep::p_accept of every level (montecarlo/mcmcstep.hh:21-72): accepted / attempted steps of
  * that level -- in the hierarchical cascade a level is only attempted by the chains all coarser

@@ -18,7 +18,7 @@ QOI_X2, QOI_ROTOR_CHI, QOI_SCHWINGER_CHI, QOI_AVG_PLAQUETTE, QOI_PHI2 = range(5)
 SAMPLER_HMC, SAMPLER_HEATBATH, SAMPLER_CLUSTER, SAMPLER_EXACT = 0, 1, 2, 3
 E_INVAL, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4
 OPT_EXPCOS_ENVELOPE, OPT_LEAPFROG_VARIANT, OPT_LEAPFROG_ROWS, OPT_LEAPFROG_FUSE = 1, 2, 3, 4
-OPT_SWEEP_REVERSE, OPT_OVERRELAX_ONE_PASS, OPT_FUSED_QM_HIERARCHY, OPT_GFF_COARSE_SMOOTHING, OPT_CASCADE_CACHE = 5, 6, 7, 8, 9
+OPT_SWEEP_REVERSE, OPT_OVERRELAX_ONE_PASS, OPT_FUSED_QM_HIERARCHY, OPT_GFF_COARSE_SMOOTHING, OPT_CASCADE_CACHE, OPT_TAU_REFRESH = 5, 6, 7, 8, 9, 10
 
 
 class Model(C.Structure):
@@ -122,6 +122,8 @@ SIGNATURES = {
     "mlmcpi_sampler_level_model": (_i, [_vp, _i, _MP]),
     "mlmcpi_dof_update": (_i, [_vp, _MP, _vp, _i, _i, _i, _u32, _u64]),
     "mlmcpi_sampler_get_state": (_i, [_vp, _vp]),
+    "mlmcpi_sampler_draw_host_async": (_i, [_vp, _i, _vp, _vp]),
+    "mlmcpi_sampler_wait_host": (_i, [_vp]),
     "mlmcpi_sampler_stats": (_i, [_vp, _dp]),
     "mlmcpi_sampler_reset_stats": (_i, [_vp]),
     "mlmcpi_sampler_work": (_i, [_vp, _dp]),

@@ -358,6 +358,17 @@ class Sampler:
                                                      else a.data_ptr())
         self.ctx._ck(L.mlmcpi_sampler_draw_host(self.h, hp(x_in), qoi, hp(q_out), hp(x_out)))
 
+    def draw_host_async(self, qoi=QOI_SCHWINGER_CHI, q_out=None, x_out=None):
+        """pipelined host hand-over (mlmcpi_sampler_draw_host_async): pinned host tensors / numpy arrays;
+        the buffers of this call are complete after the next call or after wait_host()"""
+        def hp(a):
+            return None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray)
+                                                     else a.data_ptr())
+        self.ctx._ck(L.mlmcpi_sampler_draw_host_async(self.h, qoi, hp(q_out), hp(x_out)))
+
+    def wait_host(self):
+        self.ctx._ck(L.mlmcpi_sampler_wait_host(self.h))
+
     def level_model(self, level):
         m = Model()
         self.ctx._ck(L.mlmcpi_sampler_level_model(self.h, level, C.byref(m)))

@@ -216,6 +216,10 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
     ctx->leapfrog_rows = value;
     return 0;
   }
+  if (option == MLMCPI_OPT_TAU_REFRESH && value >= 1 && value <= 1024) {
+    ctx->tau_refresh = value;
+    return 0;
+  }
   if (option == MLMCPI_OPT_CASCADE_CACHE && (value == 0 || value == 1)) {
     ctx->cascade_cache = value;
     return 0;
@@ -931,6 +935,12 @@ static int twolevel_step_impl(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const m
 
 // ================================================================== samplers
 static mlmcpi_ctx *mlmcpi_stats_ctx(mlmcpi_stats *st);
+// cached answer of a tau_int query (stats_query_cached below)
+struct TauCache {
+  double st[6] = {0, 0, 0, 1, 0, 0};
+  int age = 0, interval = 1;
+  bool valid = false;
+};
 struct mlmcpi_sampler {
   mlmcpi_ctx *ctx = nullptr;
   mlmcpi_sampler_params prm;
@@ -951,7 +961,9 @@ struct mlmcpi_sampler {
   // of the step one level finer, and S_f(theta) of the step on this level) and after the level's
   // own update (= S_c(phi_c) of the step one level finer); [L][B] each
   double *S_old = nullptr, *S_new = nullptr;
-  cudaStream_t copy_stream = nullptr; // H2D stream of mlmcpi_sampler_draw_host
+  cudaStream_t copy_stream = nullptr; // H2D stream of mlmcpi_sampler_draw_host, D2H stream of ..._async
+  double *stage_x = nullptr, *stage_q = nullptr; // snapshots the asynchronous host copies read
+  bool host_copy_pending = false;
   cudaEvent_t ev[9] = {};
   int32_t *acc = nullptr, *acc_step = nullptr;          // [B]
   unsigned long long *counters = nullptr;               // [L] accepted chains per level
@@ -964,6 +976,7 @@ struct mlmcpi_sampler {
   std::vector<double> t_indep;
   std::vector<int> n_indep, t_sampler;
   std::vector<uint64_t> n_steps; // steps taken on every level (acceptance rates of the level walk)
+  std::vector<TauCache> tau_cache; // [L] cached tau_int of stats_sampler (level walk decisions)
   // cascade_draw_cached: the coarse levels are only ever changed by a fully accepted cascade, so
   // state[l] == restrict^l(state[0]) holds between draws and S_l(state[l]) / S_cond(state[l]) are cached
   bool cascade_valid = false;
@@ -986,6 +999,28 @@ static int stats_query(mlmcpi_stats *st, int k_max, double out[6]) {
   if ((rc = ctx_allreduce_host(mlmcpi_stats_ctx(st), packed.data(), packed.size())))
     return rc;
   return mlmcpi_stats_finalize(packed.data(), k_max, out);
+}
+
+// The host-side decisions of MultilevelSampler::draw and MonteCarloMultiLevel::draw_coarse_sample need
+// tau_int of a device Statistics object: pack kernel + device-to-host copy + stream synchronisation (+ an
+// all-reduce over the processes).  The reference asks for it at every sample
+// (multilevelsampler.cc:92, montecarlomultilevel.cc:176); tau_int of a running series changes slowly, so
+// the answer is reused for a number of calls that doubles from 1 up to MLMCPI_OPT_TAU_REFRESH (default 16;
+// 1 = ask every time, the reference's schedule).  Every process follows the same schedule (lockstep).
+static int stats_query_cached(mlmcpi_stats *st, int k_max, TauCache &c, double out[6]) {
+  mlmcpi_ctx *ctx = mlmcpi_stats_ctx(st);
+  if (!c.valid || c.age >= c.interval) {
+    const int rc = stats_query(st, k_max, c.st);
+    if (rc)
+      return rc;
+    c.valid = true;
+    c.age = 0;
+    c.interval = std::min(std::max(1, ctx->tau_refresh), 2 * c.interval);
+  }
+  c.age++;
+  for (int k = 0; k < 6; ++k)
+    out[k] = c.st[k];
+  return 0;
 }
 
 // Start state of a chain that is advanced by two-level Metropolis steps.  The reference starts such
@@ -1416,7 +1451,9 @@ static int multilevel_draw(mlmcpi_sampler *s) {
       return rc;
     s->t_sampler[level]++;
     double st[6];
-    if ((rc = stats_query(s->stats_sampler[level], k_max, st)))
+    if (s->tau_cache.size() != (size_t)L)
+      s->tau_cache.assign(L, TauCache());
+    if ((rc = stats_query_cached(s->stats_sampler[level], k_max, s->tau_cache[level], st)))
       return rc;
     if (s->t_sampler[level] >= std::ceil(st[3])) { // :92-106
       s->t_indep[level] =
@@ -1605,6 +1642,10 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
   }
   if (s->psi)
     cudaFree(s->psi);
+  if (s->stage_x)
+    cudaFree(s->stage_x);
+  if (s->stage_q)
+    cudaFree(s->stage_q);
   for (double *d : s->trial)
     if (d)
       cudaFree(d);
@@ -1759,6 +1800,56 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
     MLMCPI_CUDA(cudaMemcpyAsync(h_x_out, s->state[0], n * sizeof(double), cudaMemcpyDeviceToHost,
                                 ctx->stream));
   MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Sampler::draw(state) with the state handed back to the HOST, pipelined: the chains stay resident on the
+// device (as the reference's samplers keep phi_state_cur), one draw is made, the QoI of the new states is
+// evaluated, and the states are snapshot into a staging buffer whose device-to-host copy runs on a second
+// stream WHILE THE NEXT DRAW COMPUTES.  The call returns without synchronising; h_q / h_x_out of this call are
+// complete after the next call of this function or after mlmcpi_sampler_wait_host.  (The caller alternates
+// two pinned host buffers.)  Per step the device pays the draw and one device-to-device snapshot; the host
+// link pays sample_size * B * 8 bytes.
+int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, double *h_x_out) {
+  mlmcpi_ctx *ctx = s->ctx;
+  const size_t n = (size_t)mlmcpi_sample_size(&s->model[0]) * s->B;
+  int rc;
+  if (!s->copy_stream) {
+    MLMCPI_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 9; ++k)
+      MLMCPI_CUDA(cudaEventCreateWithFlags(&s->ev[k], cudaEventDisableTiming));
+  }
+  if (h_x_out && !s->stage_x && (rc = mlmcpi_alloc(ctx, n, &s->stage_x)))
+    return rc;
+  if (h_q && !s->stage_q && (rc = mlmcpi_alloc(ctx, (size_t)s->B, &s->stage_q)))
+    return rc;
+  if ((rc = mlmcpi_sampler_draw(s, nullptr, nullptr)))
+    return rc;
+  if (h_q && (rc = mlmcpi_qoi(ctx, &s->model[0], qoi, s->state[0], s->B, s->q, nullptr)))
+    return rc;
+  // the snapshot must not overwrite the staging buffers while the previous copy still reads them
+  if (s->host_copy_pending)
+    MLMCPI_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev[7], 0));
+  if (h_x_out)
+    MLMCPI_CUDA(cudaMemcpyAsync(s->stage_x, s->state[0], n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (h_q)
+    MLMCPI_CUDA(cudaMemcpyAsync(s->stage_q, s->q, sizeof(double) * s->B, cudaMemcpyDeviceToDevice, ctx->stream));
+  MLMCPI_CUDA(cudaEventRecord(s->ev[6], ctx->stream));
+  MLMCPI_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev[6], 0));
+  if (h_q)
+    MLMCPI_CUDA(cudaMemcpyAsync(h_q, s->stage_q, sizeof(double) * s->B, cudaMemcpyDeviceToHost, s->copy_stream));
+  if (h_x_out)
+    MLMCPI_CUDA(cudaMemcpyAsync(h_x_out, s->stage_x, n * sizeof(double), cudaMemcpyDeviceToHost, s->copy_stream));
+  MLMCPI_CUDA(cudaEventRecord(s->ev[7], s->copy_stream));
+  s->host_copy_pending = true;
+  return 0;
+}
+int mlmcpi_sampler_wait_host(mlmcpi_sampler *s) {
+  mlmcpi_ctx *ctx = s->ctx;
+  if (s->copy_stream)
+    MLMCPI_CUDA(cudaStreamSynchronize(s->copy_stream));
+  MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
+  s->host_copy_pending = false;
   return 0;
 }
 
@@ -1936,6 +2027,7 @@ struct mlmcpi_mlmc {
   std::vector<double> n_target;
   double *q_fine = nullptr, *q_coarse = nullptr;
   int32_t *acc = nullptr;
+  std::vector<TauCache> tau_cache; // [L-1] cached tau_int of stats_coarse (sub-sampling decisions)
 };
 
 namespace {
@@ -1952,7 +2044,9 @@ int mlmc_draw_coarse_sample(mlmcpi_mlmc *m, int level, double *state) {
   const int k_max = m->prm.n_autocorr_window;
   double st[6];
   int rc;
-  if ((rc = stats_query(m->stats_coarse[level - 1], k_max, st)))
+  if (m->tau_cache.size() != (size_t)(m->L - 1))
+    m->tau_cache.assign(m->L - 1, TauCache());
+  if ((rc = stats_query_cached(m->stats_coarse[level - 1], k_max, m->tau_cache[level - 1], st)))
     return rc;
   const double tau_int = std::ceil(2. * st[3]);
   while (m->t_sampler[level - 1] < tau_int) {
