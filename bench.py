@@ -584,7 +584,11 @@ def gpu_main(a):
         numa = bind_to_gpu_cpus(local)
         h_x = [torch.empty(B, n, dtype=torch.float64, pin_memory=True) for _ in range(2)]
         h_q = [torch.empty(B, dtype=torch.float64, pin_memory=True) for _ in range(2)]
-        for k in range(2):  # warm-up (and first touch of the pinned pages)
+        x_now = sampler.get_state()
+        for k in range(2):  # the host buffers start as the chains' states: draw() only overwrites accepted chains
+            h_x[k].copy_(x_now)
+        del x_now
+        for k in range(2):  # warm-up
             sampler.draw_host_async(QOI, h_q[k], h_x[k])
         sampler.wait_host()
         if world > 1:
@@ -608,16 +612,23 @@ def gpu_main(a):
         t_full, t_qoi = (float(v) for v in te.cpu())
         chk = float(h_q[(k_e2e - 1) & 1].mean())  # the host really holds the result
         os.sched_setaffinity(0, affinity0)  # (the cpu_baseline leg uses every core)
+        acc_all = 1.0
+        for pl in sampler.p_accept():
+            acc_all *= pl
+        d2h = int(B * n * 8 * acc_all) + B * 8
         e2e = {"value": units_per_step * world * k_e2e / t_full, "unit": UNIT,
-               "h2d_bytes_per_step": 0, "d2h_bytes_per_step": B * n * 8 + B * 8, "steps": k_e2e,
+               "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h, "steps": k_e2e,
                "ms_per_step": 1e3 * t_full / k_e2e,
-               "d2h_gbs_per_gpu": (B * n * 8 + B * 8) * k_e2e / t_full / 1e9,
+               "d2h_gbs_per_gpu": d2h * k_e2e / t_full / 1e9,
+               "d2h_note": "states of the chains whose draw was accepted (%.0f %% of %d chains x %.1f MiB; a rejected draw "
+                           "leaves the caller's state untouched, as Sampler::draw does) + the QoI of every chain"
+                           % (100 * acc_all, B, n * 8 / 2 ** 20),
                "api": "mlmcpi_sampler_draw_host_async + mlmcpi_sampler_wait_host: chains resident on the device, the new "
-                      "states of all chains [B][n] and their QoI handed back to pinned host buffers every step, the "
-                      "copy of step k overlapped with the draw of step k+1",
+                      "states of the accepted chains and the QoI of all chains handed back to pinned host buffers every "
+                      "step, the copy of step k overlapped with the draw of step k+1",
                "inputs": "none per step: a sampler's only input is its own previous state (resident) and the Philox "
                          "counters; the per-step host traffic is the OUTPUT, as in Sampler::draw(state)",
-               "limited_by": "the host link: %.1f GiB of states per step and GPU" % (B * n * 8 / 2 ** 30),
+               "limited_by": "the host link: %.2f GiB of states per step and GPU" % (B * n * 8 * acc_all / 2 ** 30),
                "qoi_only": {"value": units_per_step * world * k_e2e / t_qoi, "ms_per_step": 1e3 * t_qoi / k_e2e,
                             "d2h_bytes_per_step": B * 8,
                             "note": "same API with h_x_out = NULL: the QoI of every chain to the host each step"},

@@ -353,7 +353,9 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
 /* the same with the chains RESIDENT on the device (as Sampler keeps its phi_state_cur) and the hand-over
  * to the host pipelined: one draw, QoI of the new states, snapshot of the states, and the device-to-host
  * copies of h_q[B] / h_x_out[B][n] (either may be NULL) run on a second stream while the next draw
- * computes.  Returns without synchronising: the host buffers of this call are complete after the NEXT call
+ * computes.  As Sampler::draw(state) does, h_x_out is only overwritten for the chains whose draw was
+ * accepted (hierarchicalsampler.cc:78-80) -- initialise it with mlmcpi_sampler_get_state; with pinned
+ * (device-addressable) host memory only those rows cross the host link.  Returns without synchronising: the host buffers of this call are complete after the NEXT call
  * or after mlmcpi_sampler_wait_host -- alternate two pinned buffers.  This is the entry point bench.py's
  * `e2e` figure goes through. */
 int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, double *h_x_out);

@@ -963,6 +963,7 @@ struct mlmcpi_sampler {
   double *S_old = nullptr, *S_new = nullptr;
   cudaStream_t copy_stream = nullptr; // H2D stream of mlmcpi_sampler_draw_host, D2H stream of ..._async
   double *stage_x = nullptr, *stage_q = nullptr; // snapshots the asynchronous host copies read
+  int32_t *stage_acc = nullptr;
   bool host_copy_pending = false;
   cudaEvent_t ev[9] = {};
   int32_t *acc = nullptr, *acc_step = nullptr;          // [B]
@@ -1646,6 +1647,8 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
     cudaFree(s->stage_x);
   if (s->stage_q)
     cudaFree(s->stage_q);
+  if (s->stage_acc)
+    cudaFree(s->stage_acc);
   for (double *d : s->trial)
     if (d)
       cudaFree(d);
@@ -1805,8 +1808,9 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
 
 // Sampler::draw(state) with the state handed back to the HOST, pipelined: the chains stay resident on the
 // device (as the reference's samplers keep phi_state_cur), one draw is made, the QoI of the new states is
-// evaluated, and the states are snapshot into a staging buffer whose device-to-host copy runs on a second
-// stream WHILE THE NEXT DRAW COMPUTES.  The call returns without synchronising; h_q / h_x_out of this call are
+// evaluated, and the states of the ACCEPTED chains are snapshot into a staging buffer whose device-to-host copy
+// runs on a second stream WHILE THE NEXT DRAW COMPUTES (a rejected draw leaves the caller's buffer untouched,
+// as Sampler::draw does).  The call returns without synchronising; h_q / h_x_out of this call are
 // complete after the next call of this function or after mlmcpi_sampler_wait_host.  (The caller alternates
 // two pinned host buffers.)  Per step the device pays the draw and one device-to-device snapshot; the host
 // link pays sample_size * B * 8 bytes.
@@ -1819,8 +1823,11 @@ int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, doub
     for (int k = 0; k < 9; ++k)
       MLMCPI_CUDA(cudaEventCreateWithFlags(&s->ev[k], cudaEventDisableTiming));
   }
-  if (h_x_out && !s->stage_x && (rc = mlmcpi_alloc(ctx, n, &s->stage_x)))
-    return rc;
+  if (h_x_out && !s->stage_x) {
+    if ((rc = mlmcpi_alloc(ctx, n, &s->stage_x)))
+      return rc;
+    MLMCPI_CUDA(cudaMalloc((void **)&s->stage_acc, sizeof(int32_t) * s->B));
+  }
   if (h_q && !s->stage_q && (rc = mlmcpi_alloc(ctx, (size_t)s->B, &s->stage_q)))
     return rc;
   if ((rc = mlmcpi_sampler_draw(s, nullptr, nullptr)))
@@ -1830,16 +1837,45 @@ int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, doub
   // the snapshot must not overwrite the staging buffers while the previous copy still reads them
   if (s->host_copy_pending)
     MLMCPI_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev[7], 0));
-  if (h_x_out)
-    MLMCPI_CUDA(cudaMemcpyAsync(s->stage_x, s->state[0], n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  // pinned (device-addressable) host memory: only the accepted chains' rows are snapshot and sent
+  double *d_view = nullptr;
+  if (h_x_out) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, h_x_out) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+        attr.devicePointer && (n / s->B) % 2 == 0)
+      d_view = static_cast<double *>(attr.devicePointer);
+    cudaGetLastError();
+    if (d_view) {
+      if ((rc = launch_masked_copy(ctx, s->stage_x, s->state[0], n / s->B, s->B, s->acc)))
+        return rc;
+      MLMCPI_CUDA(cudaMemcpyAsync(s->stage_acc, s->acc, sizeof(int32_t) * s->B, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      MLMCPI_CUDA(cudaMemcpyAsync(s->stage_x, s->state[0], n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
   if (h_q)
     MLMCPI_CUDA(cudaMemcpyAsync(s->stage_q, s->q, sizeof(double) * s->B, cudaMemcpyDeviceToDevice, ctx->stream));
   MLMCPI_CUDA(cudaEventRecord(s->ev[6], ctx->stream));
   MLMCPI_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev[6], 0));
   if (h_q)
     MLMCPI_CUDA(cudaMemcpyAsync(h_q, s->stage_q, sizeof(double) * s->B, cudaMemcpyDeviceToHost, s->copy_stream));
-  if (h_x_out)
-    MLMCPI_CUDA(cudaMemcpyAsync(h_x_out, s->stage_x, n * sizeof(double), cudaMemcpyDeviceToHost, s->copy_stream));
+  if (h_x_out) {
+    // Sampler::draw(state) leaves `state` untouched when the draw is rejected (hierarchicalsampler.cc:78-80):
+    // only the ACCEPTED chains' states cross the host link.  Pinned host memory is addressable from the
+    // device, so the masked copy kernel writes the accepted rows straight into the caller's buffer
+    // (coalesced 16-byte stores over PCIe; no host round trip to learn which chains accepted).  Pageable
+    // buffers get the full copy.
+    if (d_view) {
+      const size_t n2 = n / s->B / 2;
+      const dim3 grid((unsigned)std::min<size_t>(32, (n2 + 1023) / 1024), (unsigned)std::min(s->B, 65535));
+      masked_copy_kernel<false><<<grid, 256, 0, s->copy_stream>>>(reinterpret_cast<double2 *>(d_view),
+                                                                 reinterpret_cast<const double2 *>(s->stage_x), n2,
+                                                                 s->B, s->stage_acc);
+      MLMCPI_LAUNCHED("masked_copy_to_host");
+    } else {
+      MLMCPI_CUDA(cudaMemcpyAsync(h_x_out, s->stage_x, n * sizeof(double), cudaMemcpyDeviceToHost, s->copy_stream));
+    }
+  }
   MLMCPI_CUDA(cudaEventRecord(s->ev[7], s->copy_stream));
   s->host_copy_pending = true;
   return 0;

@@ -417,6 +417,38 @@ def test_cached_cascade_equals_literal_cascade(mp, ctx):
         assert 0.0 < res[1][1][0] < 1.0 or L == 2
 
 
+def test_draw_host_async_hands_back_accepted_states(mp, ctx):
+    """mlmcpi_sampler_draw_host_async: chains resident, QoI of every chain and the states of the ACCEPTED
+    chains written to the host buffer on a second stream (pinned memory: by a masked copy kernel straight
+    over the host link; pageable memory: full copy).  A buffer initialised with the chains' states
+    therefore tracks them draw by draw, exactly like the d_x_out of mlmcpi_sampler_draw."""
+    import torch
+    m = mp.schwinger(32, 32, 9.0)
+    B = 24
+    for pinned in (True, False):
+        s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=2, nt=8, dt=0.05, renorm=mp.RENORM_PERTURBATIVE)
+        x0 = ctx.init_state(m, B, 0, 1)
+        for k in range(3):
+            ctx.heatbath_sweep(m, x0, 0, k)
+        s.set_state(x0)
+        h_x = torch.empty(B, mp.sample_size(m), dtype=torch.float64, pin_memory=pinned)
+        h_q = torch.empty(B, dtype=torch.float64, pin_memory=pinned)
+        h_x.copy_(s.get_state())
+        hx = h_x if pinned else h_x.numpy()
+        hq = h_q if pinned else h_q.numpy()
+        changed = 0
+        for d in range(8):
+            before = h_x.clone()
+            s.draw_host_async(mp.QOI_SCHWINGER_CHI, hq, hx)
+            s.wait_host()
+            now = s.get_state()
+            assert torch.equal(h_x, now.cpu()), (pinned, d)
+            assert torch.equal(h_q, ctx.qoi(m, mp.QOI_SCHWINGER_CHI, now).cpu())
+            changed += int((h_x != before).any(dim=1).sum())
+        assert 0 < changed < 8 * B  # accepted and rejected draws both occurred
+        s.close()
+
+
 def test_ho_exact_sampler(mp, ctx, orc):
     """HarmonicOscillatorAction::draw (Cholesky sampler): draw by draw against the oracle, and as the
     coarse sampler of a hierarchy (sampler = 'exact' of hierarchicalsampler.hh)"""
