@@ -6,12 +6,13 @@ set -e
 N=$1
 shift
 F=$(mktemp -u /tmp/mlmcpi_comm.XXXXXX)
+NONCE=$(( ($$ << 16) ^ RANDOM ^ $(date +%s) ))   # readers ignore a rendezvous file that is not this run's
+trap 'rm -f "$F" "$F.tmp"' EXIT INT TERM
 pids=()
 for r in $(seq 0 $((N - 1))); do
-  MLMCPI_RANK=$r MLMCPI_WORLD_SIZE=$N MLMCPI_COMM_FILE=$F "$@" &
+  MLMCPI_RANK=$r MLMCPI_WORLD_SIZE=$N MLMCPI_COMM_FILE=$F MLMCPI_COMM_NONCE=$NONCE "$@" &
   pids+=($!)
 done
 rc=0
 for p in "${pids[@]}"; do wait $p || rc=$?; done
-rm -f "$F"
 exit $rc

@@ -96,14 +96,32 @@ void prof_end(mlmcpi_ctx *ctx, uint64_t launches, double algorithmic_bytes) {
   ctx->prof_bytes += algorithmic_bytes;
 }
 
+// Every entry point runs on the device of its context, whatever device is current in the calling thread,
+// and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const mlmcpi_ctx *ctx) {
+    if (ctx && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device)
+      cudaSetDevice(ctx->device);
+    else
+      prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0)
+      cudaSetDevice(prev);
+  }
+};
+
 extern "C" {
 
 int mlmcpi_profile(mlmcpi_ctx *ctx, int enable) {
+  DeviceGuard device_guard(ctx);
   ctx->profile = enable != 0;
   return 0;
 }
 
 int mlmcpi_profile_read(mlmcpi_ctx *ctx, double out[3]) {
+  DeviceGuard device_guard(ctx);
   MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
   for (size_t k = 0; k + 1 < ctx->prof_events.size(); k += 2) {
     float ms = 0.f;
@@ -138,6 +156,7 @@ int mlmcpi_create(mlmcpi_ctx **out, int device, uint64_t seed, void *stream) {
     return MLMCPI_ENOMEM;
   ctx->device = device;
   ctx->seed = seed;
+  DeviceGuard device_guard(ctx); // (the caller's current device is restored on return)
   if (cudaSetDevice(device) != cudaSuccess) {
     delete ctx;
     return MLMCPI_ECUDA;
@@ -159,6 +178,7 @@ int mlmcpi_create(mlmcpi_ctx **out, int device, uint64_t seed, void *stream) {
 }
 
 void mlmcpi_destroy(mlmcpi_ctx *ctx) {
+  DeviceGuard device_guard(ctx);
   if (!ctx)
     return;
   cudaSetDevice(ctx->device);
@@ -184,10 +204,12 @@ int mlmcpi_device(const mlmcpi_ctx *ctx) { return ctx ? ctx->device : -1; }
 void *mlmcpi_stream(const mlmcpi_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int mlmcpi_sync(mlmcpi_ctx *ctx) {
+  DeviceGuard device_guard(ctx);
   MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
+  DeviceGuard device_guard(ctx);
   if (option == MLMCPI_OPT_EXPCOS_ENVELOPE && value >= 0 && value <= 2) {
     ctx->expcos_envelope = value;
     return 0;
@@ -231,10 +253,12 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
   return ctx_fail(ctx, MLMCPI_EINVAL, "unknown option or value");
 }
 int mlmcpi_set_seed(mlmcpi_ctx *ctx, uint64_t seed) {
+  DeviceGuard device_guard(ctx);
   ctx->seed = seed;
   return 0;
 }
 int mlmcpi_set_allreduce(mlmcpi_ctx *ctx, mlmcpi_allreduce_fn fn, void *user, int world_size, int rank) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || world_size < 1 || rank < 0 || rank >= world_size)
     return ctx ? ctx_fail(ctx, MLMCPI_EINVAL, "bad world size / rank") : MLMCPI_EINVAL;
   ctx->allreduce = fn;
@@ -249,6 +273,7 @@ uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx) { return ctx->launches; }
 
 // =================================================================== memory
 int mlmcpi_alloc(mlmcpi_ctx *ctx, size_t n, double **d_ptr) {
+  DeviceGuard device_guard(ctx);
   if (!d_ptr)
     return ctx_fail(ctx, MLMCPI_EINVAL, "null output pointer");
   *d_ptr = nullptr;
@@ -262,20 +287,24 @@ int mlmcpi_alloc(mlmcpi_ctx *ctx, size_t n, double **d_ptr) {
   return 0;
 }
 int mlmcpi_free(mlmcpi_ctx *ctx, double *d_ptr) {
+  DeviceGuard device_guard(ctx);
   if (d_ptr)
     MLMCPI_CUDA(cudaFree(d_ptr));
   return 0;
 }
 int mlmcpi_upload(mlmcpi_ctx *ctx, double *d_dst, const double *h_src, size_t n) {
+  DeviceGuard device_guard(ctx);
   MLMCPI_CUDA(cudaMemcpyAsync(d_dst, h_src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 int mlmcpi_download(mlmcpi_ctx *ctx, double *h_dst, const double *d_src, size_t n) {
+  DeviceGuard device_guard(ctx);
   MLMCPI_CUDA(cudaMemcpyAsync(h_dst, d_src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 int mlmcpi_copy(mlmcpi_ctx *ctx, double *d_dst, const double *d_src, size_t n) {
+  DeviceGuard device_guard(ctx);
   MLMCPI_CUDA(cudaMemcpyAsync(d_dst, d_src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
@@ -286,6 +315,7 @@ __global__ void axpy_kernel(double *out, const double *a, double alpha, const do
     out[k] = a[k] + alpha * b[k];
 }
 int mlmcpi_axpy(mlmcpi_ctx *ctx, double *d_out, const double *d_a, double alpha, const double *d_b, size_t n) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !d_out || !d_a || !d_b)
     return MLMCPI_EINVAL;
   if (n == 0)
@@ -778,34 +808,42 @@ extern "C" {
 
 int mlmcpi_init_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0,
                       uint64_t draw) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, init_state, ctx, m, d_x, B, chain0, draw);
 }
 int mlmcpi_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_x, int B, double *d_S) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, action, ctx, m, d_x, B, d_S);
 }
 int mlmcpi_force(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_x, double *d_f, int B) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, force, ctx, m, d_x, d_f, B);
 }
 int mlmcpi_leapfrog(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *d_x,
                     double *d_p, int B) {
+  DeviceGuard device_guard(ctx);
   if (nt < 0)
     return ctx_fail(ctx, MLMCPI_EINVAL, "nt must be non-negative");
   DISPATCH(m, leapfrog, ctx, m, nt, dt, d_x, d_p, B);
 }
 int mlmcpi_hmc_momentum(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_p, int B, uint32_t chain0,
                         uint64_t draw) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, hmc_momentum, ctx, m, d_p, B, chain0, draw);
 }
 int mlmcpi_hmc_step(mlmcpi_ctx *ctx, const mlmcpi_model *m, int nt, double dt, double *d_x, int B,
                     uint32_t chain0, uint64_t draw, int32_t *d_accept, double *d_diag) {
+  DeviceGuard device_guard(ctx);
   if (nt < 0)
     return ctx_fail(ctx, MLMCPI_EINVAL, "nt must be non-negative");
   DISPATCH(m, hmc_step, ctx, m, nt, dt, d_x, B, chain0, draw, d_accept, d_diag);
 }
 int mlmcpi_overrelax_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, overrelax_sweep, ctx, m, d_x, B);
 }
 int mlmcpi_overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, int n_sweeps) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !m || B <= 0 || n_sweeps < 0)
     return MLMCPI_EINVAL;
   if (m->model == MLMCPI_SCHWINGER && m->Mt_lat >= 2 && m->Mx_lat >= 2 && m->Mt_lat % 2 == 0 &&
@@ -822,45 +860,56 @@ int mlmcpi_overrelax_sweeps(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x,
 }
 int mlmcpi_heatbath_sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B,
                           uint32_t chain0, uint64_t draw) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, heatbath_sweep, ctx, m, d_x, B, chain0, draw);
 }
 int mlmcpi_dof_update(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, int ell, int heatbath,
                       uint32_t chain0, uint64_t draw) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, dof_update, ctx, m, d_x, B, ell, heatbath, chain0, draw);
 }
 int mlmcpi_prolong(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_xc, double *d_x, int B) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, prolong, ctx, m, d_xc, d_x, B);
 }
 int mlmcpi_restrict(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_xf, double *d_xc, int B) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, restrict_, ctx, m, d_xf, d_xc, B);
 }
 int mlmcpi_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0,
                 uint64_t draw) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, fill, ctx, m, d_x, B, chain0, draw);
 }
 int mlmcpi_prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_xc, double *d_x,
                         int B, uint32_t chain0, uint64_t draw) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, prolong_fill, ctx, m, d_xc, d_x, B, chain0, draw);
 }
 int mlmcpi_prolong_fill_eval(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_xc, double *d_x,
                              int B, uint32_t chain0, uint64_t draw, double *d_S) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, prolong_fill_eval, ctx, m, d_xc, d_x, B, chain0, draw, d_S);
 }
 int mlmcpi_cond_action(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_x, int B, double *d_S) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, cond_action, ctx, m, d_x, B, d_S);
 }
 int mlmcpi_qoi(mlmcpi_ctx *ctx, const mlmcpi_model *m, int qoi, const double *d_x, int B, double *d_q,
                int64_t *d_Qint) {
+  DeviceGuard device_guard(ctx);
   DISPATCH(m, qoi, ctx, m, qoi, d_x, B, d_q, d_Qint);
 }
 
 int mlmcpi_cluster_update(mlmcpi_ctx *ctx, const mlmcpi_model *rotor, double *d_x, int B, uint32_t chain0,
                           uint64_t update0, int n_updates) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !rotor || B <= 0 || n_updates < 0)
     return MLMCPI_EINVAL;
   return qm::cluster_update(ctx, rotor, d_x, B, chain0, update0, n_updates);
 }
 int mlmcpi_exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0, uint64_t draw) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !m || !d_x || B <= 0)
     return MLMCPI_EINVAL;
   if (m->model == MLMCPI_GFF)
@@ -872,6 +921,7 @@ int mlmcpi_exact_draw(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B
 }
 int mlmcpi_schwinger_from_cluster(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *d_psi, double *d_x,
                                   int B, uint32_t chain0, uint64_t draw) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !m || B <= 0 || m->model != MLMCPI_SCHWINGER)
     return MLMCPI_EINVAL;
   return schwinger::from_cluster(ctx, m, d_psi, d_x, B, chain0, draw);
@@ -879,6 +929,7 @@ int mlmcpi_schwinger_from_cluster(mlmcpi_ctx *ctx, const mlmcpi_model *m, const 
 
 static int thermal_start(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chain0);
 int mlmcpi_thermal_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, int B, uint32_t chain0) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !m || !d_x || B <= 0)
     return MLMCPI_EINVAL;
   return thermal_start(ctx, m, d_x, B, chain0);
@@ -886,6 +937,7 @@ int mlmcpi_thermal_state(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *d_x, in
 int mlmcpi_twolevel_step(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_model *coarse,
                          const double *d_xc, double *d_xf, double *d_Sf, double *d_Scond, int B,
                          uint32_t chain0, uint64_t draw, int32_t *d_accept, double *d_deltas) {
+  DeviceGuard device_guard(ctx);
   return twolevel_step_impl(ctx, fine, coarse, d_xc, d_xf, d_Sf, d_Scond, B, chain0, draw, nullptr,
                             d_accept, d_deltas);
 }
@@ -1480,6 +1532,7 @@ extern "C" {
 
 int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_sampler_params *prm,
                           int B, uint32_t chain0, mlmcpi_sampler **out) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !fine || !prm || !out || B <= 0)
     return MLMCPI_EINVAL;
   *out = nullptr;
@@ -1632,6 +1685,7 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
 }
 
 void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   if (!s)
     return;
   cudaStreamSynchronize(s->ctx->stream);
@@ -1691,6 +1745,7 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
 }
 
 int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   // MultilevelSampler::set_state only overwrites the output buffer that the next draw
   // overwrites again (multilevelsampler.cc:115-117): the chains are unaffected
   if (s->prm.multilevel)
@@ -1702,12 +1757,14 @@ int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x) {
 
 // the current state of every chain (what the sampler classes keep in phi_state_cur / phi_sampler_state[0])
 int mlmcpi_sampler_get_state(mlmcpi_sampler *s, double *d_x) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   if (!s || !d_x)
     return MLMCPI_EINVAL;
   return mlmcpi_copy(s->ctx, d_x, s->state[0], (size_t)mlmcpi_sample_size(&s->model[0]) * s->B);
 }
 
 int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   mlmcpi_ctx *ctx = s->ctx;
   const int B = s->B;
   int rc;
@@ -1754,6 +1811,7 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
 // range instead of copy + compute.
 int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, double *h_q,
                              double *h_x_out) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   mlmcpi_ctx *ctx = s->ctx;
   const size_t nd = (size_t)mlmcpi_sample_size(&s->model[0]);
   const size_t n = nd * s->B;
@@ -1815,6 +1873,7 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
 // two pinned host buffers.)  Per step the device pays the draw and one device-to-device snapshot; the host
 // link pays sample_size * B * 8 bytes.
 int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, double *h_x_out) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   mlmcpi_ctx *ctx = s->ctx;
   const size_t n = (size_t)mlmcpi_sample_size(&s->model[0]) * s->B;
   int rc;
@@ -1881,6 +1940,7 @@ int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, doub
   return 0;
 }
 int mlmcpi_sampler_wait_host(mlmcpi_sampler *s) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   mlmcpi_ctx *ctx = s->ctx;
   if (s->copy_stream)
     MLMCPI_CUDA(cudaStreamSynchronize(s->copy_stream));
@@ -1890,6 +1950,7 @@ int mlmcpi_sampler_wait_host(mlmcpi_sampler *s) {
 }
 
 int mlmcpi_sampler_level_model(const mlmcpi_sampler *s, int level, mlmcpi_model *m) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   if (!s || !m || level < 0 || level >= s->L)
     return MLMCPI_EINVAL;
   *m = s->model[level];
@@ -1897,6 +1958,7 @@ int mlmcpi_sampler_level_model(const mlmcpi_sampler *s, int level, mlmcpi_model 
 }
 
 int mlmcpi_sampler_stats(mlmcpi_sampler *s, double *h_p_accept) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   mlmcpi_ctx *ctx = s->ctx;
   std::vector<unsigned long long> c(s->L);
   MLMCPI_CUDA(cudaMemcpyAsync(c.data(), s->counters, sizeof(unsigned long long) * s->L,
@@ -1922,6 +1984,7 @@ int mlmcpi_sampler_stats(mlmcpi_sampler *s, double *h_p_accept) {
 
 // MCMCStep::reset_stats (montecarlo/mcmcstep.hh) for every level of the sampler
 int mlmcpi_sampler_reset_stats(mlmcpi_sampler *s) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   mlmcpi_ctx *ctx = s->ctx;
   MLMCPI_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->L, ctx->stream));
   s->n_draws = 0;
@@ -1931,6 +1994,7 @@ int mlmcpi_sampler_reset_stats(mlmcpi_sampler *s) {
 }
 
 int mlmcpi_sampler_work(const mlmcpi_sampler *s, double out[3]) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   out[0] = s->work[0];
   out[1] = s->work[1];
   out[2] = s->work[2];
@@ -1944,6 +2008,7 @@ int mlmcpi_sampler_work(const mlmcpi_sampler *s, double out[3]) {
 // unchanged if no round came within 1e-2 of the target.
 int mlmcpi_sampler_autotune(mlmcpi_sampler *s, double p_accept_target, int n_rounds, int n_samples,
                             double *dt_out, double *p_accept_out) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   mlmcpi_ctx *ctx = s->ctx;
   if (s->prm.kind != MLMCPI_SAMPLER_HMC)
     return ctx_fail(ctx, MLMCPI_EINVAL, "autotune is defined for the HMC sampler");
@@ -2002,6 +2067,7 @@ int mlmcpi_sampler_autotune(mlmcpi_sampler *s, double p_accept_target, int n_rou
 }
 
 int mlmcpi_sampler_set_dt(mlmcpi_sampler *s, double dt) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   s->prm.dt = dt;
   return 0;
 }
@@ -2012,6 +2078,7 @@ int mlmcpi_sampler_set_dt(mlmcpi_sampler *s, double dt) {
 extern "C" {
 
 int mlmcpi_sampler_cost(mlmcpi_sampler *s, int n_meas, double *usec_per_sample) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   mlmcpi_ctx *ctx = s->ctx;
   if (n_meas < 1 || !usec_per_sample)
     return ctx_fail(ctx, MLMCPI_EINVAL, "bad arguments");
@@ -2035,6 +2102,7 @@ int mlmcpi_sampler_cost(mlmcpi_sampler *s, int n_meas, double *usec_per_sample) 
 }
 
 int mlmcpi_sampler_indep(const mlmcpi_sampler *s, double *out) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
   if (!s->prm.multilevel)
     return MLMCPI_EINVAL;
   for (int l = 0; l < s->L; ++l) {
@@ -2157,6 +2225,7 @@ int mlmc_cost_eff(mlmcpi_mlmc *m, int ell, double *cost_out) {
 extern "C" {
 
 void mlmcpi_mlmc_destroy(mlmcpi_mlmc *m) {
+  DeviceGuard device_guard(m ? m->ctx : nullptr);
   if (!m)
     return;
   cudaStreamSynchronize(m->ctx->stream);
@@ -2182,6 +2251,7 @@ void mlmcpi_mlmc_destroy(mlmcpi_mlmc *m) {
 // MonteCarloMultiLevel constructor, montecarlomultilevel.cc:7-68
 int mlmcpi_mlmc_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_mlmc_params *prm, int B,
                        uint32_t chain0, mlmcpi_mlmc **out) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !fine || !prm || !out || B <= 0)
     return MLMCPI_EINVAL;
   *out = nullptr;
@@ -2309,6 +2379,7 @@ int mlmcpi_mlmc_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_m
 
 // MonteCarloMultiLevel::evaluate, montecarlomultilevel.cc:71-167
 int mlmcpi_mlmc_evaluate(mlmcpi_mlmc *m) {
+  DeviceGuard device_guard(m ? m->ctx : nullptr);
   mlmcpi_ctx *ctx = m->ctx;
   const int L = m->L, B = m->B, k_max = m->prm.n_autocorr_window;
   int rc;
@@ -2398,6 +2469,7 @@ int mlmcpi_mlmc_evaluate(mlmcpi_mlmc *m) {
 }
 
 int mlmcpi_mlmc_result(mlmcpi_mlmc *m, double *value, double *error, double *level_out) {
+  DeviceGuard device_guard(m ? m->ctx : nullptr);
   double v = 0.0, e2 = 0.0;
   for (int l = 0; l < m->L; ++l) {
     double st[6], cost = 0.0;
@@ -2489,6 +2561,7 @@ __global__ void stats_pack_kernel(int B, const double *acc, double *packed) {
 extern "C" {
 
 int mlmcpi_stats_create(mlmcpi_ctx *ctx, int k_max, int B, mlmcpi_stats **out) {
+  DeviceGuard device_guard(ctx);
   if (!ctx || !out || k_max < 1 || B < 1)
     return MLMCPI_EINVAL;
   mlmcpi_stats *st = new (std::nothrow) mlmcpi_stats;
@@ -2507,6 +2580,7 @@ int mlmcpi_stats_create(mlmcpi_ctx *ctx, int k_max, int B, mlmcpi_stats **out) {
 }
 
 void mlmcpi_stats_destroy(mlmcpi_stats *st) {
+  DeviceGuard device_guard(st ? mlmcpi_stats_ctx(st) : nullptr);
   if (!st)
     return;
   cudaStreamSynchronize(st->ctx->stream);
@@ -2532,6 +2606,7 @@ int mlmcpi_stats_reset(mlmcpi_stats *st) { // Statistics::reset, statistics.hh:1
 }
 
 int mlmcpi_stats_record(mlmcpi_stats *st, const double *d_q) {
+  DeviceGuard device_guard(st ? mlmcpi_stats_ctx(st) : nullptr);
   mlmcpi_ctx *ctx = st->ctx;
   st->n_samples++;
   st->n_samples_longterm++;
@@ -2550,6 +2625,7 @@ static void stats_head(const mlmcpi_stats *st, double head[3]) {
 }
 
 int mlmcpi_stats_pack_device(mlmcpi_stats *st, double *d_packed) {
+  DeviceGuard device_guard(st ? mlmcpi_stats_ctx(st) : nullptr);
   mlmcpi_ctx *ctx = st->ctx;
   stats_pack_kernel<<<5 + st->k_max, 256, 0, ctx->stream>>>(st->B, st->acc, d_packed + 3);
   MLMCPI_LAUNCHED("stats_pack");
@@ -2561,6 +2637,7 @@ int mlmcpi_stats_pack_device(mlmcpi_stats *st, double *d_packed) {
 }
 
 int mlmcpi_stats_pack(mlmcpi_stats *st, double *h_packed) {
+  DeviceGuard device_guard(st ? mlmcpi_stats_ctx(st) : nullptr);
   mlmcpi_ctx *ctx = st->ctx;
   stats_pack_kernel<<<5 + st->k_max, 256, 0, ctx->stream>>>(st->B, st->acc, st->packed);
   MLMCPI_LAUNCHED("stats_pack");

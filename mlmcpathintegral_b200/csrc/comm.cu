@@ -4,6 +4,7 @@
 #include <nccl.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -66,25 +67,36 @@ int mlmcpi_comm_create_from_env(mlmcpi_ctx *ctx, mlmcpi_comm **out) {
     return mlmcpi_comm_create(ctx, 0, 1, nullptr, out);
   if (!f)
     return MLMCPI_EINVAL;
+  // Rendezvous file = 8-byte run nonce (MLMCPI_COMM_NONCE, set by the launcher) + the NCCL unique id.
+  // Rank 0 removes whatever a killed run left under the path before it publishes (atomically, by rename);
+  // the other ranks ignore a file whose nonce is not this run's, so a stale id can never reach
+  // ncclCommInitRank, and they give up after MLMCPI_COMM_TIMEOUT_S seconds (default 120).
   char id[MLMCPI_COMM_ID_BYTES];
   const std::string path(f), tmp = path + ".tmp";
+  const char *nv = std::getenv("MLMCPI_COMM_NONCE"), *tv = std::getenv("MLMCPI_COMM_TIMEOUT_S");
+  const unsigned long long nonce = nv ? std::strtoull(nv, nullptr, 10) : 0ull;
+  const int timeout_s = tv ? std::max(1, std::atoi(tv)) : 120;
   if (rank == 0) {
     int rc = mlmcpi_comm_unique_id(id);
     if (rc)
       return rc;
+    std::remove(path.c_str());
     FILE *fp = std::fopen(tmp.c_str(), "wb");
     if (!fp)
       return MLMCPI_EINVAL;
+    std::fwrite(&nonce, 1, sizeof(nonce), fp);
     std::fwrite(id, 1, sizeof(id), fp);
     std::fclose(fp);
     if (std::rename(tmp.c_str(), path.c_str()) != 0) // atomic publish
       return MLMCPI_EINVAL;
   } else {
     bool ok = false;
-    for (int tries = 0; tries < 6000 && !ok; ++tries) { // up to 10 minutes
+    for (int tries = 0; tries < 10 * timeout_s && !ok; ++tries) {
       FILE *fp = std::fopen(path.c_str(), "rb");
       if (fp) {
-        ok = std::fread(id, 1, sizeof(id), fp) == sizeof(id);
+        unsigned long long got = 0;
+        ok = std::fread(&got, 1, sizeof(got), fp) == sizeof(got) && got == nonce &&
+             std::fread(id, 1, sizeof(id), fp) == sizeof(id);
         std::fclose(fp);
       }
       if (!ok)
