@@ -53,6 +53,14 @@ enum { MLMCPI_RENORM_NONE = 0, MLMCPI_RENORM_PERTURBATIVE = 1,
  * qoi/qft/qoiavgplaquette.hh, qoi/qft/qoi2dphisquared.hh */
 enum { MLMCPI_QOI_X2 = 0, MLMCPI_QOI_ROTOR_CHI = 1, MLMCPI_QOI_SCHWINGER_CHI = 2,
        MLMCPI_QOI_AVG_PLAQUETTE = 3, MLMCPI_QOI_PHI2 = 4 };
+/* Philox4x32-10 streams: counter = (index, global chain, draw, stream << 24 | call), key = (seed, draw_hi).
+ * Variate-to-degree-of-freedom maps that are not one stream per dof:
+ *   FILL3, coarsening both: the two horizontal interior links (2i, 2j+1, 0), (2i+1, 2j+1, 0) of a coarse cell take
+ *     the first attempts of their ExpCos draws from ONE normal pair and ONE uniform pair -- calls 0, 1 of the
+ *     stream with index Mt j + 2i: (z0, u0) and (z1, u1); further attempts continue on the link's own stream
+ *     (index Mt j + 2i from call 2, index Mt j + 2i + 1 from call 0);
+ *   CLUSTER: index 0 = (reflection angle, start site) of an update, index 1 + k = (forward, backward) uniform of
+ *     the link between the sites k and k + 1. */
 enum { MLMCPI_STREAM_INIT = 1, MLMCPI_STREAM_HMC_MOMENTUM = 2, MLMCPI_STREAM_HMC_ACCEPT = 3,
        MLMCPI_STREAM_HEATBATH = 4, MLMCPI_STREAM_FILL1 = 5, MLMCPI_STREAM_FILL2 = 6,
        MLMCPI_STREAM_FILL3 = 7, MLMCPI_STREAM_TWOLEVEL_ACCEPT = 8, MLMCPI_STREAM_CLUSTER = 9,

@@ -95,7 +95,15 @@ struct Rng {
   uint32_t c0, c1, c2, a, k0, k1;
 };
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+// MLMCPI_PHILOX_NOINLINE (set per translation unit): one shared copy of the ten rounds instead of one per call
+// site.  The Schwinger fill-in kernels run through ~2500 of their 4096 instructions ONCE per thread and stall on
+// instruction fetch ("no_instructions" is their top stall reason); a called Philox shrinks the footprint.
+#ifdef MLMCPI_PHILOX_NOINLINE
+#define MLMCPI_PHILOX_INLINE __noinline__
+#else
+#define MLMCPI_PHILOX_INLINE __forceinline__
+#endif
+__device__ MLMCPI_PHILOX_INLINE void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t out[4]) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -340,7 +348,13 @@ __device__ __forceinline__ double expsin2_pdf(const double x, const double sigma
 //                  u <= 1 - tau delta x^2 / 2 <= exp(log acceptance) accepts most proposals
 //                  without evaluating cos or exp.
 #define EXPCOS_TIGHT_TAU 64.0
-__device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, const int envelope) {
+// have_first: the first Gaussian attempt uses the variates (z_first, u_first) handed in by the caller instead of
+// a block of the stream r -- the fused fill-in draws ONE normal pair and ONE uniform pair per coarse cell and gives
+// a half of each to its two horizontal links, whose further attempts (rare: 0.3 % at tau = 2048) continue on
+// their own streams.  Without it the sequence of attempts is (z0, u0), (z1, u1) of block 0, then block 1, ...
+__device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, const int envelope,
+                                                   const bool have_first = false, const double z_first = 0.0,
+                                                   const double u_first = 0.0) {
   double x = 0.0;
   bool accepted = false;
   if (envelope >= 1 && tau < 0.5) {
@@ -372,21 +386,30 @@ __device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, con
     q = tau * (envelope >= 1 ? 2. / (M_PI * M_PI) : 1. / (4. * M_PI * M_PI));
     sq = 0.0;
   }
-  while (!accepted) {
-    double z0, z1, u0, u1;
-    rng_normal2(r, z0, z1);
-    rng_uniform2(r, u0, u1);
+  double z0 = 0.0, z1 = 0.0, u0 = 0.0, u1 = 0.0;
+  int t = have_first ? -1 : 0; // attempt counter: -1 = the caller's variates, then (z0,u0), (z1,u1) of block t / 2
 #pragma unroll 1
-    for (int t = 0; t < 2 && !accepted; ++t) {
-      x = sigma * (t == 0 ? z0 : z1);
-      const double u = (t == 0 ? u0 : u1);
-      const double x2 = x * x;
-      const bool inside = tight ? (tau * x2 <= 160.) : ((-M_PI <= x) && (x < M_PI)); // x^2 <= 160 / tau
-      if (inside) {
-        accepted = tight && (u <= 1. - sq * x2);
-        if (!accepted)
-          accepted = (u <= exp(tau * (cos(x) - 1.) + q * x2));
+  while (!accepted) {
+    double z, u;
+    if (t < 0) {
+      z = z_first;
+      u = u_first;
+    } else {
+      if ((t & 1) == 0) {
+        rng_normal2(r, z0, z1);
+        rng_uniform2(r, u0, u1);
       }
+      z = (t & 1) ? z1 : z0;
+      u = (t & 1) ? u1 : u0;
+    }
+    ++t;
+    x = sigma * z;
+    const double x2 = x * x;
+    const bool inside = tight ? (tau * x2 <= 160.) : ((-M_PI <= x) && (x < M_PI)); // x^2 <= 160 / tau
+    if (inside) {
+      accepted = tight && (u <= 1. - sq * x2);
+      if (!accepted)
+        accepted = (u <= exp(tau * (cos(x) - 1.) + q * x2));
     }
   }
   return x;
@@ -400,10 +423,11 @@ struct ExpCosDrawn {
 };
 __device__ __forceinline__ double expcos_draw(Rng &r, const double beta, const double x_p,
                                               const double x_m, const int envelope,
-                                              ExpCosDrawn *info = nullptr) {
+                                              ExpCosDrawn *info = nullptr, const bool have_first = false,
+                                              const double z_first = 0.0, const double u_first = 0.0) {
   const double dx = x_m - x_p;
   const double tau = 2. * beta * fabs(cos(0.5 * dx));
-  const double x = expcos_draw_core(r, tau, envelope);
+  const double x = expcos_draw_core(r, tau, envelope, have_first, z_first, u_first);
   if (info) {
     info->x = x;
     info->tau = tau;

@@ -1048,7 +1048,20 @@ __device__ __forceinline__ double cell_plaquette_sum(const CellLinks &c) {
 //   (1 - cos P) + (1 - cos P') of the two plaquettes it separates = 2 - (tau / beta) cos x
 // and the mixture pdf of the vertical pair is evaluated at w (approxbessel_pdf_w); these are the
 // reference's formulas with the angle differences taken before the final mod_2pi rounding.
-template <bool APPROX, bool EVAL>
+// threads per block of the fused fill-in kernel, measured at 512 chains x 512^2 <- 256^2, beta = 1024:
+// 64: 3.81, 128: 3.70, 256: 3.53, 512: 3.57 ms (256 with 4 resident blocks)
+#ifndef FILL_THREADS
+#define FILL_THREADS 256
+#endif
+#ifndef FILL_PHASE_SYNC
+#define FILL_PHASE_SYNC 0
+#endif
+// PHASE_SYNC: block-wide barriers between the phases of the draw.  They order nothing -- the phases of a cell
+// only touch the cell's registers -- but keep the warps of a block in the same stretch of the instruction
+// stream (the fused kernel's threads run through 2500 of its 4500 instructions once and "no_instructions" is
+// its top stall reason).  Measured: no gain (3.54 ms with and without); off.  Neither did a called
+// (non-inlined) Philox help: 4.29 ms.
+template <bool APPROX, bool EVAL, bool PHASE_SYNC = false>
 __device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double beta,
                                                    const int envelope,
                                                    const BesselProductConst &bp, uint64_t seed,
@@ -1070,20 +1083,35 @@ __device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double be
     const double theta_tilde = APPROX ? approxbessel_draw(r, beta, theta_p, theta_m, u1, EVAL ? &ad : nullptr)
                                       : besselproduct_draw(r, bp, theta_p, theta_m);
     __syncwarp(wmask);
+    if (PHASE_SYNC)
+      __syncthreads();
     c.V0 = mod_2pi_fast(0.5 * theta_tilde + dtheta);
     c.V1 = mod_2pi_fast(0.5 * theta_tilde - dtheta);
   }
   // STEP 3 for the two horizontal interior links (2i, 2j+1, 0) and (2i+1, 2j+1, 0); a rolled
   // loop, so that the rejection sampler exists once in the instruction stream
+  // ONE normal pair and ONE uniform pair (calls 0, 1 of the stream of link (2i, 2j+1, 0)) serve the first attempt
+  // of BOTH links: (z0, u0) for h = 0, (z1, u1) for h = 1; further attempts continue on the link's own stream
+  // (h = 0: calls 2, 3, ...; h = 1: the stream of link (2i+1, 2j+1, 0) from call 0).  Two Philox calls and one
+  // Box-Muller transform fewer per cell than a block per link (15 % of the kernel's instructions).
   double Zprod = 1.0, tsum = 0.0, tcos = 0.0;
+  Rng r0 = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i);
+  double zs0, zs1, us0, us1;
+  rng_normal2(r0, zs0, zs1);
+  rng_uniform2(r0, us0, us1);
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     const double theta_p = mod_2pi_fast(h == 0 ? c.A0 + c.V0 - c.B0 : c.A1 + c.R0 - c.V0);
     const double theta_m = mod_2pi_fast(h == 0 ? c.B1 + c.T0 - c.V1 : c.V1 + c.T1 - c.R1);
-    Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i + h);
+    Rng r = r0;
+    if (h == 1)
+      r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i + 1);
     ExpCosDrawn e;
-    const double H = expcos_draw(r, beta, theta_p, theta_m, envelope, &e);
+    const double H = expcos_draw(r, beta, theta_p, theta_m, envelope, &e, true, h == 0 ? zs0 : zs1,
+                                 h == 0 ? us0 : us1);
     __syncwarp(wmask);
+    if (PHASE_SYNC)
+      __syncthreads();
     if (h == 0)
       c.H0 = H;
     else
@@ -1147,18 +1175,22 @@ __global__ void fill_both_step23_kernel(SW sw, BesselProductConst bp, double *x_
 // and third pass over theta').  Grid: nblk blocks of 128 cells per chain.
 template <bool APPROX, bool EVAL>
 #ifndef FILL_MINBLK
-#define FILL_MINBLK 8
+#define FILL_MINBLK (1024 / FILL_THREADS)
 #endif
-__global__ void __launch_bounds__(128, FILL_MINBLK) prolong_fill_both_kernel(SW sw, BesselProductConst bp, const double *xc_all,
+__global__ void __launch_bounds__(FILL_THREADS, FILL_MINBLK) prolong_fill_both_kernel(SW sw, BesselProductConst bp, const double *xc_all,
                                          double *x_all, int B, uint32_t chain0, uint64_t seed,
                                          uint64_t draw, int nblk, double *partial) {
   const int Mt = sw.Mt, Mx = sw.Mx, Mtc = Mt / 2, Mxc = Mx / 2;
   const int nc = Mtc * Mxc;
   const int chain = blockIdx.x / nblk, blk = blockIdx.x - chain * nblk;
-  const int cell = blk * blockDim.x + threadIdx.x;
+  const int cell_raw = blk * blockDim.x + threadIdx.x;
+  // (threads beyond the last cell of the chain redo the last cell and store nothing, so that every thread of
+  // the block passes the same barriers)
+  const bool live = cell_raw < nc;
+  const int cell = live ? cell_raw : nc - 1;
   double sf = 0.0, sc = 0.0;
-  const unsigned wmask = __ballot_sync(0xffffffffu, cell < nc);
-  if (cell < nc) {
+  const unsigned wmask = 0xffffffffu;
+  {
     const int j = cell / Mtc, i = cell - j * Mtc;
     const uint32_t gchain = chain0 + (uint32_t)chain;
     const double2 *xc = reinterpret_cast<const double2 *>(xc_all) + (size_t)chain * nc;
@@ -1191,13 +1223,20 @@ __global__ void __launch_bounds__(128, FILL_MINBLK) prolong_fill_both_kernel(SW 
       c.T0 = mod_2pi_fast(0.5 * ct + dth_t);
       c.T1 = mod_2pi_fast(0.5 * ct - dth_t);
     }
-    fill_cell_interior<APPROX, EVAL>(c, sw.beta, sw.envelope, bp, seed, draw, gchain, Mt, i, j, cell, sf, sc, wmask);
-    // rows 2j and 2j+1, sites 2i and 2i+1: four aligned double2 stores
-    double2 *xs = reinterpret_cast<double2 *>(x);
-    xs[(size_t)Mt * (2 * j) + 2 * i] = make_double2(c.A0, c.B0);
-    xs[(size_t)Mt * (2 * j) + 2 * i + 1] = make_double2(c.A1, c.V0);
-    xs[(size_t)Mt * (2 * j + 1) + 2 * i] = make_double2(c.H0, c.B1);
-    xs[(size_t)Mt * (2 * j + 1) + 2 * i + 1] = make_double2(c.H1, c.V1);
+    if (FILL_PHASE_SYNC)
+      __syncthreads();
+    fill_cell_interior<APPROX, EVAL, (FILL_PHASE_SYNC != 0)>(c, sw.beta, sw.envelope, bp, seed, draw, gchain, Mt, i, j, cell,
+                                                            sf, sc, wmask);
+    if (live) {
+      // rows 2j and 2j+1, sites 2i and 2i+1: four aligned double2 stores
+      double2 *xs = reinterpret_cast<double2 *>(x);
+      xs[(size_t)Mt * (2 * j) + 2 * i] = make_double2(c.A0, c.B0);
+      xs[(size_t)Mt * (2 * j) + 2 * i + 1] = make_double2(c.A1, c.V0);
+      xs[(size_t)Mt * (2 * j + 1) + 2 * i] = make_double2(c.H0, c.B1);
+      xs[(size_t)Mt * (2 * j + 1) + 2 * i + 1] = make_double2(c.H1, c.V1);
+    } else {
+      sf = sc = 0.0;
+    }
   }
   if (EVAL) {
     const double v0 = block_sum(sf);
@@ -1896,7 +1935,7 @@ static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const doubl
     return 0;
   }
   SW sw = make_sw(ctx, m);
-  const int nblk = cdiv(n_coarse_sites(m), 128);
+  const int nblk = cdiv(n_coarse_sites(m), FILL_THREADS);
   const int grid = nblk * B;
   double *partial = nullptr;
   if (S_out && !(partial = ctx_scratch(ctx, (size_t)2 * B * nblk)))
@@ -1905,18 +1944,18 @@ static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const doubl
   if (sw.beta > 8.0) {
     bp.beta = sw.beta;
     if (S_out)
-      prolong_fill_both_kernel<true, true><<<grid, 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
+      prolong_fill_both_kernel<true, true><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
                                                                          draw, nblk, partial);
     else
-      prolong_fill_both_kernel<true, false><<<grid, 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
+      prolong_fill_both_kernel<true, false><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
                                                                           draw, nblk, nullptr);
   } else {
     besselproduct_setup(sw.beta, &bp);
     if (S_out)
-      prolong_fill_both_kernel<false, true><<<grid, 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
+      prolong_fill_both_kernel<false, true><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
                                                                           draw, nblk, partial);
     else
-      prolong_fill_both_kernel<false, false><<<grid, 128, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
+      prolong_fill_both_kernel<false, false><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
                                                                            draw, nblk, nullptr);
   }
   MLMCPI_LAUNCHED("schwinger::prolong_fill");

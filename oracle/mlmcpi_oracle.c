@@ -923,27 +923,16 @@ double orc_expsin2_draw(orc_rng *r, double sigma) {
 static int g_expcos_envelope = 0;
 void orc_set_expcos_envelope(int envelope) { g_expcos_envelope = envelope; }
 
-double orc_expcos_draw(orc_rng *r, double beta, double x_p, double x_m) {
+/* first != NULL: the first Gaussian attempt uses the variates (first[0] = z, first[1] = u) handed in by the
+ * caller instead of a block of the stream r (the fill-in of CoarsenBoth shares one normal pair and one
+ * uniform pair between the two horizontal interior links of a coarse cell); further attempts consume blocks
+ * of r: (z0, u0), (z1, u1), next block, ...  The uniform-proposal branch (tau < 1/2) ignores `first`. */
+static double expcos_draw_impl(orc_rng *r, double beta, double x_p, double x_m, const double *first) {
   const double dx = x_m - x_p;
   const double tau = 2. * beta * fabs(cos(0.5 * dx));
   double x = 0.0;
   int accepted = 0;
-  if (g_expcos_envelope == 2 && tau >= 64.0) {
-    const double a = tau - 40. / 3.;
-    const double sigma = 1.0 / sqrt(a);
-    while (!accepted) {
-      double z[2], u[2];
-      orc_rng_normal2(r, &z[0], &z[1]);
-      orc_rng_uniform2(r, &u[0], &u[1]);
-      for (int t = 0; t < 2 && !accepted; ++t) {
-        x = sigma * z[t];
-        const double x2 = x * x;
-        if (tau * x2 <= 160.)
-          accepted = (u[t] <= 1. - (20. / 3.) * x2) ||
-                     (u[t] <= exp(tau * (cos(x) - 1.) + 0.5 * a * x2));
-      }
-    }
-  } else if (g_expcos_envelope >= 1 && tau < 0.5) {
+  if (g_expcos_envelope >= 1 && tau < 0.5) {
     while (!accepted) {
       double a[2], u[2];
       orc_rng_uniform2(r, &a[0], &a[1]);
@@ -954,24 +943,42 @@ double orc_expcos_draw(orc_rng *r, double beta, double x_p, double x_m) {
       }
     }
   } else {
-    /* envelope 0: expcosdistribution.hh:53-61 (sigma = pi sqrt(2/tau),
-     * fourpi2_inv = 1/(4 pi^2)) */
-    const double sigma =
-        g_expcos_envelope >= 1 ? 0.5 * M_PI / sqrt(tau) : M_PI * sqrt(2. / tau);
-    const double quad =
-        g_expcos_envelope >= 1 ? 2. / (M_PI * M_PI) : 1. / (4. * M_PI * M_PI);
+    const int tight = (g_expcos_envelope == 2 && tau >= 64.0);
+    const double a = tau - 40. / 3.;
+    /* envelope 0: expcosdistribution.hh:53-61 (sigma = pi sqrt(2/tau), fourpi2_inv = 1/(4 pi^2)) */
+    const double sigma = tight ? 1.0 / sqrt(a)
+                               : (g_expcos_envelope >= 1 ? 0.5 * M_PI / sqrt(tau) : M_PI * sqrt(2. / tau));
+    const double quad = g_expcos_envelope >= 1 ? 2. / (M_PI * M_PI) : 1. / (4. * M_PI * M_PI);
+    double z[2] = {0, 0}, u[2] = {0, 0};
+    int t = first ? -1 : 0;
     while (!accepted) {
-      double z[2], u[2];
-      orc_rng_normal2(r, &z[0], &z[1]);
-      orc_rng_uniform2(r, &u[0], &u[1]);
-      for (int t = 0; t < 2 && !accepted; ++t) {
-        x = sigma * z[t];
-        if ((-M_PI <= x) && (x < M_PI))
-          accepted = (u[t] <= exp(tau * (cos(x) - 1. + quad * x * x)));
+      double zz, uu;
+      if (t < 0) {
+        zz = first[0];
+        uu = first[1];
+      } else {
+        if ((t & 1) == 0) {
+          orc_rng_normal2(r, &z[0], &z[1]);
+          orc_rng_uniform2(r, &u[0], &u[1]);
+        }
+        zz = z[t & 1];
+        uu = u[t & 1];
+      }
+      ++t;
+      x = sigma * zz;
+      if (tight) {
+        const double x2 = x * x;
+        if (tau * x2 <= 160.)
+          accepted = (uu <= 1. - (20. / 3.) * x2) || (uu <= exp(tau * (cos(x) - 1.) + 0.5 * a * x2));
+      } else if ((-M_PI <= x) && (x < M_PI)) {
+        accepted = (uu <= exp(tau * (cos(x) - 1. + quad * x * x)));
       }
     }
   }
   return orc_mod_2pi(x + 0.5 * (x_p + x_m) + (fabs(dx) > M_PI) * M_PI);
+}
+double orc_expcos_draw(orc_rng *r, double beta, double x_p, double x_m) {
+  return expcos_draw_impl(r, beta, x_p, x_m, NULL);
 }
 
 /* distribution/besselproductdistribution.hh:82-142.  Per outer attempt one
@@ -1693,16 +1700,28 @@ void orc_fill(const orc_model *fine, uint64_t seed, uint64_t draw, uint32_t chai
           x[LNK(2 * i + 1, 2 * j, 1)] = orc_mod_2pi(0.5 * theta_tilde + dtheta);
           x[LNK(2 * i + 1, 2 * j + 1, 1)] = orc_mod_2pi(0.5 * theta_tilde - dtheta);
         }
-      for (int i = 0; i < Mt; ++i) /* STEP 3 (:63-77) */
+      /* STEP 3 (:63-77).  Variates: the two horizontal interior links (2ic, 2j+1, 0), (2ic+1, 2j+1, 0) of a
+       * coarse cell share one normal pair and one uniform pair -- calls 0, 1 of the stream of the first link --
+       * for their FIRST attempts, (z0, u0) and (z1, u1); further attempts continue on the link's own stream
+       * (first link: calls 2, 3, ...; second link: its stream from call 0). */
+      for (int ic = 0; ic < Mt / 2; ++ic)
         for (int j = 0; j < Mx / 2; ++j) {
-          const double theta_p = orc_mod_2pi(
-              x[LNK(i, 2 * j, 0)] + x[LNK(i + 1, 2 * j, 1)] - x[LNK(i, 2 * j, 1)]);
-          const double theta_m =
-              orc_mod_2pi(x[LNK(i, 2 * j + 1, 1)] + x[LNK(i, 2 * j + 2, 0)] -
-                          x[LNK(i + 1, 2 * j + 1, 1)]);
-          orc_rng r;
-          orc_rng_init(&r, seed, ORC_STREAM_FILL3, draw, chain, Mt * j + i);
-          x[LNK(i, 2 * j + 1, 0)] = orc_expcos_draw(&r, beta, theta_p, theta_m);
+          orc_rng r0, r1;
+          double z[2], u[2];
+          orc_rng_init(&r0, seed, ORC_STREAM_FILL3, draw, chain, Mt * j + 2 * ic);
+          orc_rng_normal2(&r0, &z[0], &z[1]);
+          orc_rng_uniform2(&r0, &u[0], &u[1]);
+          orc_rng_init(&r1, seed, ORC_STREAM_FILL3, draw, chain, Mt * j + 2 * ic + 1);
+          for (int h = 0; h < 2; ++h) {
+            const int i = 2 * ic + h;
+            const double theta_p = orc_mod_2pi(
+                x[LNK(i, 2 * j, 0)] + x[LNK(i + 1, 2 * j, 1)] - x[LNK(i, 2 * j, 1)]);
+            const double theta_m =
+                orc_mod_2pi(x[LNK(i, 2 * j + 1, 1)] + x[LNK(i, 2 * j + 2, 0)] -
+                            x[LNK(i + 1, 2 * j + 1, 1)]);
+            const double first[2] = {z[h], u[h]};
+            x[LNK(i, 2 * j + 1, 0)] = expcos_draw_impl(h == 0 ? &r0 : &r1, beta, theta_p, theta_m, first);
+          }
         }
     } else if (fine->coarsening == ORC_COARSEN_TEMPORAL) {
       /* qft/quenchedschwingerconditionedfineaction.cc:147-174 */
