@@ -146,7 +146,8 @@ int mlmcpi_rank(const mlmcpi_ctx *ctx);
  * MLMCPI_OPT_LEAPFROG_FUSE: leapfrog steps per pass over HBM (temporal blocking, variant 0 only):
  * 0 = one; 1 (default) = four for Mt in {64, 128, 256}, two for Mt = 512 (K-stage register pipeline
  * with compile-time block size), two for every other Mt (round-1 kernel); 2 / 3 = two / four steps
- * through the K-stage kernel; 4 = the round-1 two-step kernel.  Same trajectory, bit for bit.
+ * through the K-stage kernel; 4 = the round-1 two-step kernel; 5 = eight steps (Mt <= 128; 236 registers, two
+ * blocks per SM: measured slower than four, 29.0 vs 25.4 us per step).  Same trajectory, bit for bit.
  * MLMCPI_OPT_SWEEP_REVERSE: 1 = the coloured sweeps visit the colours in descending order (the
  * exact reverse of the default; used to make a sequence of sweeps a reversible kernel).
  * MLMCPI_OPT_OVERRELAX_ONE_PASS: 1 (default) = a Schwinger overrelaxation sweep updates all four

@@ -222,7 +222,7 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
     ctx->sweep_reverse = value;
     return 0;
   }
-  if (option == MLMCPI_OPT_LEAPFROG_FUSE && value >= 0 && value <= 4) {
+  if (option == MLMCPI_OPT_LEAPFROG_FUSE && value >= 0 && value <= 5) {
     ctx->leapfrog_fuse = value;
     return 0;
   }

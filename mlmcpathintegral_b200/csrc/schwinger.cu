@@ -567,7 +567,7 @@ template <int K> struct LeapDt {
 #define MLMCPI_LFK_BLOCKS_128 4 // resident blocks per SM the register allocation aims at, MT <= 128 (measured: 3 -> 27.5, 4 -> 25.5, 5 (spills) -> 50 us per step)
 #endif
 template <int K, int MT, int S>
-__global__ void __launch_bounds__(MT, (MT <= 128 ? MLMCPI_LFK_BLOCKS_128 : (MT <= 256 ? 2 : 1)))
+__global__ void __launch_bounds__(MT, (K >= 8 ? 2 : (MT <= 128 ? MLMCPI_LFK_BLOCKS_128 : (MT <= 256 ? 2 : 1))))
     leapfrog_rowpipek_kernel(const double beta, const LeapDt<K> dt, const int Mx, const double *__restrict__ x_in,
                              double *__restrict__ x_out, const double *__restrict__ p_in,
                              double *__restrict__ p_out, const int R, const int chunks) {
@@ -1561,6 +1561,17 @@ int leapfrog_multi(mlmcpi_ctx *ctx, const SW &sw, const double *dtp, const doubl
   }
   return MLMCPI_EUNSUPPORTED;
 }
+// eight steps per pass: Mt <= 128 only (the register queues of seven stages)
+int leapfrog_multi8(mlmcpi_ctx *ctx, const SW &sw, const double *dtp, const double *dtx, const double *x_in,
+                    double *x_out, const double *p_in, double *p_out, int B) {
+  if (sw.Mx < 18)
+    return MLMCPI_EUNSUPPORTED;
+  if (sw.Mt == 64)
+    return leapfrog_multi_launch<8, 64>(ctx, sw, dtp, dtx, x_in, x_out, p_in, p_out, B);
+  if (sw.Mt == 128)
+    return leapfrog_multi_launch<8, 128>(ctx, sw, dtp, dtx, x_in, x_out, p_in, p_out, B);
+  return MLMCPI_EUNSUPPORTED;
+}
 // steps per HBM pass for this shape: MLMCPI_OPT_LEAPFROG_FUSE = 1 picks 4 where the register pipeline
 // fits three blocks per SM (Mt <= 128) and 2 otherwise; 2, 3 (= 4 steps) select explicitly
 int leapfrog_steps_per_pass(const mlmcpi_ctx *ctx, const SW &sw) {
@@ -1575,6 +1586,8 @@ int leapfrog_steps_per_pass(const mlmcpi_ctx *ctx, const SW &sw) {
     return 2;
   if (ctx->leapfrog_fuse == 3)
     return 4;
+  if (ctx->leapfrog_fuse == 5)
+    return 8;
   return sw.Mt <= 256 ? 4 : 2;
 }
 
@@ -1602,16 +1615,19 @@ int trajectory(mlmcpi_ctx *ctx, const SW &sw, int nt, double dt, const double *x
   const int per_pass = fuse ? leapfrog_steps_per_pass(ctx, sw) : 1;
   while (k <= nt) {
     int rc;
-    const int K = (per_pass >= 4 && k + 3 <= nt) ? 4 : ((per_pass >= 2 && k + 1 <= nt) ? 2 : 0);
+    const int K = (per_pass >= 8 && k + 7 <= nt && sw.Mt <= 128)
+                      ? 8
+                      : ((per_pass >= 4 && k + 3 <= nt) ? 4 : ((per_pass >= 2 && k + 1 <= nt) ? 2 : 0));
     if (K) { // steps k .. k+K-1 in one pass (compile-time block size, K-stage register pipeline)
-      double a[4], b[4];
+      double a[8], b[8];
       for (int q = 0; q < K; ++q) {
         a[q] = dtp(k + q);
         b[q] = dtx(k + q);
       }
       double *p_next = (p_cur == p) ? p_alt : p;
-      rc = (K == 4) ? leapfrog_multi<4>(ctx, sw, a, b, in, out, p_cur, p_next, B)
-                    : leapfrog_multi<2>(ctx, sw, a, b, in, out, p_cur, p_next, B);
+      rc = (K == 8) ? leapfrog_multi8(ctx, sw, a, b, in, out, p_cur, p_next, B)
+                    : ((K == 4) ? leapfrog_multi<4>(ctx, sw, a, b, in, out, p_cur, p_next, B)
+                                : leapfrog_multi<2>(ctx, sw, a, b, in, out, p_cur, p_next, B));
       if (rc == 0) {
         p_cur = p_next;
         last = out;

@@ -767,18 +767,18 @@ def test_leapfrog_k_stage_pipeline_is_bit_identical(mp, ctx, orc):
     trajectories whose length leaves 1, 2 or 3 steps for the fall-back kernels, and against the oracle"""
     rng = np.random.default_rng(17)
     for Mt, Mx, B, nt in [(64, 64, 3, 9), (128, 128, 2, 12), (128, 40, 2, 7), (256, 34, 2, 6), (512, 12, 1, 5),
-                          (128, 10, 2, 4), (64, 200, 2, 11)]:
+                          (128, 10, 2, 4), (64, 200, 2, 11), (128, 96, 2, 19)]:
         m = mp.schwinger(Mt, Mx, 5.0)
         x0 = dev(ctx, rng.uniform(-3, 3, (B, 2 * Mt * Mx)))
         p0 = dev(ctx, rng.normal(size=(B, 2 * Mt * Mx)))
         res = {}
-        for fuse in (0, 2, 3, 4, 1):
+        for fuse in (0, 2, 3, 4, 5, 1):     # 5 = eight steps per pass (Mt <= 128, else four)
             ctx.set_option(mp._lib.OPT_LEAPFROG_FUSE, fuse)
             x, p = x0.clone(), p0.clone()
             ctx.leapfrog(m, nt, 0.03, x, p)
             res[fuse] = (host(x).copy(), host(p).copy())
         ctx.set_option(mp._lib.OPT_LEAPFROG_FUSE, 1)
-        for fuse in (2, 3, 4, 1):
+        for fuse in (2, 3, 4, 5, 1):
             assert np.array_equal(res[fuse][0], res[0][0]), (Mt, Mx, nt, fuse, "theta")
             assert np.array_equal(res[fuse][1], res[0][1]), (Mt, Mx, nt, fuse, "p")
         o = po.schwinger(Mt, Mx, 5.0)
