@@ -712,10 +712,10 @@ def gpu_main(a):
         steps_per_launch = (a.nt + 1) * a.steps / lf_launches if lf_launches else None
         roofline = {
             "bound": "hbm",
-            "kernel": "leapfrog_rowpipe2_kernel (two leapfrog steps per launch; the last, kick-only step of a "
-                      "trajectory runs in leapfrog_rowpipe_kernel)",
+            "kernel": "leapfrog_rowpipek_kernel<4, 128, 8> (four leapfrog steps per launch on the 128^2 coarsest level; "
+                      "the last, kick-only step of a trajectory runs in leapfrog_rowpipe_kernel)",
             # algorithmic bytes (64 B per site and leapfrog step) / CUDA-event time of the
-            # leapfrog launches; above 1.0 because the kernel blocks two steps per pass over HBM
+            # leapfrog launches; above 1.0 because the kernel blocks four steps per pass over HBM
             "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None,
             "steps_per_hbm_pass": steps_per_launch,
