@@ -143,13 +143,19 @@ __device__ __forceinline__ void rng_uniform2(Rng &r, double &u0, double &u1) {
   u1 = ((double)(o[2] >> 5) * 67108864.0 + (double)(o[3] >> 6)) * (1.0 / 9007199254740992.0);
 }
 
-__device__ __forceinline__ void rng_normal2(Rng &r, double &z0, double &z1) {
-  double u0, u1, s, c;
-  rng_uniform2(r, u0, u1);
+// Box-Muller: two uniforms in [0, 1) -> two standard normals
+__device__ __forceinline__ void box_muller(const double u0, const double u1, double &z0, double &z1) {
+  double s, c;
   const double rad = sqrt(-2.0 * log(1.0 - u0));
   sincospi(2.0 * u1, &s, &c);
   z0 = rad * c;
   z1 = rad * s;
+}
+
+__device__ __forceinline__ void rng_normal2(Rng &r, double &z0, double &z1) {
+  double u0, u1;
+  rng_uniform2(r, u0, u1);
+  box_muller(u0, u1, z0, z1);
 }
 
 __device__ __forceinline__ double rng_angle2(Rng &r, double &second) {
@@ -219,6 +225,14 @@ __device__ __forceinline__ double sin_force(const double x) {
   return __hiloint2double(__double2hiint(s) ^ parity_bit, __double2loint(s));
 }
 
+// cos x = 1 - 2 sin^2(x / 2) through the branch-free sine above (relative accuracy of 1 - cos x for small x,
+// 4e-16 absolute otherwise): for the stochastic kernels, whose instruction footprint has to stay inside the
+// SM's instruction cache (CUDA's cos() is three times the code, plus a slow path that is never taken)
+__device__ __forceinline__ double cos_fast(const double x) {
+  const double s = sin_force(0.5 * x);
+  return fma(-2.0 * s, s, 1.0);
+}
+
 // the same for a divisor b known at run time with c = RN(1 / b) (computed once per thread: the callers'
 // divisor is a kernel argument): u / b, correctly rounded
 __device__ __forceinline__ double div_exact(const double u, const double b, const double c) {
@@ -285,7 +299,7 @@ __device__ __forceinline__ double fast_bessel_I0_scaled(const double z) {
     p = z_inv * p + a2;
     p = z_inv * p + a1;
     p = z_inv * p + 1.0;
-    return p / sqrt(2. * M_PI * z);
+    return p * rsqrt(2. * M_PI * z);
   }
   return bessel_I0_scaled(z);
 }
@@ -352,9 +366,12 @@ __device__ __forceinline__ double expsin2_pdf(const double x, const double sigma
 // a block of the stream r -- the fused fill-in draws ONE normal pair and ONE uniform pair per coarse cell and gives
 // a half of each to its two horizontal links, whose further attempts (rare: 0.3 % at tau = 2048) continue on
 // their own streams.  Without it the sequence of attempts is (z0, u0), (z1, u1) of block 0, then block 1, ...
-__device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, const int envelope,
-                                                   const bool have_first = false, const double z_first = 0.0,
-                                                   const double u_first = 0.0) {
+// refill(z0, z1, u0, u1): the next block of the stream (one normal pair, one uniform pair); a parameter so that the
+// fused fill-in kernel can route it through its one shared copy of the generator code
+template <class Refill>
+__device__ __forceinline__ double expcos_draw_core_f(Rng &r, Refill refill, const double tau, const int envelope,
+                                                     const bool have_first = false, const double z_first = 0.0,
+                                                     const double u_first = 0.0) {
   double x = 0.0;
   bool accepted = false;
   if (envelope >= 1 && tau < 0.5) {
@@ -363,10 +380,10 @@ __device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, con
       rng_uniform2(r, a0, a1);
       rng_uniform2(r, u0, u1);
       x = -M_PI + 2. * M_PI * a0;
-      accepted = (u0 <= exp(tau * (cos(x) - 1.)));
+      accepted = (u0 <= exp(tau * (cos_fast(x) - 1.)));
       if (!accepted) {
         x = -M_PI + 2. * M_PI * a1;
-        accepted = (u1 <= exp(tau * (cos(x) - 1.)));
+        accepted = (u1 <= exp(tau * (cos_fast(x) - 1.)));
       }
     }
     return x;
@@ -395,10 +412,8 @@ __device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, con
       z = z_first;
       u = u_first;
     } else {
-      if ((t & 1) == 0) {
-        rng_normal2(r, z0, z1);
-        rng_uniform2(r, u0, u1);
-      }
+      if ((t & 1) == 0)
+        refill(z0, z1, u0, u1);
       z = (t & 1) ? z1 : z0;
       u = (t & 1) ? u1 : u0;
     }
@@ -409,10 +424,22 @@ __device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, con
     if (inside) {
       accepted = tight && (u <= 1. - sq * x2);
       if (!accepted)
-        accepted = (u <= exp(tau * (cos(x) - 1.) + q * x2));
+        accepted = (u <= exp(tau * (cos_fast(x) - 1.) + q * x2));
     }
   }
   return x;
+}
+
+__device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, const int envelope,
+                                                   const bool have_first = false, const double z_first = 0.0,
+                                                   const double u_first = 0.0) {
+  return expcos_draw_core_f(
+      r,
+      [&r](double &z0, double &z1, double &u0, double &u1) {
+        rng_normal2(r, z0, z1);
+        rng_uniform2(r, u0, u1);
+      },
+      tau, envelope, have_first, z_first, u_first);
 }
 
 // by-products of a draw, from which the fused fill-in kernel evaluates -log pdf of the drawn
@@ -421,18 +448,30 @@ __device__ __forceinline__ double expcos_draw_core(Rng &r, const double tau, con
 struct ExpCosDrawn {
   double x, tau;
 };
-__device__ __forceinline__ double expcos_draw(Rng &r, const double beta, const double x_p,
-                                              const double x_m, const int envelope,
-                                              ExpCosDrawn *info = nullptr, const bool have_first = false,
-                                              const double z_first = 0.0, const double u_first = 0.0) {
+template <class Refill>
+__device__ __forceinline__ double expcos_draw_f(Rng &r, Refill refill, const double beta, const double x_p,
+                                                const double x_m, const int envelope, ExpCosDrawn *info,
+                                                const bool have_first, const double z_first, const double u_first) {
   const double dx = x_m - x_p;
-  const double tau = 2. * beta * fabs(cos(0.5 * dx));
-  const double x = expcos_draw_core(r, tau, envelope, have_first, z_first, u_first);
+  const double tau = 2. * beta * fabs(cos_fast(0.5 * dx));
+  const double x = expcos_draw_core_f(r, refill, tau, envelope, have_first, z_first, u_first);
   if (info) {
     info->x = x;
     info->tau = tau;
   }
   return mod_2pi_fast(x + 0.5 * (x_p + x_m) + (fabs(dx) > M_PI) * M_PI);
+}
+__device__ __forceinline__ double expcos_draw(Rng &r, const double beta, const double x_p,
+                                              const double x_m, const int envelope,
+                                              ExpCosDrawn *info = nullptr, const bool have_first = false,
+                                              const double z_first = 0.0, const double u_first = 0.0) {
+  return expcos_draw_f(
+      r,
+      [&r](double &z0, double &z1, double &u0, double &u1) {
+        rng_normal2(r, z0, z1);
+        rng_uniform2(r, u0, u1);
+      },
+      beta, x_p, x_m, envelope, info, have_first, z_first, u_first);
 }
 
 // distribution/expcosdistribution.cc:7-21
@@ -447,7 +486,7 @@ __device__ __forceinline__ double expcos_pdf(const double beta, const double x, 
     dx = 2. * M_PI - dx;
   }
   z *= sign_flip;
-  const double sigma = 2. * beta * fabs(cos(0.5 * dx));
+  const double sigma = 2. * beta * fabs(cos_fast(0.5 * dx));
   const double Z_norm = 2. * M_PI * fast_bessel_I0_scaled(sigma);
   return 1. / Z_norm * exp(sigma * (cos(z - 0.5 * dx) - 1.0));
 }
@@ -541,8 +580,8 @@ __device__ __forceinline__ void approx_N_p_sigma2inv(const double beta, const do
     sigma2_m_inv = 0.0;
     N_p = 1.0;
   } else {
-    sigma2_p_inv = beta * cos(0.25 * x0);
-    sigma2_m_inv = beta * sin(0.25 * x0);
+    sigma2_p_inv = beta * cos_fast(0.25 * x0);
+    sigma2_m_inv = beta * sin_force(0.25 * x0);
     const double q = sigma2_p_inv / sigma2_m_inv;
     const double rho = q * sqrt(q) * exp(-4.0 * (sigma2_p_inv - sigma2_m_inv));
     N_p = 1.0 / (1.0 + rho);
@@ -558,9 +597,10 @@ struct ApproxDrawn {
 // distribution/approximatebesselproductdistribution.hh:81-106; xi: the uniform variate that
 // selects the mode (supplied by the caller, which gets it for free from the Philox call
 // that also yields the step-2 split angle), the normal comes from one rng_normal2
-__device__ __forceinline__ double approxbessel_draw(Rng &r, const double beta, const double x_p,
-                                                    const double x_m, const double xi,
-                                                    ApproxDrawn *info = nullptr) {
+// (approxbessel_draw_z: the same with the normal variate handed in)
+__device__ __forceinline__ double approxbessel_draw_z(const double z0, const double beta, const double x_p,
+                                                      const double x_m, const double xi,
+                                                      ApproxDrawn *info = nullptr) {
   double x0 = x_p - x_m;
   double sign_flip = (x0 < 0) ? -1 : +1;
   x0 *= sign_flip;
@@ -570,8 +610,6 @@ __device__ __forceinline__ double approxbessel_draw(Rng &r, const double beta, c
   }
   double N_p, sigma2_p_inv, sigma2_m_inv;
   approx_N_p_sigma2inv(beta, x0, N_p, sigma2_p_inv, sigma2_m_inv);
-  double z0, z1;
-  rng_normal2(r, z0, z1);
   double sigma, xshift;
   if (xi <= N_p) {
     sigma = 1. / sqrt(sigma2_p_inv);
@@ -589,6 +627,13 @@ __device__ __forceinline__ double approxbessel_draw(Rng &r, const double beta, c
   const double x = sigma * z0 + 0.5 * x0 - xshift;
   return mod_2pi_fast(sign_flip * x + x_m);
 }
+__device__ __forceinline__ double approxbessel_draw(Rng &r, const double beta, const double x_p,
+                                                    const double x_m, const double xi,
+                                                    ApproxDrawn *info = nullptr) {
+  double z0, z1;
+  rng_normal2(r, z0, z1);
+  return approxbessel_draw_z(z0, beta, x_p, x_m, xi, info);
+}
 
 // the mixture pdf of distribution/approximatebesselproductdistribution.cc:17-35 as a function of
 // w = z - x0/2 (distance from the main peak)
@@ -597,8 +642,18 @@ __device__ __forceinline__ double approxbessel_pdf_w(const double N_p, const dou
   const double N_m = 1. - N_p;
   const double sq_p = sqrt(sigma2_p_inv), sq_m = sqrt(sigma2_m_inv);
   double s_p = 0.0, s_m = 0.0;
+  // images that can contribute: a < 746 needs |w + 2 k pi| (first mode) or |w + (2k + 1) pi| (second mode)
+  // below R = sqrt(1492 / sigma2_inv) <= sqrt(1492 / min), so k runs over [(-R - pi - w) / 2 pi, (R - w) / 2 pi]
+  // (one image for beta >~ 150; the tests inside the loop still decide term by term)
+  int k_lo = -4, k_hi = 4;
+  {
+    const double smin = (sq_m != 0.0) ? fmin(sigma2_p_inv, sigma2_m_inv) : sigma2_p_inv;
+    const double R = 1492.0 * rsqrt(1492.0 * smin) + 1e-6;
+    k_lo = max(-4, (int)floor((-R - M_PI - w) * (0.5 / M_PI)));
+    k_hi = min(4, (int)ceil((R - w) * (0.5 / M_PI)));
+  }
 #pragma unroll 1
-  for (int k = -4; k <= 4; ++k) {
+  for (int k = k_lo; k <= k_hi; ++k) {
     // exp(-a) == +0.0 exactly for a > 746 in IEEE double, and the second mode has weight
     // sq_m == 0 when x0 < pi/8: skipping those terms leaves the sums bit-identical
     double z_shifted = w + 2 * k * M_PI;

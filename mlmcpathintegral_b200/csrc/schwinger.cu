@@ -1061,8 +1061,44 @@ __device__ __forceinline__ double cell_plaquette_sum(const CellLinks &c) {
 // stream (the fused kernel's threads run through 2500 of its 4500 instructions once and "no_instructions" is
 // its top stall reason).  Measured: no gain (3.54 ms with and without); off.  Neither did a called
 // (non-inlined) Philox help: 4.29 ms.
+// The seven Philox blocks every cell consumes, drawn in ONE rolled loop (one copy of the ten rounds, of the
+// conversion and of the Box-Muller transform in the instruction stream instead of seven / two): the fused
+// fill-in kernel runs through its code once per thread, and what it executes on the common path has to stay
+// inside the 32 KB instruction cache of the SM (ncu: gcc__cache_requests_type_instruction at 99.5 % of peak
+// with one copy per call site).  Same counters, same variates as the straight-line version.
+//   q = 0, 1, 2: FILL1 of the cell, its right and its upper neighbour (NEIGH only): step-1 split angles
+//   q = 3: FILL2 call 0 (split angle of the vertical pair, mode selector)   q = 4: FILL2 call 1 (normal pair)
+//   q = 5: FILL3 call 0 of link (2i, 2j+1, 0) (normal pair)                 q = 6: FILL3 call 1 (uniform pair)
+//   q = 7, 8: a later block of a FILL3 stream (normal pair, uniform pair: the retry of a rejected horizontal link)
+// One NON-INLINED function: the retry (taken by a few lanes of every fifth warp) calls the same code as the start of the
+// kernel, where next to nothing is live across the call.
+struct FillVariates {
+  double v[9][2];
+};
+__device__ __noinline__ void fill_gen(FillVariates *V, int q_begin, int q_end, uint64_t seed, uint64_t draw,
+                                      uint32_t gchain, int cell, int cell_r, int cell_t, int hidx, uint32_t hcall) {
+  Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell);
+#pragma unroll 1
+  for (int q = q_begin; q < q_end; ++q) {
+    r.c0 = (uint32_t)((q == 1) ? cell_r : ((q == 2) ? cell_t : ((q >= 5) ? hidx : cell)));
+    const uint32_t stream = (q < 3) ? MLMCPI_STREAM_FILL1 : ((q < 5) ? MLMCPI_STREAM_FILL2 : MLMCPI_STREAM_FILL3);
+    r.a = (stream << 24) | ((q >= 7) ? hcall + (uint32_t)(q - 7) : ((q == 4 || q == 6) ? 1u : 0u));
+    double v0, v1;
+    rng_uniform2(r, v0, v1);
+    if (q == 4 || q == 5 || q == 7)
+      box_muller(v0, v1, v0, v1);
+    V->v[q][0] = v0;
+    V->v[q][1] = v1;
+  }
+}
+template <bool NEIGH>
+__device__ __forceinline__ void fill_variates(FillVariates &V, uint64_t seed, uint64_t draw, uint32_t gchain,
+                                              int cell, int cell_r, int cell_t, int hidx) {
+  fill_gen(&V, NEIGH ? 0 : 3, 7, seed, draw, gchain, cell, cell_r, cell_t, hidx, 0);
+}
+
 template <bool APPROX, bool EVAL, bool PHASE_SYNC = false>
-__device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double beta,
+__device__ __forceinline__ void fill_cell_interior(CellLinks &c, const FillVariates &V, const double beta,
                                                    const int envelope,
                                                    const BesselProductConst &bp, uint64_t seed,
                                                    uint64_t draw, uint32_t gchain, int Mt, int i,
@@ -1075,13 +1111,17 @@ __device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double be
   {
     const double theta_p = mod_2pi_fast(c.A1 + c.R0 + c.R1 - c.T1);
     const double theta_m = mod_2pi_fast(c.B0 + c.B1 + c.T0 - c.A0);
-    Rng r = rng_init(seed, MLMCPI_STREAM_FILL2, draw, gchain, cell);
-    // first call of the stream: (split angle, mode selector of the approximate distribution)
-    double u0, u1;
-    rng_uniform2(r, u0, u1);
-    const double dtheta = -M_PI + 2. * M_PI * u0;
-    const double theta_tilde = APPROX ? approxbessel_draw(r, beta, theta_p, theta_m, u1, EVAL ? &ad : nullptr)
-                                      : besselproduct_draw(r, bp, theta_p, theta_m);
+    // first call of the FILL2 stream: (split angle, mode selector of the approximate distribution); the
+    // second: the normal pair of the approximate draw (the exact draw continues on the stream itself)
+    const double dtheta = -M_PI + 2. * M_PI * V.v[3][0];
+    double theta_tilde;
+    if (APPROX) {
+      theta_tilde = approxbessel_draw_z(V.v[4][0], beta, theta_p, theta_m, V.v[3][1], EVAL ? &ad : nullptr);
+    } else {
+      Rng r = rng_init(seed, MLMCPI_STREAM_FILL2, draw, gchain, cell);
+      r.a += 1;
+      theta_tilde = besselproduct_draw(r, bp, theta_p, theta_m);
+    }
     __syncwarp(wmask);
     if (PHASE_SYNC)
       __syncthreads();
@@ -1095,20 +1135,26 @@ __device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double be
   // (h = 0: calls 2, 3, ...; h = 1: the stream of link (2i+1, 2j+1, 0) from call 0).  Two Philox calls and one
   // Box-Muller transform fewer per cell than a block per link (15 % of the kernel's instructions).
   double Zprod = 1.0, tsum = 0.0, tcos = 0.0;
-  Rng r0 = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i);
-  double zs0, zs1, us0, us1;
-  rng_normal2(r0, zs0, zs1);
-  rng_uniform2(r0, us0, us1);
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     const double theta_p = mod_2pi_fast(h == 0 ? c.A0 + c.V0 - c.B0 : c.A1 + c.R0 - c.V0);
     const double theta_m = mod_2pi_fast(h == 0 ? c.B1 + c.T0 - c.V1 : c.V1 + c.T1 - c.R1);
-    Rng r = r0;
-    if (h == 1)
-      r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i + 1);
+    Rng r = rng_init(seed, MLMCPI_STREAM_FILL3, draw, gchain, Mt * j + 2 * i + h);
+    if (h == 0)
+      r.a += 2;
     ExpCosDrawn e;
-    const double H = expcos_draw(r, beta, theta_p, theta_m, envelope, &e, true, h == 0 ? zs0 : zs1,
-                                 h == 0 ? us0 : us1);
+    FillVariates *Vp = const_cast<FillVariates *>(&V);
+    const double H = expcos_draw_f(
+        r,
+        [&r, Vp, seed, draw, gchain](double &z0, double &z1, double &u0, double &u1) {
+          fill_gen(Vp, 7, 9, seed, draw, gchain, 0, 0, 0, (int)r.c0, r.a & 0xffffffu);
+          r.a += 2;
+          z0 = Vp->v[7][0];
+          z1 = Vp->v[7][1];
+          u0 = Vp->v[8][0];
+          u1 = Vp->v[8][1];
+        },
+        beta, theta_p, theta_m, envelope, &e, true, V.v[5][h], V.v[6][h]);
     __syncwarp(wmask);
     if (PHASE_SYNC)
       __syncthreads();
@@ -1119,12 +1165,13 @@ __device__ __forceinline__ void fill_cell_interior(CellLinks &c, const double be
     if (EVAL && APPROX) {
       Zprod *= 2. * M_PI * fast_bessel_I0_scaled(e.tau);
       tsum += e.tau;
-      tcos += e.tau * cos(e.x);
+      tcos += e.tau * cos_fast(e.x);
     }
   }
   if (EVAL) {
     if (APPROX) {
-      sc = (log(Zprod) - log(approxbessel_pdf_w(ad.N_p, ad.s_p, ad.s_m, ad.w))) + (tsum - tcos);
+      // log Zprod - log pdf as one logarithm (the pdf at a point that was just drawn is >= exp(-37) of its maximum)
+      sc = log(Zprod / approxbessel_pdf_w(ad.N_p, ad.s_p, ad.s_m, ad.w)) + (tsum - tcos);
       sf = 4. - tcos / beta;
     } else {
       sc = cond_both_bessel_cell(c, beta, bp);
@@ -1158,7 +1205,10 @@ __global__ void fill_both_step23_kernel(SW sw, BesselProductConst bp, double *x_
   c.T0 = TH(x, 2 * i, j2, 0);
   c.T1 = TH(x, 2 * i + 1, j2, 0);
   double sf_unused, sc_unused;
-  fill_cell_interior<APPROX, false>(c, sw.beta, sw.envelope, bp, seed, draw, chain0 + (uint32_t)chain, Mt, i, j, cell,
+  FillVariates V;
+  fill_variates<false>(V, seed, draw, chain0 + (uint32_t)chain, cell, 0, 0, Mt * j + 2 * i);
+  __syncwarp(wmask);
+  fill_cell_interior<APPROX, false>(c, V, sw.beta, sw.envelope, bp, seed, draw, chain0 + (uint32_t)chain, Mt, i, j, cell,
                                     sf_unused, sc_unused, wmask);
   TH(x, 2 * i + 1, 2 * j, 1) = c.V0;
   TH(x, 2 * i + 1, 2 * j + 1, 1) = c.V1;
@@ -1200,32 +1250,28 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MINBLK) prolong_fill_both_k
     const double2 own = xc[cell];
     const double cr = xc[cell_r].y, ct = xc[cell_t].x;
     CellLinks c;
+    FillVariates V;
+    fill_variates<true>(V, seed, draw, gchain, cell, cell_r, cell_t, Mt * j + 2 * i);
     {
-      Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell);
-      double dth_s;
-      const double dth_t = rng_angle2(r, dth_s);
+      const double dth_t = -M_PI + 2. * M_PI * V.v[0][0], dth_s = -M_PI + 2. * M_PI * V.v[0][1];
       c.A0 = mod_2pi_fast(0.5 * own.x + dth_t);
       c.A1 = mod_2pi_fast(0.5 * own.x - dth_t);
       c.B0 = mod_2pi_fast(0.5 * own.y + dth_s);
       c.B1 = mod_2pi_fast(0.5 * own.y - dth_s);
     }
     {
-      Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell_r);
-      double dth_s;
-      (void)rng_angle2(r, dth_s);
+      const double dth_s = -M_PI + 2. * M_PI * V.v[1][1];
       c.R0 = mod_2pi_fast(0.5 * cr + dth_s);
       c.R1 = mod_2pi_fast(0.5 * cr - dth_s);
     }
     {
-      Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell_t);
-      double dth_s;
-      const double dth_t = rng_angle2(r, dth_s);
+      const double dth_t = -M_PI + 2. * M_PI * V.v[2][0];
       c.T0 = mod_2pi_fast(0.5 * ct + dth_t);
       c.T1 = mod_2pi_fast(0.5 * ct - dth_t);
     }
     if (FILL_PHASE_SYNC)
       __syncthreads();
-    fill_cell_interior<APPROX, EVAL, (FILL_PHASE_SYNC != 0)>(c, sw.beta, sw.envelope, bp, seed, draw, gchain, Mt, i, j, cell,
+    fill_cell_interior<APPROX, EVAL, (FILL_PHASE_SYNC != 0)>(c, V, sw.beta, sw.envelope, bp, seed, draw, gchain, Mt, i, j, cell,
                                                             sf, sc, wmask);
     if (live) {
       // rows 2j and 2j+1, sites 2i and 2i+1: four aligned double2 stores
@@ -1238,13 +1284,14 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MINBLK) prolong_fill_both_k
       sf = sc = 0.0;
     }
   }
-  if (EVAL) {
-    const double v0 = block_sum(sf);
-    if (threadIdx.x == 0)
-      partial[(size_t)chain * nblk + blk] = v0;
-    const double v1 = block_sum(sc);
-    if (threadIdx.x == 0)
-      partial[((size_t)B + chain) * nblk + blk] = v1;
+  if (EVAL) { // one partial sum per WARP: no block-wide barrier at the end of the kernel (ncu: 14 % of the stall samples)
+    constexpr int WARPS = FILL_THREADS / 32;
+    const double v0 = warp_sum(sf), v1 = warp_sum(sc);
+    if ((threadIdx.x & 31) == 0) {
+      const size_t slot = (size_t)blk * WARPS + (threadIdx.x >> 5), npart = (size_t)nblk * WARPS;
+      partial[(size_t)chain * npart + slot] = v0;
+      partial[((size_t)B + chain) * npart + slot] = v1;
+    }
   }
 }
 
@@ -1954,7 +2001,8 @@ static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const doubl
   const int nblk = cdiv(n_coarse_sites(m), FILL_THREADS);
   const int grid = nblk * B;
   double *partial = nullptr;
-  if (S_out && !(partial = ctx_scratch(ctx, (size_t)2 * B * nblk)))
+  const int npart = nblk * (FILL_THREADS / 32); // one partial sum per warp
+  if (S_out && !(partial = ctx_scratch(ctx, (size_t)2 * B * npart)))
     return MLMCPI_ENOMEM;
   BesselProductConst bp;
   if (sw.beta > 8.0) {
@@ -1976,7 +2024,7 @@ static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const doubl
   }
   MLMCPI_LAUNCHED("schwinger::prolong_fill");
   if (S_out)
-    return launch_reduce_finish(ctx, partial, nblk, B, 2, EPI_SCALE, sw.beta, 1.0, S_out, nullptr);
+    return launch_reduce_finish(ctx, partial, npart, B, 2, EPI_SCALE, sw.beta, 1.0, S_out, nullptr);
   return 0;
 }
 
