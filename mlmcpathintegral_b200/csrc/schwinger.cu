@@ -1070,12 +1070,18 @@ __device__ __forceinline__ double cell_plaquette_sum(const CellLinks &c) {
 //   q = 3: FILL2 call 0 (split angle of the vertical pair, mode selector)   q = 4: FILL2 call 1 (normal pair)
 //   q = 5: FILL3 call 0 of link (2i, 2j+1, 0) (normal pair)                 q = 6: FILL3 call 1 (uniform pair)
 //   q = 7, 8: a later block of a FILL3 stream (normal pair, uniform pair: the retry of a rejected horizontal link)
-// One NON-INLINED function: the retry (taken by a few lanes of every fifth warp) calls the same code as the start of the
-// kernel, where next to nothing is live across the call.
+// One function for the first seven blocks and for the retry (taken by a few lanes of every fifth warp); see FILL_GEN_ATTR.
 struct FillVariates {
   double v[9][2];
 };
-__device__ __noinline__ void fill_gen(FillVariates *V, int q_begin, int q_end, uint64_t seed, uint64_t draw,
+// FILL_GEN_ATTR: __noinline__ takes the kernel off the instruction-cache limit (3.17 ms against 3.08 - 3.15 alone, GPC cache
+// requests 62 % of peak instead of 99 %) but costs the whole step 4 % (8.5 against 8.1 - 8.2 ms, profiles/r02_summary.md
+// section 12: the step runs at the board's power cap, and the faster, denser kernel lowers the clock of the leapfrog launches
+// that follow it); inlined is the default.
+#ifndef FILL_GEN_ATTR
+#define FILL_GEN_ATTR __forceinline__
+#endif
+__device__ FILL_GEN_ATTR void fill_gen(FillVariates *V, int q_begin, int q_end, uint64_t seed, uint64_t draw,
                                       uint32_t gchain, int cell, int cell_r, int cell_t, int hidx, uint32_t hcall) {
   Rng r = rng_init(seed, MLMCPI_STREAM_FILL1, draw, gchain, cell);
 #pragma unroll 1
