@@ -59,6 +59,10 @@ enum { MLMCPI_QOI_X2 = 0, MLMCPI_QOI_ROTOR_CHI = 1, MLMCPI_QOI_SCHWINGER_CHI = 2
  *     the first attempts of their ExpCos draws from ONE normal pair and ONE uniform pair -- calls 0, 1 of the
  *     stream with index Mt j + 2i: (z0, u0) and (z1, u1); further attempts continue on the link's own stream
  *     (index Mt j + 2i from call 2, index Mt j + 2i + 1 from call 0);
+ *   HEATBATH, quenched Schwinger model: the links of a colour in a lattice row, numbered n = i (mu = 0) or i / 2
+ *     (mu = 1), are updated in pairs (2p, 2p + 1): calls 0, 1 of the stream of the EVEN link give (z0, u0), (z1, u1),
+ *     the first ExpCos attempt of the even and of the odd link; further attempts continue on the link's own stream
+ *     (even link from call 2, odd link from call 0).  mlmcpi_dof_update follows the same map;
  *   CLUSTER: index 0 = (reflection angle, start site) of an update, index 1 + k = (forward, backward) uniform of
  *     the link between the sites k and k + 1. */
 enum { MLMCPI_STREAM_INIT = 1, MLMCPI_STREAM_HMC_MOMENTUM = 2, MLMCPI_STREAM_HMC_ACCEPT = 3,

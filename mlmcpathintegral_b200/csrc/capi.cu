@@ -2383,27 +2383,43 @@ int mlmcpi_mlmc_evaluate(mlmcpi_mlmc *m) {
   mlmcpi_ctx *ctx = m->ctx;
   const int L = m->L, B = m->B, k_max = m->prm.n_autocorr_window;
   int rc;
-  // cost_per_sample of the samplers and two-level steps (measured in the reference's
-  // constructors with 10000 draws each; here a short CUDA-event measurement, usec per chain-sample)
+  // cost_per_sample of the samplers and two-level steps (measured in the reference's constructors with 10000
+  // draws each, sampler/sampler.hh cost_per_sample): CUDA-event measurement, usec per chain-sample.  One untimed
+  // draw first (work buffers, library handles), then batches of 8, 32, 128 draws until a batch lasts 10 ms --
+  // with B chains per draw that is 8 B ... 128 B chain-samples per figure.
   for (int l = 0; l + 1 < L; ++l) {
-    if ((rc = mlmcpi_sampler_cost(m->coarse_sampler[l], 4, &m->cost_sampler[l])))
+    double unused;
+    if ((rc = mlmcpi_sampler_cost(m->coarse_sampler[l], 1, &unused)))
       return rc;
+    for (int n = 8; n <= 128; n *= 4) {
+      if ((rc = mlmcpi_sampler_cost(m->coarse_sampler[l], n, &m->cost_sampler[l])))
+        return rc;
+      if (m->cost_sampler[l] * n * B >= 1.0e4)
+        break;
+    }
     cudaEvent_t e0, e1;
     MLMCPI_CUDA(cudaEventCreate(&e0));
     MLMCPI_CUDA(cudaEventCreate(&e1));
-    MLMCPI_CUDA(cudaEventRecord(e0, ctx->stream));
-    for (int k = 0; k < 4; ++k)
-      if ((rc = twolevel_step_impl(ctx, &m->model[l], &m->model[l + 1], m->phi_coarse_state[l + 1],
-                                   m->phi_state[l], m->Sf[l], m->Scond[l], B, m->chain0,
-                                   (m->draw++ << 12) | ((uint64_t)l << 8) | 0xfd, nullptr, m->acc, nullptr)))
-        return rc;
-    MLMCPI_CUDA(cudaEventRecord(e1, ctx->stream));
-    MLMCPI_CUDA(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    MLMCPI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    for (int n = 1; n <= 128; n = (n == 1) ? 8 : 4 * n) { // n == 1: the untimed first step
+      MLMCPI_CUDA(cudaEventRecord(e0, ctx->stream));
+      for (int k = 0; k < n; ++k)
+        if ((rc = twolevel_step_impl(ctx, &m->model[l], &m->model[l + 1], m->phi_coarse_state[l + 1],
+                                     m->phi_state[l], m->Sf[l], m->Scond[l], B, m->chain0,
+                                     (m->draw++ << 12) | ((uint64_t)l << 8) | 0xfd, nullptr, m->acc, nullptr))) {
+          cudaEventDestroy(e0);
+          cudaEventDestroy(e1);
+          return rc;
+        }
+      MLMCPI_CUDA(cudaEventRecord(e1, ctx->stream));
+      MLMCPI_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      MLMCPI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      m->cost_twolevel[l] = 1.0e3 * ms / ((double)n * B);
+      if (n > 1 && ms >= 10.f)
+        break;
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    m->cost_twolevel[l] = 1.0e3 * ms / (4.0 * B);
   }
   if (ctx->world > 1) { // every process must allocate samples with the same costs: mean over the processes
     std::vector<double> c(m->cost_sampler.begin(), m->cost_sampler.end());

@@ -735,51 +735,97 @@ __global__ void __launch_bounds__(MT, (K >= 8 ? 2 : (MT <= 128 ? MLMCPI_LFK_BLOC
 // colours: 0 {mu=0, j even}, 1 {mu=0, j odd}, 2 {mu=1, i even}, 3 {mu=1, i odd}.
 // Grid: x = strips of a lattice row, y = the rows that hold links of this colour, z = chains
 // (folded when B exceeds the grid limit) -- no integer division anywhere.
-template <bool HEATBATH>
-__global__ void sweep_colour_kernel(SW sw, int colour, double *x, int B, uint32_t chain0,
-                                    uint64_t seed, uint64_t draw) {
+// (overrelaxation; the heat bath is heatbath_pair_kernel below)
+__global__ void sweep_colour_kernel(SW sw, int colour, double *x, int B) {
   const int Mt = sw.Mt, Mx = sw.Mx;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   int i, j, mu;
-  bool inside;
   if (colour < 2) {
     mu = 0;
     i = k;
     j = 2 * blockIdx.y + colour;
-    inside = (i < Mt);
   } else {
     mu = 1;
     i = 2 * k + (colour - 2);
     j = blockIdx.y;
-    inside = (i < Mt);
   }
-  const unsigned wmask = __ballot_sync(0xffffffffu, inside);
-  if (!inside)
+  if (i >= Mt)
     return;
   const size_t ell = 2 * ((size_t)Mt * j + i) + mu;
   for (int chain = blockIdx.z; chain < B; chain += gridDim.z) {
     double *xc = x + (size_t)chain * 2 * Mt * Mx;
-    if (HEATBATH) { // qft/quenchedschwingeraction.cc:46-54
-      double theta_p, theta_m;
-      staple_angles(xc, Mt, Mx, i, j, mu, theta_p, theta_m);
-      Rng rg = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, (uint32_t)ell);
-      const double v = expcos_draw(rg, sw.beta, theta_p, theta_m, sw.envelope);
-      __syncwarp(wmask); // reconverge after the rejection loop: one coalesced store
-      xc[ell] = v;
-    } else { // qft/quenchedschwingeraction.cc:57-65
-      // theta <- mod_2pi(theta_+ + theta_- - theta).  The reference reduces both staple angles
-      // to [-pi, pi) first; the outer mod_2pi makes those two reductions redundant modulo 2 pi
-      // (the result differs by rounding in the last bits only), so they are skipped
-      const int ip = wrap_inc(i, Mt), im = wrap_dec(i, Mt), jp = wrap_inc(j, Mx), jm = wrap_dec(j, Mx);
-      double sp, sm;
-      if (mu == 0) {
-        sp = TH(xc, i, jp, 0) + TH(xc, i, j, 1) - TH(xc, ip, j, 1);
-        sm = TH(xc, i, jm, 0) + TH(xc, ip, jm, 1) - TH(xc, i, jm, 1);
-      } else {
-        sp = TH(xc, i, j, 0) + TH(xc, ip, j, 1) - TH(xc, i, jp, 0);
-        sm = TH(xc, im, jp, 0) + TH(xc, im, j, 1) - TH(xc, im, j, 0);
+    // qft/quenchedschwingeraction.cc:57-65: theta <- mod_2pi(theta_+ + theta_- - theta).  The reference reduces both
+    // staple angles to [-pi, pi) first; the outer mod_2pi makes those two reductions redundant modulo 2 pi
+    // (the result differs by rounding in the last bits only), so they are skipped
+    const int ip = wrap_inc(i, Mt), im = wrap_dec(i, Mt), jp = wrap_inc(j, Mx), jm = wrap_dec(j, Mx);
+    double sp, sm;
+    if (mu == 0) {
+      sp = TH(xc, i, jp, 0) + TH(xc, i, j, 1) - TH(xc, ip, j, 1);
+      sm = TH(xc, i, jm, 0) + TH(xc, ip, jm, 1) - TH(xc, i, jm, 1);
+    } else {
+      sp = TH(xc, i, j, 0) + TH(xc, ip, j, 1) - TH(xc, i, jp, 0);
+      sm = TH(xc, im, jp, 0) + TH(xc, im, j, 1) - TH(xc, im, j, 0);
+    }
+    xc[ell] = mod_2pi((sp + sm) - xc[ell]);
+  }
+}
+
+// Heat-bath sweep of one colour with PAIRED variates (stream convention: include/mlmcpi.h).  The links of a colour in a
+// lattice row are numbered n = 0, 1, ... (mu = 0: n = i; mu = 1: n = i / 2) and updated in pairs (2p, 2p + 1) by one
+// thread: ONE Philox block of the even link -- a normal pair and a uniform pair -- serves the first ExpCos attempt of both
+// (z0, u0 for the even, z1, u1 for the odd link); further attempts (3 % of the links at tau = 256, 0.3 % at 2048)
+// continue on the link's own stream: calls 2, 3, ... for the even link, calls 0, 1, ... for the odd one.  Half the
+// Philox rounds and Box-Muller transforms of a block per link; a last link without a partner behaves like an even one.
+__device__ __forceinline__ void heatbath_pair_role(int i, int mu, int &first, int &i_first) {
+  const int n = (mu == 0) ? i : (i >> 1);
+  first = ((n & 1) == 0);
+  i_first = first ? i : ((mu == 0) ? i - 1 : i - 2);
+}
+__global__ void heatbath_pair_kernel(SW sw, int colour, double *x, int B, uint32_t chain0, uint64_t seed,
+                                     uint64_t draw) {
+  const int Mt = sw.Mt, Mx = sw.Mx;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x; // pair index in the row
+  int iA, iB, j, mu, cnt;
+  if (colour < 2) {
+    mu = 0;
+    j = 2 * blockIdx.y + colour;
+    cnt = Mt;
+    iA = 2 * p;
+    iB = 2 * p + 1;
+  } else {
+    mu = 1;
+    j = blockIdx.y;
+    cnt = Mt / 2;
+    iA = 4 * p + (colour - 2);
+    iB = iA + 2;
+  }
+  const bool inside = 2 * p < cnt;
+  const bool hasB = 2 * p + 1 < cnt;
+  const unsigned wmask = __ballot_sync(0xffffffffu, inside);
+  if (!inside)
+    return;
+  const size_t ellA = 2 * ((size_t)Mt * j + iA) + mu, ellB = 2 * ((size_t)Mt * j + iB) + mu;
+  for (int chain = blockIdx.z; chain < B; chain += gridDim.z) {
+    double *xc = x + (size_t)chain * 2 * Mt * Mx;
+    const uint32_t gchain = chain0 + (uint32_t)chain;
+    Rng rA = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, gchain, (uint32_t)ellA);
+    double z0, z1, u0, u1;
+    rng_normal2(rA, z0, z1);
+    rng_uniform2(rA, u0, u1);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      double v = 0.0;
+      if (h == 0 || hasB) { // qft/quenchedschwingeraction.cc:46-54
+        double theta_p, theta_m;
+        staple_angles(xc, Mt, Mx, h ? iB : iA, j, mu, theta_p, theta_m);
+        Rng r = rA;
+        if (h)
+          r = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, gchain, (uint32_t)ellB);
+        v = expcos_draw(r, sw.beta, theta_p, theta_m, sw.envelope, nullptr, true, h ? z1 : z0, h ? u1 : u0);
       }
-      xc[ell] = mod_2pi((sp + sm) - xc[ell]);
+      __syncwarp(wmask); // reconverge after the rejection loop: one coalesced store
+      if (h == 0 || hasB)
+        xc[h ? ellB : ellA] = v;
     }
   }
 }
@@ -806,9 +852,18 @@ __global__ void dof_update_kernel(SW sw, int ell, double *x, int B, uint32_t cha
     theta_p = mod_2pi(TH(xc, i, j, 0) + TH(xc, ip, j, 1) - TH(xc, i, jp, 0));
     theta_m = mod_2pi(TH(xc, im, jp, 0) + TH(xc, im, j, 1) - TH(xc, im, j, 0));
   }
-  if (HEATBATH) {
-    Rng rg = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, chain0 + (uint32_t)chain, (uint32_t)ell);
-    xc[ell] = expcos_draw(rg, sw.beta, theta_p, theta_m, sw.envelope);
+  if (HEATBATH) { // the paired variates of heatbath_pair_kernel: a single-link call reproduces the sweep's draw
+    int first, i_first;
+    heatbath_pair_role(i, mu, first, i_first);
+    const uint32_t gchain = chain0 + (uint32_t)chain;
+    Rng rA = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, gchain, (uint32_t)(2 * (Mt * j + i_first) + mu));
+    double z0, z1, u0, u1;
+    rng_normal2(rA, z0, z1);
+    rng_uniform2(rA, u0, u1);
+    Rng rg = rA;
+    if (!first)
+      rg = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, gchain, (uint32_t)ell);
+    xc[ell] = expcos_draw(rg, sw.beta, theta_p, theta_m, sw.envelope, nullptr, true, first ? z0 : z1, first ? u0 : u1);
   } else {
     xc[ell] = mod_2pi(theta_p + theta_m - xc[ell]);
   }
@@ -824,7 +879,7 @@ __global__ void dof_update_kernel(SW sw, int ell, double *x, int B, uint32_t cha
 // theta_0 rows in a 3-slot ring.  One row below and two rows above the chunk are read in addition
 // (theta_0 of the first and of the row after the last are recomputed, not stored), so the traffic is
 // 16 (1 + 3/R) B read + 16 B written per site; the update of every link is the same expression
-// on the same operands as in sweep_colour_kernel<false>, i.e. the result is bit-identical.
+// on the same operands as in sweep_colour_kernel, i.e. the result is bit-identical.
 __global__ void __launch_bounds__(1024)
     overrelax_rowpipe_kernel(SW sw, const double *__restrict__ x_in, double *__restrict__ x_out, int R,
                              int chunks) {
@@ -1821,14 +1876,15 @@ static int sweep(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, bool 
     const int colour = ctx->sweep_reverse ? 3 - pass : pass;
     const int per_row = (colour < 2) ? sw.Mt : sw.Mt / 2; // links of this colour in one row
     const int rows = (colour < 2) ? sw.Mx / 2 : sw.Mx;
-    const int threads = std::min(heatbath ? 128 : 256, ((per_row + 31) / 32) * 32);
-    const dim3 grid(cdiv(per_row, threads), rows, std::min(B, 32768));
+    const int work = heatbath ? (per_row + 1) / 2 : per_row; // the heat bath updates the links in pairs
+    const int threads = std::min(heatbath ? 128 : 256, ((work + 31) / 32) * 32);
+    const dim3 grid(cdiv(work, threads), rows, std::min(B, 32768));
     if (rows > 65535)
       return ctx_fail(ctx, MLMCPI_EINVAL, "lattice too large for the sweep kernel");
     if (heatbath)
-      sweep_colour_kernel<true><<<grid, threads, 0, ctx->stream>>>(sw, colour, x, B, chain0, ctx->seed, draw);
+      heatbath_pair_kernel<<<grid, threads, 0, ctx->stream>>>(sw, colour, x, B, chain0, ctx->seed, draw);
     else
-      sweep_colour_kernel<false><<<grid, threads, 0, ctx->stream>>>(sw, colour, x, B, 0, 0, 0);
+      sweep_colour_kernel<<<grid, threads, 0, ctx->stream>>>(sw, colour, x, B);
     MLMCPI_LAUNCHED("schwinger::sweep_colour");
   }
   return 0;

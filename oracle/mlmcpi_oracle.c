@@ -1586,7 +1586,22 @@ static void heatbath_update(const orc_model *m, uint64_t seed, uint64_t draw,
     double theta_p, theta_m;
     orc_link_lin2cart(Mt, Mx, ell, &i, &j, &mu);
     staple_angles(x, Mt, Mx, i, j, mu, &theta_p, &theta_m);
-    x[ell] = orc_expcos_draw(&r, m->beta, theta_p, theta_m);
+    /* paired variates (include/mlmcpi.h, stream convention): the links of a colour in a row are numbered
+     * n = i (mu = 0) or i / 2 (mu = 1); the block of the even link of the pair (2p, 2p + 1) gives the first
+     * attempt of both, further attempts come from the link's own stream (even link: from call 2) */
+    {
+      const int n = (mu == 0) ? i : i / 2;
+      const int is_first = ((n & 1) == 0);
+      const int i_first = is_first ? i : (mu == 0 ? i - 1 : i - 2);
+      orc_rng rA;
+      double z[2], u[2], first[2];
+      orc_rng_init(&rA, seed, ORC_STREAM_HEATBATH, draw, chain, (uint32_t)(2 * (Mt * j + i_first) + mu));
+      orc_rng_normal2(&rA, &z[0], &z[1]);
+      orc_rng_uniform2(&rA, &u[0], &u[1]);
+      first[0] = z[is_first ? 0 : 1];
+      first[1] = u[is_first ? 0 : 1];
+      x[ell] = expcos_draw_impl(is_first ? &rA : &r, m->beta, theta_p, theta_m, first);
+    }
     return;
   }
   }
