@@ -670,7 +670,8 @@ def gpu_main(a):
                            % (100 * acc_all, B, n * 8 / 2 ** 20),
                "api": "mlmcpi_sampler_draw_host_async + mlmcpi_sampler_wait_host: chains resident on the device, the new "
                       "states of the accepted chains and the QoI of all chains handed back to pinned host buffers every "
-                      "step, the copy of step k overlapped with the draw of step k+1",
+                      "step by the copy engine (one copy per run of accepted chains, issued when the step's accept flags "
+                      "have reached the host), the copies of step k overlapped with the draw of step k+1",
                "inputs": "none per step: a sampler's only input is its own previous state (resident) and the Philox "
                          "counters; the per-step host traffic is the OUTPUT, as in Sampler::draw(state)",
                "limited_by": "the host link: %.2f GiB of states per step and GPU" % (B * n * 8 * acc_all / 2 ** 30),

@@ -63,6 +63,8 @@ enum { MLMCPI_QOI_X2 = 0, MLMCPI_QOI_ROTOR_CHI = 1, MLMCPI_QOI_SCHWINGER_CHI = 2
  *     (mu = 1), are updated in pairs (2p, 2p + 1): calls 0, 1 of the stream of the EVEN link give (z0, u0), (z1, u1),
  *     the first ExpCos attempt of the even and of the odd link; further attempts continue on the link's own stream
  *     (even link from call 2, odd link from call 0).  mlmcpi_dof_update follows the same map;
+ *   HEATBATH, Gaussian free field: the vertices 2q and 2q + 1 take the two Box-Muller normals of ONE block,
+ *     index 2q: z0 the even, z1 the odd vertex (sweeps and mlmcpi_dof_update alike);
  *   CLUSTER: index 0 = (reflection angle, start site) of an update, index 1 + k = (forward, backward) uniform of
  *     the link between the sites k and k + 1. */
 enum { MLMCPI_STREAM_INIT = 1, MLMCPI_STREAM_HMC_MOMENTUM = 2, MLMCPI_STREAM_HMC_ACCEPT = 3,
@@ -167,13 +169,19 @@ int mlmcpi_rank(const mlmcpi_ctx *ctx);
  *   decide on tau_int of a device Statistics object (a pack kernel, a device-to-host copy, a stream
  *   synchronisation and, with several processes, an all-reduce).  The reference asks at every sample; here an
  *   answer is reused for a number of calls that doubles from 1 up to this value (default 16; 1 = every call).
+ * MLMCPI_OPT_HOST_COPY_ENGINE: how mlmcpi_sampler_draw_host_async hands the accepted chains' states to a PINNED host
+ *   buffer.  1 (default) = the copy engine: the step's accept flags go to the host, the next call (or
+ *   mlmcpi_sampler_wait_host) issues one copy per run of accepted chains -- it blocks until the previous step's draw has
+ *   finished -- 54 GB/s on the host link; 0 = a kernel stores the accepted rows straight into the (device-addressable)
+ *   buffer, no host round trip, 38 GB/s.  Same bytes in the buffer.
  * MLMCPI_OPT_GFF_COARSE_SMOOTHING: 1 (default) = the coarse levels a sampler / multilevel driver builds
  *   for a GFF carry the reference's Gibbs-smoothed action Q_hat (gffaction.hh:201-208), whatever sampler
  *   runs on them; 0 = the plain 5-point action on every level (consistent with a heat-bath / HMC coarse
  *   sampler, but the two-level acceptance is ~ 0 beyond 16 x 16). */
 enum { MLMCPI_OPT_EXPCOS_ENVELOPE = 1, MLMCPI_OPT_LEAPFROG_VARIANT = 2, MLMCPI_OPT_LEAPFROG_ROWS = 3,
        MLMCPI_OPT_LEAPFROG_FUSE = 4, MLMCPI_OPT_SWEEP_REVERSE = 5, MLMCPI_OPT_OVERRELAX_ONE_PASS = 6,
-       MLMCPI_OPT_FUSED_QM_HIERARCHY = 7, MLMCPI_OPT_GFF_COARSE_SMOOTHING = 8, MLMCPI_OPT_CASCADE_CACHE = 9, MLMCPI_OPT_TAU_REFRESH = 10 };
+       MLMCPI_OPT_FUSED_QM_HIERARCHY = 7, MLMCPI_OPT_GFF_COARSE_SMOOTHING = 8, MLMCPI_OPT_CASCADE_CACHE = 9, MLMCPI_OPT_TAU_REFRESH = 10,
+       MLMCPI_OPT_HOST_COPY_ENGINE = 11 };
 int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value);
 /* number of kernels this context has launched so far */
 uint64_t mlmcpi_launch_count(const mlmcpi_ctx *ctx);

@@ -19,6 +19,7 @@ SAMPLER_HMC, SAMPLER_HEATBATH, SAMPLER_CLUSTER, SAMPLER_EXACT = 0, 1, 2, 3
 E_INVAL, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4
 OPT_EXPCOS_ENVELOPE, OPT_LEAPFROG_VARIANT, OPT_LEAPFROG_ROWS, OPT_LEAPFROG_FUSE = 1, 2, 3, 4
 OPT_SWEEP_REVERSE, OPT_OVERRELAX_ONE_PASS, OPT_FUSED_QM_HIERARCHY, OPT_GFF_COARSE_SMOOTHING, OPT_CASCADE_CACHE, OPT_TAU_REFRESH = 5, 6, 7, 8, 9, 10
+OPT_HOST_COPY_ENGINE = 11
 
 
 class Model(C.Structure):

@@ -238,6 +238,10 @@ int mlmcpi_set_option(mlmcpi_ctx *ctx, int option, int value) {
     ctx->leapfrog_rows = value;
     return 0;
   }
+  if (option == MLMCPI_OPT_HOST_COPY_ENGINE && (value == 0 || value == 1)) {
+    ctx->host_copy_engine = value;
+    return 0;
+  }
   if (option == MLMCPI_OPT_TAU_REFRESH && value >= 1 && value <= 1024) {
     ctx->tau_refresh = value;
     return 0;
@@ -1018,6 +1022,14 @@ struct mlmcpi_sampler {
   int32_t *stage_acc = nullptr;
   bool host_copy_pending = false;
   cudaEvent_t ev[9] = {};
+  // copy-engine hand-over of mlmcpi_sampler_draw_host_async (MLMCPI_OPT_HOST_COPY_ENGINE): two snapshot buffers, the
+  // accept flags of a step in pinned host memory, one cudaMemcpyAsync per run of accepted chains
+  double *ce_stage[2] = {nullptr, nullptr};
+  int32_t *ce_flags[2] = {nullptr, nullptr};
+  cudaEvent_t ce_ev_flags[2] = {}, ce_ev_copied[2] = {};
+  bool ce_used[2] = {false, false}, ce_pending = false;
+  int ce_cur = 0, ce_pending_stage = 0;
+  double *ce_target = nullptr;
   int32_t *acc = nullptr, *acc_step = nullptr;          // [B]
   unsigned long long *counters = nullptr;               // [L] accepted chains per level
   uint64_t n_draws = 0;
@@ -1397,6 +1409,7 @@ __global__ void cascade_commit_kernel(int B, const int32_t *acc, double *S_old, 
 // removes two restrictions, four full-lattice reductions, the conditioned-action pass of level 1 and the
 // level >= 1 commits of rejected cascades (2.0 of 9.4 ms at 512^2 x 512 chains); the draws are the same,
 // bit for bit (tests/test_gpu_parity.py::test_hierarchical_draw_equals_explicit_cascade).
+static bool cascade_hmc_trial(const mlmcpi_sampler *s);
 static int cascade_draw_cached(mlmcpi_sampler *s) {
   mlmcpi_ctx *ctx = s->ctx;
   const int L = s->L, B = s->B;
@@ -1422,13 +1435,27 @@ static int cascade_draw_cached(mlmcpi_sampler *s) {
     if ((rc = mlmcpi_cond_action(ctx, &s->model[0], s->state[0], B, s->Scond0)))
       return rc;
   }
-  // coarsest level: tentative HMC step (hmcsampler.cc:21-69)
   const double *coarse_trial = nullptr;
-  if ((rc = schwinger::hmc_trial(ctx, &s->model[L - 1], s->prm.nt, s->prm.dt, s->state[L - 1], B, chain0,
-                                 level_draw(s->draw, L - 1, 0), S_old(L - 1), Sp(L - 1, 0), s->acc, &coarse_trial)))
-    return rc;
-  const double *const hmc_fin = coarse_trial; // (the trajectory's end state, in an HMC work buffer)
-  s->work[0] += (double)B * (s->prm.nt + 1) * n_sites(s->model[L - 1]);
+  const bool hmc_trial = cascade_hmc_trial(s);
+  if (hmc_trial) { // coarsest level: tentative HMC step (hmcsampler.cc:21-69)
+    if ((rc = schwinger::hmc_trial(ctx, &s->model[L - 1], s->prm.nt, s->prm.dt, s->state[L - 1], B, chain0,
+                                   level_draw(s->draw, L - 1, 0), S_old(L - 1), Sp(L - 1, 0), s->acc, &coarse_trial)))
+      return rc;
+    s->work[0] += (double)B * (s->prm.nt + 1) * n_sites(s->model[L - 1]);
+  } else { // any other coarse sampler advances a COPY of the coarsest state (the sampler works on s->state[L-1])
+    double *keep = s->state[L - 1], *trialC = s->trial[L - 1];
+    if ((rc = mlmcpi_copy(ctx, trialC, keep, (size_t)mlmcpi_sample_size(&s->model[L - 1]) * B)))
+      return rc;
+    s->state[L - 1] = trialC;
+    rc = coarse_draw(s, 0, B);
+    s->state[L - 1] = keep;
+    if (rc)
+      return rc;
+    if ((rc = mlmcpi_action(ctx, &s->model[L - 1], trialC, B, Sp(L - 1, 0))))
+      return rc;
+    coarse_trial = trialC;
+  }
+  const double *const hmc_fin = coarse_trial; // (the trajectory's end state in an HMC work buffer / the advanced copy)
   count_accept_kernel<<<std::min(cdiv(B, 256), 64), 256, 0, ctx->stream>>>(B, s->acc, s->counters + (L - 1));
   MLMCPI_LAUNCHED("count_accept");
   for (int l = L - 2; l >= 0; --l) {
@@ -1460,7 +1487,7 @@ static int cascade_draw_cached(mlmcpi_sampler *s) {
     // this copy stands in for, does: quenchedschwingeraction.cc:152-195)
     const double *src = (l == L - 1) ? hmc_fin : s->trial[l];
     if (src != s->state[l] && (rc = launch_masked_copy(ctx, s->state[l], src, (size_t)mlmcpi_sample_size(&s->model[l]),
-                                                       B, s->acc, l == L - 1)))
+                                                       B, s->acc, hmc_trial && l == L - 1)))
       return rc;
     cascade_commit_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, s->acc, S_old(l), Sp(l, 0),
                                                                 (l <= L - 2) ? Scond_l(l) : nullptr, Sp(l, 1));
@@ -1521,11 +1548,19 @@ static int multilevel_draw(mlmcpi_sampler *s) {
   return 0;
 }
 
-// cascade_draw_cached serves the hierarchical sampler of the quenched Schwinger model with one HMC
-// trajectory per draw on the coarsest level (BASELINE config C4 / C5)
+// cascade_draw_cached serves the hierarchical samplers of the two field theories with one coarse draw per cascade:
+// the quenched Schwinger model with one HMC trajectory on the coarsest level (BASELINE config C4 / C5: the trajectory
+// is run tentatively, schwinger::hmc_trial) and, through a copy of the coarsest state that the coarse sampler then
+// advances, every other coarse sampler of the Schwinger model and of the GFF (C3: one dense Q_hat evaluation per level
+// and draw instead of three).  The 1-D models have their own one-kernel cascade (fused_qm_hierarchy).
+static bool cascade_hmc_trial(const mlmcpi_sampler *s) {
+  return s->model[0].model == MLMCPI_SCHWINGER && s->prm.kind == MLMCPI_SAMPLER_HMC && s->prm.nt >= 1;
+}
 static bool cascade_cache_applies(const mlmcpi_sampler *s) {
-  return s->ctx->cascade_cache && s->L >= 2 && !s->prm.multilevel && s->model[0].model == MLMCPI_SCHWINGER &&
-         s->prm.kind == MLMCPI_SAMPLER_HMC && std::max(1, s->prm.n_rep) == 1 && s->prm.nt >= 1;
+  const int model = s->model[0].model;
+  return s->ctx->cascade_cache && s->L >= 2 && !s->prm.multilevel && std::max(1, s->prm.n_rep) == 1 &&
+         (cascade_hmc_trial(s) || ((model == MLMCPI_SCHWINGER || model == MLMCPI_GFF) &&
+                                   (s->prm.kind != MLMCPI_SAMPLER_HMC || s->prm.nt >= 1)));
 }
 
 extern "C" {
@@ -1547,6 +1582,14 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
   s->chain0 = chain0;
   s->L = prm->n_levels;
   s->model.push_back(*fine);
+  // the GFF fill-in is an independent conditional draw only under CoarsenRotate (qft/gffconditionedfineaction.hh:
+  // 20-37: all four neighbours of a fine-only vertex are coarse); any other coarsening would read unfilled neighbours
+  if (s->L > 1 && fine->model == MLMCPI_GFF &&
+      (prm->ctype != MLMCPI_COARSEN_ROTATE || fine->coarsening != MLMCPI_COARSEN_ROTATE)) {
+    delete s;
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED,
+                    "a GFF hierarchy needs coarsening = rotate (in the sampler parameters and in the fine-level model)");
+  }
   // HierarchicalSampler constructor, sampler/hierarchicalsampler.cc:19-29
   for (int l = 0; l + 1 < s->L; ++l) {
     mlmcpi_model c;
@@ -1587,7 +1630,7 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
   cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long) * s->L, ctx->stream);
   if (cascade_cache_applies(s)) {
     s->trial.assign(s->L, nullptr);
-    for (int l = 1; l + 2 <= s->L && ok; ++l)
+    for (int l = 1; l + (cascade_hmc_trial(s) ? 2 : 1) <= s->L && ok; ++l)
       ok = mlmcpi_alloc(ctx, (size_t)mlmcpi_sample_size(&s->model[l]) * B, &s->trial[l]) == 0;
     ok = ok && mlmcpi_alloc(ctx, (size_t)s->L * B, &s->Scond_lvl) == 0 &&
          mlmcpi_alloc(ctx, (size_t)s->L * 2 * B, &s->Sprime) == 0;
@@ -1703,6 +1746,15 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
     cudaFree(s->stage_q);
   if (s->stage_acc)
     cudaFree(s->stage_acc);
+  for (int b = 0; b < 2; ++b) {
+    if (s->ce_stage[b])
+      cudaFree(s->ce_stage[b]);
+    if (s->ce_flags[b]) {
+      cudaFreeHost(s->ce_flags[b]);
+      cudaEventDestroy(s->ce_ev_flags[b]);
+      cudaEventDestroy(s->ce_ev_copied[b]);
+    }
+  }
   for (double *d : s->trial)
     if (d)
       cudaFree(d);
@@ -1872,11 +1924,85 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
 // complete after the next call of this function or after mlmcpi_sampler_wait_host.  (The caller alternates
 // two pinned host buffers.)  Per step the device pays the draw and one device-to-device snapshot; the host
 // link pays sample_size * B * 8 bytes.
+// the copies of the previous step's hand-over: needs that step's accept flags on the host, i.e. blocks until its draw
+// has finished; one cudaMemcpyAsync per run of consecutive accepted chains on the copy stream
+static int ce_issue(mlmcpi_sampler *s) {
+  if (!s->ce_pending)
+    return 0;
+  mlmcpi_ctx *ctx = s->ctx;
+  const int b = s->ce_pending_stage;
+  const size_t nd = (size_t)mlmcpi_sample_size(&s->model[0]);
+  MLMCPI_CUDA(cudaEventSynchronize(s->ce_ev_flags[b]));
+  const int32_t *acc = s->ce_flags[b];
+  for (int c = 0; c < s->B;) {
+    if (!acc[c]) {
+      ++c;
+      continue;
+    }
+    int c1 = c;
+    while (c1 < s->B && acc[c1])
+      ++c1;
+    MLMCPI_CUDA(cudaMemcpyAsync(s->ce_target + (size_t)c * nd, s->ce_stage[b] + (size_t)c * nd,
+                                (size_t)(c1 - c) * nd * sizeof(double), cudaMemcpyDeviceToHost, s->copy_stream));
+    c = c1;
+  }
+  MLMCPI_CUDA(cudaEventRecord(s->ce_ev_copied[b], s->copy_stream));
+  s->ce_used[b] = true;
+  s->ce_pending = false;
+  return 0;
+}
+
 int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, double *h_x_out) {
   DeviceGuard device_guard(s ? s->ctx : nullptr);
   mlmcpi_ctx *ctx = s->ctx;
   const size_t n = (size_t)mlmcpi_sample_size(&s->model[0]) * s->B;
   int rc;
+  if ((rc = ce_issue(s)))
+    return rc;
+  {
+    cudaPointerAttributes attr;
+    const bool pinned = h_x_out && cudaPointerGetAttributes(&attr, h_x_out) == cudaSuccess &&
+                        attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned && ctx->host_copy_engine) {
+      // Copy-engine hand-over (default): 54 GB/s over the host link against 38 GB/s for stores from the SMs.  The
+      // accept flags of this step go to pinned host memory; the NEXT call (or mlmcpi_sampler_wait_host) reads them
+      // and issues one copy per run of accepted chains, which then overlaps the draw that call enqueues.  Two
+      // snapshot buffers, so that the snapshot of step k + 1 does not wait for the copies of step k.
+      if (!s->copy_stream) {
+        MLMCPI_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 9; ++k)
+          MLMCPI_CUDA(cudaEventCreateWithFlags(&s->ev[k], cudaEventDisableTiming));
+      }
+      for (int b = 0; b < 2; ++b)
+        if (!s->ce_stage[b]) {
+          if ((rc = mlmcpi_alloc(ctx, n, &s->ce_stage[b])))
+            return rc;
+          MLMCPI_CUDA(cudaMallocHost((void **)&s->ce_flags[b], sizeof(int32_t) * s->B));
+          MLMCPI_CUDA(cudaEventCreateWithFlags(&s->ce_ev_flags[b], cudaEventDisableTiming));
+          MLMCPI_CUDA(cudaEventCreateWithFlags(&s->ce_ev_copied[b], cudaEventDisableTiming));
+        }
+      if ((rc = mlmcpi_sampler_draw(s, nullptr, nullptr)))
+        return rc;
+      if (h_q) {
+        if ((rc = mlmcpi_qoi(ctx, &s->model[0], qoi, s->state[0], s->B, s->q, nullptr)))
+          return rc;
+        MLMCPI_CUDA(cudaMemcpyAsync(h_q, s->q, sizeof(double) * s->B, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      const int b = s->ce_cur;
+      s->ce_cur ^= 1;
+      if (s->ce_used[b]) // the copies that read this snapshot buffer two steps ago
+        MLMCPI_CUDA(cudaStreamWaitEvent(ctx->stream, s->ce_ev_copied[b], 0));
+      if ((rc = launch_masked_copy(ctx, s->ce_stage[b], s->state[0], n / s->B, s->B, s->acc)))
+        return rc;
+      MLMCPI_CUDA(cudaMemcpyAsync(s->ce_flags[b], s->acc, sizeof(int32_t) * s->B, cudaMemcpyDeviceToHost, ctx->stream));
+      MLMCPI_CUDA(cudaEventRecord(s->ce_ev_flags[b], ctx->stream));
+      s->ce_pending = true;
+      s->ce_pending_stage = b;
+      s->ce_target = h_x_out;
+      return 0;
+    }
+  }
   if (!s->copy_stream) {
     MLMCPI_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     for (int k = 0; k < 9; ++k)
@@ -1942,6 +2068,9 @@ int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, doub
 int mlmcpi_sampler_wait_host(mlmcpi_sampler *s) {
   DeviceGuard device_guard(s ? s->ctx : nullptr);
   mlmcpi_ctx *ctx = s->ctx;
+  int rc;
+  if ((rc = ce_issue(s)))
+    return rc;
   if (s->copy_stream)
     MLMCPI_CUDA(cudaStreamSynchronize(s->copy_stream));
   MLMCPI_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -2268,6 +2397,12 @@ int mlmcpi_mlmc_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcpi_m
   if (m->prm.n_autocorr_window < 1)
     m->prm.n_autocorr_window = 20;
   const int L = m->L;
+  if (L > 1 && fine->model == MLMCPI_GFF &&
+      (prm->sampler.ctype != MLMCPI_COARSEN_ROTATE || fine->coarsening != MLMCPI_COARSEN_ROTATE)) {
+    delete m;
+    return ctx_fail(ctx, MLMCPI_EUNSUPPORTED,
+                    "a GFF hierarchy needs coarsening = rotate (in the sampler parameters and in the fine-level model)");
+  }
   m->model.push_back(*fine);
   int rc = 0;
   for (int l = 0; l + 1 < L && !rc; ++l) {

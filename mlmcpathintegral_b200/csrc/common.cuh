@@ -33,6 +33,7 @@ struct mlmcpi_ctx {
   int sweep_reverse = 0;    // MLMCPI_OPT_SWEEP_REVERSE: colours visited in descending order
   int overrelax_one_pass = 1; // MLMCPI_OPT_OVERRELAX_ONE_PASS: all colours of a Schwinger OR sweep in one HBM pass
   int fused_qm_hierarchy = 1; // MLMCPI_OPT_FUSED_QM_HIERARCHY: 1-D hierarchical draw in one kernel
+  int host_copy_engine = 1; // MLMCPI_OPT_HOST_COPY_ENGINE: accepted states to pinned host memory by the copy engine
   int tau_refresh = 16;  // MLMCPI_OPT_TAU_REFRESH: calls a tau_int answer is reused for (host decisions of the level walks)
   int cascade_cache = 1; // MLMCPI_OPT_CASCADE_CACHE: Schwinger / HMC hierarchy without the per-draw restriction chain
   int gff_coarse_smoothing = 1; // MLMCPI_OPT_GFF_COARSE_SMOOTHING: coarse GFF levels carry Q_hat (reference)

@@ -300,14 +300,24 @@ __global__ void leapfrog_kernel(GF g, double dt_p, double dt_x, const double *x_
 // the update of one vertex given the sum Delta over its four neighbours: heat bath
 // (qft/gffaction.cc:32-42) or overrelaxation (:68-79); one function for every sweep kernel, so that they
 // produce the same bits
+// Heat-bath variates (stream convention, include/mlmcpi.h): the vertices ell = 2q and 2q + 1 share ONE Philox block,
+// index 2q of the HEATBATH stream: its two Box-Muller normals are z0 for the even and z1 for the odd vertex.  The
+// one-pass kernel, whose threads own such a pair in every row, draws the block once per pair.
+__device__ __forceinline__ void heatbath_pair_normals(uint64_t seed, uint64_t draw, uint32_t gchain, int ell_even,
+                                                      double &z0, double &z1) {
+  Rng r = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, gchain, ell_even);
+  rng_normal2(r, z0, z1);
+}
+__device__ __forceinline__ double site_heatbath_z(const GF &g, const double Delta, const double z) {
+  return (1. / sqrt(4. + g.mu2)) * z + div_exact(Delta, 4. + g.mu2, 1. / (4. + g.mu2));
+}
 template <bool HEATBATH>
 __device__ __forceinline__ double site_update(const GF &g, const double Delta, const double phi, uint64_t seed,
                                               uint64_t draw, uint32_t gchain, int ell) {
   if (HEATBATH) {
-    Rng r = rng_init(seed, MLMCPI_STREAM_HEATBATH, draw, gchain, ell);
     double z0, z1;
-    rng_normal2(r, z0, z1);
-    return (1. / sqrt(4. + g.mu2)) * z0 + div_exact(Delta, 4. + g.mu2, 1. / (4. + g.mu2));
+    heatbath_pair_normals(seed, draw, gchain, ell & ~1, z0, z1);
+    return site_heatbath_z(g, Delta, (ell & 1) ? z1 : z0);
   }
   return div_exact(2. * Delta, 4. + g.mu2, 1. / (4. + g.mu2)) - phi;
 }
@@ -386,21 +396,29 @@ __global__ void __launch_bounds__(1024)
   // colour 0 on lattice row j (parity par = j & 1; Mx is even, so the parity survives the wrap):
   // below / own / above = old rows j-1, j, j+1 of this thread's pair
   // (slot = ring slot of that row: the UNWRAPPED row number & 3)
-  auto stage_a = [&](int j, int slot, int par, double2 below, double2 own, double2 above) {
+  // heat bath: the thread's two sites of row j, (2t, j) and (2t+1, j), are the vertex pair of one Philox block
+  // (heatbath_pair_normals): stage A draws it for its colour-0 site and hands the other normal (zother) to stage B
+  // of the same row, one loop iteration later
+  auto stage_a = [&](int j, int slot, int par, double2 below, double2 own, double2 above, double &zother) {
     const double *cv = c1val + (size_t)slot * H;
+    double z0 = 0.0, z1 = 0.0;
+    if (HEATBATH)
+      heatbath_pair_normals(seed, draw, gchain, Mt * j + 2 * t, z0, z1);
     double d = 0.0;
     if (par == 0) { // site 2t: neighbours (2t+1, j) own .y, (2t-1, j) of thread t-1, (2t, j+1), (2t, j-1)
       d += own.y;
       d += cv[tm];
       d += above.x;
       d += below.x;
-      return site_update<HEATBATH>(g, d, own.x, seed, draw, gchain, Mt * j + 2 * t);
+      zother = z1;
+      return HEATBATH ? site_heatbath_z(g, d, z0) : site_update<false>(g, d, own.x, 0, 0, 0, 0);
     }
     d += cv[tp]; // site 2t+1: neighbours (2t+2, j) of thread t+1, (2t, j) own .x
     d += own.x;
     d += above.y;
     d += below.y;
-    return site_update<HEATBATH>(g, d, own.y, seed, draw, gchain, Mt * j + 2 * t + 1);
+    zother = z0;
+    return HEATBATH ? site_heatbath_z(g, d, z1) : site_update<false>(g, d, own.y, 0, 0, 0, 0);
   };
   int jl = wrap(e0 - 2);
   double2 o0 = xin[(size_t)jl * H + t]; // old rows e0-2, e0-1, e0, e0+1
@@ -418,8 +436,9 @@ __global__ void __launch_bounds__(1024)
   jn = jn + 1 == Mx ? 0 : jn + 1;
   double2 pre2 = xin[(size_t)jn * H + t]; // row e0 + 3
   __syncthreads();
-  double nm1 = stage_a(wrap(e0 - 1), (e0 - 1) & 3, 1, o0, o1, o2); // new colour-0 values of rows e0-1 and e0
-  double n0 = stage_a(e0, e0 & 3, 0, o1, o2, o3);
+  double zc0, zc1, zunused;
+  double nm1 = stage_a(wrap(e0 - 1), (e0 - 1) & 3, 1, o0, o1, o2, zunused); // new colour-0 values of rows e0-1 and e0
+  double n0 = stage_a(e0, e0 & 3, 0, o1, o2, o3, zc0);                      // zc0: the normal of row e0's colour-1 site
   n0row[(size_t)(e0 & 1) * H + t] = n0;
   __syncthreads();
   // loop invariant for output row r: o2 = old(r), o3 = old(r+1), pre = old(r+2), nm1 / n0 = new colour 0 of
@@ -434,7 +453,7 @@ __global__ void __launch_bounds__(1024)
       pre2 = xin[(size_t)jn * H + t];
     }
     const int r1 = r + 1 == Mx ? 0 : r + 1;
-    const double n1 = stage_a(r1, (r + 1) & 3, par ^ 1, o2, o3, o4); // colour 0 on row r + 1
+    const double n1 = stage_a(r1, (r + 1) & 3, par ^ 1, o2, o3, o4, zc1); // colour 0 on row r + 1
     n0row[(size_t)((r + 1) & 1) * H + t] = n1;
     // colour 1 on row r: the new colour-0 neighbours
     const double *nr = n0row + (size_t)(r & 1) * H;
@@ -444,14 +463,14 @@ __global__ void __launch_bounds__(1024)
       d += n0;
       d += n1;
       d += nm1;
-      m = site_update<HEATBATH>(g, d, o2.y, seed, draw, gchain, Mt * r + 2 * t + 1);
+      m = HEATBATH ? site_heatbath_z(g, d, zc0) : site_update<false>(g, d, o2.y, 0, 0, 0, 0);
       xout[(size_t)r * H + t] = make_double2(n0, m);
     } else { // site 2t: (2t+1, r) own, (2t-1, r) of thread t-1
       d += n0;
       d += nr[tm];
       d += n1;
       d += nm1;
-      m = site_update<HEATBATH>(g, d, o2.x, seed, draw, gchain, Mt * r + 2 * t);
+      m = HEATBATH ? site_heatbath_z(g, d, zc0) : site_update<false>(g, d, o2.x, 0, 0, 0, 0);
       xout[(size_t)r * H + t] = make_double2(m, n0);
     }
     __syncthreads();
@@ -459,6 +478,7 @@ __global__ void __launch_bounds__(1024)
     o3 = o4;
     nm1 = n0;
     n0 = n1;
+    zc0 = zc1;
   }
 }
 

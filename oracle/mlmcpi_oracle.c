@@ -1575,9 +1575,11 @@ static void heatbath_update(const orc_model *m, uint64_t seed, uint64_t draw,
   case ORC_GFF: { /* qft/gffaction.cc:32-42 */
     const double Delta = gff_nn_sum(m, x, ell);
     const double sigma = 1. / sqrt(4. + m->gff_mu2);
+    /* the vertices 2q, 2q + 1 share the block with index 2q: z0 for the even, z1 for the odd one (include/mlmcpi.h) */
     double z0, z1;
+    orc_rng_init(&r, seed, ORC_STREAM_HEATBATH, draw, chain, ell & ~1u);
     orc_rng_normal2(&r, &z0, &z1);
-    x[ell] = sigma * z0 + Delta / (4. + m->gff_mu2);
+    x[ell] = sigma * ((ell & 1u) ? z1 : z0) + Delta / (4. + m->gff_mu2);
     return;
   }
   case ORC_SCHWINGER: { /* qft/quenchedschwingeraction.cc:46-54 */

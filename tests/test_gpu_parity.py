@@ -417,6 +417,47 @@ def test_cached_cascade_equals_literal_cascade(mp, ctx):
         assert 0.0 < res[1][1][0] < 1.0 or L == 2
 
 
+def test_cached_cascade_other_coarse_samplers(mp, ctx):
+    """the cached cascade with a coarse sampler that advances a COPY of the coarsest state (heat bath, cluster; GFF
+    with heat bath on the Gibbs-smoothed dense coarse actions and with the exact coarse sampler) against the literal
+    sequence: same states (up to the rounding of the cached level actions), same acceptance counters"""
+    cases = [("schwinger", 32, 9.0, 3, dict(kind=mp.SAMPLER_HEATBATH, n_sweep_overrelax=2, n_sweep_heatbath=1)),
+             ("schwinger", 64, 64.0, 3, dict(kind=mp.SAMPLER_CLUSTER, n_updates=20)),
+             ("schwinger", 32, 16.0, 2, dict(kind=mp.SAMPLER_CLUSTER, n_updates=10)),
+             ("gff", 16, 3.0, 3, dict(kind=mp.SAMPLER_HEATBATH, n_sweep_overrelax=2, n_sweep_heatbath=1)),
+             ("gff", 32, 10.0, 4, dict(kind=mp.SAMPLER_HEATBATH, n_sweep_overrelax=1, n_sweep_heatbath=1)),
+             ("gff", 16, 3.0, 2, dict(kind=mp.SAMPLER_EXACT))]
+    for name, M, par, L, kw in cases:
+        B = 12
+        if name == "schwinger":
+            m = mp.schwinger(M, M, par)
+            kw = dict(kw, renorm=mp.RENORM_PERTURBATIVE)
+        else:
+            m = mp.gff(M, M, par, mp.COARSEN_ROTATE)
+            kw = dict(kw, ctype=mp.COARSEN_ROTATE)
+            with pytest.raises(mp.MlmcpiError):  # any other coarsening of a GFF hierarchy is refused
+                mp.Sampler(ctx, m, B, n_levels=L, **dict(kw, ctype=mp.COARSEN_BOTH))
+        res = []
+        for cache in (0, 1):
+            ctx.set_option(mp._lib.OPT_CASCADE_CACHE, cache)
+            smp = mp.Sampler(ctx, m, B, n_levels=L, chain0=3, **kw)
+            x = smp.get_state()
+            states = []
+            for d in range(10):
+                smp.draw(x)
+                states.append(host(x).copy())
+                if d == 5:
+                    smp.set_state(x)
+            res.append((states, smp.p_accept(), host(smp.get_state()).copy()))
+            smp.close()
+        ctx.set_option(mp._lib.OPT_CASCADE_CACHE, 1)
+        cmp = ang_close if name == "schwinger" else (lambda a, b, tol, what: close(a, b, tol, what))
+        for d, (a, b) in enumerate(zip(res[0][0], res[1][0])):
+            cmp(a, b, tol=1e-9, what=f"{name} {M}^2 {L} levels {kw['kind']}, draw {d}")
+        assert res[0][1] == res[1][1], (name, M, L, res[0][1], res[1][1])
+        cmp(res[0][2], res[1][2], tol=1e-9, what="get_state")
+
+
 def test_draw_host_async_hands_back_accepted_states(mp, ctx):
     """mlmcpi_sampler_draw_host_async: chains resident, QoI of every chain and the states of the ACCEPTED
     chains written to the host buffer on a second stream (pinned memory: by a masked copy kernel straight
@@ -425,7 +466,10 @@ def test_draw_host_async_hands_back_accepted_states(mp, ctx):
     import torch
     m = mp.schwinger(32, 32, 9.0)
     B = 24
-    for pinned in (True, False):
+    # pinned + copy engine (default: accept flags to the host, one copy per run of accepted chains, two snapshot
+    # buffers), pinned + masked copy kernel over the host link, pageable (full copy)
+    for pinned, engine in ((True, 1), (True, 0), (False, 1)):
+        ctx.set_option(mp._lib.OPT_HOST_COPY_ENGINE, engine)
         s = mp.Sampler(ctx, m, B, kind=mp.SAMPLER_HMC, n_levels=2, nt=8, dt=0.05, renorm=mp.RENORM_PERTURBATIVE)
         x0 = ctx.init_state(m, B, 0, 1)
         for k in range(3):
@@ -446,7 +490,21 @@ def test_draw_host_async_hands_back_accepted_states(mp, ctx):
             assert torch.equal(h_q, ctx.qoi(m, mp.QOI_SCHWINGER_CHI, now).cpu())
             changed += int((h_x != before).any(dim=1).sum())
         assert 0 < changed < 8 * B  # accepted and rejected draws both occurred
+        if pinned:  # back-to-back calls without waiting in between (two alternating host buffers, as bench.py does)
+            h2 = [h_x.clone().pin_memory(), h_x.clone().pin_memory()]
+            q2 = [h_q.clone().pin_memory(), h_q.clone().pin_memory()]
+            for d in range(6):
+                s.draw_host_async(mp.QOI_SCHWINGER_CHI, q2[d & 1], h2[d & 1])
+            s.wait_host()
+            now = s.get_state().cpu()
+            # the buffer of the last call holds every chain whose LAST draw was accepted; all rows are states the
+            # chain has been in (rows of rejected draws keep an older state of that buffer)
+            last = h2[5 & 1]
+            assert torch.equal(q2[5 & 1], ctx.qoi(m, mp.QOI_SCHWINGER_CHI, s.get_state()).cpu())
+            same = (last == now).all(dim=1)
+            assert same.any()
         s.close()
+    ctx.set_option(mp._lib.OPT_HOST_COPY_ENGINE, 1)
 
 
 def test_ho_exact_sampler(mp, ctx, orc):
@@ -552,6 +610,33 @@ def test_per_dof_updates_reproduce_the_reference_lexicographic_sweep(mp, ctx):
     ctx.heatbath_sweep(m, b, 3, 11)
     assert np.array_equal(host(a)[:, 0], host(b)[:, 0])
     assert len(set(host(a)[:, 0])) == 4  # one variate stream per chain
+
+
+def test_schwinger_heatbath_paired_variates(mp, ctx, orc):
+    """heatbath_pair_kernel (two links of a colour per Philox block) against the oracle's restatement of the same
+    variate map, on lattices where a row holds an ODD number of links of a colour (Mt / 2 odd: the last link has no
+    partner), for small and large beta (retries on the links' own streams); and the single-link entry point
+    mlmcpi_dof_update(heatbath) for both roles: every link of colour 0 -- which the sweep updates first, from the
+    original neighbours -- gets the sweep's value"""
+    rng = np.random.default_rng(5)
+    orc.lib.orc_set_expcos_envelope(2)  # the product's default envelope (the oracle's default is the reference's)
+    for Mt, Mx, beta in [(6, 4, 2.0), (10, 6, 40.0), (12, 8, 900.0), (34, 6, 3.0)]:
+        o = po.schwinger(Mt, Mx, beta)
+        m = mp.schwinger(Mt, Mx, beta)
+        B, chain0, draw = 3, 5, (2 << 32) + 7
+        x = rng.uniform(-np.pi, np.pi, (B, 2 * Mt * Mx))
+        xd = dev(ctx, x)
+        ctx.heatbath_sweep(m, xd, chain0, draw)
+        want = np.array([orc.heatbath_sweep(o, SEED, draw, chain0 + b, x[b]) for b in range(B)])
+        ang_close(host(xd), want, tol=1e-9, what=f"paired heat bath {Mt}x{Mx} beta {beta}")
+        got = host(xd)
+        for j in range(0, Mx, 2):          # colour 0: mu = 0, even rows
+            for i in range(Mt):
+                ell = 2 * (Mt * j + i)
+                a = dev(ctx, x)
+                ctx.dof_update(m, a, ell, heatbath=True, chain0=chain0, draw=draw)
+                assert np.array_equal(host(a)[:, ell], got[:, ell]), (Mt, Mx, i, j)
+    orc.lib.orc_set_expcos_envelope(0)
 
 
 def test_gff_dense_action_2048_vertices_against_reference(mp, ctx):
