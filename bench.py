@@ -344,7 +344,7 @@ def ess_leg(mp, ctx, torch, dist, a, m, B, rank, world):
     e0.record()
     for _ in range(a.ess_draws):
         s.draw(x)
-        st.record(ctx.qoi(m, mp.QOI_SCHWINGER_CHI, x))
+        st.record(s.qoi(mp.QOI_SCHWINGER_CHI))
         st.pack_device(packed)
         if world > 1:
             dist.all_reduce(packed)
@@ -576,7 +576,9 @@ def gpu_main(a):
 
     def step():
         sampler.draw(x)
-        stats.record(ctx.qoi(m, QOI, x))
+        # QoI of the chains' states (x holds them: draw() overwrote the accepted chains).  mlmcpi_sampler_qoi: for the
+        # susceptibility of a hierarchical Schwinger sampler the charge of the trial state came out of the fill-in kernel
+        stats.record(sampler.qoi(QOI))
         stats.pack_device(packed)
         if world > 1:  # QoI moments + autocorrelation sums: the only inter-GPU traffic
             dist.all_reduce(packed)
@@ -655,6 +657,20 @@ def gpu_main(a):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         t_full, t_qoi = (float(v) for v in te.cpu())
+        # the ceiling: what the copy engine moves device -> pinned host when every rank copies at the same time
+        link = None
+        try:
+            probe = torch.empty(B * n // 2, dtype=torch.float64, device=ctx.device)  # half the states: 1 GiB
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t_l0 = time.perf_counter()
+            h_x[0].view(-1)[:probe.numel()].copy_(probe, non_blocking=True)
+            torch.cuda.synchronize()
+            link = probe.numel() * 8 / (time.perf_counter() - t_l0) / 1e9
+            del probe
+        except Exception:  # pragma: no cover
+            link = None
         chk = float(h_q[(k_e2e - 1) & 1].mean())  # the host really holds the result
         os.sched_setaffinity(0, affinity0)  # (the cpu_baseline leg uses every core)
         acc_all = 1.0
@@ -675,6 +691,9 @@ def gpu_main(a):
                "inputs": "none per step: a sampler's only input is its own previous state (resident) and the Philox "
                          "counters; the per-step host traffic is the OUTPUT, as in Sampler::draw(state)",
                "limited_by": "the host link: %.2f GiB of states per step and GPU" % (B * n * 8 * acc_all / 2 ** 30),
+               "host_link_gbs_per_gpu": link,
+               "host_link_note": "copy-engine D2H of 1 GiB into the same pinned buffer, all ranks at the same time "
+                                 "(rank 0's figure): the ceiling of d2h_gbs_per_gpu",
                "qoi_only": {"value": units_per_step * world * k_e2e / t_qoi, "ms_per_step": 1e3 * t_qoi / k_e2e,
                             "d2h_bytes_per_step": B * 8,
                             "note": "same API with h_x_out = NULL: the QoI of every chain to the host each step"},

@@ -366,6 +366,11 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept);
  * was accepted (MCMCStep::copy_if_rejected = false, hierarchicalsampler.cc:78-80), so an output buffer
  * that is to hold the chains' states from the first draw on is initialised with this call */
 int mlmcpi_sampler_get_state(mlmcpi_sampler *s, double *d_x);
+/* QoI::evaluate (qoi/quantityofinterest.hh) of the chains' current states, d_q[B].  Equal to mlmcpi_qoi of
+ * mlmcpi_sampler_get_state; for MLMCPI_QOI_SCHWINGER_CHI (qoi/qft/qoi2dsusceptibility.cc:7-27) of a hierarchical
+ * sampler the values are maintained by the draws -- the fill-in kernel of the finest level returns the topological
+ * charge of the trial state next to S_f and S_cond -- and the call copies B doubles */
+int mlmcpi_sampler_qoi(mlmcpi_sampler *s, int qoi, double *d_q);
 /* the same with HOST buffers: h_x_in (may be NULL: keep the current state) is
  * uploaded, one draw is made, the QoI of the new state is evaluated, and
  * h_q[B] (and h_x_out[B][n] if not NULL) are copied back; synchronous */

@@ -166,6 +166,9 @@ public:
   /** Sampler::draw for every chain; the new states are in states() */
   void draw() { Device::check(mlmcpi_sampler_draw(s_, x_.ptr(), nullptr), "Sampler::draw"); }
   double *states() { return x_.ptr(); }
+  /** QoI::evaluate of every chain's state (mlmcpi_sampler_qoi: the susceptibility of a hierarchical Schwinger sampler
+   *  comes out of the draw itself) */
+  void evaluate(int qoi, double *d_q) { Device::check(mlmcpi_sampler_qoi(s_, qoi, d_q), "QoI::evaluate"); }
   unsigned int chains() const { return B_; }
   const std::shared_ptr<Action> &action() const { return action_; }
   double cost_per_sample() {
@@ -408,8 +411,7 @@ private:
   }
   void sample() {
     sampler->draw();
-    Device::check(mlmcpi_qoi(Device::ctx(), &action->model(), qoi->id(), sampler->states(), (int)B, q_.ptr(), nullptr),
-                  "QoI::evaluate");
+    sampler->evaluate(qoi->id(), q_.ptr());
     stats_Q.record_sample(q_.ptr());
   }
   const std::shared_ptr<Action> action;

@@ -123,6 +123,7 @@ SIGNATURES = {
     "mlmcpi_sampler_level_model": (_i, [_vp, _i, _MP]),
     "mlmcpi_dof_update": (_i, [_vp, _MP, _vp, _i, _i, _i, _u32, _u64]),
     "mlmcpi_sampler_get_state": (_i, [_vp, _vp]),
+    "mlmcpi_sampler_qoi": (_i, [_vp, _i, _vp]),
     "mlmcpi_sampler_draw_host_async": (_i, [_vp, _i, _vp, _vp]),
     "mlmcpi_sampler_wait_host": (_i, [_vp]),
     "mlmcpi_sampler_stats": (_i, [_vp, _dp]),

@@ -348,6 +348,12 @@ class Sampler:
         self.ctx._ck(L.mlmcpi_sampler_get_state(self.h, _ptr(x)))
         return x
 
+    def qoi(self, which):
+        """QoI of the chains' current states (mlmcpi_sampler_qoi: maintained by the draws where the library can)"""
+        q = self.ctx.empty(self.B)
+        self.ctx._ck(L.mlmcpi_sampler_qoi(self.h, which, _ptr(q)))
+        return q
+
     def draw(self, x_out=None, accept=None):
         self.ctx._ck(L.mlmcpi_sampler_draw(self.h, _ptr(x_out), _ptr(accept)))
 

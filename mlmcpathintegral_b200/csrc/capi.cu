@@ -580,7 +580,7 @@ __global__ void reduce_finish_kernel(const double *partial, int nblk, int B, int
   const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (chain >= B)
     return;
-  double s[2] = {0.0, 0.0};
+  double s[3] = {0.0, 0.0, 0.0};
   for (int k = 0; k < nout; ++k) {
     const double *p = partial + ((size_t)k * B + chain) * nblk;
     double acc = 0.0;
@@ -598,6 +598,8 @@ __global__ void reduce_finish_kernel(const double *partial, int nblk, int B, int
     out[chain] = scale0 * s[0];
     if (nout > 1)
       out[B + chain] = scale1 * s[1];
+    if (nout > 2)
+      out[2 * (size_t)B + chain] = s[2];
   }
 }
 
@@ -1048,6 +1050,11 @@ struct mlmcpi_sampler {
   std::vector<double *> trial;   // [L] theta'_l of the current draw, levels 1 .. L-2 (sampler-owned)
   double *Scond_lvl = nullptr;   // [L][B] S_cond(state[l]), 1 <= l <= L-2
   double *Sprime = nullptr;      // [L][2][B] S_f(theta'_l), S_cond(theta'_l) of the current draw
+  // Schwinger model, coarsening both: the fill-in of the finest level also returns the topological charge of theta',
+  // so the susceptibility QoI of the chains' states is kept up to date without a pass of its own (mlmcpi_sampler_qoi)
+  double *S3 = nullptr;          // [3][B] S_f, S_cond, sum_P mod_2pi(P) of theta'_0
+  double *chi_cur = nullptr;     // [B] QOI_SCHWINGER_CHI of state[0]
+  bool chi_valid = false;
   // QuenchedSchwingerClusterSampler: the rotor chain psi [B][Mt*Mx] and its action
   double *psi = nullptr;
   mlmcpi_model psi_model = {};
@@ -1382,6 +1389,13 @@ static int sampler_draw_range(mlmcpi_sampler *s, int c0, int B, bool cache0_vali
   return 0;
 }
 
+// QOI_SCHWINGER_CHI of the accepted trial states from the charge sum the fill-in returned (schwinger::qoi: 0.25 / pi^2 s^2)
+__global__ void chi_commit_kernel(int B, const int32_t *acc, double *chi, const double *qsum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < B && acc[c])
+    chi[c] = (0.25 / (M_PI * M_PI)) * qsum[c] * qsum[c];
+}
+
 // commit of a fully accepted cascade on a coarse level: the cached actions follow the state
 __global__ void cascade_commit_kernel(int B, const int32_t *acc, double *S_old, const double *S_prime, double *Scond,
                                       const double *Scond_prime) {
@@ -1435,6 +1449,12 @@ static int cascade_draw_cached(mlmcpi_sampler *s) {
     if ((rc = mlmcpi_cond_action(ctx, &s->model[0], s->state[0], B, s->Scond0)))
       return rc;
   }
+  const bool fused_chi = s->S3 != nullptr;
+  if (fused_chi && !s->chi_valid) {
+    if ((rc = mlmcpi_qoi(ctx, &s->model[0], MLMCPI_QOI_SCHWINGER_CHI, s->state[0], B, s->chi_cur, nullptr)))
+      return rc;
+    s->chi_valid = true;
+  }
   const double *coarse_trial = nullptr;
   const bool hmc_trial = cascade_hmc_trial(s);
   if (hmc_trial) { // coarsest level: tentative HMC step (hmcsampler.cc:21-69)
@@ -1464,11 +1484,17 @@ static int cascade_draw_cached(mlmcpi_sampler *s) {
     if (!theta_prime)
       return MLMCPI_ENOMEM;
     // theta' = fill(prolong(trial state of level l+1)), S_f(theta'), S_cond(theta')  (twolevelmetropolisstep.cc:40-66)
-    if ((rc = mlmcpi_prolong_fill_eval(ctx, &s->model[l], coarse_trial, theta_prime, B, chain0,
-                                       level_draw(s->draw, l, 0), Sp(l, 0))))
+    double *Sprime_l = (l == 0 && fused_chi) ? s->S3 : Sp(l, 0);
+    if (l == 0 && fused_chi)
+      rc = schwinger::prolong_fill_eval_charge(ctx, &s->model[0], coarse_trial, theta_prime, B, chain0,
+                                               level_draw(s->draw, 0, 0), Sprime_l);
+    else
+      rc = mlmcpi_prolong_fill_eval(ctx, &s->model[l], coarse_trial, theta_prime, B, chain0, level_draw(s->draw, l, 0),
+                                    Sprime_l);
+    if (rc)
       return rc;
     twolevel_accept_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(
-        B, chain0, ctx->seed, level_draw(s->draw, l, 0), Sp(l, 0), S_old(l + 1), Sp(l + 1, 0),
+        B, chain0, ctx->seed, level_draw(s->draw, l, 0), Sprime_l, S_old(l + 1), Sp(l + 1, 0),
         (l == 0) ? s->Sf0 : S_old(l), (l == 0) ? s->Sf0 : nullptr, (l == 0) ? s->Scond0 : Scond_l(l),
         (l == 0) ? 1 : 0, s->acc, s->acc, nullptr);
     MLMCPI_LAUNCHED("twolevel_accept");
@@ -1478,6 +1504,10 @@ static int cascade_draw_cached(mlmcpi_sampler *s) {
     if (l == 0) {
       if ((rc = launch_masked_copy(ctx, s->state[0], theta_prime, nf, B, s->acc))) // :78-88
         return rc;
+      if (fused_chi) {
+        chi_commit_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, s->acc, s->chi_cur, s->S3 + 2 * (size_t)B);
+        MLMCPI_LAUNCHED("chi_commit");
+      }
     }
     coarse_trial = theta_prime;
   }
@@ -1634,6 +1664,9 @@ int mlmcpi_sampler_create(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const mlmcp
       ok = mlmcpi_alloc(ctx, (size_t)mlmcpi_sample_size(&s->model[l]) * B, &s->trial[l]) == 0;
     ok = ok && mlmcpi_alloc(ctx, (size_t)s->L * B, &s->Scond_lvl) == 0 &&
          mlmcpi_alloc(ctx, (size_t)s->L * 2 * B, &s->Sprime) == 0;
+    if (ok && fine->model == MLMCPI_SCHWINGER && fine->coarsening == MLMCPI_COARSEN_BOTH &&
+        fine->Mt_lat % 2 == 0 && fine->Mx_lat % 2 == 0)
+      ok = mlmcpi_alloc(ctx, (size_t)3 * B, &s->S3) == 0 && mlmcpi_alloc(ctx, (size_t)B, &s->chi_cur) == 0;
     if (!ok) {
       cudaGetLastError();
       mlmcpi_sampler_destroy(s);
@@ -1762,6 +1795,10 @@ void mlmcpi_sampler_destroy(mlmcpi_sampler *s) {
     cudaFree(s->Scond_lvl);
   if (s->Sprime)
     cudaFree(s->Sprime);
+  if (s->S3)
+    cudaFree(s->S3);
+  if (s->chi_cur)
+    cudaFree(s->chi_cur);
   for (mlmcpi_stats *st : s->stats_sampler)
     mlmcpi_stats_destroy(st);
   for (double *d : s->SfL)
@@ -1804,6 +1841,7 @@ int mlmcpi_sampler_set_state(mlmcpi_sampler *s, const double *d_x) {
     return 0;
   s->cache0_valid = false;
   s->cascade_valid = false;
+  s->chi_valid = false;
   return mlmcpi_copy(s->ctx, s->state[0], d_x, (size_t)mlmcpi_sample_size(&s->model[0]) * s->B);
 }
 
@@ -1840,6 +1878,7 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
       return rc;
   } else {
     s->cascade_valid = false;
+    s->chi_valid = false;
     if ((rc = sampler_draw_range(s, 0, B, s->cache0_valid)))
       return rc;
   }
@@ -1855,6 +1894,18 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
     MLMCPI_CUDA(cudaMemcpyAsync(d_accept, s->acc, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice,
                                 ctx->stream));
   return 0;
+}
+
+// QoI::evaluate of the chains' current states.  For QOI_SCHWINGER_CHI with the cached cascade the values are kept up
+// to date by the draws themselves (the fill-in of the finest level returns the charge of the trial state): a copy
+// of B doubles instead of a pass over the states.
+int mlmcpi_sampler_qoi(mlmcpi_sampler *s, int qoi, double *d_q) {
+  DeviceGuard device_guard(s ? s->ctx : nullptr);
+  if (!s || !d_q)
+    return MLMCPI_EINVAL;
+  if (qoi == MLMCPI_QOI_SCHWINGER_CHI && s->chi_cur && s->chi_valid && s->model[0].model == MLMCPI_SCHWINGER)
+    return mlmcpi_copy(s->ctx, d_q, s->chi_cur, (size_t)s->B);
+  return mlmcpi_qoi(s->ctx, &s->model[0], qoi, s->state[0], s->B, d_q, nullptr);
 }
 
 // Host-buffer entry point.  With an input state the batch is cut into ranges of chains: the
@@ -1896,6 +1947,7 @@ int mlmcpi_sampler_draw_host(mlmcpi_sampler *s, const double *h_x_in, int qoi, d
       const int c0 = (int)((long long)s->B * k / n_ranges), c1 = (int)((long long)s->B * (k + 1) / n_ranges);
       MLMCPI_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev[k], 0));
       s->cascade_valid = false;
+      s->chi_valid = false;
       if ((rc = sampler_draw_range(s, c0, c1 - c0, false)))
         return rc;
       if (h_q)
@@ -1985,7 +2037,7 @@ int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, doub
       if ((rc = mlmcpi_sampler_draw(s, nullptr, nullptr)))
         return rc;
       if (h_q) {
-        if ((rc = mlmcpi_qoi(ctx, &s->model[0], qoi, s->state[0], s->B, s->q, nullptr)))
+        if ((rc = mlmcpi_sampler_qoi(s, qoi, s->q)))
           return rc;
         MLMCPI_CUDA(cudaMemcpyAsync(h_q, s->q, sizeof(double) * s->B, cudaMemcpyDeviceToHost, ctx->stream));
       }
@@ -2017,7 +2069,7 @@ int mlmcpi_sampler_draw_host_async(mlmcpi_sampler *s, int qoi, double *h_q, doub
     return rc;
   if ((rc = mlmcpi_sampler_draw(s, nullptr, nullptr)))
     return rc;
-  if (h_q && (rc = mlmcpi_qoi(ctx, &s->model[0], qoi, s->state[0], s->B, s->q, nullptr)))
+  if (h_q && (rc = mlmcpi_sampler_qoi(s, qoi, s->q)))
     return rc;
   // the snapshot must not overwrite the staging buffers while the previous copy still reads them
   if (s->host_copy_pending)

@@ -762,6 +762,8 @@ int sweep_sequence(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int, int, 
 namespace schwinger {
 int overrelax_sweeps(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int);
 int from_cluster(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t, uint64_t);
+int prolong_fill_eval_charge(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t, uint64_t,
+                             double *);
 int hmc_trial(mlmcpi_ctx *, const mlmcpi_model *, int, double, const double *, int, uint32_t, uint64_t,
               const double *, double *, int32_t *, const double **);
 }

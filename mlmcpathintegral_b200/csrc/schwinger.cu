@@ -1284,7 +1284,9 @@ __global__ void fill_both_step23_kernel(SW sw, BesselProductConst bp, double *x_
 // EVAL: the block additionally reduces S_f(theta') / beta and S_cond(theta') of its cells into
 // partial[{0,1}][chain][block] (TwoLevelMetropolisStep::draw lines 48 and 65-66 without a second
 // and third pass over theta').  Grid: nblk blocks of 128 cells per chain.
-template <bool APPROX, bool EVAL>
+// CHARGE (with EVAL): a third partial sum, sum over the cell's four plaquettes of mod_2pi(P) -- the topological charge
+// of theta' times 2 pi (qoi/qft/qoi2dsusceptibility.cc:7-27), so that the QoI of an accepted draw needs no pass of its own
+template <bool APPROX, bool EVAL, bool CHARGE = false>
 #ifndef FILL_MINBLK
 #define FILL_MINBLK (1024 / FILL_THREADS)
 #endif
@@ -1299,7 +1301,7 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MINBLK) prolong_fill_both_k
   // the block passes the same barriers)
   const bool live = cell_raw < nc;
   const int cell = live ? cell_raw : nc - 1;
-  double sf = 0.0, sc = 0.0;
+  double sf = 0.0, sc = 0.0, qs = 0.0;
   const unsigned wmask = 0xffffffffu;
   {
     const int j = cell / Mtc, i = cell - j * Mtc;
@@ -1334,6 +1336,9 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MINBLK) prolong_fill_both_k
       __syncthreads();
     fill_cell_interior<APPROX, EVAL, (FILL_PHASE_SYNC != 0)>(c, V, sw.beta, sw.envelope, bp, seed, draw, gchain, Mt, i, j, cell,
                                                             sf, sc, wmask);
+    if (CHARGE) // the cell's four plaquettes, summed in the order of plaq()
+      qs = (mod_2pi(c.A0 + c.V0 - c.H0 - c.B0) + mod_2pi(c.A1 + c.R0 - c.H1 - c.V0)) +
+           (mod_2pi(c.H0 + c.V1 - c.T0 - c.B1) + mod_2pi(c.H1 + c.R1 - c.T1 - c.V1));
     if (live) {
       // rows 2j and 2j+1, sites 2i and 2i+1: four aligned double2 stores
       double2 *xs = reinterpret_cast<double2 *>(x);
@@ -1342,7 +1347,7 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MINBLK) prolong_fill_both_k
       xs[(size_t)Mt * (2 * j + 1) + 2 * i] = make_double2(c.H0, c.B1);
       xs[(size_t)Mt * (2 * j + 1) + 2 * i + 1] = make_double2(c.H1, c.V1);
     } else {
-      sf = sc = 0.0;
+      sf = sc = qs = 0.0;
     }
   }
   if (EVAL) { // one partial sum per WARP: no block-wide barrier at the end of the kernel (ncu: 14 % of the stall samples)
@@ -1352,6 +1357,11 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MINBLK) prolong_fill_both_k
       const size_t slot = (size_t)blk * WARPS + (threadIdx.x >> 5), npart = (size_t)nblk * WARPS;
       partial[(size_t)chain * npart + slot] = v0;
       partial[((size_t)B + chain) * npart + slot] = v1;
+    }
+    if (CHARGE) {
+      const double v2 = warp_sum(qs);
+      if ((threadIdx.x & 31) == 0)
+        partial[((size_t)2 * B + chain) * ((size_t)nblk * WARPS) + (size_t)blk * WARPS + (threadIdx.x >> 5)] = v2;
     }
   }
 }
@@ -2041,13 +2051,16 @@ int fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chai
   return 0;
 }
 
-// S_out: nullptr, or [2][B] receiving S_f(theta') and S_cond(theta') (fused evaluation)
+// S_out: nullptr, or [2][B] receiving S_f(theta') and S_cond(theta') (fused evaluation); charge: [3][B], the third row
+// sum_P mod_2pi(P) of theta' (coarsening both only)
 static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
-                             uint32_t chain0, uint64_t draw, double *S_out) {
+                             uint32_t chain0, uint64_t draw, double *S_out, bool charge = false) {
   int rc = check_even(ctx, m);
   if (rc)
     return rc;
   if (m->coarsening != MLMCPI_COARSEN_BOTH) {
+    if (charge)
+      return ctx_fail(ctx, MLMCPI_EUNSUPPORTED, "fused topological charge: coarsening both only");
     if ((rc = prolong(ctx, m, xc, x, B)))
       return rc;
     if ((rc = fill(ctx, m, x, B, chain0, draw)))
@@ -2064,12 +2077,15 @@ static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const doubl
   const int grid = nblk * B;
   double *partial = nullptr;
   const int npart = nblk * (FILL_THREADS / 32); // one partial sum per warp
-  if (S_out && !(partial = ctx_scratch(ctx, (size_t)2 * B * npart)))
+  if (S_out && !(partial = ctx_scratch(ctx, (size_t)(charge ? 3 : 2) * B * npart)))
     return MLMCPI_ENOMEM;
   BesselProductConst bp;
   if (sw.beta > 8.0) {
     bp.beta = sw.beta;
-    if (S_out)
+    if (S_out && charge)
+      prolong_fill_both_kernel<true, true, true><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0,
+                                                                                       ctx->seed, draw, nblk, partial);
+    else if (S_out)
       prolong_fill_both_kernel<true, true><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
                                                                          draw, nblk, partial);
     else
@@ -2077,7 +2093,10 @@ static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const doubl
                                                                           draw, nblk, nullptr);
   } else {
     besselproduct_setup(sw.beta, &bp);
-    if (S_out)
+    if (S_out && charge)
+      prolong_fill_both_kernel<false, true, true><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0,
+                                                                                        ctx->seed, draw, nblk, partial);
+    else if (S_out)
       prolong_fill_both_kernel<false, true><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
                                                                           draw, nblk, partial);
     else
@@ -2086,8 +2105,14 @@ static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const doubl
   }
   MLMCPI_LAUNCHED("schwinger::prolong_fill");
   if (S_out)
-    return launch_reduce_finish(ctx, partial, npart, B, 2, EPI_SCALE, sw.beta, 1.0, S_out, nullptr);
+    return launch_reduce_finish(ctx, partial, npart, B, charge ? 3 : 2, EPI_SCALE, sw.beta, 1.0, S_out, nullptr);
   return 0;
+}
+
+// prolong_fill_eval with a third output row: sum over the plaquettes of theta' of mod_2pi(P)  (S_out: [3][B])
+int prolong_fill_eval_charge(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B, uint32_t chain0,
+                             uint64_t draw, double *S_out) {
+  return prolong_fill_impl(ctx, m, xc, x, B, chain0, draw, S_out, true);
 }
 
 int prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
