@@ -651,13 +651,16 @@ __global__ void hmc_accept_kernel(int B, uint32_t chain0, uint64_t seed, uint64_
 // dst[chain] = src[chain] where accept[chain]: blocks of a rejected chain leave at once (the chain index is
 // block-uniform: grid.y folds the chains, no per-thread division).  WRAP: angles are reduced to [-pi, pi)
 // on the way (what Action::copy_from_fine's mod_2pi would make of them).
+// dst2: a second destination (the caller's output state of a draw next to the sampler's own), or nullptr
 template <bool WRAP>
-__global__ void masked_copy_kernel(double2 *dst, const double2 *src, size_t n2, int B, const int32_t *accept) {
+__global__ void masked_copy_kernel(double2 *dst, const double2 *src, size_t n2, int B, const int32_t *accept,
+                                   double2 *dst2 = nullptr) {
   for (int chain = blockIdx.y; chain < B; chain += gridDim.y) {
     if (!accept[chain])
       continue;
     const double2 *s = src + (size_t)chain * n2;
     double2 *d = dst + (size_t)chain * n2;
+    double2 *d2 = dst2 ? dst2 + (size_t)chain * n2 : nullptr;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (size_t)gridDim.x * blockDim.x) {
       double2 v = s[t];
       if (WRAP) {
@@ -665,6 +668,8 @@ __global__ void masked_copy_kernel(double2 *dst, const double2 *src, size_t n2, 
         v.y = mod_2pi(v.y);
       }
       d[t] = v;
+      if (d2)
+        d2[t] = v;
     }
   }
 }
@@ -751,16 +756,22 @@ int launch_hmc_accept(mlmcpi_ctx *ctx, int B, uint32_t chain0, uint64_t draw, co
 }
 
 int launch_masked_copy(mlmcpi_ctx *ctx, double *dst, const double *src, size_t n, int B,
-                       const int32_t *accept, bool wrap_angles) {
+                       const int32_t *accept, bool wrap_angles, double *dst2) {
+  if (dst2 && (n % 2 != 0 || (uintptr_t)dst2 % 16 != 0 || (uintptr_t)dst % 16 != 0 || (uintptr_t)src % 16 != 0)) {
+    int rc = launch_masked_copy(ctx, dst, src, n, B, accept, wrap_angles, nullptr);
+    return rc ? rc : launch_masked_copy(ctx, dst2, src, n, B, accept, wrap_angles, nullptr);
+  }
   if (n % 2 == 0 && ((uintptr_t)dst % 16 == 0) && ((uintptr_t)src % 16 == 0)) {
     const size_t n2 = n / 2;
     const dim3 grid((unsigned)std::min<size_t>(64, (n2 + 1023) / 1024), (unsigned)std::min(B, 65535));
     if (wrap_angles)
       masked_copy_kernel<true><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<double2 *>(dst),
-                                                             reinterpret_cast<const double2 *>(src), n2, B, accept);
+                                                             reinterpret_cast<const double2 *>(src), n2, B, accept,
+                                                             reinterpret_cast<double2 *>(dst2));
     else
       masked_copy_kernel<false><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<double2 *>(dst),
-                                                              reinterpret_cast<const double2 *>(src), n2, B, accept);
+                                                              reinterpret_cast<const double2 *>(src), n2, B, accept,
+                                                              reinterpret_cast<double2 *>(dst2));
   } else {
     if (wrap_angles)
       return ctx_fail(ctx, MLMCPI_EINVAL, "masked copy with angle reduction needs an even, aligned state");
@@ -1424,7 +1435,9 @@ __global__ void cascade_commit_kernel(int B, const int32_t *acc, double *S_old, 
 // level >= 1 commits of rejected cascades (2.0 of 9.4 ms at 512^2 x 512 chains); the draws are the same,
 // bit for bit (tests/test_gpu_parity.py::test_hierarchical_draw_equals_explicit_cascade).
 static bool cascade_hmc_trial(const mlmcpi_sampler *s);
-static int cascade_draw_cached(mlmcpi_sampler *s) {
+// d_x_out: the caller's output state of the draw (Sampler::draw(state)), written for the accepted chains by the same
+// pass that commits the finest level, or nullptr
+static int cascade_draw_cached(mlmcpi_sampler *s, double *d_x_out) {
   mlmcpi_ctx *ctx = s->ctx;
   const int L = s->L, B = s->B;
   const uint32_t chain0 = s->chain0;
@@ -1502,7 +1515,7 @@ static int cascade_draw_cached(mlmcpi_sampler *s) {
     MLMCPI_LAUNCHED("count_accept");
     s->work[2] += (double)B * n_sites(s->model[l]);
     if (l == 0) {
-      if ((rc = launch_masked_copy(ctx, s->state[0], theta_prime, nf, B, s->acc))) // :78-88
+      if ((rc = launch_masked_copy(ctx, s->state[0], theta_prime, nf, B, s->acc, false, d_x_out))) // :78-88
         return rc;
       if (fused_chi) {
         chi_commit_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(B, s->acc, s->chi_cur, s->S3 + 2 * (size_t)B);
@@ -1873,8 +1886,9 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
                                   ctx->stream));
     return 0;
   }
-  if (cascade_cache_applies(s) && !s->trial.empty()) {
-    if ((rc = cascade_draw_cached(s)))
+  const bool cached = cascade_cache_applies(s) && !s->trial.empty();
+  if (cached) {
+    if ((rc = cascade_draw_cached(s, d_x_out)))
       return rc;
   } else {
     s->cascade_valid = false;
@@ -1886,7 +1900,7 @@ int mlmcpi_sampler_draw(mlmcpi_sampler *s, double *d_x_out, int32_t *d_accept) {
   s->draw++;
   s->cluster_updates += std::max(1, s->prm.n_updates);
   s->n_draws++;
-  if (d_x_out) // hierarchicalsampler.cc:78-80
+  if (d_x_out && !cached) // hierarchicalsampler.cc:78-80 (the cached cascade wrote it with the commit of level 0)
     if ((rc = launch_masked_copy(ctx, d_x_out, s->state[0], (size_t)mlmcpi_sample_size(&s->model[0]), B,
                                  s->acc)))
       return rc;

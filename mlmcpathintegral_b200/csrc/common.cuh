@@ -775,7 +775,7 @@ int launch_hmc_accept(mlmcpi_ctx *ctx, int B, uint32_t chain0, uint64_t draw, co
                       const double *d_S_trial, const double *d_T_cur, const double *d_T_trial,
                       int32_t *d_accept, double *d_diag);
 int launch_masked_copy(mlmcpi_ctx *ctx, double *d_dst, const double *d_src, size_t n, int B,
-                       const int32_t *d_accept, bool wrap_angles = false);
+                       const int32_t *d_accept, bool wrap_angles = false, double *d_dst2 = nullptr);
 int launch_half_sqnorm(mlmcpi_ctx *ctx, const double *d_p, size_t n, int B, double *d_T);
 
 // ------------------------------------------- deterministic two-pass reductions
