@@ -594,6 +594,7 @@ def gpu_main(a):
     ctx.profile(True)
     ctx.profile_read()
     launches0 = ctx.launches
+    sampler.reset_stats()  # acceptance rates of the timed region (they decide how many chains a level fills in)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()
@@ -609,6 +610,17 @@ def gpu_main(a):
     ctx.profile(False)
     launches = ctx.launches - launches0
     work = sampler.work()
+    p_timed = sampler.p_accept()
+    if is_schwinger and len(p_timed) > 1:
+        # a level is only filled in for the chains whose cascade is still alive (hierarchicalsampler.cc:73-74; the
+        # fill-in kernel skips the others): count the fine sites that WERE filled, from the measured acceptance rates
+        filled, alive = 0.0, 1.0
+        for l in range(len(p_timed) - 2, -1, -1):
+            alive *= p_timed[l + 1]
+            lm = sampler.level_model(l)
+            filled += B * lm.Mt_lat * lm.Mx_lat * alive
+        work["filled_fine_sites_nominal"] = work["filled_fine_sites"]
+        work["filled_fine_sites"] = filled
     units_per_step = work["leapfrog_site_steps"] + work["filled_fine_sites"] + work["sweep_site_updates"]
     t = torch.tensor([ms], dtype=torch.float64, device=ctx.device)
     if world > 1:

@@ -576,10 +576,10 @@ void besselproduct_setup(double beta, BesselProductConst *bp) {
 // ===================================================== small generic kernels
 // one warp per chain: lanes stride over the per-block partials, fixed-order shuffle tree
 __global__ void reduce_finish_kernel(const double *partial, int nblk, int B, int nout, int epi,
-                                     double scale0, double scale1, double *out, int64_t *Qint) {
+                                     double scale0, double scale1, double *out, int64_t *Qint, const int32_t *mask) {
   const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (chain >= B)
-    return;
+  if (chain >= B || (mask && !mask[chain]))
+    return; // (masked chains: their partial sums were not written)
   double s[3] = {0.0, 0.0, 0.0};
   for (int k = 0; k < nout; ++k) {
     const double *p = partial + ((size_t)k * B + chain) * nblk;
@@ -604,9 +604,9 @@ __global__ void reduce_finish_kernel(const double *partial, int nblk, int B, int
 }
 
 int launch_reduce_finish(mlmcpi_ctx *ctx, const double *partial, int nblk, int B, int nout, int epi,
-                         double scale0, double scale1, double *out, int64_t *Qint) {
+                         double scale0, double scale1, double *out, int64_t *Qint, const int32_t *mask) {
   reduce_finish_kernel<<<cdiv(B, 4), 128, 0, ctx->stream>>>(partial, nblk, B, nout, epi, scale0,
-                                                             scale1, out, Qint);
+                                                             scale1, out, Qint, mask);
   MLMCPI_LAUNCHED("reduce_finish");
   return 0;
 }
@@ -976,7 +976,11 @@ static int twolevel_step_impl(mlmcpi_ctx *ctx, const mlmcpi_model *fine, const m
   int32_t *acc = d_accept ? d_accept : reinterpret_cast<int32_t *>(red + 4 * B);
   int rc;
   // :40-42, :48 and :65-66 in one pass: theta' = fill(prolong(phi_c)), S_f(theta'), S_cond(theta')
-  if ((rc = mlmcpi_prolong_fill_eval(ctx, fine, d_xc, theta_prime, B, chain0, draw, red)))
+  if (fine->model == MLMCPI_SCHWINGER && d_mask) // no proposal for the chains whose cascade has stopped
+    rc = schwinger::prolong_fill_eval_masked(ctx, fine, d_xc, theta_prime, B, chain0, draw, red, d_mask);
+  else
+    rc = mlmcpi_prolong_fill_eval(ctx, fine, d_xc, theta_prime, B, chain0, draw, red);
+  if (rc)
     return rc;
   const double *ScC = known.d_ScC, *Scc = known.d_Scc;
   if (!ScC) {
@@ -1498,9 +1502,13 @@ static int cascade_draw_cached(mlmcpi_sampler *s, double *d_x_out) {
       return MLMCPI_ENOMEM;
     // theta' = fill(prolong(trial state of level l+1)), S_f(theta'), S_cond(theta')  (twolevelmetropolisstep.cc:40-66)
     double *Sprime_l = (l == 0 && fused_chi) ? s->S3 : Sp(l, 0);
+    // (s->acc: the chains whose cascade is still alive; no proposal is made for the others)
     if (l == 0 && fused_chi)
       rc = schwinger::prolong_fill_eval_charge(ctx, &s->model[0], coarse_trial, theta_prime, B, chain0,
-                                               level_draw(s->draw, 0, 0), Sprime_l);
+                                               level_draw(s->draw, 0, 0), Sprime_l, s->acc);
+    else if (s->model[l].model == MLMCPI_SCHWINGER)
+      rc = schwinger::prolong_fill_eval_masked(ctx, &s->model[l], coarse_trial, theta_prime, B, chain0,
+                                               level_draw(s->draw, l, 0), Sprime_l, s->acc);
     else
       rc = mlmcpi_prolong_fill_eval(ctx, &s->model[l], coarse_trial, theta_prime, B, chain0, level_draw(s->draw, l, 0),
                                     Sprime_l);

@@ -763,7 +763,9 @@ namespace schwinger {
 int overrelax_sweeps(mlmcpi_ctx *, const mlmcpi_model *, double *, int, int);
 int from_cluster(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t, uint64_t);
 int prolong_fill_eval_charge(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t, uint64_t,
-                             double *);
+                             double *, const int32_t *mask);
+int prolong_fill_eval_masked(mlmcpi_ctx *, const mlmcpi_model *, const double *, double *, int, uint32_t, uint64_t,
+                             double *, const int32_t *mask);
 int hmc_trial(mlmcpi_ctx *, const mlmcpi_model *, int, double, const double *, int, uint32_t, uint64_t,
               const double *, double *, int32_t *, const double **);
 }
@@ -804,7 +806,7 @@ enum { EPI_SCALE = 0, EPI_CHI = 1 };
 // out[k][chain] = scale_k * sum;  EPI_CHI: out[chain] = scale_0 * sum_0^2 and
 // Qint[chain] = -round(sum_1)
 int launch_reduce_finish(mlmcpi_ctx *ctx, const double *partial, int nblk, int B, int nout, int epi,
-                         double scale0, double scale1, double *out, int64_t *Qint);
+                         double scale0, double scale1, double *out, int64_t *Qint, const int32_t *mask = nullptr);
 
 // number of blocks per chain for a site reduction
 static inline int reduce_nblk(const mlmcpi_ctx *ctx, long long nsites, int B, int threads) {

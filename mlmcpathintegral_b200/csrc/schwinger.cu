@@ -1290,12 +1290,16 @@ template <bool APPROX, bool EVAL, bool CHARGE = false>
 #ifndef FILL_MINBLK
 #define FILL_MINBLK (1024 / FILL_THREADS)
 #endif
+// mask: chains whose cascade has already stopped (mask[chain] == 0) are skipped -- no proposal is made for them
+// (hierarchicalsampler.cc:73-74 breaks out of the level loop); their rows of x and of the sums are left untouched
 __global__ void __launch_bounds__(FILL_THREADS, FILL_MINBLK) prolong_fill_both_kernel(SW sw, BesselProductConst bp, const double *xc_all,
                                          double *x_all, int B, uint32_t chain0, uint64_t seed,
-                                         uint64_t draw, int nblk, double *partial) {
+                                         uint64_t draw, int nblk, double *partial, const int32_t *mask = nullptr) {
   const int Mt = sw.Mt, Mx = sw.Mx, Mtc = Mt / 2, Mxc = Mx / 2;
   const int nc = Mtc * Mxc;
   const int chain = blockIdx.x / nblk, blk = blockIdx.x - chain * nblk;
+  if (mask && !mask[chain])
+    return; // (block-uniform)
   const int cell_raw = blk * blockDim.x + threadIdx.x;
   // (threads beyond the last cell of the chain redo the last cell and store nothing, so that every thread of
   // the block passes the same barriers)
@@ -2054,7 +2058,8 @@ int fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, double *x, int B, uint32_t chai
 // S_out: nullptr, or [2][B] receiving S_f(theta') and S_cond(theta') (fused evaluation); charge: [3][B], the third row
 // sum_P mod_2pi(P) of theta' (coarsening both only)
 static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
-                             uint32_t chain0, uint64_t draw, double *S_out, bool charge = false) {
+                             uint32_t chain0, uint64_t draw, double *S_out, bool charge = false,
+                             const int32_t *mask = nullptr) {
   int rc = check_even(ctx, m);
   if (rc)
     return rc;
@@ -2084,35 +2089,41 @@ static int prolong_fill_impl(mlmcpi_ctx *ctx, const mlmcpi_model *m, const doubl
     bp.beta = sw.beta;
     if (S_out && charge)
       prolong_fill_both_kernel<true, true, true><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0,
-                                                                                       ctx->seed, draw, nblk, partial);
+                                                                                       ctx->seed, draw, nblk, partial, mask);
     else if (S_out)
       prolong_fill_both_kernel<true, true><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
-                                                                         draw, nblk, partial);
+                                                                         draw, nblk, partial, mask);
     else
       prolong_fill_both_kernel<true, false><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
-                                                                          draw, nblk, nullptr);
+                                                                          draw, nblk, nullptr, mask);
   } else {
     besselproduct_setup(sw.beta, &bp);
     if (S_out && charge)
       prolong_fill_both_kernel<false, true, true><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0,
-                                                                                        ctx->seed, draw, nblk, partial);
+                                                                                        ctx->seed, draw, nblk, partial, mask);
     else if (S_out)
       prolong_fill_both_kernel<false, true><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
-                                                                          draw, nblk, partial);
+                                                                          draw, nblk, partial, mask);
     else
       prolong_fill_both_kernel<false, false><<<grid, FILL_THREADS, 0, ctx->stream>>>(sw, bp, xc, x, B, chain0, ctx->seed,
-                                                                           draw, nblk, nullptr);
+                                                                           draw, nblk, nullptr, mask);
   }
   MLMCPI_LAUNCHED("schwinger::prolong_fill");
   if (S_out)
-    return launch_reduce_finish(ctx, partial, npart, B, charge ? 3 : 2, EPI_SCALE, sw.beta, 1.0, S_out, nullptr);
+    return launch_reduce_finish(ctx, partial, npart, B, charge ? 3 : 2, EPI_SCALE, sw.beta, 1.0, S_out, nullptr, mask);
   return 0;
 }
 
 // prolong_fill_eval with a third output row: sum over the plaquettes of theta' of mod_2pi(P)  (S_out: [3][B])
 int prolong_fill_eval_charge(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B, uint32_t chain0,
-                             uint64_t draw, double *S_out) {
-  return prolong_fill_impl(ctx, m, xc, x, B, chain0, draw, S_out, true);
+                             uint64_t draw, double *S_out, const int32_t *mask) {
+  return prolong_fill_impl(ctx, m, xc, x, B, chain0, draw, S_out, true, mask);
+}
+// prolong_fill_eval for the chains with mask[chain] != 0 only (nullptr: all); the S_out entries of the others are not written
+int prolong_fill_eval_masked(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B, uint32_t chain0,
+                             uint64_t draw, double *S_out, const int32_t *mask) {
+  return prolong_fill_impl(ctx, m, xc, x, B, chain0, draw, S_out, false,
+                           m->coarsening == MLMCPI_COARSEN_BOTH ? mask : nullptr);
 }
 
 int prolong_fill(mlmcpi_ctx *ctx, const mlmcpi_model *m, const double *xc, double *x, int B,
