@@ -713,10 +713,11 @@ __global__ void twolevel_accept_kernel(int B, uint32_t chain0, uint64_t seed, ui
   if (acc && update_scond)
     Scond[c] = Scond_prime;
   accept[c] = acc ? 1 : 0;
-  if (deltas) {
-    deltas[3 * (size_t)c] = dS_fine;
-    deltas[3 * (size_t)c + 1] = dS_coarse;
-    deltas[3 * (size_t)c + 2] = dS_trial;
+  if (deltas) { // (no proposal was made for a masked chain: its sums are not defined)
+    const bool live = !(mask && !mask[c]);
+    deltas[3 * (size_t)c] = live ? dS_fine : 0.0;
+    deltas[3 * (size_t)c + 1] = live ? dS_coarse : 0.0;
+    deltas[3 * (size_t)c + 2] = live ? dS_trial : 0.0;
   }
 }
 
