@@ -646,6 +646,36 @@ def test_per_dof_updates_reproduce_the_reference_lexicographic_sweep(mp, ctx):
     assert len(set(host(a)[:, 0])) == 4  # one variate stream per chain
 
 
+def test_schwinger_force_elementwise(mp, ctx, orc):
+    """the force component by component (the norm-wise bound of close() says nothing about a component whose two
+    sines nearly cancel): |dS/dtheta (CUDA) - oracle| <= 8 eps beta for EVERY link -- the branch-free sine of the
+    leapfrog kernels is accurate to 2.2e-16 absolute, a component is beta (sin P - sin P'), the rest is the rounding
+    of the plaquette sums -- on random states, on nearly flat states (all sines small: cancellation between
+    neighbouring plaquettes) and at plaquette angles near +-pi, for beta = 1 ... 4096; the same for the positions
+    after a short leapfrog trajectory (errors scale with dt^2 beta)"""
+    rng = np.random.default_rng(23)
+    eps = np.finfo(np.float64).eps
+    for Mt, Mx, beta in [(16, 16, 1.0), (32, 16, 64.0), (64, 64, 1024.0), (128, 128, 4096.0)]:
+        o = po.schwinger(Mt, Mx, beta)
+        m = mp.schwinger(Mt, Mx, beta)
+        n = 2 * Mt * Mx
+        flat = 1e-3 * rng.normal(size=n)
+        pis = rng.choice([-np.pi, np.pi], size=n) * (1 + 1e-9 * rng.normal(size=n))
+        x = np.stack([rng.uniform(-np.pi, np.pi, n), flat, 0.25 * pis, rng.uniform(-30, 30, n)])
+        got = host(ctx.force(m, dev(ctx, x)))
+        want = np.array([orc.force(o, x[b]) for b in range(x.shape[0])])
+        err = np.abs(got - want)
+        assert err.max() <= 8 * eps * beta * max(1.0, np.abs(x).max() / np.pi), (Mt, beta, err.max() / (eps * beta))
+        p = rng.normal(size=x.shape)
+        y, pd = dev(ctx, x), dev(ctx, p)
+        ctx.leapfrog(m, 4, 0.01, y, pd)
+        res = [orc.leapfrog(o, 4, 0.01, x[b], p[b]) for b in range(x.shape[0])]
+        ex = np.abs(host(y) - np.array([r[0] for r in res])).max()
+        ep = np.abs(host(pd) - np.array([r[1] for r in res])).max()
+        assert ex <= 64 * eps * max(np.abs(x).max(), 1e-2 * beta), (Mt, beta, ex)
+        assert ep <= 64 * eps * max(1.0, 0.04 * beta) * max(1.0, np.abs(x).max() / np.pi), (Mt, beta, ep)
+
+
 def test_schwinger_heatbath_paired_variates(mp, ctx, orc):
     """heatbath_pair_kernel (two links of a colour per Philox block) against the oracle's restatement of the same
     variate map, on lattices where a row holds an ODD number of links of a colour (Mt / 2 odd: the last link has no
