@@ -32,6 +32,27 @@ def test_library_exports_every_declared_symbol(mp):
     assert lib.mlmcpi_version() == 100
 
 
+def test_python_constants_match_the_header(mp):
+    """every enumerator of include/mlmcpi.h that the ctypes layer names (options, streams, samplers, QoIs, models,
+    coarsenings) has the header's value"""
+    hdr = open(os.path.join(ROOT, "include", "mlmcpi.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    enums = dict((k, int(v)) for k, v in re.findall(r"\b(MLMCPI_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr))
+    assert len(enums) > 40
+    checked = 0
+    for name, value in vars(mp._lib).items():
+        if not name.isupper() or not isinstance(value, int):
+            continue
+        for key in ("MLMCPI_" + name, "MLMCPI_MODEL_" + name, "MLMCPI_E" + name[2:] if name.startswith("E_") else None):
+            if key and key in enums:
+                assert enums[key] == value, (name, value, key, enums[key])
+                checked += 1
+                break
+    assert checked >= 30, checked
+    for opt in [k for k in enums if k.startswith("MLMCPI_OPT_")]:
+        assert hasattr(mp._lib, opt[len("MLMCPI_"):]), opt
+
+
 def test_no_cpu_fallback(mp):
     import torch
     if torch.cuda.is_available():
