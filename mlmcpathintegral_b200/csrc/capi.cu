@@ -2818,6 +2818,7 @@ void mlmcpi_stats_destroy(mlmcpi_stats *st) {
 }
 
 int mlmcpi_stats_hard_reset(mlmcpi_stats *st) { // Statistics::hard_reset, statistics.hh:125-137
+  DeviceGuard device_guard(st ? st->ctx : nullptr);
   mlmcpi_ctx *ctx = st->ctx;
   st->n_samples = st->n_samples_longterm = 0;
   MLMCPI_CUDA(cudaMemsetAsync(st->acc, 0, sizeof(double) * (5 + 2 * st->k_max) * st->B, ctx->stream));
@@ -2825,6 +2826,7 @@ int mlmcpi_stats_hard_reset(mlmcpi_stats *st) { // Statistics::hard_reset, stati
 }
 
 int mlmcpi_stats_reset(mlmcpi_stats *st) { // Statistics::reset, statistics.hh:119-122
+  DeviceGuard device_guard(st ? st->ctx : nullptr);
   mlmcpi_ctx *ctx = st->ctx;
   st->n_samples = 0;
   MLMCPI_CUDA(cudaMemsetAsync(st->acc, 0, sizeof(double) * st->B, ctx->stream));

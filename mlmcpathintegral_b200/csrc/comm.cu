@@ -126,8 +126,17 @@ int mlmcpi_comm_allreduce_sum(mlmcpi_comm *c, double *d_buf, size_t n) {
     return MLMCPI_EINVAL;
   if (c->world == 1 || n == 0)
     return 0;
+  // (the library's entry points restore the caller's current device; the collective is issued on the context's)
+  int prev = -1;
+  const int dev = mlmcpi_device(c->ctx);
+  if (cudaGetDevice(&prev) == cudaSuccess && prev != dev)
+    cudaSetDevice(dev);
+  else
+    prev = -1;
   const ncclResult_t rc =
       ncclAllReduce(d_buf, d_buf, n, ncclDouble, ncclSum, c->nccl, (cudaStream_t)mlmcpi_stream(c->ctx));
+  if (prev >= 0)
+    cudaSetDevice(prev);
   return rc == ncclSuccess ? 0 : MLMCPI_ECUDA;
 }
 

@@ -53,6 +53,25 @@ def test_python_constants_match_the_header(mp):
         assert hasattr(mp._lib, opt[len("MLMCPI_"):]), opt
 
 
+def test_every_entry_point_sets_its_device():
+    """every C-ABI entry point that takes a context, sampler, statistics or multilevel object starts with a
+    DeviceGuard: the library restores the caller's current device on return, so an entry point without one runs
+    on the wrong device in a process whose context is not on device 0 (found by the two-process driver run:
+    Statistics::hard_reset on rank 1 failed with 'invalid argument' and rank 0 waited in the all-reduce)"""
+    src = open(os.path.join(ROOT, "mlmcpathintegral_b200", "csrc", "capi.cu")).read()
+    missing = []
+    pat = r"^(?:int|void|uint64_t|const char \*|double|void \*|size_t)\s+(mlmcpi_[a-z0-9_]+)\s*\(([^)]*)\)\s*\{"
+    for m in re.finditer(pat, src, re.M):
+        name, args = m.group(1), m.group(2)
+        if not any(t in args for t in ("mlmcpi_ctx", "mlmcpi_stats", "mlmcpi_mlmc", "mlmcpi_sampler")):
+            continue
+        body = src[m.end():m.end() + 600].split("\n}\n")[0]
+        if "DeviceGuard" not in body and name not in ("mlmcpi_last_error", "mlmcpi_device", "mlmcpi_stream",
+                                                      "mlmcpi_world_size", "mlmcpi_launch_count"):
+            missing.append(name)
+    assert not missing, missing
+
+
 def test_no_cpu_fallback(mp):
     import torch
     if torch.cuda.is_available():
