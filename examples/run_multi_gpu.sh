@@ -13,6 +13,16 @@ for r in $(seq 0 $((N - 1))); do
   MLMCPI_RANK=$r MLMCPI_WORLD_SIZE=$N MLMCPI_COMM_FILE=$F MLMCPI_COMM_NONCE=$NONCE "$@" &
   pids+=($!)
 done
+# a process that fails must not leave its peers waiting in a collective: the first non-zero exit stops the run
 rc=0
-for p in "${pids[@]}"; do wait $p || rc=$?; done
+left=${#pids[@]}
+while [ "$left" -gt 0 ]; do
+  wait -n
+  s=$?
+  left=$((left - 1))
+  if [ "$s" -ne 0 ] && [ "$rc" -eq 0 ]; then
+    rc=$s
+    kill "${pids[@]}" 2>/dev/null
+  fi
+done
 exit $rc

@@ -229,7 +229,7 @@ def test_driver_two_processes_two_gpus(drivers, tmp_path):
     p = tmp_path / "parameters.in"
     p.write_text(QFT.format(**dict(QFT_DEFAULTS, n_samples=200000)))
     r = subprocess.run([os.path.join(ROOT, "examples", "run_multi_gpu.sh"), "2", drivers["driver_qft"], str(p), "64"],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr
     assert r.stdout.count("Single level MC") == 1  # only the master prints
     assert "on 2 x 64 chains" in r.stdout
@@ -249,7 +249,7 @@ def test_driver_multilevel_two_processes_two_gpus(drivers, tmp_path):
     p = tmp_path / "parameters.in"
     p.write_text(QFT.format(**dict(QFT_DEFAULTS, method="multilevel", n_max_level=2, epsilon=0.05)))
     r = subprocess.run([os.path.join(ROOT, "examples", "run_multi_gpu.sh"), "2", drivers["driver_qft"], str(p), "64"],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr
     assert r.stdout.count("tolerance epsilon") == 1  # only the master prints
     assert sigma_ratio(r.stdout) < 5.0, r.stdout[-1500:]
