@@ -2601,10 +2601,15 @@ int mlmcpi_mlmc_evaluate(mlmcpi_mlmc *m) {
     double unused;
     if ((rc = mlmcpi_sampler_cost(m->coarse_sampler[l], 1, &unused)))
       return rc;
+    // (every process must run the same number of batches -- a draw of a MultilevelSampler contains all-reduced
+    // decisions -- so the time that ends the loop is the mean over the processes)
     for (int n = 8; n <= 128; n *= 4) {
       if ((rc = mlmcpi_sampler_cost(m->coarse_sampler[l], n, &m->cost_sampler[l])))
         return rc;
-      if (m->cost_sampler[l] * n * B >= 1.0e4)
+      double t_usec = m->cost_sampler[l] * n * B;
+      if ((rc = ctx_allreduce_host(ctx, &t_usec, 1)))
+        return rc;
+      if (t_usec / std::max(1, ctx->world) >= 1.0e4)
         break;
     }
     cudaEvent_t e0, e1;
@@ -2625,7 +2630,13 @@ int mlmcpi_mlmc_evaluate(mlmcpi_mlmc *m) {
       float ms = 0.f;
       MLMCPI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       m->cost_twolevel[l] = 1.0e3 * ms / ((double)n * B);
-      if (n > 1 && ms >= 10.f)
+      double t_ms = ms;
+      if ((rc = ctx_allreduce_host(ctx, &t_ms, 1))) {
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return rc;
+      }
+      if (n > 1 && t_ms / std::max(1, ctx->world) >= 10.0)
         break;
     }
     cudaEventDestroy(e0);
